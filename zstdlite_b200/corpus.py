@@ -1,0 +1,95 @@
+"""Deterministic synthetic corpora.  Pure numpy; used by tests and bench.
+
+Families: text (Zipf words), rdf (columnar f64/i32/factor slab, as man/benchmark.R:14-21),
+lowent (4-bit entropy bytes), rand (uniform bytes), rle (long runs).
+"""
+import numpy as np
+
+FAMILIES = ("text", "rdf", "lowent", "rand", "rle")
+
+
+def _text(rng, n):
+    vocab_n = 4096
+    lens = rng.integers(2, 10, size=vocab_n)
+    letters = rng.integers(97, 123, size=int(lens.sum()), dtype=np.uint8)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    ranks = np.arange(1, vocab_n + 1, dtype=np.float64)
+    p = 1.0 / ranks
+    p /= p.sum()
+    need = n // 5 + 64
+    ids = rng.choice(vocab_n, size=need, p=p)
+    wl = lens[ids] + 1
+    total = int(wl.sum())
+    while total < n:
+        more = rng.choice(vocab_n, size=need, p=p)
+        ids = np.concatenate([ids, more])
+        wl = lens[ids] + 1
+        total = int(wl.sum())
+    out = np.full(total, 32, dtype=np.uint8)
+    pos = np.concatenate([[0], np.cumsum(wl)[:-1]])
+    # vectorised scatter of word letters
+    maxlen = int(lens.max())
+    for k in range(maxlen):
+        m = lens[ids] > k
+        out[pos[m] + k] = letters[starts[ids[m]] + k]
+    return out[:n]
+
+
+def _rdf(rng, n):
+    # byte proportion 8:4:4 (f64 : i32 : i32 factor codes), column-major inside the slab
+    rows = max(1, n // 16)
+    real = (rng.integers(0, 20, size=rows).astype(np.float64) / 100.0).astype("<f8").view(np.uint8)
+    integer = rng.integers(1, rows + 1, size=rows).astype("<i4").view(np.uint8)
+    factor = rng.integers(1, 11, size=rows).astype("<i4").view(np.uint8)
+    out = np.concatenate([real, integer, factor])
+    if out.size < n:
+        out = np.concatenate([out, np.zeros(n - out.size, dtype=np.uint8)])
+    return out[:n]
+
+
+def _lowent(rng, n):
+    return rng.integers(0, 16, size=n, dtype=np.uint8)
+
+
+def _rand(rng, n):
+    return rng.integers(0, 256, size=n, dtype=np.uint8)
+
+
+def _rle(rng, n):
+    out = np.empty(n, dtype=np.uint8)
+    pos = 0
+    while pos < n:
+        run = int(rng.geometric(1.0 / 4096.0))
+        out[pos:pos + run] = rng.integers(0, 256)
+        pos += run
+    return out
+
+
+_GEN = {"text": _text, "rdf": _rdf, "lowent": _lowent, "rand": _rand, "rle": _rle}
+_SEED = {"text": 1, "rdf": 2, "lowent": 3, "rand": 4, "rle": 5}
+
+
+def make(family, nbytes, index=0):
+    """One buffer of `nbytes` bytes of the named family; `index` varies the stream."""
+    rng = np.random.default_rng([_SEED[family], index])
+    return _GEN[family](rng, int(nbytes))
+
+
+def mixed_frames(nframes, frame_bytes, mix=(("text", 0.4), ("rdf", 0.4), ("lowent", 0.1), ("rand", 0.1)), pool=64):
+    """Config-2/3 style corpus: returns (uint8 array [nframes, frame_bytes], family name per frame).
+
+    To keep generation fast, each family is generated as `pool` distinct frames and tiled; every
+    frame is still decoded/encoded independently so throughput is unaffected by the repetition.
+    """
+    fams = []
+    out = np.empty((nframes, frame_bytes), dtype=np.uint8)
+    start = 0
+    for k, (fam, frac) in enumerate(mix):
+        cnt = nframes - start if k == len(mix) - 1 else int(round(nframes * frac))
+        npool = min(pool, max(cnt, 1))
+        base = make(fam, npool * frame_bytes, index=7).reshape(npool, frame_bytes)
+        for j in range(cnt):
+            out[start + j] = base[j % npool]
+        fams += [fam] * cnt
+        start += cnt
+    return out, fams
