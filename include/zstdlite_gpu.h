@@ -1,0 +1,118 @@
+/*
+ * zstdlite_gpu.h -- C ABI of libzstdlite_gpu.so, the B200-native Zstandard engine that stands in
+ * for the vendored libzstd on zstdlite's ONE-SHOT path.
+ *
+ * Every ZSTD_* entry point below has the exact signature of the libzstd 1.5.6 symbol that the
+ * reference's C layer calls (citations: file:line under /root/reference).  The library exports each
+ * of them twice: under the canonical name and under a `zlg_` prefix (zlg_ZSTD_compress2, ...) so a
+ * package that keeps the vendored libzstd for its streaming/ZDICT code can bind the one-shot path
+ * explicitly.  There is no CPU fallback: when no CUDA device is usable the
+ * compute entry points return a libzstd-style error code (ZSTD_isError() is true).
+ *
+ * Plain C: pointers and sizes only.
+ */
+#ifndef ZSTDLITE_GPU_H
+#define ZSTDLITE_GPU_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ZSTD_CCtx_s ZSTD_CCtx;
+typedef struct ZSTD_DCtx_s ZSTD_DCtx;
+
+/* src/zstd/zstd.h:566-568 */
+typedef enum { ZSTD_reset_session_only = 1, ZSTD_reset_parameters = 2, ZSTD_reset_session_and_parameters = 3 } ZSTD_ResetDirective;
+/* the parameters zstdlite sets: src/zstd/zstd.h:333,440,449,507-508,2083,2103 and 638-639,2422,2433 */
+typedef enum {
+    ZSTD_c_compressionLevel = 100, ZSTD_c_checksumFlag = 201, ZSTD_c_nbWorkers = 400,
+    ZSTD_c_stableInBuffer = 1006, ZSTD_c_stableOutBuffer = 1007
+} ZSTD_cParameter;
+typedef enum { ZSTD_d_windowLogMax = 100, ZSTD_d_stableOutBuffer = 1001, ZSTD_d_forceIgnoreChecksum = 1002 } ZSTD_dParameter;
+typedef enum { ZSTD_frame = 0, ZSTD_skippableFrame = 1 } ZSTD_frameType_e;
+/* src/zstd/zstd.h:1472-1482 */
+typedef struct {
+    unsigned long long frameContentSize;
+    unsigned long long windowSize;
+    unsigned blockSizeMax;
+    ZSTD_frameType_e frameType;
+    unsigned headerSize;
+    unsigned dictID;
+    unsigned checksumFlag;
+    unsigned _reserved1;
+    unsigned _reserved2;
+} ZSTD_frameHeader;
+
+#define ZSTD_CONTENTSIZE_UNKNOWN (0ULL - 1)   /* src/zstd/zstd.h:190 */
+#define ZSTD_CONTENTSIZE_ERROR   (0ULL - 2)   /* src/zstd/zstd.h:191 */
+
+/* ---- errors / version: src/cctx.c, src/dctx.c, src/raw-file.c, src/serialize.c (43 + 27 call sites) ---- */
+unsigned    ZSTD_isError(size_t code);                       /* zstd.c:15758 */
+const char* ZSTD_getErrorName(size_t code);                  /* zstd.c:15762, strings zstd.c:3590-3630 */
+const char* ZSTD_versionString(void);                        /* zstd.c:15748; src/serialize.c:27 */
+
+/* ---- compression context: src/cctx.c:205,222,72-92,265-304,352-354 ---- */
+ZSTD_CCtx* ZSTD_createCCtx(void);                                                   /* zstd.c:22610 */
+size_t     ZSTD_freeCCtx(ZSTD_CCtx* cctx);                                          /* zstd.c:22693 */
+size_t     ZSTD_CCtx_reset(ZSTD_CCtx* cctx, ZSTD_ResetDirective reset);             /* zstd.c:23872 */
+size_t     ZSTD_CCtx_setParameter(ZSTD_CCtx* cctx, ZSTD_cParameter param, int v);   /* zstd.c:23223 */
+size_t     ZSTD_CCtx_getParameter(const ZSTD_CCtx* cctx, ZSTD_cParameter param, int* v); /* zstd.c:23531 */
+size_t     ZSTD_CCtx_loadDictionary(ZSTD_CCtx* cctx, const void* dict, size_t dictSize); /* zstd.c:23826 (copies) */
+size_t     ZSTD_CCtx_setPledgedSrcSize(ZSTD_CCtx* cctx, unsigned long long pledged); /* zstd.c:23735 */
+
+/* ---- one-shot compression: src/raw-file.c:52,74; src/serialize.c:73,91 ---- */
+size_t ZSTD_compressBound(size_t srcSize);                                          /* zstd.c:22583 */
+size_t ZSTD_compress2(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize); /* zstd.c:28949 */
+
+/* ---- decompression context: src/dctx.c:54,99,119,163,181,186,234 ---- */
+ZSTD_DCtx* ZSTD_createDCtx(void);                                                   /* zstd.c:40913 */
+size_t     ZSTD_freeDCtx(ZSTD_DCtx* dctx);                                          /* zstd.c:40927 */
+size_t     ZSTD_DCtx_reset(ZSTD_DCtx* dctx, ZSTD_ResetDirective reset);             /* zstd.c:42548 */
+size_t     ZSTD_DCtx_setParameter(ZSTD_DCtx* dctx, ZSTD_dParameter param, int v);   /* zstd.c:42507 */
+size_t     ZSTD_DCtx_getParameter(ZSTD_DCtx* dctx, ZSTD_dParameter param, int* v);  /* zstd.c:42478 */
+size_t     ZSTD_DCtx_loadDictionary(ZSTD_DCtx* dctx, const void* dict, size_t dictSize); /* zstd.c:42321 (copies) */
+
+/* ---- one-shot decompression: src/raw-file.c:150,155,189; src/serialize.c:171,177,197 ---- */
+size_t             ZSTD_findFrameCompressedSize(const void* src, size_t srcSize);   /* zstd.c:41410 */
+unsigned long long ZSTD_getFrameContentSize(const void* src, size_t srcSize);       /* zstd.c:41170 */
+size_t ZSTD_decompressDCtx(ZSTD_DCtx* dctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize); /* zstd.c:41798 */
+
+/* ---- introspection: src/zstd-info.c:61; src/dictionaries.c:52,54 ---- */
+size_t   ZSTD_getFrameHeader(ZSTD_frameHeader* zfhPtr, const void* src, size_t srcSize); /* zstd.c:41160 */
+unsigned ZSTD_getDictID_fromFrame(const void* src, size_t srcSize);                 /* zstd.c:42245 */
+unsigned ZSTD_getDictID_fromDict(const void* dict, size_t dictSize);                /* zstd.c:42225 */
+unsigned ZDICT_getDictID(const void* dict, size_t dictSize);                        /* zstd.c:49974 */
+
+/* ---- batch extension (needed because src/raw-file.c:150-189 decodes one frame per call and
+ *      R's length() is 32-bit).  Arrays live in HOST memory; when ptrs_are_device != 0 the src[i] / dst[i]
+ *      pointers themselves are DEVICE pointers (inputs/outputs already resident in HBM).  Each item is
+ *      exactly one Zstandard frame.  result[i] receives the produced size or a libzstd error code.
+ *      Returns 0, or an error code if the batch as a whole could not run. ---- */
+size_t zl_decompress_batch(ZSTD_DCtx* dctx, const void* const* src, const size_t* srcSize,
+                           void* const* dst, const size_t* dstCapacity, size_t* result,
+                           size_t n, int ptrs_are_device);
+size_t zl_compress_batch(ZSTD_CCtx* cctx, const void* const* src, const size_t* srcSize,
+                         void* const* dst, const size_t* dstCapacity, size_t* result,
+                         size_t n, int ptrs_are_device);
+/* one buffer -> concatenated independent frames of `frameSize` content bytes each (a standard multi-frame
+ * zstd stream); frameSizes[k] (optional, may be NULL, capacity ceil(srcSize/frameSize)) receives the compressed
+ * size of frame k.  Returns total compressed size or an error code. */
+size_t zl_compress_split(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize,
+                         size_t frameSize, size_t* frameSizes, int ptrs_are_device);
+
+/* CUDA stream (cudaStream_t passed as void*) the context launches on; default: a private non-blocking stream */
+size_t zl_dctx_set_stream(ZSTD_DCtx* dctx, void* cuda_stream);
+size_t zl_cctx_set_stream(ZSTD_CCtx* cctx, void* cuda_stream);
+/* number of kernel launches issued by the context since creation (bench.py's gpu_launches) */
+unsigned long long zl_dctx_launch_count(const ZSTD_DCtx* dctx);
+unsigned long long zl_cctx_launch_count(const ZSTD_CCtx* cctx);
+/* milliseconds spent on-device by the kernels of the most recent batch call (CUDA events on the context's stream) */
+double zl_dctx_last_kernel_ms(const ZSTD_DCtx* dctx);
+double zl_cctx_last_kernel_ms(const ZSTD_CCtx* cctx);
+const char* zl_backend_string(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

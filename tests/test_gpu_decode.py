@@ -1,0 +1,148 @@
+"""-m gpu parity tests for the CUDA decoder: byte-exact against the reference's libzstd (oracle/_ref)
+and the C restatement, through the C ABI (zl_decompress_batch / ZSTD_decompressDCtx)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def z():
+    import torch
+    assert torch.cuda.is_available()
+    import zstdlite_b200 as zz
+    return zz
+
+
+def test_kat_data_json(z):
+    """reference KAT man/figures/data.json.zst <-> README.md:199-205 (committed under tests/golden)."""
+    c = open(os.path.join(GOLD, "data.json.zst"), "rb").read()
+    want = open(os.path.join(GOLD, "data.json"), "rb").read()
+    assert z.zstd_decompress(c) == want
+    assert z.zstd_info(c) == {"uncompressed_size": 172, "compressed_size": 126, "dict_id": 0, "has_checksum": True}
+
+
+@pytest.mark.parametrize("family", ["text", "rdf", "lowent", "rand", "rle"])
+def test_families_levels_sizes(z, ref, family):
+    from zstdlite_b200 import corpus
+    from tests.gpu_util import gpu_decompress_batch
+    frames, want = [], []
+    for size in (0, 1, 7, 100, 1000, 4096, 65536, 131072, 300000, 1 << 20):
+        d = corpus.make(family, size, 11).tobytes()
+        for lvl in (1, 2, 3, 5, 9, 19, -3):
+            for ck in (False, True):
+                frames.append(ref.compress(d, lvl, ck))
+                want.append(d)
+    res, outs = gpu_decompress_batch(frames, [len(w) for w in want])
+    for i, (r, o, w) in enumerate(zip(res, outs, want)):
+        assert not z.is_error(r), (i, z.error_name(r))
+        assert r == len(w) and o == w, i
+    # same frames, host pointers (staging path), arbitrary packing
+    res2, outs2 = gpu_decompress_batch(frames[:40], [len(w) for w in want[:40]], device=False)
+    assert outs2 == want[:40]
+
+
+def test_one_shot_api_multiframe_and_skippable(z, ref):
+    from zstdlite_b200 import corpus, _lib
+    import ctypes as C
+    a = corpus.make("text", 50000, 1).tobytes()
+    b = corpus.make("rdf", 200000, 2).tobytes()
+    skip = (0x184D2A53).to_bytes(4, "little") + (5).to_bytes(4, "little") + b"hello"
+    blob = ref.compress(a, 3, True) + skip + ref.compress(b, 1) + ref.compress(b"", 3)
+    L = _lib.lib()
+    d = z.zstd_dctx()
+    dst = C.create_string_buffer(len(a) + len(b))
+    r = L.ZSTD_decompressDCtx(d._p, dst, len(a) + len(b), blob, len(blob))
+    assert not z.is_error(r), z.error_name(r)
+    assert dst.raw[:r] == a + b
+    # reference semantics: zstd_decompress() only looks at the first frame (src/raw-file.c:150-189)
+    assert z.zstd_decompress(blob) == a
+    # too small destination
+    r = L.ZSTD_decompressDCtx(d._p, dst, len(a) - 1, blob, len(blob))
+    assert z.is_error(r) and z.error_name(r) == "Destination buffer is too small"
+
+
+def test_checksum_behaviour(z, ref):
+    """tests/testthat/test-checksums.R:2-35"""
+    from zstdlite_b200 import corpus
+    d = corpus.make("text", 100000, 5).tobytes()
+    plain, ck = ref.compress(d, 3, False), ref.compress(d, 3, True)
+    assert len(ck) == len(plain) + 4
+    assert z.zstd_decompress(ck) == d
+    bad = bytearray(ck)
+    bad[-1] ^= 0x5A
+    with pytest.raises(z.ZstdError, match="doesn't match checksum"):
+        z.zstd_decompress(bytes(bad))
+    assert z.zstd_decompress(bytes(bad), dctx=z.zstd_dctx(validate_checksum=False)) == d
+    assert z.zstd_dctx(validate_checksum=False).settings() == {"validate_checksum": 1}     # reference quirk, src/dctx.c:233-239
+
+
+def test_corrupted_inputs_never_crash(z, ref, restate):
+    """every mutated frame must yield an error or output identical to what libzstd produces"""
+    from zstdlite_b200 import corpus
+    from tests.gpu_util import gpu_decompress_batch
+    rng = np.random.default_rng(99)
+    frames, caps = [], []
+    for fam in ("text", "rdf", "lowent"):
+        d = corpus.make(fam, 20000, 3).tobytes()
+        c = bytearray(ref.compress(d, 3, True))
+        for _ in range(60):
+            m = bytearray(c)
+            k = int(rng.integers(0, len(m)))
+            m[k] ^= 1 << int(rng.integers(0, 8))
+            frames.append(bytes(m)); caps.append(len(d))
+        for cut in (1, 5, 10, len(c) // 2, len(c) - 1):
+            frames.append(bytes(c[:cut])); caps.append(len(d))
+    res, outs = gpu_decompress_batch(frames, caps)
+    import oracle.ref as R
+    for f, cap, r, o in zip(frames, caps, res, outs):
+        try:
+            want = R.DCtx().decompress(f, cap=cap, all_frames=True)
+        except R.RefError:
+            want = None
+        if want is None:
+            assert z.is_error(r), "reference rejects this frame, GPU accepted it"
+        else:
+            assert not z.is_error(r) and o == want
+
+
+def test_dictionary_decode(z, ref):
+    """config 4 shape: small objects compressed by libzstd with a trained dictionary; raw-content dict too."""
+    from tests.gpu_util import gpu_decompress_batch
+    rng = np.random.default_rng(4)
+    names = [("country_%02d" % i).encode() for i in range(50)]
+    samples = []
+    for i in range(2000):
+        perm = rng.permutation(50)
+        samples.append(b"X\n\x00\x00\x00\x03" + b"".join(names[j] + int(rng.integers(0, 1000)).to_bytes(4, "little") for j in perm[: int(rng.integers(10, 50))]))
+    d = ref.train_dict(samples[:1000], 5000)
+    assert z.zstd_dict_id(d) == ref.lib().ZDICT_getDictID(d, len(d)) != 0
+    for dd in (d, b"".join(samples[:20])):          # trained dict, raw-content dict
+        frames = [ref.compress(s, 3, False, dict=dd) for s in samples[1000:1400]]
+        res, outs = gpu_decompress_batch(frames, [len(s) for s in samples[1000:1400]], dctx=z.zstd_dctx(dict=dd))
+        assert outs == samples[1000:1400]
+    # wrong / missing dictionary -> error like the reference (zstd.c:41318)
+    frames = [ref.compress(samples[0], 3, False, dict=d)]
+    res, _ = gpu_decompress_batch(frames, [len(samples[0])])
+    assert z.is_error(res[0])
+
+
+def test_config2_batch_shape(z, ref):
+    """configs[1] at reduced count: 512 independent 64 KiB frames, mixed families, level 3."""
+    from zstdlite_b200 import corpus
+    from tests.gpu_util import gpu_decompress_batch
+    data, fams = corpus.mixed_frames(512, 65536, pool=16)
+    cache = {}
+    frames = []
+    for i in range(512):
+        key = data[i].tobytes()
+        if key not in cache:
+            cache[key] = ref.compress(key, 3)
+        frames.append(cache[key])
+    res, outs = gpu_decompress_batch(frames, [65536] * 512)
+    for i in range(512):
+        assert res[i] == 65536 and outs[i] == data[i].tobytes(), (i, fams[i])

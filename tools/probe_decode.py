@@ -1,0 +1,41 @@
+"""Quick device-resident timing probe of the decode pipeline (not the bench; used during development)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import zstdlite_b200 as z
+from zstdlite_b200 import corpus
+from oracle import ref
+
+nframes = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+fb = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+mixname = sys.argv[4] if len(sys.argv) > 4 else "mix"
+mix = {"mix": (("text", 0.4), ("rdf", 0.4), ("lowent", 0.1), ("rand", 0.1)), "text": (("text", 1.0),), "rdf": (("rdf", 1.0),),
+       "lowent": (("lowent", 1.0),), "rand": (("rand", 1.0),)}[mixname]
+t0 = time.time()
+data, fams = corpus.mixed_frames(nframes, fb, mix=mix, pool=32)
+cache = {}
+frames = []
+for i in range(nframes):
+    k = data[i].tobytes()
+    if k not in cache: cache[k] = ref.compress(k, 3)
+    frames.append(cache[k])
+csz = sum(len(f) for f in frames)
+print(f"corpus {nframes} x {fb}: ratio {nframes*fb/csz:.3f}, prep {time.time()-t0:.1f}s", flush=True)
+sizes = [len(f) for f in frames]
+offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+src = torch.from_numpy(np.frombuffer(b"".join(frames), dtype=np.uint8).copy()).cuda()
+src = torch.cat([src, torch.zeros(64, dtype=torch.uint8, device="cuda")])
+dst = torch.zeros(nframes * fb + 64, dtype=torch.uint8, device="cuda")
+d = z.zstd_dctx()
+plan = z.BatchPlan([src.data_ptr() + int(o) for o in offs[:-1]], sizes, [dst.data_ptr() + i * fb for i in range(nframes)], [fb] * nframes)
+for it in range(iters):
+    t = time.time()
+    res = plan.decompress(d)
+    wall = (time.time() - t) * 1e3
+    ms = d.last_kernel_ms
+    print(f"iter {it}: kernels {ms:.3f} ms -> {nframes*fb/ms/1e6:.1f} GB/s ; wall {wall:.2f} ms", flush=True)
+bad = [i for i in range(nframes) if res[i] != fb]
+print("bad results:", len(bad), bad[:5], [z.error_name(res[i]) for i in bad[:3]])
+out = dst[:nframes * fb].cpu().numpy().reshape(nframes, fb)
+print("bytes equal:", bool((out == data).all()))

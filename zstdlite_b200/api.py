@@ -1,0 +1,265 @@
+"""Host-side mirror of zstdlite's R API for the one-shot path, over the C ABI.
+
+Names, argument meaning and error behaviour follow the reference:
+  zstd_cctx / zstd_dctx          R/cctx.R:38-48,72-80  -> src/cctx.c:213-315, src/dctx.c:110-197
+  zstd_compress / zstd_decompress R/serialize.R:128-156 -> src/raw-file.c:25-118,125-210
+  zstd_info                      R/zstd-info.R:19      -> src/zstd-info.c:60-87
+  zstd_dict_id                   R/dictionaries.R:27   -> src/dictionaries.c:23-58
+plus the batch entry points the benchmark shapes need.
+Everything computes on the GPU through libzstdlite_gpu.so; there is no CPU path here.
+"""
+import ctypes as C
+import warnings
+
+from . import _lib
+from ._lib import CONTENTSIZE_ERROR, CONTENTSIZE_UNKNOWN
+
+
+class ZstdError(RuntimeError):
+    pass
+
+
+def _check(r, what):
+    L = _lib.lib()
+    if L.ZSTD_isError(r):
+        raise ZstdError(f"{what}: {L.ZSTD_getErrorName(r).decode()}")
+    return r
+
+
+def _as_buffer(x):
+    """bytes-like -> (ctypes pointer-able object, length). str is UTF-8 encoded (src/raw-file.c:41-46)."""
+    if isinstance(x, str):
+        x = x.encode("utf-8")
+    mv = memoryview(x).cast("B")
+    n = mv.nbytes
+    if n == 0:
+        return C.c_char_p(b""), 0, mv
+    if mv.readonly:
+        buf = (C.c_char * n).from_buffer_copy(mv)
+    else:
+        buf = (C.c_char * n).from_buffer(mv)
+    return buf, n, mv
+
+
+class zstd_dctx:
+    """zstd_dctx(validate_checksum = TRUE, dict = NULL)  (R/cctx.R:72-80, src/dctx.c:110-197)."""
+
+    def __init__(self, validate_checksum=True, dict=None, **unknown):
+        for k in unknown:
+            warnings.warn(f"init_dctx(): Unknown option '{k}'")          # src/dctx.c:171
+        L = _lib.lib()
+        self._p = L.ZSTD_createDCtx()
+        if not self._p:
+            raise ZstdError("init_dctx(): Couldn't initialse memory for 'dctx'")
+        self.validate_checksum = bool(validate_checksum)
+        _check(L.ZSTD_DCtx_setParameter(self._p, _lib.ZSTD_d_forceIgnoreChecksum, 0 if validate_checksum else 1), "init_dctx()")
+        if dict is not None:
+            if isinstance(dict, str):
+                with open(dict, "rb") as fh:                              # filename form, src/dctx.c:183-190
+                    dict = fh.read()
+            buf, n, _ = _as_buffer(dict)
+            _check(L.ZSTD_DCtx_loadDictionary(self._p, buf, n), "init_dctx() dictionary")
+
+    def settings(self):
+        """get_dctx_settings_ (src/dctx.c:228-245; reports forceIgnoreChecksum under the name validate_checksum)."""
+        v = C.c_int(0)
+        _lib.lib().ZSTD_DCtx_getParameter(self._p, _lib.ZSTD_d_forceIgnoreChecksum, C.byref(v))
+        return {"validate_checksum": v.value}
+
+    def set_stream(self, cuda_stream):
+        _lib.lib().zl_dctx_set_stream(self._p, C.c_void_p(cuda_stream))
+
+    @property
+    def launch_count(self):
+        return _lib.lib().zl_dctx_launch_count(self._p)
+
+    @property
+    def last_kernel_ms(self):
+        return _lib.lib().zl_dctx_last_kernel_ms(self._p)
+
+    def __del__(self):
+        p = getattr(self, "_p", None)
+        if p:
+            try:
+                _lib.lib().ZSTD_freeDCtx(p)
+            except Exception:
+                pass
+            self._p = None
+
+
+class zstd_cctx:
+    """zstd_cctx(level = 3, num_threads = 1, include_checksum = FALSE, dict = NULL)  (R/cctx.R:38-48, src/cctx.c:213-315)."""
+
+    def __init__(self, level=3, num_threads=1, include_checksum=False, dict=None, **unknown):
+        for k in unknown:
+            warnings.warn(f"init_cctx(): Unknown option '{k}'")          # src/cctx.c:288
+        L = _lib.lib()
+        self._p = L.ZSTD_createCCtx()
+        if not self._p:
+            raise ZstdError("init_cctx(): Couldn't initialse memory for 'cctx'")
+        level = max(-5, min(22, int(level)))                              # src/cctx.c:261-268
+        _check(L.ZSTD_CCtx_setParameter(self._p, _lib.ZSTD_c_compressionLevel, level), "init_cctx() level")
+        if int(num_threads) > 1:                                          # src/cctx.c:269-277
+            _check(L.ZSTD_CCtx_setParameter(self._p, _lib.ZSTD_c_nbWorkers, int(num_threads)), "init_cctx() num_threads")
+        _check(L.ZSTD_CCtx_setParameter(self._p, _lib.ZSTD_c_checksumFlag, 1 if include_checksum else 0), "init_cctx() checksum")
+        if dict is not None:
+            if isinstance(dict, str):
+                with open(dict, "rb") as fh:
+                    dict = fh.read()
+            buf, n, _ = _as_buffer(dict)
+            _check(L.ZSTD_CCtx_loadDictionary(self._p, buf, n), "init_cctx() dictionary")
+
+    def settings(self):
+        """get_cctx_settings_ (src/cctx.c:343-369)."""
+        L = _lib.lib()
+        out = {}
+        for name, par in (("level", _lib.ZSTD_c_compressionLevel), ("num_threads", _lib.ZSTD_c_nbWorkers),
+                          ("include_checksum", _lib.ZSTD_c_checksumFlag)):
+            v = C.c_int(0)
+            L.ZSTD_CCtx_getParameter(self._p, par, C.byref(v))
+            out[name] = v.value
+        return out
+
+    def set_stream(self, cuda_stream):
+        _lib.lib().zl_cctx_set_stream(self._p, C.c_void_p(cuda_stream))
+
+    @property
+    def launch_count(self):
+        return _lib.lib().zl_cctx_launch_count(self._p)
+
+    @property
+    def last_kernel_ms(self):
+        return _lib.lib().zl_cctx_last_kernel_ms(self._p)
+
+    def __del__(self):
+        p = getattr(self, "_p", None)
+        if p:
+            try:
+                _lib.lib().ZSTD_freeCCtx(p)
+            except Exception:
+                pass
+            self._p = None
+
+
+def zstd_compress(src, cctx=None, **opts):
+    """zstd_compress(src, ..., cctx)  (src/raw-file.c:25-118): raw vector or string -> one zstd frame."""
+    L = _lib.lib()
+    if cctx is None:
+        cctx = zstd_cctx(**opts)
+    buf, n, _keep = _as_buffer(src)
+    cap = L.ZSTD_compressBound(n)
+    dst = C.create_string_buffer(max(1, cap))
+    L.ZSTD_CCtx_setParameter(cctx._p, _lib.ZSTD_c_stableInBuffer, 1)      # src/cctx.c:70-96
+    L.ZSTD_CCtx_setParameter(cctx._p, _lib.ZSTD_c_stableOutBuffer, 1)
+    r = L.ZSTD_compress2(cctx._p, dst, cap, buf, n)
+    _check(r, "zstd_compress(): Compression error")
+    return dst.raw[:r]
+
+
+def zstd_decompress(src, type="raw", dctx=None, **opts):
+    """zstd_decompress(src, type, ..., dctx)  (src/raw-file.c:125-210): first frame only, like the reference."""
+    L = _lib.lib()
+    if dctx is None:
+        dctx = zstd_dctx(**opts)
+    buf, n, _keep = _as_buffer(src)
+    csize = L.ZSTD_findFrameCompressedSize(buf, n)
+    _check(csize, "zstd_decompress(): Error finding compressed size")
+    usize = L.ZSTD_getFrameContentSize(buf, csize)
+    if usize >= CONTENTSIZE_ERROR:
+        # the reference does not check this and would try a 2^64 allocation; we raise instead
+        raise ZstdError("zstd_decompress(): frame does not record its content size")
+    dst = C.create_string_buffer(max(1, usize))
+    L.ZSTD_DCtx_setParameter(dctx._p, _lib.ZSTD_d_stableOutBuffer, 1)     # src/dctx.c:98-103
+    r = L.ZSTD_decompressDCtx(dctx._p, dst, usize, buf, csize)
+    _check(r, "zstd_decompress(): De-compression error")
+    out = dst.raw[:r]
+    return out.decode("utf-8") if type == "string" else out
+
+
+def zstd_info(src):
+    """zstd_info(src)  (src/zstd-info.c:60-87)."""
+    L = _lib.lib()
+    if isinstance(src, str):
+        with open(src, "rb") as fh:
+            src = fh.read(18)
+    buf, n, _keep = _as_buffer(src)
+    fh = _lib.FrameHeader()
+    r = L.ZSTD_getFrameHeader(C.byref(fh), buf, min(n, 18))
+    if r != 0:
+        raise ZstdError("zstd_info(): Couldn't read frame header")
+    whole, m, _k = _as_buffer(src)
+    csize = L.ZSTD_findFrameCompressedSize(whole, m)
+    return {"uncompressed_size": None if fh.frameContentSize == CONTENTSIZE_UNKNOWN else int(fh.frameContentSize),
+            "compressed_size": None if L.ZSTD_isError(csize) else int(csize),
+            "dict_id": int(fh.dictID), "has_checksum": bool(fh.checksumFlag)}
+
+
+def zstd_dict_id(x):
+    """zstd_dict_id(dict | compressed frame)  (src/dictionaries.c:23-58)."""
+    L = _lib.lib()
+    buf, n, _keep = _as_buffer(x)
+    did = L.ZDICT_getDictID(buf, n)
+    if did == 0:
+        did = L.ZSTD_getDictID_fromFrame(buf, n)
+    return int(did)
+
+
+def zstd_version():
+    return _lib.lib().ZSTD_versionString().decode()
+
+
+# ---- batch extension ---------------------------------------------------------------------------------
+def _ptr_arrays(ptrs, sizes):
+    n = len(ptrs)
+    return (C.c_void_p * n)(*ptrs), (C.c_size_t * n)(*sizes)
+
+
+def decompress_batch(dctx, src_ptrs, src_sizes, dst_ptrs, dst_caps, device=True):
+    """zl_decompress_batch: lists of raw addresses (device pointers when device=True). Returns list of sizes/error codes."""
+    L = _lib.lib()
+    n = len(src_ptrs)
+    sp, ss = _ptr_arrays(src_ptrs, src_sizes)
+    dp, ds = _ptr_arrays(dst_ptrs, dst_caps)
+    res = (C.c_size_t * n)()
+    r = L.zl_decompress_batch(dctx._p, sp, ss, dp, ds, res, n, 1 if device else 0)
+    _check(r, "zl_decompress_batch()")
+    return list(res)
+
+
+def compress_batch(cctx, src_ptrs, src_sizes, dst_ptrs, dst_caps, device=True):
+    L = _lib.lib()
+    n = len(src_ptrs)
+    sp, ss = _ptr_arrays(src_ptrs, src_sizes)
+    dp, ds = _ptr_arrays(dst_ptrs, dst_caps)
+    res = (C.c_size_t * n)()
+    r = L.zl_compress_batch(cctx._p, sp, ss, dp, ds, res, n, 1 if device else 0)
+    _check(r, "zl_compress_batch()")
+    return list(res)
+
+
+class BatchPlan:
+    """Pre-built ctypes argument arrays for repeated batch calls on the same buffers (bench loop)."""
+
+    def __init__(self, src_ptrs, src_sizes, dst_ptrs, dst_caps):
+        self.n = len(src_ptrs)
+        self.sp, self.ss = _ptr_arrays(src_ptrs, src_sizes)
+        self.dp, self.ds = _ptr_arrays(dst_ptrs, dst_caps)
+        self.res = (C.c_size_t * self.n)()
+
+    def decompress(self, dctx, device=True):
+        r = _lib.lib().zl_decompress_batch(dctx._p, self.sp, self.ss, self.dp, self.ds, self.res, self.n, 1 if device else 0)
+        _check(r, "zl_decompress_batch()")
+        return self.res
+
+    def compress(self, cctx, device=True):
+        r = _lib.lib().zl_compress_batch(cctx._p, self.sp, self.ss, self.dp, self.ds, self.res, self.n, 1 if device else 0)
+        _check(r, "zl_compress_batch()")
+        return self.res
+
+
+def is_error(code):
+    return bool(_lib.lib().ZSTD_isError(code))
+
+
+def error_name(code):
+    return _lib.lib().ZSTD_getErrorName(code).decode()

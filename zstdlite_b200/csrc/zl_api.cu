@@ -1,0 +1,422 @@
+// zl_api.cu -- the C ABI (include/zstdlite_gpu.h): error/version helpers, frame introspection, the
+// decompression context and the batched decode driver.  Compression entry points are in zl_api_compress.cu.
+#include <stdio.h>
+#include <stdlib.h>
+#include <new>
+#include "../../include/zstdlite_gpu.h"
+#include "zl_host.h"
+#include "zl_plan.h"
+#include "zl_dec_entropy.cuh"     // ZL_HD table builders reused to digest dictionaries on the host (zstd.c:42053)
+
+#define ZL_EXPORT extern "C" __attribute__((visibility("default")))
+#define ZL_ALIAS(ret, name, params) extern "C" __attribute__((visibility("default"), alias(#name))) ret zlg_##name params;
+
+// ---------------------------------------------------------------------------------------------- errors
+ZL_EXPORT unsigned ZSTD_isError(size_t code) { return zl_is_error(code); }
+ZL_EXPORT const char* ZSTD_getErrorName(size_t code)
+{
+    if (!zl_is_error(code)) return "No error detected";
+    switch ((unsigned)((size_t)0 - code)) {          // strings: zstd.c:3590-3630
+    case ZL_E_GENERIC: return "Error (generic)";
+    case ZL_E_prefix_unknown: return "Unknown frame descriptor";
+    case ZL_E_version_unsupported: return "Version not supported";
+    case ZL_E_frameParameter_unsupported: return "Unsupported frame parameter";
+    case ZL_E_frameParameter_windowTooLarge: return "Frame requires too much memory for decoding";
+    case ZL_E_corruption_detected: return "Data corruption detected";
+    case ZL_E_checksum_wrong: return "Restored data doesn't match checksum";
+    case ZL_E_literals_headerWrong: return "Header of Literals' block doesn't respect format specification";
+    case ZL_E_parameter_unsupported: return "Unsupported parameter";
+    case ZL_E_parameter_combination_unsupported: return "Unsupported combination of parameters";
+    case ZL_E_parameter_outOfBound: return "Parameter is out of bound";
+    case ZL_E_init_missing: return "Context should be init first";
+    case ZL_E_memory_allocation: return "Allocation error : not enough memory";
+    case ZL_E_workSpace_tooSmall: return "workSpace buffer is not large enough";
+    case ZL_E_stage_wrong: return "Operation not authorized at current processing stage";
+    case ZL_E_tableLog_tooLarge: return "tableLog requires too much memory : unsupported";
+    case ZL_E_maxSymbolValue_tooLarge: return "Unsupported max Symbol Value : too large";
+    case ZL_E_maxSymbolValue_tooSmall: return "Specified maxSymbolValue is too small";
+    case ZL_E_stabilityCondition_notRespected: return "pledged buffer stability condition is not respected";
+    case ZL_E_dictionary_corrupted: return "Dictionary is corrupted";
+    case ZL_E_dictionary_wrong: return "Dictionary mismatch";
+    case ZL_E_dictionaryCreation_failed: return "Cannot create Dictionary from provided samples";
+    case ZL_E_dstSize_tooSmall: return "Destination buffer is too small";
+    case ZL_E_srcSize_wrong: return "Src size is incorrect";
+    case ZL_E_dstBuffer_null: return "Operation on NULL destination buffer";
+    case ZL_E_noForwardProgress_destFull: return "Operation made no progress over multiple calls, due to output buffer being full";
+    case ZL_E_noForwardProgress_inputEmpty: return "Operation made no progress over multiple calls, due to input being empty";
+    default: return "Unspecified error code";
+    }
+}
+ZL_EXPORT const char* ZSTD_versionString(void) { return "1.5.6"; }      // format/ABI level of the reference's libzstd
+ZL_EXPORT const char* zl_backend_string(void) { return "zstdlite-b200 0.1 (CUDA sm_100a; no CPU fallback)"; }
+ZL_ALIAS(unsigned, ZSTD_isError, (size_t))
+ZL_ALIAS(const char*, ZSTD_getErrorName, (size_t))
+ZL_ALIAS(const char*, ZSTD_versionString, (void))
+
+// ---------------------------------------------------------------------------------------------- frame introspection (host)
+size_t zl_host_frame_header(ZlHostFrameHeader* h, const void* srcv, size_t srcSize)
+{
+    const u8* ip = (const u8*)srcv;
+    memset(h, 0, sizeof(*h));
+    if (srcSize > 0 && ip == nullptr) return ZL_ERROR(GENERIC);
+    if (srcSize < 5) {                               // zstd.c:41061-41077: a too-short prefix must still look like a magic number
+        if (srcSize > 0) {
+            u8 m[4] = {0x28, 0xB5, 0x2F, 0xFD};
+            u8 sk[4] = {0x50, 0x2A, 0x4D, 0x18};
+            bool a = true, b = true;
+            for (size_t i = 0; i < srcSize && i < 4; i++) { if (ip[i] != m[i]) a = false; if (i > 0 && ip[i] != sk[i]) b = false; if (i == 0 && (ip[i] & 0xF0) != 0x50) b = false; }
+            if (!a && !b) return ZL_ERROR(prefix_unknown);
+        }
+        return 5;
+    }
+    u32 magic = zl_rd32(ip);
+    if ((magic & 0xFFFFFFF0u) == ZL_MAGIC_SKIP) {
+        if (srcSize < 8) return 8;
+        h->skippable = 1; h->contentSize = zl_rd32(ip + 4); h->headerSize = 8;
+        return 0;
+    }
+    if (magic != ZL_MAGIC) return ZL_ERROR(prefix_unknown);
+    u32 fhd = ip[4], didCode = fhd & 3, single = (fhd >> 5) & 1, fcsID = fhd >> 6;
+    u32 didSz = didCode == 3 ? 4 : didCode, fcsSz = fcsID == 0 ? (single ? 1u : 0u) : (1u << fcsID);
+    u32 hs = 5 + (single ? 0 : 1) + didSz + fcsSz;
+    if (srcSize < hs) return hs;
+    h->headerSize = hs;
+    if (fhd & 8) return ZL_ERROR(frameParameter_unsupported);
+    u32 p = 5; u64 window = 0;
+    if (!single) {
+        u32 wl = ip[p++], wlog = (wl >> 3) + 10;
+        if (wlog > 31) return ZL_ERROR(frameParameter_windowTooLarge);
+        window = 1ull << wlog; window += (window >> 3) * (wl & 7);
+    }
+    u32 did = 0;
+    if (didSz == 1) did = ip[p]; else if (didSz == 2) did = zl_rd16(ip + p); else if (didSz == 4) did = zl_rd32(ip + p);
+    p += didSz;
+    u64 fcs = ZSTD_CONTENTSIZE_UNKNOWN;
+    if (fcsID == 0) { if (single) fcs = ip[p]; } else if (fcsID == 1) fcs = zl_rd16(ip + p) + 256; else if (fcsID == 2) fcs = zl_rd32(ip + p); else fcs = zl_rd64(ip + p);
+    if (single) window = fcs;
+    h->contentSize = fcs; h->windowSize = window;
+    h->blockSizeMax = (unsigned)(window < ZL_BLOCKSIZE_MAX ? window : ZL_BLOCKSIZE_MAX);
+    h->dictID = did; h->checksumFlag = (fhd >> 2) & 1;
+    return 0;
+}
+
+size_t zl_host_find_frame_size(const void* srcv, size_t srcSize, unsigned* nblocksOut)
+{
+    const u8* ip = (const u8*)srcv;
+    if (nblocksOut) *nblocksOut = 0;
+    if (srcSize >= 8 && (zl_rd32(ip) & 0xFFFFFFF0u) == ZL_MAGIC_SKIP) {         // zstd.c:41188
+        u64 sz = (u64)zl_rd32(ip + 4) + 8;
+        if (sz > srcSize) return ZL_ERROR(srcSize_wrong);
+        return (size_t)sz;
+    }
+    ZlHostFrameHeader h;
+    size_t r = zl_host_frame_header(&h, srcv, srcSize);
+    if (zl_is_error(r)) return r;
+    if (r > 0) return ZL_ERROR(srcSize_wrong);
+    size_t pos = h.headerSize; unsigned nb = 0;
+    for (;;) {                                                                   // zstd.c:41370-41384
+        if (srcSize - pos < 3) return ZL_ERROR(srcSize_wrong);
+        u32 bh = zl_rd24(ip + pos), last = bh & 1, type = (bh >> 1) & 3, cs = bh >> 3;
+        if (type == 3) return ZL_ERROR(corruption_detected);
+        if (type == 1) cs = 1;
+        if (3 + (size_t)cs > srcSize - pos) return ZL_ERROR(srcSize_wrong);
+        pos += 3 + cs; nb++;
+        if (last) break;
+    }
+    if (h.checksumFlag) { if (srcSize - pos < 4) return ZL_ERROR(srcSize_wrong); pos += 4; }
+    if (nblocksOut) *nblocksOut = nb;
+    return pos;
+}
+
+ZL_EXPORT size_t ZSTD_getFrameHeader(ZSTD_frameHeader* z, const void* src, size_t srcSize)
+{
+    ZlHostFrameHeader h;
+    size_t r = zl_host_frame_header(&h, src, srcSize);
+    if (r != 0) return r;
+    memset(z, 0, sizeof(*z));
+    z->frameContentSize = h.contentSize; z->windowSize = h.windowSize; z->blockSizeMax = h.blockSizeMax;
+    z->frameType = h.skippable ? ZSTD_skippableFrame : ZSTD_frame; z->headerSize = h.headerSize;
+    z->dictID = h.dictID; z->checksumFlag = h.checksumFlag;
+    return 0;
+}
+ZL_EXPORT unsigned long long ZSTD_getFrameContentSize(const void* src, size_t srcSize)
+{
+    ZlHostFrameHeader h;
+    if (zl_host_frame_header(&h, src, srcSize) != 0) return ZSTD_CONTENTSIZE_ERROR;
+    return h.skippable ? 0ULL : h.contentSize;
+}
+ZL_EXPORT size_t ZSTD_findFrameCompressedSize(const void* src, size_t srcSize) { return zl_host_find_frame_size(src, srcSize, nullptr); }
+ZL_EXPORT unsigned ZSTD_getDictID_fromFrame(const void* src, size_t srcSize)
+{
+    ZlHostFrameHeader h;
+    if (zl_host_frame_header(&h, src, srcSize) != 0) return 0;
+    return h.dictID;
+}
+ZL_EXPORT unsigned ZSTD_getDictID_fromDict(const void* dict, size_t dictSize)
+{
+    if (dictSize < 8 || zl_rd32((const u8*)dict) != ZL_MAGIC_DICT) return 0;
+    return zl_rd32((const u8*)dict + 4);
+}
+ZL_EXPORT unsigned ZDICT_getDictID(const void* dict, size_t dictSize) { return ZSTD_getDictID_fromDict(dict, dictSize); }
+ZL_ALIAS(size_t, ZSTD_getFrameHeader, (ZSTD_frameHeader*, const void*, size_t))
+ZL_ALIAS(unsigned long long, ZSTD_getFrameContentSize, (const void*, size_t))
+ZL_ALIAS(size_t, ZSTD_findFrameCompressedSize, (const void*, size_t))
+ZL_ALIAS(unsigned, ZSTD_getDictID_fromFrame, (const void*, size_t))
+ZL_ALIAS(unsigned, ZSTD_getDictID_fromDict, (const void*, size_t))
+ZL_ALIAS(unsigned, ZDICT_getDictID, (const void*, size_t))
+
+// ---------------------------------------------------------------------------------------------- decompression context
+struct ZSTD_DCtx_s {
+    int forceIgnoreChecksum = 0, stableOut = 0, windowLogMax = 27;
+    std::vector<u8> dictRaw;
+    ZlDevBuf dDictContent, dDict;          // device copies (content bytes, ZlDictDev)
+    bool hasDict = false;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double lastKernelMs = 0.0;
+    unsigned long long launches = 0;
+    ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dSrc, dDst;
+    ZlPinBuf hDescs, hResults;
+};
+
+static bool zl_ctx_stream(cudaStream_t* st, bool* own, cudaEvent_t* e0, cudaEvent_t* e1)
+{
+    if (!*st && !*own) {
+        if (cudaStreamCreateWithFlags(st, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        *own = true;
+    }
+    if (!*e0) { if (cudaEventCreate(e0) != cudaSuccess || cudaEventCreate(e1) != cudaSuccess) { (void)cudaGetLastError(); return false; } }
+    return true;
+}
+
+ZL_EXPORT ZSTD_DCtx* ZSTD_createDCtx(void) { return new (std::nothrow) ZSTD_DCtx_s(); }
+ZL_EXPORT size_t ZSTD_freeDCtx(ZSTD_DCtx* c)
+{
+    if (!c) return 0;
+    ZlDevBuf* bufs[] = {&c->dDictContent, &c->dDict, &c->dDescs, &c->dInfos, &c->dResults, &c->dHdr, &c->dRec, &c->dCk, &c->dLit, &c->dSrc, &c->dDst};
+    for (ZlDevBuf* b : bufs) b->release();
+    c->hDescs.release(); c->hResults.release();
+    if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
+    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+ZL_EXPORT size_t ZSTD_DCtx_reset(ZSTD_DCtx* c, ZSTD_ResetDirective r)
+{
+    if (r == ZSTD_reset_parameters || r == ZSTD_reset_session_and_parameters) {       // zstd.c:42548-42565
+        c->forceIgnoreChecksum = 0; c->stableOut = 0; c->windowLogMax = 27;
+        c->hasDict = false; c->dictRaw.clear();
+    }
+    return 0;
+}
+ZL_EXPORT size_t ZSTD_DCtx_setParameter(ZSTD_DCtx* c, ZSTD_dParameter p, int v)
+{
+    switch ((int)p) {
+    case ZSTD_d_windowLogMax: if (v == 0) v = 27; if (v < 10 || v > 31) return ZL_ERROR(parameter_outOfBound); c->windowLogMax = v; return 0;
+    case ZSTD_d_stableOutBuffer: if (v < 0 || v > 1) return ZL_ERROR(parameter_outOfBound); c->stableOut = v; return 0;
+    case ZSTD_d_forceIgnoreChecksum: if (v < 0 || v > 1) return ZL_ERROR(parameter_outOfBound); c->forceIgnoreChecksum = v; return 0;
+    default: return ZL_ERROR(parameter_unsupported);
+    }
+}
+ZL_EXPORT size_t ZSTD_DCtx_getParameter(ZSTD_DCtx* c, ZSTD_dParameter p, int* v)
+{
+    switch ((int)p) {
+    case ZSTD_d_windowLogMax: *v = c->windowLogMax; return 0;
+    case ZSTD_d_stableOutBuffer: *v = c->stableOut; return 0;
+    case ZSTD_d_forceIgnoreChecksum: *v = c->forceIgnoreChecksum; return 0;
+    default: return ZL_ERROR(parameter_unsupported);
+    }
+}
+ZL_EXPORT size_t zl_dctx_set_stream(ZSTD_DCtx* c, void* s)
+{
+    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)s; c->ownStream = false;
+    if (!s) { c->ownStream = false; c->stream = nullptr; }
+    return 0;
+}
+ZL_EXPORT unsigned long long zl_dctx_launch_count(const ZSTD_DCtx* c) { return c->launches; }
+ZL_EXPORT double zl_dctx_last_kernel_ms(const ZSTD_DCtx* c) { return c->lastKernelMs; }
+
+// Digest a dictionary (zstd.c:42053-42137 ZSTD_loadDEntropy, 42140 insertDictionary) into ZlDictDev.
+ZL_EXPORT size_t ZSTD_DCtx_loadDictionary(ZSTD_DCtx* c, const void* dict, size_t dictSize)
+{
+    c->hasDict = false; c->dictRaw.clear();
+    if (!dict || !dictSize) return 0;
+    c->dictRaw.assign((const u8*)dict, (const u8*)dict + dictSize);
+    std::vector<u8> pad(dictSize + 16, 0);
+    u8* d = pad.data() + 4 - (((size_t)pad.data()) & 3);            // 4-aligned copy for the word reader
+    memcpy(d, dict, dictSize);
+    ZlDictDev* hd = new (std::nothrow) ZlDictDev();
+    if (!hd) return ZL_ERROR(memory_allocation);
+    memset(hd, 0, sizeof(*hd));
+    size_t contentOff = 0;
+    if (dictSize >= 8 && zl_rd32(d) == ZL_MAGIC_DICT) {
+        static const ZlConstTables ct = {ZL_LL_BASE_INIT, ZL_ML_BASE_INIT, ZL_LL_BITS_INIT, ZL_ML_BITS_INIT, ZL_LL_DEFNORM_INIT, ZL_ML_DEFNORM_INIT, ZL_OF_DEFNORM_INIT};
+        hd->dictID = zl_rd32(d + 4);
+        ZlFrameSm* f = new (std::nothrow) ZlFrameSm();
+        if (!f) { delete hd; return ZL_ERROR(memory_allocation); }
+        memset(f, 0, sizeof(*f));
+        size_t p = 8; bool ok = true;
+        u32 th = zl_huf_read_stats(*f, d + p, (u32)(dictSize - p), (const u32*)d, 0, (u32)p);
+        if (!th) ok = false;
+        if (ok) { for (u32 q = 0; q < 4; q++) zl_huf_fill(*f, q); memcpy(hd->huf, f->huf, sizeof(hd->huf)); hd->hufLog = f->ctl.hufLog; p += th; }
+        const u32 order[3] = {1, 2, 0}, maxSym[3] = {35, 31, 52}, maxLog[3] = {9, 8, 9};      // OF, ML, LL in the file
+        for (int k = 0; ok && k < 3; k++) {
+            u32 t = order[k], ms = maxSym[t], tl; i16 norm[64];
+            u32 h = p < dictSize ? zl_read_ncount(d + p, (u32)(dictSize - p), norm, &ms, &tl) : 0;
+            if (!h || tl > maxLog[t]) { ok = false; break; }
+            u32* tbl = t == 0 ? hd->fseLL : (t == 1 ? hd->fseOF : hd->fseML);
+            if (!zl_fse_build(tbl, norm, ms, tl, t, ct)) { ok = false; break; }
+            hd->tlog[t] = tl; p += h;
+        }
+        if (ok && p + 12 > dictSize) ok = false;
+        if (ok) {
+            size_t content = dictSize - (p + 12);
+            for (int i = 0; i < 3; i++) { u32 r = zl_rd32(d + p + 4 * i); if (r == 0 || r > content) ok = false; hd->rep[i] = r; }
+            contentOff = p + 12;
+        }
+        delete f;
+        if (!ok) { delete hd; c->dictRaw.clear(); return ZL_ERROR(dictionary_corrupted); }
+        hd->hasEntropy = 1;
+    }
+    hd->contentSize = (u32)(dictSize - contentOff);
+    bool ok = c->dDictContent.reserve(hd->contentSize + 16) && c->dDict.reserve(sizeof(ZlDictDev));
+    if (ok) {
+        hd->content = c->dDictContent.as<u8>();
+        ok = cudaMemcpy(c->dDictContent.p, d + contentOff, hd->contentSize, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(c->dDict.p, hd, sizeof(ZlDictDev), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    delete hd;
+    if (!ok) { (void)cudaGetLastError(); c->dictRaw.clear(); return ZL_ERROR(memory_allocation); }
+    c->hasDict = true;
+    return 0;
+}
+ZL_ALIAS(ZSTD_DCtx*, ZSTD_createDCtx, (void))
+ZL_ALIAS(size_t, ZSTD_freeDCtx, (ZSTD_DCtx*))
+ZL_ALIAS(size_t, ZSTD_DCtx_reset, (ZSTD_DCtx*, ZSTD_ResetDirective))
+ZL_ALIAS(size_t, ZSTD_DCtx_setParameter, (ZSTD_DCtx*, ZSTD_dParameter, int))
+ZL_ALIAS(size_t, ZSTD_DCtx_getParameter, (ZSTD_DCtx*, ZSTD_dParameter, int*))
+ZL_ALIAS(size_t, ZSTD_DCtx_loadDictionary, (ZSTD_DCtx*, const void*, size_t))
+
+// ---------------------------------------------------------------------------------------------- batched decode
+static void zl_build_runs(std::vector<ZlRun>& runs, const void* const* ptr, const size_t* size, size_t n, size_t* total)
+{
+    runs.clear();
+    size_t off = 0;
+    for (size_t i = 0; i < n; i++) {
+        const u8* p = (const u8*)ptr[i];
+        if (!runs.empty()) {
+            ZlRun& r = runs.back();
+            if (p == r.hbase + r.bytes) { r.bytes += size[i]; r.count++; continue; }
+            off = (r.devOff + r.bytes + 255) & ~(size_t)255;
+        }
+        ZlRun r; r.first = i; r.count = 1; r.hbase = p; r.bytes = size[i]; r.devOff = off;
+        runs.push_back(r);
+    }
+    *total = runs.empty() ? 0 : runs.back().devOff + runs.back().bytes;
+}
+
+ZL_EXPORT size_t zl_decompress_batch(ZSTD_DCtx* c, const void* const* src, const size_t* srcSize, void* const* dst,
+                                     const size_t* dstCap, size_t* result, size_t n, int dev)
+{
+    if (!c) return ZL_ERROR(GENERIC);
+    if (n == 0) return 0;
+    if (n > 0x7FFFFFFFull / 8) return ZL_ERROR(memory_allocation);
+    if (!zl_ctx_stream(&c->stream, &c->ownStream, &c->ev0, &c->ev1)) return ZL_ERROR(memory_allocation);
+    cudaStream_t st = c->stream;
+    if (!c->hDescs.reserve(n * sizeof(ZlFrameDesc)) || !c->hResults.reserve(n * 8)) return ZL_ERROR(memory_allocation);
+    ZlFrameDesc* hd = c->hDescs.as<ZlFrameDesc>();
+    std::vector<ZlRun> sruns, druns;
+    size_t srcTotal = 0, dstTotal = 0;
+    if (!dev) {
+        zl_build_runs(sruns, src, srcSize, n, &srcTotal);
+        zl_build_runs(druns, (const void* const*)dst, dstCap, n, &dstTotal);
+        if (!c->dSrc.reserve(srcTotal + 64) || !c->dDst.reserve(dstTotal + 64)) return ZL_ERROR(memory_allocation);
+    }
+    u64 lit = 0, rec = 0, hdr = 0, ck = 0;
+    size_t sr = 0, dr = 0;
+    for (size_t i = 0; i < n; i++) {
+        ZlFrameDesc& d = hd[i];
+        if (srcSize[i] > 0xFFFFFFF0ull || dstCap[i] > 0x7FFFFFF0ull) { return ZL_ERROR(memory_allocation); }
+        if (dev) { d.src = (const u8*)src[i]; d.dst = (u8*)dst[i]; }
+        else {
+            while (sr + 1 < sruns.size() && i >= sruns[sr + 1].first) sr++;
+            while (dr + 1 < druns.size() && i >= druns[dr + 1].first) dr++;
+            d.src = c->dSrc.as<u8>() + sruns[sr].devOff + ((const u8*)src[i] - sruns[sr].hbase);
+            d.dst = c->dDst.as<u8>() + druns[dr].devOff + ((const u8*)dst[i] - druns[dr].hbase);
+        }
+        d.srcSize = (u32)srcSize[i]; d.dstCap = (u32)dstCap[i];
+        zl_plan_frame(d.srcSize, d.dstCap, &d.litCap, &d.recCap, &d.hdrCap, &d.ckCap);
+        d.litBase = lit; d.recBase = rec; d.hdrBase = hdr; d.ckBase = ck;
+        lit += ((u64)d.litCap + 15) & ~15ull; rec += d.recCap; hdr += d.hdrCap; ck += d.ckCap;
+    }
+    if (!c->dDescs.reserve(n * sizeof(ZlFrameDesc)) || !c->dInfos.reserve(n * sizeof(ZlFrameInfo)) || !c->dResults.reserve(n * 8) ||
+        !c->dLit.reserve(lit + 64) || !c->dRec.reserve(rec * 8) || !c->dHdr.reserve(hdr * sizeof(ZlBlockHdr)) || !c->dCk.reserve(ck * 8))
+        return ZL_ERROR(memory_allocation);
+    cudaMemcpyAsync(c->dDescs.p, hd, n * sizeof(ZlFrameDesc), cudaMemcpyHostToDevice, st);
+    if (!dev) for (const ZlRun& r : sruns) if (r.bytes) cudaMemcpyAsync(c->dSrc.as<u8>() + r.devOff, r.hbase, r.bytes, cudaMemcpyHostToDevice, st);
+    ZlDecodeLaunch L;
+    L.descs = c->dDescs.as<ZlFrameDesc>(); L.infos = c->dInfos.as<ZlFrameInfo>(); L.hdrArena = c->dHdr.as<ZlBlockHdr>();
+    L.recArena = c->dRec.as<u64>(); L.ckArena = c->dCk.as<u64>(); L.litArena = c->dLit.as<u8>(); L.results = c->dResults.as<u64>();
+    L.nframes = (u32)n; L.verifyChecksum = !c->forceIgnoreChecksum; L.dict = c->hasDict ? c->dDict.as<ZlDictDev>() : nullptr;
+    cudaEventRecord(c->ev0, st);
+    cudaError_t e = zl_launch_decode(L, st);
+    cudaEventRecord(c->ev1, st);
+    c->launches += 2 + (L.verifyChecksum ? 1 : 0);
+    if (e != cudaSuccess) { fprintf(stderr, "zstdlite_gpu: kernel launch failed: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
+    cudaMemcpyAsync(c->hResults.p, c->dResults.p, n * 8, cudaMemcpyDeviceToHost, st);
+    if (!dev) for (const ZlRun& r : druns) if (r.bytes) cudaMemcpyAsync((void*)r.hbase, c->dDst.as<u8>() + r.devOff, r.bytes, cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { fprintf(stderr, "zstdlite_gpu: device error: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->lastKernelMs = ms;
+    const u64* hr = c->hResults.as<u64>();
+    for (size_t i = 0; i < n; i++) result[i] = (size_t)hr[i];
+    return 0;
+}
+
+// zstd.c:41798 ZSTD_decompressDCtx -> 41671 ZSTD_decompressMultiFrame: concatenated + skippable frames.
+ZL_EXPORT size_t ZSTD_decompressDCtx(ZSTD_DCtx* c, void* dst, size_t dstCap, const void* srcv, size_t srcSize)
+{
+    const u8* src = (const u8*)srcv;
+    std::vector<const void*> fsrc; std::vector<size_t> fsize, fcap, fres; std::vector<void*> fdst;
+    size_t op = 0; bool more = false;
+    auto flush = [&]() -> size_t {
+        if (fsrc.empty()) return 0;
+        fres.assign(fsrc.size(), 0);
+        size_t r = zl_decompress_batch(c, fsrc.data(), fsize.data(), fdst.data(), fcap.data(), fres.data(), fsrc.size(), 0);
+        if (zl_is_error(r)) return r;
+        for (size_t k = 0; k < fres.size(); k++) if (zl_is_error(fres[k])) return fres[k];
+        size_t last = fres.back();
+        fsrc.clear(); fsize.clear(); fdst.clear(); fcap.clear();
+        return last;
+    };
+    while (srcSize >= 5) {                                     // ZSTD_startingInputLength, zstd.c:41681
+        if ((zl_rd32(src) & 0xFFFFFFF0u) == ZL_MAGIC_SKIP) {
+            size_t sk = zl_host_find_frame_size(src, srcSize, nullptr);
+            if (zl_is_error(sk)) return sk;
+            src += sk; srcSize -= sk; more = true; continue;
+        }
+        ZlHostFrameHeader h;
+        size_t r = zl_host_frame_header(&h, src, srcSize);
+        if (zl_is_error(r)) { if (more && r == ZL_ERROR(prefix_unknown)) return ZL_ERROR(srcSize_wrong); return r; }   // zstd.c:41724-41729
+        if (r > 0) return ZL_ERROR(srcSize_wrong);
+        size_t fs = zl_host_find_frame_size(src, srcSize, nullptr);
+        if (zl_is_error(fs)) return fs;
+        if (h.contentSize != ZSTD_CONTENTSIZE_UNKNOWN) {
+            if (h.contentSize > dstCap - op) return ZL_ERROR(dstSize_tooSmall);
+            fsrc.push_back(src); fsize.push_back(fs); fdst.push_back((u8*)dst + op); fcap.push_back((size_t)h.contentSize);
+            op += (size_t)h.contentSize;
+        } else {                                               // size only known after decoding: run what we have, then this one alone
+            size_t e = flush(); if (zl_is_error(e)) return e;
+            fsrc.push_back(src); fsize.push_back(fs); fdst.push_back((u8*)dst + op); fcap.push_back(dstCap - op);
+            e = flush(); if (zl_is_error(e)) return e;
+            op += e;
+        }
+        src += fs; srcSize -= fs; more = true;
+    }
+    if (srcSize) return ZL_ERROR(srcSize_wrong);               // zstd.c:41766
+    size_t e = flush(); if (zl_is_error(e)) return e;
+    return op;
+}
+ZL_ALIAS(size_t, ZSTD_decompressDCtx, (ZSTD_DCtx*, void*, size_t, const void*, size_t))

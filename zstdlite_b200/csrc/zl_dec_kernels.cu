@@ -1,0 +1,170 @@
+// zl_dec_kernels.cu -- the three decode kernels and their launchers (sm_100a).
+//   K1 zl_k_entropy   quad-per-frame entropy decode -> literal / record / header arenas
+//   K2 zl_k_execute   warp-per-frame sequence execution -> frame output
+//   K3 zl_k_checksum  quad-per-frame XXH64 of the output, compared with the frame trailer
+#include "zl_dec_entropy.cuh"
+#include "zl_dec_exec.cuh"
+#include "zl_launch.h"
+
+__constant__ ZlConstTables c_tables = {
+    ZL_LL_BASE_INIT, ZL_ML_BASE_INIT, ZL_LL_BITS_INIT, ZL_ML_BITS_INIT,
+    ZL_LL_DEFNORM_INIT, ZL_ML_DEFNORM_INIT, ZL_OF_DEFNORM_INIT};
+
+#define ZL_CT_BYTES ((sizeof(ZlConstTables) + 15) & ~(size_t)15)
+
+__global__ void __launch_bounds__(32)
+zl_k_entropy(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, ZlBlockHdr* hdrArena,
+             u64* recArena, u64* ckArena, u8* litArena, u32 nframes, const ZlDictDev* dict)
+{
+    extern __shared__ __align__(16) u8 smraw[];
+    ZlConstTables& ct = *reinterpret_cast<ZlConstTables*>(smraw);
+    ZlFrameSm* fs = reinterpret_cast<ZlFrameSm*>(smraw + ZL_CT_BYTES);
+    const u32 lane = threadIdx.x, quad = lane >> 2, q = lane & 3;
+    const u32 qmask = 0xFu << (quad * 4);
+    {   // constant tables -> shared memory (divergent lookups by code are conflict-cheap there)
+        const u32* s = reinterpret_cast<const u32*>(&c_tables);
+        u32* d = reinterpret_cast<u32*>(&ct);
+        for (u32 i = lane; i < sizeof(ZlConstTables) / 4; i += 32) d[i] = s[i];
+    }
+    __syncwarp();
+    const u32 frame = blockIdx.x * ZL_QUADS_PER_WARP + quad;
+    if (frame >= nframes) return;
+    ZlFrameSm& f = fs[quad];
+    const ZlFrameDesc d = descs[frame];
+    ZlFrameInfo& info = infos[frame];
+    ZlBlockHdr* hdrs = hdrArena + d.hdrBase;
+    u64* recs = recArena + d.recBase;
+    u64* cks = ckArena + d.ckBase;
+    u8* lits = litArena + d.litBase;
+    const u32 bias = (u32)(((size_t)d.src) & 3);
+    const u32* wbase = reinterpret_cast<const u32*>(d.src - bias);
+
+    if (q == 0) {
+        zl_ent_begin_frame(f, d, info, dict ? dict->contentSize : 0u, dict ? dict->dictID : 0u);
+        if (dict && dict->hasEntropy && !f.ctl.err) {          // zstd.c:42140-42159: seed tables + repcodes
+            f.ctl.hufValid = 1; f.ctl.hufLog = dict->hufLog; f.ctl.fseValid = 7;
+            f.ctl.tlog[0] = dict->tlog[0]; f.ctl.tlog[1] = dict->tlog[1]; f.ctl.tlog[2] = dict->tlog[2];
+            f.ctl.rep[0] = dict->rep[0]; f.ctl.rep[1] = dict->rep[1]; f.ctl.rep[2] = dict->rep[2];
+        }
+    }
+    __syncwarp(qmask);
+    if (dict && dict->hasEntropy) {
+        for (u32 i = q; i < 512; i += 4) { f.fseLL[i] = dict->fseLL[i]; f.fseML[i] = dict->fseML[i]; }
+        for (u32 i = q; i < 256; i += 4) f.fseOF[i] = dict->fseOF[i];
+        for (u32 i = q; i < 2048; i += 4) f.huf[i] = dict->huf[i];
+        __syncwarp(qmask);
+    }
+    // Lane 0 writes f.ctl between quad barriers; the other lanes snapshot what they need right after a
+    // barrier and a second barrier keeps lane 0 from overwriting it before everyone has read it.
+    for (;;) {
+        if (q == 0) zl_ent_block_head(f, d, info, hdrs, wbase, bias);
+        __syncwarp(qmask);
+        const u32 done = f.ctl.done, comp = f.ctl.isCompressed, fill = f.ctl.needHufFill, ns = f.ctl.nStreams;
+        __syncwarp(qmask);
+        if (done) break;
+        if (!comp) continue;
+        if (fill) { zl_huf_fill(f, q); __syncwarp(qmask); }
+        if (q < ns)
+            f.ctl.sErr[q] = zl_huf_stream(f.huf, f.ctl.hufLog, wbase, bias, f.ctl.sBeg[q], f.ctl.sEnd[q],
+                                          lits + f.ctl.sOut[q], f.ctl.sLen[q]);
+        __syncwarp(qmask);
+        if (q == 0) zl_ent_seq_head(f, d, ct);
+        __syncwarp(qmask);
+        const u32 build = f.ctl.err ? 0u : f.ctl.needBuild;
+        __syncwarp(qmask);
+        if (build) { if (q < 3) zl_ent_fse_build(f, q, ct); __syncwarp(qmask); }
+        if (q == 0) zl_ent_seq_decode(f, d, info, hdrs, recs, cks, wbase, bias, ct);
+    }
+}
+
+template <bool kDict>
+__global__ void __launch_bounds__(ZL_EXEC_WARPS * 32)
+zl_k_execute(const ZlFrameDesc* __restrict__ descs, const ZlFrameInfo* __restrict__ infos,
+             const ZlBlockHdr* __restrict__ hdrArena, const u64* __restrict__ recArena,
+             const u8* __restrict__ litArena, u64* __restrict__ results, u32 nframes, const ZlDictDev* dict)
+{
+    const u32 lane = threadIdx.x & 31;
+    const u32 frame = blockIdx.x * ZL_EXEC_WARPS + (threadIdx.x >> 5);
+    if (frame >= nframes) return;
+    const ZlFrameInfo info = infos[frame];
+    if (info.err) { if (lane == 0) results[frame] = (u64)0 - (u64)info.err; return; }
+    const ZlFrameDesc d = descs[frame];
+    const ZlBlockHdr* hdrs = hdrArena + d.hdrBase;
+    const u8* dictContent = kDict ? dict->content : nullptr;
+    const u32 dictSize = kDict ? dict->contentSize : 0u;
+    u32 op = 0;
+    for (u32 b = 0; b < info.nblocks; b++) {
+        const ZlBlockHdr h = hdrs[b];
+        const u32 type = h.flags & 3;
+        if (type == 0) zl_warp_copy(d.dst + op, d.src + h.srcOff, h.regenSize, lane);
+        else if (type == 1) zl_warp_fill(d.dst + op, (h.flags >> 8) & 0xFF, h.regenSize, lane);
+        else {
+            const u32 litMode = (h.flags >> 4) & 3;
+            const u8* lit = litMode == 0 ? d.src + h.srcOff : litArena + d.litBase + h.litOff;
+            zl_exec_block<kDict>(d.dst, op, h, lit, (h.flags >> 8) & 0xFF, litMode, recArena + d.recBase + h.recOff,
+                                 dictContent, dictSize, lane);
+        }
+        op += h.regenSize;
+        __syncwarp();
+    }
+    if (lane == 0) results[frame] = (u64)op;
+}
+
+__global__ void __launch_bounds__(128)
+zl_k_checksum(const ZlFrameDesc* __restrict__ descs, const ZlFrameInfo* __restrict__ infos, u64* __restrict__ results, u32 nframes)
+{
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 frame = t >> 2, q = t & 3, lane = threadIdx.x & 31;
+    const u32 qbase = lane & ~3u, qmask = 0xFu << qbase;
+    if (frame >= nframes) return;
+    const ZlFrameInfo info = infos[frame];
+    if (info.err || !info.checksumFlag) return;
+    const u64 h = zl_quad_xxh64(descs[frame].dst, info.totalOut, q, qmask, qbase);
+    if (q == 0 && (u32)h != info.checksum) results[frame] = (u64)0 - (u64)ZL_E_checksum_wrong;   // zstd.c:41650-41657
+}
+
+// generic XXH64 of independent buffers (used by the compressor for frame trailers)
+__global__ void __launch_bounds__(128)
+zl_k_xxh64(const u8* const* __restrict__ ptrs, const u32* __restrict__ sizes, u64* __restrict__ out, u32 n)
+{
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 i = t >> 2, q = t & 3, lane = threadIdx.x & 31;
+    const u32 qbase = lane & ~3u, qmask = 0xFu << qbase;
+    if (i >= n) return;
+    const u64 h = zl_quad_xxh64(ptrs[i], sizes[i], q, qmask, qbase);
+    if (q == 0) out[i] = h;
+}
+
+// ---- launchers ---------------------------------------------------------------------------------------
+size_t zl_entropy_smem_bytes() { return ZL_CT_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlFrameSm); }
+
+cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
+{
+    if (L.nframes == 0) return cudaSuccess;
+    static bool attrDone = false;
+    const size_t smem = zl_entropy_smem_bytes();
+    if (!attrDone) {
+        cudaError_t e = cudaFuncSetAttribute(zl_k_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attrDone = true;
+    }
+    const u32 g1 = (L.nframes + ZL_QUADS_PER_WARP - 1) / ZL_QUADS_PER_WARP;
+    zl_k_entropy<<<g1, 32, smem, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.ckArena, L.litArena, L.nframes, L.dict);
+    const u32 g2 = (L.nframes + ZL_EXEC_WARPS - 1) / ZL_EXEC_WARPS;
+    if (L.dict)
+        zl_k_execute<true><<<g2, ZL_EXEC_WARPS * 32, 0, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.results, L.nframes, L.dict);
+    else
+        zl_k_execute<false><<<g2, ZL_EXEC_WARPS * 32, 0, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.results, L.nframes, nullptr);
+    if (L.verifyChecksum) {
+        const u32 g3 = (L.nframes * 4 + 127) / 128;
+        zl_k_checksum<<<g3, 128, 0, st>>>(L.descs, L.infos, L.results, L.nframes);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t zl_launch_xxh64(const u8* const* ptrs, const u32* sizes, u64* out, u32 n, cudaStream_t st)
+{
+    if (!n) return cudaSuccess;
+    zl_k_xxh64<<<(n * 4 + 127) / 128, 128, 0, st>>>(ptrs, sizes, out, n);
+    return cudaGetLastError();
+}
