@@ -1,0 +1,30 @@
+"""ctypes access to the CPU emulation of the CUDA entropy kernels (tests/emul/, test infra only)."""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "emul", "libzl_emul.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        srcs = [os.path.join(_HERE, "emul", "emul_decode.cpp")]
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-Wno-unused-function", "-o", _SO] + srcs)
+        L = C.CDLL(_SO)
+        L.zl_emul_decompress_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint)]
+        L.zl_emul_decompress_frame.restype = C.c_size_t
+        _lib = L
+    return _lib
+
+
+def decompress_frame(c, cap):
+    """returns bytes, or ('ERR', code)"""
+    dst = C.create_string_buffer(cap + 8)
+    n = C.c_uint(0)
+    r = lib().zl_emul_decompress_frame(dst, cap, bytes(c), len(c), C.byref(n))
+    if r > 2**63:
+        return ("ERR", 2**64 - r)
+    return dst.raw[:r]

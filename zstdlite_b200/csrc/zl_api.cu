@@ -254,7 +254,7 @@ ZL_EXPORT size_t ZSTD_DCtx_loadDictionary(ZSTD_DCtx* c, const void* dict, size_t
     if (dictSize >= 8 && zl_rd32(d) == ZL_MAGIC_DICT) {
         static const ZlConstTables ct = {ZL_LL_BASE_INIT, ZL_ML_BASE_INIT, ZL_LL_BITS_INIT, ZL_ML_BITS_INIT, ZL_LL_DEFNORM_INIT, ZL_ML_DEFNORM_INIT, ZL_OF_DEFNORM_INIT};
         hd->dictID = zl_rd32(d + 4);
-        ZlFrameSm* f = new (std::nothrow) ZlFrameSm();
+        ZlLitSm* f = new (std::nothrow) ZlLitSm();
         if (!f) { delete hd; return ZL_ERROR(memory_allocation); }
         memset(f, 0, sizeof(*f));
         size_t p = 8; bool ok = true;
@@ -352,18 +352,18 @@ ZL_EXPORT size_t zl_decompress_batch(ZSTD_DCtx* c, const void* const* src, const
         lit += ((u64)d.litCap + 15) & ~15ull; rec += d.recCap; hdr += d.hdrCap; ck += d.ckCap;
     }
     if (!c->dDescs.reserve(n * sizeof(ZlFrameDesc)) || !c->dInfos.reserve(n * sizeof(ZlFrameInfo)) || !c->dResults.reserve(n * 8) ||
-        !c->dLit.reserve(lit + 64) || !c->dRec.reserve(rec * 8) || !c->dHdr.reserve(hdr * sizeof(ZlBlockHdr)) || !c->dCk.reserve(ck * 8))
+        !c->dLit.reserve(lit + 64) || !c->dRec.reserve(rec * 8) || !c->dHdr.reserve(hdr * sizeof(ZlBlockHdr)))
         return ZL_ERROR(memory_allocation);
     cudaMemcpyAsync(c->dDescs.p, hd, n * sizeof(ZlFrameDesc), cudaMemcpyHostToDevice, st);
     if (!dev) for (const ZlRun& r : sruns) if (r.bytes) cudaMemcpyAsync(c->dSrc.as<u8>() + r.devOff, r.hbase, r.bytes, cudaMemcpyHostToDevice, st);
     ZlDecodeLaunch L;
     L.descs = c->dDescs.as<ZlFrameDesc>(); L.infos = c->dInfos.as<ZlFrameInfo>(); L.hdrArena = c->dHdr.as<ZlBlockHdr>();
-    L.recArena = c->dRec.as<u64>(); L.ckArena = c->dCk.as<u64>(); L.litArena = c->dLit.as<u8>(); L.results = c->dResults.as<u64>();
+    L.recArena = c->dRec.as<u64>(); L.litArena = c->dLit.as<u8>(); L.results = c->dResults.as<u64>();
     L.nframes = (u32)n; L.verifyChecksum = !c->forceIgnoreChecksum; L.dict = c->hasDict ? c->dDict.as<ZlDictDev>() : nullptr;
     cudaEventRecord(c->ev0, st);
     cudaError_t e = zl_launch_decode(L, st);
     cudaEventRecord(c->ev1, st);
-    c->launches += 2 + (L.verifyChecksum ? 1 : 0);
+    c->launches += 3 + (L.verifyChecksum ? 1 : 0);
     if (e != cudaSuccess) { fprintf(stderr, "zstdlite_gpu: kernel launch failed: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
     cudaMemcpyAsync(c->hResults.p, c->dResults.p, n * 8, cudaMemcpyDeviceToHost, st);
     if (!dev) for (const ZlRun& r : druns) if (r.bytes) cudaMemcpyAsync((void*)r.hbase, c->dDst.as<u8>() + r.devOff, r.bytes, cudaMemcpyDeviceToHost, st);

@@ -1,14 +1,15 @@
-// zl_dec_entropy.cuh -- entropy stage of the B200 Zstandard decoder (kernel K1).
+// zl_dec_entropy.cuh -- entropy stage of the B200 Zstandard decoder: kernels K1a (literals) and K1b (sequences).
 //
-// Work unit: one FRAME per QUAD (4 lanes), 8 frames per warp.  Lane roles inside a quad:
-//   lane 0      parses frame/block/literal/sequence headers (tiny, serial), runs the serial
-//               3-state FSE sequence decode and writes sequence records
-//   lanes 0..3  fill the Huffman table cooperatively and decode the 4 Huffman streams
-//               (one stream per lane -- HUF_decompress4X, zstd.c:38653)
-//   lanes 0..2  build the LL / OF / ML FSE decode tables concurrently (zstd.c:43497)
-// All tables live in shared memory (ZlFrameSm, ~10 KB per frame).  Output goes to scratch
-// arenas in HBM: decoded literals, u64 sequence records (+ one checkpoint per 32 records)
-// and one ZlBlockHdr per block; the execute kernel (zl_dec_exec.cuh) consumes them.
+// Work unit for both kernels: one FRAME per QUAD (4 lanes), 8 frames per warp.
+//   K1a  lane 0 walks frame/block/literal headers and reads the Huffman tree description; lanes 0..3 fill
+//        the decode table cooperatively and decode the 4 Huffman streams, one stream per lane
+//        (HUF_decompress4X, zstd.c:38653).  Shared memory per frame: the 2^11 x u16 table (~5 KB).
+//   K1b  lane 0 parses the sequences header, lanes 0..2 build the LL / OF / ML FSE decode tables
+//        concurrently (zstd.c:43497), lane 0 runs the serial 3-state FSE decode (zstd.c:44241) and
+//        writes one u64 record per sequence.  Shared memory per frame: three packed u32 tables (~5.6 KB).
+// Splitting the two keeps the per-frame shared-memory footprint small, which is what bounds the number
+// of frames in flight per SM (the decode loops are dependent-latency chains).
+// Output goes to scratch arenas in HBM (literals, records, one ZlBlockHdr per block) consumed by K2.
 //
 // Reference behaviour restated here (file:line in /root/reference/src/zstd/zstd.c):
 //   frame header 41050-41152, block header 43075, literals section 43146-43347,
@@ -17,103 +18,95 @@
 #pragma once
 #include "zl_common.cuh"
 
-// ---- packed FSE decode cell: newStateBase[0:10) nbBits[10:14) nbAdditionalBits[14:19) symbol[19:25)
-ZL_HD u32 zl_fse_pack(u32 base, u32 nb, u32 add, u32 sym) { return base | (nb << 10) | (add << 14) | (sym << 19); }
-#define ZL_FSE_BASE(e) ((e) & 1023u)
-#define ZL_FSE_NB(e) (((e) >> 10) & 15u)
-#define ZL_FSE_ADD(e) (((e) >> 14) & 31u)
-#define ZL_FSE_SYM(e) (((e) >> 19) & 63u)
+// ---- packed FSE decode cell: nbBits[0:8) nbAdditionalBits[8:16) newStateBase[16:26) symbol[26:32)
+ZL_HD u32 zl_fse_pack(u32 base, u32 nb, u32 add, u32 sym) { return nb | (add << 8) | (base << 16) | (sym << 26); }
+#define ZL_FSE_NB(e) ((e) & 0xFFu)
+#define ZL_FSE_ADD(e) (((e) >> 8) & 0xFFu)
+#define ZL_FSE_BASE(e) (((e) >> 16) & 1023u)
+#define ZL_FSE_SYM(e) ((e) >> 26)
 
-struct ZlEntCtl {
-    u32 err;            // sticky ZlErr
-    u32 done;
-    u32 pos;            // byte offset of the next unread byte in the frame
-    u32 srcSize;
-    u32 outPos;         // bytes regenerated so far in this frame
-    u32 blockIdx;
-    u32 blockSizeMax;
-    u32 hufValid;
-    u32 fseValid;       // bit t: table t (0 LL, 1 OF, 2 ML) holds a usable table
-    u32 rep[3];
-    u32 recUsed, ckUsed, litUsed;
-    u32 dictSize;       // bytes of history available before the frame start
-    u64 contentSize;
-    u32 checksumFlag;
-    // block level
-    u32 isCompressed, last, blockEnd;
-    u32 litMode, litSize, litOff, litSrcOff, rleByte;
-    u32 needHufFill, hufLog, nsym;
-    u32 nStreams;
-    u32 sBeg[4], sEnd[4], sOut[4], sLen[4], sErr[4];
-    u32 nbSeq;
-    u32 needBuild;      // bit t: build table t from norm[t]
-    u32 tlog[3], maxSym[3];
-    u32 bitBeg;
-};
-
-struct ZlFrameSm {
-    u32 fseLL[512];
-    u32 fseML[512];
-    u32 fseOF[256];
-    u16 huf[2048];
-    ZlEntCtl ctl;
-    i16 norm[3][64];
-    u8 weights[256];
-    union {
-        u16 symStart[256];
-        u32 wtbl[64];
-    } u;
-};
-
-// ---- backward bit reader over aligned 32-bit words (restates BIT_DStream_t, zstd.c:2352-2550) -------
-// `wbase` is the frame's src pointer rounded down to 4 bytes, `bias` = src - wbase (0..3); stream
-// positions are byte offsets relative to src.  Bits are consumed from the MSB side of `acc`.
+// ---- backward bit reader (restates BIT_DStream_t, zstd.c:2352-2550) ---------------------------------------
+// `wbase` is the frame's src pointer rounded down to 4 bytes, `bias` = src - wbase (0..3); stream positions
+// are byte offsets relative to src.  (hi:lo) is a 64-bit window, next bit to consume = MSB of hi; `n` valid
+// bits.  Refills are whole aligned 32-bit words.  Latency hiding: the word for the NEXT refill is already in
+// a register (`nextw`, loaded one refill earlier), and its load hits L1 because the 32-byte sector two sectors
+// further down the stream is requested with a prefetch each time the reader enters a new sector.
 struct ZlBitR {
-    u64 acc;
-    i32 avail;
-    i32 wi;      // next (lower) word to load
+    u32 hi, lo;
+    i32 n;
+    u32 nextw;
+    i32 wi;      // index of the word after `nextw` (next one to load)
     i32 wlow;    // word holding the first byte of the stream
 };
-
+ZL_HD u32 zl_ld_word(const u32* p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+ZL_HD void zl_prefetch(const u32* p)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+// Loads word `wi` (clamped to the stream: below the start the value is irrelevant, over-reading is detected by
+// zl_br_remaining) without touching the loaded value, so the load stays in flight until the next refill.
+ZL_HD u32 zl_br_fetch(ZlBitR& b, const u32* wbase)
+{
+    const i32 i = b.wi < b.wlow ? b.wlow : b.wi;
+    if ((b.wi & 7) == 7) { const i32 pf = b.wi - 16; zl_prefetch(wbase + (pf < b.wlow ? b.wlow : pf)); }
+    b.wi--;
+    return zl_ld_word(wbase + i);
+}
 ZL_HD bool zl_br_init(ZlBitR& b, const u32* wbase, u32 bias, u32 beg, u32 end)
 {
     if (end <= beg) return false;
-    u32 a = end - 1 + bias;
-    u32 W = wbase[a >> 2];
-    u32 bsel = a & 3;
-    u32 L = (W >> (8 * bsel)) & 0xFF;
-    if (!L) return false;                      // zstd.c:2369 endMark missing
-    u32 hb = zl_highbit(L);
-    u32 sh = 32 + 8 * (3 - bsel) + (8 - hb);   // drop bytes above the stream, padding and end mark
-    b.acc = sh >= 64 ? 0 : ((u64)W << sh);
-    b.avail = (i32)(8 * bsel + hb);
+    const u32 a = end - 1 + bias;
+    const u32 W = zl_ld_word(wbase + (a >> 2));
+    const u32 bsel = a & 3;
+    const u32 L = (W >> (8 * bsel)) & 0xFF;
+    if (!L) return false;                              // zstd.c:2369 end mark missing
+    const u32 hb = zl_highbit(L);
+    b.hi = zl_shl(W, 8 * (3 - bsel) + (8 - hb));       // drop bytes above the stream, the padding and the end mark
+    b.lo = 0;
+    b.n = (i32)(8 * bsel + hb);
     b.wi = (i32)(a >> 2) - 1;
     b.wlow = (i32)((beg + bias) >> 2);
+    {   const i32 p1 = b.wi - 8, p2 = b.wi - 16;
+        zl_prefetch(wbase + (p1 < b.wlow ? b.wlow : p1)); zl_prefetch(wbase + (p2 < b.wlow ? b.wlow : p2)); }
+    b.nextw = zl_br_fetch(b, wbase);
     return true;
 }
-ZL_HD void zl_br_refill(ZlBitR& b, const u32* wbase)
+ZL_HD void zl_br_refill(ZlBitR& b, const u32* wbase)       // afterwards n >= 33
 {
-    if (b.avail <= 32) {
-        u32 w = (b.wi >= b.wlow) ? wbase[b.wi] : 0u;
-        b.wi--;
-        b.acc |= (u64)w << (32 - b.avail);
-        b.avail += 32;
+    if (b.n <= 32) {
+        const u32 w = b.nextw;
+        b.nextw = zl_br_fetch(b, wbase);
+        b.hi |= zl_shr(w, (u32)b.n);
+        b.lo = zl_shl(w, 32u - (u32)b.n);
+        b.n += 32;
     }
 }
-ZL_HD u32 zl_br_take(ZlBitR& b, u32 n)         // n <= 32, n may be 0
+ZL_HD u32 zl_br_peek(const ZlBitR& b, u32 k) { return zl_shr(b.hi, 32u - k); }       // k <= 32; 0 when k == 0
+ZL_HD void zl_br_skip(ZlBitR& b, u32 k)                                               // k <= 32
 {
-    u32 v = (u32)((b.acc >> 1) >> (63 - n));
-    b.acc <<= n;
-    b.avail -= (i32)n;
-    return v;
+    b.hi = zl_fsl(b.lo, b.hi, k);
+    b.lo = zl_shl(b.lo, k);
+    b.n -= (i32)k;
 }
+ZL_HD u32 zl_br_take(ZlBitR& b, u32 k) { const u32 v = zl_br_peek(b, k); zl_br_skip(b, k); return v; }
 // bits of the stream not consumed yet; negative when the reader ran past the start
 ZL_HD i32 zl_br_remaining(const ZlBitR& b, u32 bias, u32 beg)
 {
-    return b.avail + 8 * (4 * (b.wi + 1) - (i32)(beg + bias));
+    return b.n + 8 * (4 * (b.wi + 2) - (i32)(beg + bias));     // `nextw` (word wi+1) is loaded but not in (hi:lo) yet
 }
 
-// ---- FSE normalized-count header (forward, LSB first): zstd.c:3269-3409 ----------------------------
+// ---- FSE normalized-count header (forward, LSB first): zstd.c:3269-3409 ------------------------------------
 // Returns bytes consumed, or 0 on error.
 ZL_HD u32 zl_read_ncount(const u8* src, u32 srcSize, i16* norm, u32* maxSymIO, u32* tableLog)
 {
@@ -174,7 +167,7 @@ ZL_HD u32 zl_read_ncount(const u8* src, u32 srcSize, i16* norm, u32* maxSymIO, u
     return used;
 }
 
-// ---- FSE decode table build (one lane per table): zstd.c:43497-43613 -----------------------------------
+// ---- FSE decode table build (one lane per table): zstd.c:43497-43613 ------------------------------------------
 // kind 0 LL, 1 OF, 2 ML decides the additional-bits field.  `tbl` first receives symbols, then cells.
 ZL_HD bool zl_fse_build(u32* tbl, const i16* norm, u32 maxSym, u32 log, u32 kind, const ZlConstTables& ct)
 {
@@ -204,16 +197,35 @@ ZL_HD bool zl_fse_build(u32* tbl, const i16* norm, u32 maxSym, u32 log, u32 kind
     return true;
 }
 
-// ---- frame header (lane 0): zstd.c:41050-41152 --------------------------------------------------------
-ZL_HD void zl_ent_begin_frame(ZlFrameSm& f, const ZlFrameDesc& d, ZlFrameInfo& info, u32 dictSize, u32 dictID)
+// =================================================================================================== K1a: literals
+struct ZlLitCtl {
+    u32 err, done;
+    u32 pos, srcSize;
+    u32 blockIdx, blockSizeMax;
+    u32 hufValid, hufLog, nsym;
+    u32 litUsed;
+    u32 needHufFill, nStreams;
+    u32 sBeg[4], sEnd[4], sOut[4], sLen[4], sErr[4];
+};
+struct ZlLitSm {
+    u16 huf[2048];
+    u8 weights[256];
+    union {
+        u16 symStart[256];
+        u32 wtbl[64];
+    } u;
+    ZlLitCtl ctl;
+};
+
+// frame header (lane 0): zstd.c:41050-41152
+ZL_HD void zl_lit_begin_frame(ZlLitSm& f, const ZlFrameDesc& d, ZlFrameInfo& info, u32 dictID)
 {
-    ZlEntCtl& c = f.ctl;
-    c.err = 0; c.done = 0; c.pos = 0; c.srcSize = d.srcSize; c.outPos = 0; c.blockIdx = 0;
-    c.hufValid = 0; c.fseValid = 0; c.rep[0] = 1; c.rep[1] = 4; c.rep[2] = 8;     // zstd.c:15416
-    c.recUsed = 0; c.ckUsed = 0; c.litUsed = 0; c.dictSize = dictSize;
-    c.contentSize = ~0ull; c.checksumFlag = 0; c.isCompressed = 0; c.blockSizeMax = ZL_BLOCKSIZE_MAX;
+    ZlLitCtl& c = f.ctl;
+    c.err = 0; c.done = 0; c.pos = 0; c.srcSize = d.srcSize; c.blockIdx = 0;
+    c.hufValid = 0; c.hufLog = 0; c.litUsed = 0; c.blockSizeMax = ZL_BLOCKSIZE_MAX;
+    c.needHufFill = 0; c.nStreams = 0;
     info.err = 0; info.nblocks = 0; info.contentSize = ~0ull; info.totalOut = 0;
-    info.checksumFlag = 0; info.checksum = 0; info.dictID = 0;
+    info.checksumFlag = 0; info.checksum = 0; info.dictID = 0; info.blockSizeMax = ZL_BLOCKSIZE_MAX; info.pad = 0;
     const u8* ip = d.src;
     if (d.srcSize < 5) { c.err = ZL_E_srcSize_wrong; return; }
     if (zl_rd32(ip) != ZL_MAGIC) { c.err = ZL_E_prefix_unknown; return; }
@@ -243,29 +255,27 @@ ZL_HD void zl_ent_begin_frame(ZlFrameSm& f, const ZlFrameDesc& d, ZlFrameInfo& i
     if (single) window = fcs;
     if (did != 0 && did != dictID) { c.err = ZL_E_dictionary_wrong; return; }     // zstd.c:41318
     c.blockSizeMax = window < ZL_BLOCKSIZE_MAX ? (u32)window : ZL_BLOCKSIZE_MAX;
-    c.contentSize = fcs; c.checksumFlag = (fhd >> 2) & 1;
     c.pos = hs;
-    info.contentSize = fcs; info.checksumFlag = c.checksumFlag; info.dictID = did;
+    info.contentSize = fcs; info.checksumFlag = (fhd >> 2) & 1; info.dictID = did; info.blockSizeMax = c.blockSizeMax;
 }
 
-ZL_HD void zl_ent_finish_frame(ZlFrameSm& f, const ZlFrameDesc& d, ZlFrameInfo& info)
+ZL_HD void zl_lit_finish_frame(ZlLitSm& f, const ZlFrameDesc& d, ZlFrameInfo& info)
 {
-    ZlEntCtl& c = f.ctl;
+    ZlLitCtl& c = f.ctl;
     c.done = 1;
     if (!c.err) {
-        if (c.contentSize != ~0ull && c.contentSize != (u64)c.outPos) c.err = ZL_E_corruption_detected;   // zstd.c:41646
-        else if (c.checksumFlag) {
+        if (info.checksumFlag) {
             if (c.pos + 4 > c.srcSize) c.err = ZL_E_checksum_wrong;                                          // zstd.c:41651
             else { info.checksum = zl_rd32(d.src + c.pos); c.pos += 4; }
         }
         if (!c.err && c.pos != c.srcSize) c.err = ZL_E_srcSize_wrong;       // one frame per batch item
     }
-    info.err = c.err; info.nblocks = c.blockIdx; info.totalOut = c.outPos;
+    info.err = c.err; info.nblocks = c.blockIdx;
 }
 
-// ---- Huffman tree description (lane 0): zstd.c:3470-3540, weights via FSE 3875/3790 ----------------------
+// Huffman tree description (lane 0): zstd.c:3470-3540, weights via FSE 3875/3790.
 // Fills f.weights / f.u.symStart, ctl.hufLog, ctl.nsym.  Returns bytes consumed or 0 on error.
-ZL_HD u32 zl_huf_read_stats(ZlFrameSm& f, const u8* src, u32 srcSize, const u32* wbase, u32 bias, u32 srcOff)
+ZL_HD u32 zl_huf_read_stats(ZlLitSm& f, const u8* src, u32 srcSize, const u32* wbase, u32 bias, u32 srcOff)
 {
     if (!srcSize) return 0;
     u32 hdr = src[0], nsym = 0, iSize;
@@ -327,7 +337,7 @@ ZL_HD u32 zl_huf_read_stats(ZlFrameSm& f, const u8* src, u32 srcSize, const u32*
 }
 
 // cooperative table fill, lane q of 4: zstd.c:38506-38568 (cell = nbBits<<8 | symbol)
-ZL_HD void zl_huf_fill(ZlFrameSm& f, u32 q)
+ZL_HD void zl_huf_fill(ZlLitSm& f, u32 q)
 {
     u32 tlog = f.ctl.hufLog, nsym = f.ctl.nsym;
     for (u32 n = q; n < nsym; n += 4) {
@@ -339,15 +349,61 @@ ZL_HD void zl_huf_fill(ZlFrameSm& f, u32 q)
     }
 }
 
+#if defined(__CUDACC__)
+// ---- device-only fast paths: branch-free refills (predicated PTX loads write straight into the look-ahead register,
+// so the load stays in flight until the next refill), shared-space table loads, rotated loops. ------------------------
+__device__ __forceinline__ u32 zl_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u32 zl_lds32(u32 a) { u32 v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ u32 zl_lds16(u32 a) { u32 v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+// if (n <= 32) { window |= nextw << (32 - n); nextw = *next word*; n += 32; }   -- no branch
+#define ZL_REFILL_DEV()                                                                                        \
+    {                                                                                                          \
+        const u32 need_ = (n <= 32) ? 1u : 0u;                                                                 \
+        const u32 w_ = nextw;                                                                                  \
+        const i32 i_ = wi < wlow ? wlow : wi;                                                                  \
+        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}"               \
+            : "+r"(nextw) : "l"(wbase + i_), "r"(need_));                                                      \
+        if (need_ && (wi & 7) == 7) { const i32 pf_ = wi - 16; zl_prefetch(wbase + (pf_ < wlow ? wlow : pf_)); } \
+        hi |= need_ ? zl_shr(w_, (u32)n) : 0u;                                                                 \
+        lo = need_ ? zl_shl(w_, 32u - (u32)n) : lo;                                                            \
+        n += need_ ? 32 : 0;                                                                                   \
+        wi -= (i32)need_;                                                                                      \
+    }
+#endif
+
 // one Huffman stream per lane: zstd.c:38626-38650.  Returns 0 when the stream ends exactly.
 ZL_HD u32 zl_huf_stream(const u16* huf, u32 tlog, const u32* wbase, u32 bias, u32 beg, u32 end, u8* out, u32 n)
 {
     ZlBitR b;
     if (!zl_br_init(b, wbase, bias, beg, end)) return 1;
-    const u32 sh = 64 - tlog;
+    const u32 sh = 32 - tlog;
     u32 i = 0;
-#define ZL_HUF_SYM(dst) { u32 e = huf[b.acc >> sh]; u32 nb = e >> 8; b.acc <<= nb; b.avail -= (i32)nb; dst = e & 0xFF; }
+#define ZL_HUF_SYM(dst) { const u32 e = huf[b.hi >> sh]; zl_br_skip(b, e >> 8); dst = e & 0xFF; }
     while (i < n && (((size_t)(out + i)) & 3)) { u32 s; zl_br_refill(b, wbase); ZL_HUF_SYM(s); out[i++] = (u8)s; }
+#if defined(__CUDA_ARCH__)
+    {
+        const u32 count = n;                       // `n` below is the window's valid-bit count (macro convention)
+        u32 hi = b.hi, lo = b.lo, nextw = b.nextw;
+        i32 wi = b.wi;
+        const i32 wlow = b.wlow;
+        const u32 th = zl_smem_addr(huf);
+        {
+            i32 n = b.n;
+#define ZL_HUF_SYM_DEV(dst) { const u32 e = zl_lds16(th + ((hi >> sh) << 1)); const u32 nb = e >> 8; \
+                              hi = zl_fsl(lo, hi, nb); lo <<= nb; n -= (i32)nb; dst = e & 0xFF; }
+            while (i + 4 <= count) {
+                u32 s0, s1, s2, s3;
+                ZL_REFILL_DEV(); ZL_HUF_SYM_DEV(s0); ZL_HUF_SYM_DEV(s1);
+                ZL_REFILL_DEV(); ZL_HUF_SYM_DEV(s2); ZL_HUF_SYM_DEV(s3);
+                *(u32*)(out + i) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+                i += 4;
+            }
+#undef ZL_HUF_SYM_DEV
+            b.n = n;
+        }
+        b.hi = hi; b.lo = lo; b.nextw = nextw; b.wi = wi;
+    }
+#else
     while (i + 4 <= n) {
         u32 s0, s1, s2, s3;
         zl_br_refill(b, wbase); ZL_HUF_SYM(s0); ZL_HUF_SYM(s1);
@@ -355,46 +411,46 @@ ZL_HD u32 zl_huf_stream(const u16* huf, u32 tlog, const u32* wbase, u32 bias, u3
         *(u32*)(out + i) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
         i += 4;
     }
+#endif
     while (i < n) { u32 s; zl_br_refill(b, wbase); ZL_HUF_SYM(s); out[i++] = (u8)s; }
 #undef ZL_HUF_SYM
     return zl_br_remaining(b, bias, beg) == 0 ? 0u : 1u;
 }
 
-// ---- block header + literals section header (lane 0) --------------------------------------------------
-ZL_HD void zl_ent_block_head(ZlFrameSm& f, const ZlFrameDesc& d, ZlFrameInfo& info, ZlBlockHdr* hdrs,
+// block header + literals section header (lane 0).  Writes the literal part of the block's ZlBlockHdr.
+ZL_HD void zl_lit_block_head(ZlLitSm& f, const ZlFrameDesc& d, ZlFrameInfo& info, ZlBlockHdr* hdrs,
                              const u32* wbase, u32 bias)
 {
-    ZlEntCtl& c = f.ctl;
+    ZlLitCtl& c = f.ctl;
     if (c.done) return;
-    c.isCompressed = 0; c.needHufFill = 0; c.nStreams = 0;
-    if (c.err) { zl_ent_finish_frame(f, d, info); return; }
+    for (u32 k = 0; k < c.nStreams; k++) if (c.sErr[k]) c.err = ZL_E_corruption_detected;     // streams of the previous block
+    c.needHufFill = 0; c.nStreams = 0;
+    if (c.err) { zl_lit_finish_frame(f, d, info); return; }
+    if (c.blockIdx > 0 && (hdrs[c.blockIdx - 1].flags & 4)) { zl_lit_finish_frame(f, d, info); return; }   // previous block was the last
     const u8* src = d.src;
-    if (c.pos + 3 > c.srcSize) { c.err = ZL_E_srcSize_wrong; zl_ent_finish_frame(f, d, info); return; }
+    if (c.pos + 3 > c.srcSize) { c.err = ZL_E_srcSize_wrong; zl_lit_finish_frame(f, d, info); return; }
     u32 bh = zl_rd24(src + c.pos);
     u32 last = bh & 1, type = (bh >> 1) & 3, csize = bh >> 3;
-    c.pos += 3; c.last = last;
-    if (c.blockIdx >= d.hdrCap) { c.err = ZL_E_GENERIC; zl_ent_finish_frame(f, d, info); return; }
+    c.pos += 3;
+    if (c.blockIdx >= d.hdrCap) { c.err = ZL_E_GENERIC; zl_lit_finish_frame(f, d, info); return; }
     ZlBlockHdr h;
-    h.flags = 0; h.regenSize = 0; h.srcOff = 0; h.litOff = 0; h.litSize = 0; h.nrec = 0; h.recOff = c.recUsed; h.ckOff = c.ckUsed;
+    h.flags = last ? 4u : 0u; h.regenSize = 0; h.srcOff = 0; h.litOff = 0; h.litSize = 0; h.nrec = 0; h.recOff = 0;
+    h.seqOff = 0; h.seqEnd = 0; h.pad[0] = h.pad[1] = h.pad[2] = 0;
     if (type == 3) c.err = ZL_E_corruption_detected;
     else if (type == 1) {                                                    // RLE block, zstd.c:41510
         if (c.pos + 1 > c.srcSize) c.err = ZL_E_srcSize_wrong;
-        else if (csize > d.dstCap - c.outPos) c.err = ZL_E_dstSize_tooSmall;
-        else { h.flags = 1u | ((u32)src[c.pos] << 8); h.regenSize = csize; c.pos += 1; }
+        else { h.flags |= 1u | ((u32)src[c.pos] << 8); h.regenSize = csize; c.pos += 1; }
     } else if (type == 0) {                                                  // raw block, zstd.c:41497
         if (csize > c.srcSize - c.pos) c.err = ZL_E_srcSize_wrong;
-        else if (csize > d.dstCap - c.outPos) c.err = ZL_E_dstSize_tooSmall;
-        else { h.flags = 0; h.regenSize = csize; h.srcOff = c.pos; c.pos += csize; }
+        else { h.regenSize = csize; h.srcOff = c.pos; c.pos += csize; }
     } else {
         if (csize > c.srcSize - c.pos) c.err = ZL_E_srcSize_wrong;
         else if (csize > c.blockSizeMax) c.err = ZL_E_srcSize_wrong;         // zstd.c:45099
         else if (csize < 2) c.err = ZL_E_corruption_detected;                // MIN_CBLOCK_SIZE, zstd.c:43150
         else {
-            c.isCompressed = 1; c.blockEnd = c.pos + csize;
+            const u32 blockEnd = c.pos + csize;
             const u8* ip = src + c.pos;
-            u32 ltype = ip[0] & 3, fmt = (ip[0] >> 2) & 3, lhSize, litSize, litCSize = 0;
-            u32 outCap = d.dstCap - c.outPos;
-            u32 litCap = outCap < c.blockSizeMax ? outCap : c.blockSizeMax;
+            u32 ltype = ip[0] & 3, fmt = (ip[0] >> 2) & 3, lhSize = 0, litSize = 0, litCSize = 0, litMode = 0;
             if (ltype >= 2) {
                 u32 single = 0;
                 if (ltype == 3 && !c.hufValid) c.err = ZL_E_dictionary_corrupted;      // zstd.c:43160
@@ -407,9 +463,8 @@ ZL_HD void zl_ent_block_head(ZlFrameSm& f, const ZlFrameDesc& d, ZlFrameInfo& in
                     if (litSize > c.blockSizeMax) c.err = ZL_E_corruption_detected;
                     else if (!single && litSize < 6) c.err = ZL_E_literals_headerWrong;
                     else if (litCSize + lhSize > csize) c.err = ZL_E_corruption_detected;
-                    else if (litCap < litSize) c.err = ZL_E_dstSize_tooSmall;
                     else if (litSize == 0 || litCSize == 0) c.err = ZL_E_corruption_detected;
-                    else if (c.litUsed + litSize > d.litCap) c.err = ZL_E_GENERIC;
+                    else if (c.litUsed + litSize > d.litCap) c.err = ZL_E_dstSize_tooSmall;   // more literals than dst can hold
                     else {
                         u32 hs = c.pos + lhSize, hsz = litCSize;
                         if (ltype == 2) {
@@ -418,9 +473,9 @@ ZL_HD void zl_ent_block_head(ZlFrameSm& f, const ZlFrameDesc& d, ZlFrameInfo& in
                             else { hs += th; hsz -= th; c.needHufFill = 1; c.hufValid = 1; }
                         }
                         if (!c.err) {
-                            c.litMode = 2; c.litSize = litSize; c.litOff = c.litUsed; c.litUsed += litSize;
+                            litMode = 2; h.litOff = c.litUsed; c.litUsed += litSize;
                             if (single) {
-                                c.nStreams = 1; c.sBeg[0] = hs; c.sEnd[0] = hs + hsz; c.sOut[0] = c.litOff; c.sLen[0] = litSize;
+                                c.nStreams = 1; c.sBeg[0] = hs; c.sEnd[0] = hs + hsz; c.sOut[0] = h.litOff; c.sLen[0] = litSize;
                             } else if (hsz < 10) c.err = ZL_E_corruption_detected;          // zstd.c:38659
                             else {
                                 u32 l1 = zl_rd16(src + hs), l2 = zl_rd16(src + hs + 2), l3 = zl_rd16(src + hs + 4);
@@ -432,11 +487,11 @@ ZL_HD void zl_ent_block_head(ZlFrameSm& f, const ZlFrameDesc& d, ZlFrameInfo& in
                                     c.sBeg[1] = c.sEnd[0]; c.sEnd[1] = c.sBeg[1] + l2;
                                     c.sBeg[2] = c.sEnd[1]; c.sEnd[2] = c.sBeg[2] + l3;
                                     c.sBeg[3] = c.sEnd[2]; c.sEnd[3] = hs + hsz;
-                                    for (u32 k = 0; k < 4; k++) { c.sOut[k] = c.litOff + k * seg; c.sLen[k] = seg; }
+                                    for (u32 k = 0; k < 4; k++) { c.sOut[k] = h.litOff + k * seg; c.sLen[k] = seg; }
                                     c.sLen[3] = litSize - 3 * seg;
                                 }
                             }
-                            c.pos += lhSize + litCSize;
+                            h.seqOff = c.pos + lhSize + litCSize;
                         }
                     }
                 }
@@ -447,34 +502,53 @@ ZL_HD void zl_ent_block_head(ZlFrameSm& f, const ZlFrameDesc& d, ZlFrameInfo& in
                 else { lhSize = 3; if (csize < 3) { ok = false; litSize = 0; } else litSize = zl_rd24(ip) >> 4; }
                 if (!ok) c.err = ZL_E_corruption_detected;
                 else if (litSize > c.blockSizeMax) c.err = ZL_E_corruption_detected;
-                else if (litCap < litSize) c.err = ZL_E_dstSize_tooSmall;
                 else if (ltype == 0) {
                     if (lhSize + litSize > csize) c.err = ZL_E_corruption_detected;
-                    else { c.litMode = 0; c.litSize = litSize; c.litSrcOff = c.pos + lhSize; c.pos += lhSize + litSize; }
+                    else { litMode = 0; h.srcOff = c.pos + lhSize; h.seqOff = c.pos + lhSize + litSize; }
                 } else {
                     if (lhSize + 1 > csize) c.err = ZL_E_corruption_detected;
-                    else { c.litMode = 1; c.litSize = litSize; c.rleByte = ip[lhSize]; c.pos += lhSize + 1; }
+                    else { litMode = 1; h.flags |= (u32)ip[lhSize] << 8; h.seqOff = c.pos + lhSize + 1; }
                 }
             }
+            h.flags |= 2u | (litMode << 4);
+            h.litSize = litSize; h.seqEnd = blockEnd;
+            c.pos = blockEnd;
         }
     }
-    if (c.err) { c.isCompressed = 0; zl_ent_finish_frame(f, d, info); return; }
-    if (!c.isCompressed) {
-        hdrs[c.blockIdx] = h;
-        c.outPos += h.regenSize; c.blockIdx++;
-        if (last) zl_ent_finish_frame(f, d, info);
-    }
+    if (c.err) { c.nStreams = 0; c.needHufFill = 0; zl_lit_finish_frame(f, d, info); return; }
+    hdrs[c.blockIdx] = h;
+    c.blockIdx++;
 }
 
-// ---- sequences section header (lane 0): zstd.c:43707-43790 ------------------------------------------------
-ZL_HD void zl_ent_seq_head(ZlFrameSm& f, const ZlFrameDesc& d, const ZlConstTables& ct)
+// =================================================================================================== K1b: sequences
+struct ZlSeqCtl {
+    u32 err;
+    u32 outPos;         // bytes regenerated so far in this frame
+    u32 fseValid;
+    u32 rep[3];
+    u32 recUsed;
+    u32 dictSize;       // bytes of history available before the frame start
+    u32 nbSeq;
+    u32 needBuild;      // bit t: build table t (0 LL, 1 OF, 2 ML) from norm[t]
+    u32 tlog[3], maxSym[3], bErr[3];
+    u32 bitBeg, bitEnd;
+};
+struct ZlSeqSm {
+    u32 fseLL[512];
+    u32 fseML[512];
+    u32 fseOF[256];
+    i16 norm[3][64];
+    ZlSeqCtl ctl;
+};
+
+// sequences section header (lane 0): zstd.c:43707-43790
+ZL_HD void zl_seq_head(ZlSeqSm& f, const ZlFrameDesc& d, const ZlBlockHdr& h, const ZlConstTables& ct)
 {
-    ZlEntCtl& c = f.ctl;
+    ZlSeqCtl& c = f.ctl;
     c.needBuild = 0; c.nbSeq = 0;
-    for (u32 k = 0; k < c.nStreams; k++) if (c.sErr[k]) c.err = ZL_E_corruption_detected;
     if (c.err) return;
     const u8* src = d.src;
-    u32 ip = c.pos, iend = c.blockEnd;
+    u32 ip = h.seqOff, iend = h.seqEnd;
     if (ip >= iend) { c.err = ZL_E_srcSize_wrong; return; }
     u32 nbSeq = src[ip++];
     if (nbSeq > 0x7F) {
@@ -482,7 +556,7 @@ ZL_HD void zl_ent_seq_head(ZlFrameSm& f, const ZlFrameDesc& d, const ZlConstTabl
         else { if (ip >= iend) { c.err = ZL_E_srcSize_wrong; return; } nbSeq = ((nbSeq - 0x80) << 8) + src[ip++]; }
     }
     c.nbSeq = nbSeq;
-    if (nbSeq == 0) { if (ip != iend) c.err = ZL_E_corruption_detected; c.pos = ip; return; }
+    if (nbSeq == 0) { if (ip != iend) c.err = ZL_E_corruption_detected; return; }
     if (ip + 1 > iend) { c.err = ZL_E_srcSize_wrong; return; }
     u32 modes = src[ip++];
     if (modes & 3) { c.err = ZL_E_corruption_detected; return; }
@@ -503,124 +577,236 @@ ZL_HD void zl_ent_seq_head(ZlFrameSm& f, const ZlFrameDesc& d, const ZlConstTabl
             tbl[0] = zl_fse_pack(0, 0, add, s); c.tlog[t] = 0;
         } else if (mode == 2) {                        // FSE-compressed
             u32 ms = maxSymT[t], tl;
-            u32 h = zl_read_ncount(src + ip, iend - ip, f.norm[t], &ms, &tl);
-            if (!h || tl > maxLogT[t]) { c.err = ZL_E_corruption_detected; return; }
-            ip += h; c.maxSym[t] = ms; c.tlog[t] = tl; c.needBuild |= 1u << t;
+            u32 hsz = zl_read_ncount(src + ip, iend - ip, f.norm[t], &ms, &tl);
+            if (!hsz || tl > maxLogT[t]) { c.err = ZL_E_corruption_detected; return; }
+            ip += hsz; c.maxSym[t] = ms; c.tlog[t] = tl; c.needBuild |= 1u << t;
         } else {                                       // repeat
             if (!((c.fseValid >> t) & 1)) { c.err = ZL_E_corruption_detected; return; }
         }
         c.fseValid |= 1u << t;
     }
-    c.bitBeg = ip; c.pos = ip;
+    c.bitBeg = ip; c.bitEnd = iend;
 }
 
-ZL_HD void zl_ent_fse_build(ZlFrameSm& f, u32 t, const ZlConstTables& ct)
+ZL_HD void zl_seq_fse_build(ZlSeqSm& f, u32 t, const ZlConstTables& ct)
 {
-    ZlEntCtl& c = f.ctl;
+    ZlSeqCtl& c = f.ctl;
+    c.bErr[t] = 0;
     if (!((c.needBuild >> t) & 1)) return;
     u32* tbl = t == 0 ? f.fseLL : (t == 1 ? f.fseOF : f.fseML);
-    if (!zl_fse_build(tbl, f.norm[t], c.maxSym[t], c.tlog[t], t, ct)) c.sErr[t] = 1; else c.sErr[t] = 0;
+    if (!zl_fse_build(tbl, f.norm[t], c.maxSym[t], c.tlog[t], t, ct)) c.bErr[t] = 1;
 }
 
-// ---- serial sequence decode (lane 0): zstd.c:44241-44358 + 44627-44700 -------------------------------------
-ZL_HD void zl_ent_seq_decode(ZlFrameSm& f, const ZlFrameDesc& d, ZlFrameInfo& info, ZlBlockHdr* hdrs, u64* recs, u64* cks,
-                             const u32* wbase, u32 bias, const ZlConstTables& ct)
+// One sequence (zstd.c:44241-44358).  Bit order in the stream: OF, ML, LL additional bits, then the LL, ML, OF
+// state transitions (skipped for the last sequence).  Both groups are extracted from a snapshot of the 64-bit
+// window at positions that are prefix sums of the table cells' bit counts, so the reads are independent of each
+// other and only the state -> cell -> state chain is serial.
+struct ZlSeqRegs {
+    u32 sLL, sOF, sML;
+    u32 rep0, rep1, rep2;
+    u32 outPos, litPos, nrec, err;
+};
+template <bool kLast>
+ZL_HD void zl_seq_step(const ZlSeqSm& f, ZlBitR& b, const u32* wbase, const ZlConstTables& ct, ZlSeqRegs& r,
+                       u64* rp, u32 recCap, u32 litSize, u32 outCap, u32 capErr, u32 hist)
 {
-    ZlEntCtl& c = f.ctl;
-    if (!c.err && c.needBuild) { for (u32 t = 0; t < 3; t++) if (((c.needBuild >> t) & 1) && c.sErr[t]) c.err = ZL_E_corruption_detected; }
-    u32 nrec = 0, outPos = 0, litPos = 0;
-    const u32 litSize = c.litSize;
-    u32 outCap = d.dstCap - c.outPos;
-    bool capIsDst = true;
-    if (outCap > ZL_BLOCKSIZE_MAX) { outCap = ZL_BLOCKSIZE_MAX; capIsDst = false; }
+    zl_br_refill(b, wbase);                                              // n >= 33
+    const u32 eLL = f.fseLL[r.sLL], eOF = f.fseOF[r.sOF], eML = f.fseML[r.sML];
+    const u32 aOF = ZL_FSE_ADD(eOF), aML = ZL_FSE_ADD(eML), aLL = ZL_FSE_ADD(eLL);
+    const u32 cA = aOF + aML + aLL;
+    u32 ofx, mlx, llx;
+    if (cA <= 32) {
+        const u32 hi = b.hi, lo = b.lo;
+        ofx = zl_shr(hi, 32u - aOF);
+        mlx = zl_shr(zl_fsl(lo, hi, aOF), 32u - aML);
+        llx = zl_shr(zl_fsl(lo, hi, aOF + aML), 32u - aLL);
+        zl_br_skip(b, cA);
+    } else {                                                             // very long offsets + lengths
+        ofx = zl_br_take(b, aOF);
+        zl_br_refill(b, wbase);
+        mlx = zl_br_take(b, aML);
+        llx = zl_br_take(b, aLL);
+    }
+    if (!kLast) {                                                        // LL, ML, OF order: zstd.c:44347-44353
+        zl_br_refill(b, wbase);
+        const u32 bLL = ZL_FSE_NB(eLL), bML = ZL_FSE_NB(eML), bOF = ZL_FSE_NB(eOF);
+        const u32 hi = b.hi, lo = b.lo;
+        r.sLL = ZL_FSE_BASE(eLL) + zl_shr(hi, 32u - bLL);
+        r.sML = ZL_FSE_BASE(eML) + zl_shr(zl_fsl(lo, hi, bLL), 32u - bML);
+        r.sOF = ZL_FSE_BASE(eOF) + zl_shr(zl_fsl(lo, hi, bLL + bML), 32u - bOF);
+        zl_br_skip(b, bLL + bML + bOF);                                  // <= 26 bits
+    }
+    const u32 llCode = ZL_FSE_SYM(eLL);
+    u32 ll = ct.llBase[llCode] + llx;
+    u32 ml = ct.mlBase[ZL_FSE_SYM(eML)] + mlx;
+    // offset / repcode history, branch-free (zstd.c:44290-44326).  aOF is the offset code.
+    const u32 ll0 = (llCode == 0);
+    const bool isRep = aOF <= 1;
+    const u32 idx = aOF == 0 ? ll0 : 1u + ll0 + ofx;                     // history slot (3 = rep0 - 1)
+    const u32 cand = idx == 0 ? r.rep0 : (idx == 1 ? r.rep1 : (idx == 2 ? r.rep2 : r.rep0 - 1));
+    const u32 offset = isRep ? cand : ((1u << aOF) - 3u + ofx);
+    r.rep2 = (!isRep || idx >= 2) ? r.rep1 : r.rep2;
+    r.rep1 = (!isRep || idx >= 1) ? r.rep0 : r.rep1;
+    r.rep0 = offset;
+    // validation that ZSTD_execSequence performs (zstd.c:44024-44066, 44320)
+    const u32 matchPos = r.outPos + ll;
+    if (offset == 0 || ll > litSize - r.litPos || offset > hist + matchPos) r.err = ZL_E_corruption_detected;
+    else if ((u64)matchPos + ml > outCap) r.err = capErr;
+    if (r.err) return;
+    if (((ll | ml) >> 16) == 0) {
+        rp[r.nrec++] = zl_pack_rec(ll, ml, offset);
+        r.outPos = matchPos + ml; r.litPos += ll;
+    } else {                                                             // lengths >= 65536: split into several records
+        while (ll > 65535) {
+            if (r.nrec >= recCap) { r.err = ZL_E_GENERIC; return; }
+            rp[r.nrec++] = zl_pack_rec(65535, 0, 0);
+            r.outPos += 65535; r.litPos += 65535; ll -= 65535;
+        }
+        do {
+            const u32 m = ml > 65535 ? 65535 : ml;
+            if (r.nrec >= recCap) { r.err = ZL_E_GENERIC; return; }
+            rp[r.nrec++] = zl_pack_rec(ll, m, offset);
+            r.outPos += ll + m; r.litPos += ll; ll = 0; ml -= m;
+        } while (ml);
+    }
+}
+
+#if defined(__CUDACC__)
+// Fast path over consecutive non-last sequences whose additional bits fit one window (<= 32) and whose lengths fit a
+// single record.  Returns how many sequences it consumed; it stops BEFORE any sequence it cannot handle (the generic
+// zl_seq_step takes that one) and on errors (r.err set).  The loop is rotated: the three table cells of the next
+// sequence are requested as soon as the new states are known, and the record of the current one is built under
+// that latency.
+__device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, ZlBitR& b, const u32* wbase, const ZlConstTables& ct,
+                                                ZlSeqRegs& r, u64* rp, u32 maxIter, u32 safeCap, u32 litSize, u32 outCap,
+                                                u32 capErr, u32 hist)
+{
+    const u32 tLL = zl_smem_addr(f.fseLL), tOF = zl_smem_addr(f.fseOF), tML = zl_smem_addr(f.fseML);
+    const u32 cLL = zl_smem_addr(ct.llBase), cML = zl_smem_addr(ct.mlBase);
+    u32 hi = b.hi, lo = b.lo, nextw = b.nextw;
+    i32 n = b.n, wi = b.wi;
+    const i32 wlow = b.wlow;
+    u32 sLL = r.sLL, sOF = r.sOF, sML = r.sML, rep0 = r.rep0, rep1 = r.rep1, rep2 = r.rep2;
+    u32 outPos = r.outPos, litPos = r.litPos, nrec = r.nrec;
+    u32 eLL = zl_lds32(tLL + (sLL << 2)), eOF = zl_lds32(tOF + (sOF << 2)), eML = zl_lds32(tML + (sML << 2));
+    u32 it = 0;
+    while (it < maxIter) {
+        const u32 aOF = ZL_FSE_ADD(eOF), aML = ZL_FSE_ADD(eML), aLL = ZL_FSE_ADD(eLL);
+        const u32 llCode = ZL_FSE_SYM(eLL), mlCode = ZL_FSE_SYM(eML);
+        const u32 c2 = aOF + aML, cA = c2 + aLL;
+        if (cA > 32 || llCode >= 35 || mlCode >= 51 || nrec >= safeCap) break;           // rare: leave it to the generic step
+        const u32 llb = zl_lds32(cLL + (llCode << 2)), mlb = zl_lds32(cML + (mlCode << 2));
+        ZL_REFILL_DEV();                                                                   // n >= 33
+        const u32 ofx = zl_shr(hi, 32u - aOF);
+        const u32 mlx = zl_shr(zl_fsl(lo, hi, aOF), 32u - aML);
+        const u32 llx = zl_shr(zl_fsl(lo, hi, c2), 32u - aLL);
+        hi = zl_fsl(lo, hi, cA); lo = zl_shl(lo, cA); n -= (i32)cA;
+        ZL_REFILL_DEV();
+        const u32 bLL = ZL_FSE_NB(eLL), bML = ZL_FSE_NB(eML), bOF = ZL_FSE_NB(eOF);
+        const u32 d2 = bLL + bML, cB = d2 + bOF;                                           // <= 26
+        sLL = ZL_FSE_BASE(eLL) + zl_shr(hi, 32u - bLL);                                    // LL, ML, OF order: zstd.c:44347-44353
+        sML = ZL_FSE_BASE(eML) + zl_shr(zl_fsl(lo, hi, bLL), 32u - bML);
+        sOF = ZL_FSE_BASE(eOF) + zl_shr(zl_fsl(lo, hi, d2), 32u - bOF);
+        hi = zl_fsl(lo, hi, cB); lo <<= cB; n -= (i32)cB;
+        eLL = zl_lds32(tLL + (sLL << 2)); eOF = zl_lds32(tOF + (sOF << 2)); eML = zl_lds32(tML + (sML << 2));
+        // ---- record of the current sequence (off the state chain)
+        const u32 ll = llb + llx, ml = mlb + mlx;
+        const u32 ll0 = (llCode == 0);
+        const bool isRep = aOF <= 1;
+        const u32 idx = aOF == 0 ? ll0 : 1u + ll0 + ofx;
+        const u32 cand = idx == 0 ? rep0 : (idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1));
+        const u32 offset = isRep ? cand : ((1u << aOF) - 3u + ofx);
+        rep2 = (!isRep || idx >= 2) ? rep1 : rep2;
+        rep1 = (!isRep || idx >= 1) ? rep0 : rep1;
+        rep0 = offset;
+        const u32 matchPos = outPos + ll;
+        const bool bad = (offset == 0) | (ll > litSize - litPos) | (offset > hist + matchPos);
+        const bool over = matchPos + ml > outCap;
+        if (bad | over) { r.err = bad ? (u32)ZL_E_corruption_detected : capErr; break; }
+        rp[nrec] = zl_pack_rec(ll, ml, offset);
+        nrec++; outPos = matchPos + ml; litPos += ll;
+        it++;
+    }
+    b.hi = hi; b.lo = lo; b.nextw = nextw; b.n = n; b.wi = wi;
+    r.sLL = sLL; r.sOF = sOF; r.sML = sML; r.rep0 = rep0; r.rep1 = rep1; r.rep2 = rep2;
+    r.outPos = outPos; r.litPos = litPos; r.nrec = nrec;
+    return it;
+}
+#endif
+
+// serial sequence decode of one block (lane 0): zstd.c:44627-44700.  Completes the block's ZlBlockHdr.
+ZL_HD void zl_seq_decode(ZlSeqSm& f, const ZlFrameDesc& d, ZlBlockHdr& h, u64* recs, const u32* wbase, u32 bias,
+                         const ZlConstTables& ct)
+{
+    ZlSeqCtl& c = f.ctl;
+    if (!c.err && c.needBuild) { for (u32 t = 0; t < 3; t++) if (c.bErr[t]) c.err = ZL_E_corruption_detected; }
+    const u32 litSize = h.litSize;
+    u32 outCap = d.dstCap - c.outPos, capErr = ZL_E_dstSize_tooSmall;
+    if (outCap > ZL_BLOCKSIZE_MAX) { outCap = ZL_BLOCKSIZE_MAX; capErr = ZL_E_corruption_detected; }
     u64* rp = recs + c.recUsed;
-    u64* cp = cks + c.ckUsed;
-    const u32 recCap = d.recCap - c.recUsed, ckCap = d.ckCap - c.ckUsed;
+    const u32 recCap = d.recCap - c.recUsed;
+    ZlSeqRegs r;
+    r.outPos = 0; r.litPos = 0; r.nrec = 0; r.err = 0;
+    // every record of a valid block regenerates >= 3 bytes, so nbSeq + 4 (splits) always fits; reject early otherwise
+    if (!c.err && c.nbSeq + 4 > recCap) c.err = c.nbSeq ? ZL_E_corruption_detected : 0;
     if (!c.err && c.nbSeq) {
         ZlBitR b;
-        if (!zl_br_init(b, wbase, bias, c.bitBeg, c.blockEnd)) c.err = ZL_E_corruption_detected;
+        if (!zl_br_init(b, wbase, bias, c.bitBeg, c.bitEnd)) c.err = ZL_E_corruption_detected;
         else {
-            const u32 logLL = c.tlog[0], logOF = c.tlog[1], logML = c.tlog[2];
             zl_br_refill(b, wbase);
-            u32 sLL = zl_br_take(b, logLL);
-            u32 sOF = zl_br_take(b, logOF);
+            r.sLL = zl_br_take(b, c.tlog[0]);
+            r.sOF = zl_br_take(b, c.tlog[1]);
             zl_br_refill(b, wbase);
-            u32 sML = zl_br_take(b, logML);
-            u32 rep0 = c.rep[0], rep1 = c.rep[1], rep2 = c.rep[2];
+            r.sML = zl_br_take(b, c.tlog[2]);
+            r.rep0 = c.rep[0]; r.rep1 = c.rep[1]; r.rep2 = c.rep[2];
             const u32 hist = c.outPos + c.dictSize;          // history before this block
-            u32 err = 0;
             const u32 nbSeq = c.nbSeq;
-            for (u32 i = 0; i < nbSeq; i++) {
-                zl_br_refill(b, wbase);
-                const u32 eLL = f.fseLL[sLL], eOF = f.fseOF[sOF], eML = f.fseML[sML];
-                const u32 ofCode = ZL_FSE_SYM(eOF), llCode = ZL_FSE_SYM(eLL), mlCode = ZL_FSE_SYM(eML);
-                const u32 ofx = zl_br_take(b, ZL_FSE_ADD(eOF));
-                zl_br_refill(b, wbase);
-                const u32 mlx = zl_br_take(b, ZL_FSE_ADD(eML));
-                const u32 llx = zl_br_take(b, ZL_FSE_ADD(eLL));
-                zl_br_refill(b, wbase);
-                if (i + 1 < nbSeq) {                        // LL, ML, OF order: zstd.c:44347-44353
-                    sLL = ZL_FSE_BASE(eLL) + zl_br_take(b, ZL_FSE_NB(eLL));
-                    sML = ZL_FSE_BASE(eML) + zl_br_take(b, ZL_FSE_NB(eML));
-                    sOF = ZL_FSE_BASE(eOF) + zl_br_take(b, ZL_FSE_NB(eOF));
-                }
-                u32 ll = ct.llBase[llCode] + llx;
-                u32 ml = ct.mlBase[mlCode] + mlx;
-                u32 offset;
-                if (ofCode > 1) {
-                    offset = (1u << ofCode) - 3 + ofx;
-                    rep2 = rep1; rep1 = rep0; rep0 = offset;
-                } else {
-                    const u32 ll0 = (llCode == 0);
-                    if (ofCode == 0) {
-                        if (ll0) { offset = rep1; rep1 = rep0; rep0 = offset; } else offset = rep0;
-                    } else {
-                        const u32 idx = 1 + ll0 + ofx;
-                        u32 t = idx == 3 ? rep0 - 1 : (idx == 1 ? rep1 : rep2);
-                        if (t == 0) { err = ZL_E_corruption_detected; t = 1; }      // zstd.c:44320
-                        if (idx != 1) rep2 = rep1;
-                        rep1 = rep0; rep0 = t; offset = t;
-                    }
-                }
-                // validation that ZSTD_execSequence performs (zstd.c:44024-44066)
-                if (ll > litSize - litPos) err = ZL_E_corruption_detected;
-                else if ((u64)outPos + ll + ml > outCap) err = capIsDst ? ZL_E_dstSize_tooSmall : ZL_E_corruption_detected;
-                else if (offset > hist + outPos + ll) err = ZL_E_corruption_detected;
-                if (err) break;
-                // emit (split lengths >= 65536 into several records)
-                while (ll > 65535) {
-                    if (nrec >= recCap || (nrec >> 5) >= ckCap) { err = ZL_E_GENERIC; break; }
-                    if ((nrec & 31) == 0) cp[nrec >> 5] = (u64)outPos | ((u64)litPos << 32);
-                    rp[nrec++] = zl_pack_rec(65535, 0, 0);
-                    outPos += 65535; litPos += 65535; ll -= 65535;
-                }
-                do {
-                    u32 m = ml > 65535 ? 65535 : ml;
-                    if (nrec >= recCap || (nrec >> 5) >= ckCap) { err = ZL_E_GENERIC; break; }
-                    if ((nrec & 31) == 0) cp[nrec >> 5] = (u64)outPos | ((u64)litPos << 32);
-                    rp[nrec++] = zl_pack_rec(ll, m, offset);
-                    outPos += ll + m; litPos += ll; ll = 0; ml -= m;
-                } while (ml);
-                if (err) break;
+            const u32 safeCap = recCap - 4;                  // split path re-checks exactly
+            for (u32 i = 0; i + 1 < nbSeq; i++) {
+#if defined(__CUDA_ARCH__)
+                i += zl_seq_fast_loop(f, b, wbase, ct, r, rp, nbSeq - 1 - i, safeCap, litSize, outCap, capErr, hist);
+                if (r.err || r.nrec >= safeCap || i + 1 >= nbSeq) break;
+#endif
+                zl_seq_step<false>(f, b, wbase, ct, r, rp, recCap, litSize, outCap, capErr, hist);
+                if (r.err || r.nrec >= safeCap) break;
             }
-            if (!err && zl_br_remaining(b, bias, c.bitBeg) != 0) err = ZL_E_corruption_detected;      // zstd.c:44686
-            if (err) c.err = err;
-            c.rep[0] = rep0; c.rep[1] = rep1; c.rep[2] = rep2;
+            if (!r.err && r.nrec >= safeCap && nbSeq > 1) r.err = ZL_E_corruption_detected;
+            if (!r.err) zl_seq_step<true>(f, b, wbase, ct, r, rp, recCap, litSize, outCap, capErr, hist);
+            if (!r.err && zl_br_remaining(b, bias, c.bitBeg) != 0) r.err = ZL_E_corruption_detected;      // zstd.c:44686
+            if (r.err) c.err = r.err;
+            c.rep[0] = r.rep0; c.rep[1] = r.rep1; c.rep[2] = r.rep2;
         }
     }
     if (!c.err) {
-        u32 lastLL = litSize - litPos;
-        if ((u64)outPos + lastLL > outCap) c.err = capIsDst ? ZL_E_dstSize_tooSmall : ZL_E_corruption_detected;
-        else outPos += lastLL;
+        const u32 lastLL = litSize - r.litPos;
+        if ((u64)r.outPos + lastLL > outCap) c.err = capErr;
+        else r.outPos += lastLL;
     }
-    if (c.err) { zl_ent_finish_frame(f, d, info); return; }
-    ZlBlockHdr h;
-    h.flags = 2u | (c.litMode << 4) | (c.litMode == 1 ? (c.rleByte << 8) : 0u);
-    h.regenSize = outPos;
-    h.srcOff = c.litSrcOff; h.litOff = c.litOff; h.litSize = litSize;
-    h.nrec = nrec; h.recOff = c.recUsed; h.ckOff = c.ckUsed;
-    hdrs[c.blockIdx] = h;
-    c.recUsed += nrec; c.ckUsed += (nrec + 31) >> 5;
-    c.outPos += outPos; c.blockIdx++; c.pos = c.blockEnd;
-    if (c.last) zl_ent_finish_frame(f, d, info);
+    if (c.err) return;
+    h.regenSize = r.outPos; h.nrec = r.nrec; h.recOff = c.recUsed;
+    c.recUsed += r.nrec;
+    c.outPos += r.outPos;
+}
+
+// whole-frame driver pieces for K1b (lane 0)
+ZL_HD void zl_seq_begin_frame(ZlSeqSm& f, const ZlFrameInfo& info, u32 dictSize)
+{
+    ZlSeqCtl& c = f.ctl;
+    c.err = info.err; c.outPos = 0; c.fseValid = 0; c.rep[0] = 1; c.rep[1] = 4; c.rep[2] = 8;     // zstd.c:15416
+    c.recUsed = 0; c.dictSize = dictSize; c.nbSeq = 0; c.needBuild = 0;
+    c.bErr[0] = c.bErr[1] = c.bErr[2] = 0;
+}
+// raw / RLE blocks only need their size checked against the destination (zstd.c:41497-41520)
+ZL_HD void zl_seq_plain_block(ZlSeqSm& f, const ZlFrameDesc& d, const ZlBlockHdr& h)
+{
+    ZlSeqCtl& c = f.ctl;
+    if (c.err) return;
+    if (h.regenSize > d.dstCap - c.outPos) c.err = ZL_E_dstSize_tooSmall;
+    else c.outPos += h.regenSize;
+}
+ZL_HD void zl_seq_finish_frame(ZlSeqSm& f, ZlFrameInfo& info)
+{
+    ZlSeqCtl& c = f.ctl;
+    if (!c.err && info.contentSize != ~0ull && info.contentSize != (u64)c.outPos) c.err = ZL_E_corruption_detected;   // zstd.c:41646
+    info.err = c.err; info.totalOut = c.outPos;
 }

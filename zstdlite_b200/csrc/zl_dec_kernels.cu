@@ -1,5 +1,5 @@
-// zl_dec_kernels.cu -- the three decode kernels and their launchers (sm_100a).
-//   K1 zl_k_entropy   quad-per-frame entropy decode -> literal / record / header arenas
+// zl_dec_kernels.cu -- the decode kernels and their launchers (sm_100a).
+//   K1a zl_k_literals / K1b zl_k_sequences   quad-per-frame entropy decode -> literal / record / header arenas
 //   K2 zl_k_execute   warp-per-frame sequence execution -> frame output
 //   K3 zl_k_checksum  quad-per-frame XXH64 of the output, compared with the frame trailer
 #include "zl_dec_entropy.cuh"
@@ -12,69 +12,97 @@ __constant__ ZlConstTables c_tables = {
 
 #define ZL_CT_BYTES ((sizeof(ZlConstTables) + 15) & ~(size_t)15)
 
+// ---- K1a: literals ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
-zl_k_entropy(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, ZlBlockHdr* hdrArena,
-             u64* recArena, u64* ckArena, u8* litArena, u32 nframes, const ZlDictDev* dict)
+zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, ZlBlockHdr* hdrArena,
+              u8* litArena, u32 nframes, const ZlDictDev* dict)
 {
     extern __shared__ __align__(16) u8 smraw[];
-    ZlConstTables& ct = *reinterpret_cast<ZlConstTables*>(smraw);
-    ZlFrameSm* fs = reinterpret_cast<ZlFrameSm*>(smraw + ZL_CT_BYTES);
+    ZlLitSm* fs = reinterpret_cast<ZlLitSm*>(smraw);
     const u32 lane = threadIdx.x, quad = lane >> 2, q = lane & 3;
     const u32 qmask = 0xFu << (quad * 4);
-    {   // constant tables -> shared memory (divergent lookups by code are conflict-cheap there)
-        const u32* s = reinterpret_cast<const u32*>(&c_tables);
-        u32* d = reinterpret_cast<u32*>(&ct);
-        for (u32 i = lane; i < sizeof(ZlConstTables) / 4; i += 32) d[i] = s[i];
-    }
-    __syncwarp();
     const u32 frame = blockIdx.x * ZL_QUADS_PER_WARP + quad;
     if (frame >= nframes) return;
-    ZlFrameSm& f = fs[quad];
+    ZlLitSm& f = fs[quad];
     const ZlFrameDesc d = descs[frame];
     ZlFrameInfo& info = infos[frame];
     ZlBlockHdr* hdrs = hdrArena + d.hdrBase;
-    u64* recs = recArena + d.recBase;
-    u64* cks = ckArena + d.ckBase;
     u8* lits = litArena + d.litBase;
     const u32 bias = (u32)(((size_t)d.src) & 3);
     const u32* wbase = reinterpret_cast<const u32*>(d.src - bias);
-
+    const bool seed = dict && dict->hasEntropy;
     if (q == 0) {
-        zl_ent_begin_frame(f, d, info, dict ? dict->contentSize : 0u, dict ? dict->dictID : 0u);
-        if (dict && dict->hasEntropy && !f.ctl.err) {          // zstd.c:42140-42159: seed tables + repcodes
-            f.ctl.hufValid = 1; f.ctl.hufLog = dict->hufLog; f.ctl.fseValid = 7;
-            f.ctl.tlog[0] = dict->tlog[0]; f.ctl.tlog[1] = dict->tlog[1]; f.ctl.tlog[2] = dict->tlog[2];
-            f.ctl.rep[0] = dict->rep[0]; f.ctl.rep[1] = dict->rep[1]; f.ctl.rep[2] = dict->rep[2];
-        }
+        zl_lit_begin_frame(f, d, info, dict ? dict->dictID : 0u);
+        if (seed && !f.ctl.err) { f.ctl.hufValid = 1; f.ctl.hufLog = dict->hufLog; }      // zstd.c:42140-42159
     }
-    __syncwarp(qmask);
-    if (dict && dict->hasEntropy) {
-        for (u32 i = q; i < 512; i += 4) { f.fseLL[i] = dict->fseLL[i]; f.fseML[i] = dict->fseML[i]; }
-        for (u32 i = q; i < 256; i += 4) f.fseOF[i] = dict->fseOF[i];
-        for (u32 i = q; i < 2048; i += 4) f.huf[i] = dict->huf[i];
-        __syncwarp(qmask);
-    }
+    if (seed) for (u32 i = q; i < 2048; i += 4) f.huf[i] = dict->huf[i];
     // Lane 0 writes f.ctl between quad barriers; the other lanes snapshot what they need right after a
     // barrier and a second barrier keeps lane 0 from overwriting it before everyone has read it.
     for (;;) {
-        if (q == 0) zl_ent_block_head(f, d, info, hdrs, wbase, bias);
         __syncwarp(qmask);
-        const u32 done = f.ctl.done, comp = f.ctl.isCompressed, fill = f.ctl.needHufFill, ns = f.ctl.nStreams;
+        if (q == 0) zl_lit_block_head(f, d, info, hdrs, wbase, bias);
+        __syncwarp(qmask);
+        const u32 done = f.ctl.done, fill = f.ctl.needHufFill, ns = f.ctl.nStreams;
         __syncwarp(qmask);
         if (done) break;
-        if (!comp) continue;
         if (fill) { zl_huf_fill(f, q); __syncwarp(qmask); }
         if (q < ns)
             f.ctl.sErr[q] = zl_huf_stream(f.huf, f.ctl.hufLog, wbase, bias, f.ctl.sBeg[q], f.ctl.sEnd[q],
                                           lits + f.ctl.sOut[q], f.ctl.sLen[q]);
-        __syncwarp(qmask);
-        if (q == 0) zl_ent_seq_head(f, d, ct);
+    }
+}
+
+// ---- K1b: sequences -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, ZlBlockHdr* hdrArena,
+               u64* recArena, u32 nframes, const ZlDictDev* dict)
+{
+    extern __shared__ __align__(16) u8 smraw[];
+    ZlConstTables& ct = *reinterpret_cast<ZlConstTables*>(smraw);
+    ZlSeqSm* fs = reinterpret_cast<ZlSeqSm*>(smraw + ZL_CT_BYTES);
+    const u32 lane = threadIdx.x, quad = lane >> 2, q = lane & 3;
+    const u32 qmask = 0xFu << (quad * 4);
+    {   // constant tables -> shared memory (divergent lookups by code are conflict-cheap there)
+        const u32* s = reinterpret_cast<const u32*>(&c_tables);
+        u32* dd = reinterpret_cast<u32*>(&ct);
+        for (u32 i = lane; i < sizeof(ZlConstTables) / 4; i += 32) dd[i] = s[i];
+    }
+    __syncwarp();
+    const u32 frame = blockIdx.x * ZL_QUADS_PER_WARP + quad;
+    if (frame >= nframes) return;
+    ZlSeqSm& f = fs[quad];
+    const ZlFrameDesc d = descs[frame];
+    ZlFrameInfo& info = infos[frame];
+    ZlBlockHdr* hdrs = hdrArena + d.hdrBase;
+    u64* recs = recArena + d.recBase;
+    const u32 bias = (u32)(((size_t)d.src) & 3);
+    const u32* wbase = reinterpret_cast<const u32*>(d.src - bias);
+    const u32 nblocks = info.nblocks;
+    const bool seed = dict && dict->hasEntropy;
+    if (q == 0) {
+        zl_seq_begin_frame(f, info, dict ? dict->contentSize : 0u);
+        if (seed) {                                                   // zstd.c:42140-42159: tables + repcodes from the dictionary
+            f.ctl.fseValid = 7;
+            f.ctl.tlog[0] = dict->tlog[0]; f.ctl.tlog[1] = dict->tlog[1]; f.ctl.tlog[2] = dict->tlog[2];
+            f.ctl.rep[0] = dict->rep[0]; f.ctl.rep[1] = dict->rep[1]; f.ctl.rep[2] = dict->rep[2];
+        }
+    }
+    if (seed) {
+        for (u32 i = q; i < 512; i += 4) { f.fseLL[i] = dict->fseLL[i]; f.fseML[i] = dict->fseML[i]; }
+        for (u32 i = q; i < 256; i += 4) f.fseOF[i] = dict->fseOF[i];
+    }
+    __syncwarp(qmask);
+    for (u32 b = 0; b < nblocks; b++) {
+        ZlBlockHdr h = hdrs[b];
+        if ((h.flags & 3) != 2) { if (q == 0) zl_seq_plain_block(f, d, h); continue; }
+        if (q == 0) zl_seq_head(f, d, h, ct);
         __syncwarp(qmask);
         const u32 build = f.ctl.err ? 0u : f.ctl.needBuild;
         __syncwarp(qmask);
-        if (build) { if (q < 3) zl_ent_fse_build(f, q, ct); __syncwarp(qmask); }
-        if (q == 0) zl_ent_seq_decode(f, d, info, hdrs, recs, cks, wbase, bias, ct);
+        if (build) { if (q < 3) zl_seq_fse_build(f, q, ct); __syncwarp(qmask); }
+        if (q == 0) { zl_seq_decode(f, d, h, recs, wbase, bias, ct); hdrs[b] = h; }
     }
+    if (q == 0) zl_seq_finish_frame(f, info);
 }
 
 template <bool kDict>
@@ -136,20 +164,20 @@ zl_k_xxh64(const u8* const* __restrict__ ptrs, const u32* __restrict__ sizes, u6
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------
-size_t zl_entropy_smem_bytes() { return ZL_CT_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlFrameSm); }
+size_t zl_literals_smem_bytes() { return ZL_QUADS_PER_WARP * sizeof(ZlLitSm); }
+size_t zl_sequences_smem_bytes() { return ZL_CT_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlSeqSm); }
 
 cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
 {
     if (L.nframes == 0) return cudaSuccess;
-    static bool attrDone = false;
-    const size_t smem = zl_entropy_smem_bytes();
-    if (!attrDone) {
-        cudaError_t e = cudaFuncSetAttribute(zl_k_entropy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attrDone = true;
-    }
+    const size_t smA = zl_literals_smem_bytes(), smB = zl_sequences_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(zl_k_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(zl_k_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB);
+    if (e != cudaSuccess) return e;
     const u32 g1 = (L.nframes + ZL_QUADS_PER_WARP - 1) / ZL_QUADS_PER_WARP;
-    zl_k_entropy<<<g1, 32, smem, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.ckArena, L.litArena, L.nframes, L.dict);
+    zl_k_literals<<<g1, 32, smA, st>>>(L.descs, L.infos, L.hdrArena, L.litArena, L.nframes, L.dict);
+    zl_k_sequences<<<g1, 32, smB, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.nframes, L.dict);
     const u32 g2 = (L.nframes + ZL_EXEC_WARPS - 1) / ZL_EXEC_WARPS;
     if (L.dict)
         zl_k_execute<true><<<g2, ZL_EXEC_WARPS * 32, 0, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.results, L.nframes, L.dict);

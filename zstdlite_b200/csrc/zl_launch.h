@@ -27,7 +27,6 @@ struct ZlDecodeLaunch {
     ZlFrameInfo* infos;
     ZlBlockHdr* hdrArena;
     u64* recArena;
-    u64* ckArena;
     u8* litArena;
     u64* results;
     u32 nframes;
@@ -35,6 +34,7 @@ struct ZlDecodeLaunch {
     const ZlDictDev* dict;   // device pointer or null
 };
 
-size_t zl_entropy_smem_bytes();
+size_t zl_literals_smem_bytes();
+size_t zl_sequences_smem_bytes();
 cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st);
 cudaError_t zl_launch_xxh64(const u8* const* ptrs, const u32* sizes, u64* out, u32 n, cudaStream_t st);
