@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on its configs[1] workload: batched zstd_decompress of 16,384 independent
+64 KiB frames (1 GiB of content) per B200, frames produced by the reference's libzstd at level 3.
+
+    python bench.py --gpus N --steps K --warmup W            our CUDA path through the C ABI (libzstdlite_gpu.so)
+    python bench.py --impl reference ...                      the reference's own libzstd on the host cores
+
+One JSON line on stdout (rank 0).  `value`  = whole-job GB/s of uncompressed bytes, inputs resident in HBM;
+`e2e` = same metric through the C ABI with pinned HOST buffers (H2D of the frames and D2H of the output inside the
+timed region); `roofline` = dominant kernel against the measured HBM copy bandwidth; `cpu_baseline` = the reference's
+libzstd, frame-parallel on all host cores, on a bounded sample of the same frames; `compress` = the level-1/level-3
+compressor on configs[2]'s 128 KiB slabs (reported beside the headline; BASELINE.json's metric is "decompress+compress").
+Multi-GPU: frames are independent, so every rank decodes its own 16,384-frame shard (weak scaling, no collective on
+the data path; barrier + max-over-ranks timing only).
+
+oracle/ is used here only for (1) producing the compressed input corpus with the reference's libzstd before any timed
+region, (2) the cpu_baseline leg and (3) --impl reference.  The measured path never touches it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MIX = (("text", 0.4), ("rdf", 0.4), ("lowent", 0.1), ("rand", 0.1))
+METRIC = "decompress_GBps_uncompressed"
+UNIT = "GB/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_corpus(nframes, frame_bytes, level=3, pool=64, seed_shift=0):
+    """-> (raw [nframes, frame_bytes] uint8, list of compressed frames). Distinct frames are compressed once."""
+    from zstdlite_b200 import corpus
+    from oracle import ref
+    data, fams = corpus.mixed_frames(nframes, frame_bytes, mix=MIX, pool=pool)
+    if seed_shift:
+        data = np.roll(data, seed_shift, axis=0)
+    cache, frames = {}, []
+    for i in range(nframes):
+        key = data[i].tobytes()
+        c = cache.get(key)
+        if c is None:
+            c = cache[key] = ref.compress(key, level)
+        frames.append(c)
+    return data, frames
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()                      # the exact child we started
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_leg(frames_sample, frame_bytes, budget_s, threads):
+    """reference libzstd, frame-parallel on `threads` host cores -> (GB/s, seconds per pass, passes)."""
+    from oracle import cpubench
+    blob = np.frombuffer(b"".join(frames_sample), dtype=np.uint8)
+    fs = cpubench.FrameSet(blob, [len(f) for f in frames_sample])
+    caps = [frame_bytes] * len(frames_sample)
+    t_pass, *_ = cpubench.run("decompress", fs, caps, threads)        # warm-up pass (page faults, contexts)
+    passes = max(1, min(50, int(budget_s / max(t_pass, 1e-3))))
+    best, *_ = cpubench.run("decompress", fs, caps, threads, passes=passes)
+    return len(frames_sample) * frame_bytes / best / 1e9, best, passes
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    nsample = min(args.frames, args.cpu_frames)
+    data, frames = make_corpus(args.frames, args.frame_bytes)
+    step = max(1, args.frames // nsample)
+    sample = frames[::step][:nsample]                                  # keeps the family mix
+    from oracle import cpubench
+    blob = np.frombuffer(b"".join(sample), dtype=np.uint8)
+    fs = cpubench.FrameSet(blob, [len(f) for f in sample])
+    caps = [args.frame_bytes] * len(sample)
+    for _ in range(args.warmup):
+        cpubench.run("decompress", fs, caps, threads)
+    times = [cpubench.run("decompress", fs, caps, threads)[0] for _ in range(args.steps)]
+    total = sum(times)
+    val = len(sample) * args.frame_bytes * args.steps / total / 1e9
+    desc = f"{len(sample)} of the {args.frames} frames (every {step}th, same family mix), {threads} threads, one DCtx per thread"
+    out = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u8", "data": "synthetic", "impl": "reference",
+           "config": workload_config(args, 1),
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": desc},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"configs[1]: batched zstd_decompress of {args.frames} independent {args.frame_bytes // 1024} KiB frames "
+                        f"({args.frames * args.frame_bytes / 2**30:.2f} GiB content) per GPU, libzstd level-3 frames, families text/rdf/lowent/rand 40/40/10/10",
+            "frames_per_gpu": args.frames, "frame_bytes": args.frame_bytes, "level": 3, "checksum": False,
+            "sharding": f"{world} x independent frame shards, no collective",
+            "cache": "working set (compressed in + 1 GiB out per step) exceeds the 126 MB L2; no explicit flush"}
+
+
+def compress_leg(torch, z, args, dev):
+    """configs[2] shape at reduced count: 128 KiB slabs, levels 1 and 3, device-resident; ratio vs libzstd on the same slabs."""
+    from oracle import ref
+    from zstdlite_b200 import corpus
+    n, fb = args.compress_frames, 131072
+    data, fams = corpus.mixed_frames(n, fb, mix=MIX, pool=32)
+    src = torch.from_numpy(data.reshape(-1)).to(dev)
+    bound = int(z._lib.lib().ZSTD_compressBound(fb))
+    slot = (bound + 255) // 256 * 256
+    dst = torch.zeros(n * slot + 64, dtype=torch.uint8, device=dev)
+    out = {}
+    for lvl in (1, 3):
+        cctx = z.zstd_cctx(level=lvl)
+        plan = z.BatchPlan([src.data_ptr() + i * fb for i in range(n)], [fb] * n, [dst.data_ptr() + i * slot for i in range(n)], [bound] * n)
+        res = None
+        for _ in range(2):
+            res = plan.compress(cctx)
+        torch.cuda.synchronize()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        cctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        t0.record()
+        iters = 3
+        for _ in range(iters):
+            res = plan.compress(cctx)
+        t1.record(); torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / iters
+        sizes = np.array(list(res), dtype=np.int64)
+        assert not any(z.is_error(int(s)) for s in sizes[:64])
+        csize = int(sizes.sum())
+        # reference ratio on the same slabs (distinct slabs only) and a round-trip spot check through libzstd
+        cache = {}
+        refsize = 0
+        for i in range(n):
+            k = data[i].tobytes()
+            if k not in cache:
+                cache[k] = len(ref.compress(k, lvl))
+            refsize += cache[k]
+        host = dst.cpu().numpy()
+        for i in range(0, n, max(1, n // 16)):
+            assert ref.decompress(host[i * slot:i * slot + int(sizes[i])].tobytes()) == data[i].tobytes(), "GPU frame does not round-trip through libzstd"
+        out[f"level{lvl}"] = {"GBps": n * fb / ms / 1e6, "ms": ms, "ratio": n * fb / csize, "ratio_libzstd": n * fb / refsize,
+                              "ratio_vs_libzstd": (n * fb / csize) / (n * fb / refsize), "kernel_ms": cctx.last_kernel_ms,
+                              "frames": n, "frame_bytes": fb}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=16384)
+    ap.add_argument("--frame-bytes", type=int, default=65536)
+    ap.add_argument("--cpu-frames", type=int, default=2048, help="frames in the bounded CPU sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--compress-frames", type=int, default=4096)
+    ap.add_argument("--no-compress", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; zstdlite_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import zstdlite_b200 as z
+
+    t_prep = time.time()
+    data, frames = make_corpus(args.frames, args.frame_bytes, seed_shift=rank * 17)
+    n, fb = args.frames, args.frame_bytes
+    sizes = [len(f) for f in frames]
+    csize = sum(sizes)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    blob = np.frombuffer(b"".join(frames), dtype=np.uint8)
+    log(f"[rank {rank}] corpus {n} x {fb}: ratio {n * fb / csize:.3f}, prep {time.time() - t_prep:.1f}s")
+
+    # ---- device-resident arm
+    src = torch.zeros(csize + 64, dtype=torch.uint8, device=dev)
+    src[:csize].copy_(torch.from_numpy(blob.copy()))
+    dst = torch.zeros(n * fb + 64, dtype=torch.uint8, device=dev)
+    dctx = z.zstd_dctx()
+    stream = torch.cuda.current_stream()
+    dctx.set_stream(stream.cuda_stream)
+    plan = z.BatchPlan([src.data_ptr() + int(o) for o in offs[:-1]], sizes, [dst.data_ptr() + i * fb for i in range(n)], [fb] * n)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        res = plan.decompress(dctx)
+    assert all(int(r) == fb for r in res), "decode errors in warm-up"
+    got = dst[:n * fb].cpu().numpy().reshape(n, fb)
+    assert (got == data).all(), "GPU output differs from the original bytes"
+    del got
+    sampler = ClockSampler(local)
+    stage_names = ("literals", "sequences", "execute", "checksum")
+    stage_ms = np.zeros(4)
+    launches0 = dctx.launch_count
+    sync_all()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        plan.decompress(dctx)
+        stage_ms += [z._lib.lib().zl_dctx_last_stage_ms(dctx._p, k) for k in range(4)]
+    e1.record(stream)
+    sync_all()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = dctx.launch_count - launches0
+    stage_ms /= args.steps
+
+    # ---- end-to-end arm: pinned host buffers in, pinned host buffer out, through the same C-ABI call
+    hsrc = torch.from_numpy(blob.copy()).pin_memory()
+    hdst = torch.zeros(n * fb, dtype=torch.uint8).pin_memory()
+    hplan = z.BatchPlan([hsrc.data_ptr() + int(o) for o in offs[:-1]], sizes, [hdst.data_ptr() + i * fb for i in range(n)], [fb] * n)
+    for _ in range(2):
+        hplan.decompress(dctx, device=False)
+    assert (hdst.numpy().reshape(n, fb) == data).all()
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(e2e_steps):
+        hplan.decompress(dctx, device=False)
+    e3.record(stream)
+    sync_all()
+    ms_e2e = e2.elapsed_time(e3)
+
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+    total_bytes = world * n * fb
+    value = total_bytes * args.steps / ms_total / 1e6
+    e2e_value = total_bytes * e2e_steps / ms_e2e / 1e6
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        else:
+            peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+        k = int(np.argmax(stage_ms))
+        alg_bytes = csize + n * fb                                     # compressed read + uncompressed written
+        achieved = alg_bytes / stage_ms[k] / 1e6
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(csize + n * 80), "d2h_bytes_per_step": int(n * fb + n * 8),
+                       "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+               "gpu_launches": int(launches), "clocks": clocks,
+               "roofline": {"bound": "hbm", "kernel": "zl_k_" + stage_names[k], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": float(stage_ms[k]),
+                            "whole_pipeline_frac": (alg_bytes / (ms_total / args.steps) / 1e6) / peak},
+               "stages_ms": {nm: float(v) for nm, v in zip(stage_names, stage_ms)},
+               "compression_ratio_of_input": n * fb / csize}
+        traffic_path = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+        if os.path.exists(traffic_path):
+            try:
+                tr = json.load(open(traffic_path))
+                if tr.get("kernel") == out["roofline"]["kernel"]:
+                    out["roofline"]["traffic"] = tr.get("dram_bytes_per_launch_at_bench_size")
+                    out["roofline"]["traffic_source"] = tr.get("source")
+            except (ValueError, OSError):
+                pass
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            nsample = min(n, args.cpu_frames)
+            step = max(1, n // nsample)
+            sample = frames[::step][:nsample]
+            v, t_pass, passes = cpu_leg(sample, fb, args.cpu_seconds, threads)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
+                                   "sample": f"{len(sample)} of the {n} frames (every {step}th, same family mix), best of {passes} passes, "
+                                             f"oracle/_ref libzstd 1.5.6, one DCtx per thread"}
+        if world == 1 and not args.no_compress and hasattr(z._lib.lib(), "zl_compress_batch"):
+            try:
+                out["compress"] = compress_leg(torch, z, args, dev)
+            except Exception as e:                                      # the headline is the decode arm; report, don't hide
+                out["compress"] = {"error": repr(e)}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -110,6 +110,9 @@ unsigned long long zl_cctx_launch_count(const ZSTD_CCtx* cctx);
 /* milliseconds spent on-device by the kernels of the most recent batch call (CUDA events on the context's stream) */
 double zl_dctx_last_kernel_ms(const ZSTD_DCtx* dctx);
 double zl_cctx_last_kernel_ms(const ZSTD_CCtx* cctx);
+/* per-kernel split of the above; decode stages: 0 literals, 1 sequences, 2 execute, 3 checksum; returns -1 for an unknown stage */
+double zl_dctx_last_stage_ms(const ZSTD_DCtx* dctx, int stage);
+double zl_cctx_last_stage_ms(const ZSTD_CCtx* cctx, int stage);
 const char* zl_backend_string(void);
 
 #ifdef __cplusplus

@@ -174,7 +174,8 @@ struct ZSTD_DCtx_s {
     cudaStream_t stream = nullptr;
     bool ownStream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    double lastKernelMs = 0.0;
+    cudaEvent_t stageEv[ZL_DEC_STAGES + 1] = {};
+    double lastKernelMs = 0.0, lastStageMs[ZL_DEC_STAGES] = {};
     unsigned long long launches = 0;
     ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dSrc, dDst;
     ZlPinBuf hDescs, hResults;
@@ -198,6 +199,7 @@ ZL_EXPORT size_t ZSTD_freeDCtx(ZSTD_DCtx* c)
     for (ZlDevBuf* b : bufs) b->release();
     c->hDescs.release(); c->hResults.release();
     if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
+    for (cudaEvent_t e : c->stageEv) if (e) cudaEventDestroy(e);
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -237,6 +239,7 @@ ZL_EXPORT size_t zl_dctx_set_stream(ZSTD_DCtx* c, void* s)
 }
 ZL_EXPORT unsigned long long zl_dctx_launch_count(const ZSTD_DCtx* c) { return c->launches; }
 ZL_EXPORT double zl_dctx_last_kernel_ms(const ZSTD_DCtx* c) { return c->lastKernelMs; }
+ZL_EXPORT double zl_dctx_last_stage_ms(const ZSTD_DCtx* c, int stage) { return stage >= 0 && stage < ZL_DEC_STAGES ? c->lastStageMs[stage] : -1.0; }
 
 // Digest a dictionary (zstd.c:42053-42137 ZSTD_loadDEntropy, 42140 insertDictionary) into ZlDictDev.
 ZL_EXPORT size_t ZSTD_DCtx_loadDictionary(ZSTD_DCtx* c, const void* dict, size_t dictSize)
@@ -360,6 +363,8 @@ ZL_EXPORT size_t zl_decompress_batch(ZSTD_DCtx* c, const void* const* src, const
     L.descs = c->dDescs.as<ZlFrameDesc>(); L.infos = c->dInfos.as<ZlFrameInfo>(); L.hdrArena = c->dHdr.as<ZlBlockHdr>();
     L.recArena = c->dRec.as<u64>(); L.litArena = c->dLit.as<u8>(); L.results = c->dResults.as<u64>();
     L.nframes = (u32)n; L.verifyChecksum = !c->forceIgnoreChecksum; L.dict = c->hasDict ? c->dDict.as<ZlDictDev>() : nullptr;
+    if (!c->stageEv[0]) for (cudaEvent_t& e : c->stageEv) cudaEventCreate(&e);
+    L.stageEv = c->stageEv;
     cudaEventRecord(c->ev0, st);
     cudaError_t e = zl_launch_decode(L, st);
     cudaEventRecord(c->ev1, st);
@@ -370,6 +375,7 @@ ZL_EXPORT size_t zl_decompress_batch(ZSTD_DCtx* c, const void* const* src, const
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { fprintf(stderr, "zstdlite_gpu: device error: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->lastKernelMs = ms;
+    for (int k = 0; k < ZL_DEC_STAGES; k++) { float t = 0; cudaEventElapsedTime(&t, c->stageEv[k], c->stageEv[k + 1]); c->lastStageMs[k] = t; }
     const u64* hr = c->hResults.as<u64>();
     for (size_t i = 0; i < n; i++) result[i] = (size_t)hr[i];
     return 0;

@@ -176,17 +176,23 @@ cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
     e = cudaFuncSetAttribute(zl_k_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB);
     if (e != cudaSuccess) return e;
     const u32 g1 = (L.nframes + ZL_QUADS_PER_WARP - 1) / ZL_QUADS_PER_WARP;
+    cudaEvent_t* ev = L.stageEv;
+    if (ev) cudaEventRecord(ev[0], st);
     zl_k_literals<<<g1, 32, smA, st>>>(L.descs, L.infos, L.hdrArena, L.litArena, L.nframes, L.dict);
+    if (ev) cudaEventRecord(ev[1], st);
     zl_k_sequences<<<g1, 32, smB, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.nframes, L.dict);
+    if (ev) cudaEventRecord(ev[2], st);
     const u32 g2 = (L.nframes + ZL_EXEC_WARPS - 1) / ZL_EXEC_WARPS;
     if (L.dict)
         zl_k_execute<true><<<g2, ZL_EXEC_WARPS * 32, 0, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.results, L.nframes, L.dict);
     else
         zl_k_execute<false><<<g2, ZL_EXEC_WARPS * 32, 0, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.results, L.nframes, nullptr);
+    if (ev) cudaEventRecord(ev[3], st);
     if (L.verifyChecksum) {
         const u32 g3 = (L.nframes * 4 + 127) / 128;
         zl_k_checksum<<<g3, 128, 0, st>>>(L.descs, L.infos, L.results, L.nframes);
     }
+    if (ev) cudaEventRecord(ev[4], st);
     return cudaGetLastError();
 }
 

@@ -5,6 +5,7 @@
 
 #define ZL_QUADS_PER_WARP 8
 #define ZL_EXEC_WARPS 4
+#define ZL_DEC_STAGES 4      // literals, sequences, execute, checksum
 
 // digested dictionary in device memory (zstd.c:42053-42159, ZSTD_DDict): entropy tables in the packed
 // cell formats of zl_dec_entropy.cuh plus the raw content that acts as history before the frame.
@@ -32,6 +33,7 @@ struct ZlDecodeLaunch {
     u32 nframes;
     int verifyChecksum;
     const ZlDictDev* dict;   // device pointer or null
+    cudaEvent_t* stageEv;    // null, or ZL_DEC_STAGES + 1 events recorded around each kernel (per-kernel timing for bench.py)
 };
 
 size_t zl_literals_smem_bytes();
