@@ -42,7 +42,15 @@ typedef struct {
     volatile size_t next;
     volatile int errors;
     pthread_barrier_t* start;
+    double* tBeg; double* tEnd;      /* per-worker timestamps: the pass lasts from the first start to the last end */
+    volatile int nextId;
 } job_t;
+
+static double now_s(void)
+{
+    struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
 
 static void* worker(void* arg)
 {
@@ -57,7 +65,9 @@ static void* worker(void* arg)
         d = ZSTD_createDCtx();
         if (j->dict) ZSTD_DCtx_loadDictionary(d, j->dict, j->dictSize);
     }
+    const int id = __sync_fetch_and_add(&j->nextId, 1);
     pthread_barrier_wait(j->start);
+    j->tBeg[id] = now_s();
     for (;;) {
         size_t i = __sync_fetch_and_add(&j->next, (size_t)16);      /* 16 frames per grab */
         if (i >= j->n) break;
@@ -69,20 +79,15 @@ static void* worker(void* arg)
             if (j->result) j->result[i] = r;
         }
     }
+    j->tEnd[id] = now_s();
     pthread_barrier_wait(j->start);
     if (c) ZSTD_freeCCtx(c);
     if (d) ZSTD_freeDCtx(d);
     return NULL;
 }
 
-static double now_s(void)
-{
-    struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
-    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
-}
-
 /* One timed pass over all n frames with `threads` workers; returns seconds (contexts are created outside the
- * timed region, which starts when every worker is ready and ends when the last one is done), or -1 on error. */
+ * timed region, which runs from the first worker's start to the last worker's end), or -1 on error. */
 double zlb_run(int mode, const void* src, const size_t* srcOff, const size_t* srcSize, void* dst, const size_t* dstOff,
                const size_t* dstCap, size_t* result, size_t n, int level, int checksum, const void* dict, size_t dictSize,
                int threads)
@@ -96,12 +101,14 @@ double zlb_run(int mode, const void* src, const size_t* srcOff, const size_t* sr
     j.dstOff = dstOff; j.dstCap = dstCap; j.result = result; j.n = n; j.level = level; j.checksum = checksum;
     j.dict = dictSize ? dict : NULL; j.dictSize = dictSize; j.start = &bar;
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
+    j.tBeg = (double*)calloc((size_t)threads, sizeof(double)); j.tEnd = (double*)calloc((size_t)threads, sizeof(double));
     for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, worker, &j);
     pthread_barrier_wait(&bar);
-    double t0 = now_s();
     pthread_barrier_wait(&bar);
-    double t1 = now_s();
     for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    double t0 = j.tBeg[0], t1 = j.tEnd[0];
+    for (int t = 1; t < threads; t++) { if (j.tBeg[t] < t0) t0 = j.tBeg[t]; if (j.tEnd[t] > t1) t1 = j.tEnd[t]; }
+    free(j.tBeg); free(j.tEnd);
     free(th);
     pthread_barrier_destroy(&bar);
     return j.errors ? -1.0 : (t1 - t0);

@@ -1,0 +1,133 @@
+// TEST INFRASTRUCTURE ONLY.  CPU emulation of the CUDA compressor: the product's ZL_HD entropy logic
+// (zl_enc_entropy.cuh, zl_enc_match.cuh) compiled with g++, driven serially; the two warp-parallel kernels
+// (match candidates, greedy walk) are restated as the plain serial loops whose results they must reproduce
+// (zl_enc_match.cuh header comment).  Output must decode with the reference's libzstd; on a GPU box the tests also
+// require the CUDA path to produce byte-identical frames.  Never linked into the product.
+#include <vector>
+#include <cstring>
+#include "../../zstdlite_b200/csrc/zl_enc_entropy.cuh"
+#include "../../zstdlite_b200/csrc/zl_enc_match.cuh"
+
+static u32 rd32(const u8* p) { u32 v; memcpy(&v, p, 4); return v; }
+
+static u32 match_len_capped(const u8* src, u32 n, u32 p, i32 q)
+{
+    u32 lim = n - p; if (lim > ZL_M_CAP) lim = ZL_M_CAP;
+    u32 l = 0;
+    while (l < lim && src[p + l] == src[(u32)q + l]) l++;
+    return l;
+}
+
+// stage 1: M[p] for every position
+static void emul_match(const u8* src, u32 n, const ZlEncParams& P, std::vector<u32>& M)
+{
+    M.assign(n, 0);
+    std::vector<u16> tabS((size_t)1 << P.hlogS, 0), tabL(P.hlogL ? (size_t)1 << P.hlogL : 1, 0);
+    for (u32 p = 0; p + 8 <= n; p++) {
+        const u32 lo = rd32(src + p), hi = rd32(src + p + 4);
+        const u32 hS = zl_hash_short(lo, hi, P.mls, P.hlogS);
+        const i32 qS = zl_cand_pos(tabS[hS], p); tabS[hS] = (u16)p;
+        u32 bestLen = 0, bestOff = 0;
+        if (P.hlogL) {
+            const u32 hL = zl_hash_long(lo, hi, P.hlogL);
+            const i32 qL = zl_cand_pos(tabL[hL], p); tabL[hL] = (u16)p;
+            if (qL >= 0) { const u32 l = match_len_capped(src, n, p, qL); if (l >= P.mls) { bestLen = l; bestOff = p - (u32)qL; } }
+        }
+        if (qS >= 0) { const u32 l = match_len_capped(src, n, p, qS); if (l >= P.mls && l > bestLen) { bestLen = l; bestOff = p - (u32)qS; } }
+        M[p] = bestLen ? ((bestOff << 8) | bestLen) : 0;
+    }
+}
+// stage 2: greedy walk -> records, literals, histogram
+static void emul_parse(const u8* src, u32 n, const std::vector<u32>& M, std::vector<u64>& recs, std::vector<u8>& lit, u32* hist, bool firstBlock)
+{
+    // blocks are compressed independently: only the first block of a frame knows the decoder's repeat offsets
+    // (1, 4, 8; zstd.c:15416); later blocks start with an unknown history (0 never matches an offset)
+    ZlReps reps = {firstBlock ? 1u : 0u, firstBlock ? 4u : 0u, firstBlock ? 8u : 0u};
+    u32 p = 0, anchor = 0;
+    recs.clear(); lit.clear();
+    for (u32 i = 0; i < 256; i++) hist[i] = 0;
+    while (p < n) {
+        const u32 m = M[p];
+        if (!m) { p++; continue; }
+        u32 len = m & 0xFF; const u32 off = m >> 8;
+        if (len == ZL_M_CAP) while (p + len < n && src[p + len] == src[p + len - off]) len++;
+        const u32 ll = p - anchor;
+        for (u32 k = anchor; k < p; k++) { lit.push_back(src[k]); hist[src[k]]++; }
+        recs.push_back(zl_enc_rec(ll, len, zl_rep_encode(reps, off, ll)));
+        p += len; anchor = p;
+    }
+    for (u32 k = anchor; k < n; k++) { lit.push_back(src[k]); hist[src[k]]++; }
+}
+
+// one block -> payload bytes (without the 3-byte block header); returns 0 when the block must be stored raw
+static u32 emul_block(const u8* src, u32 n, const ZlEncParams& P, const ZlEncConst& K, std::vector<u8>& out, bool firstBlock)
+{
+    out.clear();
+    if (n < 7) return 0;                                     // zstd.c:25725
+    std::vector<u32> M; std::vector<u64> recs; std::vector<u8> lit;
+    static ZlHufSm hs; static ZlSeqEncSm ss; static ZlEncBlockOut o;
+    emul_match(src, n, P, M);
+    emul_parse(src, n, M, recs, lit, hs.count, firstBlock);
+    const u32 nLit = (u32)lit.size(), nbSeq = (u32)recs.size();
+    std::vector<u8> litPad(nLit + 16); if (nLit) memcpy(litPad.data(), lit.data(), nLit);
+    // literals kernel
+    std::vector<u32> sbuf[4];
+    zl_lit_plan(hs, o, litPad.data(), nLit);
+    if (hs.ctl.mode == 2) {
+        for (u32 q = 0; q < hs.ctl.nStreams; q++) {
+            const u32 cnt = hs.ctl.sEnd[q] - hs.ctl.sBeg[q];
+            sbuf[q].assign(cnt * 11 / 32 + 4, 0);
+            hs.ctl.sBytes[q] = zl_huf_encode_stream(hs.code, litPad.data(), hs.ctl.sBeg[q], hs.ctl.sEnd[q], sbuf[q].data(), (u32)sbuf[q].size(), &hs.ctl.ovf);
+        }
+        zl_lit_finish(hs, o);
+    }
+    // sequences kernel
+    std::vector<u32> seqBits(n / 4 + 16, 0);
+    ss.ctl.nbSeq = nbSeq;
+    o.seqBitsSize = 0;
+    if (nbSeq) {
+        for (u32 t = 0; t < 3; t++) zl_seq_build_table(ss, t, recs.data(), nbSeq, K);
+        zl_seq_write_head(ss, o);
+        u32 ovf = 0;
+        o.seqBitsSize = zl_seq_encode(ss, K, recs.data(), nbSeq, seqBits.data(), (u32)seqBits.size(), &ovf);
+        if (ovf || !o.seqBitsSize) o.flags |= 2;
+    } else zl_seq_write_head(ss, o);
+    const u32 payload = zl_enc_block_payload(o, n, nbSeq);
+    if (!payload) return 0;
+    out.insert(out.end(), o.litHead, o.litHead + o.litHeadSize);
+    if (o.litBodyMode == 1) out.insert(out.end(), lit.begin(), lit.end());
+    else if (o.litBodyMode == 2) for (u32 q = 0; q < o.nStreams; q++) { const u8* b = (const u8*)sbuf[q].data(); out.insert(out.end(), b, b + o.sBytes[q]); }
+    out.insert(out.end(), o.seqHead, o.seqHead + o.seqHeadSize);
+    { const u8* b = (const u8*)seqBits.data(); out.insert(out.end(), b, b + o.seqBitsSize); }
+    return (u32)out.size() == payload ? payload : 0xFFFFFFFFu;
+}
+
+// whole frame (zstd.c:27007 frame chunk loop, 27733 epilogue); xxh32 = low 32 bits of XXH64(content) supplied by the caller
+extern "C" size_t zl_emul_compress_frame(void* dstv, size_t cap, const void* srcv, size_t size, int level, int checksumFlag, unsigned xxh32)
+{
+    static ZlEncConst K; static bool init = false;
+    if (!init) { zl_enc_const_init(&K); init = true; }
+    const ZlEncParams P = zl_enc_params(level);
+    const u8* src = (const u8*)srcv;
+    std::vector<u8> frame(32);
+    frame.resize(zl_write_frame_header(frame.data(), size, 0, checksumFlag ? 1u : 0u));
+    size_t pos = 0; bool first = true;
+    std::vector<u8> payload;
+    do {
+        const u32 n = (u32)(size - pos < ZL_BLOCKSIZE_MAX ? size - pos : ZL_BLOCKSIZE_MAX);
+        const u32 last = pos + n == size ? 1u : 0u;
+        u8 bh[3];
+        bool rle = n > 0 && !first;
+        for (u32 i = 1; rle && i < n; i++) if (src[pos + i] != src[pos]) rle = false;
+        u32 ps = rle ? 0 : emul_block(src + pos, n, P, K, payload, first);
+        if (ps == 0xFFFFFFFFu) return (size_t)0 - 1;
+        if (rle) { zl_write_block_header(bh, last, 1, n); frame.insert(frame.end(), bh, bh + 3); frame.push_back(src[pos]); }
+        else if (!ps) { zl_write_block_header(bh, last, 0, n); frame.insert(frame.end(), bh, bh + 3); frame.insert(frame.end(), src + pos, src + pos + n); }
+        else { zl_write_block_header(bh, last, 2, ps); frame.insert(frame.end(), bh, bh + 3); frame.insert(frame.end(), payload.begin(), payload.end()); }
+        pos += n; first = false;
+    } while (pos < size);
+    if (checksumFlag) for (u32 i = 0; i < 4; i++) frame.push_back((u8)(xxh32 >> (8 * i)));
+    if (frame.size() > cap) return (size_t)0 - 70;
+    memcpy(dstv, frame.data(), frame.size());
+    return frame.size();
+}

@@ -11,11 +11,13 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        srcs = [os.path.join(_HERE, "emul", "emul_decode.cpp")]
+        srcs = [os.path.join(_HERE, "emul", "emul_decode.cpp"), os.path.join(_HERE, "emul", "emul_encode.cpp")]
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-Wno-unused-function", "-o", _SO] + srcs)
         L = C.CDLL(_SO)
         L.zl_emul_decompress_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint)]
         L.zl_emul_decompress_frame.restype = C.c_size_t
+        L.zl_emul_compress_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint]
+        L.zl_emul_compress_frame.restype = C.c_size_t
         _lib = L
     return _lib
 
@@ -25,6 +27,17 @@ def decompress_frame(c, cap):
     dst = C.create_string_buffer(cap + 8)
     n = C.c_uint(0)
     r = lib().zl_emul_decompress_frame(dst, cap, bytes(c), len(c), C.byref(n))
+    if r > 2**63:
+        return ("ERR", 2**64 - r)
+    return dst.raw[:r]
+
+
+def compress_frame(data, level=3, checksum=False, xxh32=0):
+    """CPU emulation of the CUDA compressor -> one frame (bytes), or ('ERR', code)."""
+    data = bytes(data)
+    cap = len(data) + (len(data) >> 7) + 1024
+    dst = C.create_string_buffer(cap)
+    r = lib().zl_emul_compress_frame(dst, cap, data, len(data), level, 1 if checksum else 0, xxh32)
     if r > 2**63:
         return ("ERR", 2**64 - r)
     return dst.raw[:r]

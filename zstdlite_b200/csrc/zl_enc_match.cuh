@@ -1,0 +1,119 @@
+// zl_enc_match.cuh -- match-finder definitions shared by the CUDA kernels (zl_enc_kernels.cu), the host API and the
+// CPU emulation in tests/emul.
+//
+// The B200 match finder is NOT a transcription of ZSTD_compressBlock_fast / _doubleFast (zstd.c:30724, 29909); it
+// keeps their ingredients -- a short hash of `mls` bytes and (level 3) a second, long hash of 8 bytes, both with the
+// reference's multiplicative hash (zstd.c:19809-19841) -- but restructures the search for a SIMT machine:
+//   stage 1 (data-parallel): EVERY position is inserted and looks up the nearest earlier position with the same
+//            hash in each table; the candidate is verified and its length measured (capped at ZL_M_CAP);
+//            result: one u32 per position, M[p] = offset << 8 | length (0 = no match of at least minLen bytes);
+//   stage 2 (greedy walk): from p = 0, jump to the next position with M[p] != 0, take that match (extending it past
+//            the cap by direct comparison), continue after it.  Repeat-offset codes are assigned while walking
+//            (zstd.c:19648-19652, ZSTD_updateRep 19688).
+// Tables hold the low 16 bits of positions (blocks are <= 128 KiB): a candidate is rebuilt as the latest position
+// <= p with those low bits, so offsets are limited to 65,535 and stale or never-written entries are harmless
+// because every candidate is verified against the input.
+#pragma once
+#include "zl_common.cuh"
+
+#define ZL_M_CAP 255u
+
+struct ZlEncParams {       // derived from the compression level by zl_enc_params()
+    u32 level;
+    u32 mls;               // bytes hashed by the short table (also the minimum match length)
+    u32 hlogS;             // log2 entries of the short table
+    u32 hlogL;             // log2 entries of the long (8-byte) table, 0 = no long table
+};
+// levels map onto three table layouts (cf. the reference's rows for <= 128 KB inputs, zstd.c:29579-29582):
+//   1: fast-like   short 2^14            (32 KB of u16)
+//   2: fast-like   short 2^15            (64 KB)
+//   3: dfast-like  short 2^14 + long 2^15 (96 KB)
+static inline ZlEncParams zl_enc_params(int level)
+{
+    ZlEncParams p;
+    p.level = (u32)level; p.mls = 5;
+    if (level <= 1) { p.hlogS = 14; p.hlogL = 0; }
+    else if (level == 2) { p.hlogS = 15; p.hlogL = 0; }
+    else { p.hlogS = 14; p.hlogL = 15; }
+    return p;
+}
+
+ZL_HD u32 zl_hash_short(u32 lo, u32 hi, u32 mls, u32 hlog)
+{
+    const u64 v = ((u64)hi << 32) | lo;
+    if (mls == 4) return (lo * 2654435761u) >> (32 - hlog);
+    if (mls == 5) return (u32)(((v << 24) * 889523592379ULL) >> (64 - hlog));
+    return (u32)(((v << 16) * 227718039650203ULL) >> (64 - hlog));
+}
+ZL_HD u32 zl_hash_long(u32 lo, u32 hi, u32 hlog)
+{
+    const u64 v = ((u64)hi << 32) | lo;
+    return (u32)((v * 0xCF1BBCDCB7A56463ULL) >> (64 - hlog));
+}
+// candidate position from a 16-bit table entry: the latest position < p whose low 16 bits are e (-1 if none)
+ZL_HD i32 zl_cand_pos(u32 e, u32 p)
+{
+    i32 q = (i32)((p & ~0xFFFFu) | e);
+    if (q >= (i32)p) q -= 65536;
+    return q;
+}
+// number of equal leading bytes of two 8-byte little-endian words (8 when identical)
+ZL_HD u32 zl_common8(u32 alo, u32 ahi, u32 blo, u32 bhi)
+{
+    const u32 xl = alo ^ blo, xh = ahi ^ bhi;
+#if defined(__CUDA_ARCH__)
+    if (xl) return (u32)(__ffs((int)xl) - 1) >> 3;
+    if (xh) return 4 + ((u32)(__ffs((int)xh) - 1) >> 3);
+#else
+    if (xl) return (u32)__builtin_ctz(xl) >> 3;
+    if (xh) return 4 + ((u32)__builtin_ctz(xh) >> 3);
+#endif
+    return 8;
+}
+
+// repeat-offset bookkeeping while walking (zstd.c:19648-19652 offBase, 19688 ZSTD_updateRep): returns offBase
+struct ZlReps { u32 r0, r1, r2; };
+ZL_HD u32 zl_rep_encode(ZlReps& r, u32 off, u32 ll)
+{
+    u32 ob;
+    if (ll) {
+        if (off == r.r0) ob = 1; else if (off == r.r1) ob = 2; else if (off == r.r2) ob = 3; else ob = off + 3;
+        if (ob == 2) { const u32 t = r.r1; r.r1 = r.r0; r.r0 = t; }
+        else if (ob == 3) { const u32 t = r.r2; r.r2 = r.r1; r.r1 = r.r0; r.r0 = t; }
+        else if (ob > 3) { r.r2 = r.r1; r.r1 = r.r0; r.r0 = off; }
+    } else {                                        // litLength == 0 shifts the meaning of the codes (zstd.c:44311-44324)
+        if (off == r.r1) ob = 1; else if (off == r.r2) ob = 2; else if (off == r.r0 - 1 && off) ob = 3; else ob = off + 3;
+        if (ob == 1) { const u32 t = r.r1; r.r1 = r.r0; r.r0 = t; }
+        else { r.r2 = r.r1; r.r1 = r.r0; r.r0 = off; }                   // codes 2 (old r2), 3 (r0 - 1) and new offsets all push the history
+    }
+    return ob;
+}
+
+// ---- frame / block headers (zstd.c:27089-27135 ZSTD_writeFrameHeader, 19580 block header) ------------------------
+// Frames of <= 128 KiB are single-segment like the reference's (window >= content).  Larger inputs are written as one
+// frame of independent 128 KiB blocks with a 128 KiB window descriptor: nothing ever refers back across a block.
+ZL_HD u32 zl_write_frame_header(u8* dst, u64 contentSize, u32 dictID, u32 checksumFlag)
+{
+    const u32 single = contentSize <= ZL_BLOCKSIZE_MAX ? 1u : 0u;
+    const u32 didCode = dictID == 0 ? 0u : (dictID < 256 ? 1u : (dictID < 65536 ? 2u : 3u));
+    u32 fcsCode;
+    if (single) fcsCode = contentSize >= 256 ? (contentSize >= 65536 + 256 ? 2u : 1u) : 0u;
+    else fcsCode = contentSize >= 0xFFFFFFFFull ? 3u : 2u;
+    u32 p = 0;
+    dst[p++] = 0x28; dst[p++] = 0xB5; dst[p++] = 0x2F; dst[p++] = 0xFD;
+    dst[p++] = (u8)(didCode | (checksumFlag << 2) | (single << 5) | (fcsCode << 6));
+    if (!single) dst[p++] = (u8)((17 - 10) << 3);
+    if (didCode == 1) dst[p++] = (u8)dictID;
+    else if (didCode == 2) { dst[p++] = (u8)dictID; dst[p++] = (u8)(dictID >> 8); }
+    else if (didCode == 3) { for (u32 i = 0; i < 4; i++) dst[p++] = (u8)(dictID >> (8 * i)); }
+    if (fcsCode == 0) { if (single) dst[p++] = (u8)contentSize; }
+    else if (fcsCode == 1) { const u32 v = (u32)contentSize - 256; dst[p++] = (u8)v; dst[p++] = (u8)(v >> 8); }
+    else if (fcsCode == 2) { for (u32 i = 0; i < 4; i++) dst[p++] = (u8)(contentSize >> (8 * i)); }
+    else { for (u32 i = 0; i < 8; i++) dst[p++] = (u8)(contentSize >> (8 * i)); }
+    return p;
+}
+ZL_HD void zl_write_block_header(u8* dst, u32 last, u32 type, u32 size)
+{
+    const u32 v = last | (type << 1) | (size << 3);
+    dst[0] = (u8)v; dst[1] = (u8)(v >> 8); dst[2] = (u8)(v >> 16);
+}
