@@ -117,12 +117,11 @@ extern "C" size_t zl_emul_compress_frame(void* dstv, size_t cap, const void* src
         const u32 n = (u32)(size - pos < ZL_BLOCKSIZE_MAX ? size - pos : ZL_BLOCKSIZE_MAX);
         const u32 last = pos + n == size ? 1u : 0u;
         u8 bh[3];
-        bool rle = n > 0 && !first;
-        for (u32 i = 1; rle && i < n; i++) if (src[pos + i] != src[pos]) rle = false;
-        u32 ps = rle ? 0 : emul_block(src + pos, n, P, K, payload, first);
+        // (no RLE blocks: the reference only emits them for non-first blocks under 25 bytes of output, zstd.c:26873-26884;
+        //  a run compresses to ~10 bytes as one sequence, so the product skips the special case)
+        u32 ps = emul_block(src + pos, n, P, K, payload, first);
         if (ps == 0xFFFFFFFFu) return (size_t)0 - 1;
-        if (rle) { zl_write_block_header(bh, last, 1, n); frame.insert(frame.end(), bh, bh + 3); frame.push_back(src[pos]); }
-        else if (!ps) { zl_write_block_header(bh, last, 0, n); frame.insert(frame.end(), bh, bh + 3); frame.insert(frame.end(), src + pos, src + pos + n); }
+        if (!ps) { zl_write_block_header(bh, last, 0, n); frame.insert(frame.end(), bh, bh + 3); frame.insert(frame.end(), src + pos, src + pos + n); }
         else { zl_write_block_header(bh, last, 2, ps); frame.insert(frame.end(), bh, bh + 3); frame.insert(frame.end(), payload.begin(), payload.end()); }
         pos += n; first = false;
     } while (pos < size);

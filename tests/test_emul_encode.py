@@ -1,0 +1,58 @@
+"""CPU tests of the compressor's entropy/format logic: the product's ZL_HD source (zl_enc_entropy.cuh, zl_enc_match.cuh)
+compiled with g++ and driven serially (tests/emul/emul_encode.cpp).  Every frame must decode with the reference's
+libzstd and the C restatement to the original bytes; ratio within 3% of libzstd at the same level (the north-star bar).
+The -m gpu tests then require the CUDA kernels to reproduce these frames byte for byte."""
+import numpy as np
+import pytest
+
+
+@pytest.mark.parametrize("family", ["text", "rdf", "lowent", "rand", "rle"])
+def test_emulated_frames_decode_with_libzstd(ref, restate, family):
+    from zstdlite_b200 import corpus
+    from tests import emul_util
+    for size in (0, 1, 6, 7, 8, 50, 255, 256, 1023, 1024, 5000, 16384, 65536, 131072, 131073, 300000):
+        d = corpus.make(family, size, 3).tobytes()
+        for lvl in (1, 2, 3):
+            for ck in (False, True):
+                c = emul_util.compress_frame(d, lvl, ck, restate.xxh64(d) & 0xFFFFFFFF)
+                assert not isinstance(c, tuple), (family, size, lvl, c)
+                assert len(c) <= ref.lib().ZSTD_compressBound(size)
+                assert ref.decompress(c) == d, (family, size, lvl, ck)
+                assert restate.decompress(c, size) == d
+                assert emul_util.decompress_frame(c, size) == d           # and the emulated CUDA decoder
+
+
+def test_emulated_ratio_within_3_percent(ref):
+    from zstdlite_b200 import corpus
+    from tests import emul_util
+    for fam in ("text", "rdf", "lowent"):
+        for fb in (65536, 131072):
+            bufs = [corpus.make(fam, fb, 40 + i).tobytes() for i in range(6)]
+            for lvl in (1, 3):
+                ours = sum(len(emul_util.compress_frame(b, lvl)) for b in bufs)
+                theirs = sum(len(ref.compress(b, lvl)) for b in bufs)
+                assert ours <= theirs * 1.03, (fam, fb, lvl, ours, theirs)
+
+
+def test_odd_inputs(ref):
+    """few symbols, skewed histograms (depth-limited Huffman), long runs, tiny alphabets, binary ramps"""
+    from tests import emul_util
+    rng = np.random.default_rng(77)
+    cases = [bytes([7]) * 100000, bytes(range(256)) * 300, b"ab" * 40000, b"\x00" * 70000 + b"\x01" * 70000,
+             rng.choice(np.arange(256, dtype=np.uint8), 90000, p=np.array([0.5 ** min(i + 1, 40) for i in range(256)]) / sum(0.5 ** min(i + 1, 40) for i in range(256))).tobytes(),
+             rng.integers(0, 2, 50000, dtype=np.uint8).tobytes(), rng.integers(0, 256, 777, dtype=np.uint8).tobytes() * 90,
+             np.repeat(rng.integers(0, 256, 3000, dtype=np.uint8), rng.integers(1, 90, 3000)).tobytes()]
+    for d in cases:
+        for lvl in (1, 3):
+            c = emul_util.compress_frame(d, lvl, True, 0)
+            assert ref.DCtx(validate_checksum=False).decompress(c) == d
+
+
+def test_frame_header_layout_matches_reference(ref):
+    """single-segment header bytes equal libzstd's for <= 128 KiB inputs (zstd.c:27089-27135)"""
+    from tests import emul_util
+    for size in (0, 1, 255, 256, 65535, 65536, 65791, 65792, 131072):
+        d = bytes(size)
+        ours, theirs = emul_util.compress_frame(d, 3), ref.compress(d, 3)
+        hs = 5 + (1 if size < 256 else 2 if size < 65792 else 4)
+        assert ours[:hs] == theirs[:hs], size

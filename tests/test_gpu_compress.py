@@ -1,0 +1,128 @@
+"""-m gpu parity tests for the CUDA compressor, through the C ABI (ZSTD_compress2 / zl_compress_batch / zl_compress_split).
+
+Bar (BASELINE.json north_star): every GPU-compressed stream decodes with the reference's libzstd to byte-identical
+input; compression ratio within 3% of the reference at the same level on the same framing.  In addition the CUDA
+path must reproduce the CPU emulation of its own algorithm (tests/emul, same ZL_HD source) byte for byte."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def z():
+    import torch
+    assert torch.cuda.is_available()
+    import zstdlite_b200 as zz
+    return zz
+
+
+def _gpu_compress_batch(z, bufs, level, checksum=False, device=True, caps=None):
+    import torch
+    from tests.gpu_util import to_dev
+    L = z._lib.lib()
+    cctx = z.zstd_cctx(level=level, include_checksum=checksum)
+    caps = caps or [L.ZSTD_compressBound(len(b)) for b in bufs]
+    if device:
+        offs = np.concatenate([[0], np.cumsum([len(b) for b in bufs])]).astype(np.int64)
+        src = to_dev(np.frombuffer(b"".join(bufs), dtype=np.uint8))
+        doffs = np.concatenate([[0], np.cumsum([(c + 15) // 16 * 16 for c in caps])]).astype(np.int64)
+        dst = torch.zeros(int(doffs[-1]) + 64, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        res = z.compress_batch(cctx, [src.data_ptr() + int(o) for o in offs[:-1]], [len(b) for b in bufs],
+                               [dst.data_ptr() + int(o) for o in doffs[:-1]], list(caps), device=True)
+        host = dst.cpu().numpy()
+        return res, [host[int(doffs[i]):int(doffs[i]) + res[i]].tobytes() if not z.is_error(res[i]) else None for i in range(len(bufs))]
+    sb = [C.create_string_buffer(bytes(b), max(1, len(b))) for b in bufs]
+    db = [C.create_string_buffer(max(1, c)) for c in caps]
+    res = z.compress_batch(cctx, [C.addressof(b) for b in sb], [len(b) for b in bufs], [C.addressof(b) for b in db], list(caps), device=False)
+    return res, [db[i].raw[:res[i]] if not z.is_error(res[i]) else None for i in range(len(bufs))]
+
+
+@pytest.mark.parametrize("family", ["text", "rdf", "lowent", "rand", "rle"])
+def test_round_trip_and_emulation_parity(z, ref, restate, family):
+    from zstdlite_b200 import corpus
+    from tests import emul_util
+    sizes = (0, 1, 6, 7, 8, 9, 63, 64, 300, 4095, 4096, 65536, 131071, 131072, 131073, 400000)
+    bufs = [corpus.make(family, s, 13).tobytes() for s in sizes]
+    for lvl in (1, 2, 3):
+        for ck in (False, True):
+            res, outs = _gpu_compress_batch(z, bufs, lvl, ck)
+            for d, r, c in zip(bufs, res, outs):
+                assert not z.is_error(r), (len(d), lvl, z.error_name(r))
+                assert len(c) <= ref.lib().ZSTD_compressBound(len(d))
+                assert ref.decompress(c) == d, (family, len(d), lvl, ck)                  # libzstd accepts it
+                assert restate.decompress(c, len(d)) == d
+                want = emul_util.compress_frame(d, lvl, ck, restate.xxh64(d) & 0xFFFFFFFF)
+                assert c == want, (family, len(d), lvl, ck, "CUDA output differs from the CPU emulation of the same algorithm")
+    # our own decoder reads them back too
+    from tests.gpu_util import gpu_decompress_batch
+    res2, back = gpu_decompress_batch(outs, [len(b) for b in bufs])
+    assert back == bufs
+
+
+def test_one_shot_api_like_the_reference_tests(z, ref):
+    """tests/testthat/test-compress-raw.R, test-cctx.R (determinism), test-checksums.R (+4 bytes)"""
+    from zstdlite_b200 import corpus
+    d = corpus.make("text", 300000, 2).tobytes() + corpus.make("rdf", 300000, 2).tobytes()
+    a = z.zstd_compress(d)
+    assert ref.decompress(a) == d and z.zstd_decompress(a) == d
+    assert z.zstd_info(a)["uncompressed_size"] == len(d) and z.zstd_info(a)["compressed_size"] == len(a)
+    cctx = z.zstd_cctx(level=3)
+    assert z.zstd_compress(d, cctx=cctx) == a and z.zstd_compress(d, cctx=cctx) == a              # reused context, twice
+    assert z.zstd_compress(d, num_threads=2) == a                                               # nbWorkers is a hint
+    ck = z.zstd_compress(d, include_checksum=True)
+    assert len(ck) == len(a) + 4 and ref.decompress(ck) == d
+    bad = bytearray(ck); bad[-1] ^= 0xFF
+    with pytest.raises(z.ZstdError, match="doesn't match checksum"):
+        z.zstd_decompress(bytes(bad))
+    assert z.zstd_compress("héllo wörld" * 50) and z.zstd_decompress(z.zstd_compress("héllo wörld" * 50), type="string") == "héllo wörld" * 50
+    assert z.zstd_cctx(level=1, num_threads=3, include_checksum=True).settings() == {"level": 1, "num_threads": 3, "include_checksum": 1}
+    for lvl in (-5, 0, 9, 22):                        # outside 1..3: nearest engine, still a valid frame
+        assert ref.decompress(z.zstd_compress(d[:50000], level=lvl)) == d[:50000]
+
+
+def test_destination_too_small(z):
+    from zstdlite_b200 import corpus
+    d = corpus.make("rand", 50000, 1).tobytes()
+    res, outs = _gpu_compress_batch(z, [d, d], 3, caps=[1000, 60000])
+    assert z.is_error(res[0]) and z.error_name(res[0]) == "Destination buffer is too small"
+    assert not z.is_error(res[1])
+
+
+def test_batch_ratio_vs_reference(z, ref):
+    """configs[2] shape at reduced count: 128 KiB slabs, levels 1 and 3, ratio vs libzstd on the same slabs"""
+    from zstdlite_b200 import corpus
+    for fam in ("text", "rdf", "lowent"):
+        bufs = [corpus.make(fam, 131072, 100 + i).tobytes() for i in range(24)]
+        for lvl in (1, 3):
+            res, outs = _gpu_compress_batch(z, bufs, lvl)
+            ours = sum(len(c) for c in outs)
+            theirs = sum(len(ref.compress(b, lvl)) for b in bufs)
+            for b, c in zip(bufs, outs):
+                assert ref.decompress(c) == b
+            assert ours <= theirs * 1.03, (fam, lvl, ours, theirs)
+    # host-pointer path gives the same bytes
+    res_h, outs_h = _gpu_compress_batch(z, bufs[:6], 3, device=False)
+    assert outs_h == outs[:6]
+
+
+def test_compress_split_is_a_standard_multi_frame_stream(z, ref):
+    from zstdlite_b200 import corpus
+    L = z._lib.lib()
+    d = corpus.make("text", 1_000_000, 4).tobytes() + corpus.make("rand", 100_000, 4).tobytes()
+    cctx = z.zstd_cctx(level=3, include_checksum=True)
+    cap = len(d) + len(d) // 64 + 4096
+    dst = C.create_string_buffer(cap)
+    nf = (len(d) + 131071) // 131072
+    fsz = (C.c_size_t * nf)()
+    r = L.zl_compress_split(cctx._p, dst, cap, d, len(d), 131072, fsz, 0)
+    assert not z.is_error(r), z.error_name(r)
+    assert sum(fsz) == r
+    blob = dst.raw[:r]
+    assert ref.DCtx().decompress(blob, cap=len(d), all_frames=True) == d
+    out = C.create_string_buffer(len(d))
+    rr = L.ZSTD_decompressDCtx(z.zstd_dctx()._p, out, len(d), blob, len(blob))
+    assert rr == len(d) and out.raw == d

@@ -1,0 +1,351 @@
+// zl_api_compress.cu -- compression half of the C ABI (include/zstdlite_gpu.h): ZSTD_CCtx lifecycle and parameters
+// (call sites: /root/reference/src/cctx.c:205-312,352-354), ZSTD_compressBound / ZSTD_compress2 (src/raw-file.c:52,74;
+// src/serialize.c:73,91), and the batch / split extensions.  All compute runs in the kernels of zl_enc_kernels.cu.
+#include <stdio.h>
+#include <stdlib.h>
+#include <new>
+#include "../../include/zstdlite_gpu.h"
+#include "zl_host.h"
+
+#define ZL_EXPORT extern "C" __attribute__((visibility("default")))
+#define ZL_ALIAS(ret, name, params) extern "C" __attribute__((visibility("default"), alias(#name))) ret zlg_##name params;
+
+#define ZL_WAVE_BLOCKS 8192u          // blocks per launch wave (bounds the scratch arenas: ~0.9 MB per 128 KiB block)
+
+struct ZSTD_CCtx_s {
+    int level = 3, nbWorkers = 0, checksumFlag = 0, stableIn = 0, stableOut = 0;
+    unsigned long long pledged = ZSTD_CONTENTSIZE_UNKNOWN;
+    std::vector<u8> dictRaw;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t stageEv[ZL_ENC_STAGES + 1] = {};
+    double lastKernelMs = 0.0, lastStageMs[ZL_ENC_STAGES] = {};
+    unsigned long long launches = 0;
+    ZlDevBuf dBlocks, dFrames, dM, dRecs, dLit, dHist, dMetas, dOuts, dPlans, dResults, dXxh, dXxhPtrs, dXxhSizes, dSrc, dDst, dAux;
+    ZlPinBuf hBlocks, hFrames, hResults, hAux;
+};
+
+static bool g_constReady = false;
+
+static bool zl_cctx_ready(ZSTD_CCtx* c)
+{
+    if (!c->stream && !c->ownStream) {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        c->ownStream = true;
+    }
+    if (!c->ev0) {
+        if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        for (cudaEvent_t& e : c->stageEv) if (cudaEventCreate(&e) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    }
+    if (!g_constReady) {
+        if (zl_enc_upload_const() != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        g_constReady = true;
+    }
+    return true;
+}
+
+ZL_EXPORT ZSTD_CCtx* ZSTD_createCCtx(void) { return new (std::nothrow) ZSTD_CCtx_s(); }
+ZL_EXPORT size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
+{
+    if (!c) return 0;
+    ZlDevBuf* bufs[] = {&c->dBlocks, &c->dFrames, &c->dM, &c->dRecs, &c->dLit, &c->dHist, &c->dMetas, &c->dOuts, &c->dPlans, &c->dResults,
+                        &c->dXxh, &c->dXxhPtrs, &c->dXxhSizes, &c->dSrc, &c->dDst, &c->dAux};
+    for (ZlDevBuf* b : bufs) b->release();
+    c->hBlocks.release(); c->hFrames.release(); c->hResults.release(); c->hAux.release();
+    if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
+    for (cudaEvent_t e : c->stageEv) if (e) cudaEventDestroy(e);
+    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+ZL_EXPORT size_t ZSTD_CCtx_reset(ZSTD_CCtx* c, ZSTD_ResetDirective r)          // zstd.c:23872
+{
+    if (r == ZSTD_reset_session_only || r == ZSTD_reset_session_and_parameters) c->pledged = ZSTD_CONTENTSIZE_UNKNOWN;
+    if (r == ZSTD_reset_parameters || r == ZSTD_reset_session_and_parameters) {
+        c->level = 3; c->nbWorkers = 0; c->checksumFlag = 0; c->stableIn = 0; c->stableOut = 0; c->dictRaw.clear();
+    }
+    return 0;
+}
+ZL_EXPORT size_t ZSTD_CCtx_setParameter(ZSTD_CCtx* c, ZSTD_cParameter p, int v)           // zstd.c:23223 (bounds: 22900-23100)
+{
+    switch ((int)p) {
+    case ZSTD_c_compressionLevel:                        // clamped, not rejected (ZSTD_cParam_clampBounds); 0 means default
+        if (v < -131072) v = -131072;
+        if (v > 22) v = 22;
+        c->level = v == 0 ? 3 : v;
+        return 0;
+    case ZSTD_c_nbWorkers: if (v < 0) v = 0; if (v > 256) v = 256; c->nbWorkers = v; return 0;
+    case ZSTD_c_checksumFlag: if (v < 0 || v > 1) return ZL_ERROR(parameter_outOfBound); c->checksumFlag = v; return 0;
+    case ZSTD_c_stableInBuffer: if (v < 0 || v > 1) return ZL_ERROR(parameter_outOfBound); c->stableIn = v; return 0;
+    case ZSTD_c_stableOutBuffer: if (v < 0 || v > 1) return ZL_ERROR(parameter_outOfBound); c->stableOut = v; return 0;
+    default: return ZL_ERROR(parameter_unsupported);
+    }
+}
+ZL_EXPORT size_t ZSTD_CCtx_getParameter(const ZSTD_CCtx* c, ZSTD_cParameter p, int* v)
+{
+    switch ((int)p) {
+    case ZSTD_c_compressionLevel: *v = c->level; return 0;
+    case ZSTD_c_nbWorkers: *v = c->nbWorkers; return 0;
+    case ZSTD_c_checksumFlag: *v = c->checksumFlag; return 0;
+    case ZSTD_c_stableInBuffer: *v = c->stableIn; return 0;
+    case ZSTD_c_stableOutBuffer: *v = c->stableOut; return 0;
+    default: return ZL_ERROR(parameter_unsupported);
+    }
+}
+ZL_EXPORT size_t ZSTD_CCtx_setPledgedSrcSize(ZSTD_CCtx* c, unsigned long long pledged) { c->pledged = pledged; return 0; }
+// Copies the dictionary (zstd.c:23826).  The compressor does not reference dictionary content yet: frames are written
+// without a dictID and decode with or without the dictionary loaded ("dictionary mode").
+ZL_EXPORT size_t ZSTD_CCtx_loadDictionary(ZSTD_CCtx* c, const void* dict, size_t dictSize)
+{
+    c->dictRaw.clear();
+    if (dict && dictSize) c->dictRaw.assign((const u8*)dict, (const u8*)dict + dictSize);
+    return 0;
+}
+ZL_EXPORT size_t zl_cctx_set_stream(ZSTD_CCtx* c, void* s)
+{
+    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)s; c->ownStream = false;
+    return 0;
+}
+ZL_EXPORT unsigned long long zl_cctx_launch_count(const ZSTD_CCtx* c) { return c->launches; }
+ZL_EXPORT double zl_cctx_last_kernel_ms(const ZSTD_CCtx* c) { return c->lastKernelMs; }
+ZL_EXPORT double zl_cctx_last_stage_ms(const ZSTD_CCtx* c, int stage) { return stage >= 0 && stage < ZL_ENC_STAGES ? c->lastStageMs[stage] : -1.0; }
+
+ZL_EXPORT size_t ZSTD_compressBound(size_t n)                      // zstd.c:22583 / macro 4548
+{
+    if (n >= 0xFF00FF00FF00FF00ull) return ZL_ERROR(srcSize_wrong);
+    return n + (n >> 8) + (n < (128u << 10) ? (((128u << 10) - n) >> 11) : 0);
+}
+ZL_ALIAS(ZSTD_CCtx*, ZSTD_createCCtx, (void))
+ZL_ALIAS(size_t, ZSTD_freeCCtx, (ZSTD_CCtx*))
+ZL_ALIAS(size_t, ZSTD_CCtx_reset, (ZSTD_CCtx*, ZSTD_ResetDirective))
+ZL_ALIAS(size_t, ZSTD_CCtx_setParameter, (ZSTD_CCtx*, ZSTD_cParameter, int))
+ZL_ALIAS(size_t, ZSTD_CCtx_getParameter, (const ZSTD_CCtx*, ZSTD_cParameter, int*))
+ZL_ALIAS(size_t, ZSTD_CCtx_setPledgedSrcSize, (ZSTD_CCtx*, unsigned long long))
+ZL_ALIAS(size_t, ZSTD_CCtx_loadDictionary, (ZSTD_CCtx*, const void*, size_t))
+ZL_ALIAS(size_t, ZSTD_compressBound, (size_t))
+
+// The level selects one of three table layouts (zl_enc_match.cuh).  Levels below 1 run the level-1 engine and levels
+// above 3 the level-3 engine: still valid Zstandard, without the higher levels' ratio ("levels").
+static int zl_engine_level(int level) { return level < 1 ? 1 : (level > 3 ? 3 : level); }
+
+// ---- one wave: frames [f0, f1) with DEVICE src/dst pointers; asynchronous on the context's stream.
+// results land in c->dResults[f0..f1).
+static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* srcSize, u8* const* ddst, const size_t* dstCap, size_t f0, size_t f1,
+                          size_t nbTotalFrames, bool timeIt)
+{
+    cudaStream_t st = c->stream;
+    const size_t nf = f1 - f0;
+    size_t nb = 0; u32 maxBlock = 0;
+    for (size_t i = f0; i < f1; i++) {
+        const size_t s = srcSize[i];
+        nb += s ? (s + ZL_BLOCKSIZE_MAX - 1) / ZL_BLOCKSIZE_MAX : 1;
+        const u32 mb = (u32)(s < ZL_BLOCKSIZE_MAX ? s : ZL_BLOCKSIZE_MAX);
+        if (mb > maxBlock) maxBlock = mb;
+    }
+    if (nb > 0x3FFFFFFFull) return ZL_ERROR(memory_allocation);
+    const u32 S = ((maxBlock < 256 ? 256 : maxBlock) + 255) & ~255u;
+    const u32 slotM = S, slotRec = S / 5 + 8, slotLit = S + 16;
+    const u32 streamCapWords = (((S / 4 + 1) * 11) / 8 + 16 + 3) / 4, streamWordsPerBlock = 4 * streamCapWords, seqCapWords = S / 4;
+    if (!c->hBlocks.reserve(nb * sizeof(ZlEncBlock)) || !c->hFrames.reserve(nf * sizeof(ZlEncFrame))) return ZL_ERROR(memory_allocation);
+    if (!c->dBlocks.reserve(nb * sizeof(ZlEncBlock)) || !c->dFrames.reserve(nf * sizeof(ZlEncFrame)) || !c->dM.reserve(nb * (size_t)slotM * 4) ||
+        !c->dRecs.reserve(nb * (size_t)slotRec * 8) || !c->dLit.reserve(nb * (size_t)slotLit) || !c->dHist.reserve(nb * 1024) ||
+        !c->dMetas.reserve(nb * sizeof(ZlEncBlockMeta)) || !c->dOuts.reserve(nb * sizeof(ZlEncBlockOut)) || !c->dPlans.reserve(nb * sizeof(ZlEncBlockPlan)) ||
+        !c->dResults.reserve(nbTotalFrames * 8))
+        return ZL_ERROR(memory_allocation);
+    ZlEncBlock* hb = c->hBlocks.as<ZlEncBlock>();
+    ZlEncFrame* hf = c->hFrames.as<ZlEncFrame>();
+    size_t bi = 0;
+    for (size_t i = f0; i < f1; i++) {
+        ZlEncFrame& f = hf[i - f0];
+        memset(&f, 0, sizeof(f));
+        const size_t s = srcSize[i];
+        f.dst = ddst[i]; f.dstCap = dstCap[i]; f.firstBlock = (u32)bi; f.checksumFlag = (u32)c->checksumFlag;
+        f.hdrSize = zl_write_frame_header(f.hdr, s, 0, (u32)c->checksumFlag);
+        const size_t nblk = s ? (s + ZL_BLOCKSIZE_MAX - 1) / ZL_BLOCKSIZE_MAX : 1;
+        f.nblocks = (u32)nblk;
+        for (size_t k = 0; k < nblk; k++) {
+            ZlEncBlock& b = hb[bi++];
+            b.src = dsrc[i] + k * ZL_BLOCKSIZE_MAX;
+            const size_t rem = s - k * ZL_BLOCKSIZE_MAX;
+            b.srcSize = (u32)(rem < ZL_BLOCKSIZE_MAX ? rem : ZL_BLOCKSIZE_MAX);
+            b.frame = (u32)(i - f0);
+            b.flags = (k == 0 ? ZL_BLK_FIRST : 0u) | (k + 1 == nblk ? ZL_BLK_LAST : 0u);
+            b.pad = 0;
+        }
+    }
+    cudaMemcpyAsync(c->dBlocks.p, hb, nb * sizeof(ZlEncBlock), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(c->dFrames.p, hf, nf * sizeof(ZlEncFrame), cudaMemcpyHostToDevice, st);
+    const u64* xxh = nullptr;
+    if (c->checksumFlag) {                                        // XXH64 of every frame's content (zstd.c:27022-27023)
+        if (!c->hAux.reserve(nf * 16) || !c->dXxhPtrs.reserve(nf * 8) || !c->dXxhSizes.reserve(nf * 4) || !c->dXxh.reserve(nf * 8)) return ZL_ERROR(memory_allocation);
+        const u8** hp = c->hAux.as<const u8*>();
+        u32* hs = reinterpret_cast<u32*>(hp + nf);
+        for (size_t i = f0; i < f1; i++) { hp[i - f0] = dsrc[i]; hs[i - f0] = (u32)srcSize[i]; }
+        cudaMemcpyAsync(c->dXxhPtrs.p, hp, nf * 8, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(c->dXxhSizes.p, hs, nf * 4, cudaMemcpyHostToDevice, st);
+        if (zl_launch_xxh64(c->dXxhPtrs.as<const u8*>(), c->dXxhSizes.as<u32>(), c->dXxh.as<u64>(), (u32)nf, st) != cudaSuccess) return ZL_ERROR(GENERIC);
+        c->launches += 1;
+        xxh = c->dXxh.as<u64>();
+    }
+    ZlEncodeLaunch L;
+    L.blocks = c->dBlocks.as<ZlEncBlock>(); L.nblocks = (u32)nb; L.frames = c->dFrames.as<ZlEncFrame>(); L.nframes = (u32)nf;
+    L.params = zl_enc_params(zl_engine_level(c->level));
+    L.M = c->dM.as<u32>(); L.slotM = slotM; L.recs = c->dRecs.as<u64>(); L.slotRec = slotRec; L.lit = c->dLit.as<u8>(); L.slotLit = slotLit;
+    L.hist = c->dHist.as<u32>(); L.metas = c->dMetas.as<ZlEncBlockMeta>(); L.outs = c->dOuts.as<ZlEncBlockOut>(); L.plans = c->dPlans.as<ZlEncBlockPlan>();
+    L.streamCapWords = streamCapWords; L.streamWordsPerBlock = streamWordsPerBlock; L.seqCapWords = seqCapWords;
+    L.results = c->dResults.as<u64>() + f0; L.xxh = xxh; L.stageEv = timeIt ? c->stageEv : nullptr;
+    cudaError_t e = zl_launch_encode(L, st);
+    c->launches += 6;
+    if (e != cudaSuccess) { fprintf(stderr, "zstdlite_gpu: kernel launch failed: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
+    return 0;
+}
+
+// all frames, device pointers; synchronises; results in c->hResults
+static size_t zl_enc_run(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* srcSize, u8* const* ddst, const size_t* dstCap, size_t n)
+{
+    if (!c->hResults.reserve(n * 8)) return ZL_ERROR(memory_allocation);
+    cudaStream_t st = c->stream;
+    for (size_t i = 0; i < n; i++) if (srcSize[i] >= 0xFFFFFFF0ull) return ZL_ERROR(srcSize_wrong);
+    size_t f0 = 0;
+    bool firstWave = true;
+    double total = 0.0; double stage[ZL_ENC_STAGES] = {};
+    while (f0 < n) {
+        size_t f1 = f0, nb = 0;
+        while (f1 < n) {
+            const size_t k = srcSize[f1] ? (srcSize[f1] + ZL_BLOCKSIZE_MAX - 1) / ZL_BLOCKSIZE_MAX : 1;
+            if (f1 > f0 && nb + k > ZL_WAVE_BLOCKS) break;
+            nb += k; f1++;
+        }
+        if (!firstWave) {                                         // the wave's host-side descriptor buffers are reused: drain first
+            if (cudaStreamSynchronize(st) != cudaSuccess) return ZL_ERROR(GENERIC);
+            float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); total += ms;
+            for (int k = 0; k < ZL_ENC_STAGES; k++) { float t = 0; cudaEventElapsedTime(&t, c->stageEv[k], c->stageEv[k + 1]); stage[k] += t; }
+        }
+        cudaEventRecord(c->ev0, st);
+        const size_t r = zl_enc_wave(c, dsrc, srcSize, ddst, dstCap, f0, f1, n, true);
+        cudaEventRecord(c->ev1, st);
+        if (zl_is_error(r)) { cudaStreamSynchronize(st); return r; }
+        firstWave = false;
+        f0 = f1;
+    }
+    cudaMemcpyAsync(c->hResults.p, c->dResults.p, n * 8, cudaMemcpyDeviceToHost, st);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { fprintf(stderr, "zstdlite_gpu: device error: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); total += ms;
+    for (int k = 0; k < ZL_ENC_STAGES; k++) { float t = 0; cudaEventElapsedTime(&t, c->stageEv[k], c->stageEv[k + 1]); stage[k] += t; }
+    c->lastKernelMs = total;
+    for (int k = 0; k < ZL_ENC_STAGES; k++) c->lastStageMs[k] = stage[k];
+    return 0;
+}
+
+ZL_EXPORT size_t zl_compress_batch(ZSTD_CCtx* c, const void* const* src, const size_t* srcSize, void* const* dst, const size_t* dstCap,
+                                   size_t* result, size_t n, int dev)
+{
+    if (!c) return ZL_ERROR(GENERIC);
+    if (n == 0) return 0;
+    if (n > 0x0FFFFFFFull) return ZL_ERROR(memory_allocation);
+    if (!zl_cctx_ready(c)) return ZL_ERROR(memory_allocation);
+    cudaStream_t st = c->stream;
+    if (dev) {
+        const size_t r = zl_enc_run(c, (const u8* const*)src, srcSize, (u8* const*)dst, dstCap, n);
+        if (zl_is_error(r)) return r;
+        const u64* hr = c->hResults.as<u64>();
+        for (size_t i = 0; i < n; i++) result[i] = (size_t)hr[i];
+        return 0;
+    }
+    // host pointers: stage contiguous runs to the device, compress, copy the produced bytes back
+    std::vector<ZlRun> sruns;
+    size_t srcTotal = 0, dstTotal = 0;
+    {   size_t off = 0;
+        for (size_t i = 0; i < n; i++) {
+            const u8* p = (const u8*)src[i];
+            if (!sruns.empty()) { ZlRun& r = sruns.back(); if (p == r.hbase + r.bytes) { r.bytes += srcSize[i]; r.count++; continue; } off = (r.devOff + r.bytes + 255) & ~(size_t)255; }
+            ZlRun r; r.first = i; r.count = 1; r.hbase = p; r.bytes = srcSize[i]; r.devOff = off; sruns.push_back(r);
+        }
+        srcTotal = sruns.back().devOff + sruns.back().bytes;
+    }
+    std::vector<const u8*> dsrc(n); std::vector<u8*> ddst(n);
+    for (size_t i = 0; i < n; i++) dstTotal += (dstCap[i] + 15) & ~(size_t)15;
+    if (!c->dSrc.reserve(srcTotal + 64) || !c->dDst.reserve(dstTotal + 64)) return ZL_ERROR(memory_allocation);
+    {   size_t sr = 0, doff = 0;
+        for (size_t i = 0; i < n; i++) {
+            while (sr + 1 < sruns.size() && i >= sruns[sr + 1].first) sr++;
+            dsrc[i] = c->dSrc.as<u8>() + sruns[sr].devOff + ((const u8*)src[i] - sruns[sr].hbase);
+            ddst[i] = c->dDst.as<u8>() + doff;
+            doff += (dstCap[i] + 15) & ~(size_t)15;
+        }
+    }
+    for (const ZlRun& r : sruns) if (r.bytes) cudaMemcpyAsync(c->dSrc.as<u8>() + r.devOff, r.hbase, r.bytes, cudaMemcpyHostToDevice, st);
+    const size_t r = zl_enc_run(c, dsrc.data(), srcSize, ddst.data(), dstCap, n);
+    if (zl_is_error(r)) return r;
+    const u64* hr = c->hResults.as<u64>();
+    for (size_t i = 0; i < n; i++) {
+        result[i] = (size_t)hr[i];
+        if (!zl_is_error(result[i]) && result[i]) cudaMemcpyAsync(dst[i], ddst[i], result[i], cudaMemcpyDeviceToHost, st);
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) { (void)cudaGetLastError(); return ZL_ERROR(GENERIC); }
+    return 0;
+}
+
+// zstd.c:28949 ZSTD_compress2: one input -> one frame (of independent <= 128 KiB blocks) whose header records the content size
+ZL_EXPORT size_t ZSTD_compress2(ZSTD_CCtx* c, void* dst, size_t dstCap, const void* src, size_t srcSize)
+{
+    if (!c) return ZL_ERROR(GENERIC);
+    if (!dst && dstCap) return ZL_ERROR(dstBuffer_null);
+    const void* sp = src; void* dp = dst; size_t res = 0;
+    static const u8 empty = 0;
+    if (!sp) { if (srcSize) return ZL_ERROR(srcSize_wrong); sp = &empty; }
+    const size_t r = zl_compress_batch(c, &sp, &srcSize, &dp, &dstCap, &res, 1, 0);
+    c->pledged = ZSTD_CONTENTSIZE_UNKNOWN;                                  // session reset, zstd.c:28956
+    return zl_is_error(r) ? r : res;
+}
+ZL_ALIAS(size_t, ZSTD_compress2, (ZSTD_CCtx*, void*, size_t, const void*, size_t))
+
+// One buffer -> concatenated independent frames of `frameSize` content bytes (a standard multi-frame zstd stream).
+ZL_EXPORT size_t zl_compress_split(ZSTD_CCtx* c, void* dst, size_t dstCap, const void* src, size_t srcSize, size_t frameSize,
+                                   size_t* frameSizes, int dev)
+{
+    if (!c || !frameSize) return ZL_ERROR(GENERIC);
+    if (!zl_cctx_ready(c)) return ZL_ERROR(memory_allocation);
+    cudaStream_t st = c->stream;
+    const size_t nf = srcSize ? (srcSize + frameSize - 1) / frameSize : 1;
+    const size_t slot = (ZSTD_compressBound(frameSize) + 4 + 15) & ~(size_t)15;
+    const u8* dsrcBase = (const u8*)src;
+    if (!dev) {
+        if (!c->dSrc.reserve(srcSize + 64)) return ZL_ERROR(memory_allocation);
+        if (srcSize) cudaMemcpyAsync(c->dSrc.p, src, srcSize, cudaMemcpyHostToDevice, st);
+        dsrcBase = c->dSrc.as<u8>();
+    }
+    if (!c->dDst.reserve(nf * slot + 64)) return ZL_ERROR(memory_allocation);
+    std::vector<const u8*> dsrc(nf); std::vector<u8*> ddst(nf); std::vector<size_t> ssz(nf), caps(nf, slot);
+    for (size_t i = 0; i < nf; i++) {
+        dsrc[i] = dsrcBase + i * frameSize;
+        const size_t rem = srcSize - i * frameSize;
+        ssz[i] = rem < frameSize ? rem : frameSize;
+        ddst[i] = c->dDst.as<u8>() + i * slot;
+    }
+    const size_t r = zl_enc_run(c, dsrc.data(), ssz.data(), ddst.data(), caps.data(), nf);
+    if (zl_is_error(r)) return r;
+    const u64* hr = c->hResults.as<u64>();
+    // exclusive scan of the frame sizes (host: nf integers), then one gather launch
+    if (!c->hAux.reserve(nf * 24) || !c->dAux.reserve(nf * 24)) return ZL_ERROR(memory_allocation);
+    u64* hsz = c->hAux.as<u64>(); u64* hoff = hsz + nf; const u8** hptr = reinterpret_cast<const u8**>(hoff + nf);
+    size_t total = 0;
+    for (size_t i = 0; i < nf; i++) {
+        if (zl_is_error((size_t)hr[i])) return (size_t)hr[i];
+        hsz[i] = hr[i]; hoff[i] = total; hptr[i] = ddst[i]; total += (size_t)hr[i];
+        if (frameSizes) frameSizes[i] = (size_t)hr[i];
+    }
+    if (total > dstCap) return ZL_ERROR(dstSize_tooSmall);
+    cudaMemcpyAsync(c->dAux.p, hsz, nf * 24, cudaMemcpyHostToDevice, st);
+    u8* out = (u8*)dst;
+    if (!dev) { if (!c->dSrc.reserve(total + 64)) return ZL_ERROR(memory_allocation); out = c->dSrc.as<u8>(); }   // the staged input is no longer needed
+    const u64* dsz = c->dAux.as<u64>();
+    if (zl_launch_gather(reinterpret_cast<const u8* const*>(dsz + 2 * nf), dsz, dsz + nf, out, (u32)nf, st) != cudaSuccess) return ZL_ERROR(GENERIC);
+    c->launches += 1;
+    if (!dev && total) cudaMemcpyAsync(dst, out, total, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) { (void)cudaGetLastError(); return ZL_ERROR(GENERIC); }
+    return total;
+}

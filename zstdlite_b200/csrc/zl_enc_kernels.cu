@@ -1,0 +1,405 @@
+// zl_enc_kernels.cu -- the compression kernels and their launcher (sm_100a).  Work unit: one BLOCK of <= 128 KiB.
+//   E1 zl_k_match          CTA of ZL_MATCH_WARPS warps per block: hash every position, look up / insert into the
+//                          shared-memory tables in position order (warps take 32-position groups round-robin and pass
+//                          a token through named barriers for the table section only), verify candidates -> M[p]
+//   E2 zl_k_parse          warp per block: greedy walk over M in 32-position windows (ballot + ffs jumps), repeat-offset
+//                          coding, literal gather + histogram -> sequence records, literal buffer
+//   E3 zl_k_enc_literals   quad per block: Huffman code construction, tree description, 4 streams (one per lane)
+//   E4 zl_k_enc_sequences  quad per block: three FSE tables (one lane each), table descriptions, interleaved bitstream
+//   E5 zl_k_enc_plan       thread per frame: block types (compressed / raw), sizes, offsets, capacity check
+//   E6 zl_k_enc_assemble   warp per block: frame header, block header, section copies into the destination, checksum
+// The serial per-lane logic lives in zl_enc_entropy.cuh / zl_enc_match.cuh (shared with the CPU emulation in tests/emul).
+#include "zl_enc_entropy.cuh"
+#include "zl_enc_match.cuh"
+#include "zl_dec_exec.cuh"        // zl_warp_copy
+#include "zl_launch.h"
+
+__constant__ ZlEncConst c_enc;
+
+cudaError_t zl_enc_upload_const()
+{
+    ZlEncConst h;
+    zl_enc_const_init(&h);
+    return cudaMemcpyToSymbol(c_enc, &h, sizeof(h));
+}
+
+// ---------------------------------------------------------------------------------------------- helpers
+__device__ __forceinline__ void zl_bar_sync(u32 id, u32 count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void zl_bar_arrive(u32 id, u32 count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// 8 bytes at byte offset `bo` from the 4-aligned base; words past `lastWord` are clamped (callers bound lengths by the block size)
+__device__ __forceinline__ void zl_ld8(const u32* __restrict__ wbase, u32 bo, u32 lastWord, u32& lo, u32& hi)
+{
+    const u32 wi = bo >> 2, sh = (bo & 3) * 8;
+    const u32 a = __ldg(wbase + min(wi, lastWord)), b = __ldg(wbase + min(wi + 1, lastWord)), c = __ldg(wbase + min(wi + 2, lastWord));
+    lo = __funnelshift_r(a, b, sh); hi = __funnelshift_r(b, c, sh);
+}
+// length of the match between positions p and q (< p), capped at lim (<= ZL_M_CAP); (lo, hi) = the 8 bytes at p
+__device__ __forceinline__ u32 zl_match_len(const u32* __restrict__ wbase, u32 bias, u32 lastWord, u32 p, u32 q, u32 lo, u32 hi, u32 lim)
+{
+    u32 blo, bhi;
+    zl_ld8(wbase, bias + q, lastWord, blo, bhi);
+    u32 len = zl_common8(lo, hi, blo, bhi);
+    if (len == 8) {
+        for (u32 k = 8; k < lim; k += 8) {
+            u32 alo, ahi;
+            zl_ld8(wbase, bias + p + k, lastWord, alo, ahi);
+            zl_ld8(wbase, bias + q + k, lastWord, blo, bhi);
+            const u32 c = zl_common8(alo, ahi, blo, bhi);
+            len += c;
+            if (c < 8) break;
+        }
+    }
+    return len < lim ? len : lim;
+}
+
+// ---------------------------------------------------------------------------------------------- E1: match candidates
+template <bool kLong>
+__global__ void __launch_bounds__(ZL_MATCH_WARPS * 32)
+zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 slotM, ZlEncParams P)
+{
+    extern __shared__ __align__(16) u8 smraw[];
+    u16* tabS = reinterpret_cast<u16*>(smraw);
+    u16* tabL = tabS + (1u << P.hlogS);
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const ZlEncBlock b = blocks[blockIdx.x];
+    const u32 n = b.srcSize;
+    u32* __restrict__ M = Marena + (size_t)blockIdx.x * slotM;
+    {   const u32 bytes = (2u << P.hlogS) + (kLong ? (2u << P.hlogL) : 0u);
+        uint4* z = reinterpret_cast<uint4*>(smraw);
+        for (u32 i = tid; i < bytes / 16; i += ZL_MATCH_WARPS * 32) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    if (n == 0) return;
+    const u32 bias = (u32)(((size_t)b.src) & 3);
+    const u32* __restrict__ wbase = reinterpret_cast<const u32*>(b.src - bias);
+    const u32 lastWord = (bias + n - 1) >> 2;
+    const u32 ngroups = (n + 31) >> 5;
+    const u32 ltMask = (1u << lane) - 1;
+    for (u32 g = warp; g < ngroups; g += ZL_MATCH_WARPS) {
+        const u32 p = (g << 5) + lane;
+        // the 8 bytes at every position of the group from 11 coalesced words
+        const u32 wb = (bias + (g << 5)) >> 2;
+        const u32 w = lane < 11 ? __ldg(wbase + min(wb + lane, lastWord)) : 0u;
+        const u32 bo = (bias & 3) + lane, j = bo >> 2, sh = (bo & 3) * 8;
+        const u32 w0 = __shfl_sync(ZL_FULL, w, j), w1 = __shfl_sync(ZL_FULL, w, j + 1), w2 = __shfl_sync(ZL_FULL, w, j + 2);
+        const u32 lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        const bool valid = p + 8 <= n;
+        const u32 hS = valid ? zl_hash_short(lo, hi, P.mls, P.hlogS) : (0x10000u + lane);
+        const u32 mS = __match_any_sync(ZL_FULL, hS);
+        const bool lastS = (mS >> lane) == 1u;                    // no higher lane shares the hash: this lane's insert survives
+        const i32 prevS = (mS & ltMask) ? (31 - __clz((int)(mS & ltMask))) : -1;
+        u32 hL = 0; bool lastL = false; i32 prevL = -1;
+        if (kLong) {
+            hL = valid ? zl_hash_long(lo, hi, P.hlogL) : (0x10000u + lane);
+            const u32 mL = __match_any_sync(ZL_FULL, hL);
+            lastL = (mL >> lane) == 1u;
+            prevL = (mL & ltMask) ? (31 - __clz((int)(mL & ltMask))) : -1;
+        }
+        // ---- table section, in position order across warps
+        if (ZL_MATCH_WARPS > 1 && g > 0) zl_bar_sync(1 + warp, 64);
+        u32 eS = 0, eL = 0;
+        if (valid) {
+            eS = tabS[hS];
+            if (kLong) eL = tabL[hL];
+            if (lastS) tabS[hS] = (u16)p;
+            if (kLong && lastL) tabL[hL] = (u16)p;
+        }
+        if (ZL_MATCH_WARPS > 1 && g + 1 < ngroups) { __threadfence_block(); zl_bar_arrive(1 + (warp + 1) % ZL_MATCH_WARPS, 64); }
+        // ---- verify
+        u32 m = 0;
+        if (valid) {
+            const u32 lim = min(n - p, ZL_M_CAP);
+            u32 bestLen = 0, bestOff = 0;
+            if (kLong) {
+                const i32 qL = prevL >= 0 ? (i32)((g << 5) + (u32)prevL) : zl_cand_pos(eL, p);
+                if (qL >= 0) { const u32 l = zl_match_len(wbase, bias, lastWord, p, (u32)qL, lo, hi, lim); if (l >= P.mls) { bestLen = l; bestOff = p - (u32)qL; } }
+            }
+            const i32 qS = prevS >= 0 ? (i32)((g << 5) + (u32)prevS) : zl_cand_pos(eS, p);
+            if (qS >= 0) { const u32 l = zl_match_len(wbase, bias, lastWord, p, (u32)qS, lo, hi, lim); if (l >= P.mls && l > bestLen) { bestLen = l; bestOff = p - (u32)qS; } }
+            if (bestLen) m = (bestOff << 8) | bestLen;
+        }
+        if (p < n) M[p] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- E2: greedy walk
+// cooperative extension of a match that hit the cap: compares 256 bytes per round
+__device__ __forceinline__ u32 zl_extend_match(const u32* __restrict__ wbase, u32 bias, u32 lastWord, u32 n, u32 pos, u32 off, u32 lane)
+{
+    u32 len = ZL_M_CAP;
+    for (;;) {
+        const u32 q = pos + len + 8 * lane;
+        u32 c = 0;
+        if (q < n) {
+            u32 alo, ahi, blo, bhi;
+            zl_ld8(wbase, bias + q, lastWord, alo, ahi);
+            zl_ld8(wbase, bias + q - off, lastWord, blo, bhi);
+            c = zl_common8(alo, ahi, blo, bhi);
+            if (c > n - q) c = n - q;
+        }
+        const bool full = c == 8 && q + 8 <= n;
+        const u32 stop = __ballot_sync(ZL_FULL, !full);
+        if (!stop) { len += 256; continue; }
+        const u32 first = (u32)__ffs((int)stop) - 1;
+        return len + 8 * first + __shfl_sync(ZL_FULL, c, first);
+    }
+}
+
+__global__ void __launch_bounds__(ZL_PARSE_WARPS * 32)
+zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __restrict__ Marena, u32 slotM, u64* __restrict__ recArena,
+           u32 slotRec, u8* __restrict__ litArena, u32 slotLit, u32* __restrict__ histArena, ZlEncBlockMeta* __restrict__ metas)
+{
+    __shared__ u32 hist[ZL_PARSE_WARPS][256];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 blk = blockIdx.x * ZL_PARSE_WARPS + warp;
+    if (blk >= nblocks) return;
+    for (u32 i = lane; i < 256; i += 32) hist[warp][i] = 0;
+    __syncwarp();
+    const ZlEncBlock b = blocks[blk];
+    const u32 n = b.srcSize;
+    const u32* __restrict__ M = Marena + (size_t)blk * slotM;
+    u64* __restrict__ recs = recArena + (size_t)blk * slotRec;
+    u8* __restrict__ lit = litArena + (size_t)blk * slotLit;
+    const u32 bias = (u32)(((size_t)b.src) & 3);
+    const u32* __restrict__ wbase = reinterpret_cast<const u32*>(b.src - bias);
+    const u32 lastWord = n ? (bias + n - 1) >> 2 : 0;
+    const u32 ltMask = (1u << lane) - 1;
+    const bool first = (b.flags & ZL_BLK_FIRST) != 0;
+    ZlReps reps;                                             // zl_enc_match.cuh: unknown history (0) for non-first blocks
+    reps.r0 = first ? 1u : 0u; reps.r1 = first ? 4u : 0u; reps.r2 = first ? 8u : 0u;
+    u32 p = 0, anchor = 0, nseq = 0, nlit = 0;
+    u32 mNext = lane < n ? M[lane] : 0u;
+    for (u32 w0 = 0; w0 < n; w0 += 32) {
+        const u32 m = mNext;
+        { const u32 nx = w0 + 32 + lane; mNext = nx < n ? M[nx] : 0u; }
+        if (p >= w0 + 32) continue;                          // window entirely inside a match
+        const u32 pos = w0 + lane;
+        const u32 byte = pos < n ? (u32)b.src[pos] : 0u;
+        u32 len = m & 0xFF;
+        const u32 off = m >> 8;
+        u32 c = p > w0 ? p - w0 : 0;
+        const u32 cstart = c;
+        const u32 matchMask = __ballot_sync(ZL_FULL, len != 0);
+        u32 takenMask = 0, myLL = 0, myOB = 0;
+        for (;;) {
+            const u32 mm = c < 32 ? (matchMask >> c) << c : 0u;
+            if (!mm) break;
+            const u32 c1 = (u32)__ffs((int)mm) - 1;
+            u32 l = __shfl_sync(ZL_FULL, len, c1);
+            const u32 o = __shfl_sync(ZL_FULL, off, c1);
+            const u32 pos1 = w0 + c1;
+            if (l == ZL_M_CAP) l = zl_extend_match(wbase, bias, lastWord, n, pos1, o, lane);
+            const u32 ll = pos1 - anchor;
+            const u32 ob = zl_rep_encode(reps, o, ll);
+            if (lane == c1) { len = l; myLL = ll; myOB = ob; }
+            takenMask |= 1u << c1;
+            anchor = pos1 + l;
+            c = c1 + l;
+        }
+        p = w0 + (c < 32 ? 32 : c);
+        // literals of this window: positions from cstart on that no taken match covers
+        const u32 below = takenMask & (ltMask | (1u << lane));
+        const u32 t = below ? 31 - __clz((int)below) : 0;
+        const u32 endRel = lane + len;                       // meaningful on taken lanes
+        const u32 e = __shfl_sync(ZL_FULL, endRel, t);
+        const bool covered = below != 0 && e > lane;
+        const bool isLit = pos < n && lane >= cstart && !covered;
+        const u32 litMask = __ballot_sync(ZL_FULL, isLit);
+        if (isLit) { lit[nlit + __popc(litMask & ltMask)] = (u8)byte; atomicAdd(&hist[warp][byte], 1u); }
+        nlit += __popc(litMask);
+        if ((takenMask >> lane) & 1) recs[nseq + __popc(takenMask & ltMask)] = zl_enc_rec(myLL, len, myOB);
+        nseq += __popc(takenMask);
+    }
+    __syncwarp();
+    for (u32 i = lane; i < 256; i += 32) histArena[(size_t)blk * 256 + i] = hist[warp][i];
+    if (lane == 0) { metas[blk].nseq = nseq; metas[blk].nlit = nlit; }
+}
+
+// ---------------------------------------------------------------------------------------------- E3: literals
+__global__ void __launch_bounds__(32)
+zl_k_enc_literals(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u8* __restrict__ litArena, u32 slotLit,
+                  const u32* __restrict__ histArena, const ZlEncBlockMeta* __restrict__ metas, u32* __restrict__ streamArena,
+                  u32 slotStreamWords, u32 streamCapWords, ZlEncBlockOut* __restrict__ outs)
+{
+    extern __shared__ __align__(16) u8 smraw[];
+    ZlHufSm* fs = reinterpret_cast<ZlHufSm*>(smraw);
+    const u32 lane = threadIdx.x, quad = lane >> 2, q = lane & 3;
+    const u32 qmask = 0xFu << (quad * 4);
+    const u32 blk = blockIdx.x * ZL_QUADS_PER_WARP + quad;
+    if (blk >= nblocks) return;
+    ZlHufSm& f = fs[quad];
+    ZlEncBlockOut& o = outs[blk];
+    const u8* lit = litArena + (size_t)blk * slotLit;
+    const u32 nLit = metas[blk].nlit;
+    for (u32 i = q; i < 256; i += 4) f.count[i] = histArena[(size_t)blk * 256 + i];
+    __syncwarp(qmask);
+    if (q == 0) zl_lit_plan(f, o, lit, nLit);
+    __syncwarp(qmask);
+    const u32 mode = f.ctl.mode, ns = f.ctl.nStreams;
+    if (mode == 2) {
+        if (q < ns)
+            f.ctl.sBytes[q] = zl_huf_encode_stream(f.code, lit, f.ctl.sBeg[q], f.ctl.sEnd[q],
+                                                   streamArena + (size_t)blk * slotStreamWords + (size_t)q * streamCapWords, streamCapWords, &f.ctl.ovf);
+        __syncwarp(qmask);
+        if (q == 0) zl_lit_finish(f, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- E4: sequences
+#define ZL_ENC_CT_BYTES ((sizeof(ZlEncConst) + 15) & ~(size_t)15)
+__global__ void __launch_bounds__(32)
+zl_k_enc_sequences(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u64* __restrict__ recArena, u32 slotRec,
+                   const ZlEncBlockMeta* __restrict__ metas, u32* __restrict__ seqBitsArena, u32 slotSeqWords, u32 seqCapWords,
+                   ZlEncBlockOut* __restrict__ outs)
+{
+    extern __shared__ __align__(16) u8 smraw[];
+    ZlEncConst& K = *reinterpret_cast<ZlEncConst*>(smraw);
+    ZlSeqEncSm* fs = reinterpret_cast<ZlSeqEncSm*>(smraw + ZL_ENC_CT_BYTES);
+    const u32 lane = threadIdx.x, quad = lane >> 2, q = lane & 3;
+    const u32 qmask = 0xFu << (quad * 4);
+    {   const u32* s = reinterpret_cast<const u32*>(&c_enc);
+        u32* d = reinterpret_cast<u32*>(&K);
+        for (u32 i = lane; i < sizeof(ZlEncConst) / 4; i += 32) d[i] = s[i];
+    }
+    __syncwarp();
+    const u32 blk = blockIdx.x * ZL_QUADS_PER_WARP + quad;
+    if (blk >= nblocks) return;
+    ZlSeqEncSm& f = fs[quad];
+    ZlEncBlockOut& o = outs[blk];
+    const u64* recs = recArena + (size_t)blk * slotRec;
+    const u32 nbSeq = metas[blk].nseq;
+    if (q == 0) f.ctl.nbSeq = nbSeq;
+    if (nbSeq && q < 3) zl_seq_build_table(f, q, recs, nbSeq, K);
+    __syncwarp(qmask);
+    if (q == 0) {
+        zl_seq_write_head(f, o);
+        u32 bytes = 0;
+        if (nbSeq) {
+            u32 ovf = 0;
+            bytes = zl_seq_encode(f, K, recs, nbSeq, seqBitsArena + (size_t)blk * slotSeqWords, seqCapWords, &ovf);
+            if (ovf || !bytes) o.flags |= 2u;
+        }
+        o.seqBitsSize = bytes;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- E5: plan
+__global__ void __launch_bounds__(128)
+zl_k_enc_plan(const ZlEncFrame* __restrict__ frames, u32 nframes, const ZlEncBlock* __restrict__ blocks,
+              const ZlEncBlockMeta* __restrict__ metas, const ZlEncBlockOut* __restrict__ outs, ZlEncBlockPlan* __restrict__ plans,
+              u64* __restrict__ results)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nframes) return;
+    const ZlEncFrame fr = frames[i];
+    u64 pos = fr.hdrSize;
+    for (u32 k = 0; k < fr.nblocks; k++) {
+        const u32 bi = fr.firstBlock + k;
+        const u32 n = blocks[bi].srcSize;
+        const u32 payload = n >= 7 ? zl_enc_block_payload(outs[bi], n, metas[bi].nseq) : 0u;      // zstd.c:25725
+        ZlEncBlockPlan pl;
+        pl.dstOff = pos; pl.type = payload ? 2u : 0u; pl.size = payload ? payload : n;
+        plans[bi] = pl;
+        pos += 3 + pl.size;
+    }
+    if (fr.checksumFlag) pos += 4;
+    results[i] = pos <= fr.dstCap ? pos : (u64)0 - (u64)ZL_E_dstSize_tooSmall;
+}
+
+// ---------------------------------------------------------------------------------------------- E6: assemble
+__device__ __forceinline__ void zl_copy_small(u8* dst, const u8* src, u32 n, u32 lane)
+{
+    for (u32 i = lane; i < n; i += 32) dst[i] = src[i];
+}
+__global__ void __launch_bounds__(ZL_ASM_WARPS * 32)
+zl_k_enc_assemble(const ZlEncFrame* __restrict__ frames, const ZlEncBlock* __restrict__ blocks, u32 nblocks,
+                  const ZlEncBlockPlan* __restrict__ plans, const ZlEncBlockOut* __restrict__ outs, const u8* __restrict__ litArena,
+                  u32 slotLit, const u32* __restrict__ streamArena, u32 slotStreamWords, u32 streamCapWords,
+                  const u32* __restrict__ seqBitsArena, u32 slotSeqWords, const u64* __restrict__ results, const u64* __restrict__ xxh)
+{
+    const u32 lane = threadIdx.x & 31;
+    const u32 blk = blockIdx.x * ZL_ASM_WARPS + (threadIdx.x >> 5);
+    if (blk >= nblocks) return;
+    const ZlEncBlock b = blocks[blk];
+    const ZlEncFrame& fr = frames[b.frame];
+    if (results[b.frame] > (u64)0 - (u64)ZL_E_maxCode) return;        // destination too small: nothing is written
+    const ZlEncBlockPlan pl = plans[blk];
+    u8* dst = fr.dst + pl.dstOff;
+    const bool last = (b.flags & ZL_BLK_LAST) != 0;
+    if (b.flags & ZL_BLK_FIRST) zl_copy_small(fr.dst, fr.hdr, fr.hdrSize, lane);
+    if (lane == 0) zl_write_block_header(dst, last ? 1u : 0u, pl.type, pl.size);
+    if (last && fr.checksumFlag && lane < 4) dst[3 + pl.size + lane] = (u8)((u32)xxh[b.frame] >> (8 * lane));   // zstd.c:27760-27766
+    u8* op = dst + 3;
+    if (pl.type == 0) { zl_warp_copy(op, b.src, b.srcSize, lane); return; }
+    const ZlEncBlockOut& o = outs[blk];
+    zl_copy_small(op, o.litHead, o.litHeadSize, lane); op += o.litHeadSize;
+    if (o.litBodyMode == 1) { zl_warp_copy(op, litArena + (size_t)blk * slotLit, o.nLit, lane); op += o.nLit; }
+    else if (o.litBodyMode == 2) {
+        for (u32 k = 0; k < o.nStreams; k++) {
+            zl_warp_copy(op, reinterpret_cast<const u8*>(streamArena + (size_t)blk * slotStreamWords + (size_t)k * streamCapWords), o.sBytes[k], lane);
+            op += o.sBytes[k];
+        }
+    }
+    zl_copy_small(op, o.seqHead, o.seqHeadSize, lane); op += o.seqHeadSize;
+    zl_warp_copy(op, reinterpret_cast<const u8*>(seqBitsArena + (size_t)blk * slotSeqWords), o.seqBitsSize, lane);
+}
+
+// gather of variable-size frames into one contiguous stream (zl_compress_split)
+__global__ void __launch_bounds__(ZL_ASM_WARPS * 32)
+zl_k_gather(const u8* const* __restrict__ srcs, const u64* __restrict__ sizes, const u64* __restrict__ offs, u8* __restrict__ dst, u32 n)
+{
+    const u32 lane = threadIdx.x & 31;
+    const u32 i = blockIdx.x * ZL_ASM_WARPS + (threadIdx.x >> 5);
+    if (i >= n) return;
+    zl_warp_copy(dst + offs[i], srcs[i], (u32)sizes[i], lane);
+}
+
+// ---------------------------------------------------------------------------------------------- launcher
+size_t zl_enc_match_smem(const ZlEncParams& P) { return ((size_t)2 << P.hlogS) + (P.hlogL ? ((size_t)2 << P.hlogL) : 0); }
+
+cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st)
+{
+    if (L.nblocks == 0 && L.nframes == 0) return cudaSuccess;
+    cudaEvent_t* ev = L.stageEv;
+    const size_t smM = zl_enc_match_smem(L.params);
+    const size_t smL = ZL_QUADS_PER_WARP * sizeof(ZlHufSm);
+    const size_t smS = ZL_ENC_CT_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlSeqEncSm);
+    cudaError_t e;
+    if (L.params.hlogL) e = cudaFuncSetAttribute(zl_k_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smM);
+    else e = cudaFuncSetAttribute(zl_k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(zl_k_enc_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smL);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(zl_k_enc_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smS);
+    if (e != cudaSuccess) return e;
+    const u32 nb = L.nblocks;
+    if (ev) cudaEventRecord(ev[0], st);
+    if (nb) {
+        if (L.params.hlogL) zl_k_match<true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params);
+        else zl_k_match<false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params);
+    }
+    if (ev) cudaEventRecord(ev[1], st);
+    if (nb) zl_k_parse<<<(nb + ZL_PARSE_WARPS - 1) / ZL_PARSE_WARPS, ZL_PARSE_WARPS * 32, 0, st>>>(L.blocks, nb, L.M, L.slotM, L.recs, L.slotRec, L.lit, L.slotLit, L.hist, L.metas);
+    if (ev) cudaEventRecord(ev[2], st);
+    const u32 gq = (nb + ZL_QUADS_PER_WARP - 1) / ZL_QUADS_PER_WARP;
+    // the stream / bitstream buffers reuse the M arena (dead after the parse): [streams | sequence bits] per block slot
+    u32* streamArena = L.M;
+    u32* seqArena = L.M + L.streamWordsPerBlock;
+    if (nb) zl_k_enc_literals<<<gq, 32, smL, st>>>(L.blocks, nb, L.lit, L.slotLit, L.hist, L.metas, streamArena, L.slotM, L.streamCapWords, L.outs);
+    if (ev) cudaEventRecord(ev[3], st);
+    if (nb) zl_k_enc_sequences<<<gq, 32, smS, st>>>(L.blocks, nb, L.recs, L.slotRec, L.metas, seqArena, L.slotM, L.seqCapWords, L.outs);
+    if (ev) cudaEventRecord(ev[4], st);
+    zl_k_enc_plan<<<(L.nframes + 127) / 128, 128, 0, st>>>(L.frames, L.nframes, L.blocks, L.metas, L.outs, L.plans, L.results);
+    if (nb) zl_k_enc_assemble<<<(nb + ZL_ASM_WARPS - 1) / ZL_ASM_WARPS, ZL_ASM_WARPS * 32, 0, st>>>(L.frames, L.blocks, nb, L.plans, L.outs, L.lit, L.slotLit, streamArena, L.slotM,
+                                                                                             L.streamCapWords, seqArena, L.slotM, L.results, L.xxh);
+    if (ev) cudaEventRecord(ev[5], st);
+    return cudaGetLastError();
+}
+
+cudaError_t zl_launch_gather(const u8* const* srcs, const u64* sizes, const u64* offs, u8* dst, u32 n, cudaStream_t st)
+{
+    if (!n) return cudaSuccess;
+    zl_k_gather<<<(n + ZL_ASM_WARPS - 1) / ZL_ASM_WARPS, ZL_ASM_WARPS * 32, 0, st>>>(srcs, sizes, offs, dst, n);
+    return cudaGetLastError();
+}

@@ -40,3 +40,53 @@ size_t zl_literals_smem_bytes();
 size_t zl_sequences_smem_bytes();
 cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st);
 cudaError_t zl_launch_xxh64(const u8* const* ptrs, const u32* sizes, u64* out, u32 n, cudaStream_t st);
+
+// ---- compression --------------------------------------------------------------------------------------------------
+#include "zl_enc_entropy.cuh"
+#include "zl_enc_match.cuh"
+
+#define ZL_MATCH_WARPS 8
+#define ZL_PARSE_WARPS 4
+#define ZL_ASM_WARPS 4
+#define ZL_ENC_STAGES 5      // match, parse, literals, sequences, plan+assemble
+#define ZL_BLK_FIRST 1u
+#define ZL_BLK_LAST 2u
+
+struct ZlEncBlock {          // one per block of <= 128 KiB (24 B)
+    const u8* src;           // device pointer
+    u32 srcSize;
+    u32 frame;               // index into the frame array
+    u32 flags;               // ZL_BLK_FIRST / ZL_BLK_LAST within its frame
+    u32 pad;
+};
+struct ZlEncFrame {          // one per frame (64 B)
+    u8* dst;                 // device pointer to the frame's output
+    u64 dstCap;
+    u32 firstBlock, nblocks;
+    u32 hdrSize, checksumFlag;
+    u8 hdr[24];              // frame header bytes, prepared on the host (zl_write_frame_header)
+    u64 pad;
+};
+struct ZlEncBlockMeta { u32 nseq, nlit; };
+struct ZlEncBlockPlan { u64 dstOff; u32 type, size; };     // offset inside the frame's output, block type, payload size
+
+struct ZlEncodeLaunch {
+    const ZlEncBlock* blocks; u32 nblocks;
+    const ZlEncFrame* frames; u32 nframes;
+    ZlEncParams params;
+    u32* M; u32 slotM;                 // words per block slot (>= max block size); reused for streams + sequence bits
+    u64* recs; u32 slotRec;
+    u8* lit; u32 slotLit;
+    u32* hist;
+    ZlEncBlockMeta* metas;
+    ZlEncBlockOut* outs;
+    ZlEncBlockPlan* plans;
+    u32 streamCapWords, streamWordsPerBlock, seqCapWords;
+    u64* results;
+    const u64* xxh;                    // per-frame XXH64 of the content (only read when the frame carries a checksum)
+    cudaEvent_t* stageEv;              // null or ZL_ENC_STAGES + 1 events
+};
+cudaError_t zl_enc_upload_const();
+size_t zl_enc_match_smem(const ZlEncParams& P);
+cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st);
+cudaError_t zl_launch_gather(const u8* const* srcs, const u64* sizes, const u64* offs, u8* dst, u32 n, cudaStream_t st);
