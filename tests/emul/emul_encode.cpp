@@ -74,10 +74,20 @@ static u32 emul_block(const u8* src, u32 n, const ZlEncParams& P, const ZlEncCon
     std::vector<u32> sbuf[4];
     zl_lit_plan(hs, o, litPad.data(), nLit);
     if (hs.ctl.mode == 2) {
+        // as the CUDA kernel does it: 32 lanes, 32 / nStreams chunks per stream, exclusive scan of the chunk sizes
+        const u32 per = 32 / hs.ctl.nStreams;
         for (u32 q = 0; q < hs.ctl.nStreams; q++) {
             const u32 cnt = hs.ctl.sEnd[q] - hs.ctl.sBeg[q];
             sbuf[q].assign(cnt * 11 / 32 + 4, 0);
-            hs.ctl.sBytes[q] = zl_huf_encode_stream(hs.code, litPad.data(), hs.ctl.sBeg[q], hs.ctl.sEnd[q], sbuf[q].data(), (u32)sbuf[q].size(), &hs.ctl.ovf);
+            u32 bits[32], cb[32], ce[32], total = 0;
+            for (u32 k = 0; k < per; k++) { zl_huf_chunk_range(hs.ctl.sBeg[q], hs.ctl.sEnd[q], k, per, &cb[k], &ce[k]); bits[k] = zl_huf_chunk_bits(hs.nbBits, litPad.data(), cb[k], ce[k]); total += bits[k]; }
+            u32 off = 0;
+            for (i32 k = (i32)per - 1; k >= 0; k--) { zl_huf_encode_chunk(hs.code, litPad.data(), cb[k], ce[k], sbuf[q].data(), (u32)sbuf[q].size(), off, k == 0, &hs.ctl.ovf); off += bits[k]; }
+            hs.ctl.sBytes[q] = (total + 1 + 7) >> 3;
+            // cross-check against the single-lane form
+            std::vector<u32> ref1(sbuf[q].size(), 0); u32 ovf1 = 0;
+            const u32 b1 = zl_huf_encode_stream(hs.code, litPad.data(), hs.ctl.sBeg[q], hs.ctl.sEnd[q], ref1.data(), (u32)ref1.size(), &ovf1);
+            if (b1 != hs.ctl.sBytes[q] || memcmp(ref1.data(), sbuf[q].data(), b1)) return 0xFFFFFFFFu;
         }
         zl_lit_finish(hs, o);
     }

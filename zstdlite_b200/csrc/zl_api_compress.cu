@@ -145,7 +145,7 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
         if (mb > maxBlock) maxBlock = mb;
     }
     if (nb > 0x3FFFFFFFull) return ZL_ERROR(memory_allocation);
-    const u32 S = ((maxBlock < 256 ? 256 : maxBlock) + 255) & ~255u;
+    const u32 S = ((maxBlock < 512 ? 512 : maxBlock) + 255) & ~255u;      // slot layout below needs S >= 264
     const u32 slotM = S, slotRec = S / 5 + 8, slotLit = S + 16;
     const u32 streamCapWords = (((S / 4 + 1) * 11) / 8 + 16 + 3) / 4, streamWordsPerBlock = 4 * streamCapWords, seqCapWords = S / 4;
     if (!c->hBlocks.reserve(nb * sizeof(ZlEncBlock)) || !c->hFrames.reserve(nf * sizeof(ZlEncFrame))) return ZL_ERROR(memory_allocation);

@@ -365,6 +365,55 @@ ZL_HD u32 zl_huf_encode_stream(const u16* code, const u8* lit, u32 beg, u32 end,
     return bytes;
 }
 
+// Chunked form of the same stream, for many lanes per stream: a stream's literal range is cut into consecutive chunks;
+// every lane first sums the code lengths of its chunk (zl_huf_chunk_bits), an exclusive scan over the chunks that are
+// written EARLIER (the ones further towards the end of the range) gives its starting bit, and it then writes its codes
+// there.  The first and last word a lane touches may be shared with its neighbours: those are OR-ed atomically into
+// the zero-initialised buffer, the words in between are plain stores.
+#if defined(__CUDA_ARCH__)
+#define ZL_ATOMIC_OR(p, v) atomicOr((p), (v))
+#else
+#define ZL_ATOMIC_OR(p, v) (*(p) |= (v))
+#endif
+ZL_HD u32 zl_huf_chunk_bits(const u8* nbBits, const u8* lit, u32 beg, u32 end)
+{
+    u32 bits = 0, i = beg;
+    while (i < end && (i & 3)) bits += nbBits[lit[i++]];
+    for (; i + 4 <= end; i += 4) { const u32 v = *(const u32*)(lit + i); bits += nbBits[v & 0xFF] + nbBits[(v >> 8) & 0xFF] + nbBits[(v >> 16) & 0xFF] + nbBits[v >> 24]; }
+    while (i < end) bits += nbBits[lit[i++]];
+    return bits;
+}
+// writes the codes of lit[beg..end) (last literal first) starting at bit `bitOff` of `out`; `endMark` appends the
+// closing 1 bit (the chunk at the start of the range is written last).  capWords bounds the buffer.
+ZL_HD void zl_huf_encode_chunk(const u16* code, const u8* lit, u32 beg, u32 end, u32* out, u32 capWords, u32 bitOff, bool endMark, u32* ovf)
+{
+    u64 acc = 0; u32 n = bitOff & 31, pos = bitOff >> 5; bool first = true;
+#define ZL_CH_FLUSH() if (n >= 32) { if (pos < capWords) { if (first) ZL_ATOMIC_OR(out + pos, (u32)acc); else out[pos] = (u32)acc; } else *ovf = 1; first = false; pos++; acc >>= 32; n -= 32; }
+#define ZL_CH_SYM(s) { const u32 e = code[s]; acc |= (u64)(e & 0xFFF) << n; n += e >> 12; }
+    u32 i = end;
+    while (i > beg && (i & 3)) { ZL_CH_SYM(lit[--i]); ZL_CH_FLUSH(); }
+    while (i >= beg + 4) {
+        i -= 4;
+        const u32 v = *(const u32*)(lit + i);
+        ZL_CH_SYM(v >> 24); ZL_CH_SYM((v >> 16) & 0xFF); ZL_CH_FLUSH();
+        ZL_CH_SYM((v >> 8) & 0xFF); ZL_CH_SYM(v & 0xFF); ZL_CH_FLUSH();
+    }
+    while (i > beg) { ZL_CH_SYM(lit[--i]); ZL_CH_FLUSH(); }
+    if (endMark) { acc |= (u64)1 << n; n += 1; ZL_CH_FLUSH(); }
+    if (n) { if (pos < capWords) ZL_ATOMIC_OR(out + pos, (u32)acc); else *ovf = 1; }
+#undef ZL_CH_FLUSH
+#undef ZL_CH_SYM
+}
+// chunk k of `nchunks` of the range [beg, end): boundaries are multiples of 4 literals so the word loads stay aligned
+ZL_HD void zl_huf_chunk_range(u32 beg, u32 end, u32 k, u32 nchunks, u32* cbeg, u32* cend)
+{
+    const u32 len = end - beg, cs = ((len + nchunks - 1) / nchunks + 3) & ~3u;
+    u32 a = beg + k * cs, b = a + cs;
+    if (a > end) a = end;
+    if (b > end) b = end;
+    *cbeg = a; *cend = b;
+}
+
 // Per-block outputs of the entropy kernels, consumed by the plan / assemble kernels.
 struct ZlEncBlockOut {
     u32 litHeadSize;       // bytes in litHead: literals section header (+ tree description + jump table)
@@ -475,19 +524,16 @@ ZL_HD u32 zl_seq_code(const ZlEncConst& k, u32 t, u64 rec)
 {
     return t == 0 ? zl_ll_code(k, ZL_REC_LL(rec)) : (t == 1 ? zl_highbit(ZL_REC_OB(rec)) : zl_ml_code(k, ZL_REC_ML(rec)));
 }
-// Lane t (0..2): histogram of its code over all sequences, pick the table type, build the encoding table and
-// the table description.  The choice compares the exact table-description cost plus the estimated symbol cost of an
-// FSE-compressed table with the predefined one (the reference uses sequence-count heuristics at these levels, zstd.c:21034-21059).
-ZL_HD void zl_seq_build_table(ZlSeqEncSm& f, u32 t, const u64* recs, u32 nbSeq, const ZlEncConst& k)
+// Table t (0 LL, 1 OF, 2 ML) from its code histogram f.count[t] (maxSym = largest code present, lastCode = code of
+// the last sequence): pick the table type, build the encoding table and the table description.  The choice compares
+// the exact description cost plus the estimated symbol cost of an FSE-compressed table with the predefined one (the
+// reference uses sequence-count heuristics at these levels, zstd.c:21034-21059).
+ZL_HD void zl_seq_build_from_hist(ZlSeqEncSm& f, u32 t, u32 nbSeq, u32 maxSym, u32 lastCode, const ZlEncConst& k)
 {
-    const u32 maxSymT = t == 0 ? 35u : (t == 1 ? 31u : 52u), maxLogT = t == 1 ? 8u : 9u, defLog = t == 1 ? 5u : 6u;
+    const u32 maxLogT = t == 1 ? 8u : 9u, defLog = t == 1 ? 5u : 6u;
     const i16* def = t == 0 ? k.llDef : (t == 1 ? k.ofDef : k.mlDef);
     const u32 defMax = t == 0 ? 35u : (t == 1 ? 28u : 52u);
     u32* cnt = f.count[t];
-    for (u32 s = 0; s < 64; s++) cnt[s] = 0;
-    u32 maxSym = 0, lastCode = 0;
-    for (u32 i = 0; i < nbSeq; i++) { const u32 c = zl_seq_code(k, t, recs[i]); cnt[c]++; if (c > maxSym) maxSym = c; lastCode = c; }
-    (void)maxSymT;
     u32 maxCount = 0;
     for (u32 s = 0; s <= maxSym; s++) if (cnt[s] > maxCount) maxCount = cnt[s];
     ZlSeqEncCtl& c = f.ctl;
@@ -523,6 +569,15 @@ ZL_HD void zl_seq_build_table(ZlSeqEncSm& f, u32 t, const u64* recs, u32 nbSeq, 
     for (u32 s = 0; s < defSyms; s++) f.norm[t][s] = def[s];
     c.mode[t] = 0; c.log[t] = defLog; c.maxSym[t] = defSyms - 1;
     zl_fse_build_ctable(f.state[t], f.dNb[t], f.dFS[t], f.norm[t], defSyms - 1, defLog, f.symOf[t], f.cumul[t]);
+}
+// serial form (CPU emulation): histogram, then the above
+ZL_HD void zl_seq_build_table(ZlSeqEncSm& f, u32 t, const u64* recs, u32 nbSeq, const ZlEncConst& k)
+{
+    u32* cnt = f.count[t];
+    for (u32 s = 0; s < 64; s++) cnt[s] = 0;
+    u32 maxSym = 0, lastCode = 0;
+    for (u32 i = 0; i < nbSeq; i++) { const u32 c = zl_seq_code(k, t, recs[i]); cnt[c]++; if (c > maxSym) maxSym = c; lastCode = c; }
+    zl_seq_build_from_hist(f, t, nbSeq, maxSym, lastCode, k);
 }
 // sequences section header (lane 0): nbSeq, modes byte, table descriptions in LL, OF, ML order (zstd.c:25446-25490)
 ZL_HD void zl_seq_write_head(const ZlSeqEncSm& f, ZlEncBlockOut& o)

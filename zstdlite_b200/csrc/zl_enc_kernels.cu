@@ -4,8 +4,9 @@
 //                          a token through named barriers for the table section only), verify candidates -> M[p]
 //   E2 zl_k_parse          warp per block: greedy walk over M in 32-position windows (ballot + ffs jumps), repeat-offset
 //                          coding, literal gather + histogram -> sequence records, literal buffer
-//   E3 zl_k_enc_literals   quad per block: Huffman code construction, tree description, 4 streams (one per lane)
-//   E4 zl_k_enc_sequences  quad per block: three FSE tables (one lane each), table descriptions, interleaved bitstream
+//   E3 zl_k_enc_literals   warp per block: Huffman code construction (lane 0), tree description, streams in 32 chunks
+//   E4 zl_k_enc_sequences  warp per block: histograms (all lanes), three FSE tables and state chains (lanes 0-2),
+//                          bit packing by all lanes (scan + shared staging window)
 //   E5 zl_k_enc_plan       thread per frame: block types (compressed / raw), sizes, offsets, capacity check
 //   E6 zl_k_enc_assemble   warp per block: frame header, block header, section copies into the destination, checksum
 // The serial per-lane logic lives in zl_enc_entropy.cuh / zl_enc_match.cuh (shared with the CPU emulation in tests/emul).
@@ -76,50 +77,73 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
     const u32 lastWord = (bias + n - 1) >> 2;
     const u32 ngroups = (n + 31) >> 5;
     const u32 ltMask = (1u << lane) - 1;
-    for (u32 g = warp; g < ngroups; g += ZL_MATCH_WARPS) {
-        const u32 p = (g << 5) + lane;
-        // the 8 bytes at every position of the group from 11 coalesced words
-        const u32 wb = (bias + (g << 5)) >> 2;
-        const u32 w = lane < 11 ? __ldg(wbase + min(wb + lane, lastWord)) : 0u;
-        const u32 bo = (bias & 3) + lane, j = bo >> 2, sh = (bo & 3) * 8;
-        const u32 w0 = __shfl_sync(ZL_FULL, w, j), w1 = __shfl_sync(ZL_FULL, w, j + 1), w2 = __shfl_sync(ZL_FULL, w, j + 2);
-        const u32 lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-        const bool valid = p + 8 <= n;
-        const u32 hS = valid ? zl_hash_short(lo, hi, P.mls, P.hlogS) : (0x10000u + lane);
-        const u32 mS = __match_any_sync(ZL_FULL, hS);
-        const bool lastS = (mS >> lane) == 1u;                    // no higher lane shares the hash: this lane's insert survives
-        const i32 prevS = (mS & ltMask) ? (31 - __clz((int)(mS & ltMask))) : -1;
-        u32 hL = 0; bool lastL = false; i32 prevL = -1;
-        if (kLong) {
-            hL = valid ? zl_hash_long(lo, hi, P.hlogL) : (0x10000u + lane);
-            const u32 mL = __match_any_sync(ZL_FULL, hL);
-            lastL = (mL >> lane) == 1u;
-            prevL = (mL & ltMask) ? (31 - __clz((int)(mL & ltMask))) : -1;
-        }
-        // ---- table section, in position order across warps
-        if (ZL_MATCH_WARPS > 1 && g > 0) zl_bar_sync(1 + warp, 64);
-        u32 eS = 0, eL = 0;
-        if (valid) {
-            eS = tabS[hS];
-            if (kLong) eL = tabL[hL];
-            if (lastS) tabS[hS] = (u16)p;
-            if (kLong && lastL) tabL[hL] = (u16)p;
-        }
-        if (ZL_MATCH_WARPS > 1 && g + 1 < ngroups) { __threadfence_block(); zl_bar_arrive(1 + (warp + 1) % ZL_MATCH_WARPS, 64); }
-        // ---- verify
-        u32 m = 0;
-        if (valid) {
-            const u32 lim = min(n - p, ZL_M_CAP);
-            u32 bestLen = 0, bestOff = 0;
+    // Each warp takes TWO consecutive 32-position groups per turn (64 positions): their loads and verifications overlap,
+    // and the table token is passed half as often.
+    const u32 npairs = (ngroups + 1) >> 1;
+    for (u32 pr = warp; pr < npairs; pr += ZL_MATCH_WARPS) {
+        u32 lo[2], hi[2], hS[2], hL[2], eS[2], eL[2];
+        i32 prevS[2], prevL[2];
+        bool valid[2], lastS[2], lastL[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const u32 g = 2 * pr + h;
+            const u32 p = (g << 5) + lane;
+            // the 8 bytes at every position of the group from 11 coalesced words
+            const u32 wb = (bias + (g << 5)) >> 2;
+            const u32 w = lane < 11 ? __ldg(wbase + min(wb + lane, lastWord)) : 0u;
+            const u32 bo = (bias & 3) + lane, j = bo >> 2, sh = (bo & 3) * 8;
+            const u32 w0 = __shfl_sync(ZL_FULL, w, j), w1 = __shfl_sync(ZL_FULL, w, j + 1), w2 = __shfl_sync(ZL_FULL, w, j + 2);
+            lo[h] = __funnelshift_r(w0, w1, sh); hi[h] = __funnelshift_r(w1, w2, sh);
+            valid[h] = p + 8 <= n;
+            hS[h] = valid[h] ? zl_hash_short(lo[h], hi[h], P.mls, P.hlogS) : (0x10000u + lane);
+            const u32 mS = __match_any_sync(ZL_FULL, hS[h]);
+            lastS[h] = (mS >> lane) == 1u;                    // no higher lane shares the hash: this lane's insert survives
+            prevS[h] = (mS & ltMask) ? (31 - __clz((int)(mS & ltMask))) : -1;
+            hL[h] = 0; lastL[h] = false; prevL[h] = -1;
             if (kLong) {
-                const i32 qL = prevL >= 0 ? (i32)((g << 5) + (u32)prevL) : zl_cand_pos(eL, p);
-                if (qL >= 0) { const u32 l = zl_match_len(wbase, bias, lastWord, p, (u32)qL, lo, hi, lim); if (l >= P.mls) { bestLen = l; bestOff = p - (u32)qL; } }
+                hL[h] = valid[h] ? zl_hash_long(lo[h], hi[h], P.hlogL) : (0x10000u + lane);
+                const u32 mL = __match_any_sync(ZL_FULL, hL[h]);
+                lastL[h] = (mL >> lane) == 1u;
+                prevL[h] = (mL & ltMask) ? (31 - __clz((int)(mL & ltMask))) : -1;
             }
-            const i32 qS = prevS >= 0 ? (i32)((g << 5) + (u32)prevS) : zl_cand_pos(eS, p);
-            if (qS >= 0) { const u32 l = zl_match_len(wbase, bias, lastWord, p, (u32)qS, lo, hi, lim); if (l >= P.mls && l > bestLen) { bestLen = l; bestOff = p - (u32)qS; } }
-            if (bestLen) m = (bestOff << 8) | bestLen;
         }
-        if (p < n) M[p] = m;
+        // ---- table section, in position order across warps (and across the two groups: same-warp shared-memory order)
+        if (ZL_MATCH_WARPS > 1 && pr > 0) zl_bar_sync(1 + warp, 64);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const u32 p = ((2 * pr + h) << 5) + lane;
+            eS[h] = 0; eL[h] = 0;
+            if (valid[h]) {
+                eS[h] = tabS[hS[h]];
+                if (kLong) eL[h] = tabL[hL[h]];
+                if (lastS[h]) tabS[hS[h]] = (u16)p;
+                if (kLong && lastL[h]) tabL[hL[h]] = (u16)p;
+            }
+            __syncwarp();
+        }
+        if (ZL_MATCH_WARPS > 1 && pr + 1 < npairs) { __threadfence_block(); zl_bar_arrive(1 + (warp + 1) % ZL_MATCH_WARPS, 64); }
+        // ---- verify
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const u32 g = 2 * pr + h;
+            const u32 p = (g << 5) + lane;
+            u32 m = 0;
+            if (valid[h]) {
+                const u32 lim = min(n - p, ZL_M_CAP);
+                u32 bestLen = 0, bestOff = 0;
+                if (kLong) {
+                    const i32 qL = prevL[h] >= 0 ? (i32)((g << 5) + (u32)prevL[h]) : zl_cand_pos(eL[h], p);
+                    if (qL >= 0) { const u32 l = zl_match_len(wbase, bias, lastWord, p, (u32)qL, lo[h], hi[h], lim); if (l >= P.mls) { bestLen = l; bestOff = p - (u32)qL; } }
+                }
+                const i32 qS = prevS[h] >= 0 ? (i32)((g << 5) + (u32)prevS[h]) : zl_cand_pos(eS[h], p);
+                if (qS >= 0 && bestLen < lim) {               // a longer match is impossible once the limit is reached
+                    const u32 l = zl_match_len(wbase, bias, lastWord, p, (u32)qS, lo[h], hi[h], lim);
+                    if (l >= P.mls && l > bestLen) { bestLen = l; bestOff = p - (u32)qS; }
+                }
+                if (bestLen) m = (bestOff << 8) | bestLen;
+            }
+            if (p < n) M[p] = m;
+        }
     }
 }
 
@@ -169,47 +193,57 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
     ZlReps reps;                                             // zl_enc_match.cuh: unknown history (0) for non-first blocks
     reps.r0 = first ? 1u : 0u; reps.r1 = first ? 4u : 0u; reps.r2 = first ? 8u : 0u;
     u32 p = 0, anchor = 0, nseq = 0, nlit = 0;
-    u32 mNext = lane < n ? M[lane] : 0u;
-    for (u32 w0 = 0; w0 < n; w0 += 32) {
-        const u32 m = mNext;
-        { const u32 nx = w0 + 32 + lane; mNext = nx < n ? M[nx] : 0u; }
-        if (p >= w0 + 32) continue;                          // window entirely inside a match
-        const u32 pos = w0 + lane;
-        const u32 byte = pos < n ? (u32)b.src[pos] : 0u;
-        u32 len = m & 0xFF;
-        const u32 off = m >> 8;
-        u32 c = p > w0 ? p - w0 : 0;
-        const u32 cstart = c;
-        const u32 matchMask = __ballot_sync(ZL_FULL, len != 0);
-        u32 takenMask = 0, myLL = 0, myOB = 0;
-        for (;;) {
-            const u32 mm = c < 32 ? (matchMask >> c) << c : 0u;
-            if (!mm) break;
-            const u32 c1 = (u32)__ffs((int)mm) - 1;
-            u32 l = __shfl_sync(ZL_FULL, len, c1);
-            const u32 o = __shfl_sync(ZL_FULL, off, c1);
-            const u32 pos1 = w0 + c1;
-            if (l == ZL_M_CAP) l = zl_extend_match(wbase, bias, lastWord, n, pos1, o, lane);
-            const u32 ll = pos1 - anchor;
-            const u32 ob = zl_rep_encode(reps, o, ll);
-            if (lane == c1) { len = l; myLL = ll; myOB = ob; }
-            takenMask |= 1u << c1;
-            anchor = pos1 + l;
-            c = c1 + l;
+    // M and the source bytes are fetched one 128-position super-window ahead (the walk itself never waits on memory)
+    u32 mq[4], bq[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const u32 x = 32 * k + lane; mq[k] = x < n ? __ldcs(M + x) : 0u; bq[k] = x < n ? (u32)b.src[x] : 0u; }
+    for (u32 sw = 0; sw < n; sw += 128) {
+        u32 mc[4], bc[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { mc[k] = mq[k]; bc[k] = bq[k]; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const u32 x = sw + 128 + 32 * k + lane; mq[k] = x < n ? __ldcs(M + x) : 0u; bq[k] = x < n ? (u32)b.src[x] : 0u; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const u32 w0 = sw + 32 * k;
+            if (w0 >= n || p >= w0 + 32) continue;               // past the end / window entirely inside a match
+            const u32 m = mc[k], byte = bc[k];
+            const u32 pos = w0 + lane;
+            u32 len = m & 0xFF;
+            const u32 off = m >> 8;
+            u32 c = p > w0 ? p - w0 : 0;
+            const u32 cstart = c;
+            const u32 matchMask = __ballot_sync(ZL_FULL, len != 0);
+            u32 takenMask = 0, myLL = 0, myOB = 0;
+            for (;;) {
+                const u32 mm = c < 32 ? (matchMask >> c) << c : 0u;
+                if (!mm) break;
+                const u32 c1 = (u32)__ffs((int)mm) - 1;
+                u32 l = __shfl_sync(ZL_FULL, len, c1);
+                const u32 o = __shfl_sync(ZL_FULL, off, c1);
+                const u32 pos1 = w0 + c1;
+                if (l == ZL_M_CAP) l = zl_extend_match(wbase, bias, lastWord, n, pos1, o, lane);
+                const u32 ll = pos1 - anchor;
+                const u32 ob = zl_rep_encode(reps, o, ll);
+                if (lane == c1) { len = l; myLL = ll; myOB = ob; }
+                takenMask |= 1u << c1;
+                anchor = pos1 + l;
+                c = c1 + l;
+            }
+            p = w0 + (c < 32 ? 32 : c);
+            // literals of this window: positions from cstart on that no taken match covers
+            const u32 below = takenMask & (ltMask | (1u << lane));
+            const u32 t = below ? 31 - __clz((int)below) : 0;
+            const u32 endRel = lane + len;                       // meaningful on taken lanes
+            const u32 e = __shfl_sync(ZL_FULL, endRel, t);
+            const bool covered = below != 0 && e > lane;
+            const bool isLit = pos < n && lane >= cstart && !covered;
+            const u32 litMask = __ballot_sync(ZL_FULL, isLit);
+            if (isLit) { lit[nlit + __popc(litMask & ltMask)] = (u8)byte; atomicAdd(&hist[warp][byte], 1u); }
+            nlit += __popc(litMask);
+            if ((takenMask >> lane) & 1) recs[nseq + __popc(takenMask & ltMask)] = zl_enc_rec(myLL, len, myOB);
+            nseq += __popc(takenMask);
         }
-        p = w0 + (c < 32 ? 32 : c);
-        // literals of this window: positions from cstart on that no taken match covers
-        const u32 below = takenMask & (ltMask | (1u << lane));
-        const u32 t = below ? 31 - __clz((int)below) : 0;
-        const u32 endRel = lane + len;                       // meaningful on taken lanes
-        const u32 e = __shfl_sync(ZL_FULL, endRel, t);
-        const bool covered = below != 0 && e > lane;
-        const bool isLit = pos < n && lane >= cstart && !covered;
-        const u32 litMask = __ballot_sync(ZL_FULL, isLit);
-        if (isLit) { lit[nlit + __popc(litMask & ltMask)] = (u8)byte; atomicAdd(&hist[warp][byte], 1u); }
-        nlit += __popc(litMask);
-        if ((takenMask >> lane) & 1) recs[nseq + __popc(takenMask & ltMask)] = zl_enc_rec(myLL, len, myOB);
-        nseq += __popc(takenMask);
     }
     __syncwarp();
     for (u32 i = lane; i < 256; i += 32) histArena[(size_t)blk * 256 + i] = hist[warp][i];
@@ -217,70 +251,201 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
 }
 
 // ---------------------------------------------------------------------------------------------- E3: literals
-__global__ void __launch_bounds__(32)
+// warp per block.  Lane 0 builds the Huffman code from the histogram (serial, a few thousand steps); the streams are then
+// encoded by all 32 lanes: 32 / nStreams chunks per stream, bit offsets from a segmented scan of the chunk bit counts.
+__global__ void __launch_bounds__(ZL_ENT_WARPS * 32)
 zl_k_enc_literals(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u8* __restrict__ litArena, u32 slotLit,
                   const u32* __restrict__ histArena, const ZlEncBlockMeta* __restrict__ metas, u32* __restrict__ streamArena,
                   u32 slotStreamWords, u32 streamCapWords, ZlEncBlockOut* __restrict__ outs)
 {
     extern __shared__ __align__(16) u8 smraw[];
     ZlHufSm* fs = reinterpret_cast<ZlHufSm*>(smraw);
-    const u32 lane = threadIdx.x, quad = lane >> 2, q = lane & 3;
-    const u32 qmask = 0xFu << (quad * 4);
-    const u32 blk = blockIdx.x * ZL_QUADS_PER_WARP + quad;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 blk = blockIdx.x * ZL_ENT_WARPS + warp;
     if (blk >= nblocks) return;
-    ZlHufSm& f = fs[quad];
+    ZlHufSm& f = fs[warp];
     ZlEncBlockOut& o = outs[blk];
     const u8* lit = litArena + (size_t)blk * slotLit;
     const u32 nLit = metas[blk].nlit;
-    for (u32 i = q; i < 256; i += 4) f.count[i] = histArena[(size_t)blk * 256 + i];
-    __syncwarp(qmask);
-    if (q == 0) zl_lit_plan(f, o, lit, nLit);
-    __syncwarp(qmask);
-    const u32 mode = f.ctl.mode, ns = f.ctl.nStreams;
-    if (mode == 2) {
-        if (q < ns)
-            f.ctl.sBytes[q] = zl_huf_encode_stream(f.code, lit, f.ctl.sBeg[q], f.ctl.sEnd[q],
-                                                   streamArena + (size_t)blk * slotStreamWords + (size_t)q * streamCapWords, streamCapWords, &f.ctl.ovf);
-        __syncwarp(qmask);
-        if (q == 0) zl_lit_finish(f, o);
-    }
+    for (u32 i = lane; i < 256; i += 32) f.count[i] = histArena[(size_t)blk * 256 + i];
+    __syncwarp();
+    if (lane == 0) zl_lit_plan(f, o, lit, nLit);
+    __syncwarp();
+    if (f.ctl.mode != 2) return;
+    const u32 ns = f.ctl.nStreams, per = 32 / ns, sIdx = lane / per, k = lane % per;
+    u32* sOut = streamArena + (size_t)blk * slotStreamWords + (size_t)sIdx * streamCapWords;
+    u32 cbeg, cend;
+    zl_huf_chunk_range(f.ctl.sBeg[sIdx], f.ctl.sEnd[sIdx], k, per, &cbeg, &cend);
+    const u32 bits = zl_huf_chunk_bits(f.nbBits, lit, cbeg, cend);
+    // inclusive scan inside the group of `per` lanes; chunks with a larger k are written first
+    u32 inc = bits;
+    for (u32 d = 1; d < per; d <<= 1) { const u32 v = __shfl_up_sync(ZL_FULL, inc, d, per); if (k >= d) inc += v; }
+    const u32 total = __shfl_sync(ZL_FULL, inc, per - 1, per);
+    const u32 off = total - inc;
+    const u32 words = (total + 1 + 31) >> 5;
+    for (u32 i = k; i < words && i < streamCapWords; i += per) sOut[i] = 0;
+    __syncwarp();
+    u32 ovf = 0;
+    zl_huf_encode_chunk(f.code, lit, cbeg, cend, sOut, streamCapWords, off, k == 0, &ovf);
+    if (words > streamCapWords) ovf = 1;
+    if (ovf) f.ctl.ovf = 1;
+    if (k == 0) f.ctl.sBytes[sIdx] = (total + 1 + 7) >> 3;
+    __syncwarp();
+    if (lane == 0) zl_lit_finish(f, o);
 }
 
 // ---------------------------------------------------------------------------------------------- E4: sequences
+// warp per block.  (a) all lanes: codes + three histograms; (b) lanes 0-2: table choice/construction, one table each;
+// (c) rounds of 32 sequences, last sequence first: lanes 0-2 advance the three FSE state chains through shared memory,
+// (d) then all lanes pack one sequence each: warp scan of the bit counts, OR into a shared staging window, whole words
+// flushed coalesced.
 #define ZL_ENC_CT_BYTES ((sizeof(ZlEncConst) + 15) & ~(size_t)15)
-__global__ void __launch_bounds__(32)
+struct ZlSeqWarpSm {
+    ZlSeqEncSm f;
+    u32 stage[96];
+    u32 codes[32];           // cLL | cOF<<8 | cML<<16 of the round's sequences
+    u16 sbv[3][32];          // nbBits<<10 | bits emitted by each chain for the round's sequences
+    u32 finalState[3];
+    u32 pad;
+};
+__device__ __forceinline__ void zl_stage_put(u32* stage, u32 pos, u64 v, u32 nb)
+{
+    if (!nb) return;
+    const u32 w = pos >> 5, s = pos & 31;
+    const u64 lo = v << s;
+    atomicOr(&stage[w], (u32)lo);
+    if (s + nb > 32) atomicOr(&stage[w + 1], (u32)(lo >> 32));
+    if (s + nb > 64) atomicOr(&stage[w + 2], (u32)(v >> (64 - s)));
+}
+__global__ void __launch_bounds__(ZL_ENT_WARPS * 32)
 zl_k_enc_sequences(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u64* __restrict__ recArena, u32 slotRec,
                    const ZlEncBlockMeta* __restrict__ metas, u32* __restrict__ seqBitsArena, u32 slotSeqWords, u32 seqCapWords,
-                   ZlEncBlockOut* __restrict__ outs)
+                   u32 sbitsWordOff, ZlEncBlockOut* __restrict__ outs)
 {
     extern __shared__ __align__(16) u8 smraw[];
     ZlEncConst& K = *reinterpret_cast<ZlEncConst*>(smraw);
-    ZlSeqEncSm* fs = reinterpret_cast<ZlSeqEncSm*>(smraw + ZL_ENC_CT_BYTES);
-    const u32 lane = threadIdx.x, quad = lane >> 2, q = lane & 3;
-    const u32 qmask = 0xFu << (quad * 4);
+    ZlSeqWarpSm* ws = reinterpret_cast<ZlSeqWarpSm*>(smraw + ZL_ENC_CT_BYTES);
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     {   const u32* s = reinterpret_cast<const u32*>(&c_enc);
         u32* d = reinterpret_cast<u32*>(&K);
-        for (u32 i = lane; i < sizeof(ZlEncConst) / 4; i += 32) d[i] = s[i];
+        for (u32 i = threadIdx.x; i < sizeof(ZlEncConst) / 4; i += ZL_ENT_WARPS * 32) d[i] = s[i];
+    }
+    __syncthreads();
+    const u32 blk = blockIdx.x * ZL_ENT_WARPS + warp;
+    if (blk >= nblocks) return;
+    ZlSeqWarpSm& w = ws[warp];
+    ZlSeqEncSm& f = w.f;
+    ZlEncBlockOut& o = outs[blk];
+    const u64* __restrict__ recs = recArena + (size_t)blk * slotRec;
+    const u32 nbSeq = metas[blk].nseq;
+    u32* __restrict__ out = seqBitsArena + (size_t)blk * slotSeqWords;
+    if (lane == 0) f.ctl.nbSeq = nbSeq;
+    if (nbSeq == 0) { if (lane == 0) { zl_seq_write_head(f, o); o.seqBitsSize = 0; } return; }
+    // ---- (a) histograms
+    for (u32 i = lane; i < 192; i += 32) (&f.count[0][0])[i] = 0;
+    __syncwarp();
+    for (u32 i = lane; i < nbSeq; i += 32) {
+        const u64 r = recs[i];
+        atomicAdd(&f.count[0][zl_seq_code(K, 0, r)], 1u);
+        atomicAdd(&f.count[1][zl_seq_code(K, 1, r)], 1u);
+        atomicAdd(&f.count[2][zl_seq_code(K, 2, r)], 1u);
     }
     __syncwarp();
-    const u32 blk = blockIdx.x * ZL_QUADS_PER_WARP + quad;
-    if (blk >= nblocks) return;
-    ZlSeqEncSm& f = fs[quad];
-    ZlEncBlockOut& o = outs[blk];
-    const u64* recs = recArena + (size_t)blk * slotRec;
-    const u32 nbSeq = metas[blk].nseq;
-    if (q == 0) f.ctl.nbSeq = nbSeq;
-    if (nbSeq && q < 3) zl_seq_build_table(f, q, recs, nbSeq, K);
-    __syncwarp(qmask);
-    if (q == 0) {
-        zl_seq_write_head(f, o);
-        u32 bytes = 0;
-        if (nbSeq) {
-            u32 ovf = 0;
-            bytes = zl_seq_encode(f, K, recs, nbSeq, seqBitsArena + (size_t)blk * slotSeqWords, seqCapWords, &ovf);
-            if (ovf || !bytes) o.flags |= 2u;
+    u32 maxSym[3];
+#pragma unroll
+    for (u32 t = 0; t < 3; t++) {
+        const u32 m0 = __ballot_sync(ZL_FULL, f.count[t][lane] != 0), m1 = __ballot_sync(ZL_FULL, f.count[t][lane + 32] != 0);
+        maxSym[t] = m1 ? 63 - __clz((int)m1) : 31 - __clz((int)m0);
+    }
+    // ---- (b) tables
+    if (lane < 3) {
+        const u32 t = lane;
+        const u32 ms = t == 0 ? maxSym[0] : (t == 1 ? maxSym[1] : maxSym[2]);
+        zl_seq_build_from_hist(f, t, nbSeq, ms, zl_seq_code(K, t, recs[nbSeq - 1]), K);
+    }
+    __syncwarp();
+    if (lane == 0) zl_seq_write_head(f, o);
+    // ---- (c)+(d) rounds of 32 sequences in writing order (last sequence first): every lane loads one record and
+    // publishes its three codes; lanes 0-2 advance their state chain over the 32 codes (shared-memory reads only);
+    // every lane then packs the bits of its own sequence.
+    for (u32 i = lane; i < 96; i += 32) w.stage[i] = 0;
+    u32 st = 0;                                             // lanes 0-2: running FSE state of their table
+    const u32 myT = lane < 3 ? lane : 0;
+    const u16* tbl = f.state[myT];
+    u32 bitPos = 0, ovf = 0;
+    const u32 rounds = (nbSeq + 31) >> 5;
+    u64 rNext = lane < nbSeq ? recs[nbSeq - 1 - lane] : 0;
+    for (u32 rd = 0; rd <= rounds; rd++) {
+        u64 a = 0; u32 na = 0, b = 0, nb2 = 0;
+        if (rd < rounds) {
+            const u32 j = (rd << 5) + lane;
+            const u64 r = rNext;
+            { const u32 jn = j + 32; rNext = jn < nbSeq ? recs[nbSeq - 1 - jn] : 0; }
+            const u32 cLL = zl_seq_code(K, 0, r), cOF = zl_seq_code(K, 1, r), cML = zl_seq_code(K, 2, r);
+            w.codes[lane] = cLL | (cOF << 8) | (cML << 16);
+            __syncwarp();
+            if (lane < 3) {
+                const u32 cnt = min(32u, nbSeq - (rd << 5));
+                u32 s0 = 0;
+                if (rd == 0) {                              // the first sequence written only initialises the state (zstd.c:21166-21170)
+                    const u32 code = (w.codes[0] >> (8 * myT)) & 0xFF;
+                    st = zl_fse_init_state(tbl, f.dNb[myT][code], f.dFS[myT][code]);
+                    w.sbv[myT][0] = 0; s0 = 1;
+                }
+#pragma unroll 4
+                for (u32 s = s0; s < cnt; s++) {
+                    const u32 code = (w.codes[s] >> (8 * myT)) & 0xFF;
+                    const u32 e = zl_fse_step(tbl, f.dNb[myT][code], f.dFS[myT][code], st);
+                    w.sbv[myT][s] = (u16)(((e >> 16) << 10) | (e & 0x3FF));
+                }
+            }
+            __syncwarp();
+            if (j < nbSeq) {
+                const u32 eLL = w.sbv[0][lane], eOF = w.sbv[1][lane], eML = w.sbv[2][lane];
+                a = eOF & 0x3FF; na = eOF >> 10;
+                a |= (u64)(eML & 0x3FF) << na; na += eML >> 10;
+                a |= (u64)(eLL & 0x3FF) << na; na += eLL >> 10;
+                u32 x, v;
+                v = zl_seq_extra(K, 0, r, cLL, &x); a |= (u64)v << na; na += x;
+                v = zl_seq_extra(K, 2, r, cML, &x); a |= (u64)v << na; na += x;
+                b = zl_seq_extra(K, 1, r, cOF, &nb2);
+            }
+        } else {                                            // closing: ML, OF, LL states then the end mark (zstd.c:21227-21231, 2334)
+            if (lane < 3) w.finalState[lane] = st;
+            __syncwarp();
+            if (lane == 0) {
+                const u32 lML = f.ctl.log[2], lOF = f.ctl.log[1], lLL = f.ctl.log[0];
+                a = w.finalState[2] & ((1u << lML) - 1); na = lML;
+                a |= (u64)(w.finalState[1] & ((1u << lOF) - 1)) << na; na += lOF;
+                a |= (u64)(w.finalState[0] & ((1u << lLL) - 1)) << na; na += lLL;
+                a |= (u64)1 << na; na += 1;
+            }
         }
-        o.seqBitsSize = bytes;
+        const u32 mine = na + nb2;
+        u32 inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const u32 v = __shfl_up_sync(ZL_FULL, inc, d); if ((int)lane >= d) inc += v; }
+        const u32 roundBits = __shfl_sync(ZL_FULL, inc, 31);
+        const u32 start = (bitPos & 31) + inc - mine;
+        zl_stage_put(w.stage, start, a, na);
+        zl_stage_put(w.stage, start + na, (u64)b, nb2);
+        __syncwarp();
+        const u32 endPos = (bitPos & 31) + roundBits, nFull = endPos >> 5, wbase = bitPos >> 5;
+        for (u32 kx = lane; kx < nFull; kx += 32) { if (wbase + kx < seqCapWords) out[wbase + kx] = w.stage[kx]; else ovf = 1; }
+        __syncwarp();
+        const u32 carry = w.stage[nFull];
+        __syncwarp();
+        for (u32 kx = lane; kx <= nFull; kx += 32) w.stage[kx] = 0;
+        __syncwarp();
+        if (lane == 0) w.stage[0] = carry;
+        __syncwarp();
+        bitPos += roundBits;
+    }
+    if (lane == 0 && (bitPos & 31)) { if ((bitPos >> 5) < seqCapWords) out[bitPos >> 5] = w.stage[0]; else ovf = 1; }
+    ovf = __any_sync(ZL_FULL, ovf != 0) ? 1u : 0u;
+    if (lane == 0) {
+        if (ovf) o.flags |= 2u;
+        o.seqBitsSize = ovf ? 0u : (bitPos + 7) >> 3;
     }
 }
 
@@ -363,8 +528,8 @@ cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st)
     if (L.nblocks == 0 && L.nframes == 0) return cudaSuccess;
     cudaEvent_t* ev = L.stageEv;
     const size_t smM = zl_enc_match_smem(L.params);
-    const size_t smL = ZL_QUADS_PER_WARP * sizeof(ZlHufSm);
-    const size_t smS = ZL_ENC_CT_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlSeqEncSm);
+    const size_t smL = ZL_ENT_WARPS * sizeof(ZlHufSm);
+    const size_t smS = ZL_ENC_CT_BYTES + ZL_ENT_WARPS * sizeof(ZlSeqWarpSm);
     cudaError_t e;
     if (L.params.hlogL) e = cudaFuncSetAttribute(zl_k_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smM);
     else e = cudaFuncSetAttribute(zl_k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smM);
@@ -382,13 +547,13 @@ cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st)
     if (ev) cudaEventRecord(ev[1], st);
     if (nb) zl_k_parse<<<(nb + ZL_PARSE_WARPS - 1) / ZL_PARSE_WARPS, ZL_PARSE_WARPS * 32, 0, st>>>(L.blocks, nb, L.M, L.slotM, L.recs, L.slotRec, L.lit, L.slotLit, L.hist, L.metas);
     if (ev) cudaEventRecord(ev[2], st);
-    const u32 gq = (nb + ZL_QUADS_PER_WARP - 1) / ZL_QUADS_PER_WARP;
+    const u32 gq = (nb + ZL_ENT_WARPS - 1) / ZL_ENT_WARPS;
     // the stream / bitstream buffers reuse the M arena (dead after the parse): [streams | sequence bits] per block slot
     u32* streamArena = L.M;
     u32* seqArena = L.M + L.streamWordsPerBlock;
-    if (nb) zl_k_enc_literals<<<gq, 32, smL, st>>>(L.blocks, nb, L.lit, L.slotLit, L.hist, L.metas, streamArena, L.slotM, L.streamCapWords, L.outs);
+    if (nb) zl_k_enc_literals<<<gq, ZL_ENT_WARPS * 32, smL, st>>>(L.blocks, nb, L.lit, L.slotLit, L.hist, L.metas, streamArena, L.slotM, L.streamCapWords, L.outs);
     if (ev) cudaEventRecord(ev[3], st);
-    if (nb) zl_k_enc_sequences<<<gq, 32, smS, st>>>(L.blocks, nb, L.recs, L.slotRec, L.metas, seqArena, L.slotM, L.seqCapWords, L.outs);
+    if (nb) zl_k_enc_sequences<<<gq, ZL_ENT_WARPS * 32, smS, st>>>(L.blocks, nb, L.recs, L.slotRec, L.metas, seqArena, L.slotM, L.seqCapWords, L.seqCapWords, L.outs);
     if (ev) cudaEventRecord(ev[4], st);
     zl_k_enc_plan<<<(L.nframes + 127) / 128, 128, 0, st>>>(L.frames, L.nframes, L.blocks, L.metas, L.outs, L.plans, L.results);
     if (nb) zl_k_enc_assemble<<<(nb + ZL_ASM_WARPS - 1) / ZL_ASM_WARPS, ZL_ASM_WARPS * 32, 0, st>>>(L.frames, L.blocks, nb, L.plans, L.outs, L.lit, L.slotLit, streamArena, L.slotM,
