@@ -39,13 +39,14 @@ extern "C" size_t zl_emul_decompress_frame(void* dstv, size_t cap, const void* s
     }
     {   // K1b
         static ZlSeqSm f;
+        static i16 norm[3 * ZL_NORM_STRIDE];
         zl_seq_begin_frame(f, info, 0);
         for (u32 b = 0; b < info.nblocks; b++) {
             ZlBlockHdr h = hdrs[b];
             if ((h.flags & 3) != 2) { zl_seq_plain_block(f, d, h); continue; }
-            zl_seq_head(f, d, h, g_ct);
-            if (!f.ctl.err && f.ctl.needBuild) for (u32 q = 0; q < 3; q++) zl_seq_fse_build(f, q, g_ct);
-            zl_seq_decode(f, d, h, recs.data(), wbase, bias, g_ct);
+            zl_seq_head(f, d, h, g_ct, norm);
+            if (!f.ctl.err && f.ctl.needBuild) for (u32 q = 0; q < 3; q++) zl_seq_fse_build(f, q, norm);
+            zl_seq_decode(f, d, h, recs.data(), wbase, bias, g_ct, nullptr);
             hdrs[b] = h;
         }
         zl_seq_finish_frame(f, info);

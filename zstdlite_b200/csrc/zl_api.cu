@@ -177,7 +177,7 @@ struct ZSTD_DCtx_s {
     cudaEvent_t stageEv[ZL_DEC_STAGES + 1] = {};
     double lastKernelMs = 0.0, lastStageMs[ZL_DEC_STAGES] = {};
     unsigned long long launches = 0;
-    ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dSrc, dDst;
+    ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dNorm, dSrc, dDst;
     ZlPinBuf hDescs, hResults;
 };
 
@@ -195,7 +195,7 @@ ZL_EXPORT ZSTD_DCtx* ZSTD_createDCtx(void) { return new (std::nothrow) ZSTD_DCtx
 ZL_EXPORT size_t ZSTD_freeDCtx(ZSTD_DCtx* c)
 {
     if (!c) return 0;
-    ZlDevBuf* bufs[] = {&c->dDictContent, &c->dDict, &c->dDescs, &c->dInfos, &c->dResults, &c->dHdr, &c->dRec, &c->dCk, &c->dLit, &c->dSrc, &c->dDst};
+    ZlDevBuf* bufs[] = {&c->dDictContent, &c->dDict, &c->dDescs, &c->dInfos, &c->dResults, &c->dHdr, &c->dRec, &c->dCk, &c->dLit, &c->dNorm, &c->dSrc, &c->dDst};
     for (ZlDevBuf* b : bufs) b->release();
     c->hDescs.release(); c->hResults.release();
     if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
@@ -255,7 +255,6 @@ ZL_EXPORT size_t ZSTD_DCtx_loadDictionary(ZSTD_DCtx* c, const void* dict, size_t
     memset(hd, 0, sizeof(*hd));
     size_t contentOff = 0;
     if (dictSize >= 8 && zl_rd32(d) == ZL_MAGIC_DICT) {
-        static const ZlConstTables ct = {ZL_LL_BASE_INIT, ZL_ML_BASE_INIT, ZL_LL_BITS_INIT, ZL_ML_BITS_INIT, ZL_LL_DEFNORM_INIT, ZL_ML_DEFNORM_INIT, ZL_OF_DEFNORM_INIT};
         hd->dictID = zl_rd32(d + 4);
         ZlLitSm* f = new (std::nothrow) ZlLitSm();
         if (!f) { delete hd; return ZL_ERROR(memory_allocation); }
@@ -269,8 +268,8 @@ ZL_EXPORT size_t ZSTD_DCtx_loadDictionary(ZSTD_DCtx* c, const void* dict, size_t
             u32 t = order[k], ms = maxSym[t], tl; i16 norm[64];
             u32 h = p < dictSize ? zl_read_ncount(d + p, (u32)(dictSize - p), norm, &ms, &tl) : 0;
             if (!h || tl > maxLog[t]) { ok = false; break; }
-            u32* tbl = t == 0 ? hd->fseLL : (t == 1 ? hd->fseOF : hd->fseML);
-            if (!zl_fse_build(tbl, norm, ms, tl, t, ct)) { ok = false; break; }
+            u16* tbl = t == 0 ? hd->fseLL : (t == 1 ? hd->fseOF : hd->fseML);
+            if (!zl_fse_build(tbl, norm, ms, tl)) { ok = false; break; }
             hd->tlog[t] = tl; p += h;
         }
         if (ok && p + 12 > dictSize) ok = false;
@@ -355,13 +354,13 @@ ZL_EXPORT size_t zl_decompress_batch(ZSTD_DCtx* c, const void* const* src, const
         lit += ((u64)d.litCap + 15) & ~15ull; rec += d.recCap; hdr += d.hdrCap; ck += d.ckCap;
     }
     if (!c->dDescs.reserve(n * sizeof(ZlFrameDesc)) || !c->dInfos.reserve(n * sizeof(ZlFrameInfo)) || !c->dResults.reserve(n * 8) ||
-        !c->dLit.reserve(lit + 64) || !c->dRec.reserve(rec * 8) || !c->dHdr.reserve(hdr * sizeof(ZlBlockHdr)))
+        !c->dLit.reserve(lit + 64) || !c->dRec.reserve(rec * 8) || !c->dNorm.reserve(n * 3 * ZL_NORM_STRIDE * sizeof(i16)) || !c->dHdr.reserve(hdr * sizeof(ZlBlockHdr)))
         return ZL_ERROR(memory_allocation);
     cudaMemcpyAsync(c->dDescs.p, hd, n * sizeof(ZlFrameDesc), cudaMemcpyHostToDevice, st);
     if (!dev) for (const ZlRun& r : sruns) if (r.bytes) cudaMemcpyAsync(c->dSrc.as<u8>() + r.devOff, r.hbase, r.bytes, cudaMemcpyHostToDevice, st);
     ZlDecodeLaunch L;
     L.descs = c->dDescs.as<ZlFrameDesc>(); L.infos = c->dInfos.as<ZlFrameInfo>(); L.hdrArena = c->dHdr.as<ZlBlockHdr>();
-    L.recArena = c->dRec.as<u64>(); L.litArena = c->dLit.as<u8>(); L.results = c->dResults.as<u64>();
+    L.recArena = c->dRec.as<u64>(); L.litArena = c->dLit.as<u8>(); L.normArena = c->dNorm.as<i16>(); L.results = c->dResults.as<u64>();
     L.nframes = (u32)n; L.verifyChecksum = !c->forceIgnoreChecksum; L.dict = c->hasDict ? c->dDict.as<ZlDictDev>() : nullptr;
     if (!c->stageEv[0]) for (cudaEvent_t& e : c->stageEv) cudaEventCreate(&e);
     L.stageEv = c->stageEv;

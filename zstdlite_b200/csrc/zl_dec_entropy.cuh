@@ -18,12 +18,18 @@
 #pragma once
 #include "zl_common.cuh"
 
-// ---- packed FSE decode cell: nbBits[0:8) nbAdditionalBits[8:16) newStateBase[16:26) symbol[26:32)
+// ---- packed FSE decode cell of the tiny Huffman-weight table (u32): nbBits[0:8) newStateBase[16:26) symbol[26:32)
 ZL_HD u32 zl_fse_pack(u32 base, u32 nb, u32 add, u32 sym) { return nb | (add << 8) | (base << 16) | (sym << 26); }
 #define ZL_FSE_NB(e) ((e) & 0xFFu)
-#define ZL_FSE_ADD(e) (((e) >> 8) & 0xFFu)
 #define ZL_FSE_BASE(e) (((e) >> 16) & 1023u)
 #define ZL_FSE_SYM(e) ((e) >> 26)
+// ---- packed LL / OF / ML decode cell (u16): symbol[0:6) ns[6:16), where ns in [1, 2*size) is the value
+// ZSTD_buildFSETable (zstd.c:43605-43613) calls `nextState`: nbBits = log - highbit(ns), newStateBase = (ns << nbBits)
+// - size.  16-bit cells halve the shared-memory footprint of a frame, which is what bounds the frames in flight per SM;
+// the number of additional bits is a function of the symbol (OF: the symbol itself; LL / ML: ZlConstTables).
+ZL_HD u16 zl_seq_cell(u32 ns, u32 sym) { return (u16)(sym | (ns << 6)); }
+#define ZL_CELL_SYM(e) ((e) & 63u)
+#define ZL_CELL_NS(e) ((e) >> 6)
 
 // ---- backward bit reader (restates BIT_DStream_t, zstd.c:2352-2550) ---------------------------------------
 // `wbase` is the frame's src pointer rounded down to 4 bytes, `bias` = src - wbase (0..3); stream positions
@@ -168,20 +174,20 @@ ZL_HD u32 zl_read_ncount(const u8* src, u32 srcSize, i16* norm, u32* maxSymIO, u
 }
 
 // ---- FSE decode table build (one lane per table): zstd.c:43497-43613 ------------------------------------------
-// kind 0 LL, 1 OF, 2 ML decides the additional-bits field.  `tbl` first receives symbols, then cells.
-ZL_HD bool zl_fse_build(u32* tbl, const i16* norm, u32 maxSym, u32 log, u32 kind, const ZlConstTables& ct)
+// `tbl` first receives symbols, then cells.
+ZL_HD bool zl_fse_build(u16* tbl, const i16* norm, u32 maxSym, u32 log)
 {
     u32 size = 1u << log, high = size - 1, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
     u16 next[64];
     for (u32 s = 0; s <= maxSym; s++) {
-        if (norm[s] == -1) { tbl[high--] = s; next[s] = 1; }
+        if (norm[s] == -1) { tbl[high--] = (u16)s; next[s] = 1; }
         else next[s] = (u16)norm[s];
     }
     u32 pos = 0;
     for (u32 s = 0; s <= maxSym; s++) {
         i32 n = norm[s];
         for (i32 i = 0; i < n; i++) {
-            tbl[pos] = s;
+            tbl[pos] = (u16)s;
             pos = (pos + step) & mask;
             while (pos > high) pos = (pos + step) & mask;
         }
@@ -189,10 +195,7 @@ ZL_HD bool zl_fse_build(u32* tbl, const i16* norm, u32 maxSym, u32 log, u32 kind
     if (pos != 0) return false;
     for (u32 u = 0; u < size; u++) {
         u32 s = tbl[u];
-        u32 ns = next[s]++;
-        u32 nb = log - zl_highbit(ns);
-        u32 add = kind == 0 ? ct.llBits[s] : (kind == 1 ? s : ct.mlBits[s]);
-        tbl[u] = zl_fse_pack((ns << nb) - size, nb, add, s);
+        tbl[u] = zl_seq_cell(next[s]++, s);
     }
     return true;
 }
@@ -533,16 +536,17 @@ struct ZlSeqCtl {
     u32 tlog[3], maxSym[3], bErr[3];
     u32 bitBeg, bitEnd;
 };
-struct ZlSeqSm {
-    u32 fseLL[512];
-    u32 fseML[512];
-    u32 fseOF[256];
-    i16 norm[3][64];
+struct ZlSeqSm {            // 2,644 B: with 8 frames per warp, 10 warps fit one SM's shared memory
+    u16 fseLL[512];
+    u16 fseML[512];
+    u16 fseOF[256];
     ZlSeqCtl ctl;
 };
+#define ZL_NORM_STRIDE 64       // i16 per table in the per-frame normalized-count scratch (3 tables)
 
-// sequences section header (lane 0): zstd.c:43707-43790
-ZL_HD void zl_seq_head(ZlSeqSm& f, const ZlFrameDesc& d, const ZlBlockHdr& h, const ZlConstTables& ct)
+// sequences section header (lane 0): zstd.c:43707-43790.  `norm` = 3 x ZL_NORM_STRIDE i16 of scratch (global memory
+// in the kernel: it is only touched while tables are (re)built, so it does not deserve shared memory).
+ZL_HD void zl_seq_head(ZlSeqSm& f, const ZlFrameDesc& d, const ZlBlockHdr& h, const ZlConstTables& ct, i16* norm)
 {
     ZlSeqCtl& c = f.ctl;
     c.needBuild = 0; c.nbSeq = 0;
@@ -563,21 +567,21 @@ ZL_HD void zl_seq_head(ZlSeqSm& f, const ZlFrameDesc& d, const ZlBlockHdr& h, co
     const u32 maxSymT[3] = {35, 31, 52}, maxLogT[3] = {9, 8, 9}, defLogT[3] = {6, 5, 6};
     for (u32 t = 0; t < 3; t++) {
         u32 mode = (modes >> (6 - 2 * t)) & 3;
-        u32* tbl = t == 0 ? f.fseLL : (t == 1 ? f.fseOF : f.fseML);
+        u16* tbl = t == 0 ? f.fseLL : (t == 1 ? f.fseOF : f.fseML);
+        i16* nt = norm + t * ZL_NORM_STRIDE;
         if (mode == 0) {                               // predefined
             const i16* def = t == 0 ? ct.llDef : (t == 1 ? ct.ofDef : ct.mlDef);
             u32 nsym = t == 0 ? 36 : (t == 1 ? 29 : 53);
-            for (u32 s = 0; s < nsym; s++) f.norm[t][s] = def[s];
+            for (u32 s = 0; s < nsym; s++) nt[s] = def[s];
             c.maxSym[t] = nsym - 1; c.tlog[t] = defLogT[t]; c.needBuild |= 1u << t;
         } else if (mode == 1) {                        // RLE
             if (ip >= iend) { c.err = ZL_E_corruption_detected; return; }
             u32 s = src[ip++];
             if (s > maxSymT[t]) { c.err = ZL_E_corruption_detected; return; }
-            u32 add = t == 0 ? ct.llBits[s] : (t == 1 ? s : ct.mlBits[s]);
-            tbl[0] = zl_fse_pack(0, 0, add, s); c.tlog[t] = 0;
+            tbl[0] = zl_seq_cell(1, s); c.tlog[t] = 0;
         } else if (mode == 2) {                        // FSE-compressed
             u32 ms = maxSymT[t], tl;
-            u32 hsz = zl_read_ncount(src + ip, iend - ip, f.norm[t], &ms, &tl);
+            u32 hsz = zl_read_ncount(src + ip, iend - ip, nt, &ms, &tl);
             if (!hsz || tl > maxLogT[t]) { c.err = ZL_E_corruption_detected; return; }
             ip += hsz; c.maxSym[t] = ms; c.tlog[t] = tl; c.needBuild |= 1u << t;
         } else {                                       // repeat
@@ -588,18 +592,18 @@ ZL_HD void zl_seq_head(ZlSeqSm& f, const ZlFrameDesc& d, const ZlBlockHdr& h, co
     c.bitBeg = ip; c.bitEnd = iend;
 }
 
-ZL_HD void zl_seq_fse_build(ZlSeqSm& f, u32 t, const ZlConstTables& ct)
+ZL_HD void zl_seq_fse_build(ZlSeqSm& f, u32 t, const i16* norm)
 {
     ZlSeqCtl& c = f.ctl;
     c.bErr[t] = 0;
     if (!((c.needBuild >> t) & 1)) return;
-    u32* tbl = t == 0 ? f.fseLL : (t == 1 ? f.fseOF : f.fseML);
-    if (!zl_fse_build(tbl, f.norm[t], c.maxSym[t], c.tlog[t], t, ct)) c.bErr[t] = 1;
+    u16* tbl = t == 0 ? f.fseLL : (t == 1 ? f.fseOF : f.fseML);
+    if (!zl_fse_build(tbl, norm + t * ZL_NORM_STRIDE, c.maxSym[t], c.tlog[t])) c.bErr[t] = 1;
 }
 
 // One sequence (zstd.c:44241-44358).  Bit order in the stream: OF, ML, LL additional bits, then the LL, ML, OF
 // state transitions (skipped for the last sequence).  Both groups are extracted from a snapshot of the 64-bit
-// window at positions that are prefix sums of the table cells' bit counts, so the reads are independent of each
+// window at positions that are prefix sums of the bit counts, so the reads are independent of each
 // other and only the state -> cell -> state chain is serial.
 struct ZlSeqRegs {
     u32 sLL, sOF, sML;
@@ -612,7 +616,8 @@ ZL_HD void zl_seq_step(const ZlSeqSm& f, ZlBitR& b, const u32* wbase, const ZlCo
 {
     zl_br_refill(b, wbase);                                              // n >= 33
     const u32 eLL = f.fseLL[r.sLL], eOF = f.fseOF[r.sOF], eML = f.fseML[r.sML];
-    const u32 aOF = ZL_FSE_ADD(eOF), aML = ZL_FSE_ADD(eML), aLL = ZL_FSE_ADD(eLL);
+    const u32 llCode = ZL_CELL_SYM(eLL), mlCode = ZL_CELL_SYM(eML);
+    const u32 aOF = ZL_CELL_SYM(eOF), aML = ct.mlBits[mlCode], aLL = ct.llBits[llCode];
     const u32 cA = aOF + aML + aLL;
     u32 ofx, mlx, llx;
     if (cA <= 32) {
@@ -629,16 +634,17 @@ ZL_HD void zl_seq_step(const ZlSeqSm& f, ZlBitR& b, const u32* wbase, const ZlCo
     }
     if (!kLast) {                                                        // LL, ML, OF order: zstd.c:44347-44353
         zl_br_refill(b, wbase);
-        const u32 bLL = ZL_FSE_NB(eLL), bML = ZL_FSE_NB(eML), bOF = ZL_FSE_NB(eOF);
+        const u32 gLL = f.ctl.tlog[0], gOF = f.ctl.tlog[1], gML = f.ctl.tlog[2];
+        const u32 nLL = ZL_CELL_NS(eLL), nML = ZL_CELL_NS(eML), nOF = ZL_CELL_NS(eOF);
+        const u32 bLL = gLL - zl_highbit(nLL), bML = gML - zl_highbit(nML), bOF = gOF - zl_highbit(nOF);
         const u32 hi = b.hi, lo = b.lo;
-        r.sLL = ZL_FSE_BASE(eLL) + zl_shr(hi, 32u - bLL);
-        r.sML = ZL_FSE_BASE(eML) + zl_shr(zl_fsl(lo, hi, bLL), 32u - bML);
-        r.sOF = ZL_FSE_BASE(eOF) + zl_shr(zl_fsl(lo, hi, bLL + bML), 32u - bOF);
+        r.sLL = ((nLL << bLL) - (1u << gLL)) + zl_shr(hi, 32u - bLL);
+        r.sML = ((nML << bML) - (1u << gML)) + zl_shr(zl_fsl(lo, hi, bLL), 32u - bML);
+        r.sOF = ((nOF << bOF) - (1u << gOF)) + zl_shr(zl_fsl(lo, hi, bLL + bML), 32u - bOF);
         zl_br_skip(b, bLL + bML + bOF);                                  // <= 26 bits
     }
-    const u32 llCode = ZL_FSE_SYM(eLL);
     u32 ll = ct.llBase[llCode] + llx;
-    u32 ml = ct.mlBase[ZL_FSE_SYM(eML)] + mlx;
+    u32 ml = ct.mlBase[mlCode] + mlx;
     // offset / repcode history, branch-free (zstd.c:44290-44326).  aOF is the offset code.
     const u32 ll0 = (llCode == 0);
     const bool isRep = aOF <= 1;
@@ -672,45 +678,53 @@ ZL_HD void zl_seq_step(const ZlSeqSm& f, ZlBitR& b, const u32* wbase, const ZlCo
 }
 
 #if defined(__CUDACC__)
+// code -> (base value | additional bits << 24) for LL (36 entries) then ML (53 entries); built once per CTA in
+// shared memory from the constant tables so one load serves both the bit count (on the state chain) and the base.
+#define ZL_XTAB_WORDS (36 + 53)
 // Fast path over consecutive non-last sequences whose additional bits fit one window (<= 32) and whose lengths fit a
 // single record.  Returns how many sequences it consumed; it stops BEFORE any sequence it cannot handle (the generic
 // zl_seq_step takes that one) and on errors (r.err set).  The loop is rotated: the three table cells of the next
 // sequence are requested as soon as the new states are known, and the record of the current one is built under
-// that latency.
-__device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, ZlBitR& b, const u32* wbase, const ZlConstTables& ct,
+// that latency.  States are kept "primed" (state + table size): a primed state is simply the cell's ns with the
+// nbBits fresh stream bits shifted in from the right -- one funnel shift -- and indexes the table at (base - size).
+__device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xtab, ZlBitR& b, const u32* wbase,
                                                 ZlSeqRegs& r, u64* rp, u32 maxIter, u32 safeCap, u32 litSize, u32 outCap,
                                                 u32 capErr, u32 hist)
 {
-    const u32 tLL = zl_smem_addr(f.fseLL), tOF = zl_smem_addr(f.fseOF), tML = zl_smem_addr(f.fseML);
-    const u32 cLL = zl_smem_addr(ct.llBase), cML = zl_smem_addr(ct.mlBase);
+    const u32 gLL = f.ctl.tlog[0], gOF = f.ctl.tlog[1], gML = f.ctl.tlog[2];
+    const u32 zLL = 1u << gLL, zOF = 1u << gOF, zML = 1u << gML;
+    const u32 tLL = zl_smem_addr(f.fseLL) - 2u * zLL, tOF = zl_smem_addr(f.fseOF) - 2u * zOF, tML = zl_smem_addr(f.fseML) - 2u * zML;
+    const u32 kLL = 31u - gLL, kOF = 31u - gOF, kML = 31u - gML;          // nbBits = clz(ns) - k
+    const u32 cLL = zl_smem_addr(xtab), cML = cLL + 36u * 4u;
     u32 hi = b.hi, lo = b.lo, nextw = b.nextw;
     i32 n = b.n, wi = b.wi;
     const i32 wlow = b.wlow;
-    u32 sLL = r.sLL, sOF = r.sOF, sML = r.sML, rep0 = r.rep0, rep1 = r.rep1, rep2 = r.rep2;
+    u32 sLL = r.sLL + zLL, sOF = r.sOF + zOF, sML = r.sML + zML, rep0 = r.rep0, rep1 = r.rep1, rep2 = r.rep2;
     u32 outPos = r.outPos, litPos = r.litPos, nrec = r.nrec;
-    u32 eLL = zl_lds32(tLL + (sLL << 2)), eOF = zl_lds32(tOF + (sOF << 2)), eML = zl_lds32(tML + (sML << 2));
+    u32 eLL = zl_lds16(tLL + (sLL << 1)), eOF = zl_lds16(tOF + (sOF << 1)), eML = zl_lds16(tML + (sML << 1));
     u32 it = 0;
     while (it < maxIter) {
-        const u32 aOF = ZL_FSE_ADD(eOF), aML = ZL_FSE_ADD(eML), aLL = ZL_FSE_ADD(eLL);
-        const u32 llCode = ZL_FSE_SYM(eLL), mlCode = ZL_FSE_SYM(eML);
+        const u32 llCode = ZL_CELL_SYM(eLL), mlCode = ZL_CELL_SYM(eML), aOF = ZL_CELL_SYM(eOF);
+        const u32 xl = zl_lds32(cLL + (llCode << 2)), xm = zl_lds32(cML + (mlCode << 2));
+        const u32 nLL = ZL_CELL_NS(eLL), nML = ZL_CELL_NS(eML), nOF = ZL_CELL_NS(eOF);
+        const u32 bLL = (u32)__clz((int)nLL) - kLL, bML = (u32)__clz((int)nML) - kML, bOF = (u32)__clz((int)nOF) - kOF;
+        const u32 aLL = xl >> 24, aML = xm >> 24;
         const u32 c2 = aOF + aML, cA = c2 + aLL;
         if (cA > 32 || llCode >= 35 || mlCode >= 51 || nrec >= safeCap) break;           // rare: leave it to the generic step
-        const u32 llb = zl_lds32(cLL + (llCode << 2)), mlb = zl_lds32(cML + (mlCode << 2));
         ZL_REFILL_DEV();                                                                   // n >= 33
         const u32 ofx = zl_shr(hi, 32u - aOF);
         const u32 mlx = zl_shr(zl_fsl(lo, hi, aOF), 32u - aML);
         const u32 llx = zl_shr(zl_fsl(lo, hi, c2), 32u - aLL);
         hi = zl_fsl(lo, hi, cA); lo = zl_shl(lo, cA); n -= (i32)cA;
         ZL_REFILL_DEV();
-        const u32 bLL = ZL_FSE_NB(eLL), bML = ZL_FSE_NB(eML), bOF = ZL_FSE_NB(eOF);
         const u32 d2 = bLL + bML, cB = d2 + bOF;                                           // <= 26
-        sLL = ZL_FSE_BASE(eLL) + zl_shr(hi, 32u - bLL);                                    // LL, ML, OF order: zstd.c:44347-44353
-        sML = ZL_FSE_BASE(eML) + zl_shr(zl_fsl(lo, hi, bLL), 32u - bML);
-        sOF = ZL_FSE_BASE(eOF) + zl_shr(zl_fsl(lo, hi, d2), 32u - bOF);
+        sLL = __funnelshift_l(hi, nLL, bLL);                                               // LL, ML, OF order: zstd.c:44347-44353
+        sML = __funnelshift_l(zl_fsl(lo, hi, bLL), nML, bML);
+        sOF = __funnelshift_l(zl_fsl(lo, hi, d2), nOF, bOF);
         hi = zl_fsl(lo, hi, cB); lo <<= cB; n -= (i32)cB;
-        eLL = zl_lds32(tLL + (sLL << 2)); eOF = zl_lds32(tOF + (sOF << 2)); eML = zl_lds32(tML + (sML << 2));
+        eLL = zl_lds16(tLL + (sLL << 1)); eOF = zl_lds16(tOF + (sOF << 1)); eML = zl_lds16(tML + (sML << 1));
         // ---- record of the current sequence (off the state chain)
-        const u32 ll = llb + llx, ml = mlb + mlx;
+        const u32 ll = (xl & 0xFFFFFFu) + llx, ml = (xm & 0xFFFFFFu) + mlx;
         const u32 ll0 = (llCode == 0);
         const bool isRep = aOF <= 1;
         const u32 idx = aOF == 0 ? ll0 : 1u + ll0 + ofx;
@@ -728,16 +742,18 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, ZlBitR& b, con
         it++;
     }
     b.hi = hi; b.lo = lo; b.nextw = nextw; b.n = n; b.wi = wi;
-    r.sLL = sLL; r.sOF = sOF; r.sML = sML; r.rep0 = rep0; r.rep1 = rep1; r.rep2 = rep2;
+    r.sLL = sLL - zLL; r.sOF = sOF - zOF; r.sML = sML - zML; r.rep0 = rep0; r.rep1 = rep1; r.rep2 = rep2;
     r.outPos = outPos; r.litPos = litPos; r.nrec = nrec;
     return it;
 }
 #endif
 
 // serial sequence decode of one block (lane 0): zstd.c:44627-44700.  Completes the block's ZlBlockHdr.
+// `xtab` is only used by the device fast path (null in the CPU emulation).
 ZL_HD void zl_seq_decode(ZlSeqSm& f, const ZlFrameDesc& d, ZlBlockHdr& h, u64* recs, const u32* wbase, u32 bias,
-                         const ZlConstTables& ct)
+                         const ZlConstTables& ct, const u32* xtab)
 {
+    (void)xtab;
     ZlSeqCtl& c = f.ctl;
     if (!c.err && c.needBuild) { for (u32 t = 0; t < 3; t++) if (c.bErr[t]) c.err = ZL_E_corruption_detected; }
     const u32 litSize = h.litSize;
@@ -764,7 +780,7 @@ ZL_HD void zl_seq_decode(ZlSeqSm& f, const ZlFrameDesc& d, ZlBlockHdr& h, u64* r
             const u32 safeCap = recCap - 4;                  // split path re-checks exactly
             for (u32 i = 0; i + 1 < nbSeq; i++) {
 #if defined(__CUDA_ARCH__)
-                i += zl_seq_fast_loop(f, b, wbase, ct, r, rp, nbSeq - 1 - i, safeCap, litSize, outCap, capErr, hist);
+                i += zl_seq_fast_loop(f, xtab, b, wbase, r, rp, nbSeq - 1 - i, safeCap, litSize, outCap, capErr, hist);
                 if (r.err || r.nrec >= safeCap || i + 1 >= nbSeq) break;
 #endif
                 zl_seq_step<false>(f, b, wbase, ct, r, rp, recCap, litSize, outCap, capErr, hist);

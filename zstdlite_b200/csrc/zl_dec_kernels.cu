@@ -10,8 +10,6 @@ __constant__ ZlConstTables c_tables = {
     ZL_LL_BASE_INIT, ZL_ML_BASE_INIT, ZL_LL_BITS_INIT, ZL_ML_BITS_INIT,
     ZL_LL_DEFNORM_INIT, ZL_ML_DEFNORM_INIT, ZL_OF_DEFNORM_INIT};
 
-#define ZL_CT_BYTES ((sizeof(ZlConstTables) + 15) & ~(size_t)15)
-
 // ---- K1a: literals ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
 zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, ZlBlockHdr* hdrArena,
@@ -53,20 +51,19 @@ zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ i
 }
 
 // ---- K1b: sequences -----------------------------------------------------------------------------------------
+#define ZL_XTAB_BYTES ((ZL_XTAB_WORDS * 4 + 15) & ~15)
 __global__ void __launch_bounds__(32)
 zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, ZlBlockHdr* hdrArena,
-               u64* recArena, u32 nframes, const ZlDictDev* dict)
+               u64* recArena, i16* normArena, u32 nframes, const ZlDictDev* dict)
 {
     extern __shared__ __align__(16) u8 smraw[];
-    ZlConstTables& ct = *reinterpret_cast<ZlConstTables*>(smraw);
-    ZlSeqSm* fs = reinterpret_cast<ZlSeqSm*>(smraw + ZL_CT_BYTES);
+    u32* xtab = reinterpret_cast<u32*>(smraw);
+    ZlSeqSm* fs = reinterpret_cast<ZlSeqSm*>(smraw + ZL_XTAB_BYTES);
+    const ZlConstTables& ct = c_tables;          // constant memory: only the header parser and the rare generic step index it
     const u32 lane = threadIdx.x, quad = lane >> 2, q = lane & 3;
     const u32 qmask = 0xFu << (quad * 4);
-    {   // constant tables -> shared memory (divergent lookups by code are conflict-cheap there)
-        const u32* s = reinterpret_cast<const u32*>(&c_tables);
-        u32* dd = reinterpret_cast<u32*>(&ct);
-        for (u32 i = lane; i < sizeof(ZlConstTables) / 4; i += 32) dd[i] = s[i];
-    }
+    for (u32 i = lane; i < ZL_XTAB_WORDS; i += 32)
+        xtab[i] = i < 36 ? (c_tables.llBase[i] | ((u32)c_tables.llBits[i] << 24)) : (c_tables.mlBase[i - 36] | ((u32)c_tables.mlBits[i - 36] << 24));
     __syncwarp();
     const u32 frame = blockIdx.x * ZL_QUADS_PER_WARP + quad;
     if (frame >= nframes) return;
@@ -75,6 +72,7 @@ zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ 
     ZlFrameInfo& info = infos[frame];
     ZlBlockHdr* hdrs = hdrArena + d.hdrBase;
     u64* recs = recArena + d.recBase;
+    i16* norm = normArena + (size_t)frame * (3 * ZL_NORM_STRIDE);
     const u32 bias = (u32)(((size_t)d.src) & 3);
     const u32* wbase = reinterpret_cast<const u32*>(d.src - bias);
     const u32 nblocks = info.nblocks;
@@ -95,12 +93,12 @@ zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ 
     for (u32 b = 0; b < nblocks; b++) {
         ZlBlockHdr h = hdrs[b];
         if ((h.flags & 3) != 2) { if (q == 0) zl_seq_plain_block(f, d, h); continue; }
-        if (q == 0) zl_seq_head(f, d, h, ct);
+        if (q == 0) zl_seq_head(f, d, h, ct, norm);
         __syncwarp(qmask);
         const u32 build = f.ctl.err ? 0u : f.ctl.needBuild;
         __syncwarp(qmask);
-        if (build) { if (q < 3) zl_seq_fse_build(f, q, ct); __syncwarp(qmask); }
-        if (q == 0) { zl_seq_decode(f, d, h, recs, wbase, bias, ct); hdrs[b] = h; }
+        if (build) { if (q < 3) zl_seq_fse_build(f, q, norm); __syncwarp(qmask); }
+        if (q == 0) { zl_seq_decode(f, d, h, recs, wbase, bias, ct, xtab); hdrs[b] = h; }
     }
     if (q == 0) zl_seq_finish_frame(f, info);
 }
@@ -165,7 +163,7 @@ zl_k_xxh64(const u8* const* __restrict__ ptrs, const u32* __restrict__ sizes, u6
 
 // ---- launchers ---------------------------------------------------------------------------------------
 size_t zl_literals_smem_bytes() { return ZL_QUADS_PER_WARP * sizeof(ZlLitSm); }
-size_t zl_sequences_smem_bytes() { return ZL_CT_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlSeqSm); }
+size_t zl_sequences_smem_bytes() { return ZL_XTAB_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlSeqSm); }
 
 cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
 {
@@ -180,7 +178,7 @@ cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
     if (ev) cudaEventRecord(ev[0], st);
     zl_k_literals<<<g1, 32, smA, st>>>(L.descs, L.infos, L.hdrArena, L.litArena, L.nframes, L.dict);
     if (ev) cudaEventRecord(ev[1], st);
-    zl_k_sequences<<<g1, 32, smB, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.nframes, L.dict);
+    zl_k_sequences<<<g1, 32, smB, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.normArena, L.nframes, L.dict);
     if (ev) cudaEventRecord(ev[2], st);
     const u32 g2 = (L.nframes + ZL_EXEC_WARPS - 1) / ZL_EXEC_WARPS;
     if (L.dict)

@@ -10,9 +10,9 @@
 // digested dictionary in device memory (zstd.c:42053-42159, ZSTD_DDict): entropy tables in the packed
 // cell formats of zl_dec_entropy.cuh plus the raw content that acts as history before the frame.
 struct ZlDictDev {
-    u32 fseLL[512];
-    u32 fseML[512];
-    u32 fseOF[256];
+    u16 fseLL[512];
+    u16 fseML[512];
+    u16 fseOF[256];
     u16 huf[2048];
     u32 hufLog;
     u32 tlog[3];
@@ -29,6 +29,7 @@ struct ZlDecodeLaunch {
     ZlBlockHdr* hdrArena;
     u64* recArena;
     u8* litArena;
+    i16* normArena;          // 3 x 64 i16 per frame: normalized counts while FSE tables are (re)built
     u64* results;
     u32 nframes;
     int verifyChecksum;
