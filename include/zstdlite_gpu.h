@@ -104,6 +104,9 @@ size_t zl_compress_split(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity, const v
 /* CUDA stream (cudaStream_t passed as void*) the context launches on; default: a private non-blocking stream */
 size_t zl_dctx_set_stream(ZSTD_DCtx* dctx, void* cuda_stream);
 size_t zl_cctx_set_stream(ZSTD_CCtx* cctx, void* cuda_stream);
+/* 1: run the next batches as one slice on one stream with per-kernel events (zl_dctx_last_stage_ms); 0 (default): slice
+ * pipeline over internal streams, per-kernel times are then reported as -1 */
+size_t zl_dctx_set_profile(ZSTD_DCtx* dctx, int on);
 /* number of kernel launches issued by the context since creation (bench.py's gpu_launches) */
 unsigned long long zl_dctx_launch_count(const ZSTD_DCtx* dctx);
 unsigned long long zl_cctx_launch_count(const ZSTD_CCtx* cctx);

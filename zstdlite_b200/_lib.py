@@ -45,7 +45,7 @@ def lib():
         "ZSTD_getFrameHeader": (sz, [C.POINTER(FrameHeader), vp, sz]), "ZSTD_getDictID_fromFrame": (C.c_uint, [vp, sz]),
         "ZSTD_getDictID_fromDict": (C.c_uint, [vp, sz]), "ZDICT_getDictID": (C.c_uint, [vp, sz]),
         "zl_decompress_batch": (sz, [vp, pp, psz, pp, psz, psz, sz, C.c_int]),
-        "zl_dctx_set_stream": (sz, [vp, vp]), "zl_dctx_launch_count": (C.c_ulonglong, [vp]), "zl_dctx_last_kernel_ms": (C.c_double, [vp]),
+        "zl_dctx_set_stream": (sz, [vp, vp]), "zl_dctx_set_profile": (sz, [vp, C.c_int]), "zl_dctx_launch_count": (C.c_ulonglong, [vp]), "zl_dctx_last_kernel_ms": (C.c_double, [vp]),
         "zl_dctx_last_stage_ms": (C.c_double, [vp, C.c_int]),
         # compression half
         "ZSTD_createCCtx": (vp, []), "ZSTD_freeCCtx": (sz, [vp]), "ZSTD_CCtx_reset": (sz, [vp, C.c_int]),
@@ -77,6 +77,6 @@ EXPORTED_SYMBOLS = [
     "ZSTD_compressBound", "ZSTD_compress2", "ZSTD_createDCtx", "ZSTD_freeDCtx", "ZSTD_DCtx_reset", "ZSTD_DCtx_setParameter",
     "ZSTD_DCtx_getParameter", "ZSTD_DCtx_loadDictionary", "ZSTD_findFrameCompressedSize", "ZSTD_getFrameContentSize",
     "ZSTD_decompressDCtx", "ZSTD_getFrameHeader", "ZSTD_getDictID_fromFrame", "ZSTD_getDictID_fromDict", "ZDICT_getDictID",
-    "zl_decompress_batch", "zl_compress_batch", "zl_compress_split", "zl_dctx_set_stream", "zl_cctx_set_stream",
+    "zl_decompress_batch", "zl_compress_batch", "zl_compress_split", "zl_dctx_set_stream", "zl_dctx_set_profile", "zl_cctx_set_stream",
     "zl_dctx_launch_count", "zl_cctx_launch_count", "zl_dctx_last_kernel_ms", "zl_cctx_last_kernel_ms", "zl_dctx_last_stage_ms", "zl_cctx_last_stage_ms", "zl_backend_string",
 ]

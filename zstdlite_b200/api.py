@@ -69,6 +69,10 @@ class zstd_dctx:
     def set_stream(self, cuda_stream):
         _lib.lib().zl_dctx_set_stream(self._p, C.c_void_p(cuda_stream))
 
+    def set_profile(self, on):
+        """True: single-slice, single-stream batches with per-kernel timings; False (default): slice pipeline."""
+        _lib.lib().zl_dctx_set_profile(self._p, 1 if on else 0)
+
     @property
     def launch_count(self):
         return _lib.lib().zl_dctx_launch_count(self._p)

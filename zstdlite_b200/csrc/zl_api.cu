@@ -177,6 +177,11 @@ struct ZSTD_DCtx_s {
     cudaEvent_t stageEv[ZL_DEC_STAGES + 1] = {};
     double lastKernelMs = 0.0, lastStageMs[ZL_DEC_STAGES] = {};
     unsigned long long launches = 0;
+    // slice pipeline: a batch is cut into slices that run on ZL_DEC_LANES internal streams, so that the execute
+    // kernel and the PCIe copies of one slice overlap the (shared-memory-bound) entropy kernels of the others
+    cudaStream_t lane[ZL_DEC_LANES] = {};
+    cudaEvent_t laneDone[ZL_DEC_LANES] = {}, forkEv = nullptr;
+    int profileStages = 0;                 // 1: one slice, one stream, per-kernel events (zl_dctx_last_stage_ms)
     ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dNorm, dSrc, dDst;
     ZlPinBuf hDescs, hResults;
 };
@@ -200,6 +205,9 @@ ZL_EXPORT size_t ZSTD_freeDCtx(ZSTD_DCtx* c)
     c->hDescs.release(); c->hResults.release();
     if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
     for (cudaEvent_t e : c->stageEv) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->laneDone) if (e) cudaEventDestroy(e);
+    if (c->forkEv) cudaEventDestroy(c->forkEv);
+    for (cudaStream_t l : c->lane) if (l) cudaStreamDestroy(l);
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -237,6 +245,7 @@ ZL_EXPORT size_t zl_dctx_set_stream(ZSTD_DCtx* c, void* s)
     if (!s) { c->ownStream = false; c->stream = nullptr; }
     return 0;
 }
+ZL_EXPORT size_t zl_dctx_set_profile(ZSTD_DCtx* c, int on) { c->profileStages = on ? 1 : 0; return 0; }
 ZL_EXPORT unsigned long long zl_dctx_launch_count(const ZSTD_DCtx* c) { return c->launches; }
 ZL_EXPORT double zl_dctx_last_kernel_ms(const ZSTD_DCtx* c) { return c->lastKernelMs; }
 ZL_EXPORT double zl_dctx_last_stage_ms(const ZSTD_DCtx* c, int stage) { return stage >= 0 && stage < ZL_DEC_STAGES ? c->lastStageMs[stage] : -1.0; }
@@ -302,13 +311,13 @@ ZL_ALIAS(size_t, ZSTD_DCtx_getParameter, (ZSTD_DCtx*, ZSTD_dParameter, int*))
 ZL_ALIAS(size_t, ZSTD_DCtx_loadDictionary, (ZSTD_DCtx*, const void*, size_t))
 
 // ---------------------------------------------------------------------------------------------- batched decode
-static void zl_build_runs(std::vector<ZlRun>& runs, const void* const* ptr, const size_t* size, size_t n, size_t* total)
+// contiguous host ranges of frames [a, b) -> copy runs placed in the device arena from `off` on; returns the end offset
+static size_t zl_build_runs(std::vector<ZlRun>& runs, const void* const* ptr, const size_t* size, size_t a, size_t b, size_t off)
 {
-    runs.clear();
-    size_t off = 0;
-    for (size_t i = 0; i < n; i++) {
+    const size_t first = runs.size();
+    for (size_t i = a; i < b; i++) {
         const u8* p = (const u8*)ptr[i];
-        if (!runs.empty()) {
+        if (runs.size() > first) {
             ZlRun& r = runs.back();
             if (p == r.hbase + r.bytes) { r.bytes += size[i]; r.count++; continue; }
             off = (r.devOff + r.bytes + 255) & ~(size_t)255;
@@ -316,7 +325,19 @@ static void zl_build_runs(std::vector<ZlRun>& runs, const void* const* ptr, cons
         ZlRun r; r.first = i; r.count = 1; r.hbase = p; r.bytes = size[i]; r.devOff = off;
         runs.push_back(r);
     }
-    *total = runs.empty() ? 0 : runs.back().devOff + runs.back().bytes;
+    if (runs.size() > first) off = (runs.back().devOff + runs.back().bytes + 255) & ~(size_t)255;
+    return off;
+}
+
+static bool zl_dctx_lanes(ZSTD_DCtx* c)
+{
+    if (c->forkEv) return true;
+    for (int i = 0; i < ZL_DEC_LANES; i++) {
+        if (cudaStreamCreateWithFlags(&c->lane[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->laneDone[i], cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    }
+    if (cudaEventCreateWithFlags(&c->forkEv, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return true;
 }
 
 ZL_EXPORT size_t zl_decompress_batch(ZSTD_DCtx* c, const void* const* src, const size_t* srcSize, void* const* dst,
@@ -329,18 +350,47 @@ ZL_EXPORT size_t zl_decompress_batch(ZSTD_DCtx* c, const void* const* src, const
     cudaStream_t st = c->stream;
     if (!c->hDescs.reserve(n * sizeof(ZlFrameDesc)) || !c->hResults.reserve(n * 8)) return ZL_ERROR(memory_allocation);
     ZlFrameDesc* hd = c->hDescs.as<ZlFrameDesc>();
+    // ---- slices: contiguous frame ranges of about equal content; one slice when profiling or when the batch is small
+    u64 contentTotal = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (srcSize[i] > 0xFFFFFFF0ull || dstCap[i] > 0x7FFFFFF0ull) return ZL_ERROR(memory_allocation);
+        contentTotal += dstCap[i];
+    }
+    size_t nslices = 1;
+    if (!c->profileStages) {
+        // Host buffers: slices exist to overlap the PCIe copies with the kernels.  Device buffers: the entropy kernels are
+        // latency-bound (a 64 KiB frame is one ~1.5 ms dependent chain), so a launch only reaches its throughput with several
+        // times the resident capacity (148 SMs x 80 frames) in one grid; smaller slices would each pay the chain latency.
+        nslices = dev ? n / ZL_DEC_SLICE_DEV_FRAMES : (size_t)(contentTotal / ZL_DEC_SLICE_BYTES);
+        if (nslices > n / ZL_DEC_SLICE_MIN_FRAMES) nslices = n / ZL_DEC_SLICE_MIN_FRAMES;
+        if (nslices > ZL_DEC_MAX_SLICES) nslices = ZL_DEC_MAX_SLICES;
+        if (nslices < 1) nslices = 1;
+    }
+    if (nslices > 1 && !zl_dctx_lanes(c)) nslices = 1;
+    std::vector<size_t> cut(nslices + 1, n);
+    {
+        cut[0] = 0;
+        u64 acc = 0; size_t k = 1;
+        for (size_t i = 0; i < n && k < nslices; i++) {
+            acc += dstCap[i];
+            if (acc * nslices >= contentTotal * k) cut[k++] = i + 1;
+        }
+    }
     std::vector<ZlRun> sruns, druns;
+    std::vector<size_t> srunCut(nslices + 1, 0), drunCut(nslices + 1, 0);
     size_t srcTotal = 0, dstTotal = 0;
     if (!dev) {
-        zl_build_runs(sruns, src, srcSize, n, &srcTotal);
-        zl_build_runs(druns, (const void* const*)dst, dstCap, n, &dstTotal);
+        for (size_t k = 0; k < nslices; k++) {
+            srcTotal = zl_build_runs(sruns, src, srcSize, cut[k], cut[k + 1], srcTotal);
+            dstTotal = zl_build_runs(druns, (const void* const*)dst, dstCap, cut[k], cut[k + 1], dstTotal);
+            srunCut[k + 1] = sruns.size(); drunCut[k + 1] = druns.size();
+        }
         if (!c->dSrc.reserve(srcTotal + 64) || !c->dDst.reserve(dstTotal + 64)) return ZL_ERROR(memory_allocation);
     }
     u64 lit = 0, rec = 0, hdr = 0, ck = 0;
     size_t sr = 0, dr = 0;
     for (size_t i = 0; i < n; i++) {
         ZlFrameDesc& d = hd[i];
-        if (srcSize[i] > 0xFFFFFFF0ull || dstCap[i] > 0x7FFFFFF0ull) { return ZL_ERROR(memory_allocation); }
         if (dev) { d.src = (const u8*)src[i]; d.dst = (u8*)dst[i]; }
         else {
             while (sr + 1 < sruns.size() && i >= sruns[sr + 1].first) sr++;
@@ -354,27 +404,46 @@ ZL_EXPORT size_t zl_decompress_batch(ZSTD_DCtx* c, const void* const* src, const
         lit += ((u64)d.litCap + 15) & ~15ull; rec += d.recCap; hdr += d.hdrCap; ck += d.ckCap;
     }
     if (!c->dDescs.reserve(n * sizeof(ZlFrameDesc)) || !c->dInfos.reserve(n * sizeof(ZlFrameInfo)) || !c->dResults.reserve(n * 8) ||
-        !c->dLit.reserve(lit + 64) || !c->dRec.reserve(rec * 8) || !c->dNorm.reserve(n * 3 * ZL_NORM_STRIDE * sizeof(i16)) || !c->dHdr.reserve(hdr * sizeof(ZlBlockHdr)))
+        !c->dLit.reserve(lit + 64) || !c->dRec.reserve(rec * 8) || !c->dNorm.reserve(n * 3 * ZL_NORM_STRIDE * sizeof(i16)) ||
+        !c->dHdr.reserve(hdr * sizeof(ZlBlockHdr)))
         return ZL_ERROR(memory_allocation);
     cudaMemcpyAsync(c->dDescs.p, hd, n * sizeof(ZlFrameDesc), cudaMemcpyHostToDevice, st);
-    if (!dev) for (const ZlRun& r : sruns) if (r.bytes) cudaMemcpyAsync(c->dSrc.as<u8>() + r.devOff, r.hbase, r.bytes, cudaMemcpyHostToDevice, st);
-    ZlDecodeLaunch L;
-    L.descs = c->dDescs.as<ZlFrameDesc>(); L.infos = c->dInfos.as<ZlFrameInfo>(); L.hdrArena = c->dHdr.as<ZlBlockHdr>();
-    L.recArena = c->dRec.as<u64>(); L.litArena = c->dLit.as<u8>(); L.normArena = c->dNorm.as<i16>(); L.results = c->dResults.as<u64>();
-    L.nframes = (u32)n; L.verifyChecksum = !c->forceIgnoreChecksum; L.dict = c->hasDict ? c->dDict.as<ZlDictDev>() : nullptr;
     if (!c->stageEv[0]) for (cudaEvent_t& e : c->stageEv) cudaEventCreate(&e);
-    L.stageEv = c->stageEv;
+    const int verify = !c->forceIgnoreChecksum;
     cudaEventRecord(c->ev0, st);
-    cudaError_t e = zl_launch_decode(L, st);
+    if (nslices > 1) cudaEventRecord(c->forkEv, st);
+    cudaError_t e = cudaSuccess;
+    for (size_t k = 0; k < nslices && e == cudaSuccess; k++) {
+        const size_t a = cut[k], cnt = cut[k + 1] - a;
+        if (!cnt) continue;
+        cudaStream_t ls = nslices > 1 ? c->lane[k % ZL_DEC_LANES] : st;
+        if (nslices > 1 && k < ZL_DEC_LANES) cudaStreamWaitEvent(ls, c->forkEv, 0);
+        if (!dev) for (size_t r = srunCut[k]; r < srunCut[k + 1]; r++)
+            if (sruns[r].bytes) cudaMemcpyAsync(c->dSrc.as<u8>() + sruns[r].devOff, sruns[r].hbase, sruns[r].bytes, cudaMemcpyHostToDevice, ls);
+        ZlDecodeLaunch L;
+        L.descs = c->dDescs.as<ZlFrameDesc>() + a; L.infos = c->dInfos.as<ZlFrameInfo>() + a; L.hdrArena = c->dHdr.as<ZlBlockHdr>();
+        L.recArena = c->dRec.as<u64>(); L.litArena = c->dLit.as<u8>(); L.normArena = c->dNorm.as<i16>() + a * 3 * ZL_NORM_STRIDE;
+        L.results = c->dResults.as<u64>() + a;
+        L.nframes = (u32)cnt; L.verifyChecksum = verify; L.dict = c->hasDict ? c->dDict.as<ZlDictDev>() : nullptr;
+        L.stageEv = nslices > 1 ? nullptr : c->stageEv;
+        e = zl_launch_decode(L, ls);
+        c->launches += 3 + (verify ? 1 : 0);
+        if (!dev) for (size_t r = drunCut[k]; r < drunCut[k + 1]; r++)
+            if (druns[r].bytes) cudaMemcpyAsync((void*)druns[r].hbase, c->dDst.as<u8>() + druns[r].devOff, druns[r].bytes, cudaMemcpyDeviceToHost, ls);
+    }
+    if (nslices > 1)
+        for (int i = 0; i < ZL_DEC_LANES; i++) { cudaEventRecord(c->laneDone[i], c->lane[i]); cudaStreamWaitEvent(st, c->laneDone[i], 0); }
     cudaEventRecord(c->ev1, st);
-    c->launches += 3 + (L.verifyChecksum ? 1 : 0);
-    if (e != cudaSuccess) { fprintf(stderr, "zstdlite_gpu: kernel launch failed: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
+    if (e != cudaSuccess) { cudaStreamSynchronize(st); fprintf(stderr, "zstdlite_gpu: kernel launch failed: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
     cudaMemcpyAsync(c->hResults.p, c->dResults.p, n * 8, cudaMemcpyDeviceToHost, st);
-    if (!dev) for (const ZlRun& r : druns) if (r.bytes) cudaMemcpyAsync((void*)r.hbase, c->dDst.as<u8>() + r.devOff, r.bytes, cudaMemcpyDeviceToHost, st);
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { fprintf(stderr, "zstdlite_gpu: device error: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
-    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->lastKernelMs = ms;
-    for (int k = 0; k < ZL_DEC_STAGES; k++) { float t = 0; cudaEventElapsedTime(&t, c->stageEv[k], c->stageEv[k + 1]); c->lastStageMs[k] = t; }
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->lastKernelMs = ms;      // with host buffers this span includes the copies
+    for (int k = 0; k < ZL_DEC_STAGES; k++) {
+        float t = -1.0f;
+        if (nslices == 1) cudaEventElapsedTime(&t, c->stageEv[k], c->stageEv[k + 1]);
+        c->lastStageMs[k] = t;
+    }
     const u64* hr = c->hResults.as<u64>();
     for (size_t i = 0; i < n; i++) result[i] = (size_t)hr[i];
     return 0;

@@ -358,20 +358,31 @@ ZL_HD void zl_huf_fill(ZlLitSm& f, u32 q)
 __device__ __forceinline__ u32 zl_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ u32 zl_lds32(u32 a) { u32 v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ u32 zl_lds16(u32 a) { u32 v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-// if (n <= 32) { window |= nextw << (32 - n); nextw = *next word*; n += 32; }   -- no branch
+// if (n <= 32) { window |= nextw << (32 - n); nextw = *next word*; n += 32; }   -- no branch, no select on the window:
+// bits of (hi:lo) below the n valid ones are always zero and the clamped shifts make both ORs no-ops when n > 32.
+// The look-ahead load and the L1 prefetch of the sector two sectors further down are predicated PTX, so the
+// compiler cannot turn them into divergent branches.
 #define ZL_REFILL_DEV()                                                                                        \
     {                                                                                                          \
         const u32 need_ = (n <= 32) ? 1u : 0u;                                                                 \
-        const u32 w_ = nextw;                                                                                  \
+        hi |= zl_shr(nextw, (u32)n);                                                                           \
+        lo |= zl_shl(nextw, 32u - (u32)n);                                                                     \
         const i32 i_ = wi < wlow ? wlow : wi;                                                                  \
-        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}"               \
-            : "+r"(nextw) : "l"(wbase + i_), "r"(need_));                                                      \
-        if (need_ && (wi & 7) == 7) { const i32 pf_ = wi - 16; zl_prefetch(wbase + (pf_ < wlow ? wlow : pf_)); } \
-        hi |= need_ ? zl_shr(w_, (u32)n) : 0u;                                                                 \
-        lo = need_ ? zl_shl(w_, 32u - (u32)n) : lo;                                                            \
-        n += need_ ? 32 : 0;                                                                                   \
+        const i32 pf_ = (wi - 16) < wlow ? wlow : (wi - 16);                                                   \
+        const u32 pfneed_ = need_ & (((u32)wi & 7u) == 7u ? 1u : 0u);                                          \
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %3, 0;\n\tsetp.ne.u32 q, %4, 0;\n\t"              \
+                     "@p ld.global.nc.u32 %0, [%1];\n\t@q prefetch.global.L1 [%2];\n\t}"                          \
+                     : "+r"(nextw) : "l"(wbase + i_), "l"(wbase + pf_), "r"(need_), "r"(pfneed_));             \
+        n += (i32)(need_ << 5);                                                                                \
         wi -= (i32)need_;                                                                                      \
     }
+__device__ __forceinline__ u32 zl_selp(u32 a, u32 b, bool c)          // c ? a : b, guaranteed to stay a select
+{
+    u32 r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tselp.u32 %0, %1, %2, p;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"((u32)c));
+    return r;
+}
+__device__ __forceinline__ u32 zl_opaque(u32 x) { asm volatile("" : "+r"(x)); return x; }   // stops rematerialisation in loops
 #endif
 
 // one Huffman stream per lane: zstd.c:38626-38650.  Returns 0 when the stream ends exactly.
@@ -693,9 +704,10 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xta
 {
     const u32 gLL = f.ctl.tlog[0], gOF = f.ctl.tlog[1], gML = f.ctl.tlog[2];
     const u32 zLL = 1u << gLL, zOF = 1u << gOF, zML = 1u << gML;
-    const u32 tLL = zl_smem_addr(f.fseLL) - 2u * zLL, tOF = zl_smem_addr(f.fseOF) - 2u * zOF, tML = zl_smem_addr(f.fseML) - 2u * zML;
+    const u32 tLL = zl_opaque(zl_smem_addr(f.fseLL) - 2u * zLL), tOF = zl_opaque(zl_smem_addr(f.fseOF) - 2u * zOF),
+              tML = zl_opaque(zl_smem_addr(f.fseML) - 2u * zML);
     const u32 kLL = 31u - gLL, kOF = 31u - gOF, kML = 31u - gML;          // nbBits = clz(ns) - k
-    const u32 cLL = zl_smem_addr(xtab), cML = cLL + 36u * 4u;
+    const u32 cLL = zl_opaque(zl_smem_addr(xtab)), cML = cLL + 36u * 4u;
     u32 hi = b.hi, lo = b.lo, nextw = b.nextw;
     i32 n = b.n, wi = b.wi;
     const i32 wlow = b.wlow;
@@ -728,10 +740,10 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xta
         const u32 ll0 = (llCode == 0);
         const bool isRep = aOF <= 1;
         const u32 idx = aOF == 0 ? ll0 : 1u + ll0 + ofx;
-        const u32 cand = idx == 0 ? rep0 : (idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1));
-        const u32 offset = isRep ? cand : ((1u << aOF) - 3u + ofx);
-        rep2 = (!isRep || idx >= 2) ? rep1 : rep2;
-        rep1 = (!isRep || idx >= 1) ? rep0 : rep1;
+        const u32 cand = zl_selp(zl_selp(rep0 - 1, rep2, idx & 1), zl_selp(rep1, rep0, idx & 1), idx & 2);
+        const u32 offset = zl_selp(cand, (1u << aOF) - 3u + ofx, isRep);
+        rep2 = zl_selp(rep1, rep2, !isRep || idx >= 2);
+        rep1 = zl_selp(rep0, rep1, !isRep || idx >= 1);
         rep0 = offset;
         const u32 matchPos = outPos + ll;
         const bool bad = (offset == 0) | (ll > litSize - litPos) | (offset > hist + matchPos);
