@@ -7,6 +7,10 @@
 #include <cstring>
 #include "../../zstdlite_b200/csrc/zl_enc_entropy.cuh"
 #include "../../zstdlite_b200/csrc/zl_enc_match.cuh"
+#include "../../zstdlite_b200/csrc/zl_enc_dict.h"
+
+// digested dictionary of the emulation (host pointers)
+struct EmulDict { ZlEncDictDev d; std::vector<u8> content; std::vector<u32> tabS, tabL; };
 
 static u32 rd32(const u8* p) { u32 v; memcpy(&v, p, 4); return v; }
 
@@ -18,8 +22,20 @@ static u32 match_len_capped(const u8* src, u32 n, u32 p, i32 q)
     return l;
 }
 
+static u32 dict_match(const EmulDict& D, const std::vector<u32>& tab, u32 h, const u8* src, u32 n, u32 p, u32 mls, u32* off)
+{
+    const u32 e = tab[h];
+    if (!e) return 0;
+    const u32 q = e - 1, room = D.d.contentSize - q;
+    u32 lim = n - p; if (lim > ZL_M_CAP) lim = ZL_M_CAP; if (lim > room) lim = room;
+    u32 l = 0;
+    while (l < lim && src[p + l] == D.content[q + l]) l++;
+    if (l < mls) return 0;
+    *off = p + room;
+    return l;
+}
 // stage 1: M[p] for every position
-static void emul_match(const u8* src, u32 n, const ZlEncParams& P, std::vector<u32>& M)
+static void emul_match(const u8* src, u32 n, const ZlEncParams& P, std::vector<u32>& M, const EmulDict* D)
 {
     M.assign(n, 0);
     std::vector<u16> tabS((size_t)1 << P.hlogS, 0), tabL(P.hlogL ? (size_t)1 << P.hlogL : 1, 0);
@@ -34,23 +50,47 @@ static void emul_match(const u8* src, u32 n, const ZlEncParams& P, std::vector<u
             if (qL >= 0) { const u32 l = match_len_capped(src, n, p, qL); if (l >= P.mls) { bestLen = l; bestOff = p - (u32)qL; } }
         }
         if (qS >= 0) { const u32 l = match_len_capped(src, n, p, qS); if (l >= P.mls && l > bestLen) { bestLen = l; bestOff = p - (u32)qS; } }
+        u32 lim = n - p; if (lim > ZL_M_CAP) lim = ZL_M_CAP;
+        if (D && bestLen < lim) {
+            u32 dOff = 0;
+            if (P.hlogL) { const u32 l = dict_match(*D, D->tabL, zl_hash_long(lo, hi, D->d.hlogL), src, n, p, P.mls, &dOff); if (l > bestLen) { bestLen = l; bestOff = dOff; } }
+            if (bestLen < lim) { const u32 l = dict_match(*D, D->tabS, zl_hash_short(lo, hi, P.mls, D->d.hlogS), src, n, p, P.mls, &dOff); if (l > bestLen) { bestLen = l; bestOff = dOff; } }
+        }
         M[p] = bestLen ? ((bestOff << 8) | bestLen) : 0;
     }
 }
 // stage 2: greedy walk -> records, literals, histogram
-static void emul_parse(const u8* src, u32 n, const std::vector<u32>& M, std::vector<u64>& recs, std::vector<u8>& lit, u32* hist, bool firstBlock)
+static void emul_parse(const u8* src, u32 n, const std::vector<u32>& M, std::vector<u64>& recs, std::vector<u8>& lit, u32* hist, bool firstBlock,
+                       const EmulDict* D)
 {
     // blocks are compressed independently: only the first block of a frame knows the decoder's repeat offsets
     // (1, 4, 8; zstd.c:15416); later blocks start with an unknown history (0 never matches an offset)
     ZlReps reps = {firstBlock ? 1u : 0u, firstBlock ? 4u : 0u, firstBlock ? 8u : 0u};
+    if (firstBlock && D && D->d.hasEntropy) { reps.r0 = D->d.rep[0]; reps.r1 = D->d.rep[1]; reps.r2 = D->d.rep[2]; }
+    const bool repPref = firstBlock && D;
     u32 p = 0, anchor = 0;
     recs.clear(); lit.clear();
     for (u32 i = 0; i < 256; i++) hist[i] = 0;
     while (p < n) {
         const u32 m = M[p];
         if (!m) { p++; continue; }
-        u32 len = m & 0xFF; const u32 off = m >> 8;
-        if (len == ZL_M_CAP) while (p + len < n && src[p + len] == src[p + len - off]) len++;
+        u32 len = m & 0xFF; u32 off = m >> 8;
+        if (len == ZL_M_CAP && off <= p) while (p + len < n && src[p + len] == src[p + len - off]) len++;
+        // Dictionary mode only: repeat-offset preference (cf. the repcode checks at ip+1 / ip+2 of zstd.c:29989, 30801).  A match
+        // at the most recent offset starting at p, p+1 or p+2 (inside the same 32-position window) costs no offset bits; it
+        // is taken when it is at most 4 bytes shorter.  Small dictionary-compressed inputs are dominated by offset cost.
+        if (repPref && reps.r0 && off != reps.r0) {
+            for (u32 k = 0; k < 3; k++) {
+                const u32 q = p + k;
+                if ((p & 31) + k >= 32 || reps.r0 > q || q + 4 > n) continue;
+                u32 lim = n - q; if (lim > ZL_M_CAP) lim = ZL_M_CAP;
+                u32 rl = 0; while (rl < lim && src[q + rl] == src[q + rl - reps.r0]) rl++;
+                if (rl >= 4 && rl + 4 >= len) {
+                    if (rl == ZL_M_CAP) while (q + rl < n && src[q + rl] == src[q + rl - reps.r0]) rl++;
+                    p = q; len = rl; off = reps.r0; break;
+                }
+            }
+        }
         const u32 ll = p - anchor;
         for (u32 k = anchor; k < p; k++) { lit.push_back(src[k]); hist[src[k]]++; }
         recs.push_back(zl_enc_rec(ll, len, zl_rep_encode(reps, off, ll)));
@@ -60,19 +100,21 @@ static void emul_parse(const u8* src, u32 n, const std::vector<u32>& M, std::vec
 }
 
 // one block -> payload bytes (without the 3-byte block header); returns 0 when the block must be stored raw
-static u32 emul_block(const u8* src, u32 n, const ZlEncParams& P, const ZlEncConst& K, std::vector<u8>& out, bool firstBlock)
+static u32 emul_block(const u8* src, u32 n, const ZlEncParams& P, const ZlEncConst& K, std::vector<u8>& out, bool firstBlock, const EmulDict* D)
 {
+    if (!firstBlock) D = nullptr;
+    const ZlEncDictDev* De = (D && D->d.hasEntropy) ? &D->d : nullptr;
     out.clear();
     if (n < 7) return 0;                                     // zstd.c:25725
     std::vector<u32> M; std::vector<u64> recs; std::vector<u8> lit;
     static ZlHufSm hs; static ZlSeqEncSm ss; static ZlEncBlockOut o;
-    emul_match(src, n, P, M);
-    emul_parse(src, n, M, recs, lit, hs.count, firstBlock);
+    emul_match(src, n, P, M, D);
+    emul_parse(src, n, M, recs, lit, hs.count, firstBlock, D);
     const u32 nLit = (u32)lit.size(), nbSeq = (u32)recs.size();
     std::vector<u8> litPad(nLit + 16); if (nLit) memcpy(litPad.data(), lit.data(), nLit);
     // literals kernel
     std::vector<u32> sbuf[4];
-    zl_lit_plan(hs, o, litPad.data(), nLit);
+    zl_lit_plan(hs, o, litPad.data(), nLit, De);
     if (hs.ctl.mode == 2) {
         // as the CUDA kernel does it: 32 lanes, 32 / nStreams chunks per stream, exclusive scan of the chunk sizes
         const u32 per = 32 / hs.ctl.nStreams;
@@ -96,7 +138,7 @@ static u32 emul_block(const u8* src, u32 n, const ZlEncParams& P, const ZlEncCon
     ss.ctl.nbSeq = nbSeq;
     o.seqBitsSize = 0;
     if (nbSeq) {
-        for (u32 t = 0; t < 3; t++) zl_seq_build_table(ss, t, recs.data(), nbSeq, K);
+        for (u32 t = 0; t < 3; t++) zl_seq_build_table(ss, t, recs.data(), nbSeq, K, De);
         zl_seq_write_head(ss, o);
         u32 ovf = 0;
         o.seqBitsSize = zl_seq_encode(ss, K, recs.data(), nbSeq, seqBits.data(), (u32)seqBits.size(), &ovf);
@@ -113,14 +155,31 @@ static u32 emul_block(const u8* src, u32 n, const ZlEncParams& P, const ZlEncCon
 }
 
 // whole frame (zstd.c:27007 frame chunk loop, 27733 epilogue); xxh32 = low 32 bits of XXH64(content) supplied by the caller
+static size_t emul_compress(void* dstv, size_t cap, const void* srcv, size_t size, int level, int checksumFlag, unsigned xxh32, const EmulDict* D);
 extern "C" size_t zl_emul_compress_frame(void* dstv, size_t cap, const void* srcv, size_t size, int level, int checksumFlag, unsigned xxh32)
+{
+    return emul_compress(dstv, cap, srcv, size, level, checksumFlag, xxh32, nullptr);
+}
+// same with a dictionary (digested per call: test infrastructure)
+extern "C" size_t zl_emul_compress_frame_dict(void* dstv, size_t cap, const void* srcv, size_t size, int level, int checksumFlag, unsigned xxh32,
+                                              const void* dict, size_t dictSize)
+{
+    static EmulDict D; static std::vector<u8> last; static int lastLevel = -100;
+    const u8* dp = (const u8*)dict;
+    if (lastLevel != level || last.size() != dictSize || memcmp(last.data(), dp, dictSize)) {
+        if (zl_dict_digest_host(dp, dictSize, zl_enc_params(level), &D.d, D.content, D.tabS, D.tabL)) return (size_t)0 - 30;
+        last.assign(dp, dp + dictSize); lastLevel = level;
+    }
+    return emul_compress(dstv, cap, srcv, size, level, checksumFlag, xxh32, &D);
+}
+static size_t emul_compress(void* dstv, size_t cap, const void* srcv, size_t size, int level, int checksumFlag, unsigned xxh32, const EmulDict* D)
 {
     static ZlEncConst K; static bool init = false;
     if (!init) { zl_enc_const_init(&K); init = true; }
     const ZlEncParams P = zl_enc_params(level);
     const u8* src = (const u8*)srcv;
     std::vector<u8> frame(32);
-    frame.resize(zl_write_frame_header(frame.data(), size, 0, checksumFlag ? 1u : 0u));
+    frame.resize(zl_write_frame_header(frame.data(), size, D ? D->d.dictID : 0u, checksumFlag ? 1u : 0u));
     size_t pos = 0; bool first = true;
     std::vector<u8> payload;
     do {
@@ -129,7 +188,7 @@ extern "C" size_t zl_emul_compress_frame(void* dstv, size_t cap, const void* src
         u8 bh[3];
         // (no RLE blocks: the reference only emits them for non-first blocks under 25 bytes of output, zstd.c:26873-26884;
         //  a run compresses to ~10 bytes as one sequence, so the product skips the special case)
-        u32 ps = emul_block(src + pos, n, P, K, payload, first);
+        u32 ps = emul_block(src + pos, n, P, K, payload, first, D);
         if (ps == 0xFFFFFFFFu) return (size_t)0 - 1;
         if (!ps) { zl_write_block_header(bh, last, 0, n); frame.insert(frame.end(), bh, bh + 3); frame.insert(frame.end(), src + pos, src + pos + n); }
         else { zl_write_block_header(bh, last, 2, ps); frame.insert(frame.end(), bh, bh + 3); frame.insert(frame.end(), payload.begin(), payload.end()); }

@@ -18,6 +18,8 @@ def lib():
         L.zl_emul_decompress_frame.restype = C.c_size_t
         L.zl_emul_compress_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint]
         L.zl_emul_compress_frame.restype = C.c_size_t
+        L.zl_emul_compress_frame_dict.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_size_t]
+        L.zl_emul_compress_frame_dict.restype = C.c_size_t
         _lib = L
     return _lib
 
@@ -32,12 +34,15 @@ def decompress_frame(c, cap):
     return dst.raw[:r]
 
 
-def compress_frame(data, level=3, checksum=False, xxh32=0):
+def compress_frame(data, level=3, checksum=False, xxh32=0, dict=None):
     """CPU emulation of the CUDA compressor -> one frame (bytes), or ('ERR', code)."""
     data = bytes(data)
     cap = len(data) + (len(data) >> 7) + 1024
     dst = C.create_string_buffer(cap)
-    r = lib().zl_emul_compress_frame(dst, cap, data, len(data), level, 1 if checksum else 0, xxh32)
+    if dict is not None:
+        r = lib().zl_emul_compress_frame_dict(dst, cap, data, len(data), level, 1 if checksum else 0, xxh32, bytes(dict), len(dict))
+    else:
+        r = lib().zl_emul_compress_frame(dst, cap, data, len(data), level, 1 if checksum else 0, xxh32)
     if r > 2**63:
         return ("ERR", 2**64 - r)
     return dst.raw[:r]

@@ -56,3 +56,31 @@ def test_frame_header_layout_matches_reference(ref):
         ours, theirs = emul_util.compress_frame(d, 3), ref.compress(d, 3)
         hs = 5 + (1 if size < 256 else 2 if size < 65792 else 4)
         assert ours[:hs] == theirs[:hs], size
+
+
+def test_emulated_dictionary_mode(ref):
+    """configs[3] on the CPU emulation: frames made with a dictionary decode with libzstd + that dictionary, carry its
+    ID, beat the no-dictionary size, and stay within 3% of libzstd's size with the same dictionary and level."""
+    from zstdlite_b200 import corpus
+    from tests import emul_util
+    samples = corpus.small_objects(1500)
+    trained = ref.train_dict(samples[:1000], 5000)
+    raw = b"".join(samples[:20])
+    work = samples[1000:1300]
+    for dd in (trained, raw):
+        did = ref.lib().ZDICT_getDictID(dd, len(dd))
+        for lvl in (1, 3):
+            rc, rd = ref.CCtx(level=lvl, dict=dd), ref.DCtx(dict=dd)
+            ours = theirs = plain = 0
+            for s in work:
+                c = emul_util.compress_frame(s, lvl, dict=dd)
+                assert rd.decompress(c, cap=len(s)) == s
+                assert ref.lib().ZSTD_getDictID_fromFrame(c, len(c)) == did
+                ours += len(c); theirs += len(rc.compress(s)); plain += len(emul_util.compress_frame(s, lvl))
+            assert ours <= theirs * 1.03, (lvl, ours, theirs)
+            assert ours < plain
+    # multi-block input: only the first block may reference the dictionary; frames still decode
+    d = corpus.make("text", 300000, 3).tobytes()
+    tdict = ref.train_dict([corpus.make("text", 4000, 50 + i).tobytes() for i in range(200)], 20000)
+    c = emul_util.compress_frame(d, 3, dict=tdict)
+    assert ref.decompress(c, dict=tdict) == d

@@ -19,11 +19,11 @@ def z():
     return zz
 
 
-def _gpu_compress_batch(z, bufs, level, checksum=False, device=True, caps=None):
+def _gpu_compress_batch(z, bufs, level, checksum=False, device=True, caps=None, dict=None):
     import torch
     from tests.gpu_util import to_dev
     L = z._lib.lib()
-    cctx = z.zstd_cctx(level=level, include_checksum=checksum)
+    cctx = z.zstd_cctx(level=level, include_checksum=checksum, dict=dict)
     caps = caps or [L.ZSTD_compressBound(len(b)) for b in bufs]
     if device:
         offs = np.concatenate([[0], np.cumsum([len(b) for b in bufs])]).astype(np.int64)
@@ -126,3 +126,46 @@ def test_compress_split_is_a_standard_multi_frame_stream(z, ref):
     out = C.create_string_buffer(len(d))
     rr = L.ZSTD_decompressDCtx(z.zstd_dctx()._p, out, len(d), blob, len(blob))
     assert rr == len(d) and out.raw == d
+
+
+def test_dictionary_compress(z, ref):
+    """configs[3]: small objects with a trained dictionary (and a raw-content one).  Every GPU frame must decode with the
+    reference's libzstd + the same dictionary, carry the dictionary ID, and the batch must stay within 3% of the size the
+    reference produces with that dictionary at the same level (src/cctx.c:296-312 -> ZSTD_CCtx_loadDictionary)."""
+    from zstdlite_b200 import corpus
+    from tests import emul_util
+    from tests.gpu_util import gpu_decompress_batch
+    samples = corpus.small_objects(3000)
+    trained = ref.train_dict(samples[:1000], 5000)
+    big = ref.train_dict(samples[:1000], 112640)
+    raw = b"".join(samples[:20])
+    work = samples[1000:3000]
+    for dd, name in ((trained, "trained 5000 B"), (big, "trained 112640 B"), (raw, "raw content")):
+        did = z.zstd_dict_id(dd)
+        for lvl in (1, 3):
+            res, outs = _gpu_compress_batch(z, work, lvl, dict=dd)
+            rd = ref.DCtx(dict=dd)
+            for i, (s_, r, c) in enumerate(zip(work, res, outs)):
+                assert not z.is_error(r), z.error_name(r)
+                assert rd.decompress(c, cap=len(s_)) == s_
+                assert z.zstd_info(c)["dict_id"] == did
+                if i < 300:
+                    assert c == emul_util.compress_frame(s_, lvl, dict=dd), "CUDA output differs from the CPU emulation (dictionary mode)"
+            ours = sum(len(c) for c in outs)
+            rc = ref.CCtx(level=lvl, dict=dd)
+            theirs = sum(len(rc.compress(s_)) for s_ in work)
+            nodict = sum(len(ref.compress(s_, lvl)) for s_ in work[:200]) * len(work) / 200
+            print(f"dict {name} level {lvl}: ours {ours} libzstd {theirs} (no dict ~{nodict:.0f})")
+            assert ours <= theirs * 1.03, (name, lvl, ours, theirs)
+            # and our own decoder with the dictionary
+            res2, back = gpu_decompress_batch(outs, [len(s_) for s_ in work], dctx=z.zstd_dctx(dict=dd))
+            assert back == work
+    # larger inputs: only the first block of a frame sees the dictionary; host-pointer one-shot path
+    d = corpus.make("text", 300000, 3).tobytes()
+    tdict = ref.train_dict([corpus.make("text", 4000, 50 + i).tobytes() for i in range(200)], 20000)
+    c = z.zstd_compress(d, level=3, dict=tdict)
+    assert ref.decompress(c, dict=tdict) == d and z.zstd_decompress(c, dict=tdict) == d
+    assert len(c) <= len(z.zstd_compress(d, level=3)) * 1.01          # an unrelated dictionary must not hurt
+    # a frame made with a dictionary does not decode without it
+    with pytest.raises(z.ZstdError):
+        z.zstd_decompress(z.zstd_compress(work[0], dict=trained))

@@ -93,3 +93,16 @@ def mixed_frames(nframes, frame_bytes, mix=(("text", 0.4), ("rdf", 0.4), ("lowen
         fams += [fam] * cnt
         start += cnt
     return out, fams
+
+
+def small_objects(n, seed=4, lo=10, hi=50):
+    """Config-4 style corpus: `n` R-serialized-like records of ~0.2-1 KB -- a named integer vector over a
+    permutation of 50 country names (README.md:283-293) behind a short serialization header."""
+    rng = np.random.default_rng(seed)
+    names = [("country_%02d" % i).encode() for i in range(50)]
+    out = []
+    for _ in range(n):
+        perm = rng.permutation(50)
+        k = int(rng.integers(lo, hi))
+        out.append(b"X\n\x00\x00\x00\x03" + b"".join(names[j] + int(rng.integers(0, 1000)).to_bytes(4, "little") for j in perm[:k]))
+    return out

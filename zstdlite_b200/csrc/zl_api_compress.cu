@@ -6,6 +6,7 @@
 #include <new>
 #include "../../include/zstdlite_gpu.h"
 #include "zl_host.h"
+#include "zl_enc_dict.h"          // host-side dictionary digest (shared with the CPU emulation in tests/emul)
 
 #define ZL_EXPORT extern "C" __attribute__((visibility("default")))
 #define ZL_ALIAS(ret, name, params) extern "C" __attribute__((visibility("default"), alias(#name))) ret zlg_##name params;
@@ -16,6 +17,11 @@ struct ZSTD_CCtx_s {
     int level = 3, nbWorkers = 0, checksumFlag = 0, stableIn = 0, stableOut = 0;
     unsigned long long pledged = ZSTD_CONTENTSIZE_UNKNOWN;
     std::vector<u8> dictRaw;
+    bool dictDirty = false;                // dictRaw changed (or the engine level did): digest again before the next compression
+    int dictLevel = 0;                     // engine level the device tables were built for
+    u32 dictID = 0;
+    size_t dictErr = 0;                    // error found while digesting, reported by the compress calls (as libzstd does)
+    ZlDevBuf dDict, dDictContent, dDictTabS, dDictTabL;
     cudaStream_t stream = nullptr;
     bool ownStream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -50,7 +56,8 @@ ZL_EXPORT size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
 {
     if (!c) return 0;
     ZlDevBuf* bufs[] = {&c->dBlocks, &c->dFrames, &c->dM, &c->dRecs, &c->dLit, &c->dHist, &c->dMetas, &c->dOuts, &c->dPlans, &c->dResults,
-                        &c->dXxh, &c->dXxhPtrs, &c->dXxhSizes, &c->dSrc, &c->dDst, &c->dAux};
+                        &c->dXxh, &c->dXxhPtrs, &c->dXxhSizes, &c->dSrc, &c->dDst, &c->dAux,
+                        &c->dDict, &c->dDictContent, &c->dDictTabS, &c->dDictTabL};
     for (ZlDevBuf* b : bufs) b->release();
     c->hBlocks.release(); c->hFrames.release(); c->hResults.release(); c->hAux.release();
     if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
@@ -63,7 +70,7 @@ ZL_EXPORT size_t ZSTD_CCtx_reset(ZSTD_CCtx* c, ZSTD_ResetDirective r)          /
 {
     if (r == ZSTD_reset_session_only || r == ZSTD_reset_session_and_parameters) c->pledged = ZSTD_CONTENTSIZE_UNKNOWN;
     if (r == ZSTD_reset_parameters || r == ZSTD_reset_session_and_parameters) {
-        c->level = 3; c->nbWorkers = 0; c->checksumFlag = 0; c->stableIn = 0; c->stableOut = 0; c->dictRaw.clear();
+        c->level = 3; c->nbWorkers = 0; c->checksumFlag = 0; c->stableIn = 0; c->stableOut = 0; c->dictRaw.clear(); c->dictDirty = true; c->dictErr = 0;
     }
     return 0;
 }
@@ -94,13 +101,47 @@ ZL_EXPORT size_t ZSTD_CCtx_getParameter(const ZSTD_CCtx* c, ZSTD_cParameter p, i
     }
 }
 ZL_EXPORT size_t ZSTD_CCtx_setPledgedSrcSize(ZSTD_CCtx* c, unsigned long long pledged) { c->pledged = pledged; return 0; }
-// Copies the dictionary (zstd.c:23826).  The compressor does not reference dictionary content yet: frames are written
-// without a dictID and decode with or without the dictionary loaded ("dictionary mode").
+// Copies the dictionary (zstd.c:23826); it is digested lazily by the first compression that uses it, like the reference's
+// ZSTD_initLocalDict (zstd.c:23757), so a corrupted dictionary is reported by the compress call.
 ZL_EXPORT size_t ZSTD_CCtx_loadDictionary(ZSTD_CCtx* c, const void* dict, size_t dictSize)
 {
     c->dictRaw.clear();
     if (dict && dictSize) c->dictRaw.assign((const u8*)dict, (const u8*)dict + dictSize);
+    c->dictDirty = true; c->dictErr = 0;
     return 0;
+}
+
+static size_t zl_cctx_digest_dict(ZSTD_CCtx* c, const ZlEncParams& P)
+{
+    ZlEncDictDev* hd = new (std::nothrow) ZlEncDictDev();
+    if (!hd) return ZL_ERROR(memory_allocation);
+    std::vector<u8> content; std::vector<u32> tabS, tabL;
+    const u32 err = zl_dict_digest_host(c->dictRaw.data(), c->dictRaw.size(), P, hd, content, tabS, tabL);
+    if (err) { delete hd; return (size_t)0 - (size_t)err; }
+    const size_t contentSize = hd->contentSize;
+    bool ok = c->dDictContent.reserve(contentSize + 64) && c->dDictTabS.reserve(tabS.size() * 4) && c->dDictTabL.reserve(tabL.size() * 4) &&
+              c->dDict.reserve(sizeof(ZlEncDictDev));
+    if (ok) {
+        hd->content = c->dDictContent.as<u8>(); hd->tabS = c->dDictTabS.as<u32>(); hd->tabL = P.hlogL ? c->dDictTabL.as<u32>() : nullptr;
+        ok = cudaMemcpy(c->dDictContent.p, content.data(), contentSize + 64, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(c->dDictTabS.p, tabS.data(), tabS.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(c->dDictTabL.p, tabL.data(), tabL.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(c->dDict.p, hd, sizeof(ZlEncDictDev), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    c->dictID = hd->dictID;
+    delete hd;
+    if (!ok) { (void)cudaGetLastError(); return ZL_ERROR(memory_allocation); }
+    return 0;
+}
+// null when no dictionary is loaded; sets c->dictErr on failure
+static const ZlEncDictDev* zl_cctx_dict(ZSTD_CCtx* c, const ZlEncParams& P)
+{
+    if (c->dictRaw.empty()) return nullptr;
+    if (c->dictDirty || c->dictLevel != (int)P.level) {
+        c->dictErr = zl_cctx_digest_dict(c, P);
+        c->dictDirty = false; c->dictLevel = (int)P.level;
+    }
+    return c->dictErr ? nullptr : c->dDict.as<ZlEncDictDev>();
 }
 ZL_EXPORT size_t zl_cctx_set_stream(ZSTD_CCtx* c, void* s)
 {
@@ -137,6 +178,9 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
 {
     cudaStream_t st = c->stream;
     const size_t nf = f1 - f0;
+    const ZlEncParams P = zl_enc_params(zl_engine_level(c->level));
+    const ZlEncDictDev* dict = zl_cctx_dict(c, P);
+    if (c->dictErr && !c->dictRaw.empty()) return c->dictErr;
     size_t nb = 0; u32 maxBlock = 0;
     for (size_t i = f0; i < f1; i++) {
         const size_t s = srcSize[i];
@@ -162,7 +206,7 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
         memset(&f, 0, sizeof(f));
         const size_t s = srcSize[i];
         f.dst = ddst[i]; f.dstCap = dstCap[i]; f.firstBlock = (u32)bi; f.checksumFlag = (u32)c->checksumFlag;
-        f.hdrSize = zl_write_frame_header(f.hdr, s, 0, (u32)c->checksumFlag);
+        f.hdrSize = zl_write_frame_header(f.hdr, s, dict ? c->dictID : 0u, (u32)c->checksumFlag);
         const size_t nblk = s ? (s + ZL_BLOCKSIZE_MAX - 1) / ZL_BLOCKSIZE_MAX : 1;
         f.nblocks = (u32)nblk;
         for (size_t k = 0; k < nblk; k++) {
@@ -191,7 +235,7 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
     }
     ZlEncodeLaunch L;
     L.blocks = c->dBlocks.as<ZlEncBlock>(); L.nblocks = (u32)nb; L.frames = c->dFrames.as<ZlEncFrame>(); L.nframes = (u32)nf;
-    L.params = zl_enc_params(zl_engine_level(c->level));
+    L.params = P; L.dict = dict;
     L.M = c->dM.as<u32>(); L.slotM = slotM; L.recs = c->dRecs.as<u64>(); L.slotRec = slotRec; L.lit = c->dLit.as<u8>(); L.slotLit = slotLit;
     L.hist = c->dHist.as<u32>(); L.metas = c->dMetas.as<ZlEncBlockMeta>(); L.outs = c->dOuts.as<ZlEncBlockOut>(); L.plans = c->dPlans.as<ZlEncBlockPlan>();
     L.streamCapWords = streamCapWords; L.streamWordsPerBlock = streamWordsPerBlock; L.seqCapWords = seqCapWords;

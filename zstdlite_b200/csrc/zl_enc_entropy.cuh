@@ -214,10 +214,35 @@ ZL_HD u32 zl_fse_cost256(i32 n, u32 log)
     return (log << 8) - ((hb << 8) + frac);
 }
 
+// ---- digested dictionary for the compressor (zstd.c:27450 ZSTD_loadCEntropy, 27550 ZSTD_loadZstdDictionary) -----------
+// Built once on the host by ZSTD_CCtx_loadDictionary and kept in device memory.  The first block of every frame may
+// (a) find matches in the dictionary content through the two prebuilt hash tables and (b) reuse the dictionary's
+// entropy tables through the format's "repeat" modes (literals type 3, sequence table mode 3), which is where most of
+// the gain on small inputs comes from.
+struct ZlEncDictDev {
+    const u8* content;       // device pointer, 16-byte aligned, followed by >= 16 zero bytes
+    const u32* tabS;         // short-hash table: position + 1 of the last occurrence (0 = empty), 1 << hlogS entries
+    const u32* tabL;         // long (8-byte) hash table, 1 << hlogL entries (null when the level has no long table)
+    u32 contentSize;
+    u32 hlogS, hlogL;
+    u32 dictID;
+    u32 hasEntropy;
+    u32 rep[3];
+    u32 hufLog;
+    u16 hufCode[256];        // nbBits << 12 | code value, 0 when the dictionary's tree lacks the symbol
+    u8 hufNbBits[256];
+    i16 norm[3][64];         // LL, OF, ML normalized counts
+    u32 log[3], maxSym[3];
+    u16 state[3][512];
+    u32 dNb[3][64];
+    i32 dFS[3][64];
+};
+
 // =================================================================================================== Huffman (literals)
 struct ZlHufCtl {
     u32 nLit, maxSym, nPresent, maxBits;
     u32 mode;            // 0 raw, 1 rle, 2 compressed
+    u32 repeat;          // mode 2 only: 1 = coded with the dictionary's tree, no description (literals type 3)
     u32 nStreams;
     u32 descSize;        // tree description bytes in ZlHufSm.desc
     u32 sBeg[4], sEnd[4];// literal index ranges per stream
@@ -430,26 +455,40 @@ struct ZlEncBlockOut {
 };
 
 // Literals: decide raw / rle / Huffman from the histogram, build the code and the section header (lane 0).
-// `lit` is only needed for the rle byte.  Stream ranges land in ctl.sBeg / sEnd.
-ZL_HD void zl_lit_plan(ZlHufSm& f, ZlEncBlockOut& o, const u8* lit, u32 nLit)
+// `lit` is only needed for the rle byte.  Stream ranges land in ctl.sBeg / sEnd.  `dict` (null unless this is the
+// first block of a frame compressed with an entropy-carrying dictionary) offers its tree as a "repeat" table
+// (zstd.c:20714-20760: HUF_repeat_valid lowers the minimum to 6 literals and, with a 3-byte header, forces one stream).
+ZL_HD void zl_lit_plan(ZlHufSm& f, ZlEncBlockOut& o, const u8* lit, u32 nLit, const ZlEncDictDev* dict)
 {
     ZlHufCtl& c = f.ctl;
-    c.nLit = nLit; c.mode = 0; c.nStreams = 0; c.ovf = 0; c.descSize = 0;
+    c.nLit = nLit; c.mode = 0; c.repeat = 0; c.nStreams = 0; c.ovf = 0; c.descSize = 0;
     o.nLit = nLit; o.nStreams = 0; o.flags = 0;
     for (u32 k = 0; k < 4; k++) { o.sBytes[k] = 0; c.sBytes[k] = 0; }
     u32 maxCount = 0, present = 0;
     for (u32 s = 0; s < 256; s++) { if (f.count[s]) present++; if (f.count[s] > maxCount) maxCount = f.count[s]; }
-    u32 mode = 0;
+    const u32 minGain = (nLit >> 6) + 2;                                                 // zstd.c:19607
+    u32 mode = 0, estBest = 0xFFFFFFFFu;
     if (nLit >= 1 && present == 1 && nLit > 2) mode = 1;                                 // zstd.c:20644 rle literals
-    else if (nLit >= 64 && present >= 2 && maxCount > (nLit >> 7) + 4) {                 // zstd.c:20685, 18043 ("probably not compressible")
-        zl_huf_build(f);
-        if (zl_huf_write_desc(f)) {
-            u64 bits = 0;
-            for (u32 s = 0; s < 256; s++) bits += (u64)f.count[s] * f.nbBits[s];
-            const u32 nStreams = nLit < 256 ? 1u : 4u;                                   // zstd.c:20705
-            const u32 est = (u32)((bits + 7) >> 3) + c.descSize + (nStreams == 4 ? 6u + 4u : 1u);
-            const u32 minGain = (nLit >> 6) + 2;                                         // zstd.c:19607
-            if (est + minGain < nLit) { mode = 2; c.nStreams = nStreams; }
+    else {
+        if (nLit >= 64 && present >= 2 && maxCount > (nLit >> 7) + 4) {                  // zstd.c:20685, 18043 ("probably not compressible")
+            zl_huf_build(f);
+            if (zl_huf_write_desc(f)) {
+                u64 bits = 0;
+                for (u32 s = 0; s < 256; s++) bits += (u64)f.count[s] * f.nbBits[s];
+                const u32 nStreams = nLit < 256 ? 1u : 4u;                               // zstd.c:20705
+                const u32 est = (u32)((bits + 7) >> 3) + c.descSize + (nStreams == 4 ? 6u + 4u : 1u);
+                if (est + minGain < nLit) { mode = 2; c.nStreams = nStreams; estBest = est; }
+            }
+        }
+        if (dict && nLit >= 6) {                                                         // the dictionary's tree, if it covers every literal
+            u64 bits = 0; bool ok = true;
+            for (u32 s = 0; s < 256; s++) if (f.count[s]) { if (!dict->hufNbBits[s]) { ok = false; break; } bits += (u64)f.count[s] * dict->hufNbBits[s]; }
+            const u32 nStreams = nLit < 1024 ? 1u : 4u;
+            const u32 est = (u32)((bits + 7) >> 3) + (nStreams == 4 ? 6u + 4u : 1u);
+            if (ok && est + minGain < nLit && est <= estBest) {
+                mode = 2; c.repeat = 1; c.nStreams = nStreams; c.descSize = 0;
+                for (u32 s = 0; s < 256; s++) { f.code[s] = dict->hufCode[s]; f.nbBits[s] = dict->hufNbBits[s]; }
+            }
         }
     }
     c.mode = mode;
@@ -490,9 +529,10 @@ ZL_HD void zl_lit_finish(ZlHufSm& f, ZlEncBlockOut& o)
         return;
     }
     u8* h = o.litHead;
-    if (lhSize == 3) { const u32 v = 2u | ((c.nStreams == 1 ? 0u : 1u) << 2) | (nLit << 4) | (cSize << 14); h[0] = (u8)v; h[1] = (u8)(v >> 8); h[2] = (u8)(v >> 16); }
-    else if (lhSize == 4) { const u32 v = 2u | (2u << 2) | (nLit << 4) | (cSize << 18); h[0] = (u8)v; h[1] = (u8)(v >> 8); h[2] = (u8)(v >> 16); h[3] = (u8)(v >> 24); }
-    else { const u64 v = 2u | (3u << 2) | ((u64)nLit << 4) | ((u64)cSize << 22); for (u32 i = 0; i < 5; i++) h[i] = (u8)(v >> (8 * i)); }
+    const u32 ty = c.repeat ? 3u : 2u;                 // compressed literals with / without their own tree description
+    if (lhSize == 3) { const u32 v = ty | ((c.nStreams == 1 ? 0u : 1u) << 2) | (nLit << 4) | (cSize << 14); h[0] = (u8)v; h[1] = (u8)(v >> 8); h[2] = (u8)(v >> 16); }
+    else if (lhSize == 4) { const u32 v = ty | (2u << 2) | (nLit << 4) | (cSize << 18); h[0] = (u8)v; h[1] = (u8)(v >> 8); h[2] = (u8)(v >> 16); h[3] = (u8)(v >> 24); }
+    else { const u64 v = ty | (3u << 2) | ((u64)nLit << 4) | ((u64)cSize << 22); for (u32 i = 0; i < 5; i++) h[i] = (u8)(v >> (8 * i)); }
     u32 p = lhSize;
     for (u32 i = 0; i < c.descSize; i++) h[p++] = f.desc[i];
     if (c.nStreams == 4) for (u32 k = 0; k < 3; k++) { h[p++] = (u8)c.sBytes[k]; h[p++] = (u8)(c.sBytes[k] >> 8); }
@@ -503,7 +543,7 @@ ZL_HD void zl_lit_finish(ZlHufSm& f, ZlEncBlockOut& o)
 // =================================================================================================== sequences
 struct ZlSeqEncCtl {
     u32 nbSeq;
-    u32 mode[3];          // 0 predefined, 1 rle, 2 FSE-compressed
+    u32 mode[3];          // 0 predefined, 1 rle, 2 FSE-compressed, 3 repeat (the dictionary's table)
     u32 log[3];
     u32 maxSym[3];
     u32 hdrSize[3];
@@ -528,7 +568,7 @@ ZL_HD u32 zl_seq_code(const ZlEncConst& k, u32 t, u64 rec)
 // the last sequence): pick the table type, build the encoding table and the table description.  The choice compares
 // the exact description cost plus the estimated symbol cost of an FSE-compressed table with the predefined one (the
 // reference uses sequence-count heuristics at these levels, zstd.c:21034-21059).
-ZL_HD void zl_seq_build_from_hist(ZlSeqEncSm& f, u32 t, u32 nbSeq, u32 maxSym, u32 lastCode, const ZlEncConst& k)
+ZL_HD void zl_seq_build_from_hist(ZlSeqEncSm& f, u32 t, u32 nbSeq, u32 maxSym, u32 lastCode, const ZlEncConst& k, const ZlEncDictDev* dict)
 {
     const u32 maxLogT = t == 1 ? 8u : 9u, defLog = t == 1 ? 5u : 6u;
     const i16* def = t == 0 ? k.llDef : (t == 1 ? k.ofDef : k.mlDef);
@@ -559,6 +599,18 @@ ZL_HD void zl_seq_build_from_hist(ZlSeqEncSm& f, u32 t, u32 nbSeq, u32 maxSym, u
             if (nc) { u64 cst = 0; for (u32 s = 0; s <= maxSym; s++) cst += (u64)cnt[s] * zl_fse_cost256(f.norm[t][s], log); costFse = (u32)(cst >> 8) + 8 * nc; }
         }
     }
+    if (dict && maxSym <= dict->maxSym[t]) {                                  // the dictionary's table as a "repeat" table (zstd.c:21034-21076)
+        u64 cst = 0; bool ok = true;
+        for (u32 s = 0; s <= maxSym; s++) if (cnt[s]) { if (!dict->norm[t][s]) { ok = false; break; } cst += (u64)cnt[s] * zl_fse_cost256(dict->norm[t][s], dict->log[t]); }
+        const u32 costRep = ok ? (u32)(cst >> 8) : 0xFFFFFFFFu;
+        if (costRep <= costDef && costRep <= costFse) {
+            const u32 dl = dict->log[t];
+            c.mode[t] = 3; c.log[t] = dl; c.maxSym[t] = dict->maxSym[t]; c.hdrSize[t] = 0;
+            for (u32 i = 0; i < (1u << dl); i++) f.state[t][i] = dict->state[t][i];
+            for (u32 s = 0; s < 64; s++) { f.dNb[t][s] = dict->dNb[t][s]; f.dFS[t][s] = dict->dFS[t][s]; }
+            return;
+        }
+    }
     if (costFse < costDef) {
         c.mode[t] = 2; c.log[t] = log; c.maxSym[t] = maxSym; c.hdrSize[t] = nc;
         zl_fse_build_ctable(f.state[t], f.dNb[t], f.dFS[t], f.norm[t], maxSym, log, f.symOf[t], f.cumul[t]);
@@ -571,13 +623,13 @@ ZL_HD void zl_seq_build_from_hist(ZlSeqEncSm& f, u32 t, u32 nbSeq, u32 maxSym, u
     zl_fse_build_ctable(f.state[t], f.dNb[t], f.dFS[t], f.norm[t], defSyms - 1, defLog, f.symOf[t], f.cumul[t]);
 }
 // serial form (CPU emulation): histogram, then the above
-ZL_HD void zl_seq_build_table(ZlSeqEncSm& f, u32 t, const u64* recs, u32 nbSeq, const ZlEncConst& k)
+ZL_HD void zl_seq_build_table(ZlSeqEncSm& f, u32 t, const u64* recs, u32 nbSeq, const ZlEncConst& k, const ZlEncDictDev* dict)
 {
     u32* cnt = f.count[t];
     for (u32 s = 0; s < 64; s++) cnt[s] = 0;
     u32 maxSym = 0, lastCode = 0;
     for (u32 i = 0; i < nbSeq; i++) { const u32 c = zl_seq_code(k, t, recs[i]); cnt[c]++; if (c > maxSym) maxSym = c; lastCode = c; }
-    zl_seq_build_from_hist(f, t, nbSeq, maxSym, lastCode, k);
+    zl_seq_build_from_hist(f, t, nbSeq, maxSym, lastCode, k, dict);
 }
 // sequences section header (lane 0): nbSeq, modes byte, table descriptions in LL, OF, ML order (zstd.c:25446-25490)
 ZL_HD void zl_seq_write_head(const ZlSeqEncSm& f, ZlEncBlockOut& o)

@@ -55,9 +55,40 @@ __device__ __forceinline__ u32 zl_match_len(const u32* __restrict__ wbase, u32 b
 }
 
 // ---------------------------------------------------------------------------------------------- E1: match candidates
-template <bool kLong>
+// dictionary candidate for position p (first block of a frame): last occurrence of the hash in the prebuilt table,
+// verified against the dictionary content; the match may not run past the end of the content.  Returns the length
+// (0 = none) and the offset (p + distance to the end of the dictionary).
+__device__ __forceinline__ u32 zl_dict_match(const ZlEncDictDev& D, const u32* __restrict__ tab, u32 h, const u32* __restrict__ wbase, u32 bias,
+                                             u32 lastWord, u32 p, u32 lo, u32 hi, u32 lim, u32 mls, u32& offOut)
+{
+    const u32 e = __ldg(tab + h);
+    if (!e) return 0;
+    const u32 q = e - 1, room = D.contentSize - q;
+    const u32* __restrict__ dw = reinterpret_cast<const u32*>(D.content);
+    const u32 dLast = (D.contentSize + 15) >> 2;                     // the content is followed by >= 16 zero bytes
+    if (lim > room) lim = room;
+    u32 blo, bhi;
+    zl_ld8(dw, q, dLast, blo, bhi);
+    u32 len = zl_common8(lo, hi, blo, bhi);
+    if (len == 8) {
+        for (u32 k = 8; k < lim; k += 8) {
+            u32 alo, ahi;
+            zl_ld8(wbase, bias + p + k, lastWord, alo, ahi);
+            zl_ld8(dw, q + k, dLast, blo, bhi);
+            const u32 c = zl_common8(alo, ahi, blo, bhi);
+            len += c;
+            if (c < 8) break;
+        }
+    }
+    if (len > lim) len = lim;
+    if (len < mls) return 0;
+    offOut = p + room;
+    return len;
+}
+
+template <bool kLong, bool kDict>
 __global__ void __launch_bounds__(ZL_MATCH_WARPS * 32)
-zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 slotM, ZlEncParams P)
+zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 slotM, ZlEncParams P, const ZlEncDictDev* __restrict__ dict)
 {
     extern __shared__ __align__(16) u8 smraw[];
     u16* tabS = reinterpret_cast<u16*>(smraw);
@@ -140,6 +171,17 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
                     const u32 l = zl_match_len(wbase, bias, lastWord, p, (u32)qS, lo[h], hi[h], lim);
                     if (l >= P.mls && l > bestLen) { bestLen = l; bestOff = p - (u32)qS; }
                 }
+                if (kDict && (b.flags & ZL_BLK_FIRST) && bestLen < lim) {      // dictionary content precedes the first block
+                    u32 dOff = 0;
+                    if (kLong) {
+                        const u32 l = zl_dict_match(*dict, dict->tabL, zl_hash_long(lo[h], hi[h], dict->hlogL), wbase, bias, lastWord, p, lo[h], hi[h], lim, P.mls, dOff);
+                        if (l > bestLen) { bestLen = l; bestOff = dOff; }
+                    }
+                    if (bestLen < lim) {
+                        const u32 l = zl_dict_match(*dict, dict->tabS, zl_hash_short(lo[h], hi[h], P.mls, dict->hlogS), wbase, bias, lastWord, p, lo[h], hi[h], lim, P.mls, dOff);
+                        if (l > bestLen) { bestLen = l; bestOff = dOff; }
+                    }
+                }
                 if (bestLen) m = (bestOff << 8) | bestLen;
             }
             if (p < n) M[p] = m;
@@ -172,7 +214,8 @@ __device__ __forceinline__ u32 zl_extend_match(const u32* __restrict__ wbase, u3
 
 __global__ void __launch_bounds__(ZL_PARSE_WARPS * 32)
 zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __restrict__ Marena, u32 slotM, u64* __restrict__ recArena,
-           u32 slotRec, u8* __restrict__ litArena, u32 slotLit, u32* __restrict__ histArena, ZlEncBlockMeta* __restrict__ metas)
+           u32 slotRec, u8* __restrict__ litArena, u32 slotLit, u32* __restrict__ histArena, ZlEncBlockMeta* __restrict__ metas,
+           const ZlEncDictDev* __restrict__ dict)
 {
     __shared__ u32 hist[ZL_PARSE_WARPS][256];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -192,6 +235,8 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
     const bool first = (b.flags & ZL_BLK_FIRST) != 0;
     ZlReps reps;                                             // zl_enc_match.cuh: unknown history (0) for non-first blocks
     reps.r0 = first ? 1u : 0u; reps.r1 = first ? 4u : 0u; reps.r2 = first ? 8u : 0u;
+    if (first && dict && dict->hasEntropy) { reps.r0 = dict->rep[0]; reps.r1 = dict->rep[1]; reps.r2 = dict->rep[2]; }    // zstd.c:27450 (dictionary repcodes)
+    const bool repPref = first && dict != nullptr;
     u32 p = 0, anchor = 0, nseq = 0, nlit = 0;
     // M and the source bytes are fetched one 128-position super-window ahead (the walk itself never waits on memory)
     u32 mq[4], bq[4];
@@ -220,15 +265,34 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
                 if (!mm) break;
                 const u32 c1 = (u32)__ffs((int)mm) - 1;
                 u32 l = __shfl_sync(ZL_FULL, len, c1);
-                const u32 o = __shfl_sync(ZL_FULL, off, c1);
-                const u32 pos1 = w0 + c1;
-                if (l == ZL_M_CAP) l = zl_extend_match(wbase, bias, lastWord, n, pos1, o, lane);
+                u32 o = __shfl_sync(ZL_FULL, off, c1);
+                u32 pos1 = w0 + c1, c2 = c1;
+                if (l == ZL_M_CAP && o <= pos1) l = zl_extend_match(wbase, bias, lastWord, n, pos1, o, lane);   // (matches into the dictionary stay capped)
+                if (repPref && reps.r0 && o != reps.r0) {
+                    // Dictionary mode only: lanes 0..2 probe the most recent offset at pos1, pos1+1, pos1+2 (same window).  Such a
+                    // match costs no offset bits; it is taken when it is at most 4 bytes shorter (cf. the repcode checks at
+                    // ip+1 / ip+2 of zstd.c:29989, 30801).  Small dictionary-compressed inputs are dominated by offset cost.
+                    const u32 q = pos1 + lane;
+                    u32 rl = 0;
+                    if (lane < 3 && c1 + lane < 32 && reps.r0 <= q && q + 4 <= n) {
+                        u32 qlo, qhi;
+                        zl_ld8(wbase, bias + q, lastWord, qlo, qhi);
+                        rl = zl_match_len(wbase, bias, lastWord, q, q - reps.r0, qlo, qhi, min(n - q, ZL_M_CAP));
+                    }
+                    const u32 hit = __ballot_sync(ZL_FULL, rl >= 4 && rl + 4 >= l) & 7u;
+                    if (hit) {
+                        const u32 k = (u32)__ffs((int)hit) - 1;
+                        c2 = c1 + k; pos1 += k; o = reps.r0;
+                        l = __shfl_sync(ZL_FULL, rl, k);
+                        if (l == ZL_M_CAP) l = zl_extend_match(wbase, bias, lastWord, n, pos1, o, lane);
+                    }
+                }
                 const u32 ll = pos1 - anchor;
                 const u32 ob = zl_rep_encode(reps, o, ll);
-                if (lane == c1) { len = l; myLL = ll; myOB = ob; }
-                takenMask |= 1u << c1;
+                if (lane == c2) { len = l; myLL = ll; myOB = ob; }
+                takenMask |= 1u << c2;
                 anchor = pos1 + l;
-                c = c1 + l;
+                c = c2 + l;
             }
             p = w0 + (c < 32 ? 32 : c);
             // literals of this window: positions from cstart on that no taken match covers
@@ -256,7 +320,7 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
 __global__ void __launch_bounds__(ZL_ENT_WARPS * 32)
 zl_k_enc_literals(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u8* __restrict__ litArena, u32 slotLit,
                   const u32* __restrict__ histArena, const ZlEncBlockMeta* __restrict__ metas, u32* __restrict__ streamArena,
-                  u32 slotStreamWords, u32 streamCapWords, ZlEncBlockOut* __restrict__ outs)
+                  u32 slotStreamWords, u32 streamCapWords, ZlEncBlockOut* __restrict__ outs, const ZlEncDictDev* __restrict__ dict)
 {
     extern __shared__ __align__(16) u8 smraw[];
     ZlHufSm* fs = reinterpret_cast<ZlHufSm*>(smraw);
@@ -269,7 +333,7 @@ zl_k_enc_literals(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u8* 
     const u32 nLit = metas[blk].nlit;
     for (u32 i = lane; i < 256; i += 32) f.count[i] = histArena[(size_t)blk * 256 + i];
     __syncwarp();
-    if (lane == 0) zl_lit_plan(f, o, lit, nLit);
+    if (lane == 0) zl_lit_plan(f, o, lit, nLit, (dict && dict->hasEntropy && (blocks[blk].flags & ZL_BLK_FIRST)) ? dict : nullptr);
     __syncwarp();
     if (f.ctl.mode != 2) return;
     const u32 ns = f.ctl.nStreams, per = 32 / ns, sIdx = lane / per, k = lane % per;
@@ -320,7 +384,7 @@ __device__ __forceinline__ void zl_stage_put(u32* stage, u32 pos, u64 v, u32 nb)
 __global__ void __launch_bounds__(ZL_ENT_WARPS * 32)
 zl_k_enc_sequences(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u64* __restrict__ recArena, u32 slotRec,
                    const ZlEncBlockMeta* __restrict__ metas, u32* __restrict__ seqBitsArena, u32 slotSeqWords, u32 seqCapWords,
-                   u32 sbitsWordOff, ZlEncBlockOut* __restrict__ outs)
+                   u32 sbitsWordOff, ZlEncBlockOut* __restrict__ outs, const ZlEncDictDev* __restrict__ dict)
 {
     extern __shared__ __align__(16) u8 smraw[];
     ZlEncConst& K = *reinterpret_cast<ZlEncConst*>(smraw);
@@ -361,7 +425,8 @@ zl_k_enc_sequences(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u64
     if (lane < 3) {
         const u32 t = lane;
         const u32 ms = t == 0 ? maxSym[0] : (t == 1 ? maxSym[1] : maxSym[2]);
-        zl_seq_build_from_hist(f, t, nbSeq, ms, zl_seq_code(K, t, recs[nbSeq - 1]), K);
+        zl_seq_build_from_hist(f, t, nbSeq, ms, zl_seq_code(K, t, recs[nbSeq - 1]), K,
+                               (dict && dict->hasEntropy && (blocks[blk].flags & ZL_BLK_FIRST)) ? dict : nullptr);
     }
     __syncwarp();
     if (lane == 0) zl_seq_write_head(f, o);
@@ -531,8 +596,11 @@ cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st)
     const size_t smL = ZL_ENT_WARPS * sizeof(ZlHufSm);
     const size_t smS = ZL_ENC_CT_BYTES + ZL_ENT_WARPS * sizeof(ZlSeqWarpSm);
     cudaError_t e;
-    if (L.params.hlogL) e = cudaFuncSetAttribute(zl_k_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smM);
-    else e = cudaFuncSetAttribute(zl_k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smM);
+    const bool useDict = L.dict != nullptr;
+    if (L.params.hlogL) e = useDict ? cudaFuncSetAttribute(zl_k_match<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smM)
+                                    : cudaFuncSetAttribute(zl_k_match<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smM);
+    else e = useDict ? cudaFuncSetAttribute(zl_k_match<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smM)
+                     : cudaFuncSetAttribute(zl_k_match<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(zl_k_enc_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smL);
     if (e != cudaSuccess) return e;
@@ -541,19 +609,24 @@ cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st)
     const u32 nb = L.nblocks;
     if (ev) cudaEventRecord(ev[0], st);
     if (nb) {
-        if (L.params.hlogL) zl_k_match<true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params);
-        else zl_k_match<false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params);
+        if (L.params.hlogL) {
+            if (useDict) zl_k_match<true, true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, L.dict);
+            else zl_k_match<true, false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, nullptr);
+        } else {
+            if (useDict) zl_k_match<false, true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, L.dict);
+            else zl_k_match<false, false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, nullptr);
+        }
     }
     if (ev) cudaEventRecord(ev[1], st);
-    if (nb) zl_k_parse<<<(nb + ZL_PARSE_WARPS - 1) / ZL_PARSE_WARPS, ZL_PARSE_WARPS * 32, 0, st>>>(L.blocks, nb, L.M, L.slotM, L.recs, L.slotRec, L.lit, L.slotLit, L.hist, L.metas);
+    if (nb) zl_k_parse<<<(nb + ZL_PARSE_WARPS - 1) / ZL_PARSE_WARPS, ZL_PARSE_WARPS * 32, 0, st>>>(L.blocks, nb, L.M, L.slotM, L.recs, L.slotRec, L.lit, L.slotLit, L.hist, L.metas, L.dict);
     if (ev) cudaEventRecord(ev[2], st);
     const u32 gq = (nb + ZL_ENT_WARPS - 1) / ZL_ENT_WARPS;
     // the stream / bitstream buffers reuse the M arena (dead after the parse): [streams | sequence bits] per block slot
     u32* streamArena = L.M;
     u32* seqArena = L.M + L.streamWordsPerBlock;
-    if (nb) zl_k_enc_literals<<<gq, ZL_ENT_WARPS * 32, smL, st>>>(L.blocks, nb, L.lit, L.slotLit, L.hist, L.metas, streamArena, L.slotM, L.streamCapWords, L.outs);
+    if (nb) zl_k_enc_literals<<<gq, ZL_ENT_WARPS * 32, smL, st>>>(L.blocks, nb, L.lit, L.slotLit, L.hist, L.metas, streamArena, L.slotM, L.streamCapWords, L.outs, L.dict);
     if (ev) cudaEventRecord(ev[3], st);
-    if (nb) zl_k_enc_sequences<<<gq, ZL_ENT_WARPS * 32, smS, st>>>(L.blocks, nb, L.recs, L.slotRec, L.metas, seqArena, L.slotM, L.seqCapWords, L.seqCapWords, L.outs);
+    if (nb) zl_k_enc_sequences<<<gq, ZL_ENT_WARPS * 32, smS, st>>>(L.blocks, nb, L.recs, L.slotRec, L.metas, seqArena, L.slotM, L.seqCapWords, L.seqCapWords, L.outs, L.dict);
     if (ev) cudaEventRecord(ev[4], st);
     zl_k_enc_plan<<<(L.nframes + 127) / 128, 128, 0, st>>>(L.frames, L.nframes, L.blocks, L.metas, L.outs, L.plans, L.results);
     if (nb) zl_k_enc_assemble<<<(nb + ZL_ASM_WARPS - 1) / ZL_ASM_WARPS, ZL_ASM_WARPS * 32, 0, st>>>(L.frames, L.blocks, nb, L.plans, L.outs, L.lit, L.slotLit, streamArena, L.slotM,

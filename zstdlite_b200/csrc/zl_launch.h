@@ -91,6 +91,7 @@ struct ZlEncodeLaunch {
     u32 streamCapWords, streamWordsPerBlock, seqCapWords;
     u64* results;
     const u64* xxh;                    // per-frame XXH64 of the content (only read when the frame carries a checksum)
+    const ZlEncDictDev* dict;          // device pointer to the digested dictionary, or null
     cudaEvent_t* stageEv;              // null or ZL_ENC_STAGES + 1 events
 };
 cudaError_t zl_enc_upload_const();
