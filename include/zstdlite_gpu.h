@@ -78,6 +78,17 @@ size_t             ZSTD_findFrameCompressedSize(const void* src, size_t srcSize)
 unsigned long long ZSTD_getFrameContentSize(const void* src, size_t srcSize);       /* zstd.c:41170 */
 size_t ZSTD_decompressDCtx(ZSTD_DCtx* dctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize); /* zstd.c:41798 */
 
+/* ---- streaming entry points: src/raw-file-out.c:95,113; src/raw-file-in.c:102; src/serialize-*-out.c,
+ *      src/serialize-*-in.c; src/zstdfile.c:238,362,475,511.  Implemented over the same GPU engine by buffering whole frames on
+ *      the host: input is accumulated until ZSTD_e_end (compress) / until a complete frame has arrived (decompress), then the
+ *      one-shot kernels run and the result is handed out in the caller's chunk sizes.  Output is one standard frame whose
+ *      header records the content size, interchangeable with the one-shot path (tests/testthat/test-compress-raw.R:61-89). ---- */
+typedef struct { const void* src; size_t size; size_t pos; } ZSTD_inBuffer;        /* src/zstd/zstd.h:705-709 */
+typedef struct { void* dst; size_t size; size_t pos; } ZSTD_outBuffer;             /* src/zstd/zstd.h:711-715 */
+typedef enum { ZSTD_e_continue = 0, ZSTD_e_flush = 1, ZSTD_e_end = 2 } ZSTD_EndDirective;   /* src/zstd/zstd.h:775-790 */
+size_t ZSTD_compressStream2(ZSTD_CCtx* cctx, ZSTD_outBuffer* output, ZSTD_inBuffer* input, ZSTD_EndDirective endOp); /* zstd.c:28828 */
+size_t ZSTD_decompressStream(ZSTD_DCtx* dctx, ZSTD_outBuffer* output, ZSTD_inBuffer* input);                          /* zstd.c:42687 */
+
 /* ---- introspection: src/zstd-info.c:61; src/dictionaries.c:52,54 ---- */
 size_t   ZSTD_getFrameHeader(ZSTD_frameHeader* zfhPtr, const void* src, size_t srcSize); /* zstd.c:41160 */
 unsigned ZSTD_getDictID_fromFrame(const void* src, size_t srcSize);                 /* zstd.c:42245 */

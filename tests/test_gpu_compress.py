@@ -169,3 +169,35 @@ def test_dictionary_compress(z, ref):
     # a frame made with a dictionary does not decode without it
     with pytest.raises(z.ZstdError):
         z.zstd_decompress(z.zstd_compress(work[0], dict=trained))
+
+
+def test_streaming_entry_points_interoperate_with_one_shot(z, ref):
+    """tests/testthat/test-compress-raw.R:61-89: all four combinations of streaming / one-shot writer x reader must agree,
+    and the reference's libzstd (one-shot and streaming) must read what the streaming writer produced."""
+    import io
+    from zstdlite_b200 import corpus
+    for d in (b"", b"tiny", corpus.make("text", 131072, 9).tobytes(), corpus.make("rdf", 700001, 9).tobytes()):
+        sink = io.BytesIO()
+        z.zstd_compress_stream(d, sink.write, level=3, include_checksum=True)
+        streamed = sink.getvalue()
+        one = z.zstd_compress(d, level=3, include_checksum=True)
+        assert streamed == one                                           # same engine, same frame
+        assert z.zstd_info(streamed)["uncompressed_size"] == len(d)
+        assert ref.decompress(streamed) == d
+        for blob in (streamed, ref.compress(d, 3, True), ref.compress(d, 19)):
+            assert z.zstd_decompress_stream(io.BytesIO(blob).read) == d
+            assert z.zstd_decompress_stream(io.BytesIO(blob).read, out_chunk=1000) == d      # small output chunks
+    # two frames + a skippable frame in one stream; truncated input is an error
+    a, b = corpus.make("text", 50000, 1).tobytes(), corpus.make("lowent", 200000, 2).tobytes()
+    skip = (0x184D2A53).to_bytes(4, "little") + (5).to_bytes(4, "little") + b"hello"
+    blob = ref.compress(a, 3, True) + skip + ref.compress(b, 1)
+    assert z.zstd_decompress_stream(io.BytesIO(blob).read) == a + b
+    with pytest.raises(z.ZstdError):
+        z.zstd_decompress_stream(io.BytesIO(blob[:-7]).read)
+    # pledged size mismatch is reported like libzstd does (zstd.c:27190)
+    L = z._lib.lib()
+    c = z.zstd_cctx()
+    L.ZSTD_CCtx_setPledgedSrcSize(c._p, 10)
+    ib = C.create_string_buffer(b"abc", 3); ob = C.create_string_buffer(100)
+    r = L.ZSTD_compressStream2(c._p, C.byref(z._lib.OutBuffer(C.cast(ob, C.c_void_p), 100, 0)), C.byref(z._lib.InBuffer(C.cast(ib, C.c_void_p), 3, 0)), 2)
+    assert z.is_error(r) and z.error_name(r) == "Src size is incorrect"

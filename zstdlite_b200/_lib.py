@@ -15,6 +15,17 @@ ZSTD_c_stableInBuffer, ZSTD_c_stableOutBuffer = 1006, 1007
 ZSTD_d_stableOutBuffer, ZSTD_d_forceIgnoreChecksum = 1001, 1002
 
 
+class InBuffer(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("size", C.c_size_t), ("pos", C.c_size_t)]
+
+
+class OutBuffer(C.Structure):
+    _fields_ = [("dst", C.c_void_p), ("size", C.c_size_t), ("pos", C.c_size_t)]
+
+
+ZSTD_e_continue, ZSTD_e_flush, ZSTD_e_end = 0, 1, 2
+
+
 class FrameHeader(C.Structure):
     _fields_ = [("frameContentSize", C.c_ulonglong), ("windowSize", C.c_ulonglong), ("blockSizeMax", C.c_uint),
                 ("frameType", C.c_int), ("headerSize", C.c_uint), ("dictID", C.c_uint), ("checksumFlag", C.c_uint),
@@ -56,6 +67,9 @@ def lib():
         "zl_compress_split": (sz, [vp, vp, sz, vp, sz, sz, psz, C.c_int]),
         "zl_cctx_set_stream": (sz, [vp, vp]), "zl_cctx_launch_count": (C.c_ulonglong, [vp]), "zl_cctx_last_kernel_ms": (C.c_double, [vp]),
         "zl_cctx_last_stage_ms": (C.c_double, [vp, C.c_int]),
+        # streaming entry points (whole-frame buffering over the same engine)
+        "ZSTD_compressStream2": (sz, [vp, C.POINTER(OutBuffer), C.POINTER(InBuffer), C.c_int]),
+        "ZSTD_decompressStream": (sz, [vp, C.POINTER(OutBuffer), C.POINTER(InBuffer)]),
     }
     missing = []
     for name, (res, args) in sig.items():
@@ -76,7 +90,7 @@ EXPORTED_SYMBOLS = [
     "ZSTD_CCtx_setParameter", "ZSTD_CCtx_getParameter", "ZSTD_CCtx_loadDictionary", "ZSTD_CCtx_setPledgedSrcSize",
     "ZSTD_compressBound", "ZSTD_compress2", "ZSTD_createDCtx", "ZSTD_freeDCtx", "ZSTD_DCtx_reset", "ZSTD_DCtx_setParameter",
     "ZSTD_DCtx_getParameter", "ZSTD_DCtx_loadDictionary", "ZSTD_findFrameCompressedSize", "ZSTD_getFrameContentSize",
-    "ZSTD_decompressDCtx", "ZSTD_getFrameHeader", "ZSTD_getDictID_fromFrame", "ZSTD_getDictID_fromDict", "ZDICT_getDictID",
+    "ZSTD_decompressDCtx", "ZSTD_compressStream2", "ZSTD_decompressStream", "ZSTD_getFrameHeader", "ZSTD_getDictID_fromFrame", "ZSTD_getDictID_fromDict", "ZDICT_getDictID",
     "zl_decompress_batch", "zl_compress_batch", "zl_compress_split", "zl_dctx_set_stream", "zl_dctx_set_profile", "zl_cctx_set_stream",
     "zl_dctx_launch_count", "zl_cctx_launch_count", "zl_dctx_last_kernel_ms", "zl_cctx_last_kernel_ms", "zl_dctx_last_stage_ms", "zl_cctx_last_stage_ms", "zl_backend_string",
 ]

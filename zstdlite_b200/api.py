@@ -180,6 +180,67 @@ def zstd_decompress(src, type="raw", dctx=None, **opts):
     return out.decode("utf-8") if type == "string" else out
 
 
+_OUTSIZE, _INSIZE = 131591, 131072          # static buffer sizes of the reference's streaming writers (src/raw-file-out.c:23-24)
+
+
+def zstd_compress_stream(src, write, cctx=None, **opts):
+    """The reference's streaming writer loop (src/raw-file-out.c:74-118, use_file_streaming=TRUE): pledge the size, feed
+    ZSTD_compressStream2 in 128 KiB chunks with ZSTD_e_continue, finish with ZSTD_e_end; `write(bytes)` receives the output."""
+    L = _lib.lib()
+    if cctx is None:
+        cctx = zstd_cctx(**opts)
+    if isinstance(src, str):
+        src = src.encode("utf-8")
+    data = bytes(memoryview(src).cast("B"))
+    n = len(data)
+    _check(L.ZSTD_CCtx_setPledgedSrcSize(cctx._p, n), "zstd_compress_stream(): pledged size")
+    obuf = C.create_string_buffer(_OUTSIZE)
+    pos = 0
+    while True:
+        chunk = data[pos:pos + _INSIZE]
+        pos += len(chunk)
+        last = pos >= n
+        ib = C.create_string_buffer(chunk, max(1, len(chunk)))
+        inb = _lib.InBuffer(C.cast(ib, C.c_void_p), len(chunk), 0)
+        while True:
+            outb = _lib.OutBuffer(C.cast(obuf, C.c_void_p), _OUTSIZE, 0)
+            rem = L.ZSTD_compressStream2(cctx._p, C.byref(outb), C.byref(inb), _lib.ZSTD_e_end if last else _lib.ZSTD_e_continue)
+            _check(rem, "zstd_compress_stream(): Compression error")
+            if outb.pos:
+                write(obuf.raw[:outb.pos])
+            if (rem == 0) if last else (inb.pos == inb.size):
+                break
+        if last:
+            return
+
+
+def zstd_decompress_stream(read, dctx=None, out_chunk=131702, **opts):
+    """The reference's streaming reader loop (src/raw-file-in.c:94-104): `read(n)` supplies compressed bytes (b"" at the end);
+    ZSTD_decompressStream is called until the input is consumed and the decoder holds no more output."""
+    L = _lib.lib()
+    if dctx is None:
+        dctx = zstd_dctx(**opts)
+    out = bytearray()
+    obuf = C.create_string_buffer(out_chunk)
+    status = 0
+    while True:
+        chunk = read(_INSIZE)
+        if not chunk:
+            break
+        ib = C.create_string_buffer(chunk, len(chunk))
+        inb = _lib.InBuffer(C.cast(ib, C.c_void_p), len(chunk), 0)
+        while True:
+            outb = _lib.OutBuffer(C.cast(obuf, C.c_void_p), out_chunk, 0)
+            status = L.ZSTD_decompressStream(dctx._p, C.byref(outb), C.byref(inb))
+            _check(status, "zstd_decompress_stream(): De-compression error")
+            out += obuf.raw[:outb.pos]
+            if inb.pos == inb.size and outb.pos < out_chunk:
+                break
+    if status != 0:
+        raise ZstdError("zstd_decompress_stream(): input ends inside a frame")
+    return bytes(out)
+
+
 def zstd_info(src):
     """zstd_info(src)  (src/zstd-info.c:60-87)."""
     L = _lib.lib()

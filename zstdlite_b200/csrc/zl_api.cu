@@ -182,6 +182,9 @@ struct ZSTD_DCtx_s {
     cudaStream_t lane[ZL_DEC_LANES] = {};
     cudaEvent_t laneDone[ZL_DEC_LANES] = {}, forkEv = nullptr;
     int profileStages = 0;                 // 1: one slice, one stream, per-kernel events (zl_dctx_last_stage_ms)
+    // streaming session (ZSTD_decompressStream): input accumulated on the host until a whole frame is present
+    std::vector<u8> sIn, sOut;
+    size_t sOutPos = 0;
     ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dNorm, dSrc, dDst;
     ZlPinBuf hDescs, hResults;
 };
@@ -214,6 +217,7 @@ ZL_EXPORT size_t ZSTD_freeDCtx(ZSTD_DCtx* c)
 }
 ZL_EXPORT size_t ZSTD_DCtx_reset(ZSTD_DCtx* c, ZSTD_ResetDirective r)
 {
+    if (r == ZSTD_reset_session_only || r == ZSTD_reset_session_and_parameters) { c->sIn.clear(); c->sOut.clear(); c->sOutPos = 0; }
     if (r == ZSTD_reset_parameters || r == ZSTD_reset_session_and_parameters) {       // zstd.c:42548-42565
         c->forceIgnoreChecksum = 0; c->stableOut = 0; c->windowLogMax = 27;
         c->hasDict = false; c->dictRaw.clear();
@@ -494,3 +498,49 @@ ZL_EXPORT size_t ZSTD_decompressDCtx(ZSTD_DCtx* c, void* dst, size_t dstCap, con
     return op;
 }
 ZL_ALIAS(size_t, ZSTD_decompressDCtx, (ZSTD_DCtx*, void*, size_t, const void*, size_t))
+
+// zstd.c:42687 ZSTD_decompressStream over the one-shot engine: all offered input is taken and kept until a complete frame
+// is present (its end is found by walking the block headers, zstd.c:41335), the frame is decoded by the kernels into a
+// host buffer and handed out in the caller's chunk sizes.  Returns 0 when a frame has been completely decoded and
+// delivered, an error code, or a positive hint (bytes of output still held, or 1 when more input is needed).
+ZL_EXPORT size_t ZSTD_decompressStream(ZSTD_DCtx* c, ZSTD_outBuffer* out, ZSTD_inBuffer* in)
+{
+    if (!c || !out || !in) return ZL_ERROR(GENERIC);
+    if (out->pos > out->size) return ZL_ERROR(dstSize_tooSmall);
+    if (in->pos > in->size) return ZL_ERROR(srcSize_wrong);
+    if (in->size > in->pos) c->sIn.insert(c->sIn.end(), (const u8*)in->src + in->pos, (const u8*)in->src + in->size);
+    in->pos = in->size;
+    for (;;) {
+        if (c->sOutPos < c->sOut.size()) {                        // deliver what is decoded
+            const size_t room = out->size - out->pos, left = c->sOut.size() - c->sOutPos, k = room < left ? room : left;
+            if (k) memcpy((u8*)out->dst + out->pos, c->sOut.data() + c->sOutPos, k);
+            out->pos += k; c->sOutPos += k;
+            if (c->sOutPos < c->sOut.size()) return c->sOut.size() - c->sOutPos;
+            std::vector<u8>().swap(c->sOut); c->sOutPos = 0;
+            if (c->sIn.empty()) return 0;
+        }
+        if (c->sIn.empty()) return 0;
+        if (c->sIn.size() < 5) return 1;                          // not even a magic number + descriptor yet
+        const u8* p = c->sIn.data();
+        ZlHostFrameHeader h;
+        const size_t hr = zl_host_frame_header(&h, p, c->sIn.size());
+        if (zl_is_error(hr)) { c->sIn.clear(); return hr; }
+        if (hr > 0) return 1;                                     // header incomplete
+        unsigned nblocks = 0;
+        const size_t fs = zl_host_find_frame_size(p, c->sIn.size(), &nblocks);
+        if (fs == ZL_ERROR(srcSize_wrong)) return 1;              // frame incomplete: wait for more input
+        if (zl_is_error(fs)) { c->sIn.clear(); return fs; }
+        if (h.skippable) { c->sIn.erase(c->sIn.begin(), c->sIn.begin() + (ptrdiff_t)fs); if (c->sIn.empty()) return 0; continue; }
+        const size_t cap = h.contentSize != ZSTD_CONTENTSIZE_UNKNOWN ? (size_t)h.contentSize : (size_t)nblocks * h.blockSizeMax;
+        if (cap > 0x7FFFFFF0ull) { c->sIn.clear(); return ZL_ERROR(memory_allocation); }
+        c->sOut.resize(cap ? cap : 1);
+        const void* fsrc = p; void* fdst = c->sOut.data(); size_t fsz = fs, fcap = cap, fres = 0;
+        const size_t r = zl_decompress_batch(c, &fsrc, &fsz, &fdst, &fcap, &fres, 1, 0);
+        const size_t err = zl_is_error(r) ? r : (zl_is_error(fres) ? fres : 0);
+        c->sIn.erase(c->sIn.begin(), c->sIn.begin() + (ptrdiff_t)fs);
+        if (err) { c->sOut.clear(); c->sOutPos = 0; return err; }
+        c->sOut.resize(fres); c->sOutPos = 0;
+        if (!fres && c->sIn.empty()) return 0;
+    }
+}
+ZL_ALIAS(size_t, ZSTD_decompressStream, (ZSTD_DCtx*, ZSTD_outBuffer*, ZSTD_inBuffer*))

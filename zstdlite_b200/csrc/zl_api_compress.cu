@@ -30,6 +30,10 @@ struct ZSTD_CCtx_s {
     unsigned long long launches = 0;
     ZlDevBuf dBlocks, dFrames, dM, dRecs, dLit, dHist, dMetas, dOuts, dPlans, dResults, dXxh, dXxhPtrs, dXxhSizes, dSrc, dDst, dAux;
     ZlPinBuf hBlocks, hFrames, hResults, hAux;
+    // streaming session (ZSTD_compressStream2): input accumulated on the host until ZSTD_e_end, then one frame is produced
+    std::vector<u8> sIn, sOut;
+    size_t sOutPos = 0;
+    bool sFlushing = false;
 };
 
 static bool g_constReady = false;
@@ -68,7 +72,9 @@ ZL_EXPORT size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
 }
 ZL_EXPORT size_t ZSTD_CCtx_reset(ZSTD_CCtx* c, ZSTD_ResetDirective r)          // zstd.c:23872
 {
-    if (r == ZSTD_reset_session_only || r == ZSTD_reset_session_and_parameters) c->pledged = ZSTD_CONTENTSIZE_UNKNOWN;
+    if (r == ZSTD_reset_session_only || r == ZSTD_reset_session_and_parameters) {
+        c->pledged = ZSTD_CONTENTSIZE_UNKNOWN; c->sIn.clear(); c->sOut.clear(); c->sOutPos = 0; c->sFlushing = false;
+    }
     if (r == ZSTD_reset_parameters || r == ZSTD_reset_session_and_parameters) {
         c->level = 3; c->nbWorkers = 0; c->checksumFlag = 0; c->stableIn = 0; c->stableOut = 0; c->dictRaw.clear(); c->dictDirty = true; c->dictErr = 0;
     }
@@ -346,6 +352,40 @@ ZL_EXPORT size_t ZSTD_compress2(ZSTD_CCtx* c, void* dst, size_t dstCap, const vo
     return zl_is_error(r) ? r : res;
 }
 ZL_ALIAS(size_t, ZSTD_compress2, (ZSTD_CCtx*, void*, size_t, const void*, size_t))
+
+// zstd.c:28828 ZSTD_compressStream2 over the one-shot engine: ZSTD_e_continue / ZSTD_e_flush only accumulate (a flush cannot
+// close a frame whose header must record the content size); ZSTD_e_end compresses everything as one frame and hands it out
+// in the caller's chunk sizes.  Return value as libzstd: bytes still to be flushed (0 = this frame is complete).
+ZL_EXPORT size_t ZSTD_compressStream2(ZSTD_CCtx* c, ZSTD_outBuffer* out, ZSTD_inBuffer* in, ZSTD_EndDirective end)
+{
+    if (!c || !out || !in) return ZL_ERROR(GENERIC);
+    if (out->pos > out->size) return ZL_ERROR(dstSize_tooSmall);
+    if (in->pos > in->size) return ZL_ERROR(srcSize_wrong);
+    if ((int)end < 0 || (int)end > 2) return ZL_ERROR(parameter_outOfBound);
+    if (!c->sFlushing) {
+        if (in->size > in->pos) c->sIn.insert(c->sIn.end(), (const u8*)in->src + in->pos, (const u8*)in->src + in->size);
+        in->pos = in->size;
+        if (end != ZSTD_e_end) return 0;
+        if (c->pledged != ZSTD_CONTENTSIZE_UNKNOWN && c->pledged != c->sIn.size()) {           // zstd.c:27190 (pledged size check)
+            c->sIn.clear(); c->pledged = ZSTD_CONTENTSIZE_UNKNOWN;
+            return ZL_ERROR(srcSize_wrong);
+        }
+        const size_t n = c->sIn.size(), cap = ZSTD_compressBound(n);
+        if (zl_is_error(cap)) return cap;
+        c->sOut.resize(cap ? cap : 1);
+        const size_t r = ZSTD_compress2(c, c->sOut.data(), cap, c->sIn.data(), n);
+        std::vector<u8>().swap(c->sIn);
+        if (zl_is_error(r)) { c->sOut.clear(); return r; }
+        c->sOut.resize(r); c->sOutPos = 0; c->sFlushing = true;
+    } else if (in->size > in->pos) return ZL_ERROR(stage_wrong);                                // new input while a frame is being flushed
+    const size_t room = out->size - out->pos, left = c->sOut.size() - c->sOutPos, k = room < left ? room : left;
+    if (k) memcpy((u8*)out->dst + out->pos, c->sOut.data() + c->sOutPos, k);
+    out->pos += k; c->sOutPos += k;
+    const size_t remaining = c->sOut.size() - c->sOutPos;
+    if (!remaining) { std::vector<u8>().swap(c->sOut); c->sOutPos = 0; c->sFlushing = false; }
+    return remaining;
+}
+ZL_ALIAS(size_t, ZSTD_compressStream2, (ZSTD_CCtx*, ZSTD_outBuffer*, ZSTD_inBuffer*, ZSTD_EndDirective))
 
 // One buffer -> concatenated independent frames of `frameSize` content bytes (a standard multi-frame zstd stream).
 ZL_EXPORT size_t zl_compress_split(ZSTD_CCtx* c, void* dst, size_t dstCap, const void* src, size_t srcSize, size_t frameSize,
