@@ -40,10 +40,10 @@ extern "C" size_t zl_emul_decompress_frame(void* dstv, size_t cap, const void* s
     {   // K1b
         static ZlSeqSm f;
         static i16 norm[3 * ZL_NORM_STRIDE];
-        zl_seq_begin_frame(f, info, 0);
+        zl_seq_begin_frame(f, info);
         for (u32 b = 0; b < info.nblocks; b++) {
             ZlBlockHdr h = hdrs[b];
-            if ((h.flags & 3) != 2) { zl_seq_plain_block(f, d, h); continue; }
+            if ((h.flags & 3) != 2) continue;
             zl_seq_head(f, d, h, g_ct, norm);
             if (!f.ctl.err && f.ctl.needBuild) for (u32 q = 0; q < 3; q++) zl_seq_fse_build(f, q, norm);
             zl_seq_decode(f, d, h, recs.data(), wbase, bias, g_ct, nullptr);
@@ -52,29 +52,41 @@ extern "C" size_t zl_emul_decompress_frame(void* dstv, size_t cap, const void* s
         zl_seq_finish_frame(f, info);
     }
     if (info.err) return (size_t)0 - (size_t)info.err;
+    // K2 restated serially: records -> (ll, ml, offBase), repeat-offset history, the checks of ZSTD_execSequence, the copies
     u8* out = d.dst; u32 op = 0; unsigned nrecTotal = 0;
+    u32 hist[3] = {1, 4, 8};
     for (u32 b = 0; b < info.nblocks; b++) {
         const ZlBlockHdr& h = hdrs[b];
         u32 type = h.flags & 3;
-        if (type == 0) memcpy(out + op, d.src + h.srcOff, h.regenSize);
-        else if (type == 1) memset(out + op, (h.flags >> 8) & 0xFF, h.regenSize);
-        else {
-            u32 litMode = (h.flags >> 4) & 3, o = op, lp = 0;
-            const u8* lit = litMode == 0 ? d.src + h.srcOff : lits.data() + h.litOff;
-            u8 rle = (u8)((h.flags >> 8) & 0xFF);
-            for (u32 i = 0; i < h.nrec; i++) {
-                u64 r = recs[h.recOff + i];
-                u32 ll = (u32)(r & 0xFFFF), ml = (u32)((r >> 16) & 0xFFFF), off = (u32)(r >> 32);
-                for (u32 k = 0; k < ll; k++) out[o + k] = litMode == 1 ? rle : lit[lp + k];
-                o += ll; lp += ll;
-                for (u32 k = 0; k < ml; k++) { out[o] = out[o - off]; o++; }
-            }
-            for (u32 k = lp; k < h.litSize; k++) out[o++] = litMode == 1 ? rle : lit[k];
-            if (o - op != h.regenSize) return (size_t)0 - 998;
-            nrecTotal += h.nrec;
+        const u32 room = d.dstCap - op;
+        if (type != 2) {
+            if (h.regenSize > room) return (size_t)0 - (size_t)ZL_E_dstSize_tooSmall;
+            if (type == 0) memcpy(out + op, d.src + h.srcOff, h.regenSize); else memset(out + op, (h.flags >> 8) & 0xFF, h.regenSize);
+            op += h.regenSize;
+            continue;
         }
-        op += h.regenSize;
+        u32 cap = room, capErr = ZL_E_dstSize_tooSmall;
+        if (cap > ZL_BLOCKSIZE_MAX) { cap = ZL_BLOCKSIZE_MAX; capErr = ZL_E_corruption_detected; }
+        u32 litMode = (h.flags >> 4) & 3, o = op, lp = 0;
+        const u8* lit = litMode == 0 ? d.src + h.srcOff : lits.data() + h.litOff;
+        u8 rle = (u8)((h.flags >> 8) & 0xFF);
+        for (u32 i = 0; i < h.nrec; i++) {
+            u32 ll, ml, ob;
+            zl_rec_decode(recs[h.recOff + i], g_ct.llBase, g_ct.llBits, g_ct.mlBase, g_ct.mlBits, ll, ml, ob);
+            const u32 off = zl_rep_resolve(hist, ll, ml, ob);
+            if (ll > h.litSize - lp) return (size_t)0 - (size_t)ZL_E_corruption_detected;
+            if ((u64)(o - op) + ll + ml > cap) return (size_t)0 - (size_t)capErr;
+            if (ml && (off == 0 || off > o + ll)) return (size_t)0 - (size_t)ZL_E_corruption_detected;
+            for (u32 k = 0; k < ll; k++) out[o + k] = litMode == 1 ? rle : lit[lp + k];
+            o += ll; lp += ll;
+            for (u32 k = 0; k < ml; k++) { out[o] = out[o - off]; o++; }
+        }
+        if ((o - op) + (h.litSize - lp) > cap) return (size_t)0 - (size_t)capErr;
+        for (u32 k = lp; k < h.litSize; k++) out[o++] = litMode == 1 ? rle : lit[k];
+        nrecTotal += h.nrec;
+        op = o;
     }
+    if (info.contentSize != ~0ull && info.contentSize != (u64)op) return (size_t)0 - (size_t)ZL_E_corruption_detected;
     if (nrecOut) *nrecOut = nrecTotal;
     return op;
 }

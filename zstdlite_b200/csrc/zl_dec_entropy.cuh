@@ -537,11 +537,8 @@ ZL_HD void zl_lit_block_head(ZlLitSm& f, const ZlFrameDesc& d, ZlFrameInfo& info
 // =================================================================================================== K1b: sequences
 struct ZlSeqCtl {
     u32 err;
-    u32 outPos;         // bytes regenerated so far in this frame
     u32 fseValid;
-    u32 rep[3];
     u32 recUsed;
-    u32 dictSize;       // bytes of history available before the frame start
     u32 nbSeq;
     u32 needBuild;      // bit t: build table t (0 LL, 1 OF, 2 ML) from norm[t]
     u32 tlog[3], maxSym[3], bErr[3];
@@ -612,18 +609,53 @@ ZL_HD void zl_seq_fse_build(ZlSeqSm& f, u32 t, const i16* norm)
     if (!zl_fse_build(tbl, norm + t * ZL_NORM_STRIDE, c.maxSym[t], c.tlog[t])) c.bErr[t] = 1;
 }
 
-// One sequence (zstd.c:44241-44358).  Bit order in the stream: OF, ML, LL additional bits, then the LL, ML, OF
-// state transitions (skipped for the last sequence).  Both groups are extracted from a snapshot of the 64-bit
-// window at positions that are prefix sums of the bit counts, so the reads are independent of each
-// other and only the state -> cell -> state chain is serial.
+// ---- sequence records (K1b -> K2) ---------------------------------------------------------------------------------------
+// K1b only runs the part of ZSTD_decodeSequence (zstd.c:44241-44358) that is inherently serial: the three FSE state
+// chains and the bit cursor.  Everything else -- extracting the additional bits, the base values, the repeat-offset
+// history (zstd.c:44290-44326), the bounds checks of ZSTD_execSequence (44024-44066) -- happens in K2, 32 sequences at a
+// time across the lanes of a warp.  A record is one u64 in one of two forms:
+//   form A (bit 63 = 0)  [0:32) the 32 stream bits that start with this sequence's additional bits (OF, ML, LL in that order)
+//                        [32:38) LL code  [38:44) ML code  [44:49) OF code           -- requires LL+ML+OF bits <= 32
+//   form B (bit 63 = 1)  [0:16) litLength  [16:32) matchLength  [32:63) offBase      -- explicit values, written by the
+//                        generic step; lengths >= 65536 are split: (65535, 0, 0) carries literals only, (0, m, 0) continues
+//                        the previous match at the same offset without touching the history
+// offBase = (1 << OFcode) + OFbits: 1..3 are the repeat codes, >= 4 is offset + 3 (zstd.c:19648-19652).
+#define ZL_REC_B (1ull << 63)
+ZL_HD u64 zl_rec_a(u32 snap, u32 llCode, u32 mlCode, u32 ofCode) { return (u64)snap | ((u64)(llCode | (mlCode << 6) | (ofCode << 12)) << 32); }
+ZL_HD u64 zl_rec_b(u32 ll, u32 ml, u32 offBase) { return ZL_REC_B | ((u64)offBase << 32) | ((u64)ml << 16) | (u64)ll; }
+// record -> (ll, ml, offBase); ct supplies the base / bits tables (zstd.c:15470-15495, 40060-40075)
+ZL_HD void zl_rec_decode(u64 r, const u32* llBase, const u8* llBits, const u32* mlBase, const u8* mlBits, u32& ll, u32& ml, u32& ob)
+{
+    if (r & ZL_REC_B) { ll = (u32)r & 0xFFFFu; ml = ((u32)r >> 16) & 0xFFFFu; ob = (u32)(r >> 32) & 0x7FFFFFFFu; return; }
+    const u32 snap = (u32)r, c = (u32)(r >> 32);
+    const u32 llCode = c & 63u, mlCode = (c >> 6) & 63u, aOF = (c >> 12) & 31u;
+    const u32 aML = mlBits[mlCode], aLL = llBits[llCode];
+    ob = (1u << aOF) + zl_shr(snap, 32u - aOF);
+    ml = mlBase[mlCode] + zl_shr(zl_shl(snap, aOF), 32u - aML);
+    ll = llBase[llCode] + zl_shr(zl_shl(snap, aOF + aML), 32u - aLL);
+}
+// Repeat-offset history step (zstd.c:44290-44326): resolves offBase against h[3], updates h, returns the offset
+// (0 = invalid: "rep0 - 1" with rep0 == 1).  ml == 0 records and offBase == 0 continuations leave the history alone.
+ZL_HD u32 zl_rep_resolve(u32 h[3], u32 ll, u32 ml, u32 ob)
+{
+    if (ml == 0) return 0;
+    if (ob == 0) return h[0];
+    if (ob >= 4) { const u32 off = ob - 3; h[2] = h[1]; h[1] = h[0]; h[0] = off; return off; }
+    const u32 idx = ob - 1 + (ll == 0 ? 1u : 0u);
+    if (idx == 0) return h[0];
+    const u32 off = idx == 1 ? h[1] : (idx == 2 ? h[2] : h[0] - 1);
+    if (idx >= 2) h[2] = h[1];
+    h[1] = h[0]; h[0] = off;
+    return off;
+}
+
 struct ZlSeqRegs {
     u32 sLL, sOF, sML;
-    u32 rep0, rep1, rep2;
-    u32 outPos, litPos, nrec, err;
+    u32 nrec, err;
 };
+// One sequence, generic form (first / last sequence of a block, more than 32 additional bits, lengths that may reach 65536).
 template <bool kLast>
-ZL_HD void zl_seq_step(const ZlSeqSm& f, ZlBitR& b, const u32* wbase, const ZlConstTables& ct, ZlSeqRegs& r,
-                       u64* rp, u32 recCap, u32 litSize, u32 outCap, u32 capErr, u32 hist)
+ZL_HD void zl_seq_step(const ZlSeqSm& f, ZlBitR& b, const u32* wbase, const ZlConstTables& ct, ZlSeqRegs& r, u64* rp, u32 recCap)
 {
     zl_br_refill(b, wbase);                                              // n >= 33
     const u32 eLL = f.fseLL[r.sLL], eOF = f.fseOF[r.sOF], eML = f.fseML[r.sML];
@@ -654,53 +686,34 @@ ZL_HD void zl_seq_step(const ZlSeqSm& f, ZlBitR& b, const u32* wbase, const ZlCo
         r.sOF = ((nOF << bOF) - (1u << gOF)) + zl_shr(zl_fsl(lo, hi, bLL + bML), 32u - bOF);
         zl_br_skip(b, bLL + bML + bOF);                                  // <= 26 bits
     }
+    if (aOF >= 31) { r.err = ZL_E_corruption_detected; return; }         // offsets of 2 GiB and more exceed any history we accept
     u32 ll = ct.llBase[llCode] + llx;
     u32 ml = ct.mlBase[mlCode] + mlx;
-    // offset / repcode history, branch-free (zstd.c:44290-44326).  aOF is the offset code.
-    const u32 ll0 = (llCode == 0);
-    const bool isRep = aOF <= 1;
-    const u32 idx = aOF == 0 ? ll0 : 1u + ll0 + ofx;                     // history slot (3 = rep0 - 1)
-    const u32 cand = idx == 0 ? r.rep0 : (idx == 1 ? r.rep1 : (idx == 2 ? r.rep2 : r.rep0 - 1));
-    const u32 offset = isRep ? cand : ((1u << aOF) - 3u + ofx);
-    r.rep2 = (!isRep || idx >= 2) ? r.rep1 : r.rep2;
-    r.rep1 = (!isRep || idx >= 1) ? r.rep0 : r.rep1;
-    r.rep0 = offset;
-    // validation that ZSTD_execSequence performs (zstd.c:44024-44066, 44320)
-    const u32 matchPos = r.outPos + ll;
-    if (offset == 0 || ll > litSize - r.litPos || offset > hist + matchPos) r.err = ZL_E_corruption_detected;
-    else if ((u64)matchPos + ml > outCap) r.err = capErr;
-    if (r.err) return;
-    if (((ll | ml) >> 16) == 0) {
-        rp[r.nrec++] = zl_pack_rec(ll, ml, offset);
-        r.outPos = matchPos + ml; r.litPos += ll;
-    } else {                                                             // lengths >= 65536: split into several records
-        while (ll > 65535) {
-            if (r.nrec >= recCap) { r.err = ZL_E_GENERIC; return; }
-            rp[r.nrec++] = zl_pack_rec(65535, 0, 0);
-            r.outPos += 65535; r.litPos += 65535; ll -= 65535;
-        }
-        do {
-            const u32 m = ml > 65535 ? 65535 : ml;
-            if (r.nrec >= recCap) { r.err = ZL_E_GENERIC; return; }
-            rp[r.nrec++] = zl_pack_rec(ll, m, offset);
-            r.outPos += ll + m; r.litPos += ll; ll = 0; ml -= m;
-        } while (ml);
+    const u32 ob = (1u << aOF) + ofx;
+    while (ll > 65535) {                                                 // lengths >= 65536: several records
+        if (r.nrec >= recCap) { r.err = ZL_E_GENERIC; return; }
+        rp[r.nrec++] = zl_rec_b(65535, 0, 0);
+        ll -= 65535;
     }
+    u32 first = 1;
+    do {
+        const u32 m = ml > 65535 ? 65535 : ml;
+        if (r.nrec >= recCap) { r.err = ZL_E_GENERIC; return; }
+        rp[r.nrec++] = zl_rec_b(ll, m, first ? ob : 0u);
+        ll = 0; ml -= m; first = 0;
+    } while (ml);
 }
 
 #if defined(__CUDACC__)
-// code -> (base value | additional bits << 24) for LL (36 entries) then ML (53 entries); built once per CTA in
-// shared memory from the constant tables so one load serves both the bit count (on the state chain) and the base.
+// code -> (base value | additional bits << 24) for LL (36 entries) then ML (53 entries), in shared memory
 #define ZL_XTAB_WORDS (36 + 53)
-// Fast path over consecutive non-last sequences whose additional bits fit one window (<= 32) and whose lengths fit a
-// single record.  Returns how many sequences it consumed; it stops BEFORE any sequence it cannot handle (the generic
-// zl_seq_step takes that one) and on errors (r.err set).  The loop is rotated: the three table cells of the next
-// sequence are requested as soon as the new states are known, and the record of the current one is built under
-// that latency.  States are kept "primed" (state + table size): a primed state is simply the cell's ns with the
-// nbBits fresh stream bits shifted in from the right -- one funnel shift -- and indexes the table at (base - size).
+// Fast path over consecutive non-last sequences whose additional bits fit one 32-bit snapshot and whose lengths fit
+// 16 bits.  Returns how many sequences it consumed; it stops BEFORE any sequence it cannot handle (the generic
+// zl_seq_step takes that one).  The loop is rotated: the three table cells of the next sequence are requested as soon as
+// the new states are known.  States are kept "primed" (state + table size): a primed state is simply the cell's ns with
+// the nbBits fresh stream bits shifted in from the right -- one funnel shift -- and indexes the table at (base - size).
 __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xtab, ZlBitR& b, const u32* wbase,
-                                                ZlSeqRegs& r, u64* rp, u32 maxIter, u32 safeCap, u32 litSize, u32 outCap,
-                                                u32 capErr, u32 hist)
+                                                ZlSeqRegs& r, u64* rp, u32 maxIter, u32 safeCap)
 {
     const u32 gLL = f.ctl.tlog[0], gOF = f.ctl.tlog[1], gML = f.ctl.tlog[2];
     const u32 zLL = 1u << gLL, zOF = 1u << gOF, zML = 1u << gML;
@@ -711,8 +724,10 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xta
     u32 hi = b.hi, lo = b.lo, nextw = b.nextw;
     i32 n = b.n, wi = b.wi;
     const i32 wlow = b.wlow;
-    u32 sLL = r.sLL + zLL, sOF = r.sOF + zOF, sML = r.sML + zML, rep0 = r.rep0, rep1 = r.rep1, rep2 = r.rep2;
-    u32 outPos = r.outPos, litPos = r.litPos, nrec = r.nrec;
+    u32 sLL = r.sLL + zLL, sOF = r.sOF + zOF, sML = r.sML + zML;
+    u64* wp = rp + r.nrec;
+    const u32 room = safeCap > r.nrec ? safeCap - r.nrec : 0u;
+    if (maxIter > room) maxIter = room;
     u32 eLL = zl_lds16(tLL + (sLL << 1)), eOF = zl_lds16(tOF + (sOF << 1)), eML = zl_lds16(tML + (sML << 1));
     u32 it = 0;
     while (it < maxIter) {
@@ -720,13 +735,10 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xta
         const u32 xl = zl_lds32(cLL + (llCode << 2)), xm = zl_lds32(cML + (mlCode << 2));
         const u32 nLL = ZL_CELL_NS(eLL), nML = ZL_CELL_NS(eML), nOF = ZL_CELL_NS(eOF);
         const u32 bLL = (u32)__clz((int)nLL) - kLL, bML = (u32)__clz((int)nML) - kML, bOF = (u32)__clz((int)nOF) - kOF;
-        const u32 aLL = xl >> 24, aML = xm >> 24;
-        const u32 c2 = aOF + aML, cA = c2 + aLL;
-        if (cA > 32 || llCode >= 35 || mlCode >= 51 || nrec >= safeCap) break;           // rare: leave it to the generic step
+        const u32 cA = aOF + (xl >> 24) + (xm >> 24);
+        if (cA > 32 || llCode >= 35 || mlCode >= 50) break;                               // rare: leave it to the generic step
         ZL_REFILL_DEV();                                                                   // n >= 33
-        const u32 ofx = zl_shr(hi, 32u - aOF);
-        const u32 mlx = zl_shr(zl_fsl(lo, hi, aOF), 32u - aML);
-        const u32 llx = zl_shr(zl_fsl(lo, hi, c2), 32u - aLL);
+        const u32 snap = hi;
         hi = zl_fsl(lo, hi, cA); lo = zl_shl(lo, cA); n -= (i32)cA;
         ZL_REFILL_DEV();
         const u32 d2 = bLL + bML, cB = d2 + bOF;                                           // <= 26
@@ -735,32 +747,18 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xta
         sOF = __funnelshift_l(zl_fsl(lo, hi, d2), nOF, bOF);
         hi = zl_fsl(lo, hi, cB); lo <<= cB; n -= (i32)cB;
         eLL = zl_lds16(tLL + (sLL << 1)); eOF = zl_lds16(tOF + (sOF << 1)); eML = zl_lds16(tML + (sML << 1));
-        // ---- record of the current sequence (off the state chain)
-        const u32 ll = (xl & 0xFFFFFFu) + llx, ml = (xm & 0xFFFFFFu) + mlx;
-        const u32 ll0 = (llCode == 0);
-        const bool isRep = aOF <= 1;
-        const u32 idx = aOF == 0 ? ll0 : 1u + ll0 + ofx;
-        const u32 cand = zl_selp(zl_selp(rep0 - 1, rep2, idx & 1), zl_selp(rep1, rep0, idx & 1), idx & 2);
-        const u32 offset = zl_selp(cand, (1u << aOF) - 3u + ofx, isRep);
-        rep2 = zl_selp(rep1, rep2, !isRep || idx >= 2);
-        rep1 = zl_selp(rep0, rep1, !isRep || idx >= 1);
-        rep0 = offset;
-        const u32 matchPos = outPos + ll;
-        const bool bad = (offset == 0) | (ll > litSize - litPos) | (offset > hist + matchPos);
-        const bool over = matchPos + ml > outCap;
-        if (bad | over) { r.err = bad ? (u32)ZL_E_corruption_detected : capErr; break; }
-        rp[nrec] = zl_pack_rec(ll, ml, offset);
-        nrec++; outPos = matchPos + ml; litPos += ll;
+        *wp++ = zl_rec_a(snap, llCode, mlCode, aOF);
         it++;
     }
     b.hi = hi; b.lo = lo; b.nextw = nextw; b.n = n; b.wi = wi;
-    r.sLL = sLL - zLL; r.sOF = sOF - zOF; r.sML = sML - zML; r.rep0 = rep0; r.rep1 = rep1; r.rep2 = rep2;
-    r.outPos = outPos; r.litPos = litPos; r.nrec = nrec;
+    r.sLL = sLL - zLL; r.sOF = sOF - zOF; r.sML = sML - zML;
+    r.nrec += it;
     return it;
 }
 #endif
 
-// serial sequence decode of one block (lane 0): zstd.c:44627-44700.  Completes the block's ZlBlockHdr.
+// serial sequence decode of one block (lane 0): zstd.c:44627-44700.  Completes the block's ZlBlockHdr (nrec, recOff);
+// the regenerated size is only known once K2 has added up the lengths.
 // `xtab` is only used by the device fast path (null in the CPU emulation).
 ZL_HD void zl_seq_decode(ZlSeqSm& f, const ZlFrameDesc& d, ZlBlockHdr& h, u64* recs, const u32* wbase, u32 bias,
                          const ZlConstTables& ct, const u32* xtab)
@@ -768,14 +766,11 @@ ZL_HD void zl_seq_decode(ZlSeqSm& f, const ZlFrameDesc& d, ZlBlockHdr& h, u64* r
     (void)xtab;
     ZlSeqCtl& c = f.ctl;
     if (!c.err && c.needBuild) { for (u32 t = 0; t < 3; t++) if (c.bErr[t]) c.err = ZL_E_corruption_detected; }
-    const u32 litSize = h.litSize;
-    u32 outCap = d.dstCap - c.outPos, capErr = ZL_E_dstSize_tooSmall;
-    if (outCap > ZL_BLOCKSIZE_MAX) { outCap = ZL_BLOCKSIZE_MAX; capErr = ZL_E_corruption_detected; }
     u64* rp = recs + c.recUsed;
     const u32 recCap = d.recCap - c.recUsed;
     ZlSeqRegs r;
-    r.outPos = 0; r.litPos = 0; r.nrec = 0; r.err = 0;
-    // every record of a valid block regenerates >= 3 bytes, so nbSeq + 4 (splits) always fits; reject early otherwise
+    r.nrec = 0; r.err = 0;
+    // every sequence of a valid block regenerates >= 3 bytes, so nbSeq + 4 (splits) always fits; reject early otherwise
     if (!c.err && c.nbSeq + 4 > recCap) c.err = c.nbSeq ? ZL_E_corruption_detected : 0;
     if (!c.err && c.nbSeq) {
         ZlBitR b;
@@ -786,55 +781,36 @@ ZL_HD void zl_seq_decode(ZlSeqSm& f, const ZlFrameDesc& d, ZlBlockHdr& h, u64* r
             r.sOF = zl_br_take(b, c.tlog[1]);
             zl_br_refill(b, wbase);
             r.sML = zl_br_take(b, c.tlog[2]);
-            r.rep0 = c.rep[0]; r.rep1 = c.rep[1]; r.rep2 = c.rep[2];
-            const u32 hist = c.outPos + c.dictSize;          // history before this block
             const u32 nbSeq = c.nbSeq;
             const u32 safeCap = recCap - 4;                  // split path re-checks exactly
             for (u32 i = 0; i + 1 < nbSeq; i++) {
 #if defined(__CUDA_ARCH__)
-                i += zl_seq_fast_loop(f, xtab, b, wbase, r, rp, nbSeq - 1 - i, safeCap, litSize, outCap, capErr, hist);
-                if (r.err || r.nrec >= safeCap || i + 1 >= nbSeq) break;
+                i += zl_seq_fast_loop(f, xtab, b, wbase, r, rp, nbSeq - 1 - i, safeCap);
+                if (r.nrec >= safeCap || i + 1 >= nbSeq) break;
 #endif
-                zl_seq_step<false>(f, b, wbase, ct, r, rp, recCap, litSize, outCap, capErr, hist);
+                zl_seq_step<false>(f, b, wbase, ct, r, rp, recCap);
                 if (r.err || r.nrec >= safeCap) break;
             }
             if (!r.err && r.nrec >= safeCap && nbSeq > 1) r.err = ZL_E_corruption_detected;
-            if (!r.err) zl_seq_step<true>(f, b, wbase, ct, r, rp, recCap, litSize, outCap, capErr, hist);
+            if (!r.err) zl_seq_step<true>(f, b, wbase, ct, r, rp, recCap);
             if (!r.err && zl_br_remaining(b, bias, c.bitBeg) != 0) r.err = ZL_E_corruption_detected;      // zstd.c:44686
             if (r.err) c.err = r.err;
-            c.rep[0] = r.rep0; c.rep[1] = r.rep1; c.rep[2] = r.rep2;
         }
     }
-    if (!c.err) {
-        const u32 lastLL = litSize - r.litPos;
-        if ((u64)r.outPos + lastLL > outCap) c.err = capErr;
-        else r.outPos += lastLL;
-    }
     if (c.err) return;
-    h.regenSize = r.outPos; h.nrec = r.nrec; h.recOff = c.recUsed;
+    h.nrec = r.nrec; h.recOff = c.recUsed;
     c.recUsed += r.nrec;
-    c.outPos += r.outPos;
 }
 
 // whole-frame driver pieces for K1b (lane 0)
-ZL_HD void zl_seq_begin_frame(ZlSeqSm& f, const ZlFrameInfo& info, u32 dictSize)
+ZL_HD void zl_seq_begin_frame(ZlSeqSm& f, const ZlFrameInfo& info)
 {
     ZlSeqCtl& c = f.ctl;
-    c.err = info.err; c.outPos = 0; c.fseValid = 0; c.rep[0] = 1; c.rep[1] = 4; c.rep[2] = 8;     // zstd.c:15416
-    c.recUsed = 0; c.dictSize = dictSize; c.nbSeq = 0; c.needBuild = 0;
+    c.err = info.err; c.fseValid = 0;
+    c.recUsed = 0; c.nbSeq = 0; c.needBuild = 0;
     c.bErr[0] = c.bErr[1] = c.bErr[2] = 0;
-}
-// raw / RLE blocks only need their size checked against the destination (zstd.c:41497-41520)
-ZL_HD void zl_seq_plain_block(ZlSeqSm& f, const ZlFrameDesc& d, const ZlBlockHdr& h)
-{
-    ZlSeqCtl& c = f.ctl;
-    if (c.err) return;
-    if (h.regenSize > d.dstCap - c.outPos) c.err = ZL_E_dstSize_tooSmall;
-    else c.outPos += h.regenSize;
 }
 ZL_HD void zl_seq_finish_frame(ZlSeqSm& f, ZlFrameInfo& info)
 {
-    ZlSeqCtl& c = f.ctl;
-    if (!c.err && info.contentSize != ~0ull && info.contentSize != (u64)c.outPos) c.err = ZL_E_corruption_detected;   // zstd.c:41646
-    info.err = c.err; info.totalOut = c.outPos;
+    info.err = f.ctl.err;          // sizes are checked by K2 (destination capacity per block, content size at the end: zstd.c:41646)
 }

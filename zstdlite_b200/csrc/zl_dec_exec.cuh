@@ -13,6 +13,7 @@
 // zstd.c:44024-44066 were already applied by the entropy kernel when it produced the records.
 #pragma once
 #include "zl_common.cuh"
+#include "zl_dec_entropy.cuh"     // record forms, zl_rep_resolve
 
 #if defined(__CUDACC__)
 
@@ -48,19 +49,94 @@ ZL_D void zl_warp_fill(u8* dst, u32 byte, u32 n, u32 lane)
     for (u32 i = done + lane; i < n; i += 32) dst[i] = (u8)byte;
 }
 
-// Execute one compressed block.  `out` = frame output base, `op` = frame-relative position of the block.
-template <bool kDict>
-ZL_D void zl_exec_block(u8* out, u32 op, const ZlBlockHdr& h, const u8* lit, u32 rleByte, u32 litMode,
-                        const u64* __restrict__ recs, const u8* dict, u32 dictSize, u32 lane)
+// ---- repeat-offset history as a composable transform ------------------------------------------------------------------
+// A record maps the history (h0, h1, h2) to a new one.  Except for the rare "rep0 - 1" code, every output slot is either
+// one of the three input slots or the fresh offset of some record of the batch, so a transform is three bytes:
+// 0..2 = input slot, 0x80 | lane = the offset carried by that lane.  Two transforms compose with a single byte permute
+// (PRMT), and a warp scan over the 32 records of a batch gives every lane the history that precedes its record
+// (zstd.c:44290-44326 restated for 32 lanes); actual offsets are fetched from the named lane with one shuffle.
+#define ZL_REPT_ID 0x00020100u
+ZL_D u32 zl_rept_compose(u32 A, u32 B)          // A first, then B
 {
-    const u32 nrec = h.nrec;
+    const u32 m = (B >> 7) & 0x00010101u;                               // 1 in the bytes of B that name a lane
+    const u32 mm = m * 0xFFu;
+    const u32 r = (B & 0x00030303u & ~mm) | (0x00060504u & mm);         // per byte: input slot of A, or 4 + j (keep B's byte)
+    const u32 sel = (r & 0xFu) | ((r >> 4) & 0xF0u) | ((r >> 8) & 0xF00u) | 0x3000u;
+    return __byte_perm(A, B, sel) & 0x00FFFFFFu;
+}
+
+// Execute one compressed block: `out` = frame output base, `op` = frame-relative position of the block, `cap` = bytes the
+// block may still regenerate (destination room, at most one block size), `capErr` the error to report beyond it.
+// hist[3] is the repeat-offset history carried from block to block.  Returns 0 and sets `regen`, or a ZlErr.
+template <bool kDict>
+ZL_D u32 zl_exec_block(u8* out, u32 op, u32 cap, u32 capErr, const ZlBlockHdr& h, const u8* __restrict__ lit, u32 rleByte, u32 litMode,
+                       const u64* __restrict__ recs, const u8* __restrict__ dict, u32 dictSize, u32 (&hist)[3], const u32* xtab, u32 lane, u32& regen)
+{
+    const u32 nrec = h.nrec, litSize = h.litSize;
     u32 outPos = op, litPos = 0;
-    u64 recNext = lane < nrec ? recs[lane] : 0ull;
+    u32 h0 = hist[0], h1 = hist[1], h2 = hist[2];
+    u64 recNext = lane < nrec ? __ldcs(recs + lane) : 0ull;
     for (u32 base = 0; base < nrec; base += 32) {
         const u64 rec = recNext;
-        {   const u32 in = base + 32 + lane; recNext = in < nrec ? recs[in] : 0ull; }
-        const u32 ll = (u32)(rec & 0xFFFF), ml = (u32)((rec >> 16) & 0xFFFF), off = (u32)(rec >> 32);
-        // inclusive scans of ll and ll+ml
+        const bool valid = base + lane < nrec;
+        {   const u32 in = base + 32 + lane; recNext = in < nrec ? __ldcs(recs + in) : 0ull; }
+        // ---- record -> litLength, matchLength, offBase
+        u32 ll = 0, ml = 0, ob = 0;
+        if (valid) {
+            if (rec & ZL_REC_B) { ll = (u32)rec & 0xFFFFu; ml = ((u32)rec >> 16) & 0xFFFFu; ob = (u32)(rec >> 32) & 0x7FFFFFFFu; }
+            else {
+                const u32 snap = (u32)rec, c = (u32)(rec >> 32);
+                const u32 llCode = c & 63u, mlCode = (c >> 6) & 63u, aOF = (c >> 12) & 31u;
+                const u32 xl = xtab[llCode], xm = xtab[36 + mlCode];
+                const u32 aLL = xl >> 24, aML = xm >> 24;
+                ob = (1u << aOF) + zl_shr(snap, 32u - aOF);
+                ml = (xm & 0xFFFFFFu) + zl_shr(zl_shl(snap, aOF), 32u - aML);
+                ll = (xl & 0xFFFFFFu) + zl_shr(zl_shl(snap, aOF + aML), 32u - aLL);
+            }
+        }
+        // ---- repeat-offset history: offset of every record, history after the batch
+        const bool isM = ml != 0;
+        const bool isNew = isM && ob >= 4;
+        const u32 idx = (isM && ob >= 1 && ob <= 3) ? ob - 1 + (ll == 0 ? 1u : 0u) : 0u;      // 0 also for non-repeat records
+        u32 off;
+        if (__ballot_sync(ZL_FULL, idx == 3)) {
+            // rare "rep0 - 1" code somewhere in the batch: resolve the 32 records one after the other (uniform loop)
+            off = 0;
+            u32 hh[3] = {h0, h1, h2};
+            for (u32 l = 0; l < 32; l++) {
+                const u32 lll = __shfl_sync(ZL_FULL, ll, l), lml = __shfl_sync(ZL_FULL, ml, l), lob = __shfl_sync(ZL_FULL, ob, l);
+                const u32 o = zl_rep_resolve(hh, lll, lml, lob);
+                if (l == lane) off = o;
+            }
+            h0 = hh[0]; h1 = hh[1]; h2 = hh[2];
+        } else {
+            const u32 fresh = ob - 3;                                               // meaningful on isNew lanes
+            u32 T = ZL_REPT_ID;
+            if (isNew) T = 0x00010000u | 0x80u | lane;                              // (mine, h0, h1)
+            else if (idx == 1) T = 0x00020001u;                                     // (h1, h0, h2)
+            else if (idx == 2) T = 0x00010002u;                                     // (h2, h0, h1)
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 A = __shfl_up_sync(ZL_FULL, T, d);
+                if ((int)lane >= d) T = zl_rept_compose(A, T);
+            }
+            u32 E = __shfl_up_sync(ZL_FULL, T, 1);                                  // exclusive prefix: history before this record
+            if (lane == 0) E = ZL_REPT_ID;
+            // the slot of the incoming history this record reads (repeat codes and continuations): byte idx of E
+            const u32 eb = (E >> (8 * idx)) & 0xFFu;
+            const u32 fromLane = __shfl_sync(ZL_FULL, fresh, eb & 31u);
+            const u32 fromHist = (eb & 3u) == 0 ? h0 : ((eb & 3u) == 1 ? h1 : h2);
+            off = isNew ? fresh : ((eb & 0x80u) ? fromLane : fromHist);
+            // history after the batch: the inclusive prefix of lane 31
+            const u32 Lt = __shfl_sync(ZL_FULL, T, 31);
+            const u32 b0 = Lt & 0xFFu, b1 = (Lt >> 8) & 0xFFu, b2 = (Lt >> 16) & 0xFFu;
+            const u32 f0 = __shfl_sync(ZL_FULL, fresh, b0 & 31u), f1 = __shfl_sync(ZL_FULL, fresh, b1 & 31u), f2 = __shfl_sync(ZL_FULL, fresh, b2 & 31u);
+            const u32 n0 = (b0 & 0x80u) ? f0 : ((b0 & 3u) == 0 ? h0 : ((b0 & 3u) == 1 ? h1 : h2));
+            const u32 n1 = (b1 & 0x80u) ? f1 : ((b1 & 3u) == 0 ? h0 : ((b1 & 3u) == 1 ? h1 : h2));
+            const u32 n2 = (b2 & 0x80u) ? f2 : ((b2 & 3u) == 0 ? h0 : ((b2 & 3u) == 1 ? h1 : h2));
+            h0 = n0; h1 = n1; h2 = n2;
+        }
+        // ---- positions: inclusive scans of ll and ll+ml
         u32 sl = ll, so = ll + ml;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -71,56 +147,83 @@ ZL_D void zl_exec_block(u8* out, u32 op, const ZlBlockHdr& h, const u8* lit, u32
         const u32 litExcl = sl - ll;                 // literal bytes of earlier lanes in this batch
         const u32 dstLit = outPos + so - ll - ml;    // where this lane's literals go
         const u32 dm = dstLit + ll;                  // where this lane's match goes
-        // ---- literals: flat byte-parallel copy over the batch (all lanes run every iteration: shuffles)
-        for (u32 j0 = 0; j0 < totalL; j0 += 32) {
-            const u32 j = j0 + lane;
-            u32 k = 0;                               // owner = first lane whose inclusive sum exceeds j
+        // ---- the checks of ZSTD_execSequence (zstd.c:44024-44066, 44320) for the whole batch, before anything is written
+        if (totalL > litSize - litPos) return ZL_E_corruption_detected;
+        if ((outPos - op) + totalO > cap) return capErr;
+        if (__ballot_sync(ZL_FULL, isM && (off == 0 || off > dm + dictSize))) return ZL_E_corruption_detected;
+        // ---- literals: flat byte-parallel copy over the batch, two rows of 32 bytes per step (loads before stores)
+        for (u32 j0 = 0; j0 < totalL; j0 += 64) {
+            u32 dpos[2]; u32 val[2]; bool act[2];
 #pragma unroll
-            for (int st = 16; st >= 1; st >>= 1) {
-                const u32 v = __shfl_sync(ZL_FULL, sl, (k + st - 1) & 31);
-                if (v <= j) k += st;
+            for (int u = 0; u < 2; u++) {
+                const u32 j = j0 + 32 * u + lane;
+                u32 k = 0;                               // owner = first lane whose inclusive sum exceeds j
+#pragma unroll
+                for (int st = 16; st >= 1; st >>= 1) {
+                    const u32 v = __shfl_sync(ZL_FULL, sl, (k + st - 1) & 31);
+                    if (v <= j) k += st;
+                }
+                k &= 31;
+                const u32 kDst = __shfl_sync(ZL_FULL, dstLit, k), kEx = __shfl_sync(ZL_FULL, litExcl, k);
+                act[u] = j < totalL;
+                dpos[u] = kDst + (j - kEx);
+                val[u] = !act[u] ? 0u : (litMode == 1 ? rleByte : (u32)__ldg(lit + litPos + j));
             }
-            k &= 31;
-            const u32 kDst = __shfl_sync(ZL_FULL, dstLit, k), kEx = __shfl_sync(ZL_FULL, litExcl, k);
-            if (j < totalL) out[kDst + (j - kEx)] = litMode == 1 ? (u8)rleByte : lit[litPos + j];
+#pragma unroll
+            for (int u = 0; u < 2; u++) if (act[u]) out[dpos[u]] = (u8)val[u];
         }
         __syncwarp();
         // ---- matches: rounds against the high-water mark (signed positions: negative = dictionary)
-        u32 pending = __ballot_sync(ZL_FULL, ml != 0);
+        u32 pending = __ballot_sync(ZL_FULL, isM);
         const i32 srcBeg = (i32)dm - (i32)off;
-        const i32 needEnd = srcBeg + (i32)(off < ml ? off : ml);      // end of the source bytes actually read, <= dm
+        const bool overlap = off < ml;
+        const i32 needEnd = srcBeg + (i32)(overlap ? off : ml);       // end of the source bytes actually read, <= dm
         while (pending) {
             const u32 f = (u32)__ffs((int)pending) - 1;
             const i32 hwm = (i32)__shfl_sync(ZL_FULL, dm, f);
             const bool ready = ((pending >> lane) & 1) && (lane == f || needEnd <= hwm);
-            if (ready && ml <= 32) {
-                u32 s = 0;
-                for (u32 k = 0; k < ml; k += 4) {
-                    u8 t[4];
+            // (a) ready matches that do not overlap their own output: one flat byte-parallel copy over all of them, so the
+            //     lanes share the bytes evenly whatever the individual lengths are; two rows per step, loads before stores
+            const u32 fl = (ready && !overlap) ? ml : 0u;
+            u32 rs = fl;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if (k + j < ml) {
-                            const i32 sp = srcBeg + (i32)s;
-                            if (kDict && sp < 0) t[j] = dict[(i32)dictSize + sp]; else t[j] = out[sp];
-                            if (++s == off) s = 0;
-                        }
+            for (int d = 1; d < 32; d <<= 1) { const u32 a = __shfl_up_sync(ZL_FULL, rs, d); if ((int)lane >= d) rs += a; }
+            const u32 totalM = __shfl_sync(ZL_FULL, rs, 31);
+            const u32 rsExcl = rs - fl;
+            for (u32 j0 = 0; j0 < totalM; j0 += 64) {
+                u32 dpos[2]; u32 val[2]; bool act[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const u32 j = j0 + 32 * u + lane;
+                    u32 k = 0;
+#pragma unroll
+                    for (int st = 16; st >= 1; st >>= 1) {
+                        const u32 v = __shfl_sync(ZL_FULL, rs, (k + st - 1) & 31);
+                        if (v <= j) k += st;
                     }
-#pragma unroll
-                    for (int j = 0; j < 4; j++) if (k + j < ml) out[dm + k + j] = t[j];
+                    k &= 31;
+                    const u32 kDm = __shfl_sync(ZL_FULL, dm, k), kEx = __shfl_sync(ZL_FULL, rsExcl, k);
+                    const i32 kSrc = (i32)__shfl_sync(ZL_FULL, (u32)srcBeg, k);
+                    act[u] = j < totalM;
+                    const u32 r = j - kEx;
+                    dpos[u] = kDm + r;
+                    const i32 sp = kSrc + (i32)r;
+                    val[u] = !act[u] ? 0u : ((kDict && sp < 0) ? (u32)dict[(i32)dictSize + sp] : (u32)out[sp]);
                 }
+#pragma unroll
+                for (int u = 0; u < 2; u++) if (act[u]) out[dpos[u]] = (u8)val[u];
             }
-            u32 big = __ballot_sync(ZL_FULL, ready && ml > 32);
-            while (big) {
-                const u32 L = (u32)__ffs((int)big) - 1;
-                big &= big - 1;
+            // (b) ready matches that overlap their own output (offset < length): the periodic form dst[k] = src[k mod offset]
+            //     only reads bytes below the match, one match at a time across the warp
+            u32 ov = __ballot_sync(ZL_FULL, ready && overlap);
+            while (ov) {
+                const u32 L = (u32)__ffs((int)ov) - 1;
+                ov &= ov - 1;
                 const u32 bdm = __shfl_sync(ZL_FULL, dm, L), boff = __shfl_sync(ZL_FULL, off, L), bml = __shfl_sync(ZL_FULL, ml, L);
                 const i32 bsrc = (i32)bdm - (i32)boff;
-                if (boff >= bml && bsrc >= 0) zl_warp_copy(out + bdm, out + bsrc, bml, lane);
-                else {
-                    for (u32 k = lane; k < bml; k += 32) {
-                        const i32 sp = bsrc + (i32)(boff >= bml ? k : k % boff);
-                        out[bdm + k] = (kDict && sp < 0) ? dict[(i32)dictSize + sp] : out[sp];
-                    }
+                for (u32 k = lane; k < bml; k += 32) {
+                    const i32 sp = bsrc + (i32)(k % boff);
+                    out[bdm + k] = (kDict && sp < 0) ? dict[(i32)dictSize + sp] : out[sp];
                 }
             }
             __syncwarp();
@@ -129,9 +232,13 @@ ZL_D void zl_exec_block(u8* out, u32 op, const ZlBlockHdr& h, const u8* lit, u32
         outPos += totalO; litPos += totalL;
     }
     // last literals (zstd.c:44692-44698)
-    const u32 lastLL = h.litSize - litPos;
+    const u32 lastLL = litSize - litPos;
+    if ((outPos - op) + lastLL > cap) return capErr;
     if (litMode == 1) zl_warp_fill(out + outPos, rleByte, lastLL, lane);
     else zl_warp_copy(out + outPos, lit + litPos, lastLL, lane);
+    hist[0] = h0; hist[1] = h1; hist[2] = h2;
+    regen = outPos - op + lastLL;
+    return 0;
 }
 
 // ---- XXH64 (zstd.c:11509-11664), one quad per buffer: lane a of the quad owns accumulator a -----------

@@ -78,11 +78,10 @@ zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ 
     const u32 nblocks = info.nblocks;
     const bool seed = dict && dict->hasEntropy;
     if (q == 0) {
-        zl_seq_begin_frame(f, info, dict ? dict->contentSize : 0u);
-        if (seed) {                                                   // zstd.c:42140-42159: tables + repcodes from the dictionary
+        zl_seq_begin_frame(f, info);
+        if (seed) {                                                   // zstd.c:42140-42159: tables from the dictionary (repcodes: K2)
             f.ctl.fseValid = 7;
             f.ctl.tlog[0] = dict->tlog[0]; f.ctl.tlog[1] = dict->tlog[1]; f.ctl.tlog[2] = dict->tlog[2];
-            f.ctl.rep[0] = dict->rep[0]; f.ctl.rep[1] = dict->rep[1]; f.ctl.rep[2] = dict->rep[2];
         }
     }
     if (seed) {
@@ -92,7 +91,7 @@ zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ 
     __syncwarp(qmask);
     for (u32 b = 0; b < nblocks; b++) {
         ZlBlockHdr h = hdrs[b];
-        if ((h.flags & 3) != 2) { if (q == 0) zl_seq_plain_block(f, d, h); continue; }
+        if ((h.flags & 3) != 2) continue;
         if (q == 0) zl_seq_head(f, d, h, ct, norm);
         __syncwarp(qmask);
         const u32 build = f.ctl.err ? 0u : f.ctl.needBuild;
@@ -105,10 +104,14 @@ zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ 
 
 template <bool kDict>
 __global__ void __launch_bounds__(ZL_EXEC_WARPS * 32)
-zl_k_execute(const ZlFrameDesc* __restrict__ descs, const ZlFrameInfo* __restrict__ infos,
+zl_k_execute(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos,
              const ZlBlockHdr* __restrict__ hdrArena, const u64* __restrict__ recArena,
              const u8* __restrict__ litArena, u64* __restrict__ results, u32 nframes, const ZlDictDev* dict)
 {
+    __shared__ u32 xtab[ZL_XTAB_WORDS];
+    for (u32 i = threadIdx.x; i < ZL_XTAB_WORDS; i += ZL_EXEC_WARPS * 32)
+        xtab[i] = i < 36 ? (c_tables.llBase[i] | ((u32)c_tables.llBits[i] << 24)) : (c_tables.mlBase[i - 36] | ((u32)c_tables.mlBits[i - 36] << 24));
+    __syncthreads();
     const u32 lane = threadIdx.x & 31;
     const u32 frame = blockIdx.x * ZL_EXEC_WARPS + (threadIdx.x >> 5);
     if (frame >= nframes) return;
@@ -118,22 +121,34 @@ zl_k_execute(const ZlFrameDesc* __restrict__ descs, const ZlFrameInfo* __restric
     const ZlBlockHdr* hdrs = hdrArena + d.hdrBase;
     const u8* dictContent = kDict ? dict->content : nullptr;
     const u32 dictSize = kDict ? dict->contentSize : 0u;
-    u32 op = 0;
-    for (u32 b = 0; b < info.nblocks; b++) {
+    u32 hist[3] = {1, 4, 8};                                          // zstd.c:15416
+    if (kDict && dict->hasEntropy) { hist[0] = dict->rep[0]; hist[1] = dict->rep[1]; hist[2] = dict->rep[2]; }   // zstd.c:42140-42159
+    u32 op = 0, err = 0;
+    for (u32 b = 0; b < info.nblocks && !err; b++) {
         const ZlBlockHdr h = hdrs[b];
         const u32 type = h.flags & 3;
-        if (type == 0) zl_warp_copy(d.dst + op, d.src + h.srcOff, h.regenSize, lane);
-        else if (type == 1) zl_warp_fill(d.dst + op, (h.flags >> 8) & 0xFF, h.regenSize, lane);
-        else {
+        const u32 room = d.dstCap - op;
+        if (type != 2) {                                              // raw / RLE block (zstd.c:41497-41520)
+            if (h.regenSize > room) { err = ZL_E_dstSize_tooSmall; break; }
+            if (type == 0) zl_warp_copy(d.dst + op, d.src + h.srcOff, h.regenSize, lane);
+            else zl_warp_fill(d.dst + op, (h.flags >> 8) & 0xFF, h.regenSize, lane);
+            op += h.regenSize;
+        } else {
             const u32 litMode = (h.flags >> 4) & 3;
             const u8* lit = litMode == 0 ? d.src + h.srcOff : litArena + d.litBase + h.litOff;
-            zl_exec_block<kDict>(d.dst, op, h, lit, (h.flags >> 8) & 0xFF, litMode, recArena + d.recBase + h.recOff,
-                                 dictContent, dictSize, lane);
+            u32 cap = room, capErr = ZL_E_dstSize_tooSmall, regen = 0;
+            if (cap > ZL_BLOCKSIZE_MAX) { cap = ZL_BLOCKSIZE_MAX; capErr = ZL_E_corruption_detected; }
+            err = zl_exec_block<kDict>(d.dst, op, cap, capErr, h, lit, (h.flags >> 8) & 0xFF, litMode, recArena + d.recBase + h.recOff,
+                                       dictContent, dictSize, hist, xtab, lane, regen);
+            op += regen;
         }
-        op += h.regenSize;
         __syncwarp();
     }
-    if (lane == 0) results[frame] = (u64)op;
+    if (!err && info.contentSize != ~0ull && info.contentSize != (u64)op) err = ZL_E_corruption_detected;      // zstd.c:41646
+    if (lane == 0) {
+        results[frame] = err ? (u64)0 - (u64)err : (u64)op;
+        infos[frame].err = err; infos[frame].totalOut = op;
+    }
 }
 
 __global__ void __launch_bounds__(128)
