@@ -409,7 +409,7 @@ ZL_HD u32 zl_huf_stream(const u16* huf, u32 tlog, const u32* wbase, u32 bias, u3
                 u32 s0, s1, s2, s3;
                 ZL_REFILL_DEV(); ZL_HUF_SYM_DEV(s0); ZL_HUF_SYM_DEV(s1);
                 ZL_REFILL_DEV(); ZL_HUF_SYM_DEV(s2); ZL_HUF_SYM_DEV(s3);
-                *(u32*)(out + i) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+                __stcs((u32*)(out + i), s0 | (s1 << 8) | (s2 << 16) | (s3 << 24));      // streaming store: keep L1 for the bitstreams
                 i += 4;
             }
 #undef ZL_HUF_SYM_DEV
@@ -747,7 +747,7 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xta
         sOF = __funnelshift_l(zl_fsl(lo, hi, d2), nOF, bOF);
         hi = zl_fsl(lo, hi, cB); lo <<= cB; n -= (i32)cB;
         eLL = zl_lds16(tLL + (sLL << 1)); eOF = zl_lds16(tOF + (sOF << 1)); eML = zl_lds16(tML + (sML << 1));
-        *wp++ = zl_rec_a(snap, llCode, mlCode, aOF);
+        __stcs(wp++, zl_rec_a(snap, llCode, mlCode, aOF));                                  // streaming store: keep L1 for the bitstream
         it++;
     }
     b.hi = hi; b.lo = lo; b.nextw = nextw; b.n = n; b.wi = wi;

@@ -6,11 +6,13 @@
 #define ZL_QUADS_PER_WARP 8
 #define ZL_EXEC_WARPS 4
 #define ZL_DEC_STAGES 4      // literals, sequences, execute, checksum
-#define ZL_DEC_LANES 4                       // internal streams of the decode slice pipeline
-#define ZL_DEC_MAX_SLICES 16
+#define ZL_DEC_LANES 8                       // internal streams of the decode slice pipeline
+#define ZL_DEC_MAX_SLICES 8                  // one slice per lane: concurrency between streams is what pays, not queueing
 #define ZL_DEC_SLICE_BYTES (64ull << 20)     // aim for >= 64 MiB of content ...
 #define ZL_DEC_SLICE_MIN_FRAMES 512          // ... and >= 512 frames per slice (host buffers)
-#define ZL_DEC_SLICE_DEV_FRAMES 32768        // device buffers: slices of >= 32,768 frames
+#define ZL_DEC_SLICE_DEV_FRAMES 2048         // device buffers: slices of >= 2,048 frames (kernels of different slices run concurrently:
+                                             // the execute kernel is issue-bound and uses no shared memory, the entropy kernels are
+                                             // latency-bound and limited by shared memory, so they fill each other's idle resources)
 
 // digested dictionary in device memory (zstd.c:42053-42159, ZSTD_DDict): entropy tables in the packed
 // cell formats of zl_dec_entropy.cuh plus the raw content that acts as history before the frame.
