@@ -195,10 +195,67 @@ def compress_leg(torch, z, args, dev):
         host = dst.cpu().numpy()
         for i in range(0, n, max(1, n // 16)):
             assert ref.decompress(host[i * slot:i * slot + int(sizes[i])].tobytes()) == data[i].tobytes(), "GPU frame does not round-trip through libzstd"
+        L = z._lib.lib()
         out[f"level{lvl}"] = {"GBps": n * fb / ms / 1e6, "ms": ms, "ratio": n * fb / csize, "ratio_libzstd": n * fb / refsize,
                               "ratio_vs_libzstd": (n * fb / csize) / (n * fb / refsize), "kernel_ms": cctx.last_kernel_ms,
+                              "stages_ms": {nm: L.zl_cctx_last_stage_ms(cctx._p, k) for k, nm in enumerate(("match", "parse", "literals", "sequences", "plan+assemble"))},
                               "frames": n, "frame_bytes": fb}
     return out
+
+
+def dict_leg(torch, z, args, dev):
+    """configs[3]: 1e5 small objects, dictionary trained by the reference's ZDICT on the first 1e4 (5,000 B), level 3;
+    device-resident batch compress then decompress with the dictionary; sizes compared with libzstd + the same dictionary."""
+    from oracle import ref
+    from zstdlite_b200 import corpus
+    n = args.dict_objects
+    objs = corpus.small_objects(n)
+    d = ref.train_dict(objs[:min(n, 10000)], 5000)
+    sizes = [len(o) for o in objs]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    total = int(offs[-1])
+    src = torch.from_numpy(np.frombuffer(b"".join(objs), dtype=np.uint8).copy()).to(dev)
+    L = z._lib.lib()
+    caps = [int(L.ZSTD_compressBound(s)) for s in sizes]
+    coffs = np.concatenate([[0], np.cumsum([(c + 15) // 16 * 16 for c in caps])]).astype(np.int64)
+    cdst = torch.zeros(int(coffs[-1]) + 64, dtype=torch.uint8, device=dev)
+    cctx, dctx = z.zstd_cctx(level=3, dict=d), z.zstd_dctx(dict=d)
+    stream = torch.cuda.current_stream()
+    cctx.set_stream(stream.cuda_stream); dctx.set_stream(stream.cuda_stream)
+    cplan = z.BatchPlan([src.data_ptr() + int(o) for o in offs[:-1]], sizes, [cdst.data_ptr() + int(o) for o in coffs[:-1]], caps)
+    res = None
+    for _ in range(2):
+        res = cplan.compress(cctx)
+    csz = [int(r) for r in res]
+    assert not any(z.is_error(r) for r in csz[:256])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(3):
+        cplan.compress(cctx)
+    e1.record(stream); torch.cuda.synchronize()
+    ms_c = e0.elapsed_time(e1) / 3
+    ddst = torch.zeros(total + 64, dtype=torch.uint8, device=dev)
+    dplan = z.BatchPlan([cdst.data_ptr() + int(o) for o in coffs[:-1]], csz, [ddst.data_ptr() + int(o) for o in offs[:-1]], sizes)
+    for _ in range(2):
+        dres = dplan.decompress(dctx)
+    assert all(int(r) == s for r, s in zip(dres, sizes)), "dictionary decode errors"
+    assert bytes(ddst[:total].cpu().numpy()) == b"".join(objs), "dictionary round trip differs"
+    e0.record(stream)
+    for _ in range(3):
+        dplan.decompress(dctx)
+    e1.record(stream); torch.cuda.synchronize()
+    ms_d = e0.elapsed_time(e1) / 3
+    rc, rd = ref.CCtx(level=3, dict=d), ref.DCtx(dict=d)
+    step = max(1, n // 5000)
+    host = cdst.cpu().numpy()
+    ours = theirs = 0
+    for i in range(0, n, step):                       # bounded sample for the libzstd comparison + cross-decode
+        c = host[int(coffs[i]):int(coffs[i]) + csz[i]].tobytes()
+        assert rd.decompress(c, cap=sizes[i]) == objs[i], "GPU dictionary frame does not decode with libzstd"
+        ours += csz[i]; theirs += len(rc.compress(objs[i]))
+    return {"objects": n, "bytes": total, "dict_bytes": len(d), "level": 3, "compress_GBps": total / ms_c / 1e6, "compress_ms": ms_c,
+            "decompress_GBps": total / ms_d / 1e6, "decompress_ms": ms_d, "ratio": total / sum(csz),
+            "size_vs_libzstd_same_dict": ours / theirs, "sampled_objects": len(range(0, n, step))}
 
 
 def main():
@@ -213,6 +270,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--compress-frames", type=int, default=4096)
     ap.add_argument("--no-compress", action="store_true")
+    ap.add_argument("--dict-objects", type=int, default=100000)
+    ap.add_argument("--no-dict", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -361,6 +420,11 @@ def main():
                 out["compress"] = compress_leg(torch, z, args, dev)
             except Exception as e:                                      # the headline is the decode arm; report, don't hide
                 out["compress"] = {"error": repr(e)}
+        if world == 1 and not args.no_dict:
+            try:
+                out["dict"] = dict_leg(torch, z, args, dev)
+            except Exception as e:
+                out["dict"] = {"error": repr(e)}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
