@@ -207,7 +207,7 @@ struct ZlLitCtl {
     u32 blockIdx, blockSizeMax;
     u32 hufValid, hufLog, nsym;
     u32 litUsed;
-    u32 needHufFill, nStreams;
+    u32 needHufFill, nStreams, sStrict;
     u32 sBeg[4], sEnd[4], sOut[4], sLen[4], sErr[4];
 };
 struct ZlLitSm {
@@ -226,7 +226,7 @@ ZL_HD void zl_lit_begin_frame(ZlLitSm& f, const ZlFrameDesc& d, ZlFrameInfo& inf
     ZlLitCtl& c = f.ctl;
     c.err = 0; c.done = 0; c.pos = 0; c.srcSize = d.srcSize; c.blockIdx = 0;
     c.hufValid = 0; c.hufLog = 0; c.litUsed = 0; c.blockSizeMax = ZL_BLOCKSIZE_MAX;
-    c.needHufFill = 0; c.nStreams = 0;
+    c.needHufFill = 0; c.nStreams = 0; c.sStrict = 1;
     info.err = 0; info.nblocks = 0; info.contentSize = ~0ull; info.totalOut = 0;
     info.checksumFlag = 0; info.checksum = 0; info.dictID = 0; info.blockSizeMax = ZL_BLOCKSIZE_MAX; info.pad = 0;
     const u8* ip = d.src;
@@ -385,7 +385,8 @@ __device__ __forceinline__ u32 zl_selp(u32 a, u32 b, bool c)          // c ? a :
 __device__ __forceinline__ u32 zl_opaque(u32 x) { asm volatile("" : "+r"(x)); return x; }   // stops rematerialisation in loops
 #endif
 
-// one Huffman stream per lane: zstd.c:38626-38650.  Returns 0 when the stream ends exactly.
+// one Huffman stream per lane: zstd.c:38626-38650.  Returns 0 when the stream ends exactly, 2 when bits are left over,
+// 1 when the reader ran past the start (or the end mark is missing).
 ZL_HD u32 zl_huf_stream(const u16* huf, u32 tlog, const u32* wbase, u32 bias, u32 beg, u32 end, u8* out, u32 n)
 {
     ZlBitR b;
@@ -428,7 +429,8 @@ ZL_HD u32 zl_huf_stream(const u16* huf, u32 tlog, const u32* wbase, u32 bias, u3
 #endif
     while (i < n) { u32 s; zl_br_refill(b, wbase); ZL_HUF_SYM(s); out[i++] = (u8)s; }
 #undef ZL_HUF_SYM
-    return zl_br_remaining(b, bias, beg) == 0 ? 0u : 1u;
+    const i32 rem = zl_br_remaining(b, bias, beg);
+    return rem == 0 ? 0u : (rem > 0 ? 2u : 1u);
 }
 
 // block header + literals section header (lane 0).  Writes the literal part of the block's ZlBlockHdr.
@@ -437,7 +439,11 @@ ZL_HD void zl_lit_block_head(ZlLitSm& f, const ZlFrameDesc& d, ZlFrameInfo& info
 {
     ZlLitCtl& c = f.ctl;
     if (c.done) return;
-    for (u32 k = 0; k < c.nStreams; k++) if (c.sErr[k]) c.err = ZL_E_corruption_detected;     // streams of the previous block
+    // streams of the previous block.  libzstd's 4-stream decoder only insists on exact consumption when it cannot take its
+    // "fast" path, i.e. when a stream is shorter than 8 bytes (HUF_DecompressFastArgs_init, zstd.c:38772-38850; the
+    // fast path checks the regenerated sizes only); the single-stream decoder always does (zstd.c:38647).  Same here, so
+    // that a damaged frame without checksum decodes to the same bytes as with the reference.
+    for (u32 k = 0; k < c.nStreams; k++) if (c.sErr[k] == 1 || (c.sErr[k] == 2 && c.sStrict)) c.err = ZL_E_corruption_detected;
     c.needHufFill = 0; c.nStreams = 0;
     if (c.err) { zl_lit_finish_frame(f, d, info); return; }
     if (c.blockIdx > 0 && (hdrs[c.blockIdx - 1].flags & 4)) { zl_lit_finish_frame(f, d, info); return; }   // previous block was the last
@@ -489,7 +495,7 @@ ZL_HD void zl_lit_block_head(ZlLitSm& f, const ZlFrameDesc& d, ZlFrameInfo& info
                         if (!c.err) {
                             litMode = 2; h.litOff = c.litUsed; c.litUsed += litSize;
                             if (single) {
-                                c.nStreams = 1; c.sBeg[0] = hs; c.sEnd[0] = hs + hsz; c.sOut[0] = h.litOff; c.sLen[0] = litSize;
+                                c.nStreams = 1; c.sBeg[0] = hs; c.sEnd[0] = hs + hsz; c.sOut[0] = h.litOff; c.sLen[0] = litSize; c.sStrict = 1;
                             } else if (hsz < 10) c.err = ZL_E_corruption_detected;          // zstd.c:38659
                             else {
                                 u32 l1 = zl_rd16(src + hs), l2 = zl_rd16(src + hs + 2), l3 = zl_rd16(src + hs + 4);
@@ -503,6 +509,7 @@ ZL_HD void zl_lit_block_head(ZlLitSm& f, const ZlFrameDesc& d, ZlFrameInfo& info
                                     c.sBeg[3] = c.sEnd[2]; c.sEnd[3] = hs + hsz;
                                     for (u32 k = 0; k < 4; k++) { c.sOut[k] = h.litOff + k * seg; c.sLen[k] = seg; }
                                     c.sLen[3] = litSize - 3 * seg;
+                                    c.sStrict = (l1 < 8 || l2 < 8 || l3 < 8 || c.sEnd[3] - c.sBeg[3] < 8) ? 1u : 0u;
                                 }
                             }
                             h.seqOff = c.pos + lhSize + litCSize;
