@@ -18,38 +18,42 @@ extern "C" size_t zl_emul_decompress_frame(void* dstv, size_t cap, const void* s
     memcpy(src, srcv, size);
     ZlFrameDesc d; memset(&d, 0, sizeof(d));
     d.src = src; d.dst = (u8*)dstv; d.srcSize = (u32)size; d.dstCap = (u32)cap;
-    zl_plan_frame(d.srcSize, d.dstCap, &d.litCap, &d.recCap, &d.hdrCap, &d.ckCap);
+    zl_plan_frame(d.srcSize, d.dstCap, true, &d.litCap, &d.recCap, &d.hdrCap, &d.ckCap);
     std::vector<u8> lits(d.litCap + 16);
     std::vector<u64> recs(d.recCap);
     std::vector<ZlBlockHdr> hdrs(d.hdrCap);
+    std::vector<ZlUnit> units(d.hdrCap);
+    u32 nunits = 0;
     ZlFrameInfo info;
     const u32 bias = (u32)(((size_t)d.src) & 3);
     const u32* wbase = (const u32*)(d.src - bias);
-    {   // K1a
-        static ZlLitSm f;
-        zl_lit_begin_frame(f, d, info, 0);
-        for (;;) {
-            zl_lit_block_head(f, d, info, hdrs.data(), wbase, bias);
-            if (f.ctl.done) break;
-            if (f.ctl.needHufFill) for (u32 q = 0; q < 4; q++) zl_huf_fill(f, q);
-            for (u32 q = 0; q < f.ctl.nStreams; q++)
-                f.ctl.sErr[q] = zl_huf_stream(f.huf, f.ctl.hufLog, wbase, bias, f.ctl.sBeg[q], f.ctl.sEnd[q],
-                                              lits.data() + f.ctl.sOut[q], f.ctl.sLen[q]);
+    zl_index_frame(d, info, hdrs.data(), 0, 0, 0, units.data(), &nunits, d.hdrCap);          // K0
+    // K1a / K1b: every unit on its own, in an arbitrary order (here: last block first) -- blocks are independent
+    for (u32 ui = nunits; !info.err && ui-- > 0;) {
+        const u32 blk = units[ui].block;
+        if (((hdrs[blk].flags >> 4) & 3) == 2) {   // K1a
+            static ZlLitSm f;
+            u32 useDict = 0;
+            zl_lit_unit_head(f, d, hdrs.data(), blk, wbase, bias, &useDict);
+            if (useDict) f.ctl.err = ZL_E_dictionary_corrupted;
+            if (!f.ctl.err) {
+                if (f.ctl.needHufFill) for (u32 q = 0; q < 4; q++) zl_huf_fill(f, q);
+                for (u32 q = 0; q < f.ctl.nStreams; q++)
+                    f.ctl.sErr[q] = zl_huf_stream(f.huf, f.ctl.hufLog, wbase, bias, f.ctl.sBeg[q], f.ctl.sEnd[q],
+                                                  lits.data() + f.ctl.sOut[q], f.ctl.sLen[q]);
+            }
+            const u32 e = zl_lit_unit_finish(f);
+            if (e) info.err = e;
         }
-    }
-    {   // K1b
-        static ZlSeqSm f;
-        static i16 norm[3 * ZL_NORM_STRIDE];
-        zl_seq_begin_frame(f, info);
-        for (u32 b = 0; b < info.nblocks; b++) {
-            ZlBlockHdr h = hdrs[b];
-            if ((h.flags & 3) != 2) continue;
-            zl_seq_head(f, d, h, g_ct, norm);
+        if (!info.err && hdrs[blk].nbSeq) {        // K1b
+            static ZlSeqSm f;
+            static i16 norm[3 * ZL_NORM_STRIDE];
+            zl_seq_head(f, d, hdrs.data(), blk, g_ct, norm);
+            if (!f.ctl.err && f.ctl.useDict) f.ctl.err = ZL_E_corruption_detected;
             if (!f.ctl.err && f.ctl.needBuild) for (u32 q = 0; q < 3; q++) zl_seq_fse_build(f, q, norm);
-            zl_seq_decode(f, d, h, recs.data(), wbase, bias, g_ct, nullptr);
-            hdrs[b] = h;
+            hdrs[blk].nrec = zl_seq_decode(f, recs.data() + hdrs[blk].recOff, wbase, bias, g_ct, nullptr);
+            if (f.ctl.err) info.err = f.ctl.err;
         }
-        zl_seq_finish_frame(f, info);
     }
     if (info.err) return (size_t)0 - (size_t)info.err;
     // K2 restated serially: records -> (ll, ml, offBase), repeat-offset history, the checks of ZSTD_execSequence, the copies

@@ -185,7 +185,7 @@ struct ZSTD_DCtx_s {
     // streaming session (ZSTD_decompressStream): input accumulated on the host until a whole frame is present
     std::vector<u8> sIn, sOut;
     size_t sOutPos = 0;
-    ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dNorm, dSrc, dDst;
+    ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dNorm, dUnits, dCounters, dSrc, dDst;
     ZlPinBuf hDescs, hResults;
 };
 
@@ -203,7 +203,7 @@ ZL_EXPORT ZSTD_DCtx* ZSTD_createDCtx(void) { return new (std::nothrow) ZSTD_DCtx
 ZL_EXPORT size_t ZSTD_freeDCtx(ZSTD_DCtx* c)
 {
     if (!c) return 0;
-    ZlDevBuf* bufs[] = {&c->dDictContent, &c->dDict, &c->dDescs, &c->dInfos, &c->dResults, &c->dHdr, &c->dRec, &c->dCk, &c->dLit, &c->dNorm, &c->dSrc, &c->dDst};
+    ZlDevBuf* bufs[] = {&c->dDictContent, &c->dDict, &c->dDescs, &c->dInfos, &c->dResults, &c->dHdr, &c->dRec, &c->dCk, &c->dLit, &c->dNorm, &c->dUnits, &c->dCounters, &c->dSrc, &c->dDst};
     for (ZlDevBuf* b : bufs) b->release();
     c->hDescs.release(); c->hResults.release();
     if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
@@ -344,8 +344,24 @@ static bool zl_dctx_lanes(ZSTD_DCtx* c)
     return true;
 }
 
+static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, const size_t* srcSize, void* const* dst,
+                                       const size_t* dstCap, size_t* result, size_t n, int dev, bool worst);
 ZL_EXPORT size_t zl_decompress_batch(ZSTD_DCtx* c, const void* const* src, const size_t* srcSize, void* const* dst,
                                      const size_t* dstCap, size_t* result, size_t n, int dev)
+{
+    size_t r = zl_decompress_batch_impl(c, src, srcSize, dst, dstCap, result, n, dev, false);
+    if (zl_is_error(r)) return r;
+    bool retry = false;
+    for (size_t i = 0; i < n; i++) if (result[i] == (size_t)0 - (size_t)ZL_E_INTERNAL_hdrCap) { retry = true; break; }
+    if (retry) {                          // a frame with very many small blocks: run again with worst-case block arenas
+        r = zl_decompress_batch_impl(c, src, srcSize, dst, dstCap, result, n, dev, true);
+        if (zl_is_error(r)) return r;
+        for (size_t i = 0; i < n; i++) if (result[i] == (size_t)0 - (size_t)ZL_E_INTERNAL_hdrCap) result[i] = ZL_ERROR(GENERIC);
+    }
+    return 0;
+}
+static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, const size_t* srcSize, void* const* dst,
+                                       const size_t* dstCap, size_t* result, size_t n, int dev, bool worst)
 {
     if (!c) return ZL_ERROR(GENERIC);
     if (n == 0) return 0;
@@ -403,13 +419,14 @@ ZL_EXPORT size_t zl_decompress_batch(ZSTD_DCtx* c, const void* const* src, const
             d.dst = c->dDst.as<u8>() + druns[dr].devOff + ((const u8*)dst[i] - druns[dr].hbase);
         }
         d.srcSize = (u32)srcSize[i]; d.dstCap = (u32)dstCap[i];
-        zl_plan_frame(d.srcSize, d.dstCap, &d.litCap, &d.recCap, &d.hdrCap, &d.ckCap);
+        zl_plan_frame(d.srcSize, d.dstCap, worst, &d.litCap, &d.recCap, &d.hdrCap, &d.ckCap);
         d.litBase = lit; d.recBase = rec; d.hdrBase = hdr; d.ckBase = ck;
         lit += ((u64)d.litCap + 15) & ~15ull; rec += d.recCap; hdr += d.hdrCap; ck += d.ckCap;
     }
     if (!c->dDescs.reserve(n * sizeof(ZlFrameDesc)) || !c->dInfos.reserve(n * sizeof(ZlFrameInfo)) || !c->dResults.reserve(n * 8) ||
-        !c->dLit.reserve(lit + 64) || !c->dRec.reserve(rec * 8) || !c->dNorm.reserve(n * 3 * ZL_NORM_STRIDE * sizeof(i16)) ||
-        !c->dHdr.reserve(hdr * sizeof(ZlBlockHdr)))
+        !c->dLit.reserve(lit + 64) || !c->dRec.reserve(rec * 8) ||
+        !c->dNorm.reserve(nslices * (size_t)ZL_NORM_SLOTS * 3 * ZL_NORM_STRIDE * sizeof(i16)) ||
+        !c->dHdr.reserve(hdr * sizeof(ZlBlockHdr)) || !c->dUnits.reserve(hdr * sizeof(ZlUnit)) || !c->dCounters.reserve(nslices * 16))
         return ZL_ERROR(memory_allocation);
     cudaMemcpyAsync(c->dDescs.p, hd, n * sizeof(ZlFrameDesc), cudaMemcpyHostToDevice, st);
     if (!c->stageEv[0]) for (cudaEvent_t& e : c->stageEv) cudaEventCreate(&e);
@@ -426,7 +443,12 @@ ZL_EXPORT size_t zl_decompress_batch(ZSTD_DCtx* c, const void* const* src, const
             if (sruns[r].bytes) cudaMemcpyAsync(c->dSrc.as<u8>() + sruns[r].devOff, sruns[r].hbase, sruns[r].bytes, cudaMemcpyHostToDevice, ls);
         ZlDecodeLaunch L;
         L.descs = c->dDescs.as<ZlFrameDesc>() + a; L.infos = c->dInfos.as<ZlFrameInfo>() + a; L.hdrArena = c->dHdr.as<ZlBlockHdr>();
-        L.recArena = c->dRec.as<u64>(); L.litArena = c->dLit.as<u8>(); L.normArena = c->dNorm.as<i16>() + a * 3 * ZL_NORM_STRIDE;
+        L.descsAll = c->dDescs.as<ZlFrameDesc>(); L.infosAll = c->dInfos.as<ZlFrameInfo>(); L.frameBase = (u32)a;
+        L.recArena = c->dRec.as<u64>(); L.litArena = c->dLit.as<u8>();
+        L.normArena = c->dNorm.as<i16>() + k * (size_t)ZL_NORM_SLOTS * 3 * ZL_NORM_STRIDE; L.normSlots = ZL_NORM_SLOTS;
+        {   const u64 u0 = hd[a].hdrBase, u1 = cut[k + 1] < n ? hd[cut[k + 1]].hdrBase : hdr;      // the slice's share of the unit arena
+            L.units = c->dUnits.as<ZlUnit>() + u0; L.unitCap = (u32)((u1 - u0) > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : (u1 - u0)); }
+        L.counters = c->dCounters.as<u32>() + 4 * k;
         L.results = c->dResults.as<u64>() + a;
         L.nframes = (u32)cnt; L.verifyChecksum = verify; L.dict = c->hasDict ? c->dDict.as<ZlDictDev>() : nullptr;
         L.stageEv = nslices > 1 ? nullptr : c->stageEv;

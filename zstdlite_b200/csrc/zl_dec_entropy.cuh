@@ -200,13 +200,193 @@ ZL_HD bool zl_fse_build(u16* tbl, const i16* norm, u32 maxSym, u32 log)
     return true;
 }
 
+// =================================================================================================== K0: frame / block index
+// One thread per frame (zl_k_index): frame header (zstd.c:41050-41152), then every block header (43075) and -- for
+// compressed blocks -- the literals section header (43146-43347) and the first bytes of the sequences section (nbSeq and
+// the modes byte, 43707-43745).  That is enough to give every block its own slice of the literal and record arenas and
+// to name, for every entropy table a block uses, the block that carries its description, so that K1a / K1b can decode
+// all blocks of all frames independently of each other (a large frame no longer is one long serial chain).
+// Compressed blocks are appended to a global unit list (one atomic per block); raw / RLE blocks need no entropy work.
+// records reserved per block beyond nbSeq: a block regenerates <= 128 KiB, so a valid one splits at most two lengths (>= 65536);
+// the generic step checks the exact capacity, the fast loop stops 4 short of it
+#define ZL_REC_SLACK 8u
+ZL_HD u32 zl_unit_append(u32* unitCount)
+{
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(unitCount, 1u);
+#else
+    return (*unitCount)++;
+#endif
+}
+ZL_HD void zl_index_frame(const ZlFrameDesc& d, ZlFrameInfo& info, ZlBlockHdr* hdrs, u32 frameIdx, u32 dictID, u32 dictHasEntropy,
+                          ZlUnit* units, u32* unitCount, u32 unitCap)
+{
+    u32 err = 0;
+    info.err = 0; info.nblocks = 0; info.contentSize = ~0ull; info.totalOut = 0;
+    info.checksumFlag = 0; info.checksum = 0; info.dictID = 0; info.blockSizeMax = ZL_BLOCKSIZE_MAX; info.pad = 0;
+    const u8* ip = d.src;
+    const u32 srcSize = d.srcSize;
+    u32 pos = 0, blockSizeMax = ZL_BLOCKSIZE_MAX, nblocks = 0;
+    do {
+        if (srcSize < 5) { err = ZL_E_srcSize_wrong; break; }
+        if (zl_rd32(ip) != ZL_MAGIC) { err = ZL_E_prefix_unknown; break; }
+        const u32 fhd = ip[4];
+        const u32 didCode = fhd & 3, single = (fhd >> 5) & 1, fcsID = fhd >> 6;
+        const u32 didSz = didCode == 3 ? 4 : didCode, fcsSz = fcsID == 0 ? (single ? 1u : 0u) : (1u << fcsID);
+        const u32 hs = 5 + (single ? 0 : 1) + didSz + fcsSz;
+        if (srcSize < hs) { err = ZL_E_srcSize_wrong; break; }
+        if (fhd & 8) { err = ZL_E_frameParameter_unsupported; break; }
+        u32 p = 5;
+        u64 window = 0;
+        if (!single) {
+            const u32 wl = ip[p++];
+            const u32 wlog = (wl >> 3) + 10;
+            if (wlog > 31) { err = ZL_E_frameParameter_windowTooLarge; break; }
+            window = 1ull << wlog;
+            window += (window >> 3) * (wl & 7);
+        }
+        u32 did = 0;
+        if (didSz == 1) did = ip[p]; else if (didSz == 2) did = zl_rd16(ip + p); else if (didSz == 4) did = zl_rd32(ip + p);
+        p += didSz;
+        u64 fcs = ~0ull;
+        if (fcsID == 0) { if (single) fcs = ip[p]; }
+        else if (fcsID == 1) fcs = zl_rd16(ip + p) + 256;
+        else if (fcsID == 2) fcs = zl_rd32(ip + p);
+        else fcs = zl_rd64(ip + p);
+        if (single) window = fcs;
+        if (did != 0 && did != dictID) { err = ZL_E_dictionary_wrong; break; }      // zstd.c:41318
+        blockSizeMax = window < ZL_BLOCKSIZE_MAX ? (u32)window : ZL_BLOCKSIZE_MAX;
+        pos = hs;
+        info.contentSize = fcs; info.checksumFlag = (fhd >> 2) & 1; info.dictID = did; info.blockSizeMax = blockSizeMax;
+    } while (0);
+    // ---- block walk
+    u32 litUsed = 0, recUsed = 0;
+    u64 seqTotal = 0;
+    u32 hufDef = ZL_DEF_NONE, seqDef[3] = {ZL_DEF_NONE, ZL_DEF_NONE, ZL_DEF_NONE};
+    bool hufValid = dictHasEntropy != 0, seqValid = dictHasEntropy != 0, lastSeen = false;
+    const u8* src = d.src;
+    while (!err && !lastSeen) {
+        if (pos + 3 > srcSize) { err = ZL_E_srcSize_wrong; break; }
+        const u32 bh = zl_rd24(src + pos);
+        const u32 last = bh & 1, type = (bh >> 1) & 3, csize = bh >> 3;
+        pos += 3;
+        if (nblocks >= d.hdrCap) { err = ZL_E_INTERNAL_hdrCap; break; }
+        ZlBlockHdr h;
+        h.flags = last ? 4u : 0u; h.regenSize = 0; h.srcOff = 0; h.litOff = 0; h.litSize = 0; h.nrec = 0; h.recOff = 0;
+        h.seqOff = 0; h.seqEnd = 0; h.litSecOff = 0; h.hufDef = ZL_DEF_NONE; h.seqDef[0] = h.seqDef[1] = h.seqDef[2] = ZL_DEF_NONE;
+        h.nbSeq = 0; h.pad = 0;
+        if (type == 3) err = ZL_E_corruption_detected;
+        else if (type == 1) {                                                    // RLE block, zstd.c:41510
+            if (pos + 1 > srcSize) err = ZL_E_srcSize_wrong;
+            else { h.flags |= 1u | ((u32)src[pos] << 8); h.regenSize = csize; pos += 1; }
+        } else if (type == 0) {                                                  // raw block, zstd.c:41497
+            if (csize > srcSize - pos) err = ZL_E_srcSize_wrong;
+            else { h.regenSize = csize; h.srcOff = pos; pos += csize; }
+        } else {
+            if (csize > srcSize - pos) err = ZL_E_srcSize_wrong;
+            else if (csize > blockSizeMax) err = ZL_E_srcSize_wrong;             // zstd.c:45099
+            else if (csize < 2) err = ZL_E_corruption_detected;                  // MIN_CBLOCK_SIZE, zstd.c:43150
+            else {
+                const u32 blockEnd = pos + csize;
+                const u8* bp = src + pos;
+                const u32 ltype = bp[0] & 3, fmt = (bp[0] >> 2) & 3;
+                u32 lhSize = 0, litSize = 0, litCSize = 0, litMode = 0, seqOff = 0;
+                h.litSecOff = pos;
+                if (ltype >= 2) {
+                    u32 single = 0;
+                    if (ltype == 3 && !hufValid) err = ZL_E_dictionary_corrupted;      // zstd.c:43160
+                    else if (csize < 5) err = ZL_E_corruption_detected;
+                    else {
+                        const u32 lhc = zl_rd32(bp);
+                        if (fmt < 2) { single = !fmt; lhSize = 3; litSize = (lhc >> 4) & 0x3FF; litCSize = (lhc >> 14) & 0x3FF; }
+                        else if (fmt == 2) { lhSize = 4; litSize = (lhc >> 4) & 0x3FFF; litCSize = lhc >> 18; }
+                        else { lhSize = 5; litSize = (lhc >> 4) & 0x3FFFF; litCSize = (lhc >> 22) + ((u32)bp[4] << 10); }
+                        if (litSize > blockSizeMax) err = ZL_E_corruption_detected;
+                        else if (!single && litSize < 6) err = ZL_E_literals_headerWrong;
+                        else if (litCSize + lhSize > csize) err = ZL_E_corruption_detected;
+                        else if (litSize == 0 || litCSize == 0) err = ZL_E_corruption_detected;
+                        else if (litUsed + litSize > d.litCap) err = ZL_E_dstSize_tooSmall;   // more literals than dst can hold
+                        else {
+                            litMode = 2; h.litOff = litUsed; litUsed += litSize;
+                            if (ltype == 2) hufDef = nblocks;
+                            h.hufDef = hufDef; hufValid = true;
+                            seqOff = pos + lhSize + litCSize;
+                        }
+                    }
+                } else {
+                    bool ok = true;
+                    if (fmt == 0 || fmt == 2) { lhSize = 1; litSize = bp[0] >> 3; }
+                    else if (fmt == 1) { lhSize = 2; litSize = zl_rd16(bp) >> 4; }
+                    else { lhSize = 3; if (csize < 3) { ok = false; litSize = 0; } else litSize = zl_rd24(bp) >> 4; }
+                    if (!ok) err = ZL_E_corruption_detected;
+                    else if (litSize > blockSizeMax) err = ZL_E_corruption_detected;
+                    else if (ltype == 0) {
+                        if (lhSize + litSize > csize) err = ZL_E_corruption_detected;
+                        else { litMode = 0; h.srcOff = pos + lhSize; seqOff = pos + lhSize + litSize; }
+                    } else {
+                        if (lhSize + 1 > csize) err = ZL_E_corruption_detected;
+                        else { litMode = 1; h.flags |= (u32)bp[lhSize] << 8; seqOff = pos + lhSize + 1; }
+                    }
+                }
+                if (!err) {       // sequences section: nbSeq and the modes byte (zstd.c:43720-43745)
+                    u32 q = seqOff, nbSeq = 0;
+                    if (q >= blockEnd) err = ZL_E_srcSize_wrong;
+                    else {
+                        nbSeq = src[q++];
+                        if (nbSeq > 0x7F) {
+                            if (nbSeq == 0xFF) { if (q + 2 > blockEnd) err = ZL_E_srcSize_wrong; else { nbSeq = zl_rd16(src + q) + 0x7F00; q += 2; } }
+                            else { if (q >= blockEnd) err = ZL_E_srcSize_wrong; else nbSeq = ((nbSeq - 0x80) << 8) + src[q++]; }
+                        }
+                    }
+                    if (!err && nbSeq) {
+                        if (q + 1 > blockEnd) err = ZL_E_srcSize_wrong;
+                        else {
+                            const u32 modes = src[q];
+                            if (modes & 3) err = ZL_E_corruption_detected;
+                            for (u32 t = 0; t < 3 && !err; t++) {
+                                const u32 mode = (modes >> (6 - 2 * t)) & 3;
+                                if (mode != 3) seqDef[t] = nblocks;
+                                else if (seqDef[t] == ZL_DEF_NONE && !seqValid) err = ZL_E_corruption_detected;   // zstd.c:43682
+                                h.seqDef[t] = seqDef[t];
+                            }
+                        }
+                        if (!err) {
+                            seqTotal += nbSeq;
+                            if (seqTotal > (u64)d.dstCap / 3 + 8) err = ZL_E_corruption_detected;          // more sequences than dst could hold
+                            else if ((u64)recUsed + nbSeq + ZL_REC_SLACK > d.recCap) err = ZL_E_INTERNAL_hdrCap;   // many blocks: retry with the worst-case arena
+                        }
+                    }
+                    if (!err) { h.nbSeq = nbSeq; h.recOff = recUsed; if (nbSeq) recUsed += nbSeq + ZL_REC_SLACK; }
+                }
+                h.flags |= 2u | (litMode << 4);
+                h.litSize = litSize; h.seqOff = seqOff; h.seqEnd = blockEnd;
+                pos = blockEnd;
+            }
+        }
+        if (err) break;
+        hdrs[nblocks] = h;
+        if ((h.flags & 3) == 2 && (((h.flags >> 4) & 3) == 2 || h.nbSeq)) {      // entropy work to do
+            const u32 u = zl_unit_append(unitCount);
+            if (u < unitCap) { units[u].frame = frameIdx; units[u].block = nblocks; } else err = ZL_E_INTERNAL_hdrCap;
+        }
+        nblocks++;
+        lastSeen = last != 0;
+    }
+    if (!err) {
+        if (info.checksumFlag) {
+            if (pos + 4 > srcSize) err = ZL_E_checksum_wrong;                                              // zstd.c:41651
+            else { info.checksum = zl_rd32(src + pos); pos += 4; }
+        }
+        if (!err && pos != srcSize) err = ZL_E_srcSize_wrong;       // one frame per batch item
+    }
+    info.err = err; info.nblocks = nblocks;
+}
+
 // =================================================================================================== K1a: literals
+// Work unit: one compressed block whose literals are Huffman-coded (quad per unit, 8 units per warp).
 struct ZlLitCtl {
-    u32 err, done;
-    u32 pos, srcSize;
-    u32 blockIdx, blockSizeMax;
-    u32 hufValid, hufLog, nsym;
-    u32 litUsed;
+    u32 err;
+    u32 hufLog, nsym;
     u32 needHufFill, nStreams, sStrict;
     u32 sBeg[4], sEnd[4], sOut[4], sLen[4], sErr[4];
 };
@@ -219,62 +399,6 @@ struct ZlLitSm {
     } u;
     ZlLitCtl ctl;
 };
-
-// frame header (lane 0): zstd.c:41050-41152
-ZL_HD void zl_lit_begin_frame(ZlLitSm& f, const ZlFrameDesc& d, ZlFrameInfo& info, u32 dictID)
-{
-    ZlLitCtl& c = f.ctl;
-    c.err = 0; c.done = 0; c.pos = 0; c.srcSize = d.srcSize; c.blockIdx = 0;
-    c.hufValid = 0; c.hufLog = 0; c.litUsed = 0; c.blockSizeMax = ZL_BLOCKSIZE_MAX;
-    c.needHufFill = 0; c.nStreams = 0; c.sStrict = 1;
-    info.err = 0; info.nblocks = 0; info.contentSize = ~0ull; info.totalOut = 0;
-    info.checksumFlag = 0; info.checksum = 0; info.dictID = 0; info.blockSizeMax = ZL_BLOCKSIZE_MAX; info.pad = 0;
-    const u8* ip = d.src;
-    if (d.srcSize < 5) { c.err = ZL_E_srcSize_wrong; return; }
-    if (zl_rd32(ip) != ZL_MAGIC) { c.err = ZL_E_prefix_unknown; return; }
-    u32 fhd = ip[4];
-    u32 didCode = fhd & 3, single = (fhd >> 5) & 1, fcsID = fhd >> 6;
-    u32 didSz = didCode == 3 ? 4 : didCode, fcsSz = fcsID == 0 ? (single ? 1u : 0u) : (1u << fcsID);
-    u32 hs = 5 + (single ? 0 : 1) + didSz + fcsSz;
-    if (d.srcSize < hs) { c.err = ZL_E_srcSize_wrong; return; }
-    if (fhd & 8) { c.err = ZL_E_frameParameter_unsupported; return; }
-    u32 p = 5;
-    u64 window = 0;
-    if (!single) {
-        u32 wl = ip[p++];
-        u32 wlog = (wl >> 3) + 10;
-        if (wlog > 31) { c.err = ZL_E_frameParameter_windowTooLarge; return; }
-        window = 1ull << wlog;
-        window += (window >> 3) * (wl & 7);
-    }
-    u32 did = 0;
-    if (didSz == 1) did = ip[p]; else if (didSz == 2) did = zl_rd16(ip + p); else if (didSz == 4) did = zl_rd32(ip + p);
-    p += didSz;
-    u64 fcs = ~0ull;
-    if (fcsID == 0) { if (single) fcs = ip[p]; }
-    else if (fcsID == 1) fcs = zl_rd16(ip + p) + 256;
-    else if (fcsID == 2) fcs = zl_rd32(ip + p);
-    else fcs = zl_rd64(ip + p);
-    if (single) window = fcs;
-    if (did != 0 && did != dictID) { c.err = ZL_E_dictionary_wrong; return; }     // zstd.c:41318
-    c.blockSizeMax = window < ZL_BLOCKSIZE_MAX ? (u32)window : ZL_BLOCKSIZE_MAX;
-    c.pos = hs;
-    info.contentSize = fcs; info.checksumFlag = (fhd >> 2) & 1; info.dictID = did; info.blockSizeMax = c.blockSizeMax;
-}
-
-ZL_HD void zl_lit_finish_frame(ZlLitSm& f, const ZlFrameDesc& d, ZlFrameInfo& info)
-{
-    ZlLitCtl& c = f.ctl;
-    c.done = 1;
-    if (!c.err) {
-        if (info.checksumFlag) {
-            if (c.pos + 4 > c.srcSize) c.err = ZL_E_checksum_wrong;                                          // zstd.c:41651
-            else { info.checksum = zl_rd32(d.src + c.pos); c.pos += 4; }
-        }
-        if (!c.err && c.pos != c.srcSize) c.err = ZL_E_srcSize_wrong;       // one frame per batch item
-    }
-    info.err = c.err; info.nblocks = c.blockIdx;
-}
 
 // Huffman tree description (lane 0): zstd.c:3470-3540, weights via FSE 3875/3790.
 // Fills f.weights / f.u.symStart, ctl.hufLog, ctl.nsym.  Returns bytes consumed or 0 on error.
@@ -433,176 +557,155 @@ ZL_HD u32 zl_huf_stream(const u16* huf, u32 tlog, const u32* wbase, u32 bias, u3
     return rem == 0 ? 0u : (rem > 0 ? 2u : 1u);
 }
 
-// block header + literals section header (lane 0).  Writes the literal part of the block's ZlBlockHdr.
-ZL_HD void zl_lit_block_head(ZlLitSm& f, const ZlFrameDesc& d, ZlFrameInfo& info, ZlBlockHdr* hdrs,
-                             const u32* wbase, u32 bias)
+// Literals of one block (lane 0): re-reads the section header K0 validated, loads the Huffman tree description from the
+// block that carries it (this one, or an earlier one for "treeless" literals) and lays out the streams.
+// useDictHuf is set when the tree is the dictionary's (the caller copies that table instead of filling one).
+ZL_HD void zl_lit_unit_head(ZlLitSm& f, const ZlFrameDesc& d, const ZlBlockHdr* hdrs, u32 blk, const u32* wbase, u32 bias,
+                            u32* useDictHuf)
 {
     ZlLitCtl& c = f.ctl;
-    if (c.done) return;
-    // streams of the previous block.  libzstd's 4-stream decoder only insists on exact consumption when it cannot take its
-    // "fast" path, i.e. when a stream is shorter than 8 bytes (HUF_DecompressFastArgs_init, zstd.c:38772-38850; the
-    // fast path checks the regenerated sizes only); the single-stream decoder always does (zstd.c:38647).  Same here, so
-    // that a damaged frame without checksum decodes to the same bytes as with the reference.
-    for (u32 k = 0; k < c.nStreams; k++) if (c.sErr[k] == 1 || (c.sErr[k] == 2 && c.sStrict)) c.err = ZL_E_corruption_detected;
-    c.needHufFill = 0; c.nStreams = 0;
-    if (c.err) { zl_lit_finish_frame(f, d, info); return; }
-    if (c.blockIdx > 0 && (hdrs[c.blockIdx - 1].flags & 4)) { zl_lit_finish_frame(f, d, info); return; }   // previous block was the last
+    const ZlBlockHdr& h = hdrs[blk];
+    c.err = 0; c.needHufFill = 0; c.nStreams = 0; c.sStrict = 1; *useDictHuf = 0;
+    if (((h.flags >> 4) & 3) != 2) return;                                   // raw / rle literals: nothing to decode
     const u8* src = d.src;
-    if (c.pos + 3 > c.srcSize) { c.err = ZL_E_srcSize_wrong; zl_lit_finish_frame(f, d, info); return; }
-    u32 bh = zl_rd24(src + c.pos);
-    u32 last = bh & 1, type = (bh >> 1) & 3, csize = bh >> 3;
-    c.pos += 3;
-    if (c.blockIdx >= d.hdrCap) { c.err = ZL_E_GENERIC; zl_lit_finish_frame(f, d, info); return; }
-    ZlBlockHdr h;
-    h.flags = last ? 4u : 0u; h.regenSize = 0; h.srcOff = 0; h.litOff = 0; h.litSize = 0; h.nrec = 0; h.recOff = 0;
-    h.seqOff = 0; h.seqEnd = 0; h.pad[0] = h.pad[1] = h.pad[2] = 0;
-    if (type == 3) c.err = ZL_E_corruption_detected;
-    else if (type == 1) {                                                    // RLE block, zstd.c:41510
-        if (c.pos + 1 > c.srcSize) c.err = ZL_E_srcSize_wrong;
-        else { h.flags |= 1u | ((u32)src[c.pos] << 8); h.regenSize = csize; c.pos += 1; }
-    } else if (type == 0) {                                                  // raw block, zstd.c:41497
-        if (csize > c.srcSize - c.pos) c.err = ZL_E_srcSize_wrong;
-        else { h.regenSize = csize; h.srcOff = c.pos; c.pos += csize; }
-    } else {
-        if (csize > c.srcSize - c.pos) c.err = ZL_E_srcSize_wrong;
-        else if (csize > c.blockSizeMax) c.err = ZL_E_srcSize_wrong;         // zstd.c:45099
-        else if (csize < 2) c.err = ZL_E_corruption_detected;                // MIN_CBLOCK_SIZE, zstd.c:43150
+    const u8* bp = src + h.litSecOff;
+    const u32 fmt = (bp[0] >> 2) & 3;
+    const u32 lhc = zl_rd32(bp);
+    u32 single = 0, lhSize, litSize, litCSize;
+    if (fmt < 2) { single = !fmt; lhSize = 3; litSize = (lhc >> 4) & 0x3FF; litCSize = (lhc >> 14) & 0x3FF; }
+    else if (fmt == 2) { lhSize = 4; litSize = (lhc >> 4) & 0x3FFF; litCSize = lhc >> 18; }
+    else { lhSize = 5; litSize = (lhc >> 4) & 0x3FFFF; litCSize = (lhc >> 22) + ((u32)bp[4] << 10); }
+    u32 hs = h.litSecOff + lhSize, hsz = litCSize;
+    // the tree: zstd.c:43190-43260
+    if (h.hufDef == ZL_DEF_NONE) *useDictHuf = 1;
+    else {
+        const ZlBlockHdr& dh = hdrs[h.hufDef];
+        const u8* dp = src + dh.litSecOff;
+        const u32 dfmt = (dp[0] >> 2) & 3;
+        const u32 dlh = dfmt < 2 ? 3u : (dfmt == 2 ? 4u : 5u);
+        const u32 dlhc = zl_rd32(dp);
+        const u32 dcs = dfmt < 2 ? ((dlhc >> 14) & 0x3FFu) : (dfmt == 2 ? (dlhc >> 18) : ((dlhc >> 22) + ((u32)dp[4] << 10)));
+        const u32 th = zl_huf_read_stats(f, dp + dlh, dcs, wbase, bias, dh.litSecOff + dlh);
+        if (!th || th >= dcs) { c.err = ZL_E_corruption_detected; return; }
+        c.needHufFill = 1;
+        if (h.hufDef == blk) { hs += th; hsz -= th; }                        // own tree: the streams follow it
+    }
+    if (single) {
+        c.nStreams = 1; c.sBeg[0] = hs; c.sEnd[0] = hs + hsz; c.sOut[0] = h.litOff; c.sLen[0] = litSize; c.sStrict = 1;
+    } else if (hsz < 10) c.err = ZL_E_corruption_detected;                   // zstd.c:38659
+    else {
+        const u32 l1 = zl_rd16(src + hs), l2 = zl_rd16(src + hs + 2), l3 = zl_rd16(src + hs + 4);
+        const u32 seg = (litSize + 3) / 4;
+        if (6 + l1 + l2 + l3 > hsz || seg * 3 > litSize) c.err = ZL_E_corruption_detected;
         else {
-            const u32 blockEnd = c.pos + csize;
-            const u8* ip = src + c.pos;
-            u32 ltype = ip[0] & 3, fmt = (ip[0] >> 2) & 3, lhSize = 0, litSize = 0, litCSize = 0, litMode = 0;
-            if (ltype >= 2) {
-                u32 single = 0;
-                if (ltype == 3 && !c.hufValid) c.err = ZL_E_dictionary_corrupted;      // zstd.c:43160
-                else if (csize < 5) c.err = ZL_E_corruption_detected;
-                else {
-                    u32 lhc = zl_rd32(ip);
-                    if (fmt < 2) { single = !fmt; lhSize = 3; litSize = (lhc >> 4) & 0x3FF; litCSize = (lhc >> 14) & 0x3FF; }
-                    else if (fmt == 2) { lhSize = 4; litSize = (lhc >> 4) & 0x3FFF; litCSize = lhc >> 18; }
-                    else { lhSize = 5; litSize = (lhc >> 4) & 0x3FFFF; litCSize = (lhc >> 22) + ((u32)ip[4] << 10); }
-                    if (litSize > c.blockSizeMax) c.err = ZL_E_corruption_detected;
-                    else if (!single && litSize < 6) c.err = ZL_E_literals_headerWrong;
-                    else if (litCSize + lhSize > csize) c.err = ZL_E_corruption_detected;
-                    else if (litSize == 0 || litCSize == 0) c.err = ZL_E_corruption_detected;
-                    else if (c.litUsed + litSize > d.litCap) c.err = ZL_E_dstSize_tooSmall;   // more literals than dst can hold
-                    else {
-                        u32 hs = c.pos + lhSize, hsz = litCSize;
-                        if (ltype == 2) {
-                            u32 th = zl_huf_read_stats(f, src + hs, hsz, wbase, bias, hs);
-                            if (!th || th >= hsz) c.err = ZL_E_corruption_detected;
-                            else { hs += th; hsz -= th; c.needHufFill = 1; c.hufValid = 1; }
-                        }
-                        if (!c.err) {
-                            litMode = 2; h.litOff = c.litUsed; c.litUsed += litSize;
-                            if (single) {
-                                c.nStreams = 1; c.sBeg[0] = hs; c.sEnd[0] = hs + hsz; c.sOut[0] = h.litOff; c.sLen[0] = litSize; c.sStrict = 1;
-                            } else if (hsz < 10) c.err = ZL_E_corruption_detected;          // zstd.c:38659
-                            else {
-                                u32 l1 = zl_rd16(src + hs), l2 = zl_rd16(src + hs + 2), l3 = zl_rd16(src + hs + 4);
-                                u32 seg = (litSize + 3) / 4;
-                                if (6 + l1 + l2 + l3 > hsz || seg * 3 > litSize) c.err = ZL_E_corruption_detected;
-                                else {
-                                    c.nStreams = 4;
-                                    c.sBeg[0] = hs + 6; c.sEnd[0] = c.sBeg[0] + l1;
-                                    c.sBeg[1] = c.sEnd[0]; c.sEnd[1] = c.sBeg[1] + l2;
-                                    c.sBeg[2] = c.sEnd[1]; c.sEnd[2] = c.sBeg[2] + l3;
-                                    c.sBeg[3] = c.sEnd[2]; c.sEnd[3] = hs + hsz;
-                                    for (u32 k = 0; k < 4; k++) { c.sOut[k] = h.litOff + k * seg; c.sLen[k] = seg; }
-                                    c.sLen[3] = litSize - 3 * seg;
-                                    c.sStrict = (l1 < 8 || l2 < 8 || l3 < 8 || c.sEnd[3] - c.sBeg[3] < 8) ? 1u : 0u;
-                                }
-                            }
-                            h.seqOff = c.pos + lhSize + litCSize;
-                        }
-                    }
-                }
-            } else {
-                bool ok = true;
-                if (fmt == 0 || fmt == 2) { lhSize = 1; litSize = ip[0] >> 3; }
-                else if (fmt == 1) { lhSize = 2; litSize = zl_rd16(ip) >> 4; }
-                else { lhSize = 3; if (csize < 3) { ok = false; litSize = 0; } else litSize = zl_rd24(ip) >> 4; }
-                if (!ok) c.err = ZL_E_corruption_detected;
-                else if (litSize > c.blockSizeMax) c.err = ZL_E_corruption_detected;
-                else if (ltype == 0) {
-                    if (lhSize + litSize > csize) c.err = ZL_E_corruption_detected;
-                    else { litMode = 0; h.srcOff = c.pos + lhSize; h.seqOff = c.pos + lhSize + litSize; }
-                } else {
-                    if (lhSize + 1 > csize) c.err = ZL_E_corruption_detected;
-                    else { litMode = 1; h.flags |= (u32)ip[lhSize] << 8; h.seqOff = c.pos + lhSize + 1; }
-                }
-            }
-            h.flags |= 2u | (litMode << 4);
-            h.litSize = litSize; h.seqEnd = blockEnd;
-            c.pos = blockEnd;
+            c.nStreams = 4;
+            c.sBeg[0] = hs + 6; c.sEnd[0] = c.sBeg[0] + l1;
+            c.sBeg[1] = c.sEnd[0]; c.sEnd[1] = c.sBeg[1] + l2;
+            c.sBeg[2] = c.sEnd[1]; c.sEnd[2] = c.sBeg[2] + l3;
+            c.sBeg[3] = c.sEnd[2]; c.sEnd[3] = hs + hsz;
+            for (u32 k = 0; k < 4; k++) { c.sOut[k] = h.litOff + k * seg; c.sLen[k] = seg; }
+            c.sLen[3] = litSize - 3 * seg;
+            // libzstd's 4-stream decoder only insists on exact consumption when it cannot take its "fast" path, i.e. when a
+            // stream is shorter than 8 bytes (HUF_DecompressFastArgs_init, zstd.c:38772-38850; the fast path checks the
+            // regenerated sizes only); the single-stream decoder always does (zstd.c:38647).  Same here, so that a damaged
+            // frame without checksum decodes to the same bytes as with the reference.
+            c.sStrict = (l1 < 8 || l2 < 8 || l3 < 8 || c.sEnd[3] - c.sBeg[3] < 8) ? 1u : 0u;
         }
     }
-    if (c.err) { c.nStreams = 0; c.needHufFill = 0; zl_lit_finish_frame(f, d, info); return; }
-    hdrs[c.blockIdx] = h;
-    c.blockIdx++;
+}
+// after the streams ran (lane 0): 0 or the error of this block
+ZL_HD u32 zl_lit_unit_finish(const ZlLitSm& f)
+{
+    const ZlLitCtl& c = f.ctl;
+    if (c.err) return c.err;
+    for (u32 k = 0; k < c.nStreams; k++) if (c.sErr[k] == 1 || (c.sErr[k] == 2 && c.sStrict)) return ZL_E_corruption_detected;
+    return 0;
 }
 
 // =================================================================================================== K1b: sequences
 struct ZlSeqCtl {
     u32 err;
-    u32 fseValid;
-    u32 recUsed;
     u32 nbSeq;
     u32 needBuild;      // bit t: build table t (0 LL, 1 OF, 2 ML) from norm[t]
+    u32 useDict;        // bit t: table t is the dictionary's (the caller copies it)
     u32 tlog[3], maxSym[3], bErr[3];
     u32 bitBeg, bitEnd;
 };
-struct ZlSeqSm {            // 2,644 B: with 8 frames per warp, 10 warps fit one SM's shared memory
+struct ZlSeqSm {            // 2,632 B: with 8 blocks per warp, 10 warps fit one SM's shared memory
     u16 fseLL[512];
     u16 fseML[512];
     u16 fseOF[256];
     ZlSeqCtl ctl;
 };
-#define ZL_NORM_STRIDE 64       // i16 per table in the per-frame normalized-count scratch (3 tables)
+#define ZL_NORM_STRIDE 64       // i16 per table in the per-unit normalized-count scratch (3 tables)
 
-// sequences section header (lane 0): zstd.c:43707-43790.  `norm` = 3 x ZL_NORM_STRIDE i16 of scratch (global memory
-// in the kernel: it is only touched while tables are (re)built, so it does not deserve shared memory).
-ZL_HD void zl_seq_head(ZlSeqSm& f, const ZlFrameDesc& d, const ZlBlockHdr& h, const ZlConstTables& ct, i16* norm)
+// One table description at src[ip..iend) for table t with the given mode (0 predefined, 1 RLE, 2 FSE-compressed): loads it
+// into f (cell / norm + needBuild) when `load`, and returns the bytes it occupies (0xFFFFFFFF on error).
+ZL_HD u32 zl_seq_table_desc(ZlSeqSm& f, const u8* src, u32 ip, u32 iend, u32 t, u32 mode, bool load, const ZlConstTables& ct, i16* norm)
 {
     ZlSeqCtl& c = f.ctl;
-    c.needBuild = 0; c.nbSeq = 0;
-    if (c.err) return;
-    const u8* src = d.src;
-    u32 ip = h.seqOff, iend = h.seqEnd;
-    if (ip >= iend) { c.err = ZL_E_srcSize_wrong; return; }
-    u32 nbSeq = src[ip++];
-    if (nbSeq > 0x7F) {
-        if (nbSeq == 0xFF) { if (ip + 2 > iend) { c.err = ZL_E_srcSize_wrong; return; } nbSeq = zl_rd16(src + ip) + 0x7F00; ip += 2; }
-        else { if (ip >= iend) { c.err = ZL_E_srcSize_wrong; return; } nbSeq = ((nbSeq - 0x80) << 8) + src[ip++]; }
-    }
-    c.nbSeq = nbSeq;
-    if (nbSeq == 0) { if (ip != iend) c.err = ZL_E_corruption_detected; return; }
-    if (ip + 1 > iend) { c.err = ZL_E_srcSize_wrong; return; }
-    u32 modes = src[ip++];
-    if (modes & 3) { c.err = ZL_E_corruption_detected; return; }
     const u32 maxSymT[3] = {35, 31, 52}, maxLogT[3] = {9, 8, 9}, defLogT[3] = {6, 5, 6};
-    for (u32 t = 0; t < 3; t++) {
-        u32 mode = (modes >> (6 - 2 * t)) & 3;
-        u16* tbl = t == 0 ? f.fseLL : (t == 1 ? f.fseOF : f.fseML);
-        i16* nt = norm + t * ZL_NORM_STRIDE;
-        if (mode == 0) {                               // predefined
+    u16* tbl = t == 0 ? f.fseLL : (t == 1 ? f.fseOF : f.fseML);
+    i16* nt = norm + t * ZL_NORM_STRIDE;
+    if (mode == 0) {                               // predefined
+        if (load) {
             const i16* def = t == 0 ? ct.llDef : (t == 1 ? ct.ofDef : ct.mlDef);
-            u32 nsym = t == 0 ? 36 : (t == 1 ? 29 : 53);
+            const u32 nsym = t == 0 ? 36 : (t == 1 ? 29 : 53);
             for (u32 s = 0; s < nsym; s++) nt[s] = def[s];
             c.maxSym[t] = nsym - 1; c.tlog[t] = defLogT[t]; c.needBuild |= 1u << t;
-        } else if (mode == 1) {                        // RLE
-            if (ip >= iend) { c.err = ZL_E_corruption_detected; return; }
-            u32 s = src[ip++];
-            if (s > maxSymT[t]) { c.err = ZL_E_corruption_detected; return; }
-            tbl[0] = zl_seq_cell(1, s); c.tlog[t] = 0;
-        } else if (mode == 2) {                        // FSE-compressed
-            u32 ms = maxSymT[t], tl;
-            u32 hsz = zl_read_ncount(src + ip, iend - ip, nt, &ms, &tl);
-            if (!hsz || tl > maxLogT[t]) { c.err = ZL_E_corruption_detected; return; }
-            ip += hsz; c.maxSym[t] = ms; c.tlog[t] = tl; c.needBuild |= 1u << t;
-        } else {                                       // repeat
-            if (!((c.fseValid >> t) & 1)) { c.err = ZL_E_corruption_detected; return; }
         }
-        c.fseValid |= 1u << t;
+        return 0;
+    }
+    if (mode == 1) {                               // RLE
+        if (ip >= iend) return 0xFFFFFFFFu;
+        const u32 sy = src[ip];
+        if (sy > maxSymT[t]) return 0xFFFFFFFFu;
+        if (load) { tbl[0] = zl_seq_cell(1, sy); c.tlog[t] = 0; }
+        return 1;
+    }
+    u32 ms = maxSymT[t], tl;                       // FSE-compressed (the counts land in this table's scratch slot either way)
+    const u32 hsz = zl_read_ncount(src + ip, iend - ip, nt, &ms, &tl);
+    if (!hsz || tl > maxLogT[t]) return 0xFFFFFFFFu;
+    if (load) { c.maxSym[t] = ms; c.tlog[t] = tl; c.needBuild |= 1u << t; }
+    return hsz;
+}
+
+// sequences section header of block `blk` (lane 0): zstd.c:43707-43790.  A table in "repeat" mode is re-read from the
+// block that last defined it (K0 recorded which one), so blocks decode independently of each other.
+// `norm` = 3 x ZL_NORM_STRIDE i16 of scratch (global memory in the kernel).
+ZL_HD void zl_seq_head(ZlSeqSm& f, const ZlFrameDesc& d, const ZlBlockHdr* hdrs, u32 blk, const ZlConstTables& ct, i16* norm)
+{
+    ZlSeqCtl& c = f.ctl;
+    const ZlBlockHdr& h = hdrs[blk];
+    c.err = 0; c.needBuild = 0; c.useDict = 0; c.nbSeq = h.nbSeq;
+    c.bErr[0] = c.bErr[1] = c.bErr[2] = 0;
+    if (!h.nbSeq) { if (h.seqOff + 1 != h.seqEnd) c.err = ZL_E_corruption_detected; return; }     // zstd.c:43736: nothing may follow nbSeq == 0
+    const u8* src = d.src;
+    u32 ip = h.seqOff + (h.nbSeq < 128 ? 1u : (h.nbSeq < 0x7F00 ? 2u : 3u));
+    const u32 iend = h.seqEnd;
+    const u32 modes = src[ip++];
+    for (u32 t = 0; t < 3; t++) {
+        const u32 mode = (modes >> (6 - 2 * t)) & 3;
+        if (mode != 3) {
+            const u32 used = zl_seq_table_desc(f, src, ip, iend, t, mode, true, ct, norm);
+            if (used == 0xFFFFFFFFu) { c.err = ZL_E_corruption_detected; return; }
+            ip += used;
+        } else if (h.seqDef[t] == ZL_DEF_NONE) c.useDict |= 1u << t;
+        else {                                          // walk the defining block's descriptions up to table t
+            const ZlBlockHdr& dh = hdrs[h.seqDef[t]];
+            u32 q = dh.seqOff + (dh.nbSeq < 128 ? 1u : (dh.nbSeq < 0x7F00 ? 2u : 3u));
+            const u32 dm = src[q++];
+            for (u32 tt = 0; tt <= t; tt++) {
+                const u32 m2 = (dm >> (6 - 2 * tt)) & 3;
+                if (m2 == 3) continue;                  // takes no bytes (and cannot be tt == t: K0 only names defining blocks)
+                // earlier tables of that block are only measured; their counts go through table t's scratch slot
+                const u32 used = tt == t ? zl_seq_table_desc(f, src, q, dh.seqEnd, t, m2, true, ct, norm)
+                                         : (m2 == 2 ? [&]() { u32 ms = tt == 0 ? 35u : (tt == 1 ? 31u : 52u), tl; const u32 r = zl_read_ncount(src + q, dh.seqEnd - q, norm + t * ZL_NORM_STRIDE, &ms, &tl); return r ? r : 0xFFFFFFFFu; }()
+                                                    : (m2 == 1 ? 1u : 0u));
+                if (used == 0xFFFFFFFFu) { c.err = ZL_E_corruption_detected; return; }
+                q += used;
+            }
+        }
     }
     c.bitBeg = ip; c.bitEnd = iend;
 }
@@ -767,18 +870,17 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xta
 // serial sequence decode of one block (lane 0): zstd.c:44627-44700.  Completes the block's ZlBlockHdr (nrec, recOff);
 // the regenerated size is only known once K2 has added up the lengths.
 // `xtab` is only used by the device fast path (null in the CPU emulation).
-ZL_HD void zl_seq_decode(ZlSeqSm& f, const ZlFrameDesc& d, ZlBlockHdr& h, u64* recs, const u32* wbase, u32 bias,
-                         const ZlConstTables& ct, const u32* xtab)
+// `recs` = this block's slice of the record arena (room for nbSeq + 4 records: a block regenerates <= 128 KiB, so at most
+// two lengths can be split); returns the number of records written.
+ZL_HD u32 zl_seq_decode(ZlSeqSm& f, u64* recs, const u32* wbase, u32 bias, const ZlConstTables& ct, const u32* xtab)
 {
     (void)xtab;
     ZlSeqCtl& c = f.ctl;
     if (!c.err && c.needBuild) { for (u32 t = 0; t < 3; t++) if (c.bErr[t]) c.err = ZL_E_corruption_detected; }
-    u64* rp = recs + c.recUsed;
-    const u32 recCap = d.recCap - c.recUsed;
+    u64* rp = recs;
+    const u32 recCap = c.nbSeq + ZL_REC_SLACK;
     ZlSeqRegs r;
     r.nrec = 0; r.err = 0;
-    // every sequence of a valid block regenerates >= 3 bytes, so nbSeq + 4 (splits) always fits; reject early otherwise
-    if (!c.err && c.nbSeq + 4 > recCap) c.err = c.nbSeq ? ZL_E_corruption_detected : 0;
     if (!c.err && c.nbSeq) {
         ZlBitR b;
         if (!zl_br_init(b, wbase, bias, c.bitBeg, c.bitEnd)) c.err = ZL_E_corruption_detected;
@@ -804,20 +906,6 @@ ZL_HD void zl_seq_decode(ZlSeqSm& f, const ZlFrameDesc& d, ZlBlockHdr& h, u64* r
             if (r.err) c.err = r.err;
         }
     }
-    if (c.err) return;
-    h.nrec = r.nrec; h.recOff = c.recUsed;
-    c.recUsed += r.nrec;
+    return c.err ? 0u : r.nrec;
 }
 
-// whole-frame driver pieces for K1b (lane 0)
-ZL_HD void zl_seq_begin_frame(ZlSeqSm& f, const ZlFrameInfo& info)
-{
-    ZlSeqCtl& c = f.ctl;
-    c.err = info.err; c.fseValid = 0;
-    c.recUsed = 0; c.nbSeq = 0; c.needBuild = 0;
-    c.bErr[0] = c.bErr[1] = c.bErr[2] = 0;
-}
-ZL_HD void zl_seq_finish_frame(ZlSeqSm& f, ZlFrameInfo& info)
-{
-    info.err = f.ctl.err;          // sizes are checked by K2 (destination capacity per block, content size at the end: zstd.c:41646)
-}

@@ -10,43 +10,72 @@ __constant__ ZlConstTables c_tables = {
     ZL_LL_BASE_INIT, ZL_ML_BASE_INIT, ZL_LL_BITS_INIT, ZL_ML_BITS_INIT,
     ZL_LL_DEFNORM_INIT, ZL_ML_DEFNORM_INIT, ZL_OF_DEFNORM_INIT};
 
+// ---- K0: index ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+zl_k_index(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, ZlBlockHdr* hdrArena, ZlUnit* units, u32* unitCount,
+           u32 unitCap, u32 nframes, u32 frameBase, const ZlDictDev* dict)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nframes) return;
+    const ZlFrameDesc d = descs[i];
+    ZlFrameInfo info;
+    zl_index_frame(d, info, hdrArena + d.hdrBase, frameBase + i, dict ? dict->dictID : 0u, (dict && dict->hasEntropy) ? 1u : 0u,
+                   units, unitCount, unitCap);
+    infos[i] = info;
+}
+
+// Units are fetched dynamically, 8 at a time per warp (one per quad), so expensive and cheap blocks balance across the grid.
+__device__ __forceinline__ u32 zl_fetch_units(u32* cursor, u32 lane)
+{
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (u32)ZL_QUADS_PER_WARP);
+    return __shfl_sync(0xFFFFFFFFu, base, 0);
+}
+
 // ---- K1a: literals ------------------------------------------------------------------------------------------
+// descs / infos are indexed by the GLOBAL frame number carried by the unit
 __global__ void __launch_bounds__(32)
-zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, ZlBlockHdr* hdrArena,
-              u8* litArena, u32 nframes, const ZlDictDev* dict)
+zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, const ZlBlockHdr* hdrArena,
+              u8* litArena, const ZlUnit* __restrict__ units, const u32* __restrict__ unitCount, u32* cursor, const ZlDictDev* dict)
 {
     extern __shared__ __align__(16) u8 smraw[];
     ZlLitSm* fs = reinterpret_cast<ZlLitSm*>(smraw);
     const u32 lane = threadIdx.x, quad = lane >> 2, q = lane & 3;
     const u32 qmask = 0xFu << (quad * 4);
-    const u32 frame = blockIdx.x * ZL_QUADS_PER_WARP + quad;
-    if (frame >= nframes) return;
     ZlLitSm& f = fs[quad];
-    const ZlFrameDesc d = descs[frame];
-    ZlFrameInfo& info = infos[frame];
-    ZlBlockHdr* hdrs = hdrArena + d.hdrBase;
-    u8* lits = litArena + d.litBase;
-    const u32 bias = (u32)(((size_t)d.src) & 3);
-    const u32* wbase = reinterpret_cast<const u32*>(d.src - bias);
-    const bool seed = dict && dict->hasEntropy;
-    if (q == 0) {
-        zl_lit_begin_frame(f, d, info, dict ? dict->dictID : 0u);
-        if (seed && !f.ctl.err) { f.ctl.hufValid = 1; f.ctl.hufLog = dict->hufLog; }      // zstd.c:42140-42159
-    }
-    if (seed) for (u32 i = q; i < 2048; i += 4) f.huf[i] = dict->huf[i];
-    // Lane 0 writes f.ctl between quad barriers; the other lanes snapshot what they need right after a
-    // barrier and a second barrier keeps lane 0 from overwriting it before everyone has read it.
+    const u32 nunits = *unitCount;
     for (;;) {
-        __syncwarp(qmask);
-        if (q == 0) zl_lit_block_head(f, d, info, hdrs, wbase, bias);
-        __syncwarp(qmask);
-        const u32 done = f.ctl.done, fill = f.ctl.needHufFill, ns = f.ctl.nStreams;
-        __syncwarp(qmask);
-        if (done) break;
-        if (fill) { zl_huf_fill(f, q); __syncwarp(qmask); }
-        if (q < ns)
-            f.ctl.sErr[q] = zl_huf_stream(f.huf, f.ctl.hufLog, wbase, bias, f.ctl.sBeg[q], f.ctl.sEnd[q],
-                                          lits + f.ctl.sOut[q], f.ctl.sLen[q]);
+        const u32 ubase = zl_fetch_units(cursor, lane);
+        if (ubase >= nunits) break;
+        const u32 u = ubase + quad;
+        if (u < nunits) {
+            const ZlUnit un = units[u];
+            const ZlFrameDesc d = descs[un.frame];
+            const ZlBlockHdr* hdrs = hdrArena + d.hdrBase;
+            const u32 litMode = (hdrs[un.block].flags >> 4) & 3;
+            if (litMode == 2) {                                        // (units with raw / rle literals only have sequences)
+                u8* lits = litArena + d.litBase;
+                const u32 bias = (u32)(((size_t)d.src) & 3);
+                const u32* wbase = reinterpret_cast<const u32*>(d.src - bias);
+                u32 useDict = 0;
+                if (q == 0) zl_lit_unit_head(f, d, hdrs, un.block, wbase, bias, &useDict);
+                useDict = __shfl_sync(qmask, useDict, quad * 4);
+                __syncwarp(qmask);
+                const u32 fill = f.ctl.needHufFill, ns = f.ctl.err ? 0u : f.ctl.nStreams;
+                if (useDict) {                                         // zstd.c:42140-42159: the dictionary's tree
+                    for (u32 i = q; i < 2048; i += 4) f.huf[i] = dict->huf[i];
+                    if (q == 0) f.ctl.hufLog = dict->hufLog;
+                } else if (fill && !f.ctl.err) zl_huf_fill(f, q);
+                __syncwarp(qmask);
+                if (q < ns)
+                    f.ctl.sErr[q] = zl_huf_stream(f.huf, f.ctl.hufLog, wbase, bias, f.ctl.sBeg[q], f.ctl.sEnd[q],
+                                                  lits + f.ctl.sOut[q], f.ctl.sLen[q]);
+                __syncwarp(qmask);
+                if (q == 0) { const u32 e = zl_lit_unit_finish(f); if (e) infos[un.frame].err = e; }
+                __syncwarp(qmask);
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -54,7 +83,8 @@ zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ i
 #define ZL_XTAB_BYTES ((ZL_XTAB_WORDS * 4 + 15) & ~15)
 __global__ void __launch_bounds__(32)
 zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, ZlBlockHdr* hdrArena,
-               u64* recArena, i16* normArena, u32 nframes, const ZlDictDev* dict)
+               u64* recArena, i16* normArena, const ZlUnit* __restrict__ units, const u32* __restrict__ unitCount, u32* cursor,
+               const ZlDictDev* dict)
 {
     extern __shared__ __align__(16) u8 smraw[];
     u32* xtab = reinterpret_cast<u32*>(smraw);
@@ -65,41 +95,40 @@ zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ 
     for (u32 i = lane; i < ZL_XTAB_WORDS; i += 32)
         xtab[i] = i < 36 ? (c_tables.llBase[i] | ((u32)c_tables.llBits[i] << 24)) : (c_tables.mlBase[i - 36] | ((u32)c_tables.mlBits[i - 36] << 24));
     __syncwarp();
-    const u32 frame = blockIdx.x * ZL_QUADS_PER_WARP + quad;
-    if (frame >= nframes) return;
     ZlSeqSm& f = fs[quad];
-    const ZlFrameDesc d = descs[frame];
-    ZlFrameInfo& info = infos[frame];
-    ZlBlockHdr* hdrs = hdrArena + d.hdrBase;
-    u64* recs = recArena + d.recBase;
-    i16* norm = normArena + (size_t)frame * (3 * ZL_NORM_STRIDE);
-    const u32 bias = (u32)(((size_t)d.src) & 3);
-    const u32* wbase = reinterpret_cast<const u32*>(d.src - bias);
-    const u32 nblocks = info.nblocks;
-    const bool seed = dict && dict->hasEntropy;
-    if (q == 0) {
-        zl_seq_begin_frame(f, info);
-        if (seed) {                                                   // zstd.c:42140-42159: tables from the dictionary (repcodes: K2)
-            f.ctl.fseValid = 7;
-            f.ctl.tlog[0] = dict->tlog[0]; f.ctl.tlog[1] = dict->tlog[1]; f.ctl.tlog[2] = dict->tlog[2];
+    i16* norm = normArena + ((size_t)blockIdx.x * ZL_QUADS_PER_WARP + quad) * (3 * ZL_NORM_STRIDE);     // scratch per resident quad
+    const u32 nunits = *unitCount;
+    for (;;) {
+        const u32 ubase = zl_fetch_units(cursor, lane);
+        if (ubase >= nunits) break;
+        const u32 u = ubase + quad;
+        if (u < nunits) {
+            const ZlUnit un = units[u];
+            const ZlFrameDesc d = descs[un.frame];
+            ZlBlockHdr* hdrs = hdrArena + d.hdrBase;
+            if (hdrs[un.block].nbSeq) {
+                const u32 bias = (u32)(((size_t)d.src) & 3);
+                const u32* wbase = reinterpret_cast<const u32*>(d.src - bias);
+                if (q == 0) zl_seq_head(f, d, hdrs, un.block, ct, norm);
+                __syncwarp(qmask);
+                const u32 build = f.ctl.err ? 0u : f.ctl.needBuild, useDict = f.ctl.err ? 0u : f.ctl.useDict;
+                if (useDict) {                                     // zstd.c:42140-42159: tables of the dictionary
+                    if (useDict & 1) { for (u32 i = q; i < 512; i += 4) f.fseLL[i] = dict->fseLL[i]; if (q == 0) f.ctl.tlog[0] = dict->tlog[0]; }
+                    if (useDict & 2) { for (u32 i = q; i < 256; i += 4) f.fseOF[i] = dict->fseOF[i]; if (q == 0) f.ctl.tlog[1] = dict->tlog[1]; }
+                    if (useDict & 4) { for (u32 i = q; i < 512; i += 4) f.fseML[i] = dict->fseML[i]; if (q == 0) f.ctl.tlog[2] = dict->tlog[2]; }
+                }
+                if (build && q < 3) zl_seq_fse_build(f, q, norm);
+                __syncwarp(qmask);
+                if (q == 0) {
+                    const u32 nrec = zl_seq_decode(f, recArena + d.recBase + hdrs[un.block].recOff, wbase, bias, ct, xtab);
+                    hdrs[un.block].nrec = nrec;
+                    if (f.ctl.err) infos[un.frame].err = f.ctl.err;
+                }
+                __syncwarp(qmask);
+            }
         }
+        __syncwarp();
     }
-    if (seed) {
-        for (u32 i = q; i < 512; i += 4) { f.fseLL[i] = dict->fseLL[i]; f.fseML[i] = dict->fseML[i]; }
-        for (u32 i = q; i < 256; i += 4) f.fseOF[i] = dict->fseOF[i];
-    }
-    __syncwarp(qmask);
-    for (u32 b = 0; b < nblocks; b++) {
-        ZlBlockHdr h = hdrs[b];
-        if ((h.flags & 3) != 2) continue;
-        if (q == 0) zl_seq_head(f, d, h, ct, norm);
-        __syncwarp(qmask);
-        const u32 build = f.ctl.err ? 0u : f.ctl.needBuild;
-        __syncwarp(qmask);
-        if (build) { if (q < 3) zl_seq_fse_build(f, q, norm); __syncwarp(qmask); }
-        if (q == 0) { zl_seq_decode(f, d, h, recs, wbase, bias, ct, xtab); hdrs[b] = h; }
-    }
-    if (q == 0) zl_seq_finish_frame(f, info);
 }
 
 template <bool kDict>
@@ -180,20 +209,52 @@ zl_k_xxh64(const u8* const* __restrict__ ptrs, const u32* __restrict__ sizes, u6
 size_t zl_literals_smem_bytes() { return ZL_QUADS_PER_WARP * sizeof(ZlLitSm); }
 size_t zl_sequences_smem_bytes() { return ZL_XTAB_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlSeqSm); }
 
+static int g_sms = 0, g_litPerSm = 0, g_seqPerSm = 0;
+cudaError_t zl_decode_grid_limits(u32* litCtas, u32* seqCtas)
+{
+    if (!g_sms) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        const size_t smA = zl_literals_smem_bytes(), smB = zl_sequences_smem_bytes();
+        e = cudaFuncSetAttribute(zl_k_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(zl_k_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_litPerSm, zl_k_literals, 32, smA);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_seqPerSm, zl_k_sequences, 32, smB);
+        if (e != cudaSuccess) return e;
+        if (g_litPerSm < 1) g_litPerSm = 1;
+        if (g_seqPerSm < 1) g_seqPerSm = 1;
+    }
+    *litCtas = (u32)(g_sms * g_litPerSm); *seqCtas = (u32)(g_sms * g_seqPerSm);
+    return cudaSuccess;
+}
+
 cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
 {
     if (L.nframes == 0) return cudaSuccess;
     const size_t smA = zl_literals_smem_bytes(), smB = zl_sequences_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(zl_k_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA);
+    u32 litCtas = 0, seqCtas = 0;
+    cudaError_t e = zl_decode_grid_limits(&litCtas, &seqCtas);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(zl_k_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB);
-    if (e != cudaSuccess) return e;
-    const u32 g1 = (L.nframes + ZL_QUADS_PER_WARP - 1) / ZL_QUADS_PER_WARP;
+    // persistent grids: never more CTAs than fit the device at once or than there could be units (8 per CTA)
+    const u32 maxCtas = (L.unitCap + ZL_QUADS_PER_WARP - 1) / ZL_QUADS_PER_WARP;
+    if (litCtas > maxCtas) litCtas = maxCtas;
+    if (seqCtas > maxCtas) seqCtas = maxCtas;
+    if (seqCtas > L.normSlots / ZL_QUADS_PER_WARP) seqCtas = L.normSlots / ZL_QUADS_PER_WARP;
+    if (!litCtas) litCtas = 1;
+    if (!seqCtas) seqCtas = 1;
     cudaEvent_t* ev = L.stageEv;
     if (ev) cudaEventRecord(ev[0], st);
-    zl_k_literals<<<g1, 32, smA, st>>>(L.descs, L.infos, L.hdrArena, L.litArena, L.nframes, L.dict);
+    cudaMemsetAsync(L.counters, 0, 3 * sizeof(u32), st);              // unit count, literal cursor, sequence cursor
+    zl_k_index<<<(L.nframes + 127) / 128, 128, 0, st>>>(L.descs, L.infos, L.hdrArena, L.units, L.counters, L.unitCap, L.nframes, L.frameBase, L.dict);
+    zl_k_literals<<<litCtas, 32, smA, st>>>(L.descsAll, L.infosAll, L.hdrArena, L.litArena, L.units, L.counters, L.counters + 1, L.dict);
     if (ev) cudaEventRecord(ev[1], st);
-    zl_k_sequences<<<g1, 32, smB, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.normArena, L.nframes, L.dict);
+    zl_k_sequences<<<seqCtas, 32, smB, st>>>(L.descsAll, L.infosAll, L.hdrArena, L.recArena, L.normArena, L.units, L.counters, L.counters + 2, L.dict);
     if (ev) cudaEventRecord(ev[2], st);
     const u32 g2 = (L.nframes + ZL_EXEC_WARPS - 1) / ZL_EXEC_WARPS;
     if (L.dict)

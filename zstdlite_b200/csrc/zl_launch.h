@@ -5,7 +5,8 @@
 
 #define ZL_QUADS_PER_WARP 8
 #define ZL_EXEC_WARPS 4
-#define ZL_DEC_STAGES 4      // literals, sequences, execute, checksum
+#define ZL_DEC_STAGES 4      // (index +) literals, sequences, execute, checksum
+#define ZL_NORM_SLOTS 16384  // resident quads of one sequence-kernel launch the normalized-count scratch has room for
 #define ZL_DEC_LANES 8                       // internal streams of the decode slice pipeline
 #define ZL_DEC_MAX_SLICES 8                  // one slice per lane: concurrency between streams is what pays, not queueing
 #define ZL_DEC_SLICE_BYTES (64ull << 20)     // aim for >= 64 MiB of content ...
@@ -30,18 +31,25 @@ struct ZlDictDev {
     const u8* content;     // device pointer
 };
 
-struct ZlDecodeLaunch {
-    const ZlFrameDesc* descs;
+struct ZlDecodeLaunch {          // one slice of a batch: frames [frameBase, frameBase + nframes)
+    const ZlFrameDesc* descs;    // this slice's descriptors / infos / results ...
     ZlFrameInfo* infos;
+    u64* results;
+    const ZlFrameDesc* descsAll; // ... and the arrays of the whole batch (the block units carry global frame numbers)
+    ZlFrameInfo* infosAll;
+    u32 frameBase;
     ZlBlockHdr* hdrArena;
     u64* recArena;
     u8* litArena;
-    i16* normArena;          // 3 x 64 i16 per frame: normalized counts while FSE tables are (re)built
-    u64* results;
+    i16* normArena;              // 3 x 64 i16 per resident quad of the sequence kernel: normalized counts while FSE tables are built
+    u32 normSlots;               // quads the scratch has room for
+    ZlUnit* units;               // this slice's block-unit list (compressed blocks), capacity unitCap
+    u32 unitCap;
+    u32* counters;               // this slice's {unit count, literal cursor, sequence cursor}
     u32 nframes;
     int verifyChecksum;
-    const ZlDictDev* dict;   // device pointer or null
-    cudaEvent_t* stageEv;    // null, or ZL_DEC_STAGES + 1 events recorded around each kernel (per-kernel timing for bench.py)
+    const ZlDictDev* dict;       // device pointer or null
+    cudaEvent_t* stageEv;        // null, or ZL_DEC_STAGES + 1 events recorded around each kernel (per-kernel timing for bench.py)
 };
 
 size_t zl_literals_smem_bytes();
