@@ -18,7 +18,7 @@ extern "C" size_t zl_emul_decompress_frame(void* dstv, size_t cap, const void* s
     memcpy(src, srcv, size);
     ZlFrameDesc d; memset(&d, 0, sizeof(d));
     d.src = src; d.dst = (u8*)dstv; d.srcSize = (u32)size; d.dstCap = (u32)cap;
-    zl_plan_frame(d.srcSize, d.dstCap, true, &d.litCap, &d.recCap, &d.hdrCap, &d.ckCap);
+    zl_plan_frame(d.srcSize, d.dstCap, true, &d.litCap, &d.recCap, &d.hdrCap);
     std::vector<u8> lits(d.litCap + 16);
     std::vector<u64> recs(d.recCap);
     std::vector<ZlBlockHdr> hdrs(d.hdrCap);

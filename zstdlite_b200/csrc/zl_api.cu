@@ -185,8 +185,8 @@ struct ZSTD_DCtx_s {
     // streaming session (ZSTD_decompressStream): input accumulated on the host until a whole frame is present
     std::vector<u8> sIn, sOut;
     size_t sOutPos = 0;
-    ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dNorm, dUnits, dCounters, dSrc, dDst;
-    ZlPinBuf hDescs, hResults;
+    ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dNorm, dUnits, dCounters, dLargeIdx, dLb, dParent, dRemain, dSrc, dDst;
+    ZlPinBuf hDescs, hResults, hLargeIdx, hRemain;
 };
 
 static bool zl_ctx_stream(cudaStream_t* st, bool* own, cudaEvent_t* e0, cudaEvent_t* e1)
@@ -203,9 +203,9 @@ ZL_EXPORT ZSTD_DCtx* ZSTD_createDCtx(void) { return new (std::nothrow) ZSTD_DCtx
 ZL_EXPORT size_t ZSTD_freeDCtx(ZSTD_DCtx* c)
 {
     if (!c) return 0;
-    ZlDevBuf* bufs[] = {&c->dDictContent, &c->dDict, &c->dDescs, &c->dInfos, &c->dResults, &c->dHdr, &c->dRec, &c->dCk, &c->dLit, &c->dNorm, &c->dUnits, &c->dCounters, &c->dSrc, &c->dDst};
+    ZlDevBuf* bufs[] = {&c->dDictContent, &c->dDict, &c->dDescs, &c->dInfos, &c->dResults, &c->dHdr, &c->dRec, &c->dCk, &c->dLit, &c->dNorm, &c->dUnits, &c->dCounters, &c->dLargeIdx, &c->dLb, &c->dParent, &c->dRemain, &c->dSrc, &c->dDst};
     for (ZlDevBuf* b : bufs) b->release();
-    c->hDescs.release(); c->hResults.release();
+    c->hDescs.release(); c->hResults.release(); c->hLargeIdx.release(); c->hRemain.release();
     if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
     for (cudaEvent_t e : c->stageEv) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->laneDone) if (e) cudaEventDestroy(e);
@@ -407,8 +407,8 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         }
         if (!c->dSrc.reserve(srcTotal + 64) || !c->dDst.reserve(dstTotal + 64)) return ZL_ERROR(memory_allocation);
     }
-    u64 lit = 0, rec = 0, hdr = 0, ck = 0;
-    size_t sr = 0, dr = 0;
+    u64 lit = 0, rec = 0, hdr = 0, par = 0;
+    size_t sr = 0, dr = 0, nLargeTotal = 0;
     for (size_t i = 0; i < n; i++) {
         ZlFrameDesc& d = hd[i];
         if (dev) { d.src = (const u8*)src[i]; d.dst = (u8*)dst[i]; }
@@ -419,15 +419,28 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
             d.dst = c->dDst.as<u8>() + druns[dr].devOff + ((const u8*)dst[i] - druns[dr].hbase);
         }
         d.srcSize = (u32)srcSize[i]; d.dstCap = (u32)dstCap[i];
-        zl_plan_frame(d.srcSize, d.dstCap, worst, &d.litCap, &d.recCap, &d.hdrCap, &d.ckCap);
-        d.litBase = lit; d.recBase = rec; d.hdrBase = hdr; d.ckBase = ck;
-        lit += ((u64)d.litCap + 15) & ~15ull; rec += d.recCap; hdr += d.hdrCap; ck += d.ckCap;
+        zl_plan_frame(d.srcSize, d.dstCap, worst, &d.litCap, &d.recCap, &d.hdrCap);
+        d.litBase = lit; d.recBase = rec; d.hdrBase = hdr; d.parBase = par;
+        d.large = d.dstCap >= ZL_LARGE_FRAME_BYTES ? 1u : 0u;
+        if (d.large) { par += ((u64)d.dstCap + 3) & ~3ull; nLargeTotal++; }
+        lit += ((u64)d.litCap + 15) & ~15ull; rec += d.recCap; hdr += d.hdrCap;
     }
     if (!c->dDescs.reserve(n * sizeof(ZlFrameDesc)) || !c->dInfos.reserve(n * sizeof(ZlFrameInfo)) || !c->dResults.reserve(n * 8) ||
         !c->dLit.reserve(lit + 64) || !c->dRec.reserve(rec * 8) ||
         !c->dNorm.reserve(nslices * (size_t)ZL_NORM_SLOTS * 3 * ZL_NORM_STRIDE * sizeof(i16)) ||
         !c->dHdr.reserve(hdr * sizeof(ZlBlockHdr)) || !c->dUnits.reserve(hdr * sizeof(ZlUnit)) || !c->dCounters.reserve(nslices * 16))
         return ZL_ERROR(memory_allocation);
+    u32* hLarge = nullptr;
+    if (nLargeTotal) {                          // scratch of the block-parallel path for large frames (zl_dec_large.cuh)
+        if (!c->hLargeIdx.reserve(nLargeTotal * 4) || !c->dLargeIdx.reserve(nLargeTotal * 4) || !c->dLb.reserve(hdr * sizeof(ZlLBlock)) ||
+            !c->dParent.reserve(par * 4 + 64) || !c->dRemain.reserve(nslices * 64 * sizeof(u32)) || !c->hRemain.reserve(nslices * 64))
+            return ZL_ERROR(memory_allocation);
+        hLarge = c->hLargeIdx.as<u32>();
+        size_t w = 0;
+        for (size_t k = 0; k < nslices; k++) for (size_t i = cut[k]; i < cut[k + 1]; i++) if (hd[i].large) hLarge[w++] = (u32)(i - cut[k]);
+        cudaMemcpyAsync(c->dLargeIdx.p, hLarge, nLargeTotal * 4, cudaMemcpyHostToDevice, st);
+    }
+    size_t largeSeen = 0;
     cudaMemcpyAsync(c->dDescs.p, hd, n * sizeof(ZlFrameDesc), cudaMemcpyHostToDevice, st);
     if (!c->stageEv[0]) for (cudaEvent_t& e : c->stageEv) cudaEventCreate(&e);
     const int verify = !c->forceIgnoreChecksum;
@@ -449,6 +462,19 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         {   const u64 u0 = hd[a].hdrBase, u1 = cut[k + 1] < n ? hd[cut[k + 1]].hdrBase : hdr;      // the slice's share of the unit arena
             L.units = c->dUnits.as<ZlUnit>() + u0; L.unitCap = (u32)((u1 - u0) > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : (u1 - u0)); }
         L.counters = c->dCounters.as<u32>() + 4 * k;
+        L.nLarge = 0; L.largeIdx = nullptr; L.largeMaxBlocks = 0; L.largeMaxBytes = 0; L.lbArena = nullptr; L.parentArena = nullptr;
+        L.remain = nullptr; L.remainHost = nullptr;
+        if (nLargeTotal) {
+            L.largeIdx = c->dLargeIdx.as<u32>() + largeSeen;
+            for (size_t i = a; i < a + cnt; i++) if (hd[i].large) {
+                L.nLarge++;
+                if (hd[i].hdrCap > L.largeMaxBlocks) L.largeMaxBlocks = hd[i].hdrCap;
+                if (hd[i].dstCap > L.largeMaxBytes) L.largeMaxBytes = hd[i].dstCap;
+            }
+            largeSeen += L.nLarge;
+            L.lbArena = c->dLb.as<ZlLBlock>(); L.parentArena = c->dParent.as<u32>();
+            L.remain = c->dRemain.as<u32>() + 64 * k; L.remainHost = c->hRemain.as<u32>() + 16 * k;
+        }
         L.results = c->dResults.as<u64>() + a;
         L.nframes = (u32)cnt; L.verifyChecksum = verify; L.dict = c->hasDict ? c->dDict.as<ZlDictDev>() : nullptr;
         L.stageEv = nslices > 1 ? nullptr : c->stageEv;

@@ -65,6 +65,100 @@ ZL_D u32 zl_rept_compose(u32 A, u32 B)          // A first, then B
     return __byte_perm(A, B, sel) & 0x00FFFFFFu;
 }
 
+// ---- pieces shared by the warp-per-frame execute kernel and the large-frame kernels -----------------------------------------
+// one record per lane -> (litLength, matchLength, offBase); lanes without a record get zeros
+ZL_D void zl_lane_record(u64 rec, bool valid, const u32* xtab, u32& ll, u32& ml, u32& ob)
+{
+    ll = 0; ml = 0; ob = 0;
+    if (!valid) return;
+    if (rec & ZL_REC_B) { ll = (u32)rec & 0xFFFFu; ml = ((u32)rec >> 16) & 0xFFFFu; ob = (u32)(rec >> 32) & 0x7FFFFFFFu; return; }
+    const u32 snap = (u32)rec, c = (u32)(rec >> 32);
+    const u32 llCode = c & 63u, mlCode = (c >> 6) & 63u, aOF = (c >> 12) & 31u;
+    const u32 xl = xtab[llCode], xm = xtab[36 + mlCode];
+    const u32 aLL = xl >> 24, aML = xm >> 24;
+    ob = (1u << aOF) + zl_shr(snap, 32u - aOF);
+    ml = (xm & 0xFFFFFFu) + zl_shr(zl_shl(snap, aOF), 32u - aML);
+    ll = (xl & 0xFFFFFFu) + zl_shr(zl_shl(snap, aOF + aML), 32u - aLL);
+}
+// history slot (0..3, 3 = "rep0 - 1") a record reads; 0 also for records that do not read the history
+ZL_D u32 zl_rep_idx(u32 ll, u32 ml, u32 ob) { return (ml != 0 && ob >= 1 && ob <= 3) ? ob - 1 + (ll == 0 ? 1u : 0u) : 0u; }
+// the transform of one record in the byte form (never called for idx == 3)
+ZL_D u32 zl_rept_of(bool isNew, u32 idx, u32 lane)
+{
+    if (isNew) return 0x00010000u | 0x80u | lane;                                 // (mine, h0, h1)
+    if (idx == 1) return 0x00020001u;                                             // (h1, h0, h2)
+    if (idx == 2) return 0x00010002u;                                             // (h2, h0, h1)
+    return ZL_REPT_ID;
+}
+ZL_D u32 zl_rept_scan(u32 T, u32 lane)                                            // inclusive warp scan by composition
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 A = __shfl_up_sync(ZL_FULL, T, d);
+        if ((int)lane >= d) T = zl_rept_compose(A, T);
+    }
+    return T;
+}
+// Offsets of the 32 records of a batch and the history after it (zstd.c:44290-44326); h0..h2 in/out.
+ZL_D u32 zl_batch_offsets(u32 ll, u32 ml, u32 ob, u32 lane, u32& h0, u32& h1, u32& h2)
+{
+    const bool isM = ml != 0, isNew = isM && ob >= 4;
+    const u32 idx = zl_rep_idx(ll, ml, ob);
+    u32 off;
+    if (__ballot_sync(ZL_FULL, idx == 3)) {
+        // rare "rep0 - 1" code somewhere in the batch: resolve the 32 records one after the other (uniform loop)
+        off = 0;
+        u32 hh[3] = {h0, h1, h2};
+        for (u32 l = 0; l < 32; l++) {
+            const u32 lll = __shfl_sync(ZL_FULL, ll, l), lml = __shfl_sync(ZL_FULL, ml, l), lob = __shfl_sync(ZL_FULL, ob, l);
+            const u32 o = zl_rep_resolve(hh, lll, lml, lob);
+            if (l == lane) off = o;
+        }
+        h0 = hh[0]; h1 = hh[1]; h2 = hh[2];
+        return off;
+    }
+    const u32 fresh = ob - 3;                                               // meaningful on isNew lanes
+    const u32 T = zl_rept_scan(zl_rept_of(isNew, idx, lane), lane);
+    u32 E = __shfl_up_sync(ZL_FULL, T, 1);                                  // exclusive prefix: history before this record
+    if (lane == 0) E = ZL_REPT_ID;
+    // the slot of the incoming history this record reads (repeat codes and continuations): byte idx of E
+    const u32 eb = (E >> (8 * idx)) & 0xFFu;
+    const u32 fromLane = __shfl_sync(ZL_FULL, fresh, eb & 31u);
+    const u32 fromHist = (eb & 3u) == 0 ? h0 : ((eb & 3u) == 1 ? h1 : h2);
+    off = isNew ? fresh : ((eb & 0x80u) ? fromLane : fromHist);
+    // history after the batch: the inclusive prefix of lane 31
+    const u32 Lt = __shfl_sync(ZL_FULL, T, 31);
+    const u32 b0 = Lt & 0xFFu, b1 = (Lt >> 8) & 0xFFu, b2 = (Lt >> 16) & 0xFFu;
+    const u32 f0 = __shfl_sync(ZL_FULL, fresh, b0 & 31u), f1 = __shfl_sync(ZL_FULL, fresh, b1 & 31u), f2 = __shfl_sync(ZL_FULL, fresh, b2 & 31u);
+    const u32 n0 = (b0 & 0x80u) ? f0 : ((b0 & 3u) == 0 ? h0 : ((b0 & 3u) == 1 ? h1 : h2));
+    const u32 n1 = (b1 & 0x80u) ? f1 : ((b1 & 3u) == 0 ? h0 : ((b1 & 3u) == 1 ? h1 : h2));
+    const u32 n2 = (b2 & 0x80u) ? f2 : ((b2 & 3u) == 0 ? h0 : ((b2 & 3u) == 1 ? h1 : h2));
+    h0 = n0; h1 = n1; h2 = n2;
+    return off;
+}
+// inclusive warp scans of ll and ll + ml
+ZL_D void zl_batch_positions(u32 ll, u32 ml, u32 lane, u32& sl, u32& so, u32& totalL, u32& totalO)
+{
+    sl = ll; so = ll + ml;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 a = __shfl_up_sync(ZL_FULL, sl, d), b = __shfl_up_sync(ZL_FULL, so, d);
+        if ((int)lane >= d) { sl += a; so += b; }
+    }
+    totalL = __shfl_sync(ZL_FULL, sl, 31); totalO = __shfl_sync(ZL_FULL, so, 31);
+}
+// owner of flat index j: first lane whose inclusive sum `rs` exceeds j
+ZL_D u32 zl_flat_owner(u32 rs, u32 j)
+{
+    u32 k = 0;
+#pragma unroll
+    for (int st = 16; st >= 1; st >>= 1) {
+        const u32 v = __shfl_sync(ZL_FULL, rs, (k + st - 1) & 31);
+        if (v <= j) k += st;
+    }
+    return k & 31;
+}
+
 // Execute one compressed block: `out` = frame output base, `op` = frame-relative position of the block, `cap` = bytes the
 // block may still regenerate (destination room, at most one block size), `capErr` the error to report beyond it.
 // hist[3] is the repeat-offset history carried from block to block.  Returns 0 and sets `regen`, or a ZlErr.
@@ -80,70 +174,12 @@ ZL_D u32 zl_exec_block(u8* out, u32 op, u32 cap, u32 capErr, const ZlBlockHdr& h
         const u64 rec = recNext;
         const bool valid = base + lane < nrec;
         {   const u32 in = base + 32 + lane; recNext = in < nrec ? __ldcs(recs + in) : 0ull; }
-        // ---- record -> litLength, matchLength, offBase
-        u32 ll = 0, ml = 0, ob = 0;
-        if (valid) {
-            if (rec & ZL_REC_B) { ll = (u32)rec & 0xFFFFu; ml = ((u32)rec >> 16) & 0xFFFFu; ob = (u32)(rec >> 32) & 0x7FFFFFFFu; }
-            else {
-                const u32 snap = (u32)rec, c = (u32)(rec >> 32);
-                const u32 llCode = c & 63u, mlCode = (c >> 6) & 63u, aOF = (c >> 12) & 31u;
-                const u32 xl = xtab[llCode], xm = xtab[36 + mlCode];
-                const u32 aLL = xl >> 24, aML = xm >> 24;
-                ob = (1u << aOF) + zl_shr(snap, 32u - aOF);
-                ml = (xm & 0xFFFFFFu) + zl_shr(zl_shl(snap, aOF), 32u - aML);
-                ll = (xl & 0xFFFFFFu) + zl_shr(zl_shl(snap, aOF + aML), 32u - aLL);
-            }
-        }
-        // ---- repeat-offset history: offset of every record, history after the batch
+        u32 ll, ml, ob;
+        zl_lane_record(rec, valid, xtab, ll, ml, ob);
         const bool isM = ml != 0;
-        const bool isNew = isM && ob >= 4;
-        const u32 idx = (isM && ob >= 1 && ob <= 3) ? ob - 1 + (ll == 0 ? 1u : 0u) : 0u;      // 0 also for non-repeat records
-        u32 off;
-        if (__ballot_sync(ZL_FULL, idx == 3)) {
-            // rare "rep0 - 1" code somewhere in the batch: resolve the 32 records one after the other (uniform loop)
-            off = 0;
-            u32 hh[3] = {h0, h1, h2};
-            for (u32 l = 0; l < 32; l++) {
-                const u32 lll = __shfl_sync(ZL_FULL, ll, l), lml = __shfl_sync(ZL_FULL, ml, l), lob = __shfl_sync(ZL_FULL, ob, l);
-                const u32 o = zl_rep_resolve(hh, lll, lml, lob);
-                if (l == lane) off = o;
-            }
-            h0 = hh[0]; h1 = hh[1]; h2 = hh[2];
-        } else {
-            const u32 fresh = ob - 3;                                               // meaningful on isNew lanes
-            u32 T = ZL_REPT_ID;
-            if (isNew) T = 0x00010000u | 0x80u | lane;                              // (mine, h0, h1)
-            else if (idx == 1) T = 0x00020001u;                                     // (h1, h0, h2)
-            else if (idx == 2) T = 0x00010002u;                                     // (h2, h0, h1)
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const u32 A = __shfl_up_sync(ZL_FULL, T, d);
-                if ((int)lane >= d) T = zl_rept_compose(A, T);
-            }
-            u32 E = __shfl_up_sync(ZL_FULL, T, 1);                                  // exclusive prefix: history before this record
-            if (lane == 0) E = ZL_REPT_ID;
-            // the slot of the incoming history this record reads (repeat codes and continuations): byte idx of E
-            const u32 eb = (E >> (8 * idx)) & 0xFFu;
-            const u32 fromLane = __shfl_sync(ZL_FULL, fresh, eb & 31u);
-            const u32 fromHist = (eb & 3u) == 0 ? h0 : ((eb & 3u) == 1 ? h1 : h2);
-            off = isNew ? fresh : ((eb & 0x80u) ? fromLane : fromHist);
-            // history after the batch: the inclusive prefix of lane 31
-            const u32 Lt = __shfl_sync(ZL_FULL, T, 31);
-            const u32 b0 = Lt & 0xFFu, b1 = (Lt >> 8) & 0xFFu, b2 = (Lt >> 16) & 0xFFu;
-            const u32 f0 = __shfl_sync(ZL_FULL, fresh, b0 & 31u), f1 = __shfl_sync(ZL_FULL, fresh, b1 & 31u), f2 = __shfl_sync(ZL_FULL, fresh, b2 & 31u);
-            const u32 n0 = (b0 & 0x80u) ? f0 : ((b0 & 3u) == 0 ? h0 : ((b0 & 3u) == 1 ? h1 : h2));
-            const u32 n1 = (b1 & 0x80u) ? f1 : ((b1 & 3u) == 0 ? h0 : ((b1 & 3u) == 1 ? h1 : h2));
-            const u32 n2 = (b2 & 0x80u) ? f2 : ((b2 & 3u) == 0 ? h0 : ((b2 & 3u) == 1 ? h1 : h2));
-            h0 = n0; h1 = n1; h2 = n2;
-        }
-        // ---- positions: inclusive scans of ll and ll+ml
-        u32 sl = ll, so = ll + ml;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            u32 a = __shfl_up_sync(ZL_FULL, sl, d), b = __shfl_up_sync(ZL_FULL, so, d);
-            if ((int)lane >= d) { sl += a; so += b; }
-        }
-        const u32 totalL = __shfl_sync(ZL_FULL, sl, 31), totalO = __shfl_sync(ZL_FULL, so, 31);
+        const u32 off = zl_batch_offsets(ll, ml, ob, lane, h0, h1, h2);
+        u32 sl, so, totalL, totalO;
+        zl_batch_positions(ll, ml, lane, sl, so, totalL, totalO);
         const u32 litExcl = sl - ll;                 // literal bytes of earlier lanes in this batch
         const u32 dstLit = outPos + so - ll - ml;    // where this lane's literals go
         const u32 dm = dstLit + ll;                  // where this lane's match goes
@@ -157,13 +193,7 @@ ZL_D u32 zl_exec_block(u8* out, u32 op, u32 cap, u32 capErr, const ZlBlockHdr& h
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 const u32 j = j0 + 32 * u + lane;
-                u32 k = 0;                               // owner = first lane whose inclusive sum exceeds j
-#pragma unroll
-                for (int st = 16; st >= 1; st >>= 1) {
-                    const u32 v = __shfl_sync(ZL_FULL, sl, (k + st - 1) & 31);
-                    if (v <= j) k += st;
-                }
-                k &= 31;
+                const u32 k = zl_flat_owner(sl, j);
                 const u32 kDst = __shfl_sync(ZL_FULL, dstLit, k), kEx = __shfl_sync(ZL_FULL, litExcl, k);
                 act[u] = j < totalL;
                 dpos[u] = kDst + (j - kEx);
@@ -195,13 +225,7 @@ ZL_D u32 zl_exec_block(u8* out, u32 op, u32 cap, u32 capErr, const ZlBlockHdr& h
 #pragma unroll
                 for (int u = 0; u < 2; u++) {
                     const u32 j = j0 + 32 * u + lane;
-                    u32 k = 0;
-#pragma unroll
-                    for (int st = 16; st >= 1; st >>= 1) {
-                        const u32 v = __shfl_sync(ZL_FULL, rs, (k + st - 1) & 31);
-                        if (v <= j) k += st;
-                    }
-                    k &= 31;
+                    const u32 k = zl_flat_owner(rs, j);
                     const u32 kDm = __shfl_sync(ZL_FULL, dm, k), kEx = __shfl_sync(ZL_FULL, rsExcl, k);
                     const i32 kSrc = (i32)__shfl_sync(ZL_FULL, (u32)srcBeg, k);
                     act[u] = j < totalM;

@@ -4,6 +4,7 @@
 //   K3 zl_k_checksum  quad-per-frame XXH64 of the output, compared with the frame trailer
 #include "zl_dec_entropy.cuh"
 #include "zl_dec_exec.cuh"
+#include "zl_dec_large.cuh"
 #include "zl_launch.h"
 
 __constant__ ZlConstTables c_tables = {
@@ -147,6 +148,7 @@ zl_k_execute(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ in
     const ZlFrameInfo info = infos[frame];
     if (info.err) { if (lane == 0) results[frame] = (u64)0 - (u64)info.err; return; }
     const ZlFrameDesc d = descs[frame];
+    if (d.large) return;                                              // large frames: zl_dec_large.cuh
     const ZlBlockHdr* hdrs = hdrArena + d.hdrBase;
     const u8* dictContent = kDict ? dict->content : nullptr;
     const u32 dictSize = kDict ? dict->contentSize : 0u;
@@ -178,6 +180,98 @@ zl_k_execute(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ in
         results[frame] = err ? (u64)0 - (u64)err : (u64)op;
         infos[frame].err = err; infos[frame].totalOut = op;
     }
+}
+
+// ---- large frames: L1 .. L4 (zl_dec_large.cuh) ------------------------------------------------------------------------
+#define ZL_L_WARPS 4
+__device__ __forceinline__ void zl_fill_xtab(u32* xtab, u32 tid, u32 nthreads)
+{
+    for (u32 i = tid; i < ZL_XTAB_WORDS; i += nthreads)
+        xtab[i] = i < 36 ? (c_tables.llBase[i] | ((u32)c_tables.llBits[i] << 24)) : (c_tables.mlBase[i - 36] | ((u32)c_tables.mlBits[i - 36] << 24));
+}
+__global__ void __launch_bounds__(ZL_L_WARPS * 32)
+zl_k_lblock_scan(const u32* __restrict__ largeIdx, const ZlFrameDesc* __restrict__ descs, const ZlFrameInfo* __restrict__ infos,
+                 const ZlBlockHdr* __restrict__ hdrArena, const u64* __restrict__ recArena, ZlLBlock* lbArena)
+{
+    __shared__ u32 xtab[ZL_XTAB_WORDS];
+    zl_fill_xtab(xtab, threadIdx.x, ZL_L_WARPS * 32);
+    __syncthreads();
+    const u32 frame = largeIdx[blockIdx.y], b = blockIdx.x * ZL_L_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const ZlFrameInfo info = infos[frame];
+    if (info.err || b >= info.nblocks) return;
+    const ZlFrameDesc d = descs[frame];
+    const ZlBlockHdr h = hdrArena[d.hdrBase + b];
+    zl_lblock_scan(h, recArena + d.recBase + h.recOff, xtab, lane, lbArena[d.hdrBase + b]);
+}
+__global__ void __launch_bounds__(32)
+zl_k_lframe_prefix(const u32* __restrict__ largeIdx, const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, ZlLBlock* lbArena,
+                   const ZlDictDev* dict)
+{
+    const u32 frame = largeIdx[blockIdx.x];
+    if (threadIdx.x != 0) return;
+    const ZlFrameInfo info = infos[frame];
+    if (info.err) return;
+    const ZlFrameDesc d = descs[frame];
+    u32 r0 = 1, r1 = 4, r2 = 8, total = 0;                            // zstd.c:15416
+    if (dict && dict->hasEntropy) { r0 = dict->rep[0]; r1 = dict->rep[1]; r2 = dict->rep[2]; }
+    const u32 err = zl_lframe_prefix(d, info, lbArena + d.hdrBase, r0, r1, r2, &total);
+    infos[frame].err = err; infos[frame].totalOut = total;
+}
+template <bool kDict>
+__global__ void __launch_bounds__(ZL_L_WARPS * 32)
+zl_k_lblock_emit(const u32* __restrict__ largeIdx, const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos,
+                 const ZlBlockHdr* __restrict__ hdrArena, const u64* __restrict__ recArena, const u8* __restrict__ litArena,
+                 const ZlLBlock* __restrict__ lbArena, u32* parentArena, const ZlDictDev* dict)
+{
+    __shared__ u32 xtab[ZL_XTAB_WORDS];
+    zl_fill_xtab(xtab, threadIdx.x, ZL_L_WARPS * 32);
+    __syncthreads();
+    const u32 frame = largeIdx[blockIdx.y], b = blockIdx.x * ZL_L_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const ZlFrameInfo info = infos[frame];
+    if (info.err || b >= info.nblocks) return;
+    const ZlFrameDesc d = descs[frame];
+    const ZlBlockHdr h = hdrArena[d.hdrBase + b];
+    const u32 litMode = (h.flags >> 4) & 3;
+    const u8* lit = litMode == 0 ? d.src + h.srcOff : litArena + d.litBase + h.litOff;
+    const u32 err = zl_lblock_emit<kDict>(d.dst, parentArena + d.parBase, d, h, lbArena[d.hdrBase + b], lit, recArena + d.recBase + h.recOff,
+                                          kDict ? dict->content : nullptr, kDict ? dict->contentSize : 0u, xtab, lane);
+    if (err && lane == 0) infos[frame].err = err;
+}
+// one pass of pointer jumping over the bytes of the large frames; remain[pass] counts the bytes still open after it
+__global__ void __launch_bounds__(256)
+zl_k_ljump(const u32* __restrict__ largeIdx, const ZlFrameDesc* __restrict__ descs, const ZlFrameInfo* __restrict__ infos, u32* parentArena,
+           u32* remain, u32 pass)
+{
+    if (pass > 1 && remain[pass - 1] == 0) return;                    // everything was final already
+    const u32 frame = largeIdx[blockIdx.y];
+    const ZlFrameInfo info = infos[frame];
+    if (info.err) return;
+    const ZlFrameDesc d = descs[frame];
+    u32* parent = parentArena + d.parBase;
+    u8* out = d.dst;
+    u32 open = 0;
+    for (u32 p = blockIdx.x * 256 + threadIdx.x; p < info.totalOut; p += gridDim.x * 256) {
+        const u32 v = parent[p];
+        if (v >= ZL_PAR_DONE) continue;
+        const u32 pv = __ldcg(parent + v);                             // (another thread may be updating it: any value it held is valid)
+        if (pv >= ZL_PAR_DONE) {
+            if ((pv & 0xFFu) < pass) { out[p] = __ldcg(out + v); parent[p] = ZL_PAR_DONE | pass; }
+            else open++;                                               // made final in this very pass: readable after the kernel boundary
+        } else { parent[p] = pv; open++; }
+    }
+    open = __reduce_add_sync(0xFFFFFFFFu, open);
+    if ((threadIdx.x & 31) == 0 && open) atomicAdd(remain + pass, open);
+}
+__global__ void __launch_bounds__(128)
+zl_k_lfinish(const u32* __restrict__ largeIdx, u32 nLarge, ZlFrameInfo* __restrict__ infos, u64* __restrict__ results, const u32* __restrict__ remain, u32 lastPass)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nLarge) return;
+    const u32 frame = largeIdx[i];
+    u32 err = infos[frame].err;
+    if (!err && remain[lastPass] != 0) err = ZL_E_GENERIC;            // (cannot happen: ceil(log2 n) + 1 passes resolve any chain)
+    infos[frame].err = err;
+    results[frame] = err ? (u64)0 - (u64)err : (u64)infos[frame].totalOut;
 }
 
 __global__ void __launch_bounds__(128)
@@ -261,6 +355,30 @@ cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
         zl_k_execute<true><<<g2, ZL_EXEC_WARPS * 32, 0, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.results, L.nframes, L.dict);
     else
         zl_k_execute<false><<<g2, ZL_EXEC_WARPS * 32, 0, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.results, L.nframes, nullptr);
+    if (L.nLarge) {                                                   // block-parallel path for the large frames of this slice
+        const dim3 gb((L.largeMaxBlocks + ZL_L_WARPS - 1) / ZL_L_WARPS, L.nLarge);
+        zl_k_lblock_scan<<<gb, ZL_L_WARPS * 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.recArena, L.lbArena);
+        zl_k_lframe_prefix<<<L.nLarge, 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.lbArena, L.dict);
+        if (L.dict) zl_k_lblock_emit<true><<<gb, ZL_L_WARPS * 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.lbArena, L.parentArena, L.dict);
+        else zl_k_lblock_emit<false><<<gb, ZL_L_WARPS * 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.lbArena, L.parentArena, nullptr);
+        cudaMemsetAsync(L.remain, 0, (ZL_LJUMP_MAX_PASSES + 2) * sizeof(u32), st);
+        u32 gx = (u32)((L.largeMaxBytes + 255) / 256);
+        if (gx > 148u * 64u) gx = 148u * 64u;
+        const dim3 gj(gx ? gx : 1u, L.nLarge);
+        u32 pass = 1, lastPass = 0;
+        for (;;) {
+            const u32 group = pass == 1 ? 6u : 4u;                    // passes are launched in groups; the host looks at the counter in between
+            for (u32 k = 0; k < group && pass <= ZL_LJUMP_MAX_PASSES; k++, pass++)
+                zl_k_ljump<<<gj, 256, 0, st>>>(L.largeIdx, L.descs, L.infos, L.parentArena, L.remain, pass);
+            lastPass = pass - 1;
+            u32 open = 1;
+            if (cudaMemcpyAsync(L.remainHost, L.remain + lastPass, sizeof(u32), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+            if (cudaStreamSynchronize(st) != cudaSuccess) break;
+            open = *L.remainHost;
+            if (!open || pass > ZL_LJUMP_MAX_PASSES) break;
+        }
+        zl_k_lfinish<<<(L.nLarge + 127) / 128, 128, 0, st>>>(L.largeIdx, L.nLarge, L.infos, L.results, L.remain, lastPass);
+    }
     if (ev) cudaEventRecord(ev[3], st);
     if (L.verifyChecksum) {
         const u32 g3 = (L.nframes * 4 + 127) / 128;

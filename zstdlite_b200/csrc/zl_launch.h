@@ -31,6 +31,19 @@ struct ZlDictDev {
     const u8* content;     // device pointer
 };
 
+// ---- large frames (zl_dec_large.cuh) ----
+#define ZL_LARGE_FRAME_BYTES (1u << 20)      // frames that may regenerate this much take the block-parallel execute path
+#define ZL_PAR_DONE 0xFFFFFF00u
+#define ZL_LJUMP_MAX_PASSES 40
+struct ZlSymSlot { u32 kind, val; };         // symbolic history slot: kind 0..2 = incoming slot minus val, kind 3 = the constant val
+struct ZlLBlock {                            // per block of a large frame (48 B)
+    u32 regen;                               // bytes the block regenerates
+    u32 outOff;                              // frame-relative output offset (L2)
+    u32 h[3];                                // history before the block (L2)
+    ZlSymSlot t[3];                          // the block's transform of the history (L1)
+    u32 err;
+};
+
 struct ZlDecodeLaunch {          // one slice of a batch: frames [frameBase, frameBase + nframes)
     const ZlFrameDesc* descs;    // this slice's descriptors / infos / results ...
     ZlFrameInfo* infos;
@@ -48,6 +61,14 @@ struct ZlDecodeLaunch {          // one slice of a batch: frames [frameBase, fra
     u32* counters;               // this slice's {unit count, literal cursor, sequence cursor}
     u32 nframes;
     int verifyChecksum;
+    // large frames of this slice (zl_dec_large.cuh); nLarge == 0: none
+    const u32* largeIdx;         // device: indices (relative to the slice) of the large frames
+    u32 nLarge, largeMaxBlocks;  // count; largest hdrCap among them (grid bound for the warp-per-block kernels)
+    u64 largeMaxBytes;           // largest dstCap among them (grid bound for the pointer-jumping passes)
+    ZlLBlock* lbArena;    // per-block scratch, indexed like hdrArena
+    u32* parentArena;            // one u32 per output byte of the large frames
+    u32* remain;                 // device: open bytes after every pass
+    u32* remainHost;             // pinned host word for the convergence check
     const ZlDictDev* dict;       // device pointer or null
     cudaEvent_t* stageEv;        // null, or ZL_DEC_STAGES + 1 events recorded around each kernel (per-kernel timing for bench.py)
 };
