@@ -180,3 +180,69 @@ def test_damaged_frames_without_checksum_decode_like_libzstd(z, ref):
             same += 1
     assert same > 100                      # most single-bit damage lands in the Huffman streams and decodes to garbage
     assert stricter <= len(frames) // 20
+
+
+def test_large_frames_take_the_block_parallel_path(z, ref):
+    """one multi-megabyte frame with cross-block history (config 1's shape).  Frames of >= 1 MiB are
+    executed by the block-parallel kernels (parent pointers + pointer jumping); everything must stay byte-exact: levels with
+    large windows, checksums, long runs (deep copy chains), dictionaries, unknown content size, mixed batches, errors."""
+    import io
+    from zstdlite_b200 import corpus
+    from tests.gpu_util import gpu_decompress_batch
+    big = {f: corpus.make(f, 6 << 20, 31).tobytes() for f in ("text", "rdf", "rle", "lowent", "rand")}
+    frames, want = [], []
+    for fam, d in big.items():
+        for lvl, ck in ((1, False), (3, True), (19, True)):
+            if lvl == 19 and fam not in ("text", "rle"):
+                continue
+            frames.append(ref.compress(d, lvl, ck)); want.append(d)
+    # a run of one byte (offset-1 match over megabytes: the deepest possible chain) and a two-byte period
+    for d in (bytes(3 << 20), b"ab" * (1 << 20), b"x" + bytes(range(256)) * 5000):
+        frames.append(ref.compress(d, 3, True)); want.append(d)
+    # small frames in the same batch (warp-per-frame path) keep working next to large ones
+    for i in range(40):
+        d = corpus.make("text", 50000 + 1000 * i, i).tobytes()
+        frames.insert(i * 2 % len(frames), ref.compress(d, 3, i % 2 == 0)); want.insert(i * 2 % len(want), d)
+    res, outs = gpu_decompress_batch(frames, [len(w) for w in want])
+    for i, (r, o, w) in enumerate(zip(res, outs, want)):
+        assert not z.is_error(r), (i, z.error_name(r))
+        assert r == len(w) and o == w, i
+    # multi-threaded libzstd output (ZSTDMT jobs with overlap) is one ordinary frame
+    d = big["text"] + big["rdf"]
+    assert z.zstd_decompress(ref.compress(d, 3, True, num_threads=4)) == d
+    # dictionary + large frame; raw-content dictionary
+    tdict = ref.train_dict([corpus.make("text", 4000, 50 + i).tobytes() for i in range(300)], 30000)
+    for dd in (tdict, big["text"][:70000]):
+        c = ref.compress(big["text"][:3 << 20], 3, True, dict=dd)
+        assert z.zstd_decompress(c, dict=dd) == big["text"][:3 << 20]
+    # unknown content size (streamed by libzstd without a pledged size): decoded through the streaming entry point
+    L = ref.lib()
+    import ctypes as C
+    cctx = L.ZSTD_createCCtx()
+    src = big["rdf"][:2500000]
+    outb = C.create_string_buffer(L.ZSTD_compressBound(len(src)))
+    class B(C.Structure):
+        _fields_ = [("p", C.c_void_p), ("size", C.c_size_t), ("pos", C.c_size_t)]
+    ib = C.create_string_buffer(src, len(src))
+    o, i_ = B(C.cast(outb, C.c_void_p), len(outb), 0), B(C.cast(ib, C.c_void_p), len(src), 0)
+    L.ZSTD_compressStream2.restype = C.c_size_t
+    L.ZSTD_compressStream2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    assert not L.ZSTD_isError(L.ZSTD_compressStream2(cctx, C.byref(o), C.byref(i_), 0)) and i_.pos == len(src)    # ZSTD_e_continue first:
+    assert L.ZSTD_compressStream2(cctx, C.byref(o), C.byref(i_), 2) == 0                                          # the size is not in the header
+    streamed = outb.raw[:o.pos]
+    L.ZSTD_freeCCtx(cctx)
+    assert z.zstd_info(streamed)["uncompressed_size"] is None
+    assert z.zstd_decompress_stream(io.BytesIO(streamed).read) == src
+    # errors: destination too small, damaged payloads (with checksum: every damage is an error, never a crash)
+    c = ref.compress(big["text"], 3, True)
+    res, _ = gpu_decompress_batch([c], [len(big["text"]) - 1])
+    assert z.is_error(res[0])
+    rng = np.random.default_rng(8)
+    bad = []
+    for _ in range(24):
+        m = bytearray(c)
+        k = int(rng.integers(12, len(m)))
+        m[k] ^= 1 << int(rng.integers(0, 8))
+        bad.append(bytes(m))
+    res, _ = gpu_decompress_batch(bad, [len(big["text"])] * len(bad))
+    assert all(z.is_error(r) for r in res)

@@ -20,7 +20,10 @@ def main(n):
     from tests.gpu_util import gpu_decompress_batch
     rng = np.random.default_rng(2024)
     bases = []
-    for fam, size, lvl in (("text", 20000, 3), ("rdf", 30000, 1), ("lowent", 9000, 3), ("rle", 50000, 3), ("text", 200000, 19), ("text", 300, 3)):
+    sizes = (("text", 20000, 3), ("rdf", 30000, 1), ("lowent", 9000, 3), ("rle", 50000, 3), ("text", 200000, 19), ("text", 300, 3))
+    if "--large" in sys.argv:              # frames of >= 1 MiB take the block-parallel execute path (zl_dec_large.cuh)
+        sizes = (("text", 1200000, 3), ("rdf", 1500000, 1), ("rle", 2000000, 3))
+    for fam, size, lvl in sizes:
         d = corpus.make(fam, size, 5).tobytes()
         bases.append((d, ref.compress(d, lvl, True)))
         bases.append((d, ref.compress(d, lvl, False)))          # no checksum: corrupted payloads that still parse must decode identically
