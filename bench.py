@@ -258,6 +258,52 @@ def dict_leg(torch, z, args, dev):
             "size_vs_libzstd_same_dict": ours / theirs, "sampled_objects": len(range(0, n, step))}
 
 
+def large_frame_leg(torch, z, args, dev):
+    """configs[0]: zstd_serialize / zstd_unserialize of a 1e6-row data.frame (R's binary serialization restated, ~16 MB), level 3.
+    The reference compresses it into ONE frame (2 MB window, ~128 dependent blocks, num_threads = 1); the GPU decodes that
+    frame with the block-parallel large-frame path and compresses the payload as one frame of independent blocks."""
+    from oracle import ref
+    from zstdlite_b200 import corpus
+    payload = corpus.r_data_frame(args.df_rows)
+    n = len(payload)
+    t0 = time.time(); frame = ref.compress(payload, 3); t_cc = time.time() - t0
+    t0 = time.time(); back = ref.decompress(frame); t_cd = time.time() - t0
+    assert back == payload
+    src = torch.from_numpy(np.frombuffer(frame, dtype=np.uint8).copy()).to(dev)
+    dst = torch.zeros(n + 64, dtype=torch.uint8, device=dev)
+    dctx = z.zstd_dctx()
+    stream = torch.cuda.current_stream(); dctx.set_stream(stream.cuda_stream)
+    plan = z.BatchPlan([src.data_ptr()], [len(frame)], [dst.data_ptr()], [n])
+    for _ in range(2):
+        res = plan.decompress(dctx)
+    assert int(res[0]) == n and bytes(dst[:n].cpu().numpy()) == payload, "large-frame decode differs from libzstd"
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(5):
+        plan.decompress(dctx)
+    e1.record(stream); torch.cuda.synchronize()
+    ms_d = e0.elapsed_time(e1) / 5
+    # compress: the payload resident in HBM -> one frame
+    raw = torch.from_numpy(np.frombuffer(payload, dtype=np.uint8).copy()).to(dev)
+    cap = int(z._lib.lib().ZSTD_compressBound(n))
+    cdst = torch.zeros(cap + 64, dtype=torch.uint8, device=dev)
+    cctx = z.zstd_cctx(level=3); cctx.set_stream(stream.cuda_stream)
+    cplan = z.BatchPlan([raw.data_ptr()], [n], [cdst.data_ptr()], [cap])
+    for _ in range(2):
+        cres = cplan.compress(cctx)
+    csz = int(cres[0])
+    ours = bytes(cdst[:csz].cpu().numpy())
+    assert ref.decompress(ours) == payload, "GPU frame does not decode with libzstd"
+    e0.record(stream)
+    for _ in range(5):
+        cplan.compress(cctx)
+    e1.record(stream); torch.cuda.synchronize()
+    ms_c = e0.elapsed_time(e1) / 5
+    return {"rows": args.df_rows, "bytes": n, "frame_bytes_libzstd": len(frame), "frame_bytes_ours": csz, "size_vs_libzstd": csz / len(frame),
+            "decompress_GBps": n / ms_d / 1e6, "decompress_ms": ms_d, "compress_GBps": n / ms_c / 1e6, "compress_ms": ms_c,
+            "libzstd_1thread_decompress_GBps": n / t_cd / 1e9, "libzstd_1thread_compress_GBps": n / t_cc / 1e9}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -272,6 +318,8 @@ def main():
     ap.add_argument("--no-compress", action="store_true")
     ap.add_argument("--dict-objects", type=int, default=100000)
     ap.add_argument("--no-dict", action="store_true")
+    ap.add_argument("--df-rows", type=int, default=1000000)
+    ap.add_argument("--no-large", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -425,6 +473,11 @@ def main():
                 out["dict"] = dict_leg(torch, z, args, dev)
             except Exception as e:
                 out["dict"] = {"error": repr(e)}
+        if world == 1 and not args.no_large:
+            try:
+                out["large_frame"] = large_frame_leg(torch, z, args, dev)
+            except Exception as e:
+                out["large_frame"] = {"error": repr(e)}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

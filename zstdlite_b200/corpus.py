@@ -106,3 +106,40 @@ def small_objects(n, seed=4, lo=10, hi=50):
         k = int(rng.integers(lo, hi))
         out.append(b"X\n\x00\x00\x00\x03" + b"".join(names[j] + int(rng.integers(0, 1000)).to_bytes(4, "little") for j in perm[:k]))
     return out
+
+
+def r_data_frame(rows=1_000_000, seed=6):
+    """Config-1 payload: a restatement of R's binary serialization (R_pstream_binary_format, version 3,
+    src/serialize.c:53-62) of a data.frame with columns Integer (i32), Real (f64, 20 distinct values as in man/benchmark.R:19)
+    and Factor (i32 codes 1..10 with `levels` / `class` attributes), followed by the names / class / compact row.names
+    attributes.  The attribute bytes are < 1 KB of ~16 MB; the column layout is what the codec sees."""
+    import struct
+    rng = np.random.default_rng(seed)
+
+    def i32(v):
+        return struct.pack("<i", v)
+
+    def charsxp(t):
+        b = t.encode()
+        return i32(0x00040009) + i32(len(b)) + b                 # CHARSXP, UTF-8 flag
+
+    def strsxp(items):
+        return i32(16) + i32(len(items)) + b"".join(charsxp(t) for t in items)
+
+    def sym(name):
+        return i32(1) + charsxp(name)                            # SYMSXP
+
+    def attr(name, value, first=True):
+        return i32(0x402) + sym(name) + value                    # LISTSXP with tag
+
+    nil = i32(254)
+    head = b"B\n" + i32(3) + i32(0x00040301) + i32(0x00030500) + i32(5) + b"UTF-8"
+    integer = i32(13) + i32(rows) + rng.integers(1, rows + 1, size=rows).astype("<i4").tobytes()
+    real = i32(14) + i32(rows) + (rng.integers(0, 20, size=rows).astype(np.float64) / 100.0).astype("<f8").tobytes()
+    levels = ["Athens", "Barcelona", "Brussels", "Calais", "Cherbourg", "Cologne", "Copenhagen", "Geneva", "Gibraltar", "Hamburg"]
+    factor = (i32(13 | 0x300) + i32(rows) + rng.integers(1, 11, size=rows).astype("<i4").tobytes()
+              + attr("levels", strsxp(levels)) + attr("class", strsxp(["factor"])) + nil)
+    body = (i32(19 | 0x300) + i32(3) + integer + real + factor
+            + attr("names", strsxp(["Integer", "Real", "Factor"])) + attr("class", strsxp(["data.frame"]))
+            + attr("row.names", i32(13) + i32(2) + i32(-2147483648) + i32(-rows)) + nil)
+    return head + body
