@@ -76,6 +76,7 @@ size_t     ZSTD_DCtx_loadDictionary(ZSTD_DCtx* dctx, const void* dict, size_t di
 /* ---- one-shot decompression: src/raw-file.c:150,155,189; src/serialize.c:171,177,197 ---- */
 size_t             ZSTD_findFrameCompressedSize(const void* src, size_t srcSize);   /* zstd.c:41410 */
 unsigned long long ZSTD_getFrameContentSize(const void* src, size_t srcSize);       /* zstd.c:41170 */
+unsigned long long ZSTD_findDecompressedSize(const void* src, size_t srcSize);      /* zstd.c:41244; sums every frame of a stream */
 size_t ZSTD_decompressDCtx(ZSTD_DCtx* dctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize); /* zstd.c:41798 */
 
 /* ---- streaming entry points: src/raw-file-out.c:95,113; src/raw-file-in.c:102; src/serialize-*-out.c,

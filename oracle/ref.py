@@ -58,6 +58,8 @@ def lib():
         L.ZSTD_decompressDCtx.argtypes = [vp, vp, sz, vp, sz]
         L.ZSTD_decompressDCtx.restype = sz
         L.ZSTD_findFrameCompressedSize.argtypes = [vp, sz]
+        L.ZSTD_findDecompressedSize.argtypes = [vp, sz]
+        L.ZSTD_findDecompressedSize.restype = C.c_ulonglong
         L.ZSTD_findFrameCompressedSize.restype = sz
         L.ZSTD_getFrameContentSize.argtypes = [vp, sz]
         L.ZSTD_getFrameContentSize.restype = C.c_ulonglong

@@ -56,6 +56,12 @@ def test_host_only_entry_points():
     assert L.ZSTD_findFrameCompressedSize(skip, len(skip)) == 11
     d = open(os.path.join(ROOT, "tests", "golden", "sample_dict.raw"), "rb").read()
     assert z.zstd_dict_id(d) == 1895278874
+    # ZSTD_findDecompressedSize (zstd.c:41244): sums frames, skips skippable frames, trailing garbage is an error
+    assert L.ZSTD_findDecompressedSize(c, len(c)) == 172
+    assert L.ZSTD_findDecompressedSize(c + skip + c, 2 * len(c) + len(skip)) == 344
+    assert L.ZSTD_findDecompressedSize(c + b"\x00\x01", len(c) + 2) == _lib.CONTENTSIZE_ERROR
+    assert L.ZSTD_findDecompressedSize(c[:100], 100) == _lib.CONTENTSIZE_ERROR
+    assert L.ZSTD_findDecompressedSize(b"", 0) == 0
 
 
 def test_context_parameters_round_trip():

@@ -128,6 +128,32 @@ def test_compress_split_is_a_standard_multi_frame_stream(z, ref):
     assert rr == len(d) and out.raw == d
 
 
+def test_multi_frame_round_trip_through_the_package_api(z, ref):
+    """split output and concatenated streams round-trip through zstd_compress / zstd_decompress /
+    zstd_serialize / zstd_unserialize themselves (content sizes summed over all frames, one GPU batch)."""
+    from zstdlite_b200 import corpus
+    d = corpus.make("rdf", 700_000, 9).tobytes() + corpus.make("lowent", 50_001, 9).tobytes()
+    blob = z.zstd_compress(d, level=3, frame_size=65536, include_checksum=True)
+    nf = (len(d) + 65535) // 65536
+    pos = cnt = 0
+    while pos < len(blob):
+        pos += ref.lib().ZSTD_findFrameCompressedSize(blob[pos:], len(blob) - pos); cnt += 1
+    assert cnt == nf and pos == len(blob)
+    assert ref.lib().ZSTD_findDecompressedSize(blob, len(blob)) == len(d) == z._lib.lib().ZSTD_findDecompressedSize(blob, len(blob))
+    assert ref.DCtx().decompress(blob, cap=len(d), all_frames=True) == d
+    assert z.zstd_decompress(blob, all_frames=True) == d
+    assert z.zstd_decompress(blob) == d[:65536]                          # the reference's behaviour: first frame only
+    # frames written by libzstd, a skippable frame in between
+    skip = (0x184D2A50).to_bytes(4, "little") + (5).to_bytes(4, "little") + b"hello"
+    cat = ref.compress(d[:100_000], 3) + skip + ref.compress(d[100_000:300_000], 1, include_checksum=True)
+    assert z.zstd_decompress(cat, all_frames=True) == d[:300_000]
+    obj = {"Integer": list(range(2000)), "Real": [k / 100 for k in range(2000)], "Factor": ["a", "b"] * 1000, "nested": {"x": b"\x00" * 70000}}
+    assert z.zstd_unserialize(z.zstd_serialize(obj, level=3)) == obj
+    assert z.zstd_unserialize(z.zstd_serialize(obj, level=1, frame_size=16384)) == obj
+    import pickle
+    assert pickle.loads(ref.decompress(z.zstd_serialize(obj))) == obj
+
+
 def test_dictionary_compress(z, ref):
     """configs[3]: small objects with a trained dictionary (and a raw-content one).  Every GPU frame must decode with the
     reference's libzstd + the same dictionary, carry the dictionary ID, and the batch must stay within 3% of the size the

@@ -39,3 +39,12 @@ bad = [i for i in range(nframes) if res[i] != fb]
 print("bad results:", len(bad), bad[:5], [z.error_name(res[i]) for i in bad[:3]])
 out = dst[:nframes * fb].cpu().numpy().reshape(nframes, fb)
 print("bytes equal:", bool((out == data).all()))
+# per-kernel times: the batch as one slice on one stream
+d.set_profile(True)
+L = z._lib.lib()
+acc = np.zeros(4)
+plan.decompress(d)
+for it in range(iters):
+    plan.decompress(d)
+    acc += [L.zl_dctx_last_stage_ms(d._p, k) for k in range(4)]
+print("stages ms (index+literals, sequences, execute, checksum):", " ".join(f"{v:.3f}" for v in acc / iters), f"sum {acc.sum() / iters:.3f}", flush=True)

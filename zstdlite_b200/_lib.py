@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzstdlite_gpu.so")
+LIB_PATH = os.environ.get("ZSTDLITE_GPU_LIB") or os.path.join(_HERE, "libzstdlite_gpu.so")      # (override: development A/B builds)
 
 CONTENTSIZE_UNKNOWN = 2**64 - 1
 CONTENTSIZE_ERROR = 2**64 - 2
@@ -52,6 +52,7 @@ def lib():
         "ZSTD_DCtx_setParameter": (sz, [vp, C.c_int, C.c_int]), "ZSTD_DCtx_getParameter": (sz, [vp, C.c_int, C.POINTER(C.c_int)]),
         "ZSTD_DCtx_loadDictionary": (sz, [vp, vp, sz]),
         "ZSTD_findFrameCompressedSize": (sz, [vp, sz]), "ZSTD_getFrameContentSize": (C.c_ulonglong, [vp, sz]),
+        "ZSTD_findDecompressedSize": (C.c_ulonglong, [vp, sz]),
         "ZSTD_decompressDCtx": (sz, [vp, vp, sz, vp, sz]),
         "ZSTD_getFrameHeader": (sz, [C.POINTER(FrameHeader), vp, sz]), "ZSTD_getDictID_fromFrame": (C.c_uint, [vp, sz]),
         "ZSTD_getDictID_fromDict": (C.c_uint, [vp, sz]), "ZDICT_getDictID": (C.c_uint, [vp, sz]),
@@ -89,7 +90,7 @@ EXPORTED_SYMBOLS = [
     "ZSTD_isError", "ZSTD_getErrorName", "ZSTD_versionString", "ZSTD_createCCtx", "ZSTD_freeCCtx", "ZSTD_CCtx_reset",
     "ZSTD_CCtx_setParameter", "ZSTD_CCtx_getParameter", "ZSTD_CCtx_loadDictionary", "ZSTD_CCtx_setPledgedSrcSize",
     "ZSTD_compressBound", "ZSTD_compress2", "ZSTD_createDCtx", "ZSTD_freeDCtx", "ZSTD_DCtx_reset", "ZSTD_DCtx_setParameter",
-    "ZSTD_DCtx_getParameter", "ZSTD_DCtx_loadDictionary", "ZSTD_findFrameCompressedSize", "ZSTD_getFrameContentSize",
+    "ZSTD_DCtx_getParameter", "ZSTD_DCtx_loadDictionary", "ZSTD_findFrameCompressedSize", "ZSTD_getFrameContentSize", "ZSTD_findDecompressedSize",
     "ZSTD_decompressDCtx", "ZSTD_compressStream2", "ZSTD_decompressStream", "ZSTD_getFrameHeader", "ZSTD_getDictID_fromFrame", "ZSTD_getDictID_fromDict", "ZDICT_getDictID",
     "zl_decompress_batch", "zl_compress_batch", "zl_compress_split", "zl_dctx_set_stream", "zl_dctx_set_profile", "zl_cctx_set_stream",
     "zl_dctx_launch_count", "zl_cctx_launch_count", "zl_dctx_last_kernel_ms", "zl_cctx_last_kernel_ms", "zl_dctx_last_stage_ms", "zl_cctx_last_stage_ms", "zl_backend_string",

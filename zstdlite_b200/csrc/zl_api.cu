@@ -146,6 +146,24 @@ ZL_EXPORT unsigned long long ZSTD_getFrameContentSize(const void* src, size_t sr
     return h.skippable ? 0ULL : h.contentSize;
 }
 ZL_EXPORT size_t ZSTD_findFrameCompressedSize(const void* src, size_t srcSize) { return zl_host_find_frame_size(src, srcSize, nullptr); }
+// zstd.c:41244: content size of a whole stream of concatenated frames (skippable frames count as 0); SURVEY.md 8f rank 2
+ZL_EXPORT unsigned long long ZSTD_findDecompressedSize(const void* srcv, size_t srcSize)
+{
+    const u8* src = (const u8*)srcv;
+    unsigned long long total = 0;
+    while (srcSize >= 5) {                                                       // ZSTD_startingInputLength
+        if ((zl_rd32(src) & 0xFFFFFFF0u) != ZL_MAGIC_SKIP) {
+            const unsigned long long fcs = ZSTD_getFrameContentSize(src, srcSize);
+            if (fcs >= ZSTD_CONTENTSIZE_ERROR) return fcs;                       // unknown or error: reported as such
+            if (total + fcs < total) return ZSTD_CONTENTSIZE_ERROR;
+            total += fcs;
+        }
+        const size_t fs = zl_host_find_frame_size(src, srcSize, nullptr);
+        if (zl_is_error(fs)) return ZSTD_CONTENTSIZE_ERROR;
+        src += fs; srcSize -= fs;
+    }
+    return srcSize ? ZSTD_CONTENTSIZE_ERROR : total;
+}
 ZL_EXPORT unsigned ZSTD_getDictID_fromFrame(const void* src, size_t srcSize)
 {
     ZlHostFrameHeader h;
@@ -161,6 +179,7 @@ ZL_EXPORT unsigned ZDICT_getDictID(const void* dict, size_t dictSize) { return Z
 ZL_ALIAS(size_t, ZSTD_getFrameHeader, (ZSTD_frameHeader*, const void*, size_t))
 ZL_ALIAS(unsigned long long, ZSTD_getFrameContentSize, (const void*, size_t))
 ZL_ALIAS(size_t, ZSTD_findFrameCompressedSize, (const void*, size_t))
+ZL_ALIAS(unsigned long long, ZSTD_findDecompressedSize, (const void*, size_t))
 ZL_ALIAS(unsigned, ZSTD_getDictID_fromFrame, (const void*, size_t))
 ZL_ALIAS(unsigned, ZSTD_getDictID_fromDict, (const void*, size_t))
 ZL_ALIAS(unsigned, ZDICT_getDictID, (const void*, size_t))

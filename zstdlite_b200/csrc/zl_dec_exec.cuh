@@ -159,14 +159,44 @@ ZL_D u32 zl_flat_owner(u32 rs, u32 j)
     return k & 31;
 }
 
+// Flat byte-parallel copy over the (up to 32) segments of a batch, two rows of 32 bytes per step, both loads of a step before
+// its first store (4 rows and a higher occupancy were measured slower).  Lane k owns flat indices [start, start + len).  Owner of a flat index: the segments that hold bytes
+// were compacted into `seg` (x = destination - flat start, y = source - flat start); per row one REDUX ORs the start bits of the
+// segments beginning in it and a popcount up to the lane's own bit ranks the lane among them -- no per-byte search.
+template <typename LoadF>
+ZL_D void zl_flat_copy(u8* out, const uint2* seg, u32 start, u32 len, u32 total, u32 lane, u32 leMask, LoadF load)
+{
+    const u32 srow = start >> 5, sbit = len ? 1u << (start & 31u) : 0u;
+    u32 cnt = 0;
+    for (u32 j0 = 0; j0 < total; j0 += 64) {
+        const u32 r = j0 >> 5;
+        const u32 m0 = __reduce_or_sync(ZL_FULL, srow == r ? sbit : 0u);
+        const u32 m1 = __reduce_or_sync(ZL_FULL, srow == r + 1 ? sbit : 0u);
+        const u32 c0 = cnt + __popc(m0 & leMask) - 1u;
+        cnt += __popc(m0);
+        const u32 c1 = cnt + __popc(m1 & leMask) - 1u;
+        cnt += __popc(m1);
+        const u32 ja = j0 + lane, jb = ja + 32;
+        const bool aa = ja < total, ab = jb < total;
+        const uint2 sa = seg[c0 & 31u], sb = seg[c1 & 31u];
+        u32 va = 0, vb = 0;
+        if (aa) va = load(ja, sa.y);
+        if (ab) vb = load(jb, sb.y);
+        if (aa) out[ja + sa.x] = (u8)va;
+        if (ab) out[jb + sb.x] = (u8)vb;
+    }
+}
+
 // Execute one compressed block: `out` = frame output base, `op` = frame-relative position of the block, `cap` = bytes the
 // block may still regenerate (destination room, at most one block size), `capErr` the error to report beyond it.
 // hist[3] is the repeat-offset history carried from block to block.  Returns 0 and sets `regen`, or a ZlErr.
 template <bool kDict>
 ZL_D u32 zl_exec_block(u8* out, u32 op, u32 cap, u32 capErr, const ZlBlockHdr& h, const u8* __restrict__ lit, u32 rleByte, u32 litMode,
-                       const u64* __restrict__ recs, const u8* __restrict__ dict, u32 dictSize, u32 (&hist)[3], const u32* xtab, u32 lane, u32& regen)
+                       const u64* __restrict__ recs, const u8* __restrict__ dict, u32 dictSize, u32 (&hist)[3], const u32* xtab, uint2* seg, u32 lane, u32& regen)
 {
+    // `seg`: 32 x uint2 of shared memory owned by this warp -- the compacted segment table of the flat copies (below)
     const u32 nrec = h.nrec, litSize = h.litSize;
+    const u32 ltMask = (1u << lane) - 1u, leMask = 0xFFFFFFFFu >> (31u - lane);
     u32 outPos = op, litPos = 0;
     u32 h0 = hist[0], h1 = hist[1], h2 = hist[2];
     u64 recNext = lane < nrec ? __ldcs(recs + lane) : 0ull;
@@ -187,20 +217,14 @@ ZL_D u32 zl_exec_block(u8* out, u32 op, u32 cap, u32 capErr, const ZlBlockHdr& h
         if (totalL > litSize - litPos) return ZL_E_corruption_detected;
         if ((outPos - op) + totalO > cap) return capErr;
         if (__ballot_sync(ZL_FULL, isM && (off == 0 || off > dm + dictSize))) return ZL_E_corruption_detected;
-        // ---- literals: flat byte-parallel copy over the batch, two rows of 32 bytes per step (loads before stores)
-        for (u32 j0 = 0; j0 < totalL; j0 += 64) {
-            u32 dpos[2]; u32 val[2]; bool act[2];
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const u32 j = j0 + 32 * u + lane;
-                const u32 k = zl_flat_owner(sl, j);
-                const u32 kDst = __shfl_sync(ZL_FULL, dstLit, k), kEx = __shfl_sync(ZL_FULL, litExcl, k);
-                act[u] = j < totalL;
-                dpos[u] = kDst + (j - kEx);
-                val[u] = !act[u] ? 0u : (litMode == 1 ? rleByte : (u32)__ldg(lit + litPos + j));
-            }
-#pragma unroll
-            for (int u = 0; u < 2; u++) if (act[u]) out[dpos[u]] = (u8)val[u];
+        // ---- literals: one flat copy over the batch (zl_flat_copy)
+        if (totalL) {
+            const u32 ci = __popc(__ballot_sync(ZL_FULL, ll != 0) & ltMask);
+            if (ll) seg[ci].x = dstLit - litExcl;
+            __syncwarp();
+            const u8* lsrc = lit + litPos;
+            if (litMode == 1) zl_flat_copy(out, seg, litExcl, ll, totalL, lane, leMask, [&](u32, u32) { return rleByte; });
+            else zl_flat_copy(out, seg, litExcl, ll, totalL, lane, leMask, [&](u32 j, u32) { return (u32)__ldg(lsrc + j); });
         }
         __syncwarp();
         // ---- matches: rounds against the high-water mark (signed positions: negative = dictionary)
@@ -220,22 +244,14 @@ ZL_D u32 zl_exec_block(u8* out, u32 op, u32 cap, u32 capErr, const ZlBlockHdr& h
             for (int d = 1; d < 32; d <<= 1) { const u32 a = __shfl_up_sync(ZL_FULL, rs, d); if ((int)lane >= d) rs += a; }
             const u32 totalM = __shfl_sync(ZL_FULL, rs, 31);
             const u32 rsExcl = rs - fl;
-            for (u32 j0 = 0; j0 < totalM; j0 += 64) {
-                u32 dpos[2]; u32 val[2]; bool act[2];
-#pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    const u32 j = j0 + 32 * u + lane;
-                    const u32 k = zl_flat_owner(rs, j);
-                    const u32 kDm = __shfl_sync(ZL_FULL, dm, k), kEx = __shfl_sync(ZL_FULL, rsExcl, k);
-                    const i32 kSrc = (i32)__shfl_sync(ZL_FULL, (u32)srcBeg, k);
-                    act[u] = j < totalM;
-                    const u32 r = j - kEx;
-                    dpos[u] = kDm + r;
-                    const i32 sp = kSrc + (i32)r;
-                    val[u] = !act[u] ? 0u : ((kDict && sp < 0) ? (u32)dict[(i32)dictSize + sp] : (u32)out[sp]);
-                }
-#pragma unroll
-                for (int u = 0; u < 2; u++) if (act[u]) out[dpos[u]] = (u8)val[u];
+            if (totalM) {
+                const u32 ci = __popc(__ballot_sync(ZL_FULL, fl != 0) & ltMask);
+                if (fl) seg[ci] = make_uint2(dm - rsExcl, (u32)srcBeg - rsExcl);
+                __syncwarp();
+                zl_flat_copy(out, seg, rsExcl, fl, totalM, lane, leMask, [&](u32 j, u32 sd) {
+                    const i32 sp = (i32)(j + sd);
+                    return (kDict && sp < 0) ? (u32)dict[(i32)dictSize + sp] : (u32)out[sp];
+                });
             }
             // (b) ready matches that overlap their own output (offset < length): the periodic form dst[k] = src[k mod offset]
             //     only reads bytes below the match, one match at a time across the warp

@@ -133,12 +133,13 @@ zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ 
 }
 
 template <bool kDict>
-__global__ void __launch_bounds__(ZL_EXEC_WARPS * 32)
+__global__ void __launch_bounds__(ZL_EXEC_WARPS * 32, ZL_EXEC_MIN_CTAS)
 zl_k_execute(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos,
              const ZlBlockHdr* __restrict__ hdrArena, const u64* __restrict__ recArena,
              const u8* __restrict__ litArena, u64* __restrict__ results, u32 nframes, const ZlDictDev* dict)
 {
     __shared__ u32 xtab[ZL_XTAB_WORDS];
+    __shared__ uint2 segTab[ZL_EXEC_WARPS][32];
     for (u32 i = threadIdx.x; i < ZL_XTAB_WORDS; i += ZL_EXEC_WARPS * 32)
         xtab[i] = i < 36 ? (c_tables.llBase[i] | ((u32)c_tables.llBits[i] << 24)) : (c_tables.mlBase[i - 36] | ((u32)c_tables.mlBits[i - 36] << 24));
     __syncthreads();
@@ -170,7 +171,7 @@ zl_k_execute(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ in
             u32 cap = room, capErr = ZL_E_dstSize_tooSmall, regen = 0;
             if (cap > ZL_BLOCKSIZE_MAX) { cap = ZL_BLOCKSIZE_MAX; capErr = ZL_E_corruption_detected; }
             err = zl_exec_block<kDict>(d.dst, op, cap, capErr, h, lit, (h.flags >> 8) & 0xFF, litMode, recArena + d.recBase + h.recOff,
-                                       dictContent, dictSize, hist, xtab, lane, regen);
+                                       dictContent, dictSize, hist, xtab, segTab[threadIdx.x >> 5], lane, regen);
             op += regen;
         }
         __syncwarp();

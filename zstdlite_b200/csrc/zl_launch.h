@@ -5,6 +5,9 @@
 
 #define ZL_QUADS_PER_WARP 8
 #define ZL_EXEC_WARPS 4
+#ifndef ZL_EXEC_MIN_CTAS
+#define ZL_EXEC_MIN_CTAS 9
+#endif
 #define ZL_DEC_STAGES 4      // (index +) literals, sequences, execute, checksum
 #define ZL_NORM_SLOTS 16384  // resident quads of one sequence-kernel launch the normalized-count scratch has room for
 #define ZL_DEC_LANES 8                       // internal streams of the decode slice pipeline
