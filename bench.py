@@ -9,7 +9,8 @@ One JSON line on stdout (rank 0).  `value`  = whole-job GB/s of uncompressed byt
 `e2e` = same metric through the C ABI with pinned HOST buffers (H2D of the frames and D2H of the output inside the
 timed region); `roofline` = dominant kernel against the measured HBM copy bandwidth; `cpu_baseline` = the reference's
 libzstd, frame-parallel on all host cores, on a bounded sample of the same frames; `compress` = the level-1/level-3
-compressor on configs[2]'s 128 KiB slabs (reported beside the headline; BASELINE.json's metric is "decompress+compress").
+compressor on configs[2] (4 GiB per GPU as 128 KiB frames, made on the device; reported beside the headline at every N;
+BASELINE.json's metric is "decompress+compress").
 Multi-GPU: frames are independent, so every rank decodes its own 16,384-frame shard (weak scaling, no collective on
 the data path; barrier + max-over-ranks timing only).
 
@@ -38,19 +39,17 @@ def log(*a):
 
 
 def make_corpus(nframes, frame_bytes, level=3, pool=64, seed_shift=0):
-    """-> (raw [nframes, frame_bytes] uint8, list of compressed frames). Distinct frames are compressed once."""
+    """-> (raw [nframes, frame_bytes] uint8, list of compressed frames).  Every frame is distinct (rotated copies of `pool`
+    frames per family) and the families are interleaved by a fixed permutation; the frames are compressed by the reference's
+    libzstd on all host cores (oracle/cpu_bench.c) before any timed region."""
     from zstdlite_b200 import corpus
-    from oracle import ref
-    data, fams = corpus.mixed_frames(nframes, frame_bytes, mix=MIX, pool=pool)
-    if seed_shift:
-        data = np.roll(data, seed_shift, axis=0)
-    cache, frames = {}, []
-    for i in range(nframes):
-        key = data[i].tobytes()
-        c = cache.get(key)
-        if c is None:
-            c = cache[key] = ref.compress(key, level)
-        frames.append(c)
+    from oracle import cpubench
+    data, fams = corpus.mixed_frames(nframes, frame_bytes, mix=MIX, pool=pool, rotate=True)
+    data = data[np.random.default_rng(20261017 + seed_shift).permutation(nframes)]
+    bound = frame_bytes + (frame_bytes >> 8) + 64
+    fs = cpubench.FrameSet(data.reshape(-1), [frame_bytes] * nframes)
+    _, res, dst, doffs = cpubench.run("compress", fs, [bound] * nframes, os.cpu_count() or 1, level=level)
+    frames = [dst[int(o):int(o) + int(r)].tobytes() for o, r in zip(doffs, res)]
     return data, frames
 
 
@@ -155,13 +154,13 @@ def workload_config(args, world):
             "cache": "working set (compressed in + 1 GiB out per step) exceeds the 126 MB L2; no explicit flush"}
 
 
-def compress_leg(torch, z, args, dev):
-    """configs[2] shape at reduced count: 128 KiB slabs, levels 1 and 3, device-resident; ratio vs libzstd on the same slabs."""
-    from oracle import ref
+def compress_leg(torch, dist, z, args, dev, rank, world):
+    """configs[2]: a raw buffer of `--compress-frames` x 128 KiB slabs per GPU (default 32,768 = 4 GiB), made on the device, every
+    slab an independent frame at levels 1 and 3, device-resident; all ranks run it (weak scaling, max-over-ranks time).  Rank 0
+    checks a sample of frames through the reference's libzstd and compares sizes with libzstd on the same slabs."""
     from zstdlite_b200 import corpus
     n, fb = args.compress_frames, 131072
-    data, fams = corpus.mixed_frames(n, fb, mix=MIX, pool=32)
-    src = torch.from_numpy(data.reshape(-1)).to(dev)
+    src, pools, meta = corpus.device_mixed_slabs(n, fb, MIX, index=11 + rank, device=dev)
     bound = int(z._lib.lib().ZSTD_compressBound(fb))
     slot = (bound + 255) // 256 * 256
     dst = torch.zeros(n * slot + 64, dtype=torch.uint8, device=dev)
@@ -173,6 +172,8 @@ def compress_leg(torch, z, args, dev):
         for _ in range(2):
             res = plan.compress(cctx)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         cctx.set_stream(torch.cuda.current_stream().cuda_stream)
         t0.record()
@@ -181,25 +182,30 @@ def compress_leg(torch, z, args, dev):
             res = plan.compress(cctx)
         t1.record(); torch.cuda.synchronize()
         ms = t0.elapsed_time(t1) / iters
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        if rank != 0:
+            continue
         sizes = np.array(list(res), dtype=np.int64)
-        assert not any(z.is_error(int(s)) for s in sizes[:64])
+        assert not any(z.is_error(int(s)) for s in sizes), "compress errors"
         csize = int(sizes.sum())
-        # reference ratio on the same slabs (distinct slabs only) and a round-trip spot check through libzstd
-        cache = {}
-        refsize = 0
-        for i in range(n):
-            k = data[i].tobytes()
-            if k not in cache:
-                cache[k] = len(ref.compress(k, lvl))
-            refsize += cache[k]
-        host = dst.cpu().numpy()
-        for i in range(0, n, max(1, n // 16)):
-            assert ref.decompress(host[i * slot:i * slot + int(sizes[i])].tobytes()) == data[i].tobytes(), "GPU frame does not round-trip through libzstd"
+        # a sample of frames: round trip through libzstd and libzstd's own size for the same slab at the same level
+        from oracle import ref
+        ours = theirs = 0
+        for i in range(0, n, max(1, n // 128)):
+            fam, row, shift = meta[i]
+            want = np.roll(pools[fam][row], shift).tobytes()
+            frame = dst[i * slot:i * slot + int(sizes[i])].cpu().numpy().tobytes()
+            assert ref.decompress(frame) == want, "GPU frame does not round-trip through libzstd"
+            ours += len(frame); theirs += len(ref.compress(want, lvl))
         L = z._lib.lib()
-        out[f"level{lvl}"] = {"GBps": n * fb / ms / 1e6, "ms": ms, "ratio": n * fb / csize, "ratio_libzstd": n * fb / refsize,
-                              "ratio_vs_libzstd": (n * fb / csize) / (n * fb / refsize), "kernel_ms": cctx.last_kernel_ms,
+        out[f"level{lvl}"] = {"GBps": world * n * fb / ms / 1e6, "ms": ms, "ratio": n * fb / csize, "size_vs_libzstd": ours / theirs,
+                              "size_vs_libzstd_how": f"{len(range(0, n, max(1, n // 128)))} sampled frames, libzstd at the same level on the same slabs",
+                              "kernel_ms": cctx.last_kernel_ms,
                               "stages_ms": {nm: L.zl_cctx_last_stage_ms(cctx._p, k) for k, nm in enumerate(("match", "parse", "literals", "sequences", "plan+assemble"))},
-                              "frames": n, "frame_bytes": fb}
+                              "frames_per_gpu": n, "frame_bytes": fb, "n_gpus": world}
     return out
 
 
@@ -314,7 +320,7 @@ def main():
     ap.add_argument("--frame-bytes", type=int, default=65536)
     ap.add_argument("--cpu-frames", type=int, default=2048, help="frames in the bounded CPU sample")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--compress-frames", type=int, default=4096)
+    ap.add_argument("--compress-frames", type=int, default=32768)
     ap.add_argument("--no-compress", action="store_true")
     ap.add_argument("--dict-objects", type=int, default=100000)
     ap.add_argument("--no-dict", action="store_true")
@@ -421,6 +427,17 @@ def main():
     value = total_bytes * args.steps / ms_total / 1e6
     e2e_value = total_bytes * e2e_steps / ms_e2e / 1e6
 
+    # ---- compress leg (configs[2]); every rank takes part, so it runs before rank 0 goes on alone
+    comp = None
+    if not args.no_compress:
+        del hsrc, hdst, hplan
+        try:
+            comp = compress_leg(torch, dist, z, args, dev, rank, world)
+        except Exception as e:                                          # the headline is the decode arm; report, don't hide
+            if world > 1:
+                raise
+            comp = {"error": repr(e)}
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -463,11 +480,8 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
                                    "sample": f"{len(sample)} of the {n} frames (every {step}th, same family mix), best of {passes} passes, "
                                              f"oracle/_ref libzstd 1.5.6, one DCtx per thread"}
-        if world == 1 and not args.no_compress and hasattr(z._lib.lib(), "zl_compress_batch"):
-            try:
-                out["compress"] = compress_leg(torch, z, args, dev)
-            except Exception as e:                                      # the headline is the decode arm; report, don't hide
-                out["compress"] = {"error": repr(e)}
+        if comp is not None:
+            out["compress"] = comp
         if world == 1 and not args.no_dict:
             try:
                 out["dict"] = dict_leg(torch, z, args, dev)

@@ -24,33 +24,10 @@ def z():
     return zz
 
 
-def _device_corpus(nslabs, mix, pool=48):
-    """-> (device tensor [nslabs, FB] uint8, host pool {family: array [pool, FB]}, per-slab (family, pool row, shift))."""
-    import torch
-    from zstdlite_b200 import corpus
-    out = torch.empty((nslabs, FB), dtype=torch.uint8, device="cuda")
-    pools, meta = {}, []
-    start = 0
-    col = torch.arange(FB, device="cuda", dtype=torch.int64)
-    for k, (fam, frac) in enumerate(mix):
-        cnt = nslabs - start if k == len(mix) - 1 else int(round(nslabs * frac))
-        base = corpus.make(fam, pool * FB, index=11).reshape(pool, FB)
-        pools[fam] = base
-        dbase = torch.from_numpy(base.copy()).cuda()
-        for c0 in range(0, cnt, 1024):
-            c1 = min(cnt, c0 + 1024)
-            j = torch.arange(c0, c1, device="cuda", dtype=torch.int64)
-            row, shift = j % pool, (j // pool) * 13 % FB
-            idx = (col[None, :] - shift[:, None]) % FB                         # np.roll(slab, shift)
-            out[start + c0:start + c1] = torch.gather(dbase[row], 1, idx)
-        meta += [(fam, j % pool, (j // pool) * 13 % FB) for j in range(cnt)]
-        start += cnt
-    return out, pools, meta
-
-
 def _round_trip(z, ref, nslabs, mix, level, checksum):
     import torch
-    src, pools, meta = _device_corpus(nslabs, mix)
+    from zstdlite_b200 import corpus
+    src, pools, meta = corpus.device_mixed_slabs(nslabs, FB, mix)
     L = z._lib.lib()
     bound = int(L.ZSTD_compressBound(FB))
     slot = (bound + 255) // 256 * 256

@@ -22,6 +22,12 @@ for i in range(nframes):
     frames.append(cache[k])
 csz = sum(len(f) for f in frames)
 print(f"corpus {nframes} x {fb}: ratio {nframes*fb/csz:.3f}, prep {time.time()-t0:.1f}s", flush=True)
+order = os.environ.get("PROBE_ORDER", "grouped")          # grouped (by family) | shuffled | sorted (by compressed size)
+if order != "grouped":
+    perm = np.random.default_rng(1).permutation(nframes)
+    if order == "sorted":
+        perm = np.argsort([-len(f) for f in frames], kind="stable")
+    frames = [frames[i] for i in perm]; data = data[perm]
 sizes = [len(f) for f in frames]
 offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
 src = torch.from_numpy(np.frombuffer(b"".join(frames), dtype=np.uint8).copy()).cuda()

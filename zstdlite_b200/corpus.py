@@ -75,11 +75,12 @@ def make(family, nbytes, index=0):
     return _GEN[family](rng, int(nbytes))
 
 
-def mixed_frames(nframes, frame_bytes, mix=(("text", 0.4), ("rdf", 0.4), ("lowent", 0.1), ("rand", 0.1)), pool=64):
+def mixed_frames(nframes, frame_bytes, mix=(("text", 0.4), ("rdf", 0.4), ("lowent", 0.1), ("rand", 0.1)), pool=64, rotate=False):
     """Config-2/3 style corpus: returns (uint8 array [nframes, frame_bytes], family name per frame).
 
     To keep generation fast, each family is generated as `pool` distinct frames and tiled; every
     frame is still decoded/encoded independently so throughput is unaffected by the repetition.
+    rotate=True rotates the k-th copy of a pool frame by 24*k bytes, so that all frames differ.
     """
     fams = []
     out = np.empty((nframes, frame_bytes), dtype=np.uint8)
@@ -89,7 +90,7 @@ def mixed_frames(nframes, frame_bytes, mix=(("text", 0.4), ("rdf", 0.4), ("lowen
         npool = min(pool, max(cnt, 1))
         base = make(fam, npool * frame_bytes, index=7).reshape(npool, frame_bytes)
         for j in range(cnt):
-            out[start + j] = base[j % npool]
+            out[start + j] = np.roll(base[j % npool], (j // npool) * 24 % frame_bytes) if rotate else base[j % npool]
         fams += [fam] * cnt
         start += cnt
     return out, fams
@@ -143,3 +144,29 @@ def r_data_frame(rows=1_000_000, seed=6):
             + attr("names", strsxp(["Integer", "Real", "Factor"])) + attr("class", strsxp(["data.frame"]))
             + attr("row.names", i32(13) + i32(2) + i32(-2147483648) + i32(-rows)) + nil)
     return head + body
+
+
+def device_mixed_slabs(nslabs, slab_bytes, mix, pool=48, index=11, device="cuda"):
+    """Config-3/5 style corpus made ON THE DEVICE (torch is plumbing here): `pool` distinct slabs per family are generated on
+    the host, uploaded, and every copy is rotated by a different number of bytes, so that no two slabs are equal.
+    -> (uint8 tensor [nslabs, slab_bytes], {family: host array [pool, slab_bytes]}, per-slab (family, pool row, shift));
+    slab i equals np.roll(pools[family][row], shift)."""
+    import torch
+    out = torch.empty((nslabs, slab_bytes), dtype=torch.uint8, device=device)
+    pools, meta = {}, []
+    start = 0
+    col = torch.arange(slab_bytes, device=device, dtype=torch.int64)
+    for k, (fam, frac) in enumerate(mix):
+        cnt = nslabs - start if k == len(mix) - 1 else int(round(nslabs * frac))
+        base = make(fam, pool * slab_bytes, index=index).reshape(pool, slab_bytes)
+        pools[fam] = base
+        dbase = torch.from_numpy(base.copy()).to(device)
+        for c0 in range(0, cnt, 1024):
+            c1 = min(cnt, c0 + 1024)
+            j = torch.arange(c0, c1, device=device, dtype=torch.int64)
+            row, shift = j % pool, (j // pool) * 13 % slab_bytes
+            idx = (col[None, :] - shift[:, None]) % slab_bytes                     # np.roll(slab, shift)
+            out[start + c0:start + c1] = torch.gather(dbase[row], 1, idx)
+        meta += [(fam, j % pool, (j // pool) * 13 % slab_bytes) for j in range(cnt)]
+        start += cnt
+    return out, pools, meta

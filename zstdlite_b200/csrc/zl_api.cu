@@ -3,6 +3,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <new>
+#include <algorithm>
+#include <vector>
 #include "../../include/zstdlite_gpu.h"
 #include "zl_host.h"
 #include "zl_plan.h"
@@ -406,12 +408,36 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         if (nslices < 1) nslices = 1;
     }
     if (nslices > 1 && !zl_dctx_lanes(c)) nslices = 1;
+    // Scheduling order (device buffers): the frames are handed to the kernels by decreasing compressed size -- longest work
+    // first, and frames of one kind next to each other, so that the quads of a warp and the warps of a CTA finish together.
+    // Measured on config 2 with the families interleaved: 112 -> 143 GB/s.  order[pos] = caller's index of the frame at
+    // position `pos`; slices are ranges of positions.  Host buffers keep the caller's order: their slices are contiguous runs
+    // of host memory for the copies, and the end-to-end time is bound by PCIe and the chain latency of one frame, not by
+    // balance (measured: sorting inside the slices 40.3 -> 39.8 GB/s).
+    std::vector<u32> order(n), tmpOrder;
+    for (size_t i = 0; i < n; i++) order[i] = (u32)i;
+    size_t maxSrc = 1;
+    for (size_t i = 0; i < n; i++) if (srcSize[i] > maxSrc) maxSrc = srcSize[i];
+    int keyShift = 0;
+    while ((maxSrc >> keyShift) >= 4096) keyShift++;
+    // stable counting sort of order[a, b) by decreasing size class (4,096 classes): O(n), ~50 us for 16,384 frames
+    auto sortRange = [&](size_t a, size_t b) {
+        if (b - a < 2) return;
+        u32 cnt[4097] = {0};
+        for (size_t i = a; i < b; i++) cnt[4095 - (srcSize[order[i]] >> keyShift)]++;
+        u32 run = 0;
+        for (u32 k = 0; k < 4096; k++) { const u32 t = cnt[k]; cnt[k] = run; run += t; }
+        tmpOrder.resize(b - a);
+        for (size_t i = a; i < b; i++) tmpOrder[cnt[4095 - (srcSize[order[i]] >> keyShift)]++] = order[i];
+        std::copy(tmpOrder.begin(), tmpOrder.end(), order.begin() + (ptrdiff_t)a);
+    };
+    if (dev) sortRange(0, n);
     std::vector<size_t> cut(nslices + 1, n);
     {
         cut[0] = 0;
         u64 acc = 0; size_t k = 1;
         for (size_t i = 0; i < n && k < nslices; i++) {
-            acc += dstCap[i];
+            acc += dstCap[order[i]];
             if (acc * nslices >= contentTotal * k) cut[k++] = i + 1;
         }
     }
@@ -426,16 +452,26 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         }
         if (!c->dSrc.reserve(srcTotal + 64) || !c->dDst.reserve(dstTotal + 64)) return ZL_ERROR(memory_allocation);
     }
-    u64 lit = 0, rec = 0, hdr = 0, par = 0;
-    size_t sr = 0, dr = 0, nLargeTotal = 0;
-    for (size_t i = 0; i < n; i++) {
-        ZlFrameDesc& d = hd[i];
-        if (dev) { d.src = (const u8*)src[i]; d.dst = (u8*)dst[i]; }
-        else {
+    std::vector<u32> srunOf, drunOf;                 // copy run of every frame (host buffers), by caller's index
+    if (!dev) {
+        srunOf.resize(n); drunOf.resize(n);
+        size_t sr = 0, dr = 0;
+        for (size_t i = 0; i < n; i++) {
             while (sr + 1 < sruns.size() && i >= sruns[sr + 1].first) sr++;
             while (dr + 1 < druns.size() && i >= druns[dr + 1].first) dr++;
-            d.src = c->dSrc.as<u8>() + sruns[sr].devOff + ((const u8*)src[i] - sruns[sr].hbase);
-            d.dst = c->dDst.as<u8>() + druns[dr].devOff + ((const u8*)dst[i] - druns[dr].hbase);
+            srunOf[i] = (u32)sr; drunOf[i] = (u32)dr;
+        }
+    }
+    u64 lit = 0, rec = 0, hdr = 0, par = 0;
+    size_t nLargeTotal = 0;
+    for (size_t pos = 0; pos < n; pos++) {
+        const size_t i = order[pos];
+        ZlFrameDesc& d = hd[pos];
+        if (dev) { d.src = (const u8*)src[i]; d.dst = (u8*)dst[i]; }
+        else {
+            const ZlRun& rs = sruns[srunOf[i]]; const ZlRun& rd = druns[drunOf[i]];
+            d.src = c->dSrc.as<u8>() + rs.devOff + ((const u8*)src[i] - rs.hbase);
+            d.dst = c->dDst.as<u8>() + rd.devOff + ((const u8*)dst[i] - rd.hbase);
         }
         d.srcSize = (u32)srcSize[i]; d.dstCap = (u32)dstCap[i];
         zl_plan_frame(d.srcSize, d.dstCap, worst, &d.litCap, &d.recCap, &d.hdrCap);
@@ -516,7 +552,7 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         c->lastStageMs[k] = t;
     }
     const u64* hr = c->hResults.as<u64>();
-    for (size_t i = 0; i < n; i++) result[i] = (size_t)hr[i];
+    for (size_t pos = 0; pos < n; pos++) result[order[pos]] = (size_t)hr[pos];
     return 0;
 }
 
