@@ -335,6 +335,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
+    # stdout carries exactly ONE JSON line: anything libraries print to fd 1 meanwhile (NCCL's version banner) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -492,7 +495,7 @@ def main():
                 out["large_frame"] = large_frame_leg(torch, z, args, dev)
             except Exception as e:
                 out["large_frame"] = {"error": repr(e)}
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=real_stdout, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
