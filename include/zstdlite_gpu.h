@@ -96,6 +96,24 @@ unsigned ZSTD_getDictID_fromFrame(const void* src, size_t srcSize);             
 unsigned ZSTD_getDictID_fromDict(const void* dict, size_t dictSize);                /* zstd.c:42225 */
 unsigned ZDICT_getDictID(const void* dict, size_t dictSize);                        /* zstd.c:49974 */
 
+/* ---- dictionary training on the GPU: src/dictionaries.c:161 (ZDICT_trainFromBuffer), :199 (optim = TRUE),
+ *      :202-205 (error reporting).  fastCOVER's method with its default parameters (d = 8, f = 20, 4 values of k in [50, 2000],
+ *      75/25 split); every candidate is finished with entropy tables and scored by compressing the test samples on the GPU.
+ *      The dictionary is a standard Zstandard dictionary (magic, ID, Huffman + FSE tables, repeat offsets, content). ---- */
+typedef struct { int compressionLevel; unsigned notificationLevel; unsigned dictID; } ZDICT_params_t;           /* src/zstd/zstd.h (zdict section) */
+typedef struct {
+    unsigned k, d, steps, nbThreads;
+    double splitPoint;
+    unsigned shrinkDict, shrinkDictMaxRegression;
+    ZDICT_params_t zParams;
+} ZDICT_cover_params_t;
+size_t ZDICT_trainFromBuffer(void* dictBuffer, size_t dictBufferCapacity, const void* samplesBuffer,
+                             const size_t* samplesSizes, unsigned nbSamples);                                  /* zstd.c:50979 */
+size_t ZDICT_optimizeTrainFromBuffer_cover(void* dictBuffer, size_t dictBufferCapacity, const void* samplesBuffer,
+                                           const size_t* samplesSizes, unsigned nbSamples, ZDICT_cover_params_t* parameters); /* zstd.c:46957 */
+unsigned    ZDICT_isError(size_t code);                      /* zstd.c:50101 */
+const char* ZDICT_getErrorName(size_t code);                 /* zstd.c:50103 */
+
 /* ---- batch extension (needed because src/raw-file.c:150-189 decodes one frame per call and
  *      R's length() is 32-bit).  Arrays live in HOST memory; when ptrs_are_device != 0 the src[i] / dst[i]
  *      pointers themselves are DEVICE pointers (inputs/outputs already resident in HBM).  Each item is

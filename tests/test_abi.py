@@ -94,3 +94,8 @@ def test_compute_calls_fail_loudly_without_a_gpu():
         z.zstd_decompress(c)
     with pytest.raises(z.ZstdError):
         z.zstd_compress(b"no silent CPU path" * 100)
+    with pytest.raises(z.ZstdError, match="Training error"):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            z.zstd_train_dict_compress([bytes([i % 251] * 40) for i in range(100)], 1024)

@@ -26,6 +26,15 @@ class OutBuffer(C.Structure):
 ZSTD_e_continue, ZSTD_e_flush, ZSTD_e_end = 0, 1, 2
 
 
+class ZdictParams(C.Structure):
+    _fields_ = [("compressionLevel", C.c_int), ("notificationLevel", C.c_uint), ("dictID", C.c_uint)]
+
+
+class CoverParams(C.Structure):
+    _fields_ = [("k", C.c_uint), ("d", C.c_uint), ("steps", C.c_uint), ("nbThreads", C.c_uint), ("splitPoint", C.c_double),
+                ("shrinkDict", C.c_uint), ("shrinkDictMaxRegression", C.c_uint), ("zParams", ZdictParams)]
+
+
 class FrameHeader(C.Structure):
     _fields_ = [("frameContentSize", C.c_ulonglong), ("windowSize", C.c_ulonglong), ("blockSizeMax", C.c_uint),
                 ("frameType", C.c_int), ("headerSize", C.c_uint), ("dictID", C.c_uint), ("checksumFlag", C.c_uint),
@@ -68,6 +77,10 @@ def lib():
         "zl_compress_split": (sz, [vp, vp, sz, vp, sz, sz, psz, C.c_int]),
         "zl_cctx_set_stream": (sz, [vp, vp]), "zl_cctx_launch_count": (C.c_ulonglong, [vp]), "zl_cctx_last_kernel_ms": (C.c_double, [vp]),
         "zl_cctx_last_stage_ms": (C.c_double, [vp, C.c_int]),
+        # dictionary training
+        "ZDICT_trainFromBuffer": (sz, [vp, sz, vp, psz, C.c_uint]),
+        "ZDICT_optimizeTrainFromBuffer_cover": (sz, [vp, sz, vp, psz, C.c_uint, C.POINTER(CoverParams)]),
+        "ZDICT_isError": (C.c_uint, [sz]), "ZDICT_getErrorName": (C.c_char_p, [sz]),
         # streaming entry points (whole-frame buffering over the same engine)
         "ZSTD_compressStream2": (sz, [vp, C.POINTER(OutBuffer), C.POINTER(InBuffer), C.c_int]),
         "ZSTD_decompressStream": (sz, [vp, C.POINTER(OutBuffer), C.POINTER(InBuffer)]),
@@ -92,6 +105,7 @@ EXPORTED_SYMBOLS = [
     "ZSTD_compressBound", "ZSTD_compress2", "ZSTD_createDCtx", "ZSTD_freeDCtx", "ZSTD_DCtx_reset", "ZSTD_DCtx_setParameter",
     "ZSTD_DCtx_getParameter", "ZSTD_DCtx_loadDictionary", "ZSTD_findFrameCompressedSize", "ZSTD_getFrameContentSize", "ZSTD_findDecompressedSize",
     "ZSTD_decompressDCtx", "ZSTD_compressStream2", "ZSTD_decompressStream", "ZSTD_getFrameHeader", "ZSTD_getDictID_fromFrame", "ZSTD_getDictID_fromDict", "ZDICT_getDictID",
+    "ZDICT_trainFromBuffer", "ZDICT_optimizeTrainFromBuffer_cover", "ZDICT_isError", "ZDICT_getErrorName",
     "zl_decompress_batch", "zl_compress_batch", "zl_compress_split", "zl_dctx_set_stream", "zl_dctx_set_profile", "zl_cctx_set_stream",
     "zl_dctx_launch_count", "zl_cctx_launch_count", "zl_dctx_last_kernel_ms", "zl_cctx_last_kernel_ms", "zl_dctx_last_stage_ms", "zl_cctx_last_stage_ms", "zl_backend_string",
 ]

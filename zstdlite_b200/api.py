@@ -303,6 +303,53 @@ def zstd_dict_id(x):
     return int(did)
 
 
+def zstd_train_dict_compress(samples, size=100000, optim=False, optim_shrink_allow=0):
+    """zstd_train_dict_compress(samples, size, optim, optim_shrink_allow)  (R/dictionaries.R:65, src/dictionaries.c:75-208):
+    `samples` is a list of bytes-like objects (each >= 8 bytes) or strings; returns a Zstandard dictionary of at most `size`
+    bytes, trained on the GPU (csrc/zl_dict_train.cuh)."""
+    L = _lib.lib()
+    if not isinstance(samples, (list, tuple)):
+        raise ZstdError("zstd_train_dictionary(): samples must be provided as a list of raw vectors or character strings")
+    if len(samples) == 0:
+        raise ZstdError("zstd_train_dictionary(): No samples provided")
+    bufs = []
+    for s in samples:
+        if isinstance(s, str):
+            s = s.encode("utf-8")
+        else:
+            s = bytes(memoryview(s).cast("B"))
+            if len(s) < 8:
+                raise ZstdError("zstd_train_dictionary(): When samples are raw vectors, all vector lengths must be >= 8 bytes")
+        bufs.append(s)
+    total = sum(len(b) for b in bufs)
+    size = int(size)
+    if total < 100 * size:                                               # src/dictionaries.c:104-106
+        warnings.warn("zstd_train_dictionary() ZSTD documentation recommends training data size 100x dictionary size.\n"
+                      "Only supplied with %.1fx" % (total / max(size, 1)))
+    blob = b"".join(bufs)
+    sizes = (C.c_size_t * len(bufs))(*[len(b) for b in bufs])
+    dst = C.create_string_buffer(max(1, size))
+    if not optim:
+        r = L.ZDICT_trainFromBuffer(dst, size, blob, sizes, len(bufs))
+    else:
+        par = _lib.CoverParams()
+        if int(optim_shrink_allow) > 0:
+            par.shrinkDict, par.shrinkDictMaxRegression = 1, int(optim_shrink_allow)
+        r = L.ZDICT_optimizeTrainFromBuffer_cover(dst, size, blob, sizes, len(bufs), C.byref(par))
+    if L.ZDICT_isError(r):
+        raise ZstdError("zstd_train_dictionary() Training error %s" % L.ZDICT_getErrorName(r).decode())
+    return dst.raw[:r]
+
+
+def zstd_train_dict_serialize(samples, size=100000, optim=False, optim_shrink_allow=0):
+    """zstd_train_dict_serialize(samples, ...)  (R/dictionaries.R:87-93): every sample object is serialized first (pickle here,
+    R's serialize() in the reference), for use with zstd_serialize() / zstd_unserialize()."""
+    import pickle
+    if not isinstance(samples, (list, tuple)):
+        raise ZstdError("zstd_train_dict_serialize(): samples must be a list")
+    return zstd_train_dict_compress([pickle.dumps(x, protocol=5) for x in samples], size, optim, optim_shrink_allow)
+
+
 def zstd_version():
     return _lib.lib().ZSTD_versionString().decode()
 

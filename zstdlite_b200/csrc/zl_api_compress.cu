@@ -34,6 +34,7 @@ struct ZSTD_CCtx_s {
     std::vector<u8> sIn, sOut;
     size_t sOutPos = 0;
     bool sFlushing = false;
+    u32* statsDev = nullptr;               // set by the dictionary trainer: parse only, statistics summed here (zl_dict_train.cuh)
 };
 
 static bool g_constReady = false;
@@ -245,7 +246,7 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
     L.M = c->dM.as<u32>(); L.slotM = slotM; L.recs = c->dRecs.as<u64>(); L.slotRec = slotRec; L.lit = c->dLit.as<u8>(); L.slotLit = slotLit;
     L.hist = c->dHist.as<u32>(); L.metas = c->dMetas.as<ZlEncBlockMeta>(); L.outs = c->dOuts.as<ZlEncBlockOut>(); L.plans = c->dPlans.as<ZlEncBlockPlan>();
     L.streamCapWords = streamCapWords; L.streamWordsPerBlock = streamWordsPerBlock; L.seqCapWords = seqCapWords;
-    L.results = c->dResults.as<u64>() + f0; L.xxh = xxh; L.stageEv = timeIt ? c->stageEv : nullptr;
+    L.results = c->dResults.as<u64>() + f0; L.xxh = xxh; L.stageEv = timeIt ? c->stageEv : nullptr; L.stats = c->statsDev;
     cudaError_t e = zl_launch_encode(L, st);
     c->launches += 6;
     if (e != cudaSuccess) { fprintf(stderr, "zstdlite_gpu: kernel launch failed: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
@@ -433,3 +434,5 @@ ZL_EXPORT size_t zl_compress_split(ZSTD_CCtx* c, void* dst, size_t dstCap, const
     if (cudaStreamSynchronize(st) != cudaSuccess) { (void)cudaGetLastError(); return ZL_ERROR(GENERIC); }
     return total;
 }
+
+#include "zl_dict_train.cuh"

@@ -585,6 +585,32 @@ zl_k_gather(const u8* const* __restrict__ srcs, const u64* __restrict__ sizes, c
     zl_warp_copy(dst + offs[i], srcs[i], (u32)sizes[i], lane);
 }
 
+// ---------------------------------------------------------------------------------------------- dictionary training
+// warp per parsed block: literal histogram and LL / ML / OF code counts summed into one table of 512 counters
+// ([0,256) literals, [256,292) LL, [292,345) ML, [345,377) OF) -- the statistics of ZDICT_countEStats (zstd.c:50440-50510)
+__global__ void __launch_bounds__(ZL_PARSE_WARPS * 32)
+zl_k_dict_stats(u32 nblocks, const u64* __restrict__ recArena, u32 slotRec, const u32* __restrict__ histArena,
+                const ZlEncBlockMeta* __restrict__ metas, u32* stats)
+{
+    __shared__ u32 sh[ZL_PARSE_WARPS][128];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 blk = blockIdx.x * ZL_PARSE_WARPS + warp;
+    if (blk >= nblocks) return;
+    for (u32 i = lane; i < 128; i += 32) sh[warp][i] = 0;
+    __syncwarp();
+    for (u32 i = lane; i < 256; i += 32) { const u32 v = histArena[(size_t)blk * 256 + i]; if (v) atomicAdd(stats + i, v); }
+    const u64* __restrict__ recs = recArena + (size_t)blk * slotRec;
+    const u32 nseq = metas[blk].nseq;
+    for (u32 r = lane; r < nseq; r += 32) {
+        const u64 rec = recs[r];
+        atomicAdd(&sh[warp][zl_seq_code(c_enc, 0, rec)], 1u);
+        atomicAdd(&sh[warp][36 + zl_seq_code(c_enc, 2, rec)], 1u);
+        atomicAdd(&sh[warp][89 + (zl_seq_code(c_enc, 1, rec) & 31u)], 1u);
+    }
+    __syncwarp();
+    for (u32 i = lane; i < 121; i += 32) { const u32 v = sh[warp][i]; if (v) atomicAdd(stats + 256 + i, v); }
+}
+
 // ---------------------------------------------------------------------------------------------- launcher
 size_t zl_enc_match_smem(const ZlEncParams& P) { return ((size_t)2 << P.hlogS) + (P.hlogL ? ((size_t)2 << P.hlogL) : 0); }
 
@@ -620,6 +646,11 @@ cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st)
     if (ev) cudaEventRecord(ev[1], st);
     if (nb) zl_k_parse<<<(nb + ZL_PARSE_WARPS - 1) / ZL_PARSE_WARPS, ZL_PARSE_WARPS * 32, 0, st>>>(L.blocks, nb, L.M, L.slotM, L.recs, L.slotRec, L.lit, L.slotLit, L.hist, L.metas, L.dict);
     if (ev) cudaEventRecord(ev[2], st);
+    if (L.stats) {                                                  // dictionary training stops after the parse
+        if (nb) zl_k_dict_stats<<<(nb + ZL_PARSE_WARPS - 1) / ZL_PARSE_WARPS, ZL_PARSE_WARPS * 32, 0, st>>>(nb, L.recs, L.slotRec, L.hist, L.metas, L.stats);
+        if (ev) for (int k = 3; k <= 5; k++) cudaEventRecord(ev[k], st);
+        return cudaGetLastError();
+    }
     const u32 gq = (nb + ZL_ENT_WARPS - 1) / ZL_ENT_WARPS;
     // the stream / bitstream buffers reuse the M arena (dead after the parse): [streams | sequence bits] per block slot
     u32* streamArena = L.M;

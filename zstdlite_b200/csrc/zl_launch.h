@@ -127,6 +127,7 @@ struct ZlEncodeLaunch {
     const u64* xxh;                    // per-frame XXH64 of the content (only read when the frame carries a checksum)
     const ZlEncDictDev* dict;          // device pointer to the digested dictionary, or null
     cudaEvent_t* stageEv;              // null or ZL_ENC_STAGES + 1 events
+    u32* stats = nullptr;              // dictionary training: sum literal / code statistics here after the parse and stop (zl_dict_train.cuh)
 };
 cudaError_t zl_enc_upload_const();
 size_t zl_enc_match_smem(const ZlEncParams& P);
