@@ -210,13 +210,20 @@ def compress_leg(torch, dist, z, args, dev, rank, world):
 
 
 def dict_leg(torch, z, args, dev):
-    """configs[3]: 1e5 small objects, dictionary trained by the reference's ZDICT on the first 1e4 (5,000 B), level 3;
+    """configs[3]: 1e5 small objects, dictionary trained ON THE GPU on the first 1e4 (5,000 B; the reference's ZDICT timed beside it), level 3;
     device-resident batch compress then decompress with the dictionary; sizes compared with libzstd + the same dictionary."""
     from oracle import ref
     from zstdlite_b200 import corpus
+    import warnings
     n = args.dict_objects
     objs = corpus.small_objects(n)
-    d = ref.train_dict(objs[:min(n, 10000)], 5000)
+    train = objs[:min(n, 10000)]
+    # training: the GPU trainer (csrc/zl_dict_train.cuh) against the reference's ZDICT_trainFromBuffer on the same samples
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        z.zstd_train_dict_compress(train[:2000], 5000)                  # warm-up (contexts, module load)
+        t0 = time.time(); d = z.zstd_train_dict_compress(train, 5000); t_gpu = time.time() - t0
+    t0 = time.time(); d_ref = ref.train_dict(train, 5000); t_ref = time.time() - t0
     sizes = [len(o) for o in objs]
     offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     total = int(offs[-1])
@@ -251,17 +258,21 @@ def dict_leg(torch, z, args, dev):
         dplan.decompress(dctx)
     e1.record(stream); torch.cuda.synchronize()
     ms_d = e0.elapsed_time(e1) / 3
-    rc, rd = ref.CCtx(level=3, dict=d), ref.DCtx(dict=d)
+    rc, rd, rc_ref = ref.CCtx(level=3, dict=d), ref.DCtx(dict=d), ref.CCtx(level=3, dict=d_ref)
     step = max(1, n // 5000)
     host = cdst.cpu().numpy()
-    ours = theirs = 0
+    ours = theirs = refpipe = 0
     for i in range(0, n, step):                       # bounded sample for the libzstd comparison + cross-decode
         c = host[int(coffs[i]):int(coffs[i]) + csz[i]].tobytes()
         assert rd.decompress(c, cap=sizes[i]) == objs[i], "GPU dictionary frame does not decode with libzstd"
-        ours += csz[i]; theirs += len(rc.compress(objs[i]))
+        ours += csz[i]; theirs += len(rc.compress(objs[i])); refpipe += len(rc_ref.compress(objs[i]))
     return {"objects": n, "bytes": total, "dict_bytes": len(d), "level": 3, "compress_GBps": total / ms_c / 1e6, "compress_ms": ms_c,
             "decompress_GBps": total / ms_d / 1e6, "decompress_ms": ms_d, "ratio": total / sum(csz),
-            "size_vs_libzstd_same_dict": ours / theirs, "sampled_objects": len(range(0, n, step))}
+            "size_vs_libzstd_same_dict": ours / theirs, "size_vs_reference_pipeline": ours / refpipe,
+            "size_vs_reference_pipeline_how": "GPU-trained dictionary + GPU compressor against ZDICT-trained dictionary + libzstd, level 3",
+            "sampled_objects": len(range(0, n, step)),
+            "train": {"samples": len(train), "sample_bytes": sum(len(o) for o in train), "gpu_s": t_gpu, "zdict_s": t_ref,
+                      "dict_id": z.zstd_dict_id(d), "zdict_dict_id": z.zstd_dict_id(d_ref)}}
 
 
 def large_frame_leg(torch, z, args, dev):
