@@ -259,6 +259,13 @@ static size_t zl_enc_run(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* srcS
     if (!c->hResults.reserve(n * 8)) return ZL_ERROR(memory_allocation);
     cudaStream_t st = c->stream;
     for (size_t i = 0; i < n; i++) if (srcSize[i] >= 0xFFFFFFF0ull) return ZL_ERROR(srcSize_wrong);
+    // blocks per wave: the scratch of a block scales with the largest block of the batch (zl_enc_wave), so batches of small
+    // inputs run in far fewer waves (config 4's 1e5 objects: one wave instead of 13, each of which ended in a host sync)
+    size_t maxSrc = 512;
+    for (size_t i = 0; i < n; i++) if (srcSize[i] > maxSrc) maxSrc = srcSize[i];
+    if (maxSrc > ZL_BLOCKSIZE_MAX) maxSrc = ZL_BLOCKSIZE_MAX;
+    size_t waveBlocks = (size_t)ZL_WAVE_BLOCKS * (ZL_BLOCKSIZE_MAX / ((maxSrc + 255) & ~(size_t)255));
+    if (waveBlocks > ((size_t)1 << 20)) waveBlocks = (size_t)1 << 20;
     size_t f0 = 0;
     bool firstWave = true;
     double total = 0.0; double stage[ZL_ENC_STAGES] = {};
@@ -266,7 +273,7 @@ static size_t zl_enc_run(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* srcS
         size_t f1 = f0, nb = 0;
         while (f1 < n) {
             const size_t k = srcSize[f1] ? (srcSize[f1] + ZL_BLOCKSIZE_MAX - 1) / ZL_BLOCKSIZE_MAX : 1;
-            if (f1 > f0 && nb + k > ZL_WAVE_BLOCKS) break;
+            if (f1 > f0 && nb + k > waveBlocks) break;
             nb += k; f1++;
         }
         if (!firstWave) {                                         // the wave's host-side descriptor buffers are reused: drain first

@@ -468,8 +468,20 @@ ZL_HD void zl_lit_plan(ZlHufSm& f, ZlEncBlockOut& o, const u8* lit, u32 nLit, co
     for (u32 s = 0; s < 256; s++) { if (f.count[s]) present++; if (f.count[s] > maxCount) maxCount = f.count[s]; }
     const u32 minGain = (nLit >> 6) + 2;                                                 // zstd.c:19607
     u32 mode = 0, estBest = 0xFFFFFFFFu;
+    bool dictTaken = false;
     if (nLit >= 1 && present == 1 && nLit > 2) mode = 1;                                 // zstd.c:20644 rle literals
-    else {
+    else if (dict && nLit >= 6 && nLit <= 1024) {
+        // small literal sections prefer a valid dictionary tree without building their own (HUF_compress_internal's
+        // preferRepeat heuristic, zstd.c:18030-18036 with 20714: strategy < lazy and srcSize <= 1024)
+        u64 bits = 0; bool ok = true;
+        for (u32 s = 0; s < 256; s++) if (f.count[s]) { if (!dict->hufNbBits[s]) { ok = false; break; } bits += (u64)f.count[s] * dict->hufNbBits[s]; }
+        const u32 est = (u32)((bits + 7) >> 3) + 1u;
+        if (ok && est + minGain < nLit) {
+            mode = 2; c.repeat = 1; c.nStreams = 1; c.descSize = 0; dictTaken = true;
+            for (u32 s = 0; s < 256; s++) { f.code[s] = dict->hufCode[s]; f.nbBits[s] = dict->hufNbBits[s]; }
+        }
+    }
+    if (mode == 0 && !dictTaken) {
         if (nLit >= 64 && present >= 2 && maxCount > (nLit >> 7) + 4) {                  // zstd.c:20685, 18043 ("probably not compressible")
             zl_huf_build(f);
             if (zl_huf_write_desc(f)) {
