@@ -24,3 +24,18 @@ for use_dict in (True, False):
     csz = sum(int(r) for r in res)
     print(f"dict={use_dict}: kernels {cctx.last_kernel_ms:.3f} ms -> {total / cctx.last_kernel_ms / 1e6:.2f} GB/s, ratio {total / csz:.3f}; " +
           " ".join(f"{a}={b:.2f}" for a, b in zip(("match", "parse", "literals", "sequences", "plan+assemble"), st)), flush=True)
+# ---- decompression of the dictionary-compressed batch: wall, kernels, stages
+import time
+cctx = z.zstd_cctx(level=3, dict=d)
+res = z.BatchPlan([src.data_ptr() + int(o) for o in offs[:-1]], sizes, [cdst.data_ptr() + int(o) for o in coffs[:-1]], caps).compress(cctx)
+csz = [int(r) for r in res]
+ddst = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+dctx = z.zstd_dctx(dict=d)
+dplan = z.BatchPlan([cdst.data_ptr() + int(o) for o in coffs[:-1]], csz, [ddst.data_ptr() + int(o) for o in offs[:-1]], sizes)
+for prof in (False, True):
+    dctx.set_profile(prof)
+    for it in range(3):
+        t = time.time(); dplan.decompress(dctx); wall = (time.time() - t) * 1e3
+    st = [L.zl_dctx_last_stage_ms(dctx._p, k) for k in range(4)]
+    print(f"decode profile={prof}: wall {wall:.3f} ms, kernels {dctx.last_kernel_ms:.3f} ms -> {total / wall / 1e6:.2f} GB/s; stages " + " ".join(f"{v:.3f}" for v in st), flush=True)
+assert bytes(ddst[:total].cpu().numpy()) == b"".join(objs)

@@ -347,9 +347,12 @@ cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
     if (ev) cudaEventRecord(ev[0], st);
     cudaMemsetAsync(L.counters, 0, 3 * sizeof(u32), st);              // unit count, literal cursor, sequence cursor
     zl_k_index<<<(L.nframes + 127) / 128, 128, 0, st>>>(L.descs, L.infos, L.hdrArena, L.units, L.counters, L.unitCap, L.nframes, L.frameBase, L.dict);
+    const bool useSide = L.side && !ev;
+    if (useSide) { cudaEventRecord(L.sideFork, st); cudaStreamWaitEvent(L.side, L.sideFork, 0); }
     zl_k_literals<<<litCtas, 32, smA, st>>>(L.descsAll, L.infosAll, L.hdrArena, L.litArena, L.units, L.counters, L.counters + 1, L.dict);
     if (ev) cudaEventRecord(ev[1], st);
-    zl_k_sequences<<<seqCtas, 32, smB, st>>>(L.descsAll, L.infosAll, L.hdrArena, L.recArena, L.normArena, L.units, L.counters, L.counters + 2, L.dict);
+    zl_k_sequences<<<seqCtas, 32, smB, useSide ? L.side : st>>>(L.descsAll, L.infosAll, L.hdrArena, L.recArena, L.normArena, L.units, L.counters, L.counters + 2, L.dict);
+    if (useSide) { cudaEventRecord(L.sideJoin, L.side); cudaStreamWaitEvent(st, L.sideJoin, 0); }
     if (ev) cudaEventRecord(ev[2], st);
     const u32 g2 = (L.nframes + ZL_EXEC_WARPS - 1) / ZL_EXEC_WARPS;
     if (L.dict)

@@ -74,6 +74,8 @@ struct ZlDecodeLaunch {          // one slice of a batch: frames [frameBase, fra
     u32* remainHost;             // pinned host word for the convergence check
     const ZlDictDev* dict;       // device pointer or null
     cudaEvent_t* stageEv;        // null, or ZL_DEC_STAGES + 1 events recorded around each kernel (per-kernel timing for bench.py)
+    // optional: the sequence kernel of the slice runs on `side`, next to the literal kernel (both only depend on the index kernel)
+    cudaStream_t side = nullptr; cudaEvent_t sideFork = nullptr, sideJoin = nullptr;
 };
 
 size_t zl_literals_smem_bytes();
