@@ -202,6 +202,7 @@ struct ZSTD_DCtx_s {
     // kernel and the PCIe copies of one slice overlap the (shared-memory-bound) entropy kernels of the others
     cudaStream_t lane[ZL_DEC_LANES] = {};
     cudaEvent_t laneDone[ZL_DEC_LANES] = {}, forkEv = nullptr;
+    cudaEvent_t inDone[ZL_DEC_LANES] = {};                // host buffers: host-to-device copies of a slice done (they run in slice order)
     cudaStream_t side[ZL_DEC_LANES] = {};                 // per lane: the sequence kernel runs here, next to the literal kernel
     cudaEvent_t sideFork[ZL_DEC_LANES] = {}, sideJoin[ZL_DEC_LANES] = {};
     int profileStages = 0;                 // 1: one slice, one stream, per-kernel events (zl_dctx_last_stage_ms)
@@ -235,6 +236,7 @@ ZL_EXPORT size_t ZSTD_freeDCtx(ZSTD_DCtx* c)
     if (c->forkEv) cudaEventDestroy(c->forkEv);
     for (cudaStream_t l : c->lane) if (l) cudaStreamDestroy(l);
     for (cudaStream_t l : c->side) if (l) cudaStreamDestroy(l);
+    for (cudaEvent_t e : c->inDone) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->sideFork) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->sideJoin) if (e) cudaEventDestroy(e);
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
@@ -365,6 +367,7 @@ static bool zl_dctx_lanes(ZSTD_DCtx* c)
     for (int i = 0; i < ZL_DEC_LANES; i++) {
         if (cudaStreamCreateWithFlags(&c->lane[i], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->laneDone[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->inDone[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->sideFork[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->sideJoin[i], cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); return false; }
@@ -415,6 +418,12 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         if (nslices > ZL_DEC_MAX_SLICES) nslices = ZL_DEC_MAX_SLICES;
         if (nslices < 1) nslices = 1;
     }
+    // Host buffers, large batches: the device-to-host copy engine bounds the call, so it must start early and never run dry:
+    // the first slices are small (their kernels end after little more than the chain latency of one frame, ~3 ms) and every
+    // slice is as large as all before it together (1/32, 1/32, 1/16, 1/8, 1/4, 1/2), so the copy back of a slice covers the
+    // kernels of the next.
+    const bool graded = !dev && nslices >= 6;
+    if (graded) nslices = 6;
     if (nslices > 1 && !zl_dctx_lanes(c)) nslices = 1;
     // Scheduling order (device buffers): the frames are handed to the kernels by decreasing compressed size -- longest work
     // first, and frames of one kind next to each other, so that the quads of a warp and the warps of a CTA finish together.
@@ -446,7 +455,9 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         u64 acc = 0; size_t k = 1;
         for (size_t i = 0; i < n && k < nslices; i++) {
             acc += dstCap[order[i]];
-            if (acc * nslices >= contentTotal * k) cut[k++] = i + 1;
+            const bool reached = graded && nslices == 6 ? acc * 32 >= contentTotal * (k == 1 ? 1 : k == 2 ? 2 : k == 3 ? 4 : k == 4 ? 8 : 16)
+                                                        : acc * nslices >= contentTotal * k;
+            if (reached) cut[k++] = i + 1;
         }
     }
     std::vector<ZlRun> sruns, druns;
@@ -510,13 +521,23 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     cudaEventRecord(c->ev0, st);
     if (nslices > 1) cudaEventRecord(c->forkEv, st);
     cudaError_t e = cudaSuccess;
+    static const bool trace = getenv("ZL_DEC_TRACE") != nullptr;        // (development: per-slice timeline on stderr)
+    std::vector<cudaEvent_t> tev;
+    if (trace) { tev.resize(3 * nslices + 1); for (cudaEvent_t& x : tev) cudaEventCreate(&x); cudaEventRecord(tev[3 * nslices], st); }
     for (size_t k = 0; k < nslices && e == cudaSuccess; k++) {
         const size_t a = cut[k], cnt = cut[k + 1] - a;
         if (!cnt) continue;
         cudaStream_t ls = nslices > 1 ? c->lane[k % ZL_DEC_LANES] : st;
         if (nslices > 1 && k < ZL_DEC_LANES) cudaStreamWaitEvent(ls, c->forkEv, 0);
-        if (!dev) for (size_t r = srunCut[k]; r < srunCut[k + 1]; r++)
-            if (sruns[r].bytes) cudaMemcpyAsync(c->dSrc.as<u8>() + sruns[r].devOff, sruns[r].hbase, sruns[r].bytes, cudaMemcpyHostToDevice, ls);
+        if (!dev) {
+            // host-to-device copies in slice order: each waits for the previous slice's (left alone, the copy engine served the
+            // streams 0, 4, 1, 5, ...; a dedicated copy stream aliased a hardware queue with a lane and stalled behind its copy back)
+            if (nslices > 1 && k > 0) cudaStreamWaitEvent(ls, c->inDone[(k - 1) % ZL_DEC_LANES], 0);
+            for (size_t r = srunCut[k]; r < srunCut[k + 1]; r++)
+                if (sruns[r].bytes) cudaMemcpyAsync(c->dSrc.as<u8>() + sruns[r].devOff, sruns[r].hbase, sruns[r].bytes, cudaMemcpyHostToDevice, ls);
+            if (nslices > 1) cudaEventRecord(c->inDone[k % ZL_DEC_LANES], ls);
+        }
+        if (trace) cudaEventRecord(tev[3 * k], ls);
         ZlDecodeLaunch L;
         L.descs = c->dDescs.as<ZlFrameDesc>() + a; L.infos = c->dInfos.as<ZlFrameInfo>() + a; L.hdrArena = c->dHdr.as<ZlBlockHdr>();
         L.descsAll = c->dDescs.as<ZlFrameDesc>(); L.infosAll = c->dInfos.as<ZlFrameInfo>(); L.frameBase = (u32)a;
@@ -546,8 +567,10 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         if (nslices > 1 && !dev) { const int ln = (int)(k % ZL_DEC_LANES); L.side = c->side[ln]; L.sideFork = c->sideFork[ln]; L.sideJoin = c->sideJoin[ln]; }
         e = zl_launch_decode(L, ls);
         c->launches += 3 + (verify ? 1 : 0);
+        if (trace) cudaEventRecord(tev[3 * k + 1], ls);
         if (!dev) for (size_t r = drunCut[k]; r < drunCut[k + 1]; r++)
             if (druns[r].bytes) cudaMemcpyAsync((void*)druns[r].hbase, c->dDst.as<u8>() + druns[r].devOff, druns[r].bytes, cudaMemcpyDeviceToHost, ls);
+        if (trace) cudaEventRecord(tev[3 * k + 2], ls);
     }
     if (nslices > 1)
         for (int i = 0; i < ZL_DEC_LANES; i++) { cudaEventRecord(c->laneDone[i], c->lane[i]); cudaStreamWaitEvent(st, c->laneDone[i], 0); }
@@ -557,6 +580,15 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { fprintf(stderr, "zstdlite_gpu: device error: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->lastKernelMs = ms;      // with host buffers this span includes the copies
+    if (trace) {
+        for (size_t k = 0; k < nslices; k++) {
+            float t0 = 0, t1 = 0, t2 = 0;
+            cudaEventElapsedTime(&t0, tev[3 * nslices], tev[3 * k]); cudaEventElapsedTime(&t1, tev[3 * nslices], tev[3 * k + 1]); cudaEventElapsedTime(&t2, tev[3 * nslices], tev[3 * k + 2]);
+            fprintf(stderr, "slice %zu (%zu frames): h2d done %.2f, kernels done %.2f, d2h done %.2f ms\n", k, cut[k + 1] - cut[k], t0, t1, t2);
+        }
+        fprintf(stderr, "total %.2f ms\n", ms);
+        for (cudaEvent_t x : tev) cudaEventDestroy(x);
+    }
     for (int k = 0; k < ZL_DEC_STAGES; k++) {
         float t = -1.0f;
         if (nslices == 1) cudaEventElapsedTime(&t, c->stageEv[k], c->stageEv[k + 1]);
