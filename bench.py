@@ -209,6 +209,77 @@ def compress_leg(torch, dist, z, args, dev, rank, world):
     return out
 
 
+MIX5 = (("text", 0.3), ("rdf", 0.3), ("lowent", 0.15), ("rand", 0.15), ("rle", 0.1))
+
+
+def config5_leg(torch, dist, z, args, dev, rank, world):
+    """configs[4]: the 32 GiB mixed corpus (262,144 x 128 KiB frames, families text/rdf/lowent/rand/rle 30/30/15/15/10) sharded by
+    frame across the ranks (STRONG scaling: the total is fixed, every rank takes 1/N of the frame list), made on the device from
+    the seed; level-3 compress with checksums, then decompress; the round trip is compared on the device.  A rank works through
+    its share in sub-shards of <= 65,536 frames (8 GiB), so the footprint does not depend on N; the times are summed."""
+    from zstdlite_b200 import corpus
+    from oracle import ref
+    total_frames, fb = args.config5_frames, 131072
+    n = total_frames // world
+    bound = int(z._lib.lib().ZSTD_compressBound(fb))
+    slot = (bound + 255) // 256 * 256
+    cctx, dctx = z.zstd_cctx(level=3, include_checksum=True), z.zstd_dctx()
+    stream = torch.cuda.current_stream()
+    cctx.set_stream(stream.cuda_stream); dctx.set_stream(stream.cuda_stream)
+    sub, chunk = 65536, 32768
+    ms_c = ms_d = 0.0
+    csize = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for s0 in range(0, n, sub):
+        m = min(sub, n - s0)
+        src, pools, meta = corpus.device_mixed_slabs(m, fb, MIX5, index=31 + rank * 64 + s0 // sub, device=dev)
+        comp = torch.empty(m * slot + 64, dtype=torch.uint8, device=dev)
+        back = torch.empty((m, fb), dtype=torch.uint8, device=dev)
+        cplan = z.BatchPlan([src.data_ptr() + i * fb for i in range(m)], [fb] * m, [comp.data_ptr() + i * slot for i in range(m)], [bound] * m)
+        if s0 == 0:
+            cplan.compress(cctx)                                        # warm-up (arenas, contexts)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+        e0.record(stream); res = cplan.compress(cctx); e1.record(stream); torch.cuda.synchronize()
+        ms_c += e0.elapsed_time(e1)
+        sizes = [int(r) for r in res]
+        assert not any(z.is_error(v) for v in sizes), "compress errors"
+        csize += sum(sizes)
+        # decoded in calls of <= 32,768 frames: the decoder's arenas (literals, 8-byte records) are sized per call
+        dplans = [z.BatchPlan([comp.data_ptr() + i * slot for i in range(a, min(m, a + chunk))], sizes[a:a + chunk],
+                              [back.data_ptr() + i * fb for i in range(a, min(m, a + chunk))], [fb] * (min(m, a + chunk) - a)) for a in range(0, m, chunk)]
+        if s0 == 0:
+            dplans[0].decompress(dctx)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+        e0.record(stream)
+        bad = 0
+        for p in dplans:
+            bad += sum(1 for r in p.decompress(dctx) if int(r) != fb)
+        e1.record(stream); torch.cuda.synchronize()
+        ms_d += e0.elapsed_time(e1)
+        assert bad == 0, "decode errors"
+        assert torch.equal(back, src), "round trip differs"
+        if rank == 0:
+            for i in range(0, m, max(1, m // 8)):                       # sampled frames through the reference's libzstd
+                fam, row, shift = meta[i]
+                assert ref.decompress(comp[i * slot:i * slot + sizes[i]].cpu().numpy().tobytes()) == np.roll(pools[fam][row], shift).tobytes()
+        del src, comp, back, cplan, dplans
+    t = torch.tensor([ms_c, ms_d, float(csize)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t)
+        ms_c, ms_d, csize = float(mx[0]), float(mx[1]), float(t[2])
+    if rank != 0:
+        return None
+    tot = n * world * fb
+    return {"frames": n * world, "frame_bytes": fb, "bytes": tot, "n_gpus": world, "scaling": "strong", "level": 3, "checksum": True,
+            "compress_GBps": tot / ms_c / 1e6, "compress_ms": ms_c, "decompress_GBps": tot / ms_d / 1e6, "decompress_ms": ms_d,
+            "ratio": tot / float(csize), "round_trip": "device compare of every byte + sampled frames through libzstd"}
+
+
 def dict_leg(torch, z, args, dev):
     """configs[3]: 1e5 small objects, dictionary trained ON THE GPU on the first 1e4 (5,000 B; the reference's ZDICT timed beside it), level 3;
     device-resident batch compress then decompress with the dictionary; sizes compared with libzstd + the same dictionary."""
@@ -338,6 +409,8 @@ def main():
     ap.add_argument("--df-rows", type=int, default=1000000)
     ap.add_argument("--no-large", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--config5-frames", type=int, default=262144, help="frames of configs[4] in total (32 GiB), split over the ranks")
+    ap.add_argument("--no-config5", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -452,6 +525,18 @@ def main():
                 raise
             comp = {"error": repr(e)}
 
+    c5 = None
+    if not args.no_config5:
+        if comp is not None:
+            torch.cuda.empty_cache()
+        try:
+            c5 = config5_leg(torch, dist, z, args, dev, rank, world)
+        except Exception as e:
+            if world > 1:
+                raise
+            c5 = {"error": repr(e)}
+        torch.cuda.empty_cache()
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -496,6 +581,8 @@ def main():
                                              f"oracle/_ref libzstd 1.5.6, one DCtx per thread"}
         if comp is not None:
             out["compress"] = comp
+        if c5 is not None:
+            out["config5"] = c5
         if world == 1 and not args.no_dict:
             try:
                 out["dict"] = dict_leg(torch, z, args, dev)

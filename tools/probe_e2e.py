@@ -29,6 +29,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "pcie":
     dt = time.time() - t
     print(f"both directions at once: H2D {hsrc.numel() * 5 / dt / 1e9:.1f} + D2H {hdst.numel() * 5 / dt / 1e9:.1f} GB/s (wall of the pair)", flush=True)
 d = z.zstd_dctx()
+if os.environ.get("PROBE_NULL_STREAM"):
+    d.set_stream(torch.cuda.current_stream().cuda_stream)
 plan = z.BatchPlan([hsrc.data_ptr() + int(o) for o in offs[:-1]], sizes, [hdst.data_ptr() + i * fb for i in range(n)], [fb] * n)
 for _ in range(2): plan.decompress(d, device=False)
 assert (hdst.numpy().reshape(n, fb) == data).all()

@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <new>
 #include <algorithm>
+#include <chrono>
 #include <vector>
 #include "../../include/zstdlite_gpu.h"
 #include "zl_host.h"
@@ -398,6 +399,8 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     if (!c) return ZL_ERROR(GENERIC);
     if (n == 0) return 0;
     if (n > 0x7FFFFFFFull / 8) return ZL_ERROR(memory_allocation);
+    const auto hostT0 = std::chrono::steady_clock::now();
+    auto hostMs = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hostT0).count(); };
     if (!zl_ctx_stream(&c->stream, &c->ownStream, &c->ev0, &c->ev1)) return ZL_ERROR(memory_allocation);
     cudaStream_t st = c->stream;
     if (!c->hDescs.reserve(n * sizeof(ZlFrameDesc)) || !c->hResults.reserve(n * 8)) return ZL_ERROR(memory_allocation);
@@ -515,6 +518,7 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         cudaMemcpyAsync(c->dLargeIdx.p, hLarge, nLargeTotal * 4, cudaMemcpyHostToDevice, st);
     }
     size_t largeSeen = 0;
+    const double tPrep = hostMs();
     cudaMemcpyAsync(c->dDescs.p, hd, n * sizeof(ZlFrameDesc), cudaMemcpyHostToDevice, st);
     if (!c->stageEv[0]) for (cudaEvent_t& e : c->stageEv) cudaEventCreate(&e);
     const int verify = !c->forceIgnoreChecksum;
@@ -576,8 +580,10 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         for (int i = 0; i < ZL_DEC_LANES; i++) { cudaEventRecord(c->laneDone[i], c->lane[i]); cudaStreamWaitEvent(st, c->laneDone[i], 0); }
     cudaEventRecord(c->ev1, st);
     if (e != cudaSuccess) { cudaStreamSynchronize(st); fprintf(stderr, "zstdlite_gpu: kernel launch failed: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
+    const double tLaunch = hostMs();
     cudaMemcpyAsync(c->hResults.p, c->dResults.p, n * 8, cudaMemcpyDeviceToHost, st);
     e = cudaStreamSynchronize(st);
+    const double tSync = hostMs();
     if (e != cudaSuccess) { fprintf(stderr, "zstdlite_gpu: device error: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->lastKernelMs = ms;      // with host buffers this span includes the copies
     if (trace) {
@@ -586,7 +592,7 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
             cudaEventElapsedTime(&t0, tev[3 * nslices], tev[3 * k]); cudaEventElapsedTime(&t1, tev[3 * nslices], tev[3 * k + 1]); cudaEventElapsedTime(&t2, tev[3 * nslices], tev[3 * k + 2]);
             fprintf(stderr, "slice %zu (%zu frames): h2d done %.2f, kernels done %.2f, d2h done %.2f ms\n", k, cut[k + 1] - cut[k], t0, t1, t2);
         }
-        fprintf(stderr, "total %.2f ms\n", ms);
+        fprintf(stderr, "total %.2f ms; host: descriptors ready %.3f, launches issued %.3f, synchronised %.3f ms\n", ms, tPrep, tLaunch, tSync);
         for (cudaEvent_t x : tev) cudaEventDestroy(x);
     }
     for (int k = 0; k < ZL_DEC_STAGES; k++) {
