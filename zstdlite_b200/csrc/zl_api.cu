@@ -425,7 +425,8 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     // the first slices are small (their kernels end after little more than the chain latency of one frame, ~3 ms) and every
     // slice is as large as all before it together (1/32, 1/32, 1/16, 1/8, 1/4, 1/2), so the copy back of a slice covers the
     // kernels of the next.
-    const bool graded = !dev && nslices >= 6;
+    static const bool gradeOff = getenv("ZL_DEC_NOGRADE") != nullptr;      // (development switch)
+    const bool graded = !dev && nslices >= 6 && !gradeOff;
     if (graded) nslices = 6;
     if (nslices > 1 && !zl_dctx_lanes(c)) nslices = 1;
     // Scheduling order (device buffers): the frames are handed to the kernels by decreasing compressed size -- longest work
