@@ -526,6 +526,8 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     cudaEventRecord(c->ev0, st);
     if (nslices > 1) cudaEventRecord(c->forkEv, st);
     cudaError_t e = cudaSuccess;
+    // per-kernel events: one slice on one stream, unless the batch is a few (large) frames that are not being profiled
+    const bool stageTimed = nslices == 1 && (c->profileStages || n > 16);
     static const bool trace = getenv("ZL_DEC_TRACE") != nullptr;        // (development: per-slice timeline on stderr)
     std::vector<cudaEvent_t> tev;
     if (trace) { tev.resize(3 * nslices + 1); for (cudaEvent_t& x : tev) cudaEventCreate(&x); cudaEventRecord(tev[3 * nslices], st); }
@@ -566,10 +568,12 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         }
         L.results = c->dResults.as<u64>() + a;
         L.nframes = (u32)cnt; L.verifyChecksum = verify; L.dict = c->hasDict ? c->dDict.as<ZlDictDev>() : nullptr;
-        L.stageEv = nslices > 1 ? nullptr : c->stageEv;
+        L.stageEv = stageTimed ? c->stageEv : nullptr;
         // host buffers only: literals next to sequences shortens the chain of a slice, i.e. the wait before its copy back can
         // start (measured 39.9 -> 41.4 GB/s end to end); device-resident batches are throughput-bound and lose (143 -> 125 GB/s)
-        if (nslices > 1 && !dev) { const int ln = (int)(k % ZL_DEC_LANES); L.side = c->side[ln]; L.sideFork = c->sideFork[ln]; L.sideJoin = c->sideJoin[ln]; }
+        // ... and batches of a few (large) frames, whose block units leave most of the device idle: a 16 MiB frame 9.4 -> 6.8 ms
+        const bool fewFrames = n <= 16 && nslices == 1 && !stageTimed && zl_dctx_lanes(c);
+        if ((nslices > 1 && !dev) || fewFrames) { const int ln = (int)(k % ZL_DEC_LANES); L.side = c->side[ln]; L.sideFork = c->sideFork[ln]; L.sideJoin = c->sideJoin[ln]; }
         e = zl_launch_decode(L, ls);
         c->launches += 3 + (verify ? 1 : 0);
         if (trace) cudaEventRecord(tev[3 * k + 1], ls);
@@ -598,7 +602,7 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     }
     for (int k = 0; k < ZL_DEC_STAGES; k++) {
         float t = -1.0f;
-        if (nslices == 1) cudaEventElapsedTime(&t, c->stageEv[k], c->stageEv[k + 1]);
+        if (stageTimed) cudaEventElapsedTime(&t, c->stageEv[k], c->stageEv[k + 1]);
         c->lastStageMs[k] = t;
     }
     const u64* hr = c->hResults.as<u64>();
