@@ -136,13 +136,13 @@ static u32 emul_block(const u8* src, u32 n, const ZlEncParams& P, const ZlEncCon
     // sequences kernel
     std::vector<u32> seqBits(n / 4 + 16, 0);
     ss.ctl.nbSeq = nbSeq;
-    o.seqBitsSize = 0;
+    o.seqBitsSize = 0; o.seqOvf = 0;
     if (nbSeq) {
         for (u32 t = 0; t < 3; t++) zl_seq_build_table(ss, t, recs.data(), nbSeq, K, De);
         zl_seq_write_head(ss, o);
         u32 ovf = 0;
         o.seqBitsSize = zl_seq_encode(ss, K, recs.data(), nbSeq, seqBits.data(), (u32)seqBits.size(), &ovf);
-        if (ovf || !o.seqBitsSize) o.flags |= 2;
+        o.seqOvf = (ovf || !o.seqBitsSize) ? 1u : 0u;
     } else zl_seq_write_head(ss, o);
     const u32 payload = zl_enc_block_payload(o, n, nbSeq);
     if (!payload) return 0;

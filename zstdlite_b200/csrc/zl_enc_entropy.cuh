@@ -448,8 +448,9 @@ struct ZlEncBlockOut {
     u32 sBytes[4];
     u32 seqHeadSize;       // nbSeq + modes byte + table descriptions
     u32 seqBitsSize;
-    u32 flags;             // bit0: literals overflowed / undescribable (-> raw block), bit1: sequences overflowed
-    u32 pad;
+    u32 flags;             // literals kernel: nonzero = store the block raw
+    u32 seqOvf;            // sequences kernel: nonzero = the sequence bitstream overflowed (-> raw block).  Separate words: the two
+                           // kernels may run side by side
     u8 litHead[176];
     u8 seqHead[304];
 };
@@ -709,7 +710,7 @@ ZL_HD u32 zl_seq_encode(const ZlSeqEncSm& f, const ZlEncConst& k, const u64* rec
 // the block must be stored raw.
 ZL_HD u32 zl_enc_block_payload(const ZlEncBlockOut& o, u32 srcSize, u32 nbSeq)
 {
-    if (o.flags) return 0;
+    if (o.flags || o.seqOvf) return 0;
     u32 body = 0;
     if (o.litBodyMode == 1) body = o.nLit;
     else if (o.litBodyMode == 2) for (u32 k = 0; k < o.nStreams; k++) body += o.sBytes[k];

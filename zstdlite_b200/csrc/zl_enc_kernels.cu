@@ -404,7 +404,7 @@ zl_k_enc_sequences(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u64
     const u32 nbSeq = metas[blk].nseq;
     u32* __restrict__ out = seqBitsArena + (size_t)blk * slotSeqWords;
     if (lane == 0) f.ctl.nbSeq = nbSeq;
-    if (nbSeq == 0) { if (lane == 0) { zl_seq_write_head(f, o); o.seqBitsSize = 0; } return; }
+    if (nbSeq == 0) { if (lane == 0) { zl_seq_write_head(f, o); o.seqBitsSize = 0; o.seqOvf = 0; } return; }
     // ---- (a) histograms
     for (u32 i = lane; i < 192; i += 32) (&f.count[0][0])[i] = 0;
     __syncwarp();
@@ -509,7 +509,7 @@ zl_k_enc_sequences(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u64
     if (lane == 0 && (bitPos & 31)) { if ((bitPos >> 5) < seqCapWords) out[bitPos >> 5] = w.stage[0]; else ovf = 1; }
     ovf = __any_sync(ZL_FULL, ovf != 0) ? 1u : 0u;
     if (lane == 0) {
-        if (ovf) o.flags |= 2u;
+        o.seqOvf = ovf;
         o.seqBitsSize = ovf ? 0u : (bitPos + 7) >> 3;
     }
 }
@@ -655,9 +655,13 @@ cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st)
     // the stream / bitstream buffers reuse the M arena (dead after the parse): [streams | sequence bits] per block slot
     u32* streamArena = L.M;
     u32* seqArena = L.M + L.streamWordsPerBlock;
+    // the two entropy kernels write disjoint fields of `outs` and disjoint halves of the M arena: with a side stream they run together
+    const bool useSide = L.side != nullptr && nb;
+    if (useSide) { cudaEventRecord(L.sideFork, st); cudaStreamWaitEvent(L.side, L.sideFork, 0); }
     if (nb) zl_k_enc_literals<<<gq, ZL_ENT_WARPS * 32, smL, st>>>(L.blocks, nb, L.lit, L.slotLit, L.hist, L.metas, streamArena, L.slotM, L.streamCapWords, L.outs, L.dict);
     if (ev) cudaEventRecord(ev[3], st);
-    if (nb) zl_k_enc_sequences<<<gq, ZL_ENT_WARPS * 32, smS, st>>>(L.blocks, nb, L.recs, L.slotRec, L.metas, seqArena, L.slotM, L.seqCapWords, L.seqCapWords, L.outs, L.dict);
+    if (nb) zl_k_enc_sequences<<<gq, ZL_ENT_WARPS * 32, smS, useSide ? L.side : st>>>(L.blocks, nb, L.recs, L.slotRec, L.metas, seqArena, L.slotM, L.seqCapWords, L.seqCapWords, L.outs, L.dict);
+    if (useSide) { cudaEventRecord(L.sideJoin, L.side); cudaStreamWaitEvent(st, L.sideJoin, 0); }
     if (ev) cudaEventRecord(ev[4], st);
     zl_k_enc_plan<<<(L.nframes + 127) / 128, 128, 0, st>>>(L.frames, L.nframes, L.blocks, L.metas, L.outs, L.plans, L.results);
     if (nb) zl_k_enc_assemble<<<(nb + ZL_ASM_WARPS - 1) / ZL_ASM_WARPS, ZL_ASM_WARPS * 32, 0, st>>>(L.frames, L.blocks, nb, L.plans, L.outs, L.lit, L.slotLit, streamArena, L.slotM,
