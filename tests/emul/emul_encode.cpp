@@ -59,44 +59,54 @@ static void emul_match(const u8* src, u32 n, const ZlEncParams& P, std::vector<u
         M[p] = bestLen ? ((bestOff << 8) | bestLen) : 0;
     }
 }
-// stage 2: greedy walk -> records, literals, histogram
+// stage 2: greedy walk -> records, literals, histogram; the block is walked as independent segments of ZL_PARSE_SEG bytes (zl_k_parse)
 static void emul_parse(const u8* src, u32 n, const std::vector<u32>& M, std::vector<u64>& recs, std::vector<u8>& lit, u32* hist, bool firstBlock,
                        const EmulDict* D)
 {
-    // blocks are compressed independently: only the first block of a frame knows the decoder's repeat offsets
-    // (1, 4, 8; zstd.c:15416); later blocks start with an unknown history (0 never matches an offset)
-    ZlReps reps = {firstBlock ? 1u : 0u, firstBlock ? 4u : 0u, firstBlock ? 8u : 0u};
-    if (firstBlock && D && D->d.hasEntropy) { reps.r0 = D->d.rep[0]; reps.r1 = D->d.rep[1]; reps.r2 = D->d.rep[2]; }
-    const bool repPref = firstBlock && D;
-    u32 p = 0, anchor = 0;
     recs.clear(); lit.clear();
     for (u32 i = 0; i < 256; i++) hist[i] = 0;
-    while (p < n) {
-        const u32 m = M[p];
-        if (!m) { p++; continue; }
-        u32 len = m & 0xFF; u32 off = m >> 8;
-        if (len == ZL_M_CAP && off <= p) while (p + len < n && src[p + len] == src[p + len - off]) len++;
-        // Dictionary mode only: repeat-offset preference (cf. the repcode checks at ip+1 / ip+2 of zstd.c:29989, 30801).  A match
-        // at the most recent offset starting at p, p+1 or p+2 (inside the same 32-position window) costs no offset bits; it
-        // is taken when it is at most 4 bytes shorter.  Small dictionary-compressed inputs are dominated by offset cost.
-        if (repPref && reps.r0 && off != reps.r0) {
-            for (u32 k = 0; k < 3; k++) {
-                const u32 q = p + k;
-                if ((p & 31) + k >= 32 || reps.r0 > q || q + 4 > n) continue;
-                u32 lim = n - q; if (lim > ZL_M_CAP) lim = ZL_M_CAP;
-                u32 rl = 0; while (rl < lim && src[q + rl] == src[q + rl - reps.r0]) rl++;
-                if (rl >= 4 && rl + 4 >= len) {
-                    if (rl == ZL_M_CAP) while (q + rl < n && src[q + rl] == src[q + rl - reps.r0]) rl++;
-                    p = q; len = rl; off = reps.r0; break;
+    const bool repPref = firstBlock && D;
+    u32 carry = 0;                                           // literals since the last match of the segments before
+    for (u32 s0 = 0; s0 < n; s0 += ZL_PARSE_SEG) {
+        const u32 s1 = n - s0 < ZL_PARSE_SEG ? n : s0 + ZL_PARSE_SEG;
+        // blocks are compressed independently and walked in independent segments: only the first segment of a frame knows the
+        // decoder's repeat offsets (1, 4, 8; zstd.c:15416); the others start with an unknown history (0 never matches an offset)
+        const bool first = firstBlock && s0 == 0;
+        ZlReps reps = {first ? 1u : 0u, first ? 4u : 0u, first ? 8u : 0u};
+        if (first && D && D->d.hasEntropy) { reps.r0 = D->d.rep[0]; reps.r1 = D->d.rep[1]; reps.r2 = D->d.rep[2]; }
+        u32 p = s0, anchor = s0; bool firstSeq = true;
+        while (p < s1) {
+            const u32 m = M[p];
+            if (!m) { p++; continue; }
+            u32 len = m & 0xFF; u32 off = m >> 8;
+            if (len == ZL_M_CAP && off <= p) while (p + len < s1 && src[p + len] == src[p + len - off]) len++;
+            if (p + len > s1) len = s1 - p;                  // a match ends with its segment
+            if (len < 3) { p++; continue; }
+            // Dictionary mode only: repeat-offset preference (cf. the repcode checks at ip+1 / ip+2 of zstd.c:29989, 30801).  A match
+            // at the most recent offset starting at p, p+1 or p+2 (inside the same 32-position window) costs no offset bits; it
+            // is taken when it is at most 4 bytes shorter.  Small dictionary-compressed inputs are dominated by offset cost.
+            if (repPref && reps.r0 && off != reps.r0) {
+                for (u32 k = 0; k < 3; k++) {
+                    const u32 q = p + k;
+                    if ((p & 31) + k >= 32 || reps.r0 > q || q + 4 > s1) continue;
+                    u32 lim = s1 - q; if (lim > ZL_M_CAP) lim = ZL_M_CAP;
+                    u32 rl = 0; while (rl < lim && src[q + rl] == src[q + rl - reps.r0]) rl++;
+                    if (rl >= 4 && rl + 4 >= len) {
+                        if (rl == ZL_M_CAP) while (q + rl < s1 && src[q + rl] == src[q + rl - reps.r0]) rl++;
+                        p = q; len = rl; off = reps.r0; break;
+                    }
                 }
             }
+            const u32 ll = p - anchor;
+            for (u32 k = anchor; k < p; k++) { lit.push_back(src[k]); hist[src[k]]++; }
+            const u32 ob = zl_rep_encode(reps, off, ll);
+            recs.push_back(zl_enc_rec(ll + (firstSeq ? carry : 0u), len, ob));
+            firstSeq = false;
+            p += len; anchor = p;
         }
-        const u32 ll = p - anchor;
-        for (u32 k = anchor; k < p; k++) { lit.push_back(src[k]); hist[src[k]]++; }
-        recs.push_back(zl_enc_rec(ll, len, zl_rep_encode(reps, off, ll)));
-        p += len; anchor = p;
+        for (u32 k = anchor; k < s1; k++) { lit.push_back(src[k]); hist[src[k]]++; }
+        carry = firstSeq ? carry + (s1 - anchor) : s1 - anchor;
     }
-    for (u32 k = anchor; k < n; k++) { lit.push_back(src[k]); hist[src[k]]++; }
 }
 
 // one block -> payload bytes (without the 3-byte block header); returns 0 when the block must be stored raw

@@ -204,7 +204,7 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
     }
     if (nb > 0x3FFFFFFFull) return ZL_ERROR(memory_allocation);
     const u32 S = ((maxBlock < 512 ? 512 : maxBlock) + 255) & ~255u;      // slot layout below needs S >= 264
-    const u32 slotM = S, slotRec = S / 5 + 8, slotLit = S + 16;
+    const u32 slotM = S, slotRec = S / 5 + 32, slotLit = S + 16;      // records: 4 segments of <= ZL_PARSE_SEG_RECS (zl_enc_match.cuh)
     const u32 streamCapWords = (((S / 4 + 1) * 11) / 8 + 16 + 3) / 4, streamWordsPerBlock = 4 * streamCapWords, seqCapWords = S / 4;
     if (!c->hBlocks.reserve(nb * sizeof(ZlEncBlock)) || !c->hFrames.reserve(nf * sizeof(ZlEncFrame))) return ZL_ERROR(memory_allocation);
     if (!c->dBlocks.reserve(nb * sizeof(ZlEncBlock)) || !c->dFrames.reserve(nf * sizeof(ZlEncFrame)) || !c->dM.reserve(nb * (size_t)slotM * 4) ||
@@ -253,7 +253,7 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
     L.M = c->dM.as<u32>(); L.slotM = slotM; L.recs = c->dRecs.as<u64>(); L.slotRec = slotRec; L.lit = c->dLit.as<u8>(); L.slotLit = slotLit;
     L.hist = c->dHist.as<u32>(); L.metas = c->dMetas.as<ZlEncBlockMeta>(); L.outs = c->dOuts.as<ZlEncBlockOut>(); L.plans = c->dPlans.as<ZlEncBlockPlan>();
     L.streamCapWords = streamCapWords; L.streamWordsPerBlock = streamWordsPerBlock; L.seqCapWords = seqCapWords;
-    L.results = c->dResults.as<u64>() + f0; L.xxh = xxh; L.stageEv = timeIt ? c->stageEv : nullptr; L.stats = c->statsDev;
+    L.results = c->dResults.as<u64>() + f0; L.xxh = xxh; L.stageEv = timeIt ? c->stageEv : nullptr; L.stats = c->statsDev; L.maxBlock = maxBlock;
     static const int sideMode = getenv("ZL_ENC_SIDE") ? atoi(getenv("ZL_ENC_SIDE")) : 2;       // (development: 0 off, 1 few blocks, 2 always; measured +3..4% on 4,096 blocks, +13% on 128)
     if (sideMode == 2 || (sideMode == 1 && nb <= 1024)) { L.side = c->side; L.sideFork = c->sideFork; L.sideJoin = c->sideJoin; }
     cudaError_t e = zl_launch_encode(L, st);

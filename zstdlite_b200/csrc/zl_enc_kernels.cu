@@ -212,37 +212,48 @@ __device__ __forceinline__ u32 zl_extend_match(const u32* __restrict__ wbase, u3
     }
 }
 
+// One CTA per block, one warp per SEGMENT of ZL_PARSE_SEG bytes (zl_enc_match.cuh): the greedy walk is a serial chain, so a
+// 128 KiB block is walked as four independent 32 KiB pieces (each starts with an unknown repeat-offset history and clips its
+// matches at its end, exactly like blocks do inside a frame) and the pieces are then packed into one record / literal array.
 __global__ void __launch_bounds__(ZL_PARSE_WARPS * 32)
 zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __restrict__ Marena, u32 slotM, u64* __restrict__ recArena,
            u32 slotRec, u8* __restrict__ litArena, u32 slotLit, u32* __restrict__ histArena, ZlEncBlockMeta* __restrict__ metas,
-           const ZlEncDictDev* __restrict__ dict)
+           const ZlEncDictDev* __restrict__ dict, u32 segmented)
 {
+    // segmented == 0: no block of the wave is longer than one segment; a CTA then takes four blocks, one per warp
     __shared__ u32 hist[ZL_PARSE_WARPS][256];
+    __shared__ u32 segSeq[ZL_PARSE_WARPS], segLit[ZL_PARSE_WARPS], segTail[ZL_PARSE_WARPS];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 blk = blockIdx.x * ZL_PARSE_WARPS + warp;
-    if (blk >= nblocks) return;
+    const u32 blk = segmented ? blockIdx.x : blockIdx.x * ZL_PARSE_WARPS + warp;
+    if (blk >= nblocks) return;                              // (only without segments: no CTA-wide barrier follows)
+    const u32 sg = segmented ? warp : 0u;
     for (u32 i = lane; i < 256; i += 32) hist[warp][i] = 0;
     __syncwarp();
     const ZlEncBlock b = blocks[blk];
     const u32 n = b.srcSize;
     const u32* __restrict__ M = Marena + (size_t)blk * slotM;
-    u64* __restrict__ recs = recArena + (size_t)blk * slotRec;
-    u8* __restrict__ lit = litArena + (size_t)blk * slotLit;
+    u64* __restrict__ recsAll = recArena + (size_t)blk * slotRec;
+    u8* __restrict__ litAll = litArena + (size_t)blk * slotLit;
+    const u32 segBeg = sg * ZL_PARSE_SEG, segEnd = min(n, segBeg + ZL_PARSE_SEG);
+    u64* __restrict__ recs = recsAll + (size_t)sg * ZL_PARSE_SEG_RECS;
+    u8* __restrict__ lit = litAll + segBeg;
     const u32 bias = (u32)(((size_t)b.src) & 3);
     const u32* __restrict__ wbase = reinterpret_cast<const u32*>(b.src - bias);
     const u32 lastWord = n ? (bias + n - 1) >> 2 : 0;
     const u32 ltMask = (1u << lane) - 1;
-    const bool first = (b.flags & ZL_BLK_FIRST) != 0;
-    ZlReps reps;                                             // zl_enc_match.cuh: unknown history (0) for non-first blocks
+    const bool firstBlk = (b.flags & ZL_BLK_FIRST) != 0;
+    const bool first = firstBlk && sg == 0;                  // only the first segment of a frame knows the decoder's history
+    ZlReps reps;                                             // zl_enc_match.cuh: unknown history (0) otherwise
     reps.r0 = first ? 1u : 0u; reps.r1 = first ? 4u : 0u; reps.r2 = first ? 8u : 0u;
     if (first && dict && dict->hasEntropy) { reps.r0 = dict->rep[0]; reps.r1 = dict->rep[1]; reps.r2 = dict->rep[2]; }    // zstd.c:27450 (dictionary repcodes)
-    const bool repPref = first && dict != nullptr;
-    u32 p = 0, anchor = 0, nseq = 0, nlit = 0;
+    const bool repPref = firstBlk && dict != nullptr;
+    u32 p = segBeg, anchor = segBeg, nseq = 0, nlit = 0;
+    if (segBeg < n) {
     // M and the source bytes are fetched one 128-position super-window ahead (the walk itself never waits on memory)
     u32 mq[4], bq[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) { const u32 x = 32 * k + lane; mq[k] = x < n ? __ldcs(M + x) : 0u; bq[k] = x < n ? (u32)b.src[x] : 0u; }
-    for (u32 sw = 0; sw < n; sw += 128) {
+    for (int k = 0; k < 4; k++) { const u32 x = segBeg + 32 * k + lane; mq[k] = x < n ? __ldcs(M + x) : 0u; bq[k] = x < n ? (u32)b.src[x] : 0u; }
+    for (u32 sw = segBeg; sw < segEnd; sw += 128) {
         u32 mc[4], bc[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) { mc[k] = mq[k]; bc[k] = bq[k]; }
@@ -251,7 +262,7 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const u32 w0 = sw + 32 * k;
-            if (w0 >= n || p >= w0 + 32) continue;               // past the end / window entirely inside a match
+            if (w0 >= segEnd || p >= w0 + 32) continue;          // past the end / window entirely inside a match
             const u32 m = mc[k], byte = bc[k];
             const u32 pos = w0 + lane;
             u32 len = m & 0xFF;
@@ -267,24 +278,26 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
                 u32 l = __shfl_sync(ZL_FULL, len, c1);
                 u32 o = __shfl_sync(ZL_FULL, off, c1);
                 u32 pos1 = w0 + c1, c2 = c1;
-                if (l == ZL_M_CAP && o <= pos1) l = zl_extend_match(wbase, bias, lastWord, n, pos1, o, lane);   // (matches into the dictionary stay capped)
+                if (l == ZL_M_CAP && o <= pos1) l = zl_extend_match(wbase, bias, lastWord, segEnd, pos1, o, lane);   // (matches into the dictionary stay capped)
+                if (pos1 + l > segEnd) l = segEnd - pos1;        // a match ends with its segment
+                if (l < 3) { c = c1 + 1; continue; }             // (clipped below the format's minimum: literals)
                 if (repPref && reps.r0 && o != reps.r0) {
                     // Dictionary mode only: lanes 0..2 probe the most recent offset at pos1, pos1+1, pos1+2 (same window).  Such a
                     // match costs no offset bits; it is taken when it is at most 4 bytes shorter (cf. the repcode checks at
                     // ip+1 / ip+2 of zstd.c:29989, 30801).  Small dictionary-compressed inputs are dominated by offset cost.
                     const u32 q = pos1 + lane;
                     u32 rl = 0;
-                    if (lane < 3 && c1 + lane < 32 && reps.r0 <= q && q + 4 <= n) {
+                    if (lane < 3 && c1 + lane < 32 && reps.r0 <= q && q + 4 <= segEnd) {
                         u32 qlo, qhi;
                         zl_ld8(wbase, bias + q, lastWord, qlo, qhi);
-                        rl = zl_match_len(wbase, bias, lastWord, q, q - reps.r0, qlo, qhi, min(n - q, ZL_M_CAP));
+                        rl = zl_match_len(wbase, bias, lastWord, q, q - reps.r0, qlo, qhi, min(segEnd - q, ZL_M_CAP));
                     }
                     const u32 hit = __ballot_sync(ZL_FULL, rl >= 4 && rl + 4 >= l) & 7u;
                     if (hit) {
-                        const u32 k = (u32)__ffs((int)hit) - 1;
-                        c2 = c1 + k; pos1 += k; o = reps.r0;
-                        l = __shfl_sync(ZL_FULL, rl, k);
-                        if (l == ZL_M_CAP) l = zl_extend_match(wbase, bias, lastWord, n, pos1, o, lane);
+                        const u32 k2 = (u32)__ffs((int)hit) - 1;
+                        c2 = c1 + k2; pos1 += k2; o = reps.r0;
+                        l = __shfl_sync(ZL_FULL, rl, k2);
+                        if (l == ZL_M_CAP) l = zl_extend_match(wbase, bias, lastWord, segEnd, pos1, o, lane);
                     }
                 }
                 const u32 ll = pos1 - anchor;
@@ -301,7 +314,7 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
             const u32 endRel = lane + len;                       // meaningful on taken lanes
             const u32 e = __shfl_sync(ZL_FULL, endRel, t);
             const bool covered = below != 0 && e > lane;
-            const bool isLit = pos < n && lane >= cstart && !covered;
+            const bool isLit = pos < segEnd && lane >= cstart && !covered;
             const u32 litMask = __ballot_sync(ZL_FULL, isLit);
             if (isLit) { lit[nlit + __popc(litMask & ltMask)] = (u8)byte; atomicAdd(&hist[warp][byte], 1u); }
             nlit += __popc(litMask);
@@ -309,9 +322,49 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
             nseq += __popc(takenMask);
         }
     }
-    __syncwarp();
-    for (u32 i = lane; i < 256; i += 32) histArena[(size_t)blk * 256 + i] = hist[warp][i];
-    if (lane == 0) { metas[blk].nseq = nseq; metas[blk].nlit = nlit; }
+    }
+    if (!segmented) {
+        __syncwarp();
+        for (u32 i = lane; i < 256; i += 32) histArena[(size_t)blk * 256 + i] = hist[warp][i];
+        if (lane == 0) { metas[blk].nseq = nseq; metas[blk].nlit = nlit; }
+        return;
+    }
+    if (lane == 0) { segSeq[warp] = nseq; segLit[warp] = nlit; segTail[warp] = segBeg < n ? segEnd - anchor : 0u; }
+    __syncthreads();
+    // ---- pack the segments: records and literals of segment w move down behind those of the segments before it (the CTA moves
+    // one segment after the other, 128 elements per step, reads before writes: source and destination may overlap); the literals
+    // a segment ends with belong to the first sequence that follows (its litLength grows by that count)
+    const u32 tid = threadIdx.x;
+    u32 dSeq = segSeq[0], dLit = segLit[0], carry = segTail[0];
+    for (u32 w = 1; w < ZL_PARSE_WARPS; w++) {
+        const u32 ns = segSeq[w], nl = segLit[w];
+        const u64* __restrict__ rs = recsAll + (size_t)w * ZL_PARSE_SEG_RECS;
+        for (u32 i0 = 0; i0 < ns; i0 += ZL_PARSE_WARPS * 32) {
+            const u32 i = i0 + tid;
+            u64 r = i < ns ? rs[i] : 0ull;
+            if (i == 0) r += carry;                              // litLength is the low field of a record (zl_enc_rec)
+            __syncthreads();
+            if (i < ns) recsAll[dSeq + i] = r;
+            __syncthreads();
+        }
+        const u8* __restrict__ ls = litAll + (size_t)w * ZL_PARSE_SEG;
+        for (u32 i0 = 0; i0 < nl; i0 += ZL_PARSE_WARPS * 32) {
+            const u32 i = i0 + tid;
+            const u8 v = i < nl ? ls[i] : (u8)0;
+            __syncthreads();
+            if (i < nl) litAll[dLit + i] = v;
+            __syncthreads();
+        }
+        carry = ns ? segTail[w] : carry + segTail[w];
+        dSeq += ns; dLit += nl;
+    }
+    for (u32 i = tid; i < 256; i += ZL_PARSE_WARPS * 32) {
+        u32 v = 0;
+#pragma unroll
+        for (int w = 0; w < ZL_PARSE_WARPS; w++) v += hist[w][i];
+        histArena[(size_t)blk * 256 + i] = v;
+    }
+    if (tid == 0) { metas[blk].nseq = dSeq; metas[blk].nlit = dLit; }
 }
 
 // ---------------------------------------------------------------------------------------------- E3: literals
@@ -644,7 +697,9 @@ cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st)
         }
     }
     if (ev) cudaEventRecord(ev[1], st);
-    if (nb) zl_k_parse<<<(nb + ZL_PARSE_WARPS - 1) / ZL_PARSE_WARPS, ZL_PARSE_WARPS * 32, 0, st>>>(L.blocks, nb, L.M, L.slotM, L.recs, L.slotRec, L.lit, L.slotLit, L.hist, L.metas, L.dict);
+    {   const u32 segmented = L.maxBlock > ZL_PARSE_SEG ? 1u : 0u;
+        if (nb) zl_k_parse<<<segmented ? nb : (nb + ZL_PARSE_WARPS - 1) / ZL_PARSE_WARPS, ZL_PARSE_WARPS * 32, 0, st>>>(L.blocks, nb, L.M, L.slotM, L.recs, L.slotRec, L.lit, L.slotLit,
+                                                                                                                    L.hist, L.metas, L.dict, segmented); }
     if (ev) cudaEventRecord(ev[2], st);
     if (L.stats) {                                                  // dictionary training stops after the parse
         if (nb) zl_k_dict_stats<<<(nb + ZL_PARSE_WARPS - 1) / ZL_PARSE_WARPS, ZL_PARSE_WARPS * 32, 0, st>>>(nb, L.recs, L.slotRec, L.hist, L.metas, L.stats);

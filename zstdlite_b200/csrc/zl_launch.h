@@ -130,6 +130,7 @@ struct ZlEncodeLaunch {
     const ZlEncDictDev* dict;          // device pointer to the digested dictionary, or null
     cudaEvent_t* stageEv;              // null or ZL_ENC_STAGES + 1 events
     cudaStream_t side = nullptr; cudaEvent_t sideFork = nullptr, sideJoin = nullptr;   // optional: sequence coding next to literal coding
+    u32 maxBlock = ZL_BLOCKSIZE_MAX;   // largest block of the wave (the parse kernel walks blocks of more than one segment with a CTA each)
     u32* stats = nullptr;              // dictionary training: sum literal / code statistics here after the parse and stop (zl_dict_train.cuh)
 };
 cudaError_t zl_enc_upload_const();
