@@ -74,7 +74,9 @@ ZL_HD u32 zl_common8(u32 alo, u32 ahi, u32 blo, u32 bhi)
 // The greedy walk (stage 2) is a serial chain; a block is walked as independent SEGMENTS of ZL_PARSE_SEG bytes (one warp each,
 // zl_k_parse).  A segment starts with an unknown repeat-offset history (only the first segment of a frame knows the decoder's)
 // and clips its matches at its end; the literals it ends with are added to the litLength of the next sequence of the block.
-#define ZL_PARSE_SEG 32768u
+#ifndef ZL_PARSE_SEG
+#define ZL_PARSE_SEG 16384u
+#endif
 #define ZL_PARSE_SEG_RECS (ZL_PARSE_SEG / 5 + 3)          // records of a segment: matches are >= 5 bytes, the clipped last one >= 3
 
 // repeat-offset bookkeeping while walking (zstd.c:19648-19652 offBase, 19688 ZSTD_updateRep): returns offBase

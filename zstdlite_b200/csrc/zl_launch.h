@@ -88,7 +88,7 @@ cudaError_t zl_launch_xxh64(const u8* const* ptrs, const u32* sizes, u64* out, u
 #include "zl_enc_match.cuh"
 
 #define ZL_MATCH_WARPS 15     // named barriers 1..15 carry the table token (0 is __syncthreads)
-#define ZL_PARSE_WARPS 4
+#define ZL_PARSE_WARPS (ZL_BLOCKSIZE_MAX / ZL_PARSE_SEG)     // one warp per segment of a block
 #define ZL_ASM_WARPS 4
 #define ZL_ENT_WARPS 4       // warps (= blocks) per CTA in the two entropy kernels
 #define ZL_ENC_STAGES 5      // match, parse, literals, sequences, plan+assemble
