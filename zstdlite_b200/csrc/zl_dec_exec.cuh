@@ -21,8 +21,10 @@
 
 ZL_D void zl_warp_copy(u8* dst, const u8* src, u32 n, u32 lane)
 {
-    // generic byte-granular cooperative copy with a 16-byte fast path when co-aligned
-    if (n >= 64 && ((((size_t)dst) ^ ((size_t)src)) & 15) == 0) {
+    // cooperative copy of non-overlapping ranges: 16 bytes per lane when source and destination are co-aligned, otherwise
+    // aligned 4-byte stores fed by funnel-shifted aligned loads (every word touched holds at least one valid byte)
+    if (n < 64) { for (u32 i = lane; i < n; i += 32) dst[i] = src[i]; return; }
+    if (((((size_t)dst) ^ ((size_t)src)) & 15) == 0) {
         u32 head = (u32)((16 - (((size_t)dst) & 15)) & 15);
         if (lane < head) dst[lane] = src[lane];
         u32 body = (n - head) >> 4;
@@ -31,9 +33,19 @@ ZL_D void zl_warp_copy(u8* dst, const u8* src, u32 n, u32 lane)
         for (u32 i = lane; i < body; i += 32) d4[i] = s4[i];
         u32 done = head + (body << 4);
         for (u32 i = done + lane; i < n; i += 32) dst[i] = src[i];
-    } else {
-        for (u32 i = lane; i < n; i += 32) dst[i] = src[i];
+        return;
     }
+    const u32 head = (u32)((4 - (((size_t)dst) & 3)) & 3);
+    if (lane < head) dst[lane] = src[lane];
+    const u8* s = src + head;
+    u32* d4 = (u32*)(dst + head);
+    const u32 words = (n - head) >> 2;
+    const u32 sh = (u32)(((size_t)s) & 3) * 8;
+    const u32* s4 = (const u32*)(((size_t)s) & ~(size_t)3);
+    if (sh == 0) for (u32 i = lane; i < words; i += 32) d4[i] = s4[i];
+    else for (u32 i = lane; i < words; i += 32) d4[i] = __funnelshift_r(s4[i], s4[i + 1], sh);
+    const u32 done = head + (words << 2);
+    if (done + lane < n) dst[done + lane] = src[done + lane];
 }
 
 ZL_D void zl_warp_fill(u8* dst, u32 byte, u32 n, u32 lane)
