@@ -191,6 +191,25 @@ def compress_leg(torch, dist, z, args, dev, rank, world):
         sizes = np.array(list(res), dtype=np.int64)
         assert not any(z.is_error(int(s)) for s in sizes), "compress errors"
         csize = int(sizes.sum())
+        # end to end (world == 1): the same 4 GiB as ONE pinned host buffer through zl_compress_split (what zstd_compress(frame_size=)
+        # calls): host-to-device staging, kernels and the copy back of the multi-frame stream inside the timed region
+        e2e = None
+        if world == 1 and lvl == 3 and not args.no_compress_e2e:
+            import ctypes as C
+            L = z._lib.lib()
+            hsrc = torch.empty(n * fb, dtype=torch.uint8).pin_memory(); hsrc.copy_(src.reshape(-1))
+            hcap = n * (bound + 8)
+            hdst = torch.empty(hcap, dtype=torch.uint8).pin_memory()
+            tt = []
+            for _ in range(3):
+                t0 = time.time()
+                r = L.zl_compress_split(cctx._p, C.c_void_p(hdst.data_ptr()), hcap, C.c_void_p(hsrc.data_ptr()), n * fb, fb, None, 0)
+                tt.append(time.time() - t0)
+                assert not z.is_error(r), z.error_name(r)
+            assert int(r) == csize
+            e2e = {"GBps": n * fb / min(tt[1:]) / 1e9, "ms": 1e3 * min(tt[1:]), "h2d_bytes": n * fb, "d2h_bytes": int(r),
+                   "how": "zl_compress_split on one pinned host buffer, wall clock of the call, best of 2 after a warm-up call"}
+            del hsrc, hdst
         # a sample of frames: round trip through libzstd and libzstd's own size for the same slab at the same level
         from oracle import ref
         ours = theirs = 0
@@ -206,6 +225,8 @@ def compress_leg(torch, dist, z, args, dev, rank, world):
                               "kernel_ms": cctx.last_kernel_ms,
                               "stages_ms": {nm: L.zl_cctx_last_stage_ms(cctx._p, k) for k, nm in enumerate(("match", "parse", "literals", "sequences", "plan+assemble"))},
                               "frames_per_gpu": n, "frame_bytes": fb, "n_gpus": world}
+        if e2e:
+            out[f"level{lvl}"]["e2e"] = e2e
     return out
 
 
@@ -404,6 +425,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--compress-frames", type=int, default=32768)
     ap.add_argument("--no-compress", action="store_true")
+    ap.add_argument("--no-compress-e2e", action="store_true")
     ap.add_argument("--dict-objects", type=int, default=100000)
     ap.add_argument("--no-dict", action="store_true")
     ap.add_argument("--df-rows", type=int, default=1000000)

@@ -128,6 +128,33 @@ def test_compress_split_is_a_standard_multi_frame_stream(z, ref):
     assert rr == len(d) and out.raw == d
 
 
+def test_compress_split_pipelined_host_path(z, ref):
+    """host buffers of >= 2 chunks take the staged pipeline (copies of neighbouring chunks overlap the kernels): same bytes as the
+    device-pointer path, a standard multi-frame stream for libzstd"""
+    import torch
+    from zstdlite_b200 import corpus
+    L = z._lib.lib()
+    fs = 16384
+    pool, _ = corpus.mixed_frames(2048, fs, pool=32, rotate=True)
+    data = np.tile(pool.reshape(-1), 9)[: 17000 * fs + 777]                    # 17,001 frames: two full chunks of 8,192 + a short one
+    n = data.size
+    nf = (n + fs - 1) // fs
+    cap = nf * (int(L.ZSTD_compressBound(fs)) + 8)
+    cctx = z.zstd_cctx(level=3, include_checksum=True)
+    hsrc = torch.from_numpy(data.copy()).pin_memory()
+    hdst = torch.zeros(cap, dtype=torch.uint8).pin_memory()
+    fsz = (C.c_size_t * nf)()
+    r = L.zl_compress_split(cctx._p, C.c_void_p(hdst.data_ptr()), cap, C.c_void_p(hsrc.data_ptr()), n, fs, fsz, 0)
+    assert not z.is_error(r), z.error_name(r)
+    assert sum(fsz) == r
+    blob = hdst[:r].numpy().tobytes()
+    dsrc = hsrc.cuda(); ddst = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    r2 = L.zl_compress_split(cctx._p, C.c_void_p(ddst.data_ptr()), cap, C.c_void_p(dsrc.data_ptr()), n, fs, None, 1)
+    assert r2 == r and ddst[:r].cpu().numpy().tobytes() == blob
+    assert ref.DCtx().decompress(blob, cap=n, all_frames=True) == data.tobytes()
+    assert z.zstd_decompress(blob, all_frames=True) == data.tobytes()
+
+
 def test_multi_frame_round_trip_through_the_package_api(z, ref):
     """split output and concatenated streams round-trip through zstd_compress / zstd_decompress /
     zstd_serialize / zstd_unserialize themselves (content sizes summed over all frames, one GPU batch)."""

@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <new>
+#include <chrono>
 #include "../../include/zstdlite_gpu.h"
 #include "zl_host.h"
 #include "zl_enc_dict.h"          // host-side dictionary digest (shared with the CPU emulation in tests/emul)
@@ -35,6 +36,10 @@ struct ZSTD_CCtx_s {
     size_t sOutPos = 0;
     bool sFlushing = false;
     cudaStream_t side = nullptr; cudaEvent_t sideFork = nullptr, sideJoin = nullptr;   // sequence coding next to literal coding
+    cudaStream_t copyIn = nullptr, copyOut = nullptr;      // zl_compress_split with host buffers: staging pipeline
+    cudaEvent_t evIn[2] = {}, evOut[2] = {}, evGather[2] = {};
+    struct { bool valid = false; void* dst = nullptr; const void* src = nullptr; size_t bytes = 0; int slot = 0; } pendIn;   // issued by zl_enc_run once its kernels are queued
+    ZlDevBuf dOutStage;
     u32* statsDev = nullptr;               // set by the dictionary trainer: parse only, statistics summed here (zl_dict_train.cuh)
 };
 
@@ -74,6 +79,8 @@ ZL_EXPORT size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
     if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
     for (cudaEvent_t e : c->stageEv) if (e) cudaEventDestroy(e);
     if (c->side) { cudaStreamDestroy(c->side); cudaEventDestroy(c->sideFork); cudaEventDestroy(c->sideJoin); }
+    if (c->copyIn) { cudaStreamDestroy(c->copyIn); cudaStreamDestroy(c->copyOut); for (int i = 0; i < 2; i++) { cudaEventDestroy(c->evIn[i]); cudaEventDestroy(c->evOut[i]); cudaEventDestroy(c->evGather[i]); } }
+    c->dOutStage.release();
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -262,6 +269,7 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
     return 0;
 }
 
+static void zl_copy_pieces(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s);
 // all frames, device pointers; synchronises; results in c->hResults
 static size_t zl_enc_run(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* srcSize, u8* const* ddst, const size_t* dstCap, size_t n)
 {
@@ -293,6 +301,13 @@ static size_t zl_enc_run(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* srcS
         cudaEventRecord(c->ev0, st);
         const size_t r = zl_enc_wave(c, dsrc, srcSize, ddst, dstCap, f0, f1, n, true);
         cudaEventRecord(c->ev1, st);
+        if (c->pendIn.valid) {
+            // staging copy of the NEXT chunk (zl_compress_split_pipelined): queued only now, behind this wave's descriptor uploads --
+            // a copy engine serves its requests in submission order, whatever their streams
+            zl_copy_pieces(c->pendIn.dst, c->pendIn.src, c->pendIn.bytes, cudaMemcpyHostToDevice, c->copyIn);
+            cudaEventRecord(c->evIn[c->pendIn.slot], c->copyIn);
+            c->pendIn.valid = false;
+        }
         if (zl_is_error(r)) { cudaStreamSynchronize(st); return r; }
         firstWave = false;
         f0 = f1;
@@ -405,6 +420,97 @@ ZL_EXPORT size_t ZSTD_compressStream2(ZSTD_CCtx* c, ZSTD_outBuffer* out, ZSTD_in
 ZL_ALIAS(size_t, ZSTD_compressStream2, (ZSTD_CCtx*, ZSTD_outBuffer*, ZSTD_inBuffer*, ZSTD_EndDirective))
 
 // One buffer -> concatenated independent frames of `frameSize` content bytes (a standard multi-frame zstd stream).
+// host buffers, many frames: chunks of frames are staged, compressed and copied back in a pipeline -- the host-to-device copy of
+// chunk k+1 and the device-to-host copy of chunk k-1 run (on their own streams) while chunk k is compressed
+// large staging copies go out in pieces of 16 MiB (bounded latency for small copies submitted behind them)
+static void zl_copy_pieces(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s)
+{
+    const size_t piece = (size_t)16 << 20;
+    for (size_t o = 0; o < bytes; o += piece)
+        cudaMemcpyAsync((u8*)dst + o, (const u8*)src + o, bytes - o < piece ? bytes - o : piece, kind, s);
+}
+static size_t zl_compress_split_pipelined(ZSTD_CCtx* c, void* dst, size_t dstCap, const u8* src, size_t srcSize, size_t frameSize,
+                                          size_t* frameSizes, size_t nf, size_t slot, size_t chunkFrames)
+{
+    cudaStream_t st = c->stream;
+    if (!c->copyIn) {
+        if (cudaStreamCreateWithFlags(&c->copyIn, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->copyOut, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); return ZL_ERROR(memory_allocation); }
+        for (int i = 0; i < 2; i++)
+            if (cudaEventCreateWithFlags(&c->evIn[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->evOut[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&c->evGather[i], cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); return ZL_ERROR(memory_allocation); }
+    }
+    const size_t chunkBytes = chunkFrames * frameSize, inHalf = (chunkBytes + 255) & ~(size_t)255, outHalf = (chunkFrames * slot + 255) & ~(size_t)255;
+    if (!c->dSrc.reserve(2 * inHalf + 64) || !c->dDst.reserve(chunkFrames * slot + 64) || !c->dOutStage.reserve(2 * outHalf + 64) ||
+        !c->hAux.reserve(chunkFrames * 24) || !c->dAux.reserve(chunkFrames * 24)) return ZL_ERROR(memory_allocation);
+    // chunk sizes grow 1/8, 1/4, 1/2, 1, 1, ... of a full chunk: the first staging copy, which nothing can overlap, is short
+    std::vector<size_t> cstart;
+    for (size_t f = 0, sz = chunkFrames / 8 ? chunkFrames / 8 : 1; f < nf; f += sz, sz = sz * 2 < chunkFrames ? sz * 2 : chunkFrames) cstart.push_back(f);
+    cstart.push_back(nf);
+    const size_t nchunks = cstart.size() - 1;
+    std::vector<const u8*> dsrc(chunkFrames); std::vector<u8*> ddst(chunkFrames); std::vector<size_t> ssz(chunkFrames), caps(chunkFrames, slot);
+    auto chunkRange = [&](size_t k, size_t* f0, size_t* bytes) {
+        *f0 = cstart[k];
+        const size_t b0 = cstart[k] * frameSize, b1 = cstart[k + 1] * frameSize < srcSize ? cstart[k + 1] * frameSize : srcSize;
+        *bytes = b1 - b0;
+    };
+    size_t total = 0, err = 0;
+    static const bool trace = getenv("ZL_ENC_TRACE") != nullptr;      // (development: host timeline of the chunks on stderr)
+    const auto t00 = std::chrono::steady_clock::now();
+    auto nowMs = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t00).count(); };
+    {   size_t f0, bytes; chunkRange(0, &f0, &bytes);
+        zl_copy_pieces(c->dSrc.p, src, bytes, cudaMemcpyHostToDevice, c->copyIn); cudaEventRecord(c->evIn[0], c->copyIn); }
+    for (size_t k = 0; k < nchunks && !err; k++) {
+        size_t f0, bytes; chunkRange(k, &f0, &bytes);
+        const size_t cnt = cstart[k + 1] - f0;
+        u8* inBase = c->dSrc.as<u8>() + (k & 1) * inHalf;
+        if (k + 1 < nchunks) {                                   // next chunk's input (its half was last read by chunk k-1, finished)
+            size_t g0, gbytes; chunkRange(k + 1, &g0, &gbytes);
+            c->pendIn.valid = true; c->pendIn.dst = c->dSrc.as<u8>() + ((k + 1) & 1) * inHalf; c->pendIn.src = src + g0 * frameSize;
+            c->pendIn.bytes = gbytes; c->pendIn.slot = (int)((k + 1) & 1);
+        }
+        cudaStreamWaitEvent(st, c->evIn[k & 1], 0);
+        for (size_t i = 0; i < cnt; i++) {
+            dsrc[i] = inBase + i * frameSize;
+            const size_t rem = bytes - i * frameSize;
+            ssz[i] = rem < frameSize ? rem : frameSize;
+            ddst[i] = c->dDst.as<u8>() + i * slot;
+        }
+        const double tA = nowMs();
+        const size_t r = zl_enc_run(c, dsrc.data(), ssz.data(), ddst.data(), caps.data(), cnt);
+        if (zl_is_error(r)) { err = r; break; }
+        if (trace) fprintf(stderr, "chunk %zu: compress call %.1f -> %.1f ms (kernels %.1f ms: match %.1f parse %.1f literals %.1f sequences %.1f assemble %.1f)\n", k, tA, nowMs(),
+                           c->lastKernelMs, c->lastStageMs[0], c->lastStageMs[1], c->lastStageMs[2], c->lastStageMs[3], c->lastStageMs[4]);
+        const u64* hr = c->hResults.as<u64>();
+        u64* hsz = c->hAux.as<u64>(); u64* hoff = hsz + cnt; const u8** hptr = reinterpret_cast<const u8**>(hoff + cnt);
+        size_t ctotal = 0;
+        for (size_t i = 0; i < cnt; i++) {
+            if (zl_is_error((size_t)hr[i])) { err = (size_t)hr[i]; break; }
+            hsz[i] = hr[i]; hoff[i] = ctotal; hptr[i] = ddst[i]; ctotal += (size_t)hr[i];
+            if (frameSizes) frameSizes[f0 + i] = (size_t)hr[i];
+        }
+        if (err) break;
+        if (total + ctotal > dstCap) { err = ZL_ERROR(dstSize_tooSmall); break; }
+        cudaMemcpyAsync(c->dAux.p, hsz, cnt * 24, cudaMemcpyHostToDevice, st);
+        u8* stage = c->dOutStage.as<u8>() + (k & 1) * outHalf;
+        if (k >= 2) cudaStreamWaitEvent(st, c->evOut[k & 1], 0);  // the copy back of chunk k-2 has left this half
+        const u64* dsz = c->dAux.as<u64>();
+        if (zl_launch_gather(reinterpret_cast<const u8* const*>(dsz + 2 * cnt), dsz, dsz + cnt, stage, (u32)cnt, st) != cudaSuccess) { err = ZL_ERROR(GENERIC); break; }
+        c->launches += 1;
+        cudaEventRecord(c->evGather[k & 1], st);
+        cudaStreamWaitEvent(c->copyOut, c->evGather[k & 1], 0);
+        if (ctotal) zl_copy_pieces((u8*)dst + total, stage, ctotal, cudaMemcpyDeviceToHost, c->copyOut);
+        cudaEventRecord(c->evOut[k & 1], c->copyOut);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { (void)cudaGetLastError(); err = ZL_ERROR(GENERIC); break; }   // hAux / dAux are reused by the next chunk
+        total += ctotal;
+    }
+    if (trace) fprintf(stderr, "chunks done at %.1f ms\n", nowMs());
+    const bool ok = cudaStreamSynchronize(c->copyIn) == cudaSuccess && cudaStreamSynchronize(c->copyOut) == cudaSuccess;
+    if (trace) fprintf(stderr, "copies done at %.1f ms\n", nowMs());
+    if (err) return err;
+    if (!ok) { (void)cudaGetLastError(); return ZL_ERROR(GENERIC); }
+    return total;
+}
+
 ZL_EXPORT size_t zl_compress_split(ZSTD_CCtx* c, void* dst, size_t dstCap, const void* src, size_t srcSize, size_t frameSize,
                                    size_t* frameSizes, int dev)
 {
@@ -413,6 +519,13 @@ ZL_EXPORT size_t zl_compress_split(ZSTD_CCtx* c, void* dst, size_t dstCap, const
     cudaStream_t st = c->stream;
     const size_t nf = srcSize ? (srcSize + frameSize - 1) / frameSize : 1;
     const size_t slot = (ZSTD_compressBound(frameSize) + 4 + 15) & ~(size_t)15;
+    {   // host buffers of >= 2 chunks of ~1 GiB (at most ZL_WAVE_BLOCKS blocks each): the pipelined path
+        const size_t blocksPerFrame = (frameSize + ZL_BLOCKSIZE_MAX - 1) / ZL_BLOCKSIZE_MAX;
+        size_t chunkFrames = ZL_WAVE_BLOCKS / blocksPerFrame;
+        if (chunkFrames * frameSize > ((size_t)1 << 30)) chunkFrames = ((size_t)1 << 30) / frameSize;
+        if (!dev && chunkFrames >= 1 && nf >= 2 * chunkFrames && chunkFrames * frameSize >= ((size_t)64 << 20))
+            return zl_compress_split_pipelined(c, dst, dstCap, (const u8*)src, srcSize, frameSize, frameSizes, nf, slot, chunkFrames);
+    }
     const u8* dsrcBase = (const u8*)src;
     if (!dev) {
         if (!c->dSrc.reserve(srcSize + 64)) return ZL_ERROR(memory_allocation);
