@@ -210,7 +210,7 @@ struct ZSTD_DCtx_s {
     // streaming session (ZSTD_decompressStream): input accumulated on the host until a whole frame is present
     std::vector<u8> sIn, sOut;
     size_t sOutPos = 0;
-    ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dNorm, dUnits, dCounters, dLargeIdx, dLb, dParent, dRemain, dSrc, dDst;
+    ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dNorm, dUnits, dCounters, dLargeIdx, dLb, dLc, dParent, dRemain, dSrc, dDst;
     ZlPinBuf hDescs, hResults, hLargeIdx, hRemain;
 };
 
@@ -228,7 +228,7 @@ ZL_EXPORT ZSTD_DCtx* ZSTD_createDCtx(void) { return new (std::nothrow) ZSTD_DCtx
 ZL_EXPORT size_t ZSTD_freeDCtx(ZSTD_DCtx* c)
 {
     if (!c) return 0;
-    ZlDevBuf* bufs[] = {&c->dDictContent, &c->dDict, &c->dDescs, &c->dInfos, &c->dResults, &c->dHdr, &c->dRec, &c->dCk, &c->dLit, &c->dNorm, &c->dUnits, &c->dCounters, &c->dLargeIdx, &c->dLb, &c->dParent, &c->dRemain, &c->dSrc, &c->dDst};
+    ZlDevBuf* bufs[] = {&c->dDictContent, &c->dDict, &c->dDescs, &c->dInfos, &c->dResults, &c->dHdr, &c->dRec, &c->dCk, &c->dLit, &c->dNorm, &c->dUnits, &c->dCounters, &c->dLargeIdx, &c->dLb, &c->dLc, &c->dParent, &c->dRemain, &c->dSrc, &c->dDst};
     for (ZlDevBuf* b : bufs) b->release();
     c->hDescs.release(); c->hResults.release(); c->hLargeIdx.release(); c->hRemain.release();
     if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
@@ -510,7 +510,7 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         return ZL_ERROR(memory_allocation);
     u32* hLarge = nullptr;
     if (nLargeTotal) {                          // scratch of the block-parallel path for large frames (zl_dec_large.cuh)
-        if (!c->hLargeIdx.reserve(nLargeTotal * 4) || !c->dLargeIdx.reserve(nLargeTotal * 4) || !c->dLb.reserve(hdr * sizeof(ZlLBlock)) ||
+        if (!c->hLargeIdx.reserve(nLargeTotal * 4) || !c->dLargeIdx.reserve(nLargeTotal * 4) || !c->dLb.reserve(hdr * sizeof(ZlLBlock)) || !c->dLc.reserve(((rec >> ZL_LCHUNK_LOG) + hdr + 2) * sizeof(ZlLChunk)) ||
             !c->dParent.reserve(par * 4 + 64) || !c->dRemain.reserve(nslices * 64 * sizeof(u32)) || !c->hRemain.reserve(nslices * 64))
             return ZL_ERROR(memory_allocation);
         hLarge = c->hLargeIdx.as<u32>();
@@ -553,7 +553,7 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         {   const u64 u0 = hd[a].hdrBase, u1 = cut[k + 1] < n ? hd[cut[k + 1]].hdrBase : hdr;      // the slice's share of the unit arena
             L.units = c->dUnits.as<ZlUnit>() + u0; L.unitCap = (u32)((u1 - u0) > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : (u1 - u0)); }
         L.counters = c->dCounters.as<u32>() + 4 * k;
-        L.nLarge = 0; L.largeIdx = nullptr; L.largeMaxBlocks = 0; L.largeMaxBytes = 0; L.lbArena = nullptr; L.parentArena = nullptr;
+        L.nLarge = 0; L.largeIdx = nullptr; L.largeMaxBlocks = 0; L.largeMaxBytes = 0; L.lbArena = nullptr; L.lcArena = nullptr; L.parentArena = nullptr;
         L.remain = nullptr; L.remainHost = nullptr;
         if (nLargeTotal) {
             L.largeIdx = c->dLargeIdx.as<u32>() + largeSeen;
@@ -563,7 +563,7 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
                 if (hd[i].dstCap > L.largeMaxBytes) L.largeMaxBytes = hd[i].dstCap;
             }
             largeSeen += L.nLarge;
-            L.lbArena = c->dLb.as<ZlLBlock>(); L.parentArena = c->dParent.as<u32>();
+            L.lbArena = c->dLb.as<ZlLBlock>(); L.lcArena = c->dLc.as<ZlLChunk>(); L.parentArena = c->dParent.as<u32>();
             L.remain = c->dRemain.as<u32>() + 64 * k; L.remainHost = c->hRemain.as<u32>() + 16 * k;
         }
         L.results = c->dResults.as<u64>() + a;

@@ -190,23 +190,46 @@ __device__ __forceinline__ void zl_fill_xtab(u32* xtab, u32 tid, u32 nthreads)
     for (u32 i = tid; i < ZL_XTAB_WORDS; i += nthreads)
         xtab[i] = i < 36 ? (c_tables.llBase[i] | ((u32)c_tables.llBits[i] << 24)) : (c_tables.mlBase[i - 36] | ((u32)c_tables.mlBits[i - 36] << 24));
 }
+// grid: x strides over the blocks of the frame, y = large frame, z * ZL_L_WARPS + warp = chunk of the block
 __global__ void __launch_bounds__(ZL_L_WARPS * 32)
 zl_k_lblock_scan(const u32* __restrict__ largeIdx, const ZlFrameDesc* __restrict__ descs, const ZlFrameInfo* __restrict__ infos,
-                 const ZlBlockHdr* __restrict__ hdrArena, const u64* __restrict__ recArena, ZlLBlock* lbArena)
+                 const ZlBlockHdr* __restrict__ hdrArena, const u64* __restrict__ recArena, ZlLChunk* lcArena)
 {
     __shared__ u32 xtab[ZL_XTAB_WORDS];
     zl_fill_xtab(xtab, threadIdx.x, ZL_L_WARPS * 32);
     __syncthreads();
-    const u32 frame = largeIdx[blockIdx.y], b = blockIdx.x * ZL_L_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const u32 frame = largeIdx[blockIdx.y], c = blockIdx.z * ZL_L_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const ZlFrameInfo info = infos[frame];
-    if (info.err || b >= info.nblocks) return;
+    if (info.err) return;
     const ZlFrameDesc d = descs[frame];
-    const ZlBlockHdr h = hdrArena[d.hdrBase + b];
-    zl_lblock_scan(h, recArena + d.recBase + h.recOff, xtab, lane, lbArena[d.hdrBase + b]);
+    ZlLChunk* lc = lcArena + ((d.recBase >> ZL_LCHUNK_LOG) + d.hdrBase);
+    for (u32 b = blockIdx.x; b < info.nblocks; b += gridDim.x) {
+        const ZlBlockHdr h = hdrArena[d.hdrBase + b];
+        if ((h.flags & 3) != 2 || !h.nrec || c >= zl_lchunks(h.nrec)) continue;
+        const u32 r0 = c << ZL_LCHUNK_LOG, r1 = min(h.nrec, r0 + ZL_LCHUNK_RECS);
+        zl_lchunk_scan(recArena + d.recBase + h.recOff, r0, r1, xtab, lane, lc[zl_lchunk_index(h.recOff, b) + c]);
+    }
+}
+// L2a / L2c: thread per block (x strides over the blocks of the frame, y = large frame)
+__global__ void __launch_bounds__(128)
+zl_k_lblock_compose(const u32* __restrict__ largeIdx, const ZlFrameDesc* __restrict__ descs, const ZlFrameInfo* __restrict__ infos,
+                    const ZlBlockHdr* __restrict__ hdrArena, ZlLBlock* lbArena, ZlLChunk* lcArena, u32 spread)
+{
+    const u32 frame = largeIdx[blockIdx.y];
+    const ZlFrameInfo info = infos[frame];
+    if (info.err) return;
+    const ZlFrameDesc d = descs[frame];
+    ZlLChunk* lc = lcArena + ((d.recBase >> ZL_LCHUNK_LOG) + d.hdrBase);
+    for (u32 b = blockIdx.x * 128 + threadIdx.x; b < info.nblocks; b += gridDim.x * 128) {
+        const ZlBlockHdr h = hdrArena[d.hdrBase + b];
+        ZlLChunk* C = lc + zl_lchunk_index(h.recOff, b);
+        if (spread) zl_lblock_spread(h, lbArena[d.hdrBase + b], C);
+        else zl_lblock_compose(h, C, lbArena[d.hdrBase + b]);
+    }
 }
 __global__ void __launch_bounds__(32)
-zl_k_lframe_prefix(const u32* __restrict__ largeIdx, const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, ZlLBlock* lbArena,
-                   const ZlDictDev* dict)
+zl_k_lframe_prefix(const u32* __restrict__ largeIdx, const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos,
+                   const ZlBlockHdr* __restrict__ hdrArena, ZlLBlock* lbArena, const ZlDictDev* dict)
 {
     const u32 frame = largeIdx[blockIdx.x];
     if (threadIdx.x != 0) return;
@@ -215,28 +238,36 @@ zl_k_lframe_prefix(const u32* __restrict__ largeIdx, const ZlFrameDesc* __restri
     const ZlFrameDesc d = descs[frame];
     u32 r0 = 1, r1 = 4, r2 = 8, total = 0;                            // zstd.c:15416
     if (dict && dict->hasEntropy) { r0 = dict->rep[0]; r1 = dict->rep[1]; r2 = dict->rep[2]; }
-    const u32 err = zl_lframe_prefix(d, info, lbArena + d.hdrBase, r0, r1, r2, &total);
+    const u32 err = zl_lframe_prefix(d, info, hdrArena + d.hdrBase, lbArena + d.hdrBase, r0, r1, r2, &total);
     infos[frame].err = err; infos[frame].totalOut = total;
 }
 template <bool kDict>
 __global__ void __launch_bounds__(ZL_L_WARPS * 32)
 zl_k_lblock_emit(const u32* __restrict__ largeIdx, const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos,
                  const ZlBlockHdr* __restrict__ hdrArena, const u64* __restrict__ recArena, const u8* __restrict__ litArena,
-                 const ZlLBlock* __restrict__ lbArena, u32* parentArena, const ZlDictDev* dict)
+                 const ZlLBlock* __restrict__ lbArena, const ZlLChunk* __restrict__ lcArena, u32* parentArena, const ZlDictDev* dict)
 {
     __shared__ u32 xtab[ZL_XTAB_WORDS];
     zl_fill_xtab(xtab, threadIdx.x, ZL_L_WARPS * 32);
     __syncthreads();
-    const u32 frame = largeIdx[blockIdx.y], b = blockIdx.x * ZL_L_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const u32 frame = largeIdx[blockIdx.y], c = blockIdx.z * ZL_L_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const ZlFrameInfo info = infos[frame];
-    if (info.err || b >= info.nblocks) return;
+    if (info.err) return;
     const ZlFrameDesc d = descs[frame];
-    const ZlBlockHdr h = hdrArena[d.hdrBase + b];
-    const u32 litMode = (h.flags >> 4) & 3;
-    const u8* lit = litMode == 0 ? d.src + h.srcOff : litArena + d.litBase + h.litOff;
-    const u32 err = zl_lblock_emit<kDict>(d.dst, parentArena + d.parBase, d, h, lbArena[d.hdrBase + b], lit, recArena + d.recBase + h.recOff,
-                                          kDict ? dict->content : nullptr, kDict ? dict->contentSize : 0u, xtab, lane);
-    if (err && lane == 0) infos[frame].err = err;
+    const ZlLChunk* lc = lcArena + ((d.recBase >> ZL_LCHUNK_LOG) + d.hdrBase);
+    for (u32 b = blockIdx.x; b < info.nblocks; b += gridDim.x) {
+        const ZlBlockHdr h = hdrArena[d.hdrBase + b];
+        const bool comp = (h.flags & 3) == 2;
+        const u32 nch = comp ? zl_lchunks(h.nrec) : 1u;
+        if (c >= nch) continue;
+        const u32 litMode = (h.flags >> 4) & 3;
+        const u8* lit = litMode == 0 ? d.src + h.srcOff : litArena + d.litBase + h.litOff;
+        const u32 r0 = c << ZL_LCHUNK_LOG, r1 = comp ? min(h.nrec, r0 + ZL_LCHUNK_RECS) : 0u;
+        const u32 err = zl_lchunk_emit<kDict>(d.dst, parentArena + d.parBase, d, h, lbArena[d.hdrBase + b], lc[comp ? zl_lchunk_index(h.recOff, b) + c : 0u], r0, r1,
+                                              c + 1 == nch, lit, recArena + d.recBase + h.recOff, kDict ? dict->content : nullptr,
+                                              kDict ? dict->contentSize : 0u, xtab, lane);
+        if (err && lane == 0) infos[frame].err = err;
+    }
 }
 // one pass of pointer jumping over the bytes of the large frames; remain[pass] counts the bytes still open after it
 __global__ void __launch_bounds__(256)
@@ -360,11 +391,17 @@ cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
     else
         zl_k_execute<false><<<g2, ZL_EXEC_WARPS * 32, 0, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.results, L.nframes, nullptr);
     if (L.nLarge) {                                                   // block-parallel path for the large frames of this slice
-        const dim3 gb((L.largeMaxBlocks + ZL_L_WARPS - 1) / ZL_L_WARPS, L.nLarge);
-        zl_k_lblock_scan<<<gb, ZL_L_WARPS * 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.recArena, L.lbArena);
-        zl_k_lframe_prefix<<<L.nLarge, 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.lbArena, L.dict);
-        if (L.dict) zl_k_lblock_emit<true><<<gb, ZL_L_WARPS * 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.lbArena, L.parentArena, L.dict);
-        else zl_k_lblock_emit<false><<<gb, ZL_L_WARPS * 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.lbArena, L.parentArena, nullptr);
+        // x strides over the blocks (about one CTA per 16 KiB of content, at most one per possible block), z covers the chunks of a block
+        u32 gxb = (u32)(L.largeMaxBytes >> 14) + 64;
+        if (gxb > L.largeMaxBlocks) gxb = L.largeMaxBlocks;
+        const dim3 gb(gxb ? gxb : 1u, L.nLarge, (ZL_LCHUNK_MAX + ZL_L_WARPS - 1) / ZL_L_WARPS);
+        zl_k_lblock_scan<<<gb, ZL_L_WARPS * 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.recArena, L.lcArena);
+        const dim3 gt((gxb + 127) / 128 ? (gxb + 127) / 128 : 1u, L.nLarge);
+        zl_k_lblock_compose<<<gt, 128, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.lbArena, L.lcArena, 0u);
+        zl_k_lframe_prefix<<<L.nLarge, 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.lbArena, L.dict);
+        zl_k_lblock_compose<<<gt, 128, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.lbArena, L.lcArena, 1u);
+        if (L.dict) zl_k_lblock_emit<true><<<gb, ZL_L_WARPS * 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.lbArena, L.lcArena, L.parentArena, L.dict);
+        else zl_k_lblock_emit<false><<<gb, ZL_L_WARPS * 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.lbArena, L.lcArena, L.parentArena, nullptr);
         cudaMemsetAsync(L.remain, 0, (ZL_LJUMP_MAX_PASSES + 2) * sizeof(u32), st);
         u32 gx = (u32)((L.largeMaxBytes + 255) / 256);
         if (gx > 148u * 64u) gx = 148u * 64u;

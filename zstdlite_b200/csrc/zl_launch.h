@@ -39,13 +39,31 @@ struct ZlDictDev {
 #define ZL_PAR_DONE 0xFFFFFF00u
 #define ZL_LJUMP_MAX_PASSES 40
 struct ZlSymSlot { u32 kind, val; };         // symbolic history slot: kind 0..2 = incoming slot minus val, kind 3 = the constant val
-struct ZlLBlock {                            // per block of a large frame (48 B)
-    u32 regen;                               // bytes the block regenerates
-    u32 outOff;                              // frame-relative output offset (L2)
-    u32 h[3];                                // history before the block (L2)
-    ZlSymSlot t[3];                          // the block's transform of the history (L1)
+struct ZlLBlock {                            // per block of a large frame (64 B)
+    u32 regen;                               // bytes the block regenerates (L2b)
+    u32 outOff;                              // frame-relative output offset (L2b)
     u32 err;
+    u32 sumL, sumO;                          // sums over its chunks (L2a)
+    ZlSymSlot t[3];                          // the block's transform of the repeat-offset history = its chunks' composed (L2a)
+    u32 h[3];                                // history before the block (L2b)
+    u32 pad[2];
 };
+// The records of a block are handled in CHUNKS of ZL_LCHUNK_RECS (a warp each in L1 and L3): a 128 KiB block has ~12 of them.
+#define ZL_LCHUNK_LOG 10
+#define ZL_LCHUNK_RECS (1u << ZL_LCHUNK_LOG)
+#define ZL_LCHUNK_MAX ((ZL_BLOCKSIZE_MAX / 3 + ZL_LCHUNK_RECS) >> ZL_LCHUNK_LOG)     // chunks of one block: <= 128 KiB / 3 records + spares
+struct ZlLChunk {                            // per chunk (56 B)
+    u32 sumL, sumO;                          // literal bytes / output bytes of its records (L1)
+    ZlSymSlot t[3];                          // its transform of the repeat-offset history (L1)
+    u32 outOff, litOff;                      // frame-relative output offset, block-relative literal offset (L2)
+    u32 h[3];                                // history before the chunk (L2)
+    u32 pad;
+};
+// chunks of a block with nrec records (at least one: it carries the block's last literals / the raw or RLE body)
+static inline __host__ __device__ u32 zl_lchunks(u32 nrec) { return nrec ? (nrec + ZL_LCHUNK_RECS - 1) >> ZL_LCHUNK_LOG : 1u; }
+// index of a block's first chunk inside its frame's share of the chunk arena: blocks are told apart by their record offset
+// (a block owns >= nrec + 8 record slots) plus their number
+static inline __host__ __device__ u32 zl_lchunk_index(u32 recOff, u32 block) { return (recOff >> ZL_LCHUNK_LOG) + block; }
 
 struct ZlDecodeLaunch {          // one slice of a batch: frames [frameBase, frameBase + nframes)
     const ZlFrameDesc* descs;    // this slice's descriptors / infos / results ...
@@ -69,6 +87,7 @@ struct ZlDecodeLaunch {          // one slice of a batch: frames [frameBase, fra
     u32 nLarge, largeMaxBlocks;  // count; largest hdrCap among them (grid bound for the warp-per-block kernels)
     u64 largeMaxBytes;           // largest dstCap among them (grid bound for the pointer-jumping passes)
     ZlLBlock* lbArena;    // per-block scratch, indexed like hdrArena
+    ZlLChunk* lcArena;           // per-chunk scratch: frame share starts at (recBase >> ZL_LCHUNK_LOG) + hdrBase
     u32* parentArena;            // one u32 per output byte of the large frames
     u32* remain;                 // device: open bytes after every pass
     u32* remainHost;             // pinned host word for the convergence check
