@@ -32,6 +32,20 @@ ZL_D u32 zl_sym_apply(const ZlSymSlot& s, u32 h0, u32 h1, u32 h2)
     return h > s.val ? h - s.val : 0u;               // 0 = invalid offset (caught where it is used)
 }
 
+// parent[0 .. n) = ZL_PAR_DONE, 16 bytes per lane where aligned
+ZL_D void zl_mark_done(u32* parent, u32 n, u32 lane)
+{
+    u32 head = (u32)((4 - ((((size_t)parent) >> 2) & 3)) & 3);
+    if (head > n) head = n;
+    if (lane < head) parent[lane] = ZL_PAR_DONE;
+    const u32 body = (n - head) >> 2;
+    uint4* p4 = (uint4*)(parent + head);
+    const uint4 v = make_uint4(ZL_PAR_DONE, ZL_PAR_DONE, ZL_PAR_DONE, ZL_PAR_DONE);
+    for (u32 i = lane; i < body; i += 32) p4[i] = v;
+    const u32 done = head + (body << 2);
+    if (done + lane < n) parent[done + lane] = ZL_PAR_DONE;
+}
+
 // ---- L1 ------------------------------------------------------------------------------------------------------------
 // records [r0, r1) of a compressed block
 ZL_D void zl_lchunk_scan(const u64* __restrict__ recs, u32 r0, u32 r1, const u32* xtab, u32 lane, ZlLChunk& outC)
@@ -157,7 +171,7 @@ ZL_D u32 zl_lchunk_emit(u8* out, u32* parent, const ZlFrameDesc& d, const ZlBloc
     if (type != 2) {                                               // raw / RLE block: final bytes
         if (type == 0) zl_warp_copy(out + op, d.src + h.srcOff, h.regenSize, lane);
         else zl_warp_fill(out + op, (h.flags >> 8) & 0xFF, h.regenSize, lane);
-        for (u32 i = lane; i < h.regenSize; i += 32) parent[op + i] = ZL_PAR_DONE;
+        zl_mark_done(parent + op, h.regenSize, lane);
         return 0;
     }
     const u32 litMode = (h.flags >> 4) & 3, rleByte = (h.flags >> 8) & 0xFF;
@@ -177,7 +191,18 @@ ZL_D u32 zl_lchunk_emit(u8* out, u32* parent, const ZlFrameDesc& d, const ZlBloc
         if (totalL > litSize - litPos) return ZL_E_corruption_detected;
         if ((outPos - op) + totalO > B.regen) return ZL_E_corruption_detected;                       // (sizes were summed by L1 / L2)
         if (__ballot_sync(ZL_FULL, isM && (off == 0 || off > dm + dictSize))) return ZL_E_corruption_detected;   // zstd.c:44066
-        // literals: final bytes
+        // literals: final bytes.  Long runs (literal-heavy blocks: few sequences, tens of kilobytes of literals) go segment by
+        // segment through the vectorised copy; short ones through the flat byte-parallel loop
+        if (totalL >= 1024) {
+            for (u32 k = 0; k < 32; k++) {
+                const u32 kll = __shfl_sync(ZL_FULL, ll, k);
+                if (!kll) continue;
+                const u32 kDst = __shfl_sync(ZL_FULL, dstLit, k), kEx = __shfl_sync(ZL_FULL, litExcl, k);
+                if (litMode == 1) zl_warp_fill(out + kDst, rleByte, kll, lane);
+                else zl_warp_copy(out + kDst, lit + litPos + kEx, kll, lane);
+                zl_mark_done(parent + kDst, kll, lane);
+            }
+        } else
         for (u32 j0 = 0; j0 < totalL; j0 += 32) {
             const u32 j = j0 + lane;
             const u32 k = zl_flat_owner(sl, j);
@@ -212,7 +237,7 @@ ZL_D u32 zl_lchunk_emit(u8* out, u32* parent, const ZlFrameDesc& d, const ZlBloc
     if ((outPos - op) + lastLL != B.regen) return ZL_E_corruption_detected;
     if (litMode == 1) zl_warp_fill(out + outPos, rleByte, lastLL, lane);
     else zl_warp_copy(out + outPos, lit + litPos, lastLL, lane);
-    for (u32 i = lane; i < lastLL; i += 32) parent[outPos + i] = ZL_PAR_DONE;
+    zl_mark_done(parent + outPos, lastLL, lane);
     return 0;
 }
 
