@@ -313,7 +313,7 @@ def dict_leg(torch, z, args, dev):
     # training: the GPU trainer (csrc/zl_dict_train.cuh) against the reference's ZDICT_trainFromBuffer on the same samples
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        z.zstd_train_dict_compress(train[:2000], 5000)                  # warm-up (contexts, module load)
+        z.zstd_train_dict_compress(train, 5000)                         # warm-up (contexts and arenas of the trainer are kept for the process)
         t0 = time.time(); d = z.zstd_train_dict_compress(train, 5000); t_gpu = time.time() - t0
     t0 = time.time(); d_ref = ref.train_dict(train, 5000); t_ref = time.time() - t0
     sizes = [len(o) for o in objs]

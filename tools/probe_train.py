@@ -12,7 +12,7 @@ objs = corpus.small_objects(n + 5000)
 train = objs[:n]
 test = objs[n:n + 5000]
 t = time.time(); d_ref = ref.train_dict(train, size); t_ref = time.time() - t
-z.zstd_train_dict_compress(train[:2000], size)          # warm-up (context creation, module load)
+z.zstd_train_dict_compress(train, size, optim=optim)   # warm-up (contexts and arenas of the trainer are kept for the process)
 t = time.time(); d_gpu = z.zstd_train_dict_compress(train, size, optim=optim); t_gpu = time.time() - t
 print(f"samples {n} ({sum(map(len, train))} B), dict {size}: ZDICT {t_ref:.2f}s ({len(d_ref)} B), GPU {t_gpu:.3f}s ({len(d_gpu)} B), ids {z.zstd_dict_id(d_ref)} {z.zstd_dict_id(d_gpu)}")
 # the k the reference's fastCOVER search picked, and the GPU trainer forced to the same k: equal IDs = equal content

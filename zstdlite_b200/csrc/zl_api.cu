@@ -574,8 +574,8 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         // ... and batches of a few (large) frames, whose block units leave most of the device idle: a 16 MiB frame 9.4 -> 6.8 ms
         const bool fewFrames = n <= 16 && nslices == 1 && !stageTimed && zl_dctx_lanes(c);
         if ((nslices > 1 && !dev) || fewFrames) { const int ln = (int)(k % ZL_DEC_LANES); L.side = c->side[ln]; L.sideFork = c->sideFork[ln]; L.sideJoin = c->sideJoin[ln]; }
+        L.launched = &c->launches;
         e = zl_launch_decode(L, ls);
-        c->launches += 3 + (verify ? 1 : 0);
         if (trace) cudaEventRecord(tev[3 * k + 1], ls);
         if (!dev) for (size_t r = drunCut[k]; r < drunCut[k + 1]; r++)
             if (druns[r].bytes) cudaMemcpyAsync((void*)druns[r].hbase, c->dDst.as<u8>() + druns[r].devOff, druns[r].bytes, cudaMemcpyDeviceToHost, ls);

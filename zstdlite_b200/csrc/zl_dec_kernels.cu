@@ -363,6 +363,7 @@ cudaError_t zl_decode_grid_limits(u32* litCtas, u32* seqCtas)
 cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
 {
     if (L.nframes == 0) return cudaSuccess;
+    unsigned long long nk = 0;
     const size_t smA = zl_literals_smem_bytes(), smB = zl_sequences_smem_bytes();
     u32 litCtas = 0, seqCtas = 0;
     cudaError_t e = zl_decode_grid_limits(&litCtas, &seqCtas);
@@ -378,11 +379,14 @@ cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
     if (ev) cudaEventRecord(ev[0], st);
     cudaMemsetAsync(L.counters, 0, 3 * sizeof(u32), st);              // unit count, literal cursor, sequence cursor
     zl_k_index<<<(L.nframes + 127) / 128, 128, 0, st>>>(L.descs, L.infos, L.hdrArena, L.units, L.counters, L.unitCap, L.nframes, L.frameBase, L.dict);
+    nk++;
     const bool useSide = L.side && !ev;
     if (useSide) { cudaEventRecord(L.sideFork, st); cudaStreamWaitEvent(L.side, L.sideFork, 0); }
     zl_k_literals<<<litCtas, 32, smA, st>>>(L.descsAll, L.infosAll, L.hdrArena, L.litArena, L.units, L.counters, L.counters + 1, L.dict);
+    nk++;
     if (ev) cudaEventRecord(ev[1], st);
     zl_k_sequences<<<seqCtas, 32, smB, useSide ? L.side : st>>>(L.descsAll, L.infosAll, L.hdrArena, L.recArena, L.normArena, L.units, L.counters, L.counters + 2, L.dict);
+    nk++;
     if (useSide) { cudaEventRecord(L.sideJoin, L.side); cudaStreamWaitEvent(st, L.sideJoin, 0); }
     if (ev) cudaEventRecord(ev[2], st);
     const u32 g2 = (L.nframes + ZL_EXEC_WARPS - 1) / ZL_EXEC_WARPS;
@@ -390,18 +394,24 @@ cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
         zl_k_execute<true><<<g2, ZL_EXEC_WARPS * 32, 0, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.results, L.nframes, L.dict);
     else
         zl_k_execute<false><<<g2, ZL_EXEC_WARPS * 32, 0, st>>>(L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.results, L.nframes, nullptr);
+    nk++;
     if (L.nLarge) {                                                   // block-parallel path for the large frames of this slice
         // x strides over the blocks (about one CTA per 16 KiB of content, at most one per possible block), z covers the chunks of a block
         u32 gxb = (u32)(L.largeMaxBytes >> 14) + 64;
         if (gxb > L.largeMaxBlocks) gxb = L.largeMaxBlocks;
         const dim3 gb(gxb ? gxb : 1u, L.nLarge, (ZL_LCHUNK_MAX + ZL_L_WARPS - 1) / ZL_L_WARPS);
         zl_k_lblock_scan<<<gb, ZL_L_WARPS * 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.recArena, L.lcArena);
+        nk++;
         const dim3 gt((gxb + 127) / 128 ? (gxb + 127) / 128 : 1u, L.nLarge);
         zl_k_lblock_compose<<<gt, 128, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.lbArena, L.lcArena, 0u);
+        nk++;
         zl_k_lframe_prefix<<<L.nLarge, 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.lbArena, L.dict);
+        nk++;
         zl_k_lblock_compose<<<gt, 128, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.lbArena, L.lcArena, 1u);
+        nk++;
         if (L.dict) zl_k_lblock_emit<true><<<gb, ZL_L_WARPS * 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.lbArena, L.lcArena, L.parentArena, L.dict);
         else zl_k_lblock_emit<false><<<gb, ZL_L_WARPS * 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.hdrArena, L.recArena, L.litArena, L.lbArena, L.lcArena, L.parentArena, nullptr);
+        nk++;
         cudaMemsetAsync(L.remain, 0, (ZL_LJUMP_MAX_PASSES + 2) * sizeof(u32), st);
         u32 gx = (u32)((L.largeMaxBytes + 255) / 256);
         if (gx > 148u * 64u) gx = 148u * 64u;
@@ -411,6 +421,7 @@ cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
             const u32 group = pass == 1 ? 6u : 4u;                    // passes are launched in groups; the host looks at the counter in between
             for (u32 k = 0; k < group && pass <= ZL_LJUMP_MAX_PASSES; k++, pass++)
                 zl_k_ljump<<<gj, 256, 0, st>>>(L.largeIdx, L.descs, L.infos, L.parentArena, L.remain, pass);
+                nk++;
             lastPass = pass - 1;
             u32 open = 1;
             if (cudaMemcpyAsync(L.remainHost, L.remain + lastPass, sizeof(u32), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
@@ -419,13 +430,16 @@ cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
             if (!open || pass > ZL_LJUMP_MAX_PASSES) break;
         }
         zl_k_lfinish<<<(L.nLarge + 127) / 128, 128, 0, st>>>(L.largeIdx, L.nLarge, L.infos, L.results, L.remain, lastPass);
+        nk++;
     }
     if (ev) cudaEventRecord(ev[3], st);
     if (L.verifyChecksum) {
         const u32 g3 = (L.nframes * 4 + 127) / 128;
         zl_k_checksum<<<g3, 128, 0, st>>>(L.descs, L.infos, L.results, L.nframes);
+        nk++;
     }
     if (ev) cudaEventRecord(ev[4], st);
+    if (L.launched) *L.launched += nk;
     return cudaGetLastError();
 }
 

@@ -203,6 +203,7 @@ static u64 zl_host_xxh64(const u8* p, size_t len)        // zstd.c:11509-11664, 
 }
 
 #include <chrono>
+#include <mutex>
 static double zl_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 struct ZlTrainJob {
     double tSelect = 0, tStats = 0, tEval = 0;
@@ -296,7 +297,13 @@ static size_t zl_train(void* dictBuffer, size_t dictCap, const void* samplesBuff
     if (splitPoint <= 0.0 || splitPoint > 1.0) return ZL_ERROR(parameter_outOfBound);
     if (dPar != 0 && dPar != 6 && dPar != 8) return ZL_ERROR(parameter_outOfBound);  // zstd.c:49344
     if (kPar != 0 && (kPar > dictCap || kPar < (dPar ? dPar : 8))) return ZL_ERROR(parameter_outOfBound);
+    // the two compression contexts and the device buffers of the trainer are kept for the process (grow-only, like a context's
+    // arenas): a second training does not pay the allocations again.  One training at a time.
+    static std::mutex trainLock;
+    static ZSTD_CCtx* keepStat = nullptr; static ZSTD_CCtx* keepEval = nullptr; static ZlTrainBufs keepBufs;
+    std::lock_guard<std::mutex> guard(trainLock);
     ZlTrainJob J;
+    J.B = keepBufs;
     J.hostSamples = (const u8*)samplesBuffer; J.sizes = sizes; J.nb = nb; J.level = level ? level : 3; J.dictID = dictID;
     J.nbTrain = splitPoint < 1.0 ? (u32)((double)nb * splitPoint) : nb;             // zstd.c:49443-49446
     J.nbTest = splitPoint < 1.0 ? nb - J.nbTrain : nb;
@@ -315,7 +322,9 @@ static size_t zl_train(void* dictBuffer, size_t dictCap, const void* samplesBuff
     if (J.trainBytes < 16) return ZL_ERROR(srcSize_wrong);
     const u32 f = 20;
     const bool verbose = getenv("ZL_TRAIN_VERBOSE") != nullptr;      // (the reference reports through notificationLevel)
-    J.statCtx = ZSTD_createCCtx(); J.evalCtx = ZSTD_createCCtx();
+    if (!keepStat) keepStat = ZSTD_createCCtx();
+    if (!keepEval) keepEval = ZSTD_createCCtx();
+    J.statCtx = keepStat; J.evalCtx = keepEval;
     size_t result = ZL_ERROR(memory_allocation);
     std::vector<u8> best, cand;
     u64 bestScore = ~0ull; u32 bestK = 0, bestD = 0;
@@ -372,9 +381,9 @@ static size_t zl_train(void* dictBuffer, size_t dictCap, const void* samplesBuff
         if (verbose) fprintf(stderr, "zstdlite_gpu train: select %.1f ms, statistics %.1f ms, header + scoring %.1f ms\n", J.tSelect, J.tStats, J.tEval);
         if (!fatal && !best.empty()) { memcpy(dictBuffer, best.data(), best.size()); result = best.size(); if (kOut) *kOut = bestK; if (dOut) *dOut = bestD; }
     } while (0);
-    J.B.release();
-    if (J.statCtx) ZSTD_freeCCtx(J.statCtx);
-    if (J.evalCtx) ZSTD_freeCCtx(J.evalCtx);
+    keepBufs = J.B;                                       // (the buffers may have grown)
+    if (J.statCtx) { J.statCtx->statsDev = nullptr; ZSTD_CCtx_loadDictionary(J.statCtx, nullptr, 0); }
+    if (J.evalCtx) ZSTD_CCtx_loadDictionary(J.evalCtx, nullptr, 0);
     return result;
 }
 

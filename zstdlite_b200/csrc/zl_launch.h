@@ -95,6 +95,7 @@ struct ZlDecodeLaunch {          // one slice of a batch: frames [frameBase, fra
     cudaEvent_t* stageEv;        // null, or ZL_DEC_STAGES + 1 events recorded around each kernel (per-kernel timing for bench.py)
     // optional: the sequence kernel of the slice runs on `side`, next to the literal kernel (both only depend on the index kernel)
     cudaStream_t side = nullptr; cudaEvent_t sideFork = nullptr, sideJoin = nullptr;
+    unsigned long long* launched = nullptr;      // += kernels launched (bench.py's gpu_launches)
 };
 
 size_t zl_literals_smem_bytes();
