@@ -499,7 +499,10 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         d.srcSize = (u32)srcSize[i]; d.dstCap = (u32)dstCap[i];
         zl_plan_frame(d.srcSize, d.dstCap, worst, &d.litCap, &d.recCap, &d.hdrCap);
         d.litBase = lit; d.recBase = rec; d.hdrBase = hdr; d.parBase = par;
-        d.large = d.dstCap >= ZL_LARGE_FRAME_BYTES ? 1u : 0u;
+        // block-parallel execute path (zl_dec_large.cuh): frames of >= 1 MiB, and in batches of a few frames -- where a warp walking
+        // a frame block after block is the whole critical path -- every frame of more than two blocks
+        static const bool midOff = getenv("ZL_DEC_NOMID") != nullptr;             // (development switch)
+        d.large = (d.dstCap >= ZL_LARGE_FRAME_BYTES || (!midOff && n <= 16 && d.dstCap > 2 * ZL_BLOCKSIZE_MAX)) ? 1u : 0u;
         if (d.large) { par += ((u64)d.dstCap + 3) & ~3ull; nLargeTotal++; }
         lit += ((u64)d.litCap + 15) & ~15ull; rec += d.recCap; hdr += d.hdrCap;
     }

@@ -247,10 +247,11 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
         if (!c->hAux.reserve(nf * 16) || !c->dXxhPtrs.reserve(nf * 8) || !c->dXxhSizes.reserve(nf * 4) || !c->dXxh.reserve(nf * 8)) return ZL_ERROR(memory_allocation);
         const u8** hp = c->hAux.as<const u8*>();
         u32* hs = reinterpret_cast<u32*>(hp + nf);
-        for (size_t i = f0; i < f1; i++) { hp[i - f0] = dsrc[i]; hs[i - f0] = (u32)srcSize[i]; }
+        bool anyLarge = false;
+        for (size_t i = f0; i < f1; i++) { hp[i - f0] = dsrc[i]; hs[i - f0] = (u32)srcSize[i]; if (srcSize[i] >= ZL_LARGE_FRAME_BYTES) anyLarge = true; }
         cudaMemcpyAsync(c->dXxhPtrs.p, hp, nf * 8, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(c->dXxhSizes.p, hs, nf * 4, cudaMemcpyHostToDevice, st);
-        if (zl_launch_xxh64(c->dXxhPtrs.as<const u8*>(), c->dXxhSizes.as<u32>(), c->dXxh.as<u64>(), (u32)nf, st) != cudaSuccess) return ZL_ERROR(GENERIC);
+        if (zl_launch_xxh64(c->dXxhPtrs.as<const u8*>(), c->dXxhSizes.as<u32>(), c->dXxh.as<u64>(), (u32)nf, st, anyLarge) != cudaSuccess) return ZL_ERROR(GENERIC);
         c->launches += 1;
         xxh = c->dXxh.as<u64>();
     }

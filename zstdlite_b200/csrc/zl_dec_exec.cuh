@@ -308,16 +308,17 @@ ZL_D u64 zl_ld64u(const u8* p)
     if ((((size_t)p) & 3) == 0) return (u64)(*(const u32*)p) | ((u64)(*(const u32*)(p + 4)) << 32);
     return zl_rd64(p);
 }
-// all 4 lanes of the quad call this; result valid on every lane of the quad
-ZL_D u64 zl_quad_xxh64(const u8* p, u32 len, u32 q, u32 qmask, u32 qbase)
+// all 4 lanes of the quad call this; result valid on every lane of the quad.  `v` / `s0`: accumulator of lane q after the first
+// s0 stripes (zl_xxh_seed(q), 0 to start from the beginning)
+ZL_D u64 zl_xxh_seed(u32 q) { return q == 0 ? (ZL_P1 + ZL_P2) : (q == 1 ? ZL_P2 : (q == 2 ? 0ull : (0ull - ZL_P1))); }
+ZL_D u64 zl_quad_xxh64_from(const u8* p, u32 len, u64 v, u32 s0, u32 q, u32 qmask, u32 qbase)
 {
     u64 h;
     u32 done = 0;
     if (len >= 32) {
-        u64 v = q == 0 ? (ZL_P1 + ZL_P2) : (q == 1 ? ZL_P2 : (q == 2 ? 0ull : (0ull - ZL_P1)));
         const u32 stripes = len >> 5;
         const u8* pp = p + 8 * q;
-        for (u32 s = 0; s < stripes; s++) v = zl_xround(v, zl_ld64u(pp + 32 * s));
+        for (u32 s = s0; s < stripes; s++) v = zl_xround(v, zl_ld64u(pp + 32 * s));
         const u64 v1 = __shfl_sync(qmask, v, qbase + 0), v2 = __shfl_sync(qmask, v, qbase + 1);
         const u64 v3 = __shfl_sync(qmask, v, qbase + 2), v4 = __shfl_sync(qmask, v, qbase + 3);
         h = zl_rotl64(v1, 1) + zl_rotl64(v2, 7) + zl_rotl64(v3, 12) + zl_rotl64(v4, 18);
@@ -331,5 +332,41 @@ ZL_D u64 zl_quad_xxh64(const u8* p, u32 len, u32 q, u32 qmask, u32 qbase)
     while (r) { h ^= (u64)(*t++) * ZL_P5; h = zl_rotl64(h, 11) * ZL_P1; r--; }
     h ^= h >> 33; h *= ZL_P2; h ^= h >> 29; h *= ZL_P3; h ^= h >> 32;
     return h;
+}
+ZL_D u64 zl_quad_xxh64(const u8* p, u32 len, u32 q, u32 qmask, u32 qbase) { return zl_quad_xxh64_from(p, len, zl_xxh_seed(q), 0, q, qmask, qbase); }
+
+// One WARP per large buffer (16-byte aligned): the accumulator chains are serial (rotate and multiply do not commute) and run on
+// lanes 0-3, but their inputs are not -- all 32 lanes stream the buffer through shared memory in 2 KiB chunks (64 stripes), the
+// next chunk in flight in registers while the chains run over the current one, so the chains never wait for memory.
+#define ZL_XXH_CHUNK 2048u
+ZL_D u64 zl_warp_xxh64(const u8* p, u32 len, u8 (*buf)[ZL_XXH_CHUNK], u32 lane)
+{
+    const u32 nchunks = len / ZL_XXH_CHUNK;
+    u64 v = zl_xxh_seed(lane & 3);
+    if (nchunks) {
+        uint4 r[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) r[i] = __ldg((const uint4*)p + i * 32 + lane);
+        for (u32 c = 0; c < nchunks; c++) {
+            uint4* b4 = (uint4*)buf[c & 1];
+#pragma unroll
+            for (int i = 0; i < 4; i++) b4[i * 32 + lane] = r[i];
+            __syncwarp();
+            if (c + 1 < nchunks) {
+                const uint4* g = (const uint4*)(p + (size_t)(c + 1) * ZL_XXH_CHUNK);
+#pragma unroll
+                for (int i = 0; i < 4; i++) r[i] = __ldg(g + i * 32 + lane);
+            }
+            if (lane < 4) {
+                const u64* b8 = (const u64*)buf[c & 1] + lane;
+#pragma unroll 8
+                for (u32 s = 0; s < ZL_XXH_CHUNK / 32; s++) v = zl_xround(v, b8[4 * s]);
+            }
+        }
+        __syncwarp();
+    }
+    u64 h = 0;
+    if (lane < 4) h = zl_quad_xxh64_from(p, len, v, nchunks * (ZL_XXH_CHUNK / 32), lane, 0xFu, 0);
+    return __shfl_sync(ZL_FULL, h, 0);
 }
 #endif  // __CUDACC__

@@ -315,8 +315,21 @@ zl_k_checksum(const ZlFrameDesc* __restrict__ descs, const ZlFrameInfo* __restri
     if (frame >= nframes) return;
     const ZlFrameInfo info = infos[frame];
     if (info.err || !info.checksumFlag) return;
+    if (descs[frame].large && !(((size_t)descs[frame].dst) & 15)) return;          // zl_k_checksum_large
     const u64 h = zl_quad_xxh64(descs[frame].dst, info.totalOut, q, qmask, qbase);
     if (q == 0 && (u32)h != info.checksum) results[frame] = (u64)0 - (u64)ZL_E_checksum_wrong;   // zstd.c:41650-41657
+}
+
+// large frames: a warp per frame (zl_warp_xxh64); frames whose output is not 16-byte aligned keep the quad path of zl_k_checksum
+__global__ void __launch_bounds__(32)
+zl_k_checksum_large(const u32* __restrict__ largeIdx, const ZlFrameDesc* __restrict__ descs, const ZlFrameInfo* __restrict__ infos, u64* __restrict__ results)
+{
+    __shared__ __align__(16) u8 buf[2][ZL_XXH_CHUNK];
+    const u32 frame = largeIdx[blockIdx.x], lane = threadIdx.x;
+    const ZlFrameInfo info = infos[frame];
+    if (info.err || !info.checksumFlag || (((size_t)descs[frame].dst) & 15)) return;
+    const u64 h = zl_warp_xxh64(descs[frame].dst, info.totalOut, buf, lane);
+    if (lane == 0 && (u32)h != info.checksum) results[frame] = (u64)0 - (u64)ZL_E_checksum_wrong;   // zstd.c:41650-41657
 }
 
 // generic XXH64 of independent buffers (used by the compressor for frame trailers)
@@ -327,8 +340,18 @@ zl_k_xxh64(const u8* const* __restrict__ ptrs, const u32* __restrict__ sizes, u6
     const u32 i = t >> 2, q = t & 3, lane = threadIdx.x & 31;
     const u32 qbase = lane & ~3u, qmask = 0xFu << qbase;
     if (i >= n) return;
+    if (sizes[i] >= ZL_LARGE_FRAME_BYTES && !(((size_t)ptrs[i]) & 15)) return;       // zl_k_xxh64_large
     const u64 h = zl_quad_xxh64(ptrs[i], sizes[i], q, qmask, qbase);
     if (q == 0) out[i] = h;
+}
+__global__ void __launch_bounds__(32)
+zl_k_xxh64_large(const u8* const* __restrict__ ptrs, const u32* __restrict__ sizes, u64* __restrict__ out, u32 n)
+{
+    __shared__ __align__(16) u8 buf[2][ZL_XXH_CHUNK];
+    const u32 i = blockIdx.x;
+    if (sizes[i] < ZL_LARGE_FRAME_BYTES || (((size_t)ptrs[i]) & 15)) return;
+    const u64 h = zl_warp_xxh64(ptrs[i], sizes[i], buf, threadIdx.x);
+    if (threadIdx.x == 0) out[i] = h;
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------
@@ -436,6 +459,7 @@ cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
     if (L.verifyChecksum) {
         const u32 g3 = (L.nframes * 4 + 127) / 128;
         zl_k_checksum<<<g3, 128, 0, st>>>(L.descs, L.infos, L.results, L.nframes);
+        if (L.nLarge) { zl_k_checksum_large<<<L.nLarge, 32, 0, st>>>(L.largeIdx, L.descs, L.infos, L.results); nk++; }
         nk++;
     }
     if (ev) cudaEventRecord(ev[4], st);
@@ -443,9 +467,10 @@ cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t zl_launch_xxh64(const u8* const* ptrs, const u32* sizes, u64* out, u32 n, cudaStream_t st)
+cudaError_t zl_launch_xxh64(const u8* const* ptrs, const u32* sizes, u64* out, u32 n, cudaStream_t st, bool anyLarge)
 {
     if (!n) return cudaSuccess;
     zl_k_xxh64<<<(n * 4 + 127) / 128, 128, 0, st>>>(ptrs, sizes, out, n);
+    if (anyLarge) zl_k_xxh64_large<<<n, 32, 0, st>>>(ptrs, sizes, out, n);
     return cudaGetLastError();
 }

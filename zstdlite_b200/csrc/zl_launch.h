@@ -101,7 +101,7 @@ struct ZlDecodeLaunch {          // one slice of a batch: frames [frameBase, fra
 size_t zl_literals_smem_bytes();
 size_t zl_sequences_smem_bytes();
 cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st);
-cudaError_t zl_launch_xxh64(const u8* const* ptrs, const u32* sizes, u64* out, u32 n, cudaStream_t st);
+cudaError_t zl_launch_xxh64(const u8* const* ptrs, const u32* sizes, u64* out, u32 n, cudaStream_t st, bool anyLarge = false);
 
 // ---- compression --------------------------------------------------------------------------------------------------
 #include "zl_enc_entropy.cuh"
