@@ -128,6 +128,30 @@ def test_compress_split_is_a_standard_multi_frame_stream(z, ref):
     assert rr == len(d) and out.raw == d
 
 
+def test_large_buffers_with_checksum(z, ref):
+    """the trailer hash of a large buffer takes the warp-streamed XXH64 (16-byte aligned input) or the quad form (misaligned):
+    libzstd verifies the checksum when it decodes"""
+    import torch
+    from zstdlite_b200 import corpus
+    from tests.gpu_util import to_dev
+    d = corpus.make("text", 2_500_001, 12).tobytes()
+    c = z.zstd_compress(d, level=3, include_checksum=True)                       # host path: staged, aligned
+    assert z.zstd_info(c)["has_checksum"] and ref.decompress(c) == d and z.zstd_decompress(c) == d
+    L = z._lib.lib()
+    cctx = z.zstd_cctx(level=1, include_checksum=True)
+    cap = int(L.ZSTD_compressBound(len(d)))
+    for shift in (0, 3):                                                        # device pointers: aligned and misaligned input
+        src = to_dev(np.frombuffer(b"\x00" * shift + d, dtype=np.uint8))
+        dst = torch.zeros(cap + 64, dtype=torch.uint8, device="cuda")
+        res = z.compress_batch(cctx, [src.data_ptr() + shift], [len(d)], [dst.data_ptr()], [cap], device=True)
+        assert not z.is_error(res[0])
+        out = dst[:res[0]].cpu().numpy().tobytes()
+        assert ref.decompress(out) == d
+        bad = bytearray(out); bad[-1] ^= 0x40
+        with pytest.raises(z.ZstdError, match="checksum"):
+            z.zstd_decompress(bytes(bad))
+
+
 def test_compress_split_pipelined_host_path(z, ref):
     """host buffers of >= 2 chunks take the staged pipeline (copies of neighbouring chunks overlap the kernels): same bytes as the
     device-pointer path, a standard multi-frame stream for libzstd"""
