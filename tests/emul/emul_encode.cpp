@@ -49,7 +49,7 @@ static void emul_match(const u8* src, u32 n, const ZlEncParams& P, std::vector<u
             const i32 qL = zl_cand_pos(tabL[hL], p); tabL[hL] = (u16)p;
             if (qL >= 0) { const u32 l = match_len_capped(src, n, p, qL); if (l >= P.mls) { bestLen = l; bestOff = p - (u32)qL; } }
         }
-        if (qS >= 0) { const u32 l = match_len_capped(src, n, p, qS); if (l >= P.mls && l > bestLen) { bestLen = l; bestOff = p - (u32)qS; } }
+        if (qS >= 0 && bestLen < 8) { const u32 l = match_len_capped(src, n, p, qS); if (l >= P.mls && l > bestLen) { bestLen = l; bestOff = p - (u32)qS; } }   // (a long-hash match of >= 8 bytes is taken as it is)
         u32 lim = n - p; if (lim > ZL_M_CAP) lim = ZL_M_CAP;
         if (D && bestLen < lim) {
             u32 dOff = 0;

@@ -167,7 +167,9 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
                     if (qL >= 0) { const u32 l = zl_match_len(wbase, bias, lastWord, p, (u32)qL, lo[h], hi[h], lim); if (l >= P.mls) { bestLen = l; bestOff = p - (u32)qL; } }
                 }
                 const i32 qS = prevS[h] >= 0 ? (i32)((g << 5) + (u32)prevS[h]) : zl_cand_pos(eS[h], p);
-                if (qS >= 0 && bestLen < lim) {               // a longer match is impossible once the limit is reached
+                // a verified long-hash candidate (>= 8 bytes) is taken as it is, like the reference's double-fast search (zstd.c:29989);
+                // and a longer match is impossible once the limit is reached
+                if (qS >= 0 && bestLen < 8 && bestLen < lim) {
                     const u32 l = zl_match_len(wbase, bias, lastWord, p, (u32)qS, lo[h], hi[h], lim);
                     if (l >= P.mls && l > bestLen) { bestLen = l; bestOff = p - (u32)qS; }
                 }
