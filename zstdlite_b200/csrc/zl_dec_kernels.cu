@@ -289,7 +289,14 @@ zl_k_ljump(const u32* __restrict__ largeIdx, const ZlFrameDesc* __restrict__ des
         if (pv >= ZL_PAR_DONE) {
             if ((pv & 0xFFu) < pass) { out[p] = __ldcg(out + v); parent[p] = ZL_PAR_DONE | pass; }
             else open++;                                               // made final in this very pass: readable after the kernel boundary
-        } else { parent[p] = pv; open++; }
+        } else {
+            // two hops per pass: chains shrink four-fold, half as many passes
+            const u32 pv2 = __ldcg(parent + pv);
+            if (pv2 >= ZL_PAR_DONE) {
+                if ((pv2 & 0xFFu) < pass) { out[p] = __ldcg(out + pv); parent[p] = ZL_PAR_DONE | pass; }
+                else { parent[p] = pv; open++; }
+            } else { parent[p] = pv2; open++; }
+        }
     }
     open = __reduce_add_sync(0xFFFFFFFFu, open);
     if ((threadIdx.x & 31) == 0 && open) atomicAdd(remain + pass, open);
