@@ -16,7 +16,7 @@ static u32 rd32(const u8* p) { u32 v; memcpy(&v, p, 4); return v; }
 
 static u32 match_len_capped(const u8* src, u32 n, u32 p, i32 q)
 {
-    u32 lim = n - p; if (lim > ZL_M_CAP) lim = ZL_M_CAP;
+    u32 lim = n - p; if (lim > ZL_M_VERIFY) lim = ZL_M_VERIFY;      // in-block candidates: measured up to ZL_M_VERIFY, extended by the walk
     u32 l = 0;
     while (l < lim && src[p + l] == src[(u32)q + l]) l++;
     return l;
@@ -79,7 +79,7 @@ static void emul_parse(const u8* src, u32 n, const std::vector<u32>& M, std::vec
             const u32 m = M[p];
             if (!m) { p++; continue; }
             u32 len = m & 0xFF; u32 off = m >> 8;
-            if (len == ZL_M_CAP && off <= p) while (p + len < s1 && src[p + len] == src[p + len - off]) len++;
+            if (len >= ZL_M_VERIFY && off <= p) while (p + len < s1 && src[p + len] == src[p + len - off]) len++;
             if (p + len > s1) len = s1 - p;                  // a match ends with its segment
             if (len < 3) { p++; continue; }
             // Dictionary mode only: repeat-offset preference (cf. the repcode checks at ip+1 / ip+2 of zstd.c:29989, 30801).  A match

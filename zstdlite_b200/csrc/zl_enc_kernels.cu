@@ -160,17 +160,17 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
             const u32 p = (g << 5) + lane;
             u32 m = 0;
             if (valid[h]) {
-                const u32 lim = min(n - p, ZL_M_CAP);
+                const u32 lim = min(n - p, ZL_M_CAP), limV = min(n - p, ZL_M_VERIFY);     // dictionary / in-block candidates
                 u32 bestLen = 0, bestOff = 0;
                 if (kLong) {
                     const i32 qL = prevL[h] >= 0 ? (i32)((g << 5) + (u32)prevL[h]) : zl_cand_pos(eL[h], p);
-                    if (qL >= 0) { const u32 l = zl_match_len(wbase, bias, lastWord, p, (u32)qL, lo[h], hi[h], lim); if (l >= P.mls) { bestLen = l; bestOff = p - (u32)qL; } }
+                    if (qL >= 0) { const u32 l = zl_match_len(wbase, bias, lastWord, p, (u32)qL, lo[h], hi[h], limV); if (l >= P.mls) { bestLen = l; bestOff = p - (u32)qL; } }
                 }
                 const i32 qS = prevS[h] >= 0 ? (i32)((g << 5) + (u32)prevS[h]) : zl_cand_pos(eS[h], p);
                 // a verified long-hash candidate (>= 8 bytes) is taken as it is, like the reference's double-fast search (zstd.c:29989);
                 // and a longer match is impossible once the limit is reached
-                if (qS >= 0 && bestLen < 8 && bestLen < lim) {
-                    const u32 l = zl_match_len(wbase, bias, lastWord, p, (u32)qS, lo[h], hi[h], lim);
+                if (qS >= 0 && bestLen < 8 && bestLen < limV) {
+                    const u32 l = zl_match_len(wbase, bias, lastWord, p, (u32)qS, lo[h], hi[h], limV);
                     if (l >= P.mls && l > bestLen) { bestLen = l; bestOff = p - (u32)qS; }
                 }
                 if (kDict && (b.flags & ZL_BLK_FIRST) && bestLen < lim) {      // dictionary content precedes the first block
@@ -193,9 +193,9 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
 
 // ---------------------------------------------------------------------------------------------- E2: greedy walk
 // cooperative extension of a match that hit the cap: compares 256 bytes per round
-__device__ __forceinline__ u32 zl_extend_match(const u32* __restrict__ wbase, u32 bias, u32 lastWord, u32 n, u32 pos, u32 off, u32 lane)
+__device__ __forceinline__ u32 zl_extend_match(const u32* __restrict__ wbase, u32 bias, u32 lastWord, u32 n, u32 pos, u32 off, u32 lane, u32 len0)
 {
-    u32 len = ZL_M_CAP;
+    u32 len = len0;
     for (;;) {
         const u32 q = pos + len + 8 * lane;
         u32 c = 0;
@@ -280,7 +280,7 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
                 u32 l = __shfl_sync(ZL_FULL, len, c1);
                 u32 o = __shfl_sync(ZL_FULL, off, c1);
                 u32 pos1 = w0 + c1, c2 = c1;
-                if (l == ZL_M_CAP && o <= pos1) l = zl_extend_match(wbase, bias, lastWord, segEnd, pos1, o, lane);   // (matches into the dictionary stay capped)
+                if (l >= ZL_M_VERIFY && o <= pos1) l = zl_extend_match(wbase, bias, lastWord, segEnd, pos1, o, lane, ZL_M_VERIFY);   // (matches into the dictionary are not extended)
                 if (pos1 + l > segEnd) l = segEnd - pos1;        // a match ends with its segment
                 if (l < 3) { c = c1 + 1; continue; }             // (clipped below the format's minimum: literals)
                 if (repPref && reps.r0 && o != reps.r0) {
@@ -299,7 +299,7 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
                         const u32 k2 = (u32)__ffs((int)hit) - 1;
                         c2 = c1 + k2; pos1 += k2; o = reps.r0;
                         l = __shfl_sync(ZL_FULL, rl, k2);
-                        if (l == ZL_M_CAP) l = zl_extend_match(wbase, bias, lastWord, segEnd, pos1, o, lane);
+                        if (l == ZL_M_CAP) l = zl_extend_match(wbase, bias, lastWord, segEnd, pos1, o, lane, ZL_M_CAP);
                     }
                 }
                 const u32 ll = pos1 - anchor;

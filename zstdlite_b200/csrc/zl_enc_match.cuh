@@ -17,6 +17,11 @@
 #include "zl_common.cuh"
 
 #define ZL_M_CAP 255u
+// In-block candidates are only verified up to ZL_M_VERIFY bytes per position: a result of ZL_M_VERIFY means "at least that many",
+// and the walk (stage 2) extends such a match with the whole warp, 256 bytes per round.  Inside a long run or repeat EVERY position
+// has a maximal candidate, and measuring each to 255 bytes made the match kernel 3x slower on such data (rle corpus: 31 -> 11 ms
+// per 4,096 blocks) for lengths the walk never looks at.  Matches into a dictionary are measured up to ZL_M_CAP (they are not extended).
+#define ZL_M_VERIFY 64u
 
 struct ZlEncParams {       // derived from the compression level by zl_enc_params()
     u32 level;
