@@ -128,6 +128,29 @@ def test_compress_split_is_a_standard_multi_frame_stream(z, ref):
     assert rr == len(d) and out.raw == d
 
 
+def test_scattered_host_buffers_are_staged(z, ref):
+    """thousands of separately allocated host objects (what a list of R raw vectors is): inputs are packed into pinned staging by
+    the host, outputs gathered on the device and unpacked -- same frames as the device-pointer path, both directions"""
+    import time
+    from zstdlite_b200 import corpus
+    from tests.gpu_util import gpu_decompress_batch
+    objs = corpus.small_objects(3000) + [corpus.make("text", 40000, 5).tobytes(), b"", b"x" * 9]
+    d = ref.train_dict(objs[:2000], 4096)
+    res_h, outs_h = _gpu_compress_batch(z, objs, 3, checksum=True, device=False, dict=d)
+    res_d, outs_d = _gpu_compress_batch(z, objs, 3, checksum=True, device=True, dict=d)
+    assert outs_h == outs_d and not any(z.is_error(r) for r in res_h)
+    rd = ref.DCtx(dict=d)
+    for o, c in list(zip(objs, outs_h))[::37] + [(objs[-3], outs_h[-3]), (objs[-2], outs_h[-2]), (objs[-1], outs_h[-1])]:
+        assert rd.decompress(c, cap=len(o)) == o
+    t0 = time.time()
+    res, outs = gpu_decompress_batch(outs_h, [len(o) for o in objs], dctx=z.zstd_dctx(dict=d), device=False)
+    assert outs == objs and time.time() - t0 < 5.0
+    # a destination that is too small for one object only fails that object
+    caps = [len(o) for o in objs]; caps[5] = 3
+    res2, outs2 = gpu_decompress_batch(outs_h, caps, dctx=z.zstd_dctx(dict=d), device=False)
+    assert z.is_error(res2[5]) and outs2[4] == objs[4] and outs2[6] == objs[6]
+
+
 def test_large_buffers_with_checksum(z, ref):
     """the trailer hash of a large buffer takes the warp-streamed XXH64 (16-byte aligned input) or the quad form (misaligned):
     libzstd verifies the checksum when it decodes"""

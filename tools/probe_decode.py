@@ -11,7 +11,7 @@ fb = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 mixname = sys.argv[4] if len(sys.argv) > 4 else "mix"
 mix = {"mix": (("text", 0.4), ("rdf", 0.4), ("lowent", 0.1), ("rand", 0.1)), "text": (("text", 1.0),), "rdf": (("rdf", 1.0),),
-       "lowent": (("lowent", 1.0),), "rand": (("rand", 1.0),)}[mixname]
+       "lowent": (("lowent", 1.0),), "rand": (("rand", 1.0),), "rle": (("rle", 1.0),)}[mixname]
 t0 = time.time()
 data, fams = corpus.mixed_frames(nframes, fb, mix=mix, pool=32)
 cache = {}

@@ -211,7 +211,7 @@ struct ZSTD_DCtx_s {
     std::vector<u8> sIn, sOut;
     size_t sOutPos = 0;
     ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dNorm, dUnits, dCounters, dLargeIdx, dLb, dLc, dParent, dRemain, dSrc, dDst;
-    ZlPinBuf hDescs, hResults, hLargeIdx, hRemain;
+    ZlPinBuf hDescs, hResults, hLargeIdx, hRemain, hStageIn, hStageOut;
 };
 
 static bool zl_ctx_stream(cudaStream_t* st, bool* own, cudaEvent_t* e0, cudaEvent_t* e1)
@@ -230,7 +230,7 @@ ZL_EXPORT size_t ZSTD_freeDCtx(ZSTD_DCtx* c)
     if (!c) return 0;
     ZlDevBuf* bufs[] = {&c->dDictContent, &c->dDict, &c->dDescs, &c->dInfos, &c->dResults, &c->dHdr, &c->dRec, &c->dCk, &c->dLit, &c->dNorm, &c->dUnits, &c->dCounters, &c->dLargeIdx, &c->dLb, &c->dLc, &c->dParent, &c->dRemain, &c->dSrc, &c->dDst};
     for (ZlDevBuf* b : bufs) b->release();
-    c->hDescs.release(); c->hResults.release(); c->hLargeIdx.release(); c->hRemain.release();
+    c->hDescs.release(); c->hResults.release(); c->hLargeIdx.release(); c->hRemain.release(); c->hStageIn.release(); c->hStageOut.release();
     if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
     for (cudaEvent_t e : c->stageEv) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->laneDone) if (e) cudaEventDestroy(e);
@@ -475,6 +475,16 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         }
         if (!c->dSrc.reserve(srcTotal + 64) || !c->dDst.reserve(dstTotal + 64)) return ZL_ERROR(memory_allocation);
     }
+    // Scattered host buffers (a list of separately allocated objects: thousands of copy runs): one cudaMemcpyAsync per run would
+    // cost more than the decode (~2.5 us each).  The runs of a slice are then packed into / unpacked from pinned staging
+    // buffers by the host, and each slice moves with ONE copy per direction.
+    const bool stageIn = !dev && sruns.size() > 64 + 2 * nslices, stageOut = !dev && druns.size() > 64 + 2 * nslices;
+    if (stageIn) {
+        if (!c->hStageIn.reserve(srcTotal + 64)) return ZL_ERROR(memory_allocation);
+        u8* hs = c->hStageIn.as<u8>();
+        for (const ZlRun& r : sruns) if (r.bytes) memcpy(hs + r.devOff, r.hbase, r.bytes);
+    }
+    if (stageOut && !c->hStageOut.reserve(dstTotal + 64)) return ZL_ERROR(memory_allocation);
     std::vector<u32> srunOf, drunOf;                 // copy run of every frame (host buffers), by caller's index
     if (!dev) {
         srunOf.resize(n); drunOf.resize(n);
@@ -543,6 +553,12 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
             // host-to-device copies in slice order: each waits for the previous slice's (left alone, the copy engine served the
             // streams 0, 4, 1, 5, ...; a dedicated copy stream aliased a hardware queue with a lane and stalled behind its copy back)
             if (nslices > 1 && k > 0) cudaStreamWaitEvent(ls, c->inDone[(k - 1) % ZL_DEC_LANES], 0);
+            if (stageIn) {
+                if (srunCut[k + 1] > srunCut[k]) {
+                    const size_t o0 = sruns[srunCut[k]].devOff, o1 = sruns[srunCut[k + 1] - 1].devOff + sruns[srunCut[k + 1] - 1].bytes;
+                    if (o1 > o0) cudaMemcpyAsync(c->dSrc.as<u8>() + o0, c->hStageIn.as<u8>() + o0, o1 - o0, cudaMemcpyHostToDevice, ls);
+                }
+            } else
             for (size_t r = srunCut[k]; r < srunCut[k + 1]; r++)
                 if (sruns[r].bytes) cudaMemcpyAsync(c->dSrc.as<u8>() + sruns[r].devOff, sruns[r].hbase, sruns[r].bytes, cudaMemcpyHostToDevice, ls);
             if (nslices > 1) cudaEventRecord(c->inDone[k % ZL_DEC_LANES], ls);
@@ -580,6 +596,12 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         L.launched = &c->launches;
         e = zl_launch_decode(L, ls);
         if (trace) cudaEventRecord(tev[3 * k + 1], ls);
+        if (!dev && stageOut) {
+            if (drunCut[k + 1] > drunCut[k]) {
+                const size_t o0 = druns[drunCut[k]].devOff, o1 = druns[drunCut[k + 1] - 1].devOff + druns[drunCut[k + 1] - 1].bytes;
+                if (o1 > o0) cudaMemcpyAsync(c->hStageOut.as<u8>() + o0, c->dDst.as<u8>() + o0, o1 - o0, cudaMemcpyDeviceToHost, ls);
+            }
+        } else
         if (!dev) for (size_t r = drunCut[k]; r < drunCut[k + 1]; r++)
             if (druns[r].bytes) cudaMemcpyAsync((void*)druns[r].hbase, c->dDst.as<u8>() + druns[r].devOff, druns[r].bytes, cudaMemcpyDeviceToHost, ls);
         if (trace) cudaEventRecord(tev[3 * k + 2], ls);
@@ -610,6 +632,17 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     }
     const u64* hr = c->hResults.as<u64>();
     for (size_t pos = 0; pos < n; pos++) result[order[pos]] = (size_t)hr[pos];
+    if (stageOut) {                                       // unpack the staged output: only what each frame produced
+        const u8* ho = c->hStageOut.as<u8>();
+        for (const ZlRun& r : druns) {
+            size_t off = 0;
+            for (size_t i = r.first; i < r.first + r.count; i++) {
+                const size_t got = result[i];
+                if (!zl_is_error(got) && got) memcpy((u8*)r.hbase + off, ho + r.devOff + off, got < dstCap[i] ? got : dstCap[i]);
+                off += dstCap[i];
+            }
+        }
+    }
     return 0;
 }
 

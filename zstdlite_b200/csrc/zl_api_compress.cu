@@ -30,7 +30,7 @@ struct ZSTD_CCtx_s {
     double lastKernelMs = 0.0, lastStageMs[ZL_ENC_STAGES] = {};
     unsigned long long launches = 0;
     ZlDevBuf dBlocks, dFrames, dM, dRecs, dLit, dHist, dMetas, dOuts, dPlans, dResults, dXxh, dXxhPtrs, dXxhSizes, dSrc, dDst, dAux;
-    ZlPinBuf hBlocks, hFrames, hResults, hAux;
+    ZlPinBuf hBlocks, hFrames, hResults, hAux, hStageIn, hStageOut;
     // streaming session (ZSTD_compressStream2): input accumulated on the host until ZSTD_e_end, then one frame is produced
     std::vector<u8> sIn, sOut;
     size_t sOutPos = 0;
@@ -75,7 +75,7 @@ ZL_EXPORT size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
                         &c->dXxh, &c->dXxhPtrs, &c->dXxhSizes, &c->dSrc, &c->dDst, &c->dAux,
                         &c->dDict, &c->dDictContent, &c->dDictTabS, &c->dDictTabL};
     for (ZlDevBuf* b : bufs) b->release();
-    c->hBlocks.release(); c->hFrames.release(); c->hResults.release(); c->hAux.release();
+    c->hBlocks.release(); c->hFrames.release(); c->hResults.release(); c->hAux.release(); c->hStageIn.release(); c->hStageOut.release();
     if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
     for (cudaEvent_t e : c->stageEv) if (e) cudaEventDestroy(e);
     if (c->side) { cudaStreamDestroy(c->side); cudaEventDestroy(c->sideFork); cudaEventDestroy(c->sideJoin); }
@@ -360,10 +360,39 @@ ZL_EXPORT size_t zl_compress_batch(ZSTD_CCtx* c, const void* const* src, const s
             doff += (dstCap[i] + 15) & ~(size_t)15;
         }
     }
+    // scattered inputs (a list of separately allocated objects): packed by the host into pinned staging, ONE copy in; the frames
+    // are then gathered on the device, copied back with ONE copy and unpacked by the host (a cudaMemcpyAsync per object costs ~2.5 us)
+    const bool staged = sruns.size() > 64 || n > 256;
+    if (staged) {
+        if (!c->hStageIn.reserve(srcTotal + 64)) return ZL_ERROR(memory_allocation);
+        u8* hs = c->hStageIn.as<u8>();
+        for (const ZlRun& r : sruns) if (r.bytes) memcpy(hs + r.devOff, r.hbase, r.bytes);
+        if (srcTotal) cudaMemcpyAsync(c->dSrc.p, hs, srcTotal, cudaMemcpyHostToDevice, st);
+    } else
     for (const ZlRun& r : sruns) if (r.bytes) cudaMemcpyAsync(c->dSrc.as<u8>() + r.devOff, r.hbase, r.bytes, cudaMemcpyHostToDevice, st);
     const size_t r = zl_enc_run(c, dsrc.data(), srcSize, ddst.data(), dstCap, n);
     if (zl_is_error(r)) return r;
     const u64* hr = c->hResults.as<u64>();
+    if (staged) {
+        if (!c->hAux.reserve(n * 24) || !c->dAux.reserve(n * 24)) return ZL_ERROR(memory_allocation);
+        u64* hsz = c->hAux.as<u64>(); u64* hoff = hsz + n; const u8** hptr = reinterpret_cast<const u8**>(hoff + n);
+        size_t total = 0;
+        for (size_t i = 0; i < n; i++) {
+            result[i] = (size_t)hr[i];
+            const size_t got = zl_is_error(result[i]) ? 0 : result[i];
+            hsz[i] = got; hoff[i] = total; hptr[i] = ddst[i]; total += got;
+        }
+        if (!c->dOutStage.reserve(total + 64) || !c->hStageOut.reserve(total + 64)) return ZL_ERROR(memory_allocation);
+        cudaMemcpyAsync(c->dAux.p, hsz, n * 24, cudaMemcpyHostToDevice, st);
+        const u64* dsz = c->dAux.as<u64>();
+        if (zl_launch_gather(reinterpret_cast<const u8* const*>(dsz + 2 * n), dsz, dsz + n, c->dOutStage.as<u8>(), (u32)n, st) != cudaSuccess) return ZL_ERROR(GENERIC);
+        c->launches += 1;
+        if (total) cudaMemcpyAsync(c->hStageOut.p, c->dOutStage.p, total, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { (void)cudaGetLastError(); return ZL_ERROR(GENERIC); }
+        const u8* ho = c->hStageOut.as<u8>();
+        for (size_t i = 0; i < n; i++) if (hsz[i]) memcpy(dst[i], ho + hoff[i], hsz[i]);
+        return 0;
+    }
     for (size_t i = 0; i < n; i++) {
         result[i] = (size_t)hr[i];
         if (!zl_is_error(result[i]) && result[i]) cudaMemcpyAsync(dst[i], ddst[i], result[i], cudaMemcpyDeviceToHost, st);
