@@ -511,7 +511,11 @@ __device__ __forceinline__ u32 zl_opaque(u32 x) { asm volatile("" : "+r"(x)); re
 
 // one Huffman stream per lane: zstd.c:38626-38650.  Returns 0 when the stream ends exactly, 2 when bits are left over,
 // 1 when the reader ran past the start (or the end mark is missing).
-ZL_HD u32 zl_huf_stream(const u16* huf, u32 tlog, const u32* wbase, u32 bias, u32 beg, u32 end, u8* out, u32 n)
+// `ring` (device only; 0 = none): shared-space address of this lane's 16-byte column of the warp's stream ring (4 slots of
+// 32 x 16 bytes).  With a ring the stream words reach the lane through cp.async (16-byte chunk three chunks ahead of the
+// one being consumed) and an LDS, instead of a global load per word: the per-warp scoreboard made every refill wait for
+// the global load some other lane had issued one refill earlier (ncu: long scoreboard 6.5 of 10 cycles per issue).
+ZL_HD u32 zl_huf_stream(const u16* huf, u32 tlog, const u32* wbase, u32 bias, u32 beg, u32 end, u8* out, u32 n, u32 ring = 0)
 {
     ZlBitR b;
     if (!zl_br_init(b, wbase, bias, beg, end)) return 1;
@@ -520,7 +524,63 @@ ZL_HD u32 zl_huf_stream(const u16* huf, u32 tlog, const u32* wbase, u32 bias, u3
 #define ZL_HUF_SYM(dst) { const u32 e = huf[b.hi >> sh]; zl_br_skip(b, e >> 8); dst = e & 0xFF; }
     while (i < n && (((size_t)(out + i)) & 3)) { u32 s; zl_br_refill(b, wbase); ZL_HUF_SYM(s); out[i++] = (u8)s; }
 #if defined(__CUDA_ARCH__)
-    {
+    if (ring) {
+        const u32 count = n;                       // `n` below is the window's valid-bit count (macro convention)
+        u32 hi = b.hi, lo = b.lo, nextw = b.nextw;
+        const u32 s16 = (u32)(((size_t)wbase >> 2) & 3);
+        const u32* wb16 = wbase - s16;             // 16-byte aligned; word indices below are relative to it
+        i32 wi = b.wi + (i32)s16;
+        const i32 clow = (b.wlow + (i32)s16) >> 2; // chunk holding the first byte of the stream (never read below it)
+        const u32 th = zl_smem_addr(huf);
+        {   // chunks c0 .. c0-3 (slot = chunk & 3); later, entering chunk c fetches chunk c-3 into the slot of chunk c+1
+            const i32 c0 = wi >> 2;
+#pragma unroll
+            for (i32 k = 0; k < 4; k++) {
+                const i32 c = (c0 - k) < clow ? clow : (c0 - k);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (((u32)(c0 - k) & 3u) << 9)), "l"(wb16 + 4 * c) : "memory");
+            }
+            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        }
+        {
+            i32 n = b.n;
+            // A chunk is used 12 refills (= 12 groups) or more after its copy was issued, so wait_group 8 always covers it;
+            // the wait itself only asks for the copies issued 9 refills ago.
+#define ZL_REFILL_RING()                                                                                       \
+    {                                                                                                          \
+        const u32 need_ = (n <= 32) ? 1u : 0u;                                                                 \
+        hi |= zl_shr(nextw, (u32)n);                                                                           \
+        lo |= zl_shl(nextw, 32u - (u32)n);                                                                     \
+        const i32 c_ = (wi >> 2) - 3;                                                                          \
+        const i32 cl_ = c_ < clow ? clow : c_;                                                                 \
+        const i32 pf_ = (c_ - 16) < clow ? clow : (c_ - 16);                                                   \
+        const u32 cross_ = need_ & (((u32)wi & 3u) == 3u ? 1u : 0u);                                           \
+        const u32 pfneed_ = cross_ & (((u32)c_ & 1u) ? 0u : 1u);                                               \
+        asm volatile("{\n\t.reg .pred p, q, r;\n\tsetp.ne.u32 p, %5, 0;\n\tsetp.ne.u32 q, %6, 0;\n\tsetp.ne.u32 r, %7, 0;\n\t" \
+                     "@q cp.async.cg.shared.global [%1], [%2], 16;\n\t@r prefetch.global.L2 [%3];\n\t"        \
+                     "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t@p ld.shared.u32 %0, [%4];\n\t}"    \
+                     : "+r"(nextw)                                                                             \
+                     : "r"(ring + (((u32)c_ & 3u) << 9)), "l"(wb16 + 4 * cl_), "l"(wb16 + 4 * pf_),            \
+                       "r"(ring + (((u32)wi & 12u) << 7) + (((u32)wi & 3u) << 2)), "r"(need_), "r"(cross_), "r"(pfneed_) \
+                     : "memory");                                                                              \
+        n += (i32)(need_ << 5);                                                                                \
+        wi -= (i32)need_;                                                                                      \
+    }
+#define ZL_HUF_SYM_DEV(dst) { const u32 e = zl_lds16(th + ((hi >> sh) << 1)); const u32 nb = e >> 8; \
+                              hi = zl_fsl(lo, hi, nb); lo <<= nb; n -= (i32)nb; dst = e & 0xFF; }
+            while (i + 4 <= count) {
+                u32 s0, s1, s2, s3;
+                ZL_REFILL_RING(); ZL_HUF_SYM_DEV(s0); ZL_HUF_SYM_DEV(s1);
+                ZL_REFILL_RING(); ZL_HUF_SYM_DEV(s2); ZL_HUF_SYM_DEV(s3);
+                __stcs((u32*)(out + i), s0 | (s1 << 8) | (s2 << 16) | (s3 << 24));
+                i += 4;
+            }
+#undef ZL_HUF_SYM_DEV
+#undef ZL_REFILL_RING
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            b.n = n;
+        }
+        b.hi = hi; b.lo = lo; b.nextw = nextw; b.wi = wi - (i32)s16;
+    } else {
         const u32 count = n;                       // `n` below is the window's valid-bit count (macro convention)
         u32 hi = b.hi, lo = b.lo, nextw = b.nextw;
         i32 wi = b.wi;

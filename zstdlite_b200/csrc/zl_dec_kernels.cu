@@ -34,6 +34,9 @@ __device__ __forceinline__ u32 zl_fetch_units(u32* cursor, u32 lane)
 }
 
 // ---- K1a: literals ------------------------------------------------------------------------------------------
+#ifndef ZL_LIT_RING
+#define ZL_LIT_RING 1        // 0: stream words by global loads (the round-1 path, kept for A/B measurements)
+#endif
 // descs / infos are indexed by the GLOBAL frame number carried by the unit
 __global__ void __launch_bounds__(32)
 zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, const ZlBlockHdr* hdrArena,
@@ -44,6 +47,8 @@ zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ i
     const u32 lane = threadIdx.x, quad = lane >> 2, q = lane & 3;
     const u32 qmask = 0xFu << (quad * 4);
     ZlLitSm& f = fs[quad];
+    // stream ring: 4 slots of 32 x 16 bytes behind the eight units (zl_huf_stream)
+    const u32 ring = ZL_LIT_RING ? zl_smem_addr(smraw + ZL_QUADS_PER_WARP * sizeof(ZlLitSm)) + lane * 16u : 0u;
     const u32 nunits = *unitCount;
     for (;;) {
         const u32 ubase = zl_fetch_units(cursor, lane);
@@ -70,7 +75,7 @@ zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ i
                 __syncwarp(qmask);
                 if (q < ns)
                     f.ctl.sErr[q] = zl_huf_stream(f.huf, f.ctl.hufLog, wbase, bias, f.ctl.sBeg[q], f.ctl.sEnd[q],
-                                                  lits + f.ctl.sOut[q], f.ctl.sLen[q]);
+                                                  lits + f.ctl.sOut[q], f.ctl.sLen[q], ring);
                 __syncwarp(qmask);
                 if (q == 0) { const u32 e = zl_lit_unit_finish(f); if (e) infos[un.frame].err = e; }
                 __syncwarp(qmask);
@@ -362,7 +367,7 @@ zl_k_xxh64_large(const u8* const* __restrict__ ptrs, const u32* __restrict__ siz
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------
-size_t zl_literals_smem_bytes() { return ZL_QUADS_PER_WARP * sizeof(ZlLitSm); }
+size_t zl_literals_smem_bytes() { return ZL_QUADS_PER_WARP * sizeof(ZlLitSm) + (ZL_LIT_RING ? 4 * 32 * 16 : 0); }
 size_t zl_sequences_smem_bytes() { return ZL_XTAB_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlSeqSm); }
 
 static int g_sms = 0, g_litPerSm = 0, g_seqPerSm = 0;
