@@ -500,6 +500,42 @@ __device__ __forceinline__ u32 zl_lds16(u32 a) { u32 v; asm("ld.shared.u16 %0, [
         n += (i32)(need_ << 5);                                                                                \
         wi -= (i32)need_;                                                                                      \
     }
+// ---- stream ring: the lane's next words come from shared memory, filled by cp.async in 16-byte chunks --------------------
+// `ring` = shared-space address of the lane's 16-byte column; slot k of the ring lies at ring + (k << SH).  Word indices are
+// relative to the 16-byte aligned `wb16`; `clow` = chunk holding the first byte of the stream (nothing below it is read).
+// zl_ring_start fetches chunks c0 .. c0-3 (slot = chunk & 3); later, entering chunk c fetches chunk c-3 into the slot of c+1.
+__device__ __forceinline__ void zl_ring_start(u32 ring, u32 sh, const u32* wb16, i32 wi, i32 clow)
+{
+    const i32 c0 = wi >> 2;
+#pragma unroll
+    for (i32 k = 0; k < 4; k++) {
+        const i32 c = (c0 - k) < clow ? clow : (c0 - k);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (((u32)(c0 - k) & 3u) << sh)), "l"(wb16 + 4 * c) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// A chunk is used 12 refills (= 12 groups) or more after its copy was issued, so wait_group 8 always covers it;
+// the wait itself only asks for the copies issued 9 refills ago.
+#define ZL_REFILL_RING(SH)                                                                                       \
+    {                                                                                                          \
+        const u32 need_ = (n <= 32) ? 1u : 0u;                                                                 \
+        hi |= zl_shr(nextw, (u32)n);                                                                           \
+        lo |= zl_shl(nextw, 32u - (u32)n);                                                                     \
+        const i32 c_ = (wi >> 2) - 3;                                                                          \
+        const i32 cl_ = c_ < clow ? clow : c_;                                                                 \
+        const i32 pf_ = (c_ - 16) < clow ? clow : (c_ - 16);                                                   \
+        const u32 cross_ = need_ & (((u32)wi & 3u) == 3u ? 1u : 0u);                                           \
+        const u32 pfneed_ = cross_ & (((u32)c_ & 1u) ? 0u : 1u);                                               \
+        asm volatile("{\n\t.reg .pred p, q, r;\n\tsetp.ne.u32 p, %5, 0;\n\tsetp.ne.u32 q, %6, 0;\n\tsetp.ne.u32 r, %7, 0;\n\t" \
+                     "@q cp.async.cg.shared.global [%1], [%2], 16;\n\t@r prefetch.global.L2 [%3];\n\t"        \
+                     "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t@p ld.shared.u32 %0, [%4];\n\t}"    \
+                     : "+r"(nextw)                                                                             \
+                     : "r"(ring + (((u32)c_ & 3u) << (SH))), "l"(wb16 + 4 * cl_), "l"(wb16 + 4 * pf_),            \
+                       "r"(ring + ((((u32)wi >> 2) & 3u) << (SH)) + (((u32)wi & 3u) << 2)), "r"(need_), "r"(cross_), "r"(pfneed_) \
+                     : "memory");                                                                              \
+        n += (i32)(need_ << 5);                                                                                \
+        wi -= (i32)need_;                                                                                      \
+    }
 __device__ __forceinline__ u32 zl_selp(u32 a, u32 b, bool c)          // c ? a : b, guaranteed to stay a select
 {
     u32 r;
@@ -532,50 +568,19 @@ ZL_HD u32 zl_huf_stream(const u16* huf, u32 tlog, const u32* wbase, u32 bias, u3
         i32 wi = b.wi + (i32)s16;
         const i32 clow = (b.wlow + (i32)s16) >> 2; // chunk holding the first byte of the stream (never read below it)
         const u32 th = zl_smem_addr(huf);
-        {   // chunks c0 .. c0-3 (slot = chunk & 3); later, entering chunk c fetches chunk c-3 into the slot of chunk c+1
-            const i32 c0 = wi >> 2;
-#pragma unroll
-            for (i32 k = 0; k < 4; k++) {
-                const i32 c = (c0 - k) < clow ? clow : (c0 - k);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (((u32)(c0 - k) & 3u) << 9)), "l"(wb16 + 4 * c) : "memory");
-            }
-            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-        }
+        zl_ring_start(ring, 9, wb16, wi, clow);
         {
             i32 n = b.n;
-            // A chunk is used 12 refills (= 12 groups) or more after its copy was issued, so wait_group 8 always covers it;
-            // the wait itself only asks for the copies issued 9 refills ago.
-#define ZL_REFILL_RING()                                                                                       \
-    {                                                                                                          \
-        const u32 need_ = (n <= 32) ? 1u : 0u;                                                                 \
-        hi |= zl_shr(nextw, (u32)n);                                                                           \
-        lo |= zl_shl(nextw, 32u - (u32)n);                                                                     \
-        const i32 c_ = (wi >> 2) - 3;                                                                          \
-        const i32 cl_ = c_ < clow ? clow : c_;                                                                 \
-        const i32 pf_ = (c_ - 16) < clow ? clow : (c_ - 16);                                                   \
-        const u32 cross_ = need_ & (((u32)wi & 3u) == 3u ? 1u : 0u);                                           \
-        const u32 pfneed_ = cross_ & (((u32)c_ & 1u) ? 0u : 1u);                                               \
-        asm volatile("{\n\t.reg .pred p, q, r;\n\tsetp.ne.u32 p, %5, 0;\n\tsetp.ne.u32 q, %6, 0;\n\tsetp.ne.u32 r, %7, 0;\n\t" \
-                     "@q cp.async.cg.shared.global [%1], [%2], 16;\n\t@r prefetch.global.L2 [%3];\n\t"        \
-                     "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t@p ld.shared.u32 %0, [%4];\n\t}"    \
-                     : "+r"(nextw)                                                                             \
-                     : "r"(ring + (((u32)c_ & 3u) << 9)), "l"(wb16 + 4 * cl_), "l"(wb16 + 4 * pf_),            \
-                       "r"(ring + (((u32)wi & 12u) << 7) + (((u32)wi & 3u) << 2)), "r"(need_), "r"(cross_), "r"(pfneed_) \
-                     : "memory");                                                                              \
-        n += (i32)(need_ << 5);                                                                                \
-        wi -= (i32)need_;                                                                                      \
-    }
 #define ZL_HUF_SYM_DEV(dst) { const u32 e = zl_lds16(th + ((hi >> sh) << 1)); const u32 nb = e >> 8; \
                               hi = zl_fsl(lo, hi, nb); lo <<= nb; n -= (i32)nb; dst = e & 0xFF; }
             while (i + 4 <= count) {
                 u32 s0, s1, s2, s3;
-                ZL_REFILL_RING(); ZL_HUF_SYM_DEV(s0); ZL_HUF_SYM_DEV(s1);
-                ZL_REFILL_RING(); ZL_HUF_SYM_DEV(s2); ZL_HUF_SYM_DEV(s3);
+                ZL_REFILL_RING(9); ZL_HUF_SYM_DEV(s0); ZL_HUF_SYM_DEV(s1);
+                ZL_REFILL_RING(9); ZL_HUF_SYM_DEV(s2); ZL_HUF_SYM_DEV(s3);
                 __stcs((u32*)(out + i), s0 | (s1 << 8) | (s2 << 16) | (s3 << 24));
                 i += 4;
             }
 #undef ZL_HUF_SYM_DEV
-#undef ZL_REFILL_RING
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             b.n = n;
         }
@@ -883,7 +888,7 @@ ZL_HD void zl_seq_step(const ZlSeqSm& f, ZlBitR& b, const u32* wbase, const ZlCo
 // the new states are known.  States are kept "primed" (state + table size): a primed state is simply the cell's ns with
 // the nbBits fresh stream bits shifted in from the right -- one funnel shift -- and indexes the table at (base - size).
 __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xtab, ZlBitR& b, const u32* wbase,
-                                                ZlSeqRegs& r, u64* rp, u32 maxIter, u32 safeCap)
+                                                ZlSeqRegs& r, u64* rp, u32 maxIter, u32 safeCap, u32 ring)
 {
     const u32 gLL = f.ctl.tlog[0], gOF = f.ctl.tlog[1], gML = f.ctl.tlog[2];
     const u32 zLL = 1u << gLL, zOF = 1u << gOF, zML = 1u << gML;
@@ -900,26 +905,40 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xta
     if (maxIter > room) maxIter = room;
     u32 eLL = zl_lds16(tLL + (sLL << 1)), eOF = zl_lds16(tOF + (sOF << 1)), eML = zl_lds16(tML + (sML << 1));
     u32 it = 0;
-    while (it < maxIter) {
-        const u32 llCode = ZL_CELL_SYM(eLL), mlCode = ZL_CELL_SYM(eML), aOF = ZL_CELL_SYM(eOF);
-        const u32 xl = zl_lds32(cLL + (llCode << 2)), xm = zl_lds32(cML + (mlCode << 2));
-        const u32 nLL = ZL_CELL_NS(eLL), nML = ZL_CELL_NS(eML), nOF = ZL_CELL_NS(eOF);
-        const u32 bLL = (u32)__clz((int)nLL) - kLL, bML = (u32)__clz((int)nML) - kML, bOF = (u32)__clz((int)nOF) - kOF;
-        const u32 cA = aOF + (xl >> 24) + (xm >> 24);
-        if (cA > 32 || llCode >= 35 || mlCode >= 50) break;                               // rare: leave it to the generic step
-        ZL_REFILL_DEV();                                                                   // n >= 33
-        const u32 snap = hi;
-        hi = zl_fsl(lo, hi, cA); lo = zl_shl(lo, cA); n -= (i32)cA;
-        ZL_REFILL_DEV();
-        const u32 d2 = bLL + bML, cB = d2 + bOF;                                           // <= 26
-        sLL = __funnelshift_l(hi, nLL, bLL);                                               // LL, ML, OF order: zstd.c:44347-44353
-        sML = __funnelshift_l(zl_fsl(lo, hi, bLL), nML, bML);
-        sOF = __funnelshift_l(zl_fsl(lo, hi, d2), nOF, bOF);
-        hi = zl_fsl(lo, hi, cB); lo <<= cB; n -= (i32)cB;
-        eLL = zl_lds16(tLL + (sLL << 1)); eOF = zl_lds16(tOF + (sOF << 1)); eML = zl_lds16(tML + (sML << 1));
-        __stcs(wp++, zl_rec_a(snap, llCode, mlCode, aOF));                                  // streaming store: keep L1 for the bitstream
-        it++;
+#define ZL_SEQ_LOOP(REFILL) \
+    while (it < maxIter) { \
+        const u32 llCode = ZL_CELL_SYM(eLL), mlCode = ZL_CELL_SYM(eML), aOF = ZL_CELL_SYM(eOF); \
+        const u32 xl = zl_lds32(cLL + (llCode << 2)), xm = zl_lds32(cML + (mlCode << 2)); \
+        const u32 nLL = ZL_CELL_NS(eLL), nML = ZL_CELL_NS(eML), nOF = ZL_CELL_NS(eOF); \
+        const u32 bLL = (u32)__clz((int)nLL) - kLL, bML = (u32)__clz((int)nML) - kML, bOF = (u32)__clz((int)nOF) - kOF; \
+        const u32 cA = aOF + (xl >> 24) + (xm >> 24); \
+        if (cA > 32 || llCode >= 35 || mlCode >= 50) break; \
+        REFILL; \
+        const u32 snap = hi; \
+        hi = zl_fsl(lo, hi, cA); lo = zl_shl(lo, cA); n -= (i32)cA; \
+        REFILL; \
+        const u32 d2 = bLL + bML, cB = d2 + bOF; \
+        sLL = __funnelshift_l(hi, nLL, bLL); \
+        sML = __funnelshift_l(zl_fsl(lo, hi, bLL), nML, bML); \
+        sOF = __funnelshift_l(zl_fsl(lo, hi, d2), nOF, bOF); \
+        hi = zl_fsl(lo, hi, cB); lo <<= cB; n -= (i32)cB; \
+        eLL = zl_lds16(tLL + (sLL << 1)); eOF = zl_lds16(tOF + (sOF << 1)); eML = zl_lds16(tML + (sML << 1)); \
+        __stcs(wp++, zl_rec_a(snap, llCode, mlCode, aOF)); \
+        it++; \
     }
+    if (ring) {
+        const u32 s16 = (u32)(((size_t)wbase >> 2) & 3);
+        const u32* wb16 = wbase - s16;
+        const i32 clow = (wlow + (i32)s16) >> 2;
+        wi += (i32)s16;
+        zl_ring_start(ring, 7, wb16, wi, clow);
+        ZL_SEQ_LOOP(ZL_REFILL_RING(7))
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        wi -= (i32)s16;
+    } else {
+        ZL_SEQ_LOOP(ZL_REFILL_DEV())
+    }
+#undef ZL_SEQ_LOOP
     b.hi = hi; b.lo = lo; b.nextw = nextw; b.n = n; b.wi = wi;
     r.sLL = sLL - zLL; r.sOF = sOF - zOF; r.sML = sML - zML;
     r.nrec += it;
@@ -929,12 +948,13 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xta
 
 // serial sequence decode of one block (lane 0): zstd.c:44627-44700.  Completes the block's ZlBlockHdr (nrec, recOff);
 // the regenerated size is only known once K2 has added up the lengths.
-// `xtab` is only used by the device fast path (null in the CPU emulation).
+// `xtab` and `ring` (the lane's column of the stream ring, slots 128 bytes apart; 0 = none) are only used by the device
+// fast path (null in the CPU emulation).
 // `recs` = this block's slice of the record arena (room for nbSeq + 4 records: a block regenerates <= 128 KiB, so at most
 // two lengths can be split); returns the number of records written.
-ZL_HD u32 zl_seq_decode(ZlSeqSm& f, u64* recs, const u32* wbase, u32 bias, const ZlConstTables& ct, const u32* xtab)
+ZL_HD u32 zl_seq_decode(ZlSeqSm& f, u64* recs, const u32* wbase, u32 bias, const ZlConstTables& ct, const u32* xtab, u32 ring = 0)
 {
-    (void)xtab;
+    (void)xtab; (void)ring;
     ZlSeqCtl& c = f.ctl;
     if (!c.err && c.needBuild) { for (u32 t = 0; t < 3; t++) if (c.bErr[t]) c.err = ZL_E_corruption_detected; }
     u64* rp = recs;
@@ -954,7 +974,7 @@ ZL_HD u32 zl_seq_decode(ZlSeqSm& f, u64* recs, const u32* wbase, u32 bias, const
             const u32 safeCap = recCap - 4;                  // split path re-checks exactly
             for (u32 i = 0; i + 1 < nbSeq; i++) {
 #if defined(__CUDA_ARCH__)
-                i += zl_seq_fast_loop(f, xtab, b, wbase, r, rp, nbSeq - 1 - i, safeCap);
+                i += zl_seq_fast_loop(f, xtab, b, wbase, r, rp, nbSeq - 1 - i, safeCap, ring);
                 if (r.nrec >= safeCap || i + 1 >= nbSeq) break;
 #endif
                 zl_seq_step<false>(f, b, wbase, ct, r, rp, recCap);

@@ -87,6 +87,9 @@ zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ i
 
 // ---- K1b: sequences -----------------------------------------------------------------------------------------
 #define ZL_XTAB_BYTES ((ZL_XTAB_WORDS * 4 + 15) & ~15)
+#ifndef ZL_SEQ_RING
+#define ZL_SEQ_RING 0        // measured: 2.35 -> 2.68 ms with the ring (one decoding lane per quad keeps its words in L1: hit rate 77%)
+#endif
 __global__ void __launch_bounds__(32)
 zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, ZlBlockHdr* hdrArena,
                u64* recArena, i16* normArena, const ZlUnit* __restrict__ units, const u32* __restrict__ unitCount, u32* cursor,
@@ -102,6 +105,8 @@ zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ 
         xtab[i] = i < 36 ? (c_tables.llBase[i] | ((u32)c_tables.llBits[i] << 24)) : (c_tables.mlBase[i - 36] | ((u32)c_tables.mlBits[i - 36] << 24));
     __syncwarp();
     ZlSeqSm& f = fs[quad];
+    // stream ring of the decoding lanes: 4 slots of 8 x 16 bytes behind the eight units (zl_seq_fast_loop)
+    const u32 ring = ZL_SEQ_RING ? zl_smem_addr(smraw + ZL_XTAB_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlSeqSm)) + quad * 16u : 0u;
     i16* norm = normArena + ((size_t)blockIdx.x * ZL_QUADS_PER_WARP + quad) * (3 * ZL_NORM_STRIDE);     // scratch per resident quad
     const u32 nunits = *unitCount;
     for (;;) {
@@ -126,7 +131,7 @@ zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ 
                 if (build && q < 3) zl_seq_fse_build(f, q, norm);
                 __syncwarp(qmask);
                 if (q == 0) {
-                    const u32 nrec = zl_seq_decode(f, recArena + d.recBase + hdrs[un.block].recOff, wbase, bias, ct, xtab);
+                    const u32 nrec = zl_seq_decode(f, recArena + d.recBase + hdrs[un.block].recOff, wbase, bias, ct, xtab, ring);
                     hdrs[un.block].nrec = nrec;
                     if (f.ctl.err) infos[un.frame].err = f.ctl.err;
                 }
@@ -368,7 +373,7 @@ zl_k_xxh64_large(const u8* const* __restrict__ ptrs, const u32* __restrict__ siz
 
 // ---- launchers ---------------------------------------------------------------------------------------
 size_t zl_literals_smem_bytes() { return ZL_QUADS_PER_WARP * sizeof(ZlLitSm) + (ZL_LIT_RING ? 4 * 32 * 16 : 0); }
-size_t zl_sequences_smem_bytes() { return ZL_XTAB_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlSeqSm); }
+size_t zl_sequences_smem_bytes() { return ZL_XTAB_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlSeqSm) + (ZL_SEQ_RING ? 4 * 8 * 16 : 0); }
 
 static int g_sms = 0, g_litPerSm = 0, g_seqPerSm = 0;
 cudaError_t zl_decode_grid_limits(u32* litCtas, u32* seqCtas)
