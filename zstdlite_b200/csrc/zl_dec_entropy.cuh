@@ -516,7 +516,7 @@ __device__ __forceinline__ void zl_ring_start(u32 ring, u32 sh, const u32* wb16,
 }
 // A chunk is used 12 refills (= 12 groups) or more after its copy was issued, so wait_group 8 always covers it;
 // the wait itself only asks for the copies issued 9 refills ago.
-#define ZL_REFILL_RING(SH)                                                                                       \
+#define ZL_REFILL_RING_(SH, SYNC)                                                                               \
     {                                                                                                          \
         const u32 need_ = (n <= 32) ? 1u : 0u;                                                                 \
         hi |= zl_shr(nextw, (u32)n);                                                                           \
@@ -528,7 +528,7 @@ __device__ __forceinline__ void zl_ring_start(u32 ring, u32 sh, const u32* wb16,
         const u32 pfneed_ = cross_ & (((u32)c_ & 1u) ? 0u : 1u);                                               \
         asm volatile("{\n\t.reg .pred p, q, r;\n\tsetp.ne.u32 p, %5, 0;\n\tsetp.ne.u32 q, %6, 0;\n\tsetp.ne.u32 r, %7, 0;\n\t" \
                      "@q cp.async.cg.shared.global [%1], [%2], 16;\n\t@r prefetch.global.L2 [%3];\n\t"        \
-                     "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t@p ld.shared.u32 %0, [%4];\n\t}"    \
+                     SYNC "@p ld.shared.u32 %0, [%4];\n\t}"    \
                      : "+r"(nextw)                                                                             \
                      : "r"(ring + (((u32)c_ & 3u) << (SH))), "l"(wb16 + 4 * cl_), "l"(wb16 + 4 * pf_),            \
                        "r"(ring + ((((u32)wi >> 2) & 3u) << (SH)) + (((u32)wi & 3u) << 2)), "r"(need_), "r"(cross_), "r"(pfneed_) \
@@ -536,6 +536,7 @@ __device__ __forceinline__ void zl_ring_start(u32 ring, u32 sh, const u32* wb16,
         n += (i32)(need_ << 5);                                                                                \
         wi -= (i32)need_;                                                                                      \
     }
+#define ZL_REFILL_RING(SH) ZL_REFILL_RING_(SH, "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t")
 __device__ __forceinline__ u32 zl_selp(u32 a, u32 b, bool c)          // c ? a : b, guaranteed to stay a select
 {
     u32 r;
@@ -581,7 +582,7 @@ ZL_HD u32 zl_huf_stream(const u16* huf, u32 tlog, const u32* wbase, u32 bias, u3
                 i += 4;
             }
 #undef ZL_HUF_SYM_DEV
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("cp.async.wait_all;" ::: "memory");
             b.n = n;
         }
         b.hi = hi; b.lo = lo; b.nextw = nextw; b.wi = wi - (i32)s16;
@@ -880,6 +881,9 @@ ZL_HD void zl_seq_step(const ZlSeqSm& f, ZlBitR& b, const u32* wbase, const ZlCo
 }
 
 #if defined(__CUDACC__)
+#ifndef ZL_SEQ_RING_SYNC
+#define ZL_SEQ_RING_SYNC 2
+#endif
 // code -> (base value | additional bits << 24) for LL (36 entries) then ML (53 entries), in shared memory
 #define ZL_XTAB_WORDS (36 + 53)
 // Fast path over consecutive non-last sequences whose additional bits fit one 32-bit snapshot and whose lengths fit
@@ -905,7 +909,7 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xta
     if (maxIter > room) maxIter = room;
     u32 eLL = zl_lds16(tLL + (sLL << 1)), eOF = zl_lds16(tOF + (sOF << 1)), eML = zl_lds16(tML + (sML << 1));
     u32 it = 0;
-#define ZL_SEQ_LOOP(REFILL) \
+#define ZL_SEQ_LOOP(REFILL, REFILL2) \
     while (it < maxIter) { \
         const u32 llCode = ZL_CELL_SYM(eLL), mlCode = ZL_CELL_SYM(eML), aOF = ZL_CELL_SYM(eOF); \
         const u32 xl = zl_lds32(cLL + (llCode << 2)), xm = zl_lds32(cML + (mlCode << 2)); \
@@ -916,7 +920,7 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xta
         REFILL; \
         const u32 snap = hi; \
         hi = zl_fsl(lo, hi, cA); lo = zl_shl(lo, cA); n -= (i32)cA; \
-        REFILL; \
+        REFILL2; \
         const u32 d2 = bLL + bML, cB = d2 + bOF; \
         sLL = __funnelshift_l(hi, nLL, bLL); \
         sML = __funnelshift_l(zl_fsl(lo, hi, bLL), nML, bML); \
@@ -932,11 +936,15 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xta
         const i32 clow = (wlow + (i32)s16) >> 2;
         wi += (i32)s16;
         zl_ring_start(ring, 7, wb16, wi, clow);
-        ZL_SEQ_LOOP(ZL_REFILL_RING(7))
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#if ZL_SEQ_RING_SYNC == 1
+        ZL_SEQ_LOOP(ZL_REFILL_RING(7), ZL_REFILL_RING(7))
+#else   // one group per sequence (two refills): a chunk is used 6 sequences or more after its copy was issued
+        ZL_SEQ_LOOP(ZL_REFILL_RING_(7, "cp.async.commit_group;\n\tcp.async.wait_group 4;\n\t"), ZL_REFILL_RING_(7, ""))
+#endif
+        asm volatile("cp.async.wait_all;" ::: "memory");
         wi -= (i32)s16;
     } else {
-        ZL_SEQ_LOOP(ZL_REFILL_DEV())
+        ZL_SEQ_LOOP(ZL_REFILL_DEV(), ZL_REFILL_DEV())
     }
 #undef ZL_SEQ_LOOP
     b.hi = hi; b.lo = lo; b.nextw = nextw; b.n = n; b.wi = wi;

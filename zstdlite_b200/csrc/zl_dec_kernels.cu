@@ -88,7 +88,7 @@ zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ i
 // ---- K1b: sequences -----------------------------------------------------------------------------------------
 #define ZL_XTAB_BYTES ((ZL_XTAB_WORDS * 4 + 15) & ~15)
 #ifndef ZL_SEQ_RING
-#define ZL_SEQ_RING 0        // measured: 2.35 -> 2.68 ms with the ring (one decoding lane per quad keeps its words in L1: hit rate 77%)
+#define ZL_SEQ_RING 0        // measured: 2.35 -> 2.68 ms with the ring (stalls gone, but +47% instructions: DESIGN.md section 2)
 #endif
 __global__ void __launch_bounds__(32)
 zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, ZlBlockHdr* hdrArena,
