@@ -501,42 +501,52 @@ __device__ __forceinline__ u32 zl_lds16(u32 a) { u32 v; asm("ld.shared.u16 %0, [
         wi -= (i32)need_;                                                                                      \
     }
 // ---- stream ring: the lane's next words come from shared memory, filled by cp.async in 16-byte chunks --------------------
-// `ring` = shared-space address of the lane's 16-byte column; slot k of the ring lies at ring + (k << SH).  Word indices are
-// relative to the 16-byte aligned `wb16`; `clow` = chunk holding the first byte of the stream (nothing below it is read).
-// zl_ring_start fetches chunks c0 .. c0-3 (slot = chunk & 3); later, entering chunk c fetches chunk c-3 into the slot of c+1.
+// `ring` = shared-space address of the lane's 16-byte column; slot k of the ring lies at ring + (k << SH); NS slots (4 or 8).
+// Word indices are relative to the 16-byte aligned `wb16`; `clow` = chunk holding the first byte of the stream (nothing below
+// it is read).  zl_ring_start fetches chunks c0 .. c0-(NS-1) (slot = chunk & (NS-1)); later, entering chunk c fetches chunk
+// c-(NS-1) into the slot chunk c+1 has just left.
+template <int NS>
 __device__ __forceinline__ void zl_ring_start(u32 ring, u32 sh, const u32* wb16, i32 wi, i32 clow)
 {
     const i32 c0 = wi >> 2;
 #pragma unroll
-    for (i32 k = 0; k < 4; k++) {
+    for (i32 k = 0; k < NS; k++) {
         const i32 c = (c0 - k) < clow ? clow : (c0 - k);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (((u32)(c0 - k) & 3u) << sh)), "l"(wb16 + 4 * c) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (((u32)(c0 - k) & (u32)(NS - 1)) << sh)), "l"(wb16 + 4 * c) : "memory");
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
-// A chunk is used 12 refills (= 12 groups) or more after its copy was issued, so wait_group 8 always covers it;
-// the wait itself only asks for the copies issued 9 refills ago.
-#define ZL_REFILL_RING_(SH, SYNC)                                                                               \
+// One refill.  SYNC = the commit / wait_group text: with a group per refill a chunk is first read 4 (NS-1) refills after its
+// copy was issued, so "wait_group N" with N < 4 (NS-1) always covers it while the warp only waits for copies N+1 refills old.
+// PF = 1 adds an L2 prefetch 256 bytes further down the stream (needed with 4 slots: 9 refills do not cover DRAM latency).
+#define ZL_REFILL_RING_(SH, NS, PF, SYNC)                                                                      \
     {                                                                                                          \
         const u32 need_ = (n <= 32) ? 1u : 0u;                                                                 \
         hi |= zl_shr(nextw, (u32)n);                                                                           \
         lo |= zl_shl(nextw, 32u - (u32)n);                                                                     \
-        const i32 c_ = (wi >> 2) - 3;                                                                          \
+        const i32 c_ = (wi >> 2) - ((NS) - 1);                                                                 \
         const i32 cl_ = c_ < clow ? clow : c_;                                                                 \
-        const i32 pf_ = (c_ - 16) < clow ? clow : (c_ - 16);                                                   \
+        const i32 pf_ = (PF) ? ((c_ - 16) < clow ? clow : (c_ - 16)) : cl_;                                    \
         const u32 cross_ = need_ & (((u32)wi & 3u) == 3u ? 1u : 0u);                                           \
-        const u32 pfneed_ = cross_ & (((u32)c_ & 1u) ? 0u : 1u);                                               \
+        const u32 pfneed_ = (PF) ? (cross_ & (((u32)c_ & 1u) ? 0u : 1u)) : 0u;                                 \
         asm volatile("{\n\t.reg .pred p, q, r;\n\tsetp.ne.u32 p, %5, 0;\n\tsetp.ne.u32 q, %6, 0;\n\tsetp.ne.u32 r, %7, 0;\n\t" \
                      "@q cp.async.cg.shared.global [%1], [%2], 16;\n\t@r prefetch.global.L2 [%3];\n\t"        \
-                     SYNC "@p ld.shared.u32 %0, [%4];\n\t}"    \
+                     SYNC "@p ld.shared.u32 %0, [%4];\n\t}"                                                   \
                      : "+r"(nextw)                                                                             \
-                     : "r"(ring + (((u32)c_ & 3u) << (SH))), "l"(wb16 + 4 * cl_), "l"(wb16 + 4 * pf_),            \
-                       "r"(ring + ((((u32)wi >> 2) & 3u) << (SH)) + (((u32)wi & 3u) << 2)), "r"(need_), "r"(cross_), "r"(pfneed_) \
+                     : "r"(ring + (((u32)c_ & (u32)((NS) - 1)) << (SH))), "l"(wb16 + 4 * cl_), "l"(wb16 + 4 * pf_), \
+                       "r"(ring + ((((u32)wi >> 2) & (u32)((NS) - 1)) << (SH)) + (((u32)wi & 3u) << 2)), "r"(need_), "r"(cross_), "r"(pfneed_) \
                      : "memory");                                                                              \
         n += (i32)(need_ << 5);                                                                                \
         wi -= (i32)need_;                                                                                      \
     }
-#define ZL_REFILL_RING(SH) ZL_REFILL_RING_(SH, "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t")
+#ifndef ZL_LIT_RING_SLOTS
+#define ZL_LIT_RING_SLOTS 8
+#endif
+#if ZL_LIT_RING_SLOTS == 8
+#define ZL_REFILL_RING_LIT() ZL_REFILL_RING_(9, 8, 0, "cp.async.commit_group;\n\tcp.async.wait_group 20;\n\t")
+#else
+#define ZL_REFILL_RING_LIT() ZL_REFILL_RING_(9, 4, 1, "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t")
+#endif
 __device__ __forceinline__ u32 zl_selp(u32 a, u32 b, bool c)          // c ? a : b, guaranteed to stay a select
 {
     u32 r;
@@ -569,15 +579,15 @@ ZL_HD u32 zl_huf_stream(const u16* huf, u32 tlog, const u32* wbase, u32 bias, u3
         i32 wi = b.wi + (i32)s16;
         const i32 clow = (b.wlow + (i32)s16) >> 2; // chunk holding the first byte of the stream (never read below it)
         const u32 th = zl_smem_addr(huf);
-        zl_ring_start(ring, 9, wb16, wi, clow);
+        zl_ring_start<ZL_LIT_RING_SLOTS>(ring, 9, wb16, wi, clow);
         {
             i32 n = b.n;
 #define ZL_HUF_SYM_DEV(dst) { const u32 e = zl_lds16(th + ((hi >> sh) << 1)); const u32 nb = e >> 8; \
                               hi = zl_fsl(lo, hi, nb); lo <<= nb; n -= (i32)nb; dst = e & 0xFF; }
             while (i + 4 <= count) {
                 u32 s0, s1, s2, s3;
-                ZL_REFILL_RING(9); ZL_HUF_SYM_DEV(s0); ZL_HUF_SYM_DEV(s1);
-                ZL_REFILL_RING(9); ZL_HUF_SYM_DEV(s2); ZL_HUF_SYM_DEV(s3);
+                ZL_REFILL_RING_LIT(); ZL_HUF_SYM_DEV(s0); ZL_HUF_SYM_DEV(s1);
+                ZL_REFILL_RING_LIT(); ZL_HUF_SYM_DEV(s2); ZL_HUF_SYM_DEV(s3);
                 __stcs((u32*)(out + i), s0 | (s1 << 8) | (s2 << 16) | (s3 << 24));
                 i += 4;
             }
@@ -935,11 +945,11 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xta
         const u32* wb16 = wbase - s16;
         const i32 clow = (wlow + (i32)s16) >> 2;
         wi += (i32)s16;
-        zl_ring_start(ring, 7, wb16, wi, clow);
+        zl_ring_start<4>(ring, 7, wb16, wi, clow);
 #if ZL_SEQ_RING_SYNC == 1
-        ZL_SEQ_LOOP(ZL_REFILL_RING(7), ZL_REFILL_RING(7))
+        ZL_SEQ_LOOP(ZL_REFILL_RING_(7, 4, 1, "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t"), ZL_REFILL_RING_(7, 4, 1, "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t"))
 #else   // one group per sequence (two refills): a chunk is used 6 sequences or more after its copy was issued
-        ZL_SEQ_LOOP(ZL_REFILL_RING_(7, "cp.async.commit_group;\n\tcp.async.wait_group 4;\n\t"), ZL_REFILL_RING_(7, ""))
+        ZL_SEQ_LOOP(ZL_REFILL_RING_(7, 4, 1, "cp.async.commit_group;\n\tcp.async.wait_group 4;\n\t"), ZL_REFILL_RING_(7, 4, 1, ""))
 #endif
         asm volatile("cp.async.wait_all;" ::: "memory");
         wi -= (i32)s16;

@@ -47,7 +47,7 @@ zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ i
     const u32 lane = threadIdx.x, quad = lane >> 2, q = lane & 3;
     const u32 qmask = 0xFu << (quad * 4);
     ZlLitSm& f = fs[quad];
-    // stream ring: 4 slots of 32 x 16 bytes behind the eight units (zl_huf_stream)
+    // stream ring: ZL_LIT_RING_SLOTS slots of 32 x 16 bytes behind the eight units (zl_huf_stream)
     const u32 ring = ZL_LIT_RING ? zl_smem_addr(smraw + ZL_QUADS_PER_WARP * sizeof(ZlLitSm)) + lane * 16u : 0u;
     const u32 nunits = *unitCount;
     for (;;) {
@@ -372,7 +372,7 @@ zl_k_xxh64_large(const u8* const* __restrict__ ptrs, const u32* __restrict__ siz
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------
-size_t zl_literals_smem_bytes() { return ZL_QUADS_PER_WARP * sizeof(ZlLitSm) + (ZL_LIT_RING ? 4 * 32 * 16 : 0); }
+size_t zl_literals_smem_bytes() { return ZL_QUADS_PER_WARP * sizeof(ZlLitSm) + (ZL_LIT_RING ? ZL_LIT_RING_SLOTS * 32 * 16 : 0); }
 size_t zl_sequences_smem_bytes() { return ZL_XTAB_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlSeqSm) + (ZL_SEQ_RING ? 4 * 8 * 16 : 0); }
 
 static int g_sms = 0, g_litPerSm = 0, g_seqPerSm = 0;
