@@ -486,13 +486,16 @@ __device__ __forceinline__ u32 zl_lds16(u32 a) { u32 v; asm("ld.shared.u16 %0, [
 // bits of (hi:lo) below the n valid ones are always zero and the clamped shifts make both ORs no-ops when n > 32.
 // The look-ahead load and the L1 prefetch of the sector two sectors further down are predicated PTX, so the
 // compiler cannot turn them into divergent branches.
+#ifndef ZL_PF_DIST
+#define ZL_PF_DIST 16         // words between the lane's position and its L1 prefetch
+#endif
 #define ZL_REFILL_DEV()                                                                                        \
     {                                                                                                          \
         const u32 need_ = (n <= 32) ? 1u : 0u;                                                                 \
         hi |= zl_shr(nextw, (u32)n);                                                                           \
         lo |= zl_shl(nextw, 32u - (u32)n);                                                                     \
         const i32 i_ = wi < wlow ? wlow : wi;                                                                  \
-        const i32 pf_ = (wi - 16) < wlow ? wlow : (wi - 16);                                                   \
+        const i32 pf_ = (wi - ZL_PF_DIST) < wlow ? wlow : (wi - ZL_PF_DIST);                                   \
         const u32 pfneed_ = need_ & (((u32)wi & 7u) == 7u ? 1u : 0u);                                          \
         asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %3, 0;\n\tsetp.ne.u32 q, %4, 0;\n\t"              \
                      "@p ld.global.nc.u32 %0, [%1];\n\t@q prefetch.global.L1 [%2];\n\t}"                          \
@@ -891,6 +894,9 @@ ZL_HD void zl_seq_step(const ZlSeqSm& f, ZlBitR& b, const u32* wbase, const ZlCo
 }
 
 #if defined(__CUDACC__)
+#ifndef ZL_SEQ_RING_PF
+#define ZL_SEQ_RING_PF 0          // L2 prefetch of the sequence ring: its address arithmetic costs more than it hides
+#endif
 #ifndef ZL_SEQ_RING_SYNC
 #define ZL_SEQ_RING_SYNC 2
 #endif
@@ -947,9 +953,9 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xta
         wi += (i32)s16;
         zl_ring_start<4>(ring, 7, wb16, wi, clow);
 #if ZL_SEQ_RING_SYNC == 1
-        ZL_SEQ_LOOP(ZL_REFILL_RING_(7, 4, 1, "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t"), ZL_REFILL_RING_(7, 4, 1, "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t"))
+        ZL_SEQ_LOOP(ZL_REFILL_RING_(7, 4, ZL_SEQ_RING_PF, "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t"), ZL_REFILL_RING_(7, 4, ZL_SEQ_RING_PF, "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t"))
 #else   // one group per sequence (two refills): a chunk is used 6 sequences or more after its copy was issued
-        ZL_SEQ_LOOP(ZL_REFILL_RING_(7, 4, 1, "cp.async.commit_group;\n\tcp.async.wait_group 4;\n\t"), ZL_REFILL_RING_(7, 4, 1, ""))
+        ZL_SEQ_LOOP(ZL_REFILL_RING_(7, 4, ZL_SEQ_RING_PF, "cp.async.commit_group;\n\tcp.async.wait_group 4;\n\t"), ZL_REFILL_RING_(7, 4, ZL_SEQ_RING_PF, ""))
 #endif
         asm volatile("cp.async.wait_all;" ::: "memory");
         wi -= (i32)s16;

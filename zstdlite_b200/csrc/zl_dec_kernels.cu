@@ -88,7 +88,7 @@ zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ i
 // ---- K1b: sequences -----------------------------------------------------------------------------------------
 #define ZL_XTAB_BYTES ((ZL_XTAB_WORDS * 4 + 15) & ~15)
 #ifndef ZL_SEQ_RING
-#define ZL_SEQ_RING 0        // measured: 2.35 -> 2.68 ms with the ring (stalls gone, but +47% instructions: DESIGN.md section 2)
+#define ZL_SEQ_RING 1        // 4 slots, a group per sequence, no L2 prefetch: the kernel alone 2.38 -> 2.43 ms, the sliced step 151.3 -> 155.6 GB/s
 #endif
 __global__ void __launch_bounds__(32)
 zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ infos, ZlBlockHdr* hdrArena,
