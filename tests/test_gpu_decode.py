@@ -246,3 +246,28 @@ def test_large_frames_take_the_block_parallel_path(z, ref):
         bad.append(bytes(m))
     res, _ = gpu_decompress_batch(bad, [len(big["text"])] * len(bad))
     assert all(z.is_error(r) for r in res)
+
+
+def test_source_alignment_sweep(z, ref):
+    """The entropy kernels fetch their bitstreams as aligned 16-byte chunks (cp.async ring): the same frames at every source
+    alignment 0..15, with the last one ending on the last byte of the buffer, must decode to the same bytes."""
+    import torch
+    from zstdlite_b200 import corpus
+    datas = [corpus.make(fam, size, 5).tobytes() for fam in ("text", "lowent", "rdf") for size in (300, 5000, 65536)]
+    frames = [ref.compress(d, 3) for d in datas]
+    srcs, dsts, sizes, caps, want = [], [], [], [], []
+    bufs = []
+    for a in range(16):
+        for f, d in zip(frames, datas):
+            # the frame sits `a` bytes into a 256-byte aligned block whose last byte is the frame's last byte when a == 15
+            n = a + len(f)
+            buf = torch.zeros((n + 255) // 256 * 256 if a != 15 else n, dtype=torch.uint8, device="cuda")
+            buf[a:a + len(f)] = torch.frombuffer(bytearray(f), dtype=torch.uint8).cuda()
+            out = torch.zeros(len(d) + 16, dtype=torch.uint8, device="cuda")
+            bufs.append((buf, out))
+            srcs.append(buf.data_ptr() + a); sizes.append(len(f)); dsts.append(out.data_ptr()); caps.append(len(d)); want.append(d)
+    torch.cuda.synchronize()
+    res = z.decompress_batch(z.zstd_dctx(), srcs, sizes, dsts, caps, device=True)
+    for i, (r, w) in enumerate(zip(res, want)):
+        assert not z.is_error(r), (i, z.error_name(r))
+        assert r == len(w) and bufs[i][1][:len(w)].cpu().numpy().tobytes() == w, i
