@@ -353,10 +353,10 @@ ZL_HD void zl_index_frame(const ZlFrameDesc& d, ZlFrameInfo& info, ZlBlockHdr* h
                         if (!err) {
                             seqTotal += nbSeq;
                             if (seqTotal > (u64)d.dstCap / 3 + 8) err = ZL_E_corruption_detected;          // more sequences than dst could hold
-                            else if ((u64)recUsed + nbSeq + ZL_REC_SLACK > d.recCap) err = ZL_E_INTERNAL_hdrCap;   // many blocks: retry with the worst-case arena
+                            else if ((u64)recUsed + nbSeq + ZL_REC_SLACK + 1u > d.recCap) err = ZL_E_INTERNAL_hdrCap;   // many blocks: retry with the worst-case arena
                         }
                     }
-                    if (!err) { h.nbSeq = nbSeq; h.recOff = recUsed; if (nbSeq) recUsed += nbSeq + ZL_REC_SLACK; }
+                    if (!err) { h.nbSeq = nbSeq; h.recOff = recUsed; if (nbSeq) recUsed += (nbSeq + ZL_REC_SLACK + 1u) & ~1u; }   // even: the execute kernel loads record pairs
                 }
                 h.flags |= 2u | (litMode << 4);
                 h.litSize = litSize; h.seqOff = seqOff; h.seqEnd = blockEnd;

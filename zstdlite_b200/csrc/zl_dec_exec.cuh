@@ -95,9 +95,9 @@ ZL_D void zl_lane_record(u64 rec, bool valid, const u32* xtab, u32& ll, u32& ml,
 // history slot (0..3, 3 = "rep0 - 1") a record reads; 0 also for records that do not read the history
 ZL_D u32 zl_rep_idx(u32 ll, u32 ml, u32 ob) { return (ml != 0 && ob >= 1 && ob <= 3) ? ob - 1 + (ll == 0 ? 1u : 0u) : 0u; }
 // the transform of one record in the byte form (never called for idx == 3)
-ZL_D u32 zl_rept_of(bool isNew, u32 idx, u32 lane)
+ZL_D u32 zl_rept_of(bool isNew, u32 idx, u32 tag)       // tag < 128: names the record that carries the fresh offset
 {
-    if (isNew) return 0x00010000u | 0x80u | lane;                                 // (mine, h0, h1)
+    if (isNew) return 0x00010000u | 0x80u | tag;                                 // (mine, h0, h1)
     if (idx == 1) return 0x00020001u;                                             // (h1, h0, h2)
     if (idx == 2) return 0x00010002u;                                             // (h2, h0, h1)
     return ZL_REPT_ID;
@@ -171,115 +171,240 @@ ZL_D u32 zl_flat_owner(u32 rs, u32 j)
     return k & 31;
 }
 
-// Flat byte-parallel copy over the (up to 32) segments of a batch, two rows of 32 bytes per step, both loads of a step before
-// its first store (4 rows and a higher occupancy were measured slower).  Lane k owns flat indices [start, start + len).  Owner of a flat index: the segments that hold bytes
-// were compacted into `seg` (x = destination - flat start, y = source - flat start); per row one REDUX ORs the start bits of the
-// segments beginning in it and a popcount up to the lane's own bit ranks the lane among them -- no per-byte search.
-template <typename LoadF>
-ZL_D void zl_flat_copy(u8* out, const uint2* seg, u32 start, u32 len, u32 total, u32 lane, u32 leMask, LoadF load)
+// ---- one-pass execute ---------------------------------------------------------------------------------------------------
+// A batch is 128 records, four consecutive ones per lane.  Its (up to 256) non-empty segments -- literal run, match, literal
+// run, match ... -- tile the batch's output bytes in order, so the warp writes that output ONCE, front to back, 64 bytes (two
+// 32-byte rows) per step; rows are aligned to 32 bytes of the destination address, so a row is one full sector.
+//   planning   record -> (litLength, matchLength, offBase) per lane; one warp scan over the lane sums gives every record its
+//              place in the output and in the literal stream; the repeat-offset history (zstd.c:44290-44326) is one warp scan over
+//              the composed transforms of the lanes' four records, fresh offsets are fetched through shared memory;
+//              the bounds checks of ZSTD_execSequence (zstd.c:44024-44066) for the whole batch, before anything is written
+//   tables     `seg`: the compacted segment table (source address of flat index 0, flat start, match offset or the literal
+//              flag); `row`: for every 32-byte row of a 4 KiB window of the output the bit mask of the segments starting in it
+//              (shared-memory atomics) and the number of segments before it (a scan over the rows)
+//   steps      owner of an output byte = segments before its row + popcount of the row's start bits up to its own bit.  The steps
+//              run in output order, so every byte below the current step is final when the step loads its sources; only sources
+//              INSIDE the step (offset < 64) are not in memory yet -- those bytes are resolved between the lanes with shuffles
+//              (value + "resolved" flag of both rows packed in one register; a source always lies earlier in the step, so the
+//              lowest unresolved byte resolves every iteration; overlapping matches first fold their source below their own
+//              start with the periodic form src = start - offset + (k mod offset), zstd.c:43816 ZSTD_overlapCopy8).  Steps that
+//              lie inside one segment (no start bit in either row: long literal runs, long or run-length matches) take a
+//              uniform path without the owner lookup.
+// Round 1 handled 32 records at a time, copied their literals in one pass and resolved the matches in rounds against a
+// high-water mark (2.4 - 4.4 rounds per batch, each with its own scan and segment table): ~900 warp instructions per 32 sequences.
+#define ZL_SEG_LIT 0x80000000u
+#define ZL_XB 4                          // records per lane
+#define ZL_XBATCH (32 * ZL_XB)           // records per batch
+#define ZL_XROWS 128                     // rows per window of the row table (4 KiB of output)
+struct ZlExecSm {                        // per warp: 5 KB
+    uint4 seg[2 * ZL_XBATCH];            // x, y = P: address of the segment's source byte for flat index 0 (source of byte j = P + j);
+                                         // z = flat start; w = match offset, or ZL_SEG_LIT for a literal run
+    union { u32 fresh[ZL_XBATCH]; uint2 row[ZL_XROWS]; } u;      // fresh offsets while planning / row table while stepping
+};
+ZL_D uint2 zl_lds64(u32 a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+ZL_D uint4 zl_lds128(u32 a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+ZL_D u32 zl_lds32s(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+// k mod d for d < 64 with the reciprocal table rcp[d] = floor((2^32 - 1) / d) in shared memory (k < 2^18: the estimate is at most one short)
+ZL_D u32 zl_mod_small(u32 k, u32 d, u32 rcpA)
 {
-    const u32 srow = start >> 5, sbit = len ? 1u << (start & 31u) : 0u;
-    u32 cnt = 0;
-    for (u32 j0 = 0; j0 < total; j0 += 64) {
-        const u32 r = j0 >> 5;
-        const u32 m0 = __reduce_or_sync(ZL_FULL, srow == r ? sbit : 0u);
-        const u32 m1 = __reduce_or_sync(ZL_FULL, srow == r + 1 ? sbit : 0u);
-        const u32 c0 = cnt + __popc(m0 & leMask) - 1u;
-        cnt += __popc(m0);
-        const u32 c1 = cnt + __popc(m1 & leMask) - 1u;
-        cnt += __popc(m1);
-        const u32 ja = j0 + lane, jb = ja + 32;
-        const bool aa = ja < total, ab = jb < total;
-        const uint2 sa = seg[c0 & 31u], sb = seg[c1 & 31u];
-        u32 va = 0, vb = 0;
-        if (aa) va = load(ja, sa.y);
-        if (ab) vb = load(jb, sb.y);
-        if (aa) out[ja + sa.x] = (u8)va;
-        if (ab) out[jb + sb.x] = (u8)vb;
+    const u32 q = __umulhi(k, zl_lds32s(rcpA + (d << 2)));
+    u32 r = k - q * d;
+    if (r >= d) r -= d;
+    return r;
+}
+ZL_D const u8* zl_ptr_add(u32 lo, u32 hi, u32 j) { return reinterpret_cast<const u8*>((((u64)hi << 32) | lo) + j); }
+
+// Offsets of the 128 records of a batch (record m of lane l carries the tag 4 l + m) and the history after it; h0..h2 in/out.
+ZL_D void zl_batch_offsets4(const u32 (&ll)[ZL_XB], const u32 (&ml)[ZL_XB], const u32 (&ob)[ZL_XB], u32 lane, u32* fresh,
+                            u32& h0, u32& h1, u32& h2, u32 (&off)[ZL_XB])
+{
+    u32 idx[ZL_XB], t[ZL_XB];
+    bool minus1 = false;
+#pragma unroll
+    for (int m = 0; m < ZL_XB; m++) {
+        idx[m] = zl_rep_idx(ll[m], ml[m], ob[m]);
+        minus1 |= idx[m] == 3;
+        t[m] = zl_rept_of(ml[m] != 0 && ob[m] >= 4, idx[m], 4u * lane + (u32)m);
     }
+    if (__any_sync(ZL_FULL, minus1)) {
+        // rare "rep0 - 1" code somewhere in the batch: resolve the records one after the other (uniform loop)
+        u32 hh[3] = {h0, h1, h2};
+        for (u32 l = 0; l < 32; l++) {
+#pragma unroll
+            for (int m = 0; m < ZL_XB; m++) {
+                const u32 lll = __shfl_sync(ZL_FULL, ll[m], l), lml = __shfl_sync(ZL_FULL, ml[m], l), lob = __shfl_sync(ZL_FULL, ob[m], l);
+                const u32 o = zl_rep_resolve(hh, lll, lml, lob);
+                if (l == lane) off[m] = o;
+            }
+        }
+        h0 = hh[0]; h1 = hh[1]; h2 = hh[2];
+        return;
+    }
+    *reinterpret_cast<uint4*>(fresh + 4u * lane) = make_uint4(ob[0] - 3u, ob[1] - 3u, ob[2] - 3u, ob[3] - 3u);
+    const u32 t01 = zl_rept_compose(t[0], t[1]), t012 = zl_rept_compose(t01, t[2]);
+    const u32 T = zl_rept_scan(zl_rept_compose(t012, t[3]), lane);
+    u32 E = __shfl_up_sync(ZL_FULL, T, 1);                                  // exclusive prefix: history before this lane's records
+    if (lane == 0) E = ZL_REPT_ID;
+    __syncwarp();
+    const u32 e[ZL_XB] = {E, zl_rept_compose(E, t[0]), zl_rept_compose(E, t01), zl_rept_compose(E, t012)};
+#pragma unroll
+    for (int m = 0; m < ZL_XB; m++) {
+        const u32 eb = (e[m] >> (8u * idx[m])) & 0xFFu;                     // the slot of the incoming history this record reads
+        const u32 fromTag = fresh[eb & 127u];
+        const u32 fromHist = (eb & 3u) == 0 ? h0 : ((eb & 3u) == 1 ? h1 : h2);
+        off[m] = (ml[m] != 0 && ob[m] >= 4) ? ob[m] - 3u : ((eb & 0x80u) ? fromTag : fromHist);
+    }
+    const u32 Lt = __shfl_sync(ZL_FULL, T, 31);                            // history after the batch
+    const u32 b0 = Lt & 0xFFu, b1 = (Lt >> 8) & 0xFFu, b2 = (Lt >> 16) & 0xFFu;
+    const u32 f0 = fresh[b0 & 127u], f1 = fresh[b1 & 127u], f2 = fresh[b2 & 127u];
+    const u32 n0 = (b0 & 0x80u) ? f0 : ((b0 & 3u) == 0 ? h0 : ((b0 & 3u) == 1 ? h1 : h2));
+    const u32 n1 = (b1 & 0x80u) ? f1 : ((b1 & 3u) == 0 ? h0 : ((b1 & 3u) == 1 ? h1 : h2));
+    const u32 n2 = (b2 & 0x80u) ? f2 : ((b2 & 3u) == 0 ? h0 : ((b2 & 3u) == 1 ? h1 : h2));
+    h0 = n0; h1 = n1; h2 = n2;
 }
 
-// Execute one compressed block: `out` = frame output base, `op` = frame-relative position of the block, `cap` = bytes the
-// block may still regenerate (destination room, at most one block size), `capErr` the error to report beyond it.
-// hist[3] is the repeat-offset history carried from block to block.  Returns 0 and sets `regen`, or a ZlErr.
 template <bool kDict>
 ZL_D u32 zl_exec_block(u8* out, u32 op, u32 cap, u32 capErr, const ZlBlockHdr& h, const u8* __restrict__ lit, u32 rleByte, u32 litMode,
-                       const u64* __restrict__ recs, const u8* __restrict__ dict, u32 dictSize, u32 (&hist)[3], const u32* xtab, uint2* seg, u32 lane, u32& regen)
+                       const u64* __restrict__ recs, const u8* __restrict__ dict, u32 dictSize, u32 (&hist)[3], const u32* xtab, const u32* rcp,
+                       ZlExecSm* sm, u32 lane, u32& regen)
 {
-    // `seg`: 32 x uint2 of shared memory owned by this warp -- the compacted segment table of the flat copies (below)
+    // `recs` is 16-byte aligned (the index kernel hands out even record offsets); rcp: the 64 reciprocals of zl_mod_small
     const u32 nrec = h.nrec, litSize = h.litSize;
-    const u32 ltMask = (1u << lane) - 1u, leMask = 0xFFFFFFFFu >> (31u - lane);
+    const u32 leMask = 0xFFFFFFFFu >> (31u - lane);
+    const u32 segA = (u32)__cvta_generic_to_shared(sm->seg), rowA = (u32)__cvta_generic_to_shared(sm->u.row), rcpA = (u32)__cvta_generic_to_shared(rcp);
+    const bool rleLits = litMode == 1;
     u32 outPos = op, litPos = 0;
     u32 h0 = hist[0], h1 = hist[1], h2 = hist[2];
-    u64 recNext = lane < nrec ? __ldcs(recs + lane) : 0ull;
-    for (u32 base = 0; base < nrec; base += 32) {
-        const u64 rec = recNext;
-        const bool valid = base + lane < nrec;
-        {   const u32 in = base + 32 + lane; recNext = in < nrec ? __ldcs(recs + in) : 0ull; }
-        u32 ll, ml, ob;
-        zl_lane_record(rec, valid, xtab, ll, ml, ob);
-        const bool isM = ml != 0;
-        const u32 off = zl_batch_offsets(ll, ml, ob, lane, h0, h1, h2);
-        u32 sl, so, totalL, totalO;
-        zl_batch_positions(ll, ml, lane, sl, so, totalL, totalO);
-        const u32 litExcl = sl - ll;                 // literal bytes of earlier lanes in this batch
-        const u32 dstLit = outPos + so - ll - ml;    // where this lane's literals go
-        const u32 dm = dstLit + ll;                  // where this lane's match goes
+    // output byte at frame position sp (negative: dictionary)
+    auto outPtr = [&](i32 sp) -> const u8* { return (kDict && sp < 0) ? dict + ((i32)dictSize + sp) : out + sp; };
+    for (u32 base = 0; base < nrec; base += ZL_XBATCH) {
+        const u32 i0 = base + ZL_XB * lane;
+        ulonglong2 ra = make_ulonglong2(0ull, 0ull), rb = ra;
+        if (i0 < nrec) ra = __ldcs(reinterpret_cast<const ulonglong2*>(recs + i0));
+        if (i0 + 2 < nrec) rb = __ldcs(reinterpret_cast<const ulonglong2*>(recs + i0 + 2));
+        if (i0 + ZL_XBATCH < nrec) asm volatile("prefetch.global.L1 [%0];" ::"l"(recs + i0 + ZL_XBATCH));
+        u32 ll[ZL_XB], ml[ZL_XB], ob[ZL_XB], off[ZL_XB];
+        zl_lane_record(ra.x, i0 < nrec, xtab, ll[0], ml[0], ob[0]);
+        zl_lane_record(ra.y, i0 + 1 < nrec, xtab, ll[1], ml[1], ob[1]);
+        zl_lane_record(rb.x, i0 + 2 < nrec, xtab, ll[2], ml[2], ob[2]);
+        zl_lane_record(rb.y, i0 + 3 < nrec, xtab, ll[3], ml[3], ob[3]);
+        // ---- places: one scan over (literal bytes | non-empty segments << 23, output bytes) of the lanes
+        const u32 L = ll[0] + ll[1] + ll[2] + ll[3], O = L + ml[0] + ml[1] + ml[2] + ml[3];      // L < 2^23: lengths are < 65536
+        u32 nseg = 0;
+#pragma unroll
+        for (int m = 0; m < ZL_XB; m++) nseg += (ll[m] ? 1u : 0u) + (ml[m] ? 1u : 0u);
+        u32 sl = L | (nseg << 23), so = O;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 a = __shfl_up_sync(ZL_FULL, sl, d), b = __shfl_up_sync(ZL_FULL, so, d);
+            if ((int)lane >= d) { sl += a; so += b; }
+        }
+        const u32 tot = __shfl_sync(ZL_FULL, sl, 31), totalO = __shfl_sync(ZL_FULL, so, 31);
+        const u32 totalL = tot & 0x7FFFFFu;
         // ---- the checks of ZSTD_execSequence (zstd.c:44024-44066, 44320) for the whole batch, before anything is written
         if (totalL > litSize - litPos) return ZL_E_corruption_detected;
         if ((outPos - op) + totalO > cap) return capErr;
-        if (__ballot_sync(ZL_FULL, isM && (off == 0 || off > dm + dictSize))) return ZL_E_corruption_detected;
-        // ---- literals: one flat copy over the batch (zl_flat_copy)
-        if (totalL) {
-            const u32 ci = __popc(__ballot_sync(ZL_FULL, ll != 0) & ltMask);
-            if (ll) seg[ci].x = dstLit - litExcl;
-            __syncwarp();
-            const u8* lsrc = lit + litPos;
-            if (litMode == 1) zl_flat_copy(out, seg, litExcl, ll, totalL, lane, leMask, [&](u32, u32) { return rleByte; });
-            else zl_flat_copy(out, seg, litExcl, ll, totalL, lane, leMask, [&](u32 j, u32) { return (u32)__ldg(lsrc + j); });
-        }
-        __syncwarp();
-        // ---- matches: rounds against the high-water mark (signed positions: negative = dictionary)
-        u32 pending = __ballot_sync(ZL_FULL, isM);
-        const i32 srcBeg = (i32)dm - (i32)off;
-        const bool overlap = off < ml;
-        const i32 needEnd = srcBeg + (i32)(overlap ? off : ml);       // end of the source bytes actually read, <= dm
-        while (pending) {
-            const u32 f = (u32)__ffs((int)pending) - 1;
-            const i32 hwm = (i32)__shfl_sync(ZL_FULL, dm, f);
-            const bool ready = ((pending >> lane) & 1) && (lane == f || needEnd <= hwm);
-            // (a) ready matches that do not overlap their own output: one flat byte-parallel copy over all of them, so the
-            //     lanes share the bytes evenly whatever the individual lengths are; two rows per step, loads before stores
-            const u32 fl = (ready && !overlap) ? ml : 0u;
-            u32 rs = fl;
+        zl_batch_offsets4(ll, ml, ob, lane, sm->u.fresh, h0, h1, h2, off);
+        // ---- compacted segment table
+        const u32 ord0 = (sl >> 23) - nseg;                       // segments of earlier lanes
+        u8* const ob8 = out + outPos;                        // flat index 0 of the batch
+        {
+            u32 f = so - O, li = litPos + (sl & 0x7FFFFFu) - L, ord = ord0;
+            bool bad = false;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const u32 a = __shfl_up_sync(ZL_FULL, rs, d); if ((int)lane >= d) rs += a; }
-            const u32 totalM = __shfl_sync(ZL_FULL, rs, 31);
-            const u32 rsExcl = rs - fl;
-            if (totalM) {
-                const u32 ci = __popc(__ballot_sync(ZL_FULL, fl != 0) & ltMask);
-                if (fl) seg[ci] = make_uint2(dm - rsExcl, (u32)srcBeg - rsExcl);
-                __syncwarp();
-                zl_flat_copy(out, seg, rsExcl, fl, totalM, lane, leMask, [&](u32 j, u32 sd) {
-                    const i32 sp = (i32)(j + sd);
-                    return (kDict && sp < 0) ? (u32)dict[(i32)dictSize + sp] : (u32)out[sp];
-                });
+            for (int m = 0; m < ZL_XB; m++) {
+                if (ll[m]) { const u64 P = (u64)(size_t)lit + li - f; sm->seg[ord++] = make_uint4((u32)P, (u32)(P >> 32), f, ZL_SEG_LIT); }
+                f += ll[m]; li += ll[m];
+                bad |= ml[m] != 0 && (off[m] == 0 || off[m] > outPos + f + dictSize);
+                if (ml[m]) { const u64 P = (u64)(size_t)ob8 - off[m]; sm->seg[ord++] = make_uint4((u32)P, (u32)(P >> 32), f, off[m]); }
+                f += ml[m];
             }
-            // (b) ready matches that overlap their own output (offset < length): the periodic form dst[k] = src[k mod offset]
-            //     only reads bytes below the match, one match at a time across the warp
-            u32 ov = __ballot_sync(ZL_FULL, ready && overlap);
-            while (ov) {
-                const u32 L = (u32)__ffs((int)ov) - 1;
-                ov &= ov - 1;
-                const u32 bdm = __shfl_sync(ZL_FULL, dm, L), boff = __shfl_sync(ZL_FULL, off, L), bml = __shfl_sync(ZL_FULL, ml, L);
-                const i32 bsrc = (i32)bdm - (i32)boff;
-                for (u32 k = lane; k < bml; k += 32) {
-                    const i32 sp = bsrc + (i32)(k % boff);
-                    out[bdm + k] = (kDict && sp < 0) ? dict[(i32)dictSize + sp] : out[sp];
-                }
+            if (__any_sync(ZL_FULL, bad)) return ZL_E_corruption_detected;
+        }
+        // rows are aligned to 32 bytes of the destination: aligned flat index a = flat index + mis
+        const u32 mis = (u32)((size_t)ob8 & 31u);
+        const u32 totalA = totalO + mis;
+        u32 segsBefore = 0;                                  // segments that start in earlier windows
+        for (u32 w0 = 0; w0 < totalA; w0 += ZL_XROWS * 32) {
+            // ---- row table of the window [w0, w0 + 4 KiB): start masks by atomics, then the exclusive count over the rows
+            __syncwarp();
+            reinterpret_cast<uint4*>(sm->u.row)[2 * lane] = make_uint4(0u, 0u, 0u, 0u);
+            reinterpret_cast<uint4*>(sm->u.row)[2 * lane + 1] = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+#pragma unroll
+            for (u32 k = 0; k < 2 * ZL_XB; k++) {
+                const u32 a = zl_lds32s(segA + (((ord0 + k) & 255u) << 4) + 8u) + mis - w0;
+                if (k < nseg && a < ZL_XROWS * 32) atomicOr(&sm->u.row[a >> 5].x, 1u << (a & 31u));
             }
             __syncwarp();
-            pending &= ~__ballot_sync(ZL_FULL, ready);
+            {
+                uint4 qa = zl_lds128(rowA + lane * 32u), qb = zl_lds128(rowA + lane * 32u + 16u);      // rows 4 lane .. 4 lane + 3
+                const u32 c0 = __popc(qa.x), c1 = __popc(qa.z), c2 = __popc(qb.x), c3 = __popc(qb.z);
+                u32 inc = c0 + c1 + c2 + c3;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const u32 a = __shfl_up_sync(ZL_FULL, inc, d); if ((int)lane >= d) inc += a; }
+                const u32 ex = segsBefore + inc - (c0 + c1 + c2 + c3);
+                qa.y = ex; qa.w = ex + c0; qb.y = ex + c0 + c1; qb.w = ex + c0 + c1 + c2;
+                reinterpret_cast<uint4*>(sm->u.row)[2 * lane] = qa;
+                reinterpret_cast<uint4*>(sm->u.row)[2 * lane + 1] = qb;
+                segsBefore += __shfl_sync(ZL_FULL, inc, 31);
+            }
+            __syncwarp();
+            const u32 wEnd = min(totalA, w0 + ZL_XROWS * 32);
+            for (u32 a0 = w0; a0 < wEnd; a0 += 64) {
+                const uint4 ri = zl_lds128(rowA + ((a0 - w0) >> 5) * 8u);    // {mask, segments before} of the step's two rows
+                const u32 ja = a0 + lane - mis, jb = ja + 32;                  // flat indices of this lane's two bytes (first step: ja may wrap below 0)
+                const u32 d0 = a0 < mis ? lane - (mis - a0) : lane;            // distance of byte a from the first flat index of the step
+                if ((ri.x | ri.z) == 0u && a0 + 64 <= totalA) {
+                    // ---- the whole step lies inside one segment, which began before it: no owner lookup, no in-step sources
+                    const uint4 s = zl_lds128(segA + (((ri.y - 1u) & 255u) << 4));
+                    u32 va = rleByte, vb = rleByte;
+                    if (s.w < 64u) {                                           // sources inside the match itself: fold below its start
+                        u32 ta = ja - s.w, tb = jb - s.w;
+                        if ((i32)ta >= (i32)s.z) ta = s.z - s.w + zl_mod_small(ja - s.z, s.w, rcpA);
+                        if ((i32)tb >= (i32)s.z) tb = s.z - s.w + zl_mod_small(jb - s.z, s.w, rcpA);
+                        va = *outPtr((i32)(outPos + ta)); vb = *outPtr((i32)(outPos + tb));
+                    } else if (!(s.w == ZL_SEG_LIT && rleLits)) {
+                        const u8* pa = zl_ptr_add(s.x, s.y, ja);
+                        const u8* pb = zl_ptr_add(s.x, s.y, jb);
+                        if (kDict && s.w != ZL_SEG_LIT) { pa = outPtr((i32)(outPos + ja - s.w)); pb = outPtr((i32)(outPos + jb - s.w)); }
+                        va = *pa; vb = *pb;
+                    }
+                    ob8[ja] = (u8)va; ob8[jb] = (u8)vb;
+                    __syncwarp();
+                    continue;
+                }
+                const u32 c0 = ri.y + __popc(ri.x & leMask) - 1u, c1 = ri.w + __popc(ri.z & leMask) - 1u;
+                const uint4 sa = zl_lds128(segA + ((c0 & 255u) << 4)), sb = zl_lds128(segA + ((c1 & 255u) << 4));
+                const bool aa = ja < totalO, ab = jb < totalO;
+                bool na = aa && sa.w <= d0, nb = ab && sb.w <= d0 + 32u;       // source inside this step (offset <= distance from its start): not in memory yet
+                const u8* pa = zl_ptr_add(sa.x, sa.y, ja);
+                const u8* pb = zl_ptr_add(sb.x, sb.y, jb);
+                if (kDict) {
+                    if (sa.w != ZL_SEG_LIT) pa = outPtr((i32)(outPos + ja - sa.w));
+                    if (sb.w != ZL_SEG_LIT) pb = outPtr((i32)(outPos + jb - sb.w));
+                }
+                u32 va = rleByte, vb = rleByte;
+                if (aa && !na && !(sa.w == ZL_SEG_LIT && rleLits)) va = *pa;
+                if (ab && !nb && !(sb.w == ZL_SEG_LIT && rleLits)) vb = *pb;
+                if (__any_sync(ZL_FULL, na || nb)) {
+                    const u32 j0 = a0 < mis ? 0u : a0 - mis;                   // first flat index of the step
+                    u32 ta = ja - sa.w, tb = jb - sb.w;                        // flat source index (>= j0 where na / nb)
+                    // overlapping matches: fold the source below the match's own start (it may then lie below the step)
+                    if (na && ta >= sa.z) { ta = sa.z - sa.w + zl_mod_small(ja - sa.z, sa.w, rcpA); if ((i32)ta < (i32)j0) { na = false; va = *outPtr((i32)(outPos + ta)); } }
+                    if (nb && tb >= sb.z) { tb = sb.z - sb.w + zl_mod_small(jb - sb.z, sb.w, rcpA); if ((i32)tb < (i32)j0) { nb = false; vb = *outPtr((i32)(outPos + tb)); } }
+                    const u32 ra_ = ta + mis - a0, rb_ = tb + mis - a0;          // position of the source inside the step (0..63)
+                    while (__any_sync(ZL_FULL, na || nb)) {
+                        const u32 w = (va & 0xFFu) | (na ? 0u : 0x100u) | ((vb & 0xFFu) << 16) | (nb ? 0u : 0x1000000u);
+                        const u32 wa = __shfl_sync(ZL_FULL, w, ra_ & 31u) >> ((ra_ & 32u) >> 1), wb = __shfl_sync(ZL_FULL, w, rb_ & 31u) >> ((rb_ & 32u) >> 1);
+                        if (na && (wa & 0x100u)) { va = wa & 0xFFu; na = false; }
+                        if (nb && (wb & 0x100u)) { vb = wb & 0xFFu; nb = false; }
+                    }
+                }
+                if (aa) ob8[ja] = (u8)va;
+                if (ab) ob8[jb] = (u8)vb;
+                __syncwarp();
+            }
         }
         outPos += totalO; litPos += totalL;
     }

@@ -149,9 +149,11 @@ zl_k_execute(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ in
              const u8* __restrict__ litArena, u64* __restrict__ results, u32 nframes, const ZlDictDev* dict)
 {
     __shared__ u32 xtab[ZL_XTAB_WORDS];
-    __shared__ uint2 segTab[ZL_EXEC_WARPS][32];
+    __shared__ __align__(16) ZlExecSm execSm[ZL_EXEC_WARPS];
+    __shared__ u32 rcp[64];                                           // zl_mod_small
     for (u32 i = threadIdx.x; i < ZL_XTAB_WORDS; i += ZL_EXEC_WARPS * 32)
         xtab[i] = i < 36 ? (c_tables.llBase[i] | ((u32)c_tables.llBits[i] << 24)) : (c_tables.mlBase[i - 36] | ((u32)c_tables.mlBits[i - 36] << 24));
+    if (threadIdx.x < 64) rcp[threadIdx.x] = threadIdx.x ? 0xFFFFFFFFu / threadIdx.x : 0u;
     __syncthreads();
     const u32 lane = threadIdx.x & 31;
     const u32 frame = blockIdx.x * ZL_EXEC_WARPS + (threadIdx.x >> 5);
@@ -181,7 +183,7 @@ zl_k_execute(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ in
             u32 cap = room, capErr = ZL_E_dstSize_tooSmall, regen = 0;
             if (cap > ZL_BLOCKSIZE_MAX) { cap = ZL_BLOCKSIZE_MAX; capErr = ZL_E_corruption_detected; }
             err = zl_exec_block<kDict>(d.dst, op, cap, capErr, h, lit, (h.flags >> 8) & 0xFF, litMode, recArena + d.recBase + h.recOff,
-                                       dictContent, dictSize, hist, xtab, segTab[threadIdx.x >> 5], lane, regen);
+                                       dictContent, dictSize, hist, xtab, rcp, &execSm[threadIdx.x >> 5], lane, regen);
             op += regen;
         }
         __syncwarp();

@@ -6,7 +6,7 @@
 #define ZL_QUADS_PER_WARP 8
 #define ZL_EXEC_WARPS 4
 #ifndef ZL_EXEC_MIN_CTAS
-#define ZL_EXEC_MIN_CTAS 9
+#define ZL_EXEC_MIN_CTAS 7          // 72 registers: 9 CTAs (56 registers, spills) measured 1.76 ms per 8,192 frames, 8: 1.73, 7: 1.55
 #endif
 #define ZL_DEC_STAGES 4      // (index +) literals, sequences, execute, checksum
 #define ZL_NORM_SLOTS 16384  // resident quads of one sequence-kernel launch the normalized-count scratch has room for
