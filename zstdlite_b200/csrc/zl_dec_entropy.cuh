@@ -261,6 +261,7 @@ ZL_HD void zl_index_frame(const ZlFrameDesc& d, ZlFrameInfo& info, ZlBlockHdr* h
     } while (0);
     // ---- block walk
     u32 litUsed = 0, recUsed = 0;
+    u32 outKnown = 0; bool outValid = d.large == 0;          // output position of the next block while it only depends on headers
     u64 seqTotal = 0;
     u32 hufDef = ZL_DEF_NONE, seqDef[3] = {ZL_DEF_NONE, ZL_DEF_NONE, ZL_DEF_NONE};
     bool hufValid = dictHasEntropy != 0, seqValid = dictHasEntropy != 0, lastSeen = false;
@@ -274,14 +275,14 @@ ZL_HD void zl_index_frame(const ZlFrameDesc& d, ZlFrameInfo& info, ZlBlockHdr* h
         ZlBlockHdr h;
         h.flags = last ? 4u : 0u; h.regenSize = 0; h.srcOff = 0; h.litOff = 0; h.litSize = 0; h.nrec = 0; h.recOff = 0;
         h.seqOff = 0; h.seqEnd = 0; h.litSecOff = 0; h.hufDef = ZL_DEF_NONE; h.seqDef[0] = h.seqDef[1] = h.seqDef[2] = ZL_DEF_NONE;
-        h.nbSeq = 0; h.pad = 0;
+        h.nbSeq = 0; h.outOff = 0;
         if (type == 3) err = ZL_E_corruption_detected;
         else if (type == 1) {                                                    // RLE block, zstd.c:41510
             if (pos + 1 > srcSize) err = ZL_E_srcSize_wrong;
-            else { h.flags |= 1u | ((u32)src[pos] << 8); h.regenSize = csize; pos += 1; }
+            else { h.flags |= 1u | ((u32)src[pos] << 8); h.regenSize = csize; pos += 1; if ((u64)outKnown + csize <= d.dstCap) outKnown += csize; else outValid = false; }
         } else if (type == 0) {                                                  // raw block, zstd.c:41497
             if (csize > srcSize - pos) err = ZL_E_srcSize_wrong;
-            else { h.regenSize = csize; h.srcOff = pos; pos += csize; }
+            else { h.regenSize = csize; h.srcOff = pos; pos += csize; if ((u64)outKnown + csize <= d.dstCap) outKnown += csize; else outValid = false; }
         } else {
             if (csize > srcSize - pos) err = ZL_E_srcSize_wrong;
             else if (csize > blockSizeMax) err = ZL_E_srcSize_wrong;             // zstd.c:45099
@@ -338,6 +339,7 @@ ZL_HD void zl_index_frame(const ZlFrameDesc& d, ZlFrameInfo& info, ZlBlockHdr* h
                             else { if (q >= blockEnd) err = ZL_E_srcSize_wrong; else nbSeq = ((nbSeq - 0x80) << 8) + src[q++]; }
                         }
                     }
+                    if (!err && !nbSeq && q != blockEnd) err = ZL_E_corruption_detected;      // zstd.c:43736: nothing may follow nbSeq == 0
                     if (!err && nbSeq) {
                         if (q + 1 > blockEnd) err = ZL_E_srcSize_wrong;
                         else {
@@ -360,6 +362,11 @@ ZL_HD void zl_index_frame(const ZlFrameDesc& d, ZlFrameInfo& info, ZlBlockHdr* h
                 }
                 h.flags |= 2u | (litMode << 4);
                 h.litSize = litSize; h.seqOff = seqOff; h.seqEnd = blockEnd;
+                if (!err) {
+                    if (h.nbSeq) outValid = false;
+                    else if (outValid && litMode == 2 && (u64)outKnown + litSize <= d.dstCap) { h.flags |= ZL_BLK_DIRECT; h.outOff = outKnown; outKnown += litSize; }
+                    else outValid = false;
+                }
                 pos = blockEnd;
             }
         }
@@ -767,7 +774,7 @@ ZL_HD void zl_seq_head(ZlSeqSm& f, const ZlFrameDesc& d, const ZlBlockHdr* hdrs,
     const ZlBlockHdr& h = hdrs[blk];
     c.err = 0; c.needBuild = 0; c.useDict = 0; c.nbSeq = h.nbSeq;
     c.bErr[0] = c.bErr[1] = c.bErr[2] = 0;
-    if (!h.nbSeq) { if (h.seqOff + 1 != h.seqEnd) c.err = ZL_E_corruption_detected; return; }     // zstd.c:43736: nothing may follow nbSeq == 0
+    if (!h.nbSeq) return;                          // (the index kernel checked that nothing follows nbSeq == 0, zstd.c:43736)
     const u8* src = d.src;
     u32 ip = h.seqOff + (h.nbSeq < 128 ? 1u : (h.nbSeq < 0x7F00 ? 2u : 3u));
     const u32 iend = h.seqEnd;

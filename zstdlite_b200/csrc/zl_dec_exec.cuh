@@ -30,7 +30,12 @@ ZL_D void zl_warp_copy(u8* dst, const u8* src, u32 n, u32 lane)
         u32 body = (n - head) >> 4;
         const uint4* s4 = (const uint4*)(src + head);
         uint4* d4 = (uint4*)(dst + head);
-        for (u32 i = lane; i < body; i += 32) d4[i] = s4[i];
+        u32 i = lane;
+        for (; i + 96 < body; i += 128) {                 // four independent loads in flight per lane
+            const uint4 a = s4[i], b = s4[i + 32], c = s4[i + 64], e = s4[i + 96];
+            d4[i] = a; d4[i + 32] = b; d4[i + 64] = c; d4[i + 96] = e;
+        }
+        for (; i < body; i += 32) d4[i] = s4[i];
         u32 done = head + (body << 4);
         for (u32 i = done + lane; i < n; i += 32) dst[i] = src[i];
         return;
@@ -43,7 +48,14 @@ ZL_D void zl_warp_copy(u8* dst, const u8* src, u32 n, u32 lane)
     const u32 sh = (u32)(((size_t)s) & 3) * 8;
     const u32* s4 = (const u32*)(((size_t)s) & ~(size_t)3);
     if (sh == 0) for (u32 i = lane; i < words; i += 32) d4[i] = s4[i];
-    else for (u32 i = lane; i < words; i += 32) d4[i] = __funnelshift_r(s4[i], s4[i + 1], sh);
+    else {
+        u32 i = lane;
+        for (; i + 96 < words; i += 128) {
+            const u32 a0 = s4[i], a1 = s4[i + 1], b0 = s4[i + 32], b1 = s4[i + 33], c0 = s4[i + 64], c1 = s4[i + 65], e0 = s4[i + 96], e1 = s4[i + 97];
+            d4[i] = __funnelshift_r(a0, a1, sh); d4[i + 32] = __funnelshift_r(b0, b1, sh); d4[i + 64] = __funnelshift_r(c0, c1, sh); d4[i + 96] = __funnelshift_r(e0, e1, sh);
+        }
+        for (; i < words; i += 32) d4[i] = __funnelshift_r(s4[i], s4[i + 1], sh);
+    }
     const u32 done = head + (words << 2);
     if (done + lane < n) dst[done + lane] = src[done + lane];
 }
@@ -193,9 +205,11 @@ ZL_D u32 zl_flat_owner(u32 rs, u32 j)
 // Round 1 handled 32 records at a time, copied their literals in one pass and resolved the matches in rounds against a
 // high-water mark (2.4 - 4.4 rounds per batch, each with its own scan and segment table): ~900 warp instructions per 32 sequences.
 #define ZL_SEG_LIT 0x80000000u
-#define ZL_XB 4                          // records per lane
+#ifndef ZL_XB
+#define ZL_XB 4                          // records per lane (2 or 4)
+#endif
 #define ZL_XBATCH (32 * ZL_XB)           // records per batch
-#define ZL_XROWS 128                     // rows per window of the row table (4 KiB of output)
+#define ZL_XROWS (32 * ZL_XB)            // rows per window of the row table (4 KiB of output at 4 records per lane)
 struct ZlExecSm {                        // per warp: 5 KB
     uint4 seg[2 * ZL_XBATCH];            // x, y = P: address of the segment's source byte for flat index 0 (source of byte j = P + j);
                                          // z = flat start; w = match offset, or ZL_SEG_LIT for a literal run
@@ -224,7 +238,7 @@ ZL_D void zl_batch_offsets4(const u32 (&ll)[ZL_XB], const u32 (&ml)[ZL_XB], cons
     for (int m = 0; m < ZL_XB; m++) {
         idx[m] = zl_rep_idx(ll[m], ml[m], ob[m]);
         minus1 |= idx[m] == 3;
-        t[m] = zl_rept_of(ml[m] != 0 && ob[m] >= 4, idx[m], 4u * lane + (u32)m);
+        t[m] = zl_rept_of(ml[m] != 0 && ob[m] >= 4, idx[m], ZL_XB * lane + (u32)m);
     }
     if (__any_sync(ZL_FULL, minus1)) {
         // rare "rep0 - 1" code somewhere in the batch: resolve the records one after the other (uniform loop)
@@ -240,23 +254,33 @@ ZL_D void zl_batch_offsets4(const u32 (&ll)[ZL_XB], const u32 (&ml)[ZL_XB], cons
         h0 = hh[0]; h1 = hh[1]; h2 = hh[2];
         return;
     }
+#if ZL_XB == 4
     *reinterpret_cast<uint4*>(fresh + 4u * lane) = make_uint4(ob[0] - 3u, ob[1] - 3u, ob[2] - 3u, ob[3] - 3u);
     const u32 t01 = zl_rept_compose(t[0], t[1]), t012 = zl_rept_compose(t01, t[2]);
     const u32 T = zl_rept_scan(zl_rept_compose(t012, t[3]), lane);
+#else
+    *reinterpret_cast<uint2*>(fresh + 2u * lane) = make_uint2(ob[0] - 3u, ob[1] - 3u);
+    const u32 t01 = zl_rept_compose(t[0], t[1]);
+    const u32 T = zl_rept_scan(t01, lane);
+#endif
     u32 E = __shfl_up_sync(ZL_FULL, T, 1);                                  // exclusive prefix: history before this lane's records
     if (lane == 0) E = ZL_REPT_ID;
     __syncwarp();
+#if ZL_XB == 4
     const u32 e[ZL_XB] = {E, zl_rept_compose(E, t[0]), zl_rept_compose(E, t01), zl_rept_compose(E, t012)};
+#else
+    const u32 e[ZL_XB] = {E, zl_rept_compose(E, t[0])};
+#endif
 #pragma unroll
     for (int m = 0; m < ZL_XB; m++) {
         const u32 eb = (e[m] >> (8u * idx[m])) & 0xFFu;                     // the slot of the incoming history this record reads
-        const u32 fromTag = fresh[eb & 127u];
+        const u32 fromTag = fresh[eb & (ZL_XBATCH - 1)];
         const u32 fromHist = (eb & 3u) == 0 ? h0 : ((eb & 3u) == 1 ? h1 : h2);
         off[m] = (ml[m] != 0 && ob[m] >= 4) ? ob[m] - 3u : ((eb & 0x80u) ? fromTag : fromHist);
     }
     const u32 Lt = __shfl_sync(ZL_FULL, T, 31);                            // history after the batch
     const u32 b0 = Lt & 0xFFu, b1 = (Lt >> 8) & 0xFFu, b2 = (Lt >> 16) & 0xFFu;
-    const u32 f0 = fresh[b0 & 127u], f1 = fresh[b1 & 127u], f2 = fresh[b2 & 127u];
+    const u32 f0 = fresh[b0 & (ZL_XBATCH - 1)], f1 = fresh[b1 & (ZL_XBATCH - 1)], f2 = fresh[b2 & (ZL_XBATCH - 1)];
     const u32 n0 = (b0 & 0x80u) ? f0 : ((b0 & 3u) == 0 ? h0 : ((b0 & 3u) == 1 ? h1 : h2));
     const u32 n1 = (b1 & 0x80u) ? f1 : ((b1 & 3u) == 0 ? h0 : ((b1 & 3u) == 1 ? h1 : h2));
     const u32 n2 = (b2 & 0x80u) ? f2 : ((b2 & 3u) == 0 ? h0 : ((b2 & 3u) == 1 ? h1 : h2));
@@ -281,18 +305,19 @@ ZL_D u32 zl_exec_block(u8* out, u32 op, u32 cap, u32 capErr, const ZlBlockHdr& h
         const u32 i0 = base + ZL_XB * lane;
         ulonglong2 ra = make_ulonglong2(0ull, 0ull), rb = ra;
         if (i0 < nrec) ra = __ldcs(reinterpret_cast<const ulonglong2*>(recs + i0));
-        if (i0 + 2 < nrec) rb = __ldcs(reinterpret_cast<const ulonglong2*>(recs + i0 + 2));
+        if (ZL_XB == 4 && i0 + 2 < nrec) rb = __ldcs(reinterpret_cast<const ulonglong2*>(recs + i0 + 2));
         if (i0 + ZL_XBATCH < nrec) asm volatile("prefetch.global.L1 [%0];" ::"l"(recs + i0 + ZL_XBATCH));
         u32 ll[ZL_XB], ml[ZL_XB], ob[ZL_XB], off[ZL_XB];
         zl_lane_record(ra.x, i0 < nrec, xtab, ll[0], ml[0], ob[0]);
         zl_lane_record(ra.y, i0 + 1 < nrec, xtab, ll[1], ml[1], ob[1]);
+#if ZL_XB == 4
         zl_lane_record(rb.x, i0 + 2 < nrec, xtab, ll[2], ml[2], ob[2]);
         zl_lane_record(rb.y, i0 + 3 < nrec, xtab, ll[3], ml[3], ob[3]);
+#endif
         // ---- places: one scan over (literal bytes | non-empty segments << 23, output bytes) of the lanes
-        const u32 L = ll[0] + ll[1] + ll[2] + ll[3], O = L + ml[0] + ml[1] + ml[2] + ml[3];      // L < 2^23: lengths are < 65536
-        u32 nseg = 0;
+        u32 L = 0, O = 0, nseg = 0;                           // L < 2^23: lengths are < 65536
 #pragma unroll
-        for (int m = 0; m < ZL_XB; m++) nseg += (ll[m] ? 1u : 0u) + (ml[m] ? 1u : 0u);
+        for (int m = 0; m < ZL_XB; m++) { L += ll[m]; O += ll[m] + ml[m]; nseg += (ll[m] ? 1u : 0u) + (ml[m] ? 1u : 0u); }
         u32 sl = L | (nseg << 23), so = O;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -328,25 +353,39 @@ ZL_D u32 zl_exec_block(u8* out, u32 op, u32 cap, u32 capErr, const ZlBlockHdr& h
         for (u32 w0 = 0; w0 < totalA; w0 += ZL_XROWS * 32) {
             // ---- row table of the window [w0, w0 + 4 KiB): start masks by atomics, then the exclusive count over the rows
             __syncwarp();
+#if ZL_XB == 4
             reinterpret_cast<uint4*>(sm->u.row)[2 * lane] = make_uint4(0u, 0u, 0u, 0u);
             reinterpret_cast<uint4*>(sm->u.row)[2 * lane + 1] = make_uint4(0u, 0u, 0u, 0u);
+#else
+            reinterpret_cast<uint4*>(sm->u.row)[lane] = make_uint4(0u, 0u, 0u, 0u);
+#endif
             __syncwarp();
 #pragma unroll
             for (u32 k = 0; k < 2 * ZL_XB; k++) {
-                const u32 a = zl_lds32s(segA + (((ord0 + k) & 255u) << 4) + 8u) + mis - w0;
+                const u32 a = zl_lds32s(segA + (((ord0 + k) & (2 * ZL_XBATCH - 1)) << 4) + 8u) + mis - w0;
                 if (k < nseg && a < ZL_XROWS * 32) atomicOr(&sm->u.row[a >> 5].x, 1u << (a & 31u));
             }
             __syncwarp();
             {
+#if ZL_XB == 4
                 uint4 qa = zl_lds128(rowA + lane * 32u), qb = zl_lds128(rowA + lane * 32u + 16u);      // rows 4 lane .. 4 lane + 3
                 const u32 c0 = __popc(qa.x), c1 = __popc(qa.z), c2 = __popc(qb.x), c3 = __popc(qb.z);
+#else
+                uint4 qa = zl_lds128(rowA + lane * 16u);                                                  // rows 2 lane, 2 lane + 1
+                const u32 c0 = __popc(qa.x), c1 = __popc(qa.z), c2 = 0, c3 = 0;
+#endif
                 u32 inc = c0 + c1 + c2 + c3;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { const u32 a = __shfl_up_sync(ZL_FULL, inc, d); if ((int)lane >= d) inc += a; }
                 const u32 ex = segsBefore + inc - (c0 + c1 + c2 + c3);
-                qa.y = ex; qa.w = ex + c0; qb.y = ex + c0 + c1; qb.w = ex + c0 + c1 + c2;
+                qa.y = ex; qa.w = ex + c0;
+#if ZL_XB == 4
+                qb.y = ex + c0 + c1; qb.w = ex + c0 + c1 + c2;
                 reinterpret_cast<uint4*>(sm->u.row)[2 * lane] = qa;
                 reinterpret_cast<uint4*>(sm->u.row)[2 * lane + 1] = qb;
+#else
+                reinterpret_cast<uint4*>(sm->u.row)[lane] = qa;
+#endif
                 segsBefore += __shfl_sync(ZL_FULL, inc, 31);
             }
             __syncwarp();
@@ -357,7 +396,7 @@ ZL_D u32 zl_exec_block(u8* out, u32 op, u32 cap, u32 capErr, const ZlBlockHdr& h
                 const u32 d0 = a0 < mis ? lane - (mis - a0) : lane;            // distance of byte a from the first flat index of the step
                 if ((ri.x | ri.z) == 0u && a0 + 64 <= totalA) {
                     // ---- the whole step lies inside one segment, which began before it: no owner lookup, no in-step sources
-                    const uint4 s = zl_lds128(segA + (((ri.y - 1u) & 255u) << 4));
+                    const uint4 s = zl_lds128(segA + (((ri.y - 1u) & (2 * ZL_XBATCH - 1)) << 4));
                     u32 va = rleByte, vb = rleByte;
                     if (s.w < 64u) {                                           // sources inside the match itself: fold below its start
                         u32 ta = ja - s.w, tb = jb - s.w;
@@ -375,7 +414,7 @@ ZL_D u32 zl_exec_block(u8* out, u32 op, u32 cap, u32 capErr, const ZlBlockHdr& h
                     continue;
                 }
                 const u32 c0 = ri.y + __popc(ri.x & leMask) - 1u, c1 = ri.w + __popc(ri.z & leMask) - 1u;
-                const uint4 sa = zl_lds128(segA + ((c0 & 255u) << 4)), sb = zl_lds128(segA + ((c1 & 255u) << 4));
+                const uint4 sa = zl_lds128(segA + ((c0 & (2 * ZL_XBATCH - 1)) << 4)), sb = zl_lds128(segA + ((c1 & (2 * ZL_XBATCH - 1)) << 4));
                 const bool aa = ja < totalO, ab = jb < totalO;
                 bool na = aa && sa.w <= d0, nb = ab && sb.w <= d0 + 32u;       // source inside this step (offset <= distance from its start): not in memory yet
                 const u8* pa = zl_ptr_add(sa.x, sa.y, ja);

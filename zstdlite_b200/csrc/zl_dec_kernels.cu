@@ -60,7 +60,8 @@ zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ i
             const ZlBlockHdr* hdrs = hdrArena + d.hdrBase;
             const u32 litMode = (hdrs[un.block].flags >> 4) & 3;
             if (litMode == 2) {                                        // (units with raw / rle literals only have sequences)
-                u8* lits = litArena + d.litBase;
+                // ZL_BLK_DIRECT: the block's literals ARE its output
+                u8* lits = (hdrs[un.block].flags & ZL_BLK_DIRECT) ? d.dst + hdrs[un.block].outOff - hdrs[un.block].litOff : litArena + d.litBase;
                 const u32 bias = (u32)(((size_t)d.src) & 3);
                 const u32* wbase = reinterpret_cast<const u32*>(d.src - bias);
                 u32 useDict = 0;
@@ -177,6 +178,8 @@ zl_k_execute(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ in
             if (type == 0) zl_warp_copy(d.dst + op, d.src + h.srcOff, h.regenSize, lane);
             else zl_warp_fill(d.dst + op, (h.flags >> 8) & 0xFF, h.regenSize, lane);
             op += h.regenSize;
+        } else if (h.flags & ZL_BLK_DIRECT) {                           // already in place (literal kernel); the index kernel checked the room
+            op += h.litSize;
         } else {
             const u32 litMode = (h.flags >> 4) & 3;
             const u8* lit = litMode == 0 ? d.src + h.srcOff : litArena + d.litBase + h.litOff;
