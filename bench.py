@@ -119,28 +119,47 @@ def cpu_leg(frames_sample, frame_bytes, budget_s, threads):
     return len(frames_sample) * frame_bytes / best / 1e9, best, passes
 
 
+def cpu_compress_variants(buf, frame_bytes, level, threads, budget_s=4.0):
+    """BASELINE.md section 3 on `buf` (uint8 array, a whole number of frames): the reference's libzstd (i) one thread over the frames,
+    (ii) ZSTD_c_nbWorkers = threads on the buffer as ONE frame (the reference's num_threads semantics, src/cctx.c:269-277), (iii) frame-parallel
+    on `threads` cores.  -> dict of GB/s (uncompressed bytes) and compressed sizes."""
+    from oracle import cpubench
+    n = buf.size // frame_bytes
+    bound = frame_bytes + (frame_bytes >> 8) + 64
+    fs = cpubench.FrameSet(buf, [frame_bytes] * n)
+    t_fp, res, _, _ = cpubench.run("compress", fs, [bound] * n, threads, level=level)
+    passes = max(1, min(5, int(budget_s / 3 / max(t_fp, 1e-3))))
+    t_fp = min(t_fp, cpubench.run("compress", fs, [bound] * n, threads, level=level, passes=passes)[0])
+    n1 = max(1, min(n, int(n * (budget_s / 3) / max(t_fp * threads, 1e-3))))          # one thread: a share it finishes in ~budget/3
+    fs1 = cpubench.FrameSet(buf[:n1 * frame_bytes], [frame_bytes] * n1)
+    t_1, *_ = cpubench.run("compress", fs1, [bound] * n1, 1, level=level)
+    t_w, size_w = cpubench.run_workers(buf, level=level, workers=threads, passes=2)
+    return {"cores": threads, "level": level, "frame_parallel_GBps": buf.size / t_fp / 1e9, "one_thread_GBps": n1 * frame_bytes / t_1 / 1e9,
+            "nbWorkers_one_frame_GBps": buf.size / t_w / 1e9, "frames": n, "one_thread_frames": n1,
+            "frame_parallel_bytes": int(res.sum()), "nbWorkers_one_frame_bytes": size_w, "kind": "reference",
+            "sample": f"{n} x {frame_bytes // 1024} KiB slabs of the GPU's buffer ({buf.size / 2**20:.0f} MiB) copied to the host; one_thread over the first {n1}"}
+
+
 def run_reference(args, rank, world):
+    """The reference's own libzstd on the host cores, frame-parallel with every host thread, over ALL frames of the workload."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    nsample = min(args.frames, args.cpu_frames)
     data, frames = make_corpus(args.frames, args.frame_bytes)
-    step = max(1, args.frames // nsample)
-    sample = frames[::step][:nsample]                                  # keeps the family mix
     from oracle import cpubench
-    blob = np.frombuffer(b"".join(sample), dtype=np.uint8)
-    fs = cpubench.FrameSet(blob, [len(f) for f in sample])
-    caps = [args.frame_bytes] * len(sample)
+    blob = np.frombuffer(b"".join(frames), dtype=np.uint8)
+    fs = cpubench.FrameSet(blob, [len(f) for f in frames])
+    caps = [args.frame_bytes] * len(frames)
     for _ in range(args.warmup):
         cpubench.run("decompress", fs, caps, threads)
     times = [cpubench.run("decompress", fs, caps, threads)[0] for _ in range(args.steps)]
     total = sum(times)
-    val = len(sample) * args.frame_bytes * args.steps / total / 1e9
-    desc = f"{len(sample)} of the {args.frames} frames (every {step}th, same family mix), {threads} threads, one DCtx per thread"
+    val = len(frames) * args.frame_bytes * args.steps / total / 1e9
+    desc = f"all {args.frames} frames of one GPU's shard, {threads} threads, one DCtx per thread (oracle/_ref libzstd 1.5.6, oracle/cpu_bench.c)"
     out = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u8", "data": "synthetic", "impl": "reference",
-           "config": workload_config(args, 1),
+           "config": workload_config(args, world),
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": desc},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -152,6 +171,77 @@ def workload_config(args, world):
             "frames_per_gpu": args.frames, "frame_bytes": args.frame_bytes, "level": 3, "checksum": False,
             "sharding": f"{world} x independent frame shards, no collective",
             "cache": "working set (compressed in + 1 GiB out per step) exceeds the 126 MB L2; no explicit flush"}
+
+
+def measured_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback (of fallback)"
+
+
+def compress_traffic(level):
+    """DRAM bytes of the compress kernels from the committed ncu capture (profiles/compress_kernel_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "compress_kernel_traffic.json")
+    try:
+        return json.load(open(path)).get(f"level{level}")
+    except (OSError, ValueError):
+        return None
+
+
+def pin_to_gpu_numa_node(local):
+    """Bind this process (and the pinned host buffers it allocates afterwards) to the CPUs NVML reports as local to its GPU: with one
+    process per GPU on a two-socket box, host staging otherwise lands on whichever node the launcher started on."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        idx = local
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                idx = int(vis.split(",")[local])
+            except (ValueError, IndexError):
+                pass
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1 and 64 * w + b < ncpu}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+        return {"cpus": len(cpus) if cpus else len(allowed), "of": len(allowed), "bound": bool(cpus and cpus != allowed)}
+    except Exception as e:                                            # no NVML / not permitted: run unbound, say so
+        return {"error": repr(e)}
+
+
+def pcie_probe(torch, dist, dev, world, h2d_bytes, d2h_bytes, reps=3):
+    """Raw ceiling of the end-to-end arm: the step's H2D and D2H volumes as two plain concurrent cudaMemcpyAsync between pinned host
+    memory and HBM, on every rank at once -> (ms of the slower direction, max over ranks)."""
+    hs = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    hd = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    ds = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    dd = torch.zeros(d2h_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = None
+    for _ in range(reps + 1):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+        a0, a1, b0, b1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        with torch.cuda.stream(s1):
+            a0.record(); ds.copy_(hs, non_blocking=True); a1.record()
+        with torch.cuda.stream(s2):
+            b0.record(); hd.copy_(dd, non_blocking=True); b1.record()
+        torch.cuda.synchronize()
+        t = max(a0.elapsed_time(a1), b0.elapsed_time(b1))
+        best = t if best is None else min(best, t)
+    if world > 1:
+        tt = torch.tensor([best], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        best = float(tt[0])
+    del hs, hd, ds, dd
+    return best
 
 
 def compress_leg(torch, dist, z, args, dev, rank, world):
@@ -182,34 +272,46 @@ def compress_leg(torch, dist, z, args, dev, rank, world):
             res = plan.compress(cctx)
         t1.record(); torch.cuda.synchronize()
         ms = t0.elapsed_time(t1) / iters
+        # per-kernel times of the LAST device-resident call (read now: the end-to-end call below runs the pipelined chunks)
+        L = z._lib.lib()
+        kernel_ms = cctx.last_kernel_ms
+        stages = {nm: L.zl_cctx_last_stage_ms(cctx._p, k) for k, nm in enumerate(("match", "parse", "literals", "sequences", "plan+assemble"))}
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t[0])
-        if rank != 0:
-            continue
         sizes = np.array(list(res), dtype=np.int64)
         assert not any(z.is_error(int(s)) for s in sizes), "compress errors"
         csize = int(sizes.sum())
-        # end to end (world == 1): the same 4 GiB as ONE pinned host buffer through zl_compress_split (what zstd_compress(frame_size=)
-        # calls): host-to-device staging, kernels and the copy back of the multi-frame stream inside the timed region
+        # end to end: the buffer as ONE pinned host buffer through zl_compress_split (what zstd_compress(frame_size=) calls): host-to-device
+        # staging, kernels and the copy back of the multi-frame stream inside the timed region; every rank at once (N > 1: 1 GiB per rank)
         e2e = None
-        if world == 1 and lvl == 3 and not args.no_compress_e2e:
+        if lvl == 3 and not args.no_compress_e2e:
             import ctypes as C
-            L = z._lib.lib()
-            hsrc = torch.empty(n * fb, dtype=torch.uint8).pin_memory(); hsrc.copy_(src.reshape(-1))
-            hcap = n * (bound + 8)
+            ne = n if world == 1 else min(n, 8192)
+            hsrc = torch.empty(ne * fb, dtype=torch.uint8).pin_memory(); hsrc.copy_(src.reshape(-1)[:ne * fb])
+            hcap = ne * (bound + 8)
             hdst = torch.empty(hcap, dtype=torch.uint8).pin_memory()
             tt = []
             for _ in range(3):
-                t0 = time.time()
-                r = L.zl_compress_split(cctx._p, C.c_void_p(hdst.data_ptr()), hcap, C.c_void_p(hsrc.data_ptr()), n * fb, fb, None, 0)
-                tt.append(time.time() - t0)
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                t0w = time.time()
+                r = L.zl_compress_split(cctx._p, C.c_void_p(hdst.data_ptr()), hcap, C.c_void_p(hsrc.data_ptr()), ne * fb, fb, None, 0)
+                tt.append(time.time() - t0w)
                 assert not z.is_error(r), z.error_name(r)
-            assert int(r) == csize
-            e2e = {"GBps": n * fb / min(tt[1:]) / 1e9, "ms": 1e3 * min(tt[1:]), "h2d_bytes": n * fb, "d2h_bytes": int(r),
-                   "how": "zl_compress_split on one pinned host buffer, wall clock of the call, best of 2 after a warm-up call"}
+            assert int(r) == int(sizes[:ne].sum())
+            te = min(tt[1:])
+            if world > 1:
+                t = torch.tensor([te], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                te = float(t[0])
+            e2e = {"GBps": world * ne * fb / te / 1e9, "ms": 1e3 * te, "h2d_bytes": ne * fb, "d2h_bytes": int(r), "frames_per_gpu": ne,
+                   "how": "zl_compress_split on one pinned host buffer per rank, wall clock of the call (max over ranks), best of 2 after a warm-up call"}
             del hsrc, hdst
+        if rank != 0:
+            continue
         # a sample of frames: round trip through libzstd and libzstd's own size for the same slab at the same level
         from oracle import ref
         ours = theirs = 0
@@ -219,14 +321,25 @@ def compress_leg(torch, dist, z, args, dev, rank, world):
             frame = dst[i * slot:i * slot + int(sizes[i])].cpu().numpy().tobytes()
             assert ref.decompress(frame) == want, "GPU frame does not round-trip through libzstd"
             ours += len(frame); theirs += len(ref.compress(want, lvl))
-        L = z._lib.lib()
+        alg = n * fb + csize                                              # uncompressed read + compressed written
+        peak, peak_src = measured_peak()
+        dom = max((k for k in stages if stages[k] > 0), key=lambda k: stages[k], default=None)
         out[f"level{lvl}"] = {"GBps": world * n * fb / ms / 1e6, "ms": ms, "ratio": n * fb / csize, "size_vs_libzstd": ours / theirs,
                               "size_vs_libzstd_how": f"{len(range(0, n, max(1, n // 128)))} sampled frames, libzstd at the same level on the same slabs",
-                              "kernel_ms": cctx.last_kernel_ms,
-                              "stages_ms": {nm: L.zl_cctx_last_stage_ms(cctx._p, k) for k, nm in enumerate(("match", "parse", "literals", "sequences", "plan+assemble"))},
-                              "frames_per_gpu": n, "frame_bytes": fb, "n_gpus": world}
+                              "kernel_ms": kernel_ms, "stages_ms": stages,
+                              "stages_how": "CUDA events between the kernels of the last wave of the last device-resident call (a call of more than 8,192 blocks runs in waves)",
+                              "frames_per_gpu": n, "frame_bytes": fb, "n_gpus": world,
+                              "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / ms / 1e6 / peak,
+                                           "peak_source": peak_src, "algorithmic_bytes_per_call": int(alg), "call_ms": ms,
+                                           "dominant_kernel": ("zl_k_" + dom) if dom else None,
+                                           "dominant_share_of_wave": (stages[dom] / sum(v for v in stages.values() if v > 0)) if dom else None,
+                                           "traffic": compress_traffic(lvl)}}
         if e2e:
             out[f"level{lvl}"]["e2e"] = e2e
+        if world == 1 and not args.no_cpu:
+            nb = min(n, args.cpu_compress_frames)
+            host = src.reshape(-1)[:nb * fb].cpu().numpy()
+            out[f"level{lvl}"]["cpu_baseline"] = cpu_compress_variants(host, fb, lvl, os.cpu_count() or 1)
     return out
 
 
@@ -248,7 +361,9 @@ def config5_leg(torch, dist, z, args, dev, rank, world):
     stream = torch.cuda.current_stream()
     cctx.set_stream(stream.cuda_stream); dctx.set_stream(stream.cuda_stream)
     sub, chunk = 65536, 32768
-    ms_c = ms_d = 0.0
+    ms_c = 0.0
+    DEC_REPS = 5
+    dec_reps = [0.0] * DEC_REPS
     csize = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for s0 in range(0, n, sub):
@@ -275,29 +390,39 @@ def config5_leg(torch, dist, z, args, dev, rank, world):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier(); torch.cuda.synchronize()
-        e0.record(stream)
-        bad = 0
-        for p in dplans:
-            bad += sum(1 for r in p.decompress(dctx) if int(r) != fb)
-        e1.record(stream); torch.cuda.synchronize()
-        ms_d += e0.elapsed_time(e1)
-        assert bad == 0, "decode errors"
+        for rep in range(DEC_REPS):                                     # repeated: one slow call used to decide this leg's number
+            e0.record(stream)
+            bad = 0
+            for p in dplans:
+                bad += sum(1 for r in p.decompress(dctx) if int(r) != fb)
+            e1.record(stream); torch.cuda.synchronize()
+            dec_reps[rep] += e0.elapsed_time(e1)
+            assert bad == 0, "decode errors"
         assert torch.equal(back, src), "round trip differs"
         if rank == 0:
             for i in range(0, m, max(1, m // 8)):                       # sampled frames through the reference's libzstd
                 fam, row, shift = meta[i]
                 assert ref.decompress(comp[i * slot:i * slot + sizes[i]].cpu().numpy().tobytes()) == np.roll(pools[fam][row], shift).tobytes()
         del src, comp, back, cplan, dplans
-    t = torch.tensor([ms_c, ms_d, float(csize)], dtype=torch.float64, device=dev)
+    # the leg's decompress time: for every repeat the max over ranks, then the median of the repeats; per-rank min / median beside it
+    reps = torch.tensor(dec_reps, dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_c, float(csize)], dtype=torch.float64, device=dev)
+    per_rank = [reps.clone() for _ in range(world)]
     if world > 1:
         mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(t)
-        ms_c, ms_d, csize = float(mx[0]), float(mx[1]), float(t[2])
+        dist.all_gather(per_rank, reps)
+        dist.all_reduce(reps, op=dist.ReduceOp.MAX)
+        ms_c, csize = float(mx[0]), float(t[1])
     if rank != 0:
         return None
+    ms_d = float(reps.median())
     tot = n * world * fb
     return {"frames": n * world, "frame_bytes": fb, "bytes": tot, "n_gpus": world, "scaling": "strong", "level": 3, "checksum": True,
             "compress_GBps": tot / ms_c / 1e6, "compress_ms": ms_c, "decompress_GBps": tot / ms_d / 1e6, "decompress_ms": ms_d,
+            "decompress_how": f"median of {DEC_REPS} repeats of (max over ranks); compress: one pass, max over ranks",
+            "decompress_ms_repeats_max_over_ranks": [float(v) for v in reps],
+            "decompress_ms_per_rank_min_median": [[float(r.min()), float(r.median())] for r in per_rank],
             "ratio": tot / float(csize), "round_trip": "device compare of every byte + sampled frames through libzstd"}
 
 
@@ -378,6 +503,9 @@ def large_frame_leg(torch, z, args, dev):
     t0 = time.time(); frame = ref.compress(payload, 3); t_cc = time.time() - t0
     t0 = time.time(); back = ref.decompress(frame); t_cd = time.time() - t0
     assert back == payload
+    from oracle import cpubench
+    threads = os.cpu_count() or 1
+    t_w, size_w = cpubench.run_workers(np.frombuffer(payload, dtype=np.uint8), level=3, workers=threads, passes=3)
     src = torch.from_numpy(np.frombuffer(frame, dtype=np.uint8).copy()).to(dev)
     dst = torch.zeros(n + 64, dtype=torch.uint8, device=dev)
     dctx = z.zstd_dctx()
@@ -410,7 +538,10 @@ def large_frame_leg(torch, z, args, dev):
     ms_c = e0.elapsed_time(e1) / 5
     return {"rows": args.df_rows, "bytes": n, "frame_bytes_libzstd": len(frame), "frame_bytes_ours": csz, "size_vs_libzstd": csz / len(frame),
             "decompress_GBps": n / ms_d / 1e6, "decompress_ms": ms_d, "compress_GBps": n / ms_c / 1e6, "compress_ms": ms_c,
-            "libzstd_1thread_decompress_GBps": n / t_cd / 1e9, "libzstd_1thread_compress_GBps": n / t_cc / 1e9}
+            "libzstd_1thread_decompress_GBps": n / t_cd / 1e9, "libzstd_1thread_compress_GBps": n / t_cc / 1e9,
+            "libzstd_nbWorkers_compress_GBps": n / t_w / 1e9, "libzstd_nbWorkers": threads, "libzstd_nbWorkers_frame_bytes": size_w,
+            "cpu_baseline_how": "the reference's path for this config: one frame, level 3; num_threads = 1 (ZSTD_compress2 / ZSTD_decompressDCtx) and "
+                                "num_threads = cores (ZSTD_c_nbWorkers, src/cctx.c:269-277; compression only -- libzstd decompresses single-threaded)"}
 
 
 def main():
@@ -421,8 +552,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=16384)
     ap.add_argument("--frame-bytes", type=int, default=65536)
-    ap.add_argument("--cpu-frames", type=int, default=2048, help="frames in the bounded CPU sample")
+    ap.add_argument("--cpu-frames", type=int, default=16384, help="frames handed to the CPU baseline (default: all of them)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-compress-frames", type=int, default=4096, help="128 KiB slabs of the compress leg handed to the CPU baselines (512 MiB)")
+    ap.add_argument("--no-affinity", action="store_true", help="do not bind the process to the CPUs local to its GPU")
     ap.add_argument("--compress-frames", type=int, default=32768)
     ap.add_argument("--no-compress", action="store_true")
     ap.add_argument("--no-compress-e2e", action="store_true")
@@ -448,6 +581,7 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; zstdlite_b200 has no CPU path (use --impl reference for the CPU arm)")
+    affinity = {"bound": False, "off": True} if args.no_affinity else pin_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -527,11 +661,28 @@ def main():
     e3.record(stream)
     sync_all()
     ms_e2e = e2.elapsed_time(e3)
+    # the same call with PAGEABLE host buffers (what the reference's C layer hands over: R-allocated vectors, src/raw-file.c:166,189)
+    psrc = blob.copy()
+    pdst = np.zeros(n * fb, dtype=np.uint8)
+    pplan = z.BatchPlan([psrc.ctypes.data + int(o) for o in offs[:-1]], sizes, [pdst.ctypes.data + i * fb for i in range(n)], [fb] * n)
+    pplan.decompress(dctx, device=False)
+    assert (pdst.reshape(n, fb) == data).all()
+    sync_all()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record(stream)
+    for _ in range(3):
+        pplan.decompress(dctx, device=False)
+    e5.record(stream)
+    sync_all()
+    ms_page = e4.elapsed_time(e5) / 3
+    del psrc, pdst, pplan
+    # raw ceiling of that arm on this box: the step's two copies alone, every rank at once
+    ms_pcie = pcie_probe(torch, dist, dev, world, int(csize), int(n * fb))
 
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms_total, ms_e2e, ms_page], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e = float(t[0]), float(t[1])
+        ms_total, ms_e2e, ms_page = float(t[0]), float(t[1]), float(t[2])
     total_bytes = world * n * fb
     value = total_bytes * args.steps / ms_total / 1e6
     e2e_value = total_bytes * e2e_steps / ms_e2e / 1e6
@@ -560,11 +711,7 @@ def main():
         torch.cuda.empty_cache()
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
-        else:
-            peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+        peak, peak_src = measured_peak()
         k = int(np.argmax(stage_ms))
         alg_bytes = csize + n * fb                                     # compressed read + uncompressed written
         achieved = alg_bytes / stage_ms[k] / 1e6
@@ -572,7 +719,13 @@ def main():
                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(csize + n * 80), "d2h_bytes_per_step": int(n * fb + n * 8),
-                       "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+                       "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps, "host_buffers": "pinned",
+                       "pcie_ceiling_GBps": total_bytes / ms_pcie / 1e6, "frac_of_pcie_ceiling": (total_bytes * e2e_steps / ms_e2e) / (total_bytes / ms_pcie),
+                       "pcie_ceiling_how": "this step's H2D and D2H byte counts as two plain concurrent cudaMemcpyAsync (pinned <-> HBM) on every rank at once, "
+                                           "slower direction, max over ranks, best of 3",
+                       "pageable": {"value": total_bytes / ms_page / 1e6, "unit": UNIT, "ms_per_step": ms_page,
+                                    "how": "the same call with malloc'ed (pageable) host buffers, as the reference's C layer passes them"},
+                       "cpu_affinity": affinity},
                "gpu_launches": int(launches), "clocks": clocks,
                "roofline": {"bound": "hbm", "kernel": "zl_k_" + stage_names[k], "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -598,9 +751,12 @@ def main():
             step = max(1, n // nsample)
             sample = frames[::step][:nsample]
             v, t_pass, passes = cpu_leg(sample, fb, args.cpu_seconds, threads)
+            v1, _, _ = cpu_leg(sample[:max(1, len(sample) // threads)], fb, 2.0, 1)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
-                                   "sample": f"{len(sample)} of the {n} frames (every {step}th, same family mix), best of {passes} passes, "
-                                             f"oracle/_ref libzstd 1.5.6, one DCtx per thread"}
+                                   "sample": f"{len(sample)} of the {n} frames" + (f" (every {step}th, same family mix)" if step > 1 else "") +
+                                             f", frame-parallel, best of {passes} passes, oracle/_ref libzstd 1.5.6, one DCtx per thread",
+                                   "one_thread_GBps": v1,
+                                   "note": "libzstd has no multi-threaded decompression: num_threads = cores changes nothing on this side (BASELINE.md section 3)"}
         if comp is not None:
             out["compress"] = comp
         if c5 is not None:

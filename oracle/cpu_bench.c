@@ -9,7 +9,9 @@
  *   decompress  src/raw-file.c:180-189  (ZSTD_createDCtx once per thread, ZSTD_decompressDCtx per frame)
  *   compress    src/raw-file.c:65-74    (ZSTD_createCCtx + level/checksum parameters, ZSTD_compress2)
  * `threads` workers each own a context and pull frames from a shared atomic counter
- * ("frame-parallel x cores").
+ * ("frame-parallel x cores"; threads = 1 is item 1).
+ * zlb_run_workers is item 2, the reference's own num_threads semantics: ONE frame, ZSTD_c_nbWorkers = n
+ * (src/cctx.c:269-277; libzstd only engages its workers above 512 KB of input, zstd.c:28773).
  */
 #include <pthread.h>
 #include <stddef.h>
@@ -112,4 +114,25 @@ double zlb_run(int mode, const void* src, const size_t* srcOff, const size_t* sr
     free(th);
     pthread_barrier_destroy(&bar);
     return j.errors ? -1.0 : (t1 - t0);
+}
+
+/* One buffer -> ONE frame with ZSTD_c_nbWorkers = workers (0: single-threaded ZSTD_compress2), `passes` times; returns the
+ * best seconds and the frame size through *outSize, or -1 on error. */
+double zlb_run_workers(const void* src, size_t srcSize, void* dst, size_t dstCap, int level, int workers, int passes, size_t* outSize)
+{
+    ZSTD_CCtx* c = ZSTD_createCCtx();
+    if (!c) return -1.0;
+    ZSTD_CCtx_setParameter(c, 100, level);               /* ZSTD_c_compressionLevel */
+    if (workers > 1 && ZSTD_isError(ZSTD_CCtx_setParameter(c, 400, workers))) { ZSTD_freeCCtx(c); return -1.0; }   /* ZSTD_c_nbWorkers */
+    double best = -1.0;
+    for (int p = 0; p < passes; p++) {
+        const double t0 = now_s();
+        const size_t r = ZSTD_compress2(c, dst, dstCap, src, srcSize);
+        const double t = now_s() - t0;
+        if (ZSTD_isError(r)) { ZSTD_freeCCtx(c); return -1.0; }
+        if (outSize) *outSize = r;
+        if (best < 0 || t < best) best = t;
+    }
+    ZSTD_freeCCtx(c);
+    return best;
 }

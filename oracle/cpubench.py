@@ -24,6 +24,8 @@ def lib():
         vp, sz = C.c_void_p, C.c_size_t
         L.zlb_run.argtypes = [C.c_int, vp, vp, vp, vp, vp, vp, vp, sz, C.c_int, C.c_int, vp, sz, C.c_int]
         L.zlb_run.restype = C.c_double
+        L.zlb_run_workers.argtypes = [vp, sz, vp, sz, C.c_int, C.c_int, C.c_int, vp]
+        L.zlb_run_workers.restype = C.c_double
         _lib = L
     return _lib
 
@@ -65,3 +67,18 @@ def run(mode, src, dst_caps, threads, level=3, checksum=False, dict=None, passes
             raise RuntimeError("reference libzstd reported an error inside the CPU baseline")
         best = t if best is None else min(best, t)
     return best, res, dst, doffs
+
+
+def run_workers(buf, level=3, workers=0, passes=2):
+    """ONE frame from `buf` (uint8 array) with ZSTD_c_nbWorkers = workers (the reference's num_threads semantics, src/cctx.c:269-277).
+    Returns (best seconds, frame size)."""
+    L = lib()
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    cap = buf.size + (buf.size >> 7) + 1024
+    dst = np.zeros(cap, dtype=np.uint8)
+    dst[::4096] = 1
+    out = C.c_size_t(0)
+    t = L.zlb_run_workers(buf.ctypes.data, buf.size, dst.ctypes.data, cap, int(level), int(workers), int(passes), C.byref(out))
+    if t < 0:
+        raise RuntimeError("reference libzstd reported an error inside the CPU baseline (nbWorkers)")
+    return t, int(out.value)

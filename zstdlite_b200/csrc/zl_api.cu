@@ -211,7 +211,8 @@ struct ZSTD_DCtx_s {
     std::vector<u8> sIn, sOut;
     size_t sOutPos = 0;
     ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dNorm, dUnits, dCounters, dLargeIdx, dLb, dLc, dParent, dRemain, dSrc, dDst;
-    ZlPinBuf hDescs, hResults, hLargeIdx, hRemain, hStageIn, hStageOut;
+    ZlPinBuf hDescs, hResults, hLargeIdx, hRemain;
+    std::vector<cudaEvent_t> sliceDone;    // staged host buffers: the copy back of a slice has landed
 };
 
 static bool zl_ctx_stream(cudaStream_t* st, bool* own, cudaEvent_t* e0, cudaEvent_t* e1)
@@ -230,7 +231,8 @@ ZL_EXPORT size_t ZSTD_freeDCtx(ZSTD_DCtx* c)
     if (!c) return 0;
     ZlDevBuf* bufs[] = {&c->dDictContent, &c->dDict, &c->dDescs, &c->dInfos, &c->dResults, &c->dHdr, &c->dRec, &c->dCk, &c->dLit, &c->dNorm, &c->dUnits, &c->dCounters, &c->dLargeIdx, &c->dLb, &c->dLc, &c->dParent, &c->dRemain, &c->dSrc, &c->dDst};
     for (ZlDevBuf* b : bufs) b->release();
-    c->hDescs.release(); c->hResults.release(); c->hLargeIdx.release(); c->hRemain.release(); c->hStageIn.release(); c->hStageOut.release();
+    c->hDescs.release(); c->hResults.release(); c->hLargeIdx.release(); c->hRemain.release();
+    for (cudaEvent_t e : c->sliceDone) if (e) cudaEventDestroy(e);
     if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
     for (cudaEvent_t e : c->stageEv) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->laneDone) if (e) cudaEventDestroy(e);
@@ -478,13 +480,23 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     // Scattered host buffers (a list of separately allocated objects: thousands of copy runs): one cudaMemcpyAsync per run would
     // cost more than the decode (~2.5 us each).  The runs of a slice are then packed into / unpacked from pinned staging
     // buffers by the host, and each slice moves with ONE copy per direction.
-    const bool stageIn = !dev && sruns.size() > 64 + 2 * nslices, stageOut = !dev && druns.size() > 64 + 2 * nslices;
-    if (stageIn) {
-        if (!c->hStageIn.reserve(srcTotal + 64)) return ZL_ERROR(memory_allocation);
-        u8* hs = c->hStageIn.as<u8>();
-        for (const ZlRun& r : sruns) if (r.bytes) memcpy(hs + r.devOff, r.hbase, r.bytes);
+    // ... and PAGEABLE host buffers (what the reference's C layer passes: R vectors) are staged the same way: cudaMemcpyAsync on pageable
+    // memory runs through the driver's staging on one thread (config 2: 8.4 GB/s end to end).  Staging is pipelined with the slices:
+    // the host packs slice k+1 (zl_host.h, ZlCopyPool) while the device works on slice k, and unpacks slice k while k+1 is in flight.
+    // (small pageable calls stay with the driver's path: its staging is fine below a few MiB)
+    const bool stageIn = !dev && (sruns.size() > 64 + 2 * nslices || (srcTotal >= (4u << 20) && zl_is_pageable(sruns[0].hbase)));
+    const bool stageOut = !dev && (druns.size() > 64 + 2 * nslices || (dstTotal >= (4u << 20) && zl_is_pageable(druns[0].hbase)));
+    ZlStagePool& sp = ZlStagePool::get();
+    std::unique_lock<std::mutex> stageLock(sp.m, std::defer_lock);
+    if (stageIn || stageOut) stageLock.lock();
+    if (stageIn && !sp.in.reserve(srcTotal + 64)) return ZL_ERROR(memory_allocation);
+    if (stageOut && !sp.out.reserve(dstTotal + 64)) return ZL_ERROR(memory_allocation);
+    if (stageOut && c->sliceDone.size() < nslices) {
+        const size_t have = c->sliceDone.size();
+        c->sliceDone.resize(nslices);
+        for (size_t k = have; k < nslices; k++) if (cudaEventCreateWithFlags(&c->sliceDone[k], cudaEventDisableTiming) != cudaSuccess) { c->sliceDone.resize(k); return ZL_ERROR(memory_allocation); }
     }
-    if (stageOut && !c->hStageOut.reserve(dstTotal + 64)) return ZL_ERROR(memory_allocation);
+    std::vector<ZlCopySeg> copySegs;
     std::vector<u32> srunOf, drunOf;                 // copy run of every frame (host buffers), by caller's index
     if (!dev) {
         srunOf.resize(n); drunOf.resize(n);
@@ -555,8 +567,12 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
             if (nslices > 1 && k > 0) cudaStreamWaitEvent(ls, c->inDone[(k - 1) % ZL_DEC_LANES], 0);
             if (stageIn) {
                 if (srunCut[k + 1] > srunCut[k]) {
+                    u8* hs = sp.in.as<u8>();
+                    copySegs.clear();
+                    for (size_t r = srunCut[k]; r < srunCut[k + 1]; r++) if (sruns[r].bytes) copySegs.push_back({hs + sruns[r].devOff, sruns[r].hbase, sruns[r].bytes});
+                    ZlCopyPool::get().run(copySegs);                   // (the device is busy with the slices before this one)
                     const size_t o0 = sruns[srunCut[k]].devOff, o1 = sruns[srunCut[k + 1] - 1].devOff + sruns[srunCut[k + 1] - 1].bytes;
-                    if (o1 > o0) cudaMemcpyAsync(c->dSrc.as<u8>() + o0, c->hStageIn.as<u8>() + o0, o1 - o0, cudaMemcpyHostToDevice, ls);
+                    if (o1 > o0) cudaMemcpyAsync(c->dSrc.as<u8>() + o0, hs + o0, o1 - o0, cudaMemcpyHostToDevice, ls);
                 }
             } else
             for (size_t r = srunCut[k]; r < srunCut[k + 1]; r++)
@@ -599,8 +615,10 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         if (!dev && stageOut) {
             if (drunCut[k + 1] > drunCut[k]) {
                 const size_t o0 = druns[drunCut[k]].devOff, o1 = druns[drunCut[k + 1] - 1].devOff + druns[drunCut[k + 1] - 1].bytes;
-                if (o1 > o0) cudaMemcpyAsync(c->hStageOut.as<u8>() + o0, c->dDst.as<u8>() + o0, o1 - o0, cudaMemcpyDeviceToHost, ls);
+                if (o1 > o0) cudaMemcpyAsync(sp.out.as<u8>() + o0, c->dDst.as<u8>() + o0, o1 - o0, cudaMemcpyDeviceToHost, ls);
             }
+            cudaMemcpyAsync(c->hResults.as<u64>() + a, c->dResults.as<u64>() + a, cnt * 8, cudaMemcpyDeviceToHost, ls);
+            cudaEventRecord(c->sliceDone[k], ls);
         } else
         if (!dev) for (size_t r = drunCut[k]; r < drunCut[k + 1]; r++)
             if (druns[r].bytes) cudaMemcpyAsync((void*)druns[r].hbase, c->dDst.as<u8>() + druns[r].devOff, druns[r].bytes, cudaMemcpyDeviceToHost, ls);
@@ -611,6 +629,29 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     cudaEventRecord(c->ev1, st);
     if (e != cudaSuccess) { cudaStreamSynchronize(st); fprintf(stderr, "zstdlite_gpu: kernel launch failed: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
     const double tLaunch = hostMs();
+    if (stageOut && e == cudaSuccess) {
+        // unpack slice after slice as its copy back lands (only what each frame produced), while the later slices are still in flight
+        const u8* ho = sp.out.as<u8>();
+        const u64* hrs = c->hResults.as<u64>();
+        for (size_t k = 0; k < nslices; k++) {
+            if (cut[k + 1] == cut[k]) continue;
+            if (cudaEventSynchronize(c->sliceDone[k]) != cudaSuccess) break;
+            copySegs.clear();
+            for (size_t r = drunCut[k]; r < drunCut[k + 1]; r++) {
+                const ZlRun& run = druns[r];
+                size_t off = 0, segBeg = 0, segLen = 0;                // frames that filled their slot merge into one copy
+                for (size_t i = run.first; i < run.first + run.count; i++) {
+                    const size_t got = (size_t)hrs[i];
+                    const size_t take = zl_is_error(got) ? 0 : (got < dstCap[i] ? got : dstCap[i]);
+                    if (segLen && segBeg + segLen == off) segLen += take; else { if (segLen) copySegs.push_back({(u8*)run.hbase + segBeg, ho + run.devOff + segBeg, segLen}); segBeg = off; segLen = take; }
+                    if (take != dstCap[i]) { if (segLen) copySegs.push_back({(u8*)run.hbase + segBeg, ho + run.devOff + segBeg, segLen}); segLen = 0; }
+                    off += dstCap[i];
+                }
+                if (segLen) copySegs.push_back({(u8*)run.hbase + segBeg, ho + run.devOff + segBeg, segLen});
+            }
+            ZlCopyPool::get().run(copySegs);
+        }
+    }
     cudaMemcpyAsync(c->hResults.p, c->dResults.p, n * 8, cudaMemcpyDeviceToHost, st);
     e = cudaStreamSynchronize(st);
     const double tSync = hostMs();
@@ -632,17 +673,6 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     }
     const u64* hr = c->hResults.as<u64>();
     for (size_t pos = 0; pos < n; pos++) result[order[pos]] = (size_t)hr[pos];
-    if (stageOut) {                                       // unpack the staged output: only what each frame produced
-        const u8* ho = c->hStageOut.as<u8>();
-        for (const ZlRun& r : druns) {
-            size_t off = 0;
-            for (size_t i = r.first; i < r.first + r.count; i++) {
-                const size_t got = result[i];
-                if (!zl_is_error(got) && got) memcpy((u8*)r.hbase + off, ho + r.devOff + off, got < dstCap[i] ? got : dstCap[i]);
-                off += dstCap[i];
-            }
-        }
-    }
     return 0;
 }
 

@@ -5,6 +5,10 @@
 #include <stddef.h>
 #include <string.h>
 #include <vector>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <atomic>
 #include "zl_common.cuh"
 #include "zl_launch.h"
 
@@ -56,3 +60,88 @@ size_t zl_host_find_frame_size(const void* src, size_t srcSize, unsigned* nblock
 
 // contiguous-run staging between host buffers and a device arena
 struct ZlRun { size_t first, count; const uint8_t* hbase; size_t bytes; size_t devOff; };
+
+// ---- host copy pool ---------------------------------------------------------------------------------------------------
+// The reference's C layer hands over PAGEABLE memory (R vectors: src/raw-file.c:166,189).  cudaMemcpyAsync on such memory goes
+// through the driver's own staging, synchronously and on one thread (measured: 8.4 GB/s for config 2 end to end against 41 GB/s
+// with pinned buffers).  The library stages pageable and scattered buffers through its own pinned memory instead and moves the
+// bytes with this pool: a few worker threads (ZL_COPY_THREADS, default min(8, cores / 2)) that split a list of copies into
+// 256 KiB pieces and pull them from a shared counter; the calling thread takes part.  Process-wide, created on first use.
+struct ZlCopySeg { void* dst; const void* src; size_t bytes; };
+class ZlCopyPool {
+public:
+    static ZlCopyPool& get() { static ZlCopyPool p; return p; }
+    void run(const std::vector<ZlCopySeg>& segs)
+    {
+        size_t total = 0;
+        for (const ZlCopySeg& s : segs) total += s.bytes;
+        if (total < (4u << 20) || workers_.empty()) { for (const ZlCopySeg& s : segs) if (s.bytes) memcpy(s.dst, s.src, s.bytes); return; }
+        std::lock_guard<std::mutex> serial(runMutex_);            // one job at a time (contexts on different threads share the pool)
+        pieces_.clear();
+        for (const ZlCopySeg& s : segs)
+            for (size_t o = 0; o < s.bytes; o += kPiece) pieces_.push_back({(char*)s.dst + o, (const char*)s.src + o, s.bytes - o < kPiece ? s.bytes - o : kPiece});
+        next_.store(0); pending_.store((int)workers_.size());
+        { std::lock_guard<std::mutex> g(m_); generation_++; }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> g(m_);
+        done_.wait(g, [&] { return pending_.load() == 0; });
+    }
+    unsigned threads() const { return (unsigned)workers_.size() + 1; }
+private:
+    static constexpr size_t kPiece = 256u << 10;
+    ZlCopyPool()
+    {
+        unsigned n = std::thread::hardware_concurrency() / 2;
+        if (n > 8) n = 8;
+        if (const char* e = getenv("ZL_COPY_THREADS")) n = (unsigned)atoi(e);
+        if (n < 1) n = 1;
+        for (unsigned i = 1; i < n; i++) workers_.emplace_back([this] { loop(); });
+    }
+    ~ZlCopyPool()
+    {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; generation_++; }
+        cv_.notify_all();
+        for (std::thread& t : workers_) t.join();
+    }
+    void work()
+    {
+        for (;;) {
+            const size_t i = next_.fetch_add(1);
+            if (i >= pieces_.size()) break;
+            memcpy(pieces_[i].dst, pieces_[i].src, pieces_[i].bytes);
+        }
+    }
+    void loop()
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            { std::unique_lock<std::mutex> g(m_); cv_.wait(g, [&] { return generation_ != seen; }); seen = generation_; if (stop_) return; }
+            work();
+            if (pending_.fetch_sub(1) == 1) { std::lock_guard<std::mutex> g(m_); done_.notify_all(); }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::vector<ZlCopySeg> pieces_;
+    std::atomic<size_t> next_{0};
+    std::atomic<int> pending_{0};
+    std::mutex m_, runMutex_;
+    std::condition_variable cv_, done_;
+    unsigned long long generation_ = 0;
+    bool stop_ = false;
+};
+// true when `p` is ordinary (pageable) host memory: not pinned, not registered, not managed
+static inline bool zl_is_pageable(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// Pinned staging shared by every context of the process (the reference creates a fresh context per call -- src/raw-file.c:150-189 --
+// and pinning memory costs ~0.3 s per GB, more than the decode it would serve): grow-only, borrowed under a lock for one call.
+struct ZlStagePool {
+    std::mutex m;
+    ZlPinBuf in, out;
+    static ZlStagePool& get() { static ZlStagePool p; return p; }
+};
