@@ -131,6 +131,13 @@ size_t zl_compress_batch(ZSTD_CCtx* cctx, const void* const* src, const size_t* 
 size_t zl_compress_split(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize,
                          size_t frameSize, size_t* frameSizes, int ptrs_are_device);
 
+/* Compression levels: 1, 2, 3 are native (negative "fast" levels run the level-1 engine, 0 means 3).  Levels 4..22 -- the greedy /
+ * lazy / optimal parsers of zstd.c:31546-33746 -- are not implemented: ZSTD_CCtx_setParameter(ZSTD_c_compressionLevel, >= 4)
+ * returns parameter_unsupported, unless the context (this call) or the process (ZSTDLITE_GPU_LEVEL_FALLBACK=1) opted into running
+ * them on the level-3 engine, which is announced once on stderr.  zl_cctx_engine_level: the engine a context's level runs (1..3). */
+size_t zl_cctx_allow_level_fallback(ZSTD_CCtx* cctx, int on);
+int zl_cctx_engine_level(const ZSTD_CCtx* cctx);
+
 /* CUDA stream (cudaStream_t passed as void*) the context launches on; default: a private non-blocking stream */
 size_t zl_dctx_set_stream(ZSTD_DCtx* dctx, void* cuda_stream);
 size_t zl_cctx_set_stream(ZSTD_CCtx* cctx, void* cuda_stream);

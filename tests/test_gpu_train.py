@@ -135,3 +135,18 @@ def test_training_errors(z):
         z.zstd_train_dict_compress(objs[:4], 5000)                        # fewer than 5 training samples (zstd.c:49461); src/dictionaries.c:104
     with pytest.raises(z.ZstdError, match="Training error"):
         z.zstd_train_dict_compress(objs, 100)                             # below ZDICT_DICTSIZE_MIN
+
+
+def test_large_samples_are_accepted(z, ref):
+    """ZDICT takes samples of any size (the d-mer selection sees every byte, only the entropy statistics clip a sample to one block,
+    zstd.c:50440-50460): serialized data.frame-like objects of several hundred KiB must train, and the dictionary must be standard."""
+    from zstdlite_b200 import corpus
+    rng = np.random.default_rng(5)
+    base = corpus.make("text", 300000, 3).tobytes()
+    samples = [base[int(o):int(o) + int(n)] for o, n in zip(rng.integers(0, 100000, 24), rng.integers(140000, 200000, 24))]
+    d = _quiet(z.zstd_train_dict_compress, samples, 16384)
+    assert z.zstd_dict_id(d) != 0 and len(d) <= 16384
+    held = base[50000:50000 + 150000]
+    c = z.zstd_compress(held, level=3, dict=d)
+    assert ref.DCtx(dict=d).decompress(c, cap=len(held)) == held
+    assert len(ref.CCtx(level=3, dict=d).compress(held[:4000])) < len(ref.CCtx(level=3).compress(held[:4000]))

@@ -32,3 +32,17 @@ for _ in range(3):
     t = time.time(); r = L.ZSTD_decompressDCtx(d._p, C.c_void_p(out.ctypes.data), n * fb, C.c_void_p(ps.ctypes.data), len(blob)); dt = time.time() - t
 assert int(r) == n * fb and bool((out.reshape(n, fb) == data).all())
 print(f"ZSTD_decompressDCtx on the concatenated stream, pageable: {dt*1e3:.1f} ms -> {n*fb/dt/1e9:.1f} GB/s")
+# one-shot ZSTD_compress2 of one buffer (the reference's zstd_compress path): pinned vs pageable input/output
+from oracle import ref
+m = 4096
+raw = data[:m].reshape(-1).copy()
+cap = int(L.ZSTD_compressBound(raw.size))
+cc = z.zstd_cctx(level=3)
+for label, src_t, dst_t in (("pinned", torch.from_numpy(raw.copy()).pin_memory(), torch.zeros(cap, dtype=torch.uint8).pin_memory()), ("pageable", torch.from_numpy(raw.copy()), torch.zeros(cap, dtype=torch.uint8))):
+    tt = []
+    for _ in range(4):
+        t = time.time(); r = L.ZSTD_compress2(cc._p, C.c_void_p(dst_t.data_ptr()), cap, C.c_void_p(src_t.data_ptr()), raw.size); tt.append(time.time() - t)
+    assert not z.is_error(r)
+    back = ref.decompress(dst_t.numpy()[:int(r)].tobytes())
+    assert back == raw.tobytes()
+    print(f"ZSTD_compress2 {raw.size >> 20} MiB, {label}: best {min(tt[1:])*1e3:.1f} ms -> {raw.size/min(tt[1:])/1e9:.1f} GB/s, ratio {raw.size/int(r):.2f}")

@@ -77,6 +77,7 @@ def lib():
         "zl_compress_split": (sz, [vp, vp, sz, vp, sz, sz, psz, C.c_int]),
         "zl_cctx_set_stream": (sz, [vp, vp]), "zl_cctx_launch_count": (C.c_ulonglong, [vp]), "zl_cctx_last_kernel_ms": (C.c_double, [vp]),
         "zl_cctx_last_stage_ms": (C.c_double, [vp, C.c_int]),
+        "zl_cctx_allow_level_fallback": (sz, [vp, C.c_int]), "zl_cctx_engine_level": (C.c_int, [vp]),
         # dictionary training
         "ZDICT_trainFromBuffer": (sz, [vp, sz, vp, psz, C.c_uint]),
         "ZDICT_optimizeTrainFromBuffer_cover": (sz, [vp, sz, vp, psz, C.c_uint, C.POINTER(CoverParams)]),
@@ -108,4 +109,5 @@ EXPORTED_SYMBOLS = [
     "ZDICT_trainFromBuffer", "ZDICT_optimizeTrainFromBuffer_cover", "ZDICT_isError", "ZDICT_getErrorName",
     "zl_decompress_batch", "zl_compress_batch", "zl_compress_split", "zl_dctx_set_stream", "zl_dctx_set_profile", "zl_cctx_set_stream",
     "zl_dctx_launch_count", "zl_cctx_launch_count", "zl_dctx_last_kernel_ms", "zl_cctx_last_kernel_ms", "zl_dctx_last_stage_ms", "zl_cctx_last_stage_ms", "zl_backend_string",
+    "zl_cctx_allow_level_fallback", "zl_cctx_engine_level",
 ]

@@ -94,7 +94,9 @@ class zstd_dctx:
 class zstd_cctx:
     """zstd_cctx(level = 3, num_threads = 1, include_checksum = FALSE, dict = NULL)  (R/cctx.R:38-48, src/cctx.c:213-315)."""
 
-    def __init__(self, level=3, num_threads=1, include_checksum=False, dict=None, **unknown):
+    def __init__(self, level=3, num_threads=1, include_checksum=False, dict=None, level_fallback=False, **unknown):
+        """level_fallback (extension): levels 4..22 are not implemented on the GPU and are refused ("init_cctx(): Bad compression level",
+        src/cctx.c:265) unless this is True (or ZSTDLITE_GPU_LEVEL_FALLBACK=1): then they run the level-3 engine."""
         for k in unknown:
             warnings.warn(f"init_cctx(): Unknown option '{k}'")          # src/cctx.c:288
         L = _lib.lib()
@@ -102,7 +104,10 @@ class zstd_cctx:
         if not self._p:
             raise ZstdError("init_cctx(): Couldn't initialse memory for 'cctx'")
         level = max(-5, min(22, int(level)))                              # src/cctx.c:261-268
-        _check(L.ZSTD_CCtx_setParameter(self._p, _lib.ZSTD_c_compressionLevel, level), "init_cctx() level")
+        if level_fallback:
+            L.zl_cctx_allow_level_fallback(self._p, 1)
+        if is_error(L.ZSTD_CCtx_setParameter(self._p, _lib.ZSTD_c_compressionLevel, level)):
+            raise ZstdError("init_cctx(): Bad compression level")        # src/cctx.c:265 (levels >= 4: see level_fallback)
         if int(num_threads) > 1:                                          # src/cctx.c:269-277
             _check(L.ZSTD_CCtx_setParameter(self._p, _lib.ZSTD_c_nbWorkers, int(num_threads)), "init_cctx() num_threads")
         _check(L.ZSTD_CCtx_setParameter(self._p, _lib.ZSTD_c_checksumFlag, 1 if include_checksum else 0), "init_cctx() checksum")
@@ -209,9 +214,29 @@ def zstd_serialize(obj, cctx=None, frame_size=None, **opts):
 
 def zstd_unserialize(src, dctx=None, **opts):
     """zstd_unserialize(src, ..., dctx)  (R/serialize.R:74, src/serialize.c:141-215): decompress, then unserialize.
-    Like the reference this reads content sizes from the frame headers; every frame of `src` is decoded (8f rank 2)."""
-    import pickle
-    return pickle.loads(zstd_decompress(src, dctx=dctx, all_frames=True, **opts))
+    Like the reference this reads content sizes from the frame headers; every frame of `src` is decoded (8f rank 2).
+
+    WARNING: pickle stands in for R's unserialize() in this mirror, and unpickling runs code named by the payload.  Only the
+    plain-data types zstd_serialize() is used with in the tests are accepted (a restricted Unpickler); anything else raises
+    pickle.UnpicklingError -- never feed this frames from an untrusted source expecting more than that."""
+    import io
+    return _SafeUnpickler(io.BytesIO(zstd_decompress(src, dctx=dctx, all_frames=True, **opts))).load()
+
+
+import pickle as _pickle
+
+
+class _SafeUnpickler(_pickle.Unpickler):
+    """Plain data only: builtins' containers / scalars and numpy arrays (what a data.frame-like payload needs)."""
+    _ALLOWED = {("builtins", n) for n in ("list", "dict", "tuple", "set", "frozenset", "bytes", "bytearray", "str", "int", "float", "complex", "bool", "slice", "range")} | {
+        ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"), ("numpy", "ndarray"), ("numpy", "dtype"),
+        ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"), ("numpy._core.numeric", "_frombuffer"), ("numpy.core.numeric", "_frombuffer"),
+        ("collections", "OrderedDict")}
+
+    def find_class(self, module, name):
+        if (module, name) in self._ALLOWED:
+            return super().find_class(module, name)
+        raise _pickle.UnpicklingError(f"zstd_unserialize: {module}.{name} is not plain data; refusing to unpickle it")
 
 
 _OUTSIZE, _INSIZE = 131591, 131072          # static buffer sizes of the reference's streaming writers (src/raw-file-out.c:23-24)

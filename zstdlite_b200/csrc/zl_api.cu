@@ -754,6 +754,11 @@ ZL_EXPORT size_t ZSTD_decompressStream(ZSTD_DCtx* c, ZSTD_outBuffer* out, ZSTD_i
         if (fs == ZL_ERROR(srcSize_wrong)) return 1;              // frame incomplete: wait for more input
         if (zl_is_error(fs)) { c->sIn.clear(); return fs; }
         if (h.skippable) { c->sIn.erase(c->sIn.begin(), c->sIn.begin() + (ptrdiff_t)fs); if (c->sIn.empty()) return 0; continue; }
+        // zstd.c:42800-42806: a streaming decoder refuses windows beyond ZSTD_d_windowLogMax before it allocates anything
+        if (h.windowSize > (1ull << c->windowLogMax)) { c->sIn.clear(); return ZL_ERROR(frameParameter_windowTooLarge); }
+        // nor does a header get memory its blocks cannot fill (a block regenerates <= blockSizeMax bytes): such a frame can only
+        // end in corruption_detected (zstd.c:41646), so say it before allocating the claimed size on the host and ~8x that on the device
+        if (h.contentSize != ZSTD_CONTENTSIZE_UNKNOWN && h.contentSize > (unsigned long long)nblocks * h.blockSizeMax) { c->sIn.clear(); return ZL_ERROR(corruption_detected); }
         const size_t cap = h.contentSize != ZSTD_CONTENTSIZE_UNKNOWN ? (size_t)h.contentSize : (size_t)nblocks * h.blockSizeMax;
         if (cap > 0x7FFFFFF0ull) { c->sIn.clear(); return ZL_ERROR(memory_allocation); }
         c->sOut.resize(cap ? cap : 1);

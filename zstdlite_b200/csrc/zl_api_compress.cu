@@ -16,6 +16,7 @@
 
 struct ZSTD_CCtx_s {
     int level = 3, nbWorkers = 0, checksumFlag = 0, stableIn = 0, stableOut = 0;
+    bool levelFallback = false;            // zl_cctx_allow_level_fallback: levels >= 4 run the level-3 engine instead of being refused
     unsigned long long pledged = ZSTD_CONTENTSIZE_UNKNOWN;
     std::vector<u8> dictRaw;
     bool dictDirty = false;                // dictRaw changed (or the engine level did): digest again before the next compression
@@ -30,7 +31,7 @@ struct ZSTD_CCtx_s {
     double lastKernelMs = 0.0, lastStageMs[ZL_ENC_STAGES] = {};
     unsigned long long launches = 0;
     ZlDevBuf dBlocks, dFrames, dM, dRecs, dLit, dHist, dMetas, dOuts, dPlans, dResults, dXxh, dXxhPtrs, dXxhSizes, dSrc, dDst, dAux;
-    ZlPinBuf hBlocks, hFrames, hResults, hAux, hStageIn, hStageOut;
+    ZlPinBuf hBlocks, hFrames, hResults, hAux;
     // streaming session (ZSTD_compressStream2): input accumulated on the host until ZSTD_e_end, then one frame is produced
     std::vector<u8> sIn, sOut;
     size_t sOutPos = 0;
@@ -43,7 +44,10 @@ struct ZSTD_CCtx_s {
     u32* statsDev = nullptr;               // set by the dictionary trainer: parse only, statistics summed here (zl_dict_train.cuh)
 };
 
-static bool g_constReady = false;
+// __constant__ symbols and function attributes are per device: the encoder's code tables are uploaded once for every device a
+// context is used on (a process may compress on several devices, and from several threads)
+static std::mutex g_constMutex;
+static bool g_constReady[64] = {};
 
 static bool zl_cctx_ready(ZSTD_CCtx* c)
 {
@@ -60,9 +64,14 @@ static bool zl_cctx_ready(ZSTD_CCtx* c)
             cudaEventCreateWithFlags(&c->sideFork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->sideJoin, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); return false; }
     }
-    if (!g_constReady) {
-        if (zl_enc_upload_const() != cudaSuccess) { (void)cudaGetLastError(); return false; }
-        g_constReady = true;
+    int devId = 0;
+    if (cudaGetDevice(&devId) != cudaSuccess || devId < 0 || devId >= 64) { (void)cudaGetLastError(); return false; }
+    {
+        std::lock_guard<std::mutex> g(g_constMutex);
+        if (!g_constReady[devId]) {
+            if (zl_enc_upload_const() != cudaSuccess) { (void)cudaGetLastError(); return false; }
+            g_constReady[devId] = true;
+        }
     }
     return true;
 }
@@ -75,7 +84,7 @@ ZL_EXPORT size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
                         &c->dXxh, &c->dXxhPtrs, &c->dXxhSizes, &c->dSrc, &c->dDst, &c->dAux,
                         &c->dDict, &c->dDictContent, &c->dDictTabS, &c->dDictTabL};
     for (ZlDevBuf* b : bufs) b->release();
-    c->hBlocks.release(); c->hFrames.release(); c->hResults.release(); c->hAux.release(); c->hStageIn.release(); c->hStageOut.release();
+    c->hBlocks.release(); c->hFrames.release(); c->hResults.release(); c->hAux.release();
     if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
     for (cudaEvent_t e : c->stageEv) if (e) cudaEventDestroy(e);
     if (c->side) { cudaStreamDestroy(c->side); cudaEventDestroy(c->sideFork); cudaEventDestroy(c->sideJoin); }
@@ -98,11 +107,23 @@ ZL_EXPORT size_t ZSTD_CCtx_reset(ZSTD_CCtx* c, ZSTD_ResetDirective r)          /
 ZL_EXPORT size_t ZSTD_CCtx_setParameter(ZSTD_CCtx* c, ZSTD_cParameter p, int v)           // zstd.c:23223 (bounds: 22900-23100)
 {
     switch ((int)p) {
-    case ZSTD_c_compressionLevel:                        // clamped, not rejected (ZSTD_cParam_clampBounds); 0 means default
+    case ZSTD_c_compressionLevel: {                      // clamped like libzstd (ZSTD_cParam_clampBounds); 0 means default
         if (v < -131072) v = -131072;
         if (v > 22) v = 22;
+        // Levels 4-22 (greedy / lazy / optimal parsers, zstd.c:31546-33746) are not implemented.  They are REFUSED rather than
+        // served by the level-3 engine under another label ("unsupported level" error), unless the caller
+        // opts in: ZSTDLITE_GPU_LEVEL_FALLBACK=1 in the environment (or zl_cctx_allow_level_fallback) runs the level-3 engine for
+        // them -- valid Zstandard at level-3 ratio -- and says so once on stderr.  Negative ("fast") levels run the level-1
+        // engine: they ask for less ratio than it gives.
+        static const bool envFallback = getenv("ZSTDLITE_GPU_LEVEL_FALLBACK") != nullptr && atoi(getenv("ZSTDLITE_GPU_LEVEL_FALLBACK")) != 0;
+        if (v > 3) {
+            if (!envFallback && !c->levelFallback) return ZL_ERROR(parameter_unsupported);
+            static bool told = false;
+            if (!told) { told = true; fprintf(stderr, "zstdlite_gpu: compression level %d is not implemented; running the level-3 engine (ZSTDLITE_GPU_LEVEL_FALLBACK)\n", v); }
+        }
         c->level = v == 0 ? 3 : v;
         return 0;
+    }
     case ZSTD_c_nbWorkers: if (v < 0) v = 0; if (v > 256) v = 256; c->nbWorkers = v; return 0;
     case ZSTD_c_checksumFlag: if (v < 0 || v > 1) return ZL_ERROR(parameter_outOfBound); c->checksumFlag = v; return 0;
     case ZSTD_c_stableInBuffer: if (v < 0 || v > 1) return ZL_ERROR(parameter_outOfBound); c->stableIn = v; return 0;
@@ -110,6 +131,10 @@ ZL_EXPORT size_t ZSTD_CCtx_setParameter(ZSTD_CCtx* c, ZSTD_cParameter p, int v) 
     default: return ZL_ERROR(parameter_unsupported);
     }
 }
+// extension: accept levels 4-22 on this context and run them on the level-3 engine (see ZSTD_c_compressionLevel above)
+ZL_EXPORT size_t zl_cctx_allow_level_fallback(ZSTD_CCtx* c, int on) { if (!c) return ZL_ERROR(GENERIC); c->levelFallback = on != 0; return 0; }
+// extension: the engine level (1..3) a context's `level` actually runs
+ZL_EXPORT int zl_cctx_engine_level(const ZSTD_CCtx* c) { return c ? (c->level < 1 ? 1 : (c->level > 3 ? 3 : c->level)) : 0; }
 ZL_EXPORT size_t ZSTD_CCtx_getParameter(const ZSTD_CCtx* c, ZSTD_cParameter p, int* v)
 {
     switch ((int)p) {
@@ -188,8 +213,8 @@ ZL_ALIAS(size_t, ZSTD_CCtx_setPledgedSrcSize, (ZSTD_CCtx*, unsigned long long))
 ZL_ALIAS(size_t, ZSTD_CCtx_loadDictionary, (ZSTD_CCtx*, const void*, size_t))
 ZL_ALIAS(size_t, ZSTD_compressBound, (size_t))
 
-// The level selects one of three table layouts (zl_enc_match.cuh).  Levels below 1 run the level-1 engine and levels
-// above 3 the level-3 engine: still valid Zstandard, without the higher levels' ratio ("levels").
+// The level selects one of three table layouts (zl_enc_match.cuh).  Levels below 1 run the level-1 engine; levels above 3 are
+// refused by ZSTD_CCtx_setParameter unless the caller opted into the level-3 engine for them ("levels").
 static int zl_engine_level(int level) { return level < 1 ? 1 : (level > 3 ? 3 : level); }
 
 // ---- one wave: frames [f0, f1) with DEVICE src/dst pointers; asynchronous on the context's stream.
@@ -211,7 +236,7 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
     }
     if (nb > 0x3FFFFFFFull) return ZL_ERROR(memory_allocation);
     const u32 S = ((maxBlock < 512 ? 512 : maxBlock) + 255) & ~255u;      // slot layout below needs S >= 264
-    const u32 slotM = S, slotRec = S / 5 + 32, slotLit = S + 16;      // records: 4 segments of <= ZL_PARSE_SEG_RECS (zl_enc_match.cuh)
+    const u32 slotM = S, slotRec = S / 5 + 32, slotLit = S + 16;      // records: ZL_PARSE_WARPS segments of <= ZL_PARSE_SEG_RECS (zl_enc_match.cuh)
     const u32 streamCapWords = (((S / 4 + 1) * 11) / 8 + 16 + 3) / 4, streamWordsPerBlock = 4 * streamCapWords, seqCapWords = S / 4;
     if (!c->hBlocks.reserve(nb * sizeof(ZlEncBlock)) || !c->hFrames.reserve(nf * sizeof(ZlEncFrame))) return ZL_ERROR(memory_allocation);
     if (!c->dBlocks.reserve(nb * sizeof(ZlEncBlock)) || !c->dFrames.reserve(nf * sizeof(ZlEncFrame)) || !c->dM.reserve(nb * (size_t)slotM * 4) ||
@@ -362,12 +387,28 @@ ZL_EXPORT size_t zl_compress_batch(ZSTD_CCtx* c, const void* const* src, const s
     }
     // scattered inputs (a list of separately allocated objects): packed by the host into pinned staging, ONE copy in; the frames
     // are then gathered on the device, copied back with ONE copy and unpacked by the host (a cudaMemcpyAsync per object costs ~2.5 us)
-    const bool staged = sruns.size() > 64 || n > 256;
+    // ... and so are PAGEABLE inputs of a few MiB and more (what the reference's C layer passes to ZSTD_compress2: an R vector,
+    // src/raw-file.c:74): the host copy pool (zl_host.h) packs 64 MiB pieces into the process-wide pinned staging while the copy
+    // engine moves the piece before (the driver's own pageable path is one thread, ~8 GB/s)
+    const bool staged = sruns.size() > 64 || n > 256 || (srcTotal >= (4u << 20) && zl_is_pageable(sruns[0].hbase));
+    ZlStagePool& sp = ZlStagePool::get();
+    std::unique_lock<std::mutex> stageLock(sp.m, std::defer_lock);
     if (staged) {
-        if (!c->hStageIn.reserve(srcTotal + 64)) return ZL_ERROR(memory_allocation);
-        u8* hs = c->hStageIn.as<u8>();
-        for (const ZlRun& r : sruns) if (r.bytes) memcpy(hs + r.devOff, r.hbase, r.bytes);
-        if (srcTotal) cudaMemcpyAsync(c->dSrc.p, hs, srcTotal, cudaMemcpyHostToDevice, st);
+        stageLock.lock();
+        if (!sp.in.reserve(srcTotal + 64)) return ZL_ERROR(memory_allocation);
+        u8* hs = sp.in.as<u8>();
+        std::vector<ZlCopySeg> segs;
+        const size_t piece = (size_t)64 << 20;
+        size_t sent = 0;                                               // staging bytes already handed to the copy engine
+        auto flush = [&](size_t upTo) { if (upTo > sent) { ZlCopyPool::get().run(segs); segs.clear(); cudaMemcpyAsync(c->dSrc.as<u8>() + sent, hs + sent, upTo - sent, cudaMemcpyHostToDevice, st); sent = upTo; } };
+        for (const ZlRun& r : sruns) {
+            for (size_t o = 0; o < r.bytes; o += piece) {
+                const size_t len = r.bytes - o < piece ? r.bytes - o : piece;
+                segs.push_back({hs + r.devOff + o, r.hbase + o, len});
+                if (r.devOff + o + len - sent >= piece) flush(r.devOff + o + len);
+            }
+        }
+        flush(srcTotal);
     } else
     for (const ZlRun& r : sruns) if (r.bytes) cudaMemcpyAsync(c->dSrc.as<u8>() + r.devOff, r.hbase, r.bytes, cudaMemcpyHostToDevice, st);
     const size_t r = zl_enc_run(c, dsrc.data(), srcSize, ddst.data(), dstCap, n);
@@ -382,15 +423,17 @@ ZL_EXPORT size_t zl_compress_batch(ZSTD_CCtx* c, const void* const* src, const s
             const size_t got = zl_is_error(result[i]) ? 0 : result[i];
             hsz[i] = got; hoff[i] = total; hptr[i] = ddst[i]; total += got;
         }
-        if (!c->dOutStage.reserve(total + 64) || !c->hStageOut.reserve(total + 64)) return ZL_ERROR(memory_allocation);
+        if (!c->dOutStage.reserve(total + 64) || !sp.out.reserve(total + 64)) return ZL_ERROR(memory_allocation);
         cudaMemcpyAsync(c->dAux.p, hsz, n * 24, cudaMemcpyHostToDevice, st);
         const u64* dsz = c->dAux.as<u64>();
         if (zl_launch_gather(reinterpret_cast<const u8* const*>(dsz + 2 * n), dsz, dsz + n, c->dOutStage.as<u8>(), (u32)n, st) != cudaSuccess) return ZL_ERROR(GENERIC);
         c->launches += 1;
-        if (total) cudaMemcpyAsync(c->hStageOut.p, c->dOutStage.p, total, cudaMemcpyDeviceToHost, st);
+        if (total) cudaMemcpyAsync(sp.out.p, c->dOutStage.p, total, cudaMemcpyDeviceToHost, st);
         if (cudaStreamSynchronize(st) != cudaSuccess) { (void)cudaGetLastError(); return ZL_ERROR(GENERIC); }
-        const u8* ho = c->hStageOut.as<u8>();
-        for (size_t i = 0; i < n; i++) if (hsz[i]) memcpy(dst[i], ho + hoff[i], hsz[i]);
+        const u8* ho = sp.out.as<u8>();
+        std::vector<ZlCopySeg> osegs;
+        for (size_t i = 0; i < n; i++) if (hsz[i]) osegs.push_back({dst[i], ho + hoff[i], (size_t)hsz[i]});
+        ZlCopyPool::get().run(osegs);
         return 0;
     }
     for (size_t i = 0; i < n; i++) {

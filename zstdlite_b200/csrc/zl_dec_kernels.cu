@@ -6,6 +6,7 @@
 #include "zl_dec_exec.cuh"
 #include "zl_dec_large.cuh"
 #include "zl_launch.h"
+#include <mutex>
 
 __constant__ ZlConstTables c_tables = {
     ZL_LL_BASE_INIT, ZL_ML_BASE_INIT, ZL_LL_BITS_INIT, ZL_ML_BITS_INIT,
@@ -380,28 +381,35 @@ zl_k_xxh64_large(const u8* const* __restrict__ ptrs, const u32* __restrict__ siz
 size_t zl_literals_smem_bytes() { return ZL_QUADS_PER_WARP * sizeof(ZlLitSm) + (ZL_LIT_RING ? ZL_LIT_RING_SLOTS * 32 * 16 : 0); }
 size_t zl_sequences_smem_bytes() { return ZL_XTAB_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlSeqSm) + (ZL_SEQ_RING ? 4 * 8 * 16 : 0); }
 
-static int g_sms = 0, g_litPerSm = 0, g_seqPerSm = 0;
+// occupancy of the two persistent entropy kernels, per device (function attributes are per device too); guarded: contexts of
+// several host threads may decode for the first time at once
+struct ZlDevLimits { int sms = 0, litPerSm = 0, seqPerSm = 0; };
+static ZlDevLimits g_limits[64];
+static std::mutex g_limitsMutex;
 cudaError_t zl_decode_grid_limits(u32* litCtas, u32* seqCtas)
 {
-    if (!g_sms) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> g(g_limitsMutex);
+    ZlDevLimits& D = g_limits[dev];
+    if (!D.sms) {
+        int sms = 0, lit = 0, seq = 0;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
         const size_t smA = zl_literals_smem_bytes(), smB = zl_sequences_smem_bytes();
         e = cudaFuncSetAttribute(zl_k_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(zl_k_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_litPerSm, zl_k_literals, 32, smA);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lit, zl_k_literals, 32, smA);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_seqPerSm, zl_k_sequences, 32, smB);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&seq, zl_k_sequences, 32, smB);
         if (e != cudaSuccess) return e;
-        if (g_litPerSm < 1) g_litPerSm = 1;
-        if (g_seqPerSm < 1) g_seqPerSm = 1;
+        D.litPerSm = lit < 1 ? 1 : lit; D.seqPerSm = seq < 1 ? 1 : seq; D.sms = sms;
     }
-    *litCtas = (u32)(g_sms * g_litPerSm); *seqCtas = (u32)(g_sms * g_seqPerSm);
+    *litCtas = (u32)(D.sms * D.litPerSm); *seqCtas = (u32)(D.sms * D.seqPerSm);
     return cudaSuccess;
 }
 
@@ -464,9 +472,10 @@ cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
         u32 pass = 1, lastPass = 0;
         for (;;) {
             const u32 group = pass == 1 ? 6u : 4u;                    // passes are launched in groups; the host looks at the counter in between
-            for (u32 k = 0; k < group && pass <= ZL_LJUMP_MAX_PASSES; k++, pass++)
+            for (u32 k = 0; k < group && pass <= ZL_LJUMP_MAX_PASSES; k++, pass++) {
                 zl_k_ljump<<<gj, 256, 0, st>>>(L.largeIdx, L.descs, L.infos, L.parentArena, L.remain, pass);
                 nk++;
+            }
             lastPass = pass - 1;
             u32 open = 1;
             if (cudaMemcpyAsync(L.remainHost, L.remain + lastPass, sizeof(u32), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;

@@ -212,7 +212,7 @@ struct ZlTrainJob {
     int level; u32 dictID;
     ZlTrainBufs B;
     ZSTD_CCtx* statCtx; ZSTD_CCtx* evalCtx;
-    std::vector<const void*> srcPtr; std::vector<void*> dstPtr; std::vector<size_t> dstCap, res;
+    std::vector<const void*> srcPtr; std::vector<void*> dstPtr; std::vector<size_t> dstCap, res, statSizes;
     cudaStream_t st;
 };
 
@@ -256,7 +256,9 @@ static size_t zl_train_candidate(ZlTrainJob& J, u32 k, u32 d, u32 nbDmers, size_
     ZSTD_CCtx_loadDictionary(sc, content.data(), content.size());
     cudaMemsetAsync(J.B.stats.p, 0, ZL_STAT_WORDS * 4, sc->stream);
     sc->statsDev = J.B.stats.as<u32>();
-    size_t r = zl_compress_batch(sc, J.srcPtr.data(), J.sizes, J.dstPtr.data(), J.dstCap.data(), J.res.data(), J.nbTrain, 1);
+    // samples of any size take part in the selection above (every d-mer counts) and in the scoring below (whole samples); the
+    // statistics look at the first block of each, as ZDICT_countEStats does (zstd.c:50440-50460)
+    size_t r = zl_compress_batch(sc, J.srcPtr.data(), J.statSizes.data(), J.dstPtr.data(), J.dstCap.data(), J.res.data(), J.nbTrain, 1);
     sc->statsDev = nullptr;
     if (zl_is_error(r)) return r;
     u32 stats[ZL_STAT_WORDS];
@@ -313,10 +315,9 @@ static size_t zl_train(void* dictBuffer, size_t dictCap, const void* samplesBuff
     std::vector<u32> offs(nb + 1);
     for (u32 i = 0; i < nb; i++) {
         offs[i] = (u32)J.totalBytes;
-        if (sizes[i] > ZL_BLOCKSIZE_MAX) return ZL_ERROR(srcSize_wrong);            // (the reference truncates to ZDICT's 128 KiB per sample)
         J.totalBytes += sizes[i];
         if (i + 1 == J.nbTrain) J.trainBytes = J.totalBytes;
-        if (J.totalBytes > 0xF0000000ull) return ZL_ERROR(srcSize_wrong);
+        if (J.totalBytes > 0xF0000000ull) return ZL_ERROR(srcSize_wrong);           // as the reference: FASTCOVER_MAX_SAMPLES_SIZE (4 GiB), zstd.c:49474
     }
     offs[nb] = (u32)J.totalBytes;
     if (J.trainBytes < 16) return ZL_ERROR(srcSize_wrong);
@@ -335,7 +336,8 @@ static size_t zl_train(void* dictBuffer, size_t dictCap, const void* samplesBuff
         J.st = J.statCtx->stream;
         ZlTrainBufs& B = J.B;
         size_t dstBytes = 0;
-        J.dstCap.resize(nb); J.srcPtr.resize(nb); J.dstPtr.resize(nb); J.res.resize(nb);
+        J.dstCap.resize(nb); J.srcPtr.resize(nb); J.dstPtr.resize(nb); J.res.resize(nb); J.statSizes.resize(nb);
+        for (u32 i = 0; i < nb; i++) J.statSizes[i] = sizes[i] < ZL_BLOCKSIZE_MAX ? sizes[i] : ZL_BLOCKSIZE_MAX;
         for (u32 i = 0; i < nb; i++) { J.dstCap[i] = ZSTD_compressBound(sizes[i]) + 32; dstBytes += (J.dstCap[i] + 15) & ~(size_t)15; }
         if (!B.samples.reserve(J.totalBytes + 64) || !B.offsets.reserve(((size_t)nb + 1) * 4) || !B.h.reserve(J.trainBytes * 4 + 64) ||
             !B.freq0.reserve((size_t)4 << f) || !B.freq.reserve((size_t)4 << f) || !B.prev.reserve(J.trainBytes * 2 + 64) ||

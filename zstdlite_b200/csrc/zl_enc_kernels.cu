@@ -215,14 +215,14 @@ __device__ __forceinline__ u32 zl_extend_match(const u32* __restrict__ wbase, u3
 }
 
 // One CTA per block, one warp per SEGMENT of ZL_PARSE_SEG bytes (zl_enc_match.cuh): the greedy walk is a serial chain, so a
-// 128 KiB block is walked as four independent 32 KiB pieces (each starts with an unknown repeat-offset history and clips its
+// 128 KiB block is walked as eight independent 16 KiB pieces (each starts with an unknown repeat-offset history and clips its
 // matches at its end, exactly like blocks do inside a frame) and the pieces are then packed into one record / literal array.
 __global__ void __launch_bounds__(ZL_PARSE_WARPS * 32)
 zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __restrict__ Marena, u32 slotM, u64* __restrict__ recArena,
            u32 slotRec, u8* __restrict__ litArena, u32 slotLit, u32* __restrict__ histArena, ZlEncBlockMeta* __restrict__ metas,
            const ZlEncDictDev* __restrict__ dict, u32 segmented)
 {
-    // segmented == 0: no block of the wave is longer than one segment; a CTA then takes four blocks, one per warp
+    // segmented == 0: no block of the wave is longer than one segment; a CTA then takes ZL_PARSE_WARPS blocks, one per warp
     __shared__ u32 hist[ZL_PARSE_WARPS][256];
     __shared__ u32 segSeq[ZL_PARSE_WARPS], segLit[ZL_PARSE_WARPS], segTail[ZL_PARSE_WARPS];
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
