@@ -131,6 +131,13 @@ size_t zl_compress_batch(ZSTD_CCtx* cctx, const void* const* src, const size_t* 
 size_t zl_compress_split(ZSTD_CCtx* cctx, void* dst, size_t dstCapacity, const void* src, size_t srcSize,
                          size_t frameSize, size_t* frameSizes, int ptrs_are_device);
 
+/* Several GPUs from ONE process (frames are independent: SURVEY.md 8e).  Batches of HOST buffers (zl_decompress_batch / zl_compress_batch, and
+ * ZSTD_decompressDCtx on a multi-frame stream) are cut into contiguous frame ranges of about equal bytes, one per device, each handled by a helper
+ * context on its own host thread; no collective, no peer traffic.  How many GPUs: zl_dctx_set_gpus(n) for a DCtx; num_threads (ZSTD_c_nbWorkers) >= 2 for
+ * a CCtx -- the reference's knob for "more hardware" (src/cctx.c:269-277); 0 / unset: the ZSTDLITE_GPUS environment variable ("all" or a number;
+ * default 1).  Never more than the visible devices; a context's own device is the one current at its first use. */
+size_t zl_dctx_set_gpus(ZSTD_DCtx* dctx, int n);
+
 /* Compression levels: 1, 2, 3 are native (negative "fast" levels run the level-1 engine, 0 means 3).  Levels 4..22 -- the greedy /
  * lazy / optimal parsers of zstd.c:31546-33746 -- are not implemented: ZSTD_CCtx_setParameter(ZSTD_c_compressionLevel, >= 4)
  * returns parameter_unsupported, unless the context (this call) or the process (ZSTDLITE_GPU_LEVEL_FALLBACK=1) opted into running

@@ -67,7 +67,7 @@ def lib():
         "ZSTD_getDictID_fromDict": (C.c_uint, [vp, sz]), "ZDICT_getDictID": (C.c_uint, [vp, sz]),
         "zl_decompress_batch": (sz, [vp, pp, psz, pp, psz, psz, sz, C.c_int]),
         "zl_dctx_set_stream": (sz, [vp, vp]), "zl_dctx_set_profile": (sz, [vp, C.c_int]), "zl_dctx_launch_count": (C.c_ulonglong, [vp]), "zl_dctx_last_kernel_ms": (C.c_double, [vp]),
-        "zl_dctx_last_stage_ms": (C.c_double, [vp, C.c_int]),
+        "zl_dctx_last_stage_ms": (C.c_double, [vp, C.c_int]), "zl_dctx_set_gpus": (sz, [vp, C.c_int]),
         # compression half
         "ZSTD_createCCtx": (vp, []), "ZSTD_freeCCtx": (sz, [vp]), "ZSTD_CCtx_reset": (sz, [vp, C.c_int]),
         "ZSTD_CCtx_setParameter": (sz, [vp, C.c_int, C.c_int]), "ZSTD_CCtx_getParameter": (sz, [vp, C.c_int, C.POINTER(C.c_int)]),
@@ -109,5 +109,5 @@ EXPORTED_SYMBOLS = [
     "ZDICT_trainFromBuffer", "ZDICT_optimizeTrainFromBuffer_cover", "ZDICT_isError", "ZDICT_getErrorName",
     "zl_decompress_batch", "zl_compress_batch", "zl_compress_split", "zl_dctx_set_stream", "zl_dctx_set_profile", "zl_cctx_set_stream",
     "zl_dctx_launch_count", "zl_cctx_launch_count", "zl_dctx_last_kernel_ms", "zl_cctx_last_kernel_ms", "zl_dctx_last_stage_ms", "zl_cctx_last_stage_ms", "zl_backend_string",
-    "zl_cctx_allow_level_fallback", "zl_cctx_engine_level",
+    "zl_cctx_allow_level_fallback", "zl_cctx_engine_level", "zl_dctx_set_gpus",
 ]

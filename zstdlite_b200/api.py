@@ -44,7 +44,9 @@ def _as_buffer(x):
 class zstd_dctx:
     """zstd_dctx(validate_checksum = TRUE, dict = NULL)  (R/cctx.R:72-80, src/dctx.c:110-197)."""
 
-    def __init__(self, validate_checksum=True, dict=None, **unknown):
+    def __init__(self, validate_checksum=True, dict=None, num_gpus=0, **unknown):
+        """num_gpus (extension): GPUs a batch of HOST buffers is spread over, one contiguous frame range per device (0: the
+        ZSTDLITE_GPUS environment variable, default 1).  zstd_cctx takes the reference's own knob for this: num_threads."""
         for k in unknown:
             warnings.warn(f"init_dctx(): Unknown option '{k}'")          # src/dctx.c:171
         L = _lib.lib()
@@ -53,6 +55,8 @@ class zstd_dctx:
             raise ZstdError("init_dctx(): Couldn't initialse memory for 'dctx'")
         self.validate_checksum = bool(validate_checksum)
         _check(L.ZSTD_DCtx_setParameter(self._p, _lib.ZSTD_d_forceIgnoreChecksum, 0 if validate_checksum else 1), "init_dctx()")
+        if num_gpus:
+            _check(L.zl_dctx_set_gpus(self._p, int(num_gpus)), "init_dctx() num_gpus")
         if dict is not None:
             if isinstance(dict, str):
                 with open(dict, "rb") as fh:                              # filename form, src/dctx.c:183-190

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <chrono>
 #include <vector>
+#include <thread>
 #include "../../include/zstdlite_gpu.h"
 #include "zl_host.h"
 #include "zl_plan.h"
@@ -213,6 +214,10 @@ struct ZSTD_DCtx_s {
     ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dNorm, dUnits, dCounters, dLargeIdx, dLb, dLc, dParent, dRemain, dSrc, dDst;
     ZlPinBuf hDescs, hResults, hLargeIdx, hRemain;
     std::vector<cudaEvent_t> sliceDone;    // staged host buffers: the copy back of a slice has landed
+    // devices: the context's own (bound on first use) and, for batches of host buffers, the helpers on the other GPUs of the box
+    int device = -1, gpus = 0;             // gpus: 0 = ZSTDLITE_GPUS (default 1)
+    unsigned long long dictGen = 0, dictGenSeen = 0;
+    std::vector<ZSTD_DCtx_s*> kids;        // one per further device, created on demand, owned by this context
 };
 
 static bool zl_ctx_stream(cudaStream_t* st, bool* own, cudaEvent_t* e0, cudaEvent_t* e1)
@@ -229,6 +234,9 @@ ZL_EXPORT ZSTD_DCtx* ZSTD_createDCtx(void) { return new (std::nothrow) ZSTD_DCtx
 ZL_EXPORT size_t ZSTD_freeDCtx(ZSTD_DCtx* c)
 {
     if (!c) return 0;
+    for (ZSTD_DCtx_s* k : c->kids) ZSTD_freeDCtx(k);
+    c->kids.clear();
+    ZlDeviceGuard guard(c->device);
     ZlDevBuf* bufs[] = {&c->dDictContent, &c->dDict, &c->dDescs, &c->dInfos, &c->dResults, &c->dHdr, &c->dRec, &c->dCk, &c->dLit, &c->dNorm, &c->dUnits, &c->dCounters, &c->dLargeIdx, &c->dLb, &c->dLc, &c->dParent, &c->dRemain, &c->dSrc, &c->dDst};
     for (ZlDevBuf* b : bufs) b->release();
     c->hDescs.release(); c->hResults.release(); c->hLargeIdx.release(); c->hRemain.release();
@@ -288,7 +296,8 @@ ZL_EXPORT double zl_dctx_last_stage_ms(const ZSTD_DCtx* c, int stage) { return s
 // Digest a dictionary (zstd.c:42053-42137 ZSTD_loadDEntropy, 42140 insertDictionary) into ZlDictDev.
 ZL_EXPORT size_t ZSTD_DCtx_loadDictionary(ZSTD_DCtx* c, const void* dict, size_t dictSize)
 {
-    c->hasDict = false; c->dictRaw.clear();
+    ZlDeviceGuard guard(zl_bind_device(&c->device));
+    c->hasDict = false; c->dictRaw.clear(); c->dictGen++;
     if (!dict || !dictSize) return 0;
     c->dictRaw.assign((const u8*)dict, (const u8*)dict + dictSize);
     std::vector<u8> pad(dictSize + 16, 0);
@@ -381,9 +390,54 @@ static bool zl_dctx_lanes(ZSTD_DCtx* c)
 
 static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, const size_t* srcSize, void* const* dst,
                                        const size_t* dstCap, size_t* result, size_t n, int dev, bool worst);
+static size_t zl_decompress_batch_one(ZSTD_DCtx* c, const void* const* src, const size_t* srcSize, void* const* dst,
+                                      const size_t* dstCap, size_t* result, size_t n, int dev);
+// extension: GPUs a context spreads batches of HOST buffers over (0: ZSTDLITE_GPUS, default 1); frames are independent, so the
+// frame list is cut into contiguous ranges of about equal content, one per device, each decoded by a helper context on its own
+// host thread (copies, kernels and staging of the devices overlap); no data moves between the devices
+ZL_EXPORT size_t zl_dctx_set_gpus(ZSTD_DCtx* c, int n) { if (!c || n < 0) return ZL_ERROR(parameter_outOfBound); c->gpus = n; return 0; }
 ZL_EXPORT size_t zl_decompress_batch(ZSTD_DCtx* c, const void* const* src, const size_t* srcSize, void* const* dst,
                                      const size_t* dstCap, size_t* result, size_t n, int dev)
 {
+    if (!c) return ZL_ERROR(GENERIC);
+    const int home = zl_bind_device(&c->device);
+    size_t G = dev ? 1 : (size_t)zl_gpu_count(c->gpus);
+    unsigned long long content = 0;
+    if (G > 1) for (size_t i = 0; i < n; i++) content += dstCap[i];
+    if (G > n / 2) G = n / 2;
+    if (G < 2 || content < ((unsigned long long)64 << 20)) return zl_decompress_batch_one(c, src, srcSize, dst, dstCap, result, n, dev);
+    int ndev = 1;
+    cudaGetDeviceCount(&ndev);
+    while (c->kids.size() + 1 < G) {
+        ZSTD_DCtx_s* k = new (std::nothrow) ZSTD_DCtx_s();
+        if (!k) return ZL_ERROR(memory_allocation);
+        k->device = (home + (int)c->kids.size() + 1) % ndev; k->gpus = 1;
+        c->kids.push_back(k);
+    }
+    const std::vector<size_t> cut = zl_split_ranges(dstCap, n, G);
+    std::vector<size_t> rc(G, 0);
+    auto work = [&](size_t g) {
+        ZSTD_DCtx_s* k = g ? c->kids[g - 1] : c;
+        if (g) {
+            k->forceIgnoreChecksum = c->forceIgnoreChecksum; k->windowLogMax = c->windowLogMax;
+            if (k->dictGenSeen != c->dictGen) { rc[g] = ZSTD_DCtx_loadDictionary(k, c->dictRaw.data(), c->dictRaw.size()); k->dictGenSeen = c->dictGen; if (zl_is_error(rc[g])) return; }
+        }
+        const size_t a = cut[g], cnt = cut[g + 1] - a;
+        rc[g] = cnt ? zl_decompress_batch_one(k, src + a, srcSize + a, dst + a, dstCap + a, result + a, cnt, 0) : 0;
+    };
+    std::vector<std::thread> th;
+    for (size_t g = 1; g < G; g++) th.emplace_back(work, g);
+    work(0);
+    for (std::thread& t : th) t.join();
+    for (size_t g = 1; g < G; g++) { c->launches += c->kids[g - 1]->launches; c->kids[g - 1]->launches = 0; if (c->kids[g - 1]->lastKernelMs > c->lastKernelMs) c->lastKernelMs = c->kids[g - 1]->lastKernelMs; }
+    for (size_t g = 0; g < G; g++) if (zl_is_error(rc[g])) return rc[g];
+    return 0;
+}
+static size_t zl_decompress_batch_one(ZSTD_DCtx* c, const void* const* src, const size_t* srcSize, void* const* dst,
+                                      const size_t* dstCap, size_t* result, size_t n, int dev)
+{
+    ZlDeviceGuard guard(zl_bind_device(&c->device));
+    if (!guard.ok) return ZL_ERROR(GENERIC);
     size_t r = zl_decompress_batch_impl(c, src, srcSize, dst, dstCap, result, n, dev, false);
     if (zl_is_error(r)) return r;
     bool retry = false;

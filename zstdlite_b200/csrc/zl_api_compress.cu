@@ -6,6 +6,7 @@
 #include <new>
 #include <chrono>
 #include "../../include/zstdlite_gpu.h"
+#include <thread>
 #include "zl_host.h"
 #include "zl_enc_dict.h"          // host-side dictionary digest (shared with the CPU emulation in tests/emul)
 
@@ -42,6 +43,11 @@ struct ZSTD_CCtx_s {
     struct { bool valid = false; void* dst = nullptr; const void* src = nullptr; size_t bytes = 0; int slot = 0; } pendIn;   // issued by zl_enc_run once its kernels are queued
     ZlDevBuf dOutStage;
     u32* statsDev = nullptr;               // set by the dictionary trainer: parse only, statistics summed here (zl_dict_train.cuh)
+    // devices: the context's own (bound on first use) and, for batches of host buffers, the helpers on the other GPUs of the box
+    // (num_threads / ZSTD_c_nbWorkers >= 2 asks for that many GPUs; 0 / 1: ZSTDLITE_GPUS, default 1)
+    int device = -1;
+    unsigned long long dictGen = 0, dictGenSeen = 0;
+    std::vector<ZSTD_CCtx_s*> kids;
 };
 
 // __constant__ symbols and function attributes are per device: the encoder's code tables are uploaded once for every device a
@@ -80,6 +86,9 @@ ZL_EXPORT ZSTD_CCtx* ZSTD_createCCtx(void) { return new (std::nothrow) ZSTD_CCtx
 ZL_EXPORT size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
 {
     if (!c) return 0;
+    for (ZSTD_CCtx_s* k : c->kids) ZSTD_freeCCtx(k);
+    c->kids.clear();
+    ZlDeviceGuard guard(c->device);
     ZlDevBuf* bufs[] = {&c->dBlocks, &c->dFrames, &c->dM, &c->dRecs, &c->dLit, &c->dHist, &c->dMetas, &c->dOuts, &c->dPlans, &c->dResults,
                         &c->dXxh, &c->dXxhPtrs, &c->dXxhSizes, &c->dSrc, &c->dDst, &c->dAux,
                         &c->dDict, &c->dDictContent, &c->dDictTabS, &c->dDictTabL};
@@ -153,7 +162,7 @@ ZL_EXPORT size_t ZSTD_CCtx_loadDictionary(ZSTD_CCtx* c, const void* dict, size_t
 {
     c->dictRaw.clear();
     if (dict && dictSize) c->dictRaw.assign((const u8*)dict, (const u8*)dict + dictSize);
-    c->dictDirty = true; c->dictErr = 0;
+    c->dictDirty = true; c->dictErr = 0; c->dictGen++;
     return 0;
 }
 
@@ -348,9 +357,53 @@ static size_t zl_enc_run(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* srcS
     return 0;
 }
 
+static size_t zl_compress_batch_one(ZSTD_CCtx* c, const void* const* src, const size_t* srcSize, void* const* dst, const size_t* dstCap,
+                                    size_t* result, size_t n, int dev);
+// Batches of HOST buffers spread over the GPUs of the box when the context asks for workers (num_threads = ZSTD_c_nbWorkers >= 2 -> that many
+// GPUs) or ZSTDLITE_GPUS says so: contiguous ranges of the frame list of about equal input, one helper context and host thread per device;
+// frames are independent, nothing moves between the devices
 ZL_EXPORT size_t zl_compress_batch(ZSTD_CCtx* c, const void* const* src, const size_t* srcSize, void* const* dst, const size_t* dstCap,
                                    size_t* result, size_t n, int dev)
 {
+    if (!c) return ZL_ERROR(GENERIC);
+    const int home = zl_bind_device(&c->device);
+    size_t G = dev ? 1 : (size_t)zl_gpu_count(c->nbWorkers >= 2 ? c->nbWorkers : 0);
+    unsigned long long bytes = 0;
+    if (G > 1) for (size_t i = 0; i < n; i++) bytes += srcSize[i];
+    if (G > n / 2) G = n / 2;
+    if (G < 2 || bytes < ((unsigned long long)64 << 20) || c->statsDev) return zl_compress_batch_one(c, src, srcSize, dst, dstCap, result, n, dev);
+    int ndev = 1;
+    cudaGetDeviceCount(&ndev);
+    while (c->kids.size() + 1 < G) {
+        ZSTD_CCtx_s* k = new (std::nothrow) ZSTD_CCtx_s();
+        if (!k) return ZL_ERROR(memory_allocation);
+        k->device = (home + (int)c->kids.size() + 1) % ndev;
+        c->kids.push_back(k);
+    }
+    const std::vector<size_t> cut = zl_split_ranges(srcSize, n, G);
+    std::vector<size_t> rc(G, 0);
+    auto work = [&](size_t g) {
+        ZSTD_CCtx_s* k = g ? c->kids[g - 1] : c;
+        if (g) {
+            k->level = c->level; k->checksumFlag = c->checksumFlag; k->levelFallback = c->levelFallback; k->nbWorkers = 0;
+            if (k->dictGenSeen != c->dictGen) { k->dictRaw = c->dictRaw; k->dictDirty = true; k->dictErr = 0; k->dictGenSeen = c->dictGen; }
+        }
+        const size_t a = cut[g], cnt = cut[g + 1] - a;
+        rc[g] = cnt ? zl_compress_batch_one(k, src + a, srcSize + a, dst + a, dstCap + a, result + a, cnt, 0) : 0;
+    };
+    std::vector<std::thread> th;
+    for (size_t g = 1; g < G; g++) th.emplace_back(work, g);
+    work(0);
+    for (std::thread& t : th) t.join();
+    for (size_t g = 1; g < G; g++) { c->launches += c->kids[g - 1]->launches; c->kids[g - 1]->launches = 0; }
+    for (size_t g = 0; g < G; g++) if (zl_is_error(rc[g])) return rc[g];
+    return 0;
+}
+static size_t zl_compress_batch_one(ZSTD_CCtx* c, const void* const* src, const size_t* srcSize, void* const* dst, const size_t* dstCap,
+                                    size_t* result, size_t n, int dev)
+{
+    ZlDeviceGuard guard(zl_bind_device(&c->device));
+    if (!guard.ok) return ZL_ERROR(GENERIC);
     if (!c) return ZL_ERROR(GENERIC);
     if (n == 0) return 0;
     if (n > 0x0FFFFFFFull) return ZL_ERROR(memory_allocation);
@@ -588,6 +641,8 @@ ZL_EXPORT size_t zl_compress_split(ZSTD_CCtx* c, void* dst, size_t dstCap, const
                                    size_t* frameSizes, int dev)
 {
     if (!c || !frameSize) return ZL_ERROR(GENERIC);
+    ZlDeviceGuard guard(zl_bind_device(&c->device));
+    if (!guard.ok) return ZL_ERROR(GENERIC);
     if (!zl_cctx_ready(c)) return ZL_ERROR(memory_allocation);
     cudaStream_t st = c->stream;
     const size_t nf = srcSize ? (srcSize + frameSize - 1) / frameSize : 1;

@@ -138,10 +138,62 @@ static inline bool zl_is_pageable(const void* p)
     return a.type == cudaMemoryTypeUnregistered;
 }
 
-// Pinned staging shared by every context of the process (the reference creates a fresh context per call -- src/raw-file.c:150-189 --
-// and pinning memory costs ~0.3 s per GB, more than the decode it would serve): grow-only, borrowed under a lock for one call.
+// Pinned staging shared by every context of the process, one pool per device (the reference creates a fresh context per call --
+// src/raw-file.c:150-189 -- and pinning memory costs ~0.3 s per GB, more than the decode it would serve): grow-only, borrowed
+// under a lock for one call.
 struct ZlStagePool {
     std::mutex m;
     ZlPinBuf in, out;
-    static ZlStagePool& get() { static ZlStagePool p; return p; }
+    static ZlStagePool& get()
+    {
+        static ZlStagePool pools[64];
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { (void)cudaGetLastError(); dev = 0; }
+        return pools[dev];
+    }
 };
+
+// ---- devices --------------------------------------------------------------------------------------------------------------
+// A context belongs to the device that was current when it was first used; every entry point switches to it and back.
+struct ZlDeviceGuard {
+    int prev = -1; bool ok = true;
+    explicit ZlDeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { (void)cudaGetLastError(); prev = -1; ok = false; return; }
+        if (dev >= 0 && dev != prev) ok = cudaSetDevice(dev) == cudaSuccess;
+        else prev = -1;                                                // nothing to restore
+    }
+    ~ZlDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+static inline int zl_bind_device(int* device)                           // -> the context's device (bound on first use)
+{
+    if (*device < 0 && cudaGetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); *device = 0; }
+    return *device;
+}
+// GPUs a context may spread a batch of host buffers over: `asked` (0: the ZSTDLITE_GPUS environment variable, default 1; "all" or a
+// number), never more than the visible devices
+static inline int zl_gpu_count(int asked)
+{
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess) { (void)cudaGetLastError(); return 1; }
+    if (asked <= 0) {
+        const char* e = getenv("ZSTDLITE_GPUS");
+        asked = !e ? 1 : (!strcmp(e, "all") ? have : atoi(e));
+    }
+    if (asked < 1) asked = 1;
+    return asked < have ? asked : (have > 0 ? have : 1);
+}
+// contiguous ranges of [0, n) of about equal weight: cut[0] = 0 .. cut[parts] = n
+static inline std::vector<size_t> zl_split_ranges(const size_t* weight, size_t n, size_t parts)
+{
+    std::vector<size_t> cut(parts + 1, n);
+    unsigned long long total = 0, acc = 0;
+    for (size_t i = 0; i < n; i++) total += weight[i] + 64;
+    cut[0] = 0;
+    size_t k = 1;
+    for (size_t i = 0; i < n && k < parts; i++) {
+        acc += weight[i] + 64;
+        if (acc * parts >= total * k) cut[k++] = i + 1;
+    }
+    return cut;
+}
