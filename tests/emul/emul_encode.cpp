@@ -60,6 +60,9 @@ static void emul_match(const u8* src, u32 n, const ZlEncParams& P, std::vector<u
     }
 }
 // stage 2: greedy walk -> records, literals, histogram; the block is walked as independent segments of ZL_PARSE_SEG bytes (zl_k_parse)
+struct EmulSeq { u32 ll, ml, off; };                         // explicit form, as ZSTD_Sequence carries it (src/zstd/zstd.h:1501-1530)
+static std::vector<EmulSeq>* g_seqOut = nullptr;             // stage-level tests: the walk's sequences with explicit offsets
+static const EmulSeq* g_seqIn = nullptr; static u32 g_seqInCount = 0;     // stage-level tests: sequences to encode instead of the walk's
 static void emul_parse(const u8* src, u32 n, const std::vector<u32>& M, std::vector<u64>& recs, std::vector<u8>& lit, u32* hist, bool firstBlock,
                        const EmulDict* D)
 {
@@ -100,6 +103,7 @@ static void emul_parse(const u8* src, u32 n, const std::vector<u32>& M, std::vec
             const u32 ll = p - anchor;
             for (u32 k = anchor; k < p; k++) { lit.push_back(src[k]); hist[src[k]]++; }
             const u32 ob = zl_rep_encode(reps, off, ll);
+            if (g_seqOut) g_seqOut->push_back({ll + (firstSeq ? carry : 0u), len, off});
             recs.push_back(zl_enc_rec(ll + (firstSeq ? carry : 0u), len, ob));
             firstSeq = false;
             p += len; anchor = p;
@@ -118,8 +122,24 @@ static u32 emul_block(const u8* src, u32 n, const ZlEncParams& P, const ZlEncCon
     if (n < 7) return 0;                                     // zstd.c:25725
     std::vector<u32> M; std::vector<u64> recs; std::vector<u8> lit;
     static ZlHufSm hs; static ZlSeqEncSm ss; static ZlEncBlockOut o;
+    if (g_seqIn) {
+        // sequences from outside (the reference's ZSTD_generateSequences): only the entropy stage below is ours
+        for (u32 i = 0; i < 256; i++) hs.count[i] = 0;
+        ZlReps reps = {firstBlock ? 1u : 0u, firstBlock ? 4u : 0u, firstBlock ? 8u : 0u};
+        u32 p = 0;
+        for (u32 i = 0; i < g_seqInCount; i++) {
+            const EmulSeq q = g_seqIn[i];
+            for (u32 k = 0; k < q.ll; k++) { lit.push_back(src[p + k]); hs.count[src[p + k]]++; }
+            p += q.ll;
+            if (!q.ml) continue;                             // (a block delimiter: its literals are the last literals)
+            recs.push_back(zl_enc_rec(q.ll, q.ml, zl_rep_encode(reps, q.off, q.ll)));
+            p += q.ml;
+        }
+        for (; p < n; p++) { lit.push_back(src[p]); hs.count[src[p]]++; }
+    } else {
     emul_match(src, n, P, M, D);
     emul_parse(src, n, M, recs, lit, hs.count, firstBlock, D);
+    }
     const u32 nLit = (u32)lit.size(), nbSeq = (u32)recs.size();
     std::vector<u8> litPad(nLit + 16); if (nLit) memcpy(litPad.data(), lit.data(), nLit);
     // literals kernel
@@ -208,4 +228,32 @@ static size_t emul_compress(void* dstv, size_t cap, const void* srcv, size_t siz
     if (frame.size() > cap) return (size_t)0 - 70;
     memcpy(dstv, frame.data(), frame.size());
     return frame.size();
+}
+
+// ---- stage-level entry points (tests/test_stage_level.py) ----------------------------------------------------------------------
+// (a) the emulated match finder + walk of ONE block (<= 128 KiB) -> explicit (litLength, matchLength, offset) triples; returns the count
+extern "C" size_t zl_emul_sequences(const void* srcv, size_t size, int level, unsigned* triples, size_t cap)
+{
+    if (size > ZL_BLOCKSIZE_MAX) return 0;
+    const ZlEncParams P = zl_enc_params(level < 1 ? 1 : (level > 3 ? 3 : level));
+    std::vector<u32> M; std::vector<u64> recs; std::vector<u8> lit; u32 hist[256];
+    std::vector<EmulSeq> out;
+    emul_match((const u8*)srcv, (u32)size, P, M, nullptr);
+    g_seqOut = &out;
+    emul_parse((const u8*)srcv, (u32)size, M, recs, lit, hist, true, nullptr);
+    g_seqOut = nullptr;
+    if (out.size() > cap) return 0;
+    for (size_t i = 0; i < out.size(); i++) { triples[3 * i] = out[i].ll; triples[3 * i + 1] = out[i].ml; triples[3 * i + 2] = out[i].off; }
+    return out.size();
+}
+// (b) ONE block's frame from GIVEN sequences: the product's literal / sequence entropy stage (zl_enc_entropy.cuh) in isolation
+extern "C" size_t zl_emul_encode_sequences(void* dstv, size_t cap, const void* srcv, size_t size, int level, const unsigned* triples, size_t nseq)
+{
+    if (size > ZL_BLOCKSIZE_MAX) return 0;
+    std::vector<EmulSeq> in(nseq);
+    for (size_t i = 0; i < nseq; i++) in[i] = {triples[3 * i], triples[3 * i + 1], triples[3 * i + 2]};
+    g_seqIn = in.data(); g_seqInCount = (u32)nseq;
+    const size_t r = emul_compress(dstv, cap, srcv, size, level, 0, 0, nullptr);
+    g_seqIn = nullptr; g_seqInCount = 0;
+    return r;
 }

@@ -20,6 +20,10 @@ def lib():
         L.zl_emul_compress_frame.restype = C.c_size_t
         L.zl_emul_compress_frame_dict.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_size_t]
         L.zl_emul_compress_frame_dict.restype = C.c_size_t
+        L.zl_emul_sequences.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]
+        L.zl_emul_sequences.restype = C.c_size_t
+        L.zl_emul_encode_sequences.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]
+        L.zl_emul_encode_sequences.restype = C.c_size_t
         _lib = L
     return _lib
 
@@ -43,6 +47,28 @@ def compress_frame(data, level=3, checksum=False, xxh32=0, dict=None):
         r = lib().zl_emul_compress_frame_dict(dst, cap, data, len(data), level, 1 if checksum else 0, xxh32, bytes(dict), len(dict))
     else:
         r = lib().zl_emul_compress_frame(dst, cap, data, len(data), level, 1 if checksum else 0, xxh32)
+    if r > 2**63:
+        return ("ERR", 2**64 - r)
+    return dst.raw[:r]
+
+
+def sequences(data, level=3):
+    """the emulated match finder + greedy walk on ONE block -> numpy array [nseq, 3] of (litLength, matchLength, offset)"""
+    import numpy as np
+    data = bytes(data)
+    out = np.zeros((len(data) // 3 + 16, 3), dtype=np.uint32)
+    n = lib().zl_emul_sequences(data, len(data), level, out.ctypes.data, out.shape[0])
+    return out[:n].copy()
+
+
+def encode_sequences(data, seqs, level=3):
+    """ONE block's frame from the given (litLength, matchLength, offset) rows through the product's entropy stage only"""
+    import numpy as np
+    data = bytes(data)
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint32)
+    cap = len(data) + (len(data) >> 7) + 1024
+    dst = C.create_string_buffer(cap)
+    r = lib().zl_emul_encode_sequences(dst, cap, data, len(data), level, seqs.ctypes.data, seqs.shape[0])
     if r > 2**63:
         return ("ERR", 2**64 - r)
     return dst.raw[:r]

@@ -301,3 +301,20 @@ def test_streaming_entry_points_interoperate_with_one_shot(z, ref):
     ib = C.create_string_buffer(b"abc", 3); ob = C.create_string_buffer(100)
     r = L.ZSTD_compressStream2(c._p, C.byref(z._lib.OutBuffer(C.cast(ob, C.c_void_p), 100, 0)), C.byref(z._lib.InBuffer(C.cast(ib, C.c_void_p), 3, 0)), 2)
     assert z.is_error(r) and z.error_name(r) == "Src size is incorrect"
+
+
+@pytest.mark.parametrize("family,size,bar", [("rdf", 2 << 20, 1.03), ("text", 2 << 20, 1.03), ("text", 16 << 20, 1.03)])
+def test_large_single_frame_ratio_against_libzstd(z, ref, family, size, bar):
+    """ZSTD_compress2 of ONE large buffer (what zstd_compress / zstd_serialize of a real object calls), level 3, against libzstd on the same
+    buffer.  libzstd uses a 2 MB window there (zstd.c:29527); this compressor's blocks are independent with offsets <= 64 KiB (DESIGN.md,
+    "known limit").  Columnar payloads are within the 3 % bar (better, in fact); TEXT-like payloads are not -- a known, documented gap that
+    this test keeps visible: it is an expected failure until matches reach beyond a block ("window beyond one block")."""
+    from zstdlite_b200 import corpus
+    d = corpus.make(family, size, 21).tobytes()
+    ours = z.zstd_compress(d, level=3)
+    assert ref.decompress(ours) == d                                       # always: valid, round-trips through libzstd
+    theirs = ref.compress(d, 3)
+    ratio = len(ours) / len(theirs)
+    if family == "text" and ratio > bar:
+        pytest.xfail(f"{family} {size >> 20} MiB: {ratio:.3f}x libzstd's size (bar {bar}): no match crosses a 128 KiB block yet")
+    assert ratio <= bar, (family, size, ratio)

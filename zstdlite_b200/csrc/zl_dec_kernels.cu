@@ -7,6 +7,7 @@
 #include "zl_dec_large.cuh"
 #include "zl_launch.h"
 #include <mutex>
+#include <stdlib.h>
 
 __constant__ ZlConstTables c_tables = {
     ZL_LL_BASE_INIT, ZL_ML_BASE_INIT, ZL_LL_BITS_INIT, ZL_ML_BITS_INIT,
@@ -409,7 +410,10 @@ cudaError_t zl_decode_grid_limits(u32* litCtas, u32* seqCtas)
         if (e != cudaSuccess) return e;
         D.litPerSm = lit < 1 ? 1 : lit; D.seqPerSm = seq < 1 ? 1 : seq; D.sms = sms;
     }
-    *litCtas = (u32)(D.sms * D.litPerSm); *seqCtas = (u32)(D.sms * D.seqPerSm);
+    // (development switches: fewer resident CTAs of the shared-memory-bound entropy kernels leave room for execute CTAs beside them)
+    static const int capLit = getenv("ZL_LIT_CTAS_PER_SM") ? atoi(getenv("ZL_LIT_CTAS_PER_SM")) : 0, capSeq = getenv("ZL_SEQ_CTAS_PER_SM") ? atoi(getenv("ZL_SEQ_CTAS_PER_SM")) : 0;
+    const int lit = capLit > 0 && capLit < D.litPerSm ? capLit : D.litPerSm, seq = capSeq > 0 && capSeq < D.seqPerSm ? capSeq : D.seqPerSm;
+    *litCtas = (u32)(D.sms * lit); *seqCtas = (u32)(D.sms * seq);
     return cudaSuccess;
 }
 
