@@ -5,6 +5,7 @@
 // require the CUDA path to produce byte-identical frames.  Never linked into the product.
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 #include "../../zstdlite_b200/csrc/zl_enc_entropy.cuh"
 #include "../../zstdlite_b200/csrc/zl_enc_match.cuh"
 #include "../../zstdlite_b200/csrc/zl_enc_dict.h"
@@ -34,6 +35,9 @@ static u32 dict_match(const EmulDict& D, const std::vector<u32>& tab, u32 h, con
     *off = p + room;
     return l;
 }
+// far candidates (frames of more than one block): the frame-wide table of EARLIEST occurrences of every 8-byte hash (zl_k_far_build)
+struct EmulFar { const u8* frame = nullptr; u32 frameSize = 0, blockOff = 0, log = 0; const u32* tab = nullptr; };
+static EmulFar g_far;
 // stage 1: M[p] for every position
 static void emul_match(const u8* src, u32 n, const ZlEncParams& P, std::vector<u32>& M, const EmulDict* D)
 {
@@ -55,6 +59,16 @@ static void emul_match(const u8* src, u32 n, const ZlEncParams& P, std::vector<u
             u32 dOff = 0;
             if (P.hlogL) { const u32 l = dict_match(*D, D->tabL, zl_hash_long(lo, hi, D->d.hlogL), src, n, p, P.mls, &dOff); if (l > bestLen) { bestLen = l; bestOff = dOff; } }
             if (bestLen < lim) { const u32 l = dict_match(*D, D->tabS, zl_hash_short(lo, hi, P.mls, D->d.hlogS), src, n, p, P.mls, &dOff); if (l > bestLen) { bestLen = l; bestOff = dOff; } }
+        }
+        if (g_far.tab) {                                     // zl_far_candidate (zl_enc_match.cuh)
+            const u32 pos = g_far.blockOff + p;
+            const u32 q = g_far.tab[zl_hash_long(lo, hi, g_far.log)];
+            if (q < pos && pos - q < ZL_FAR_MAX_OFF && pos - q > 65535u) {
+                u32 limF = n - p; if (limF > ZL_M_CAP) limF = ZL_M_CAP;
+                u32 l = 0;
+                while (l < limF && g_far.frame[q + l] == src[p + l]) l++;
+                if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; }
+            }
         }
         M[p] = bestLen ? ((bestOff << 8) | bestLen) : 0;
     }
@@ -209,7 +223,19 @@ static size_t emul_compress(void* dstv, size_t cap, const void* srcv, size_t siz
     const ZlEncParams P = zl_enc_params(level);
     const u8* src = (const u8*)srcv;
     std::vector<u8> frame(32);
-    frame.resize(zl_write_frame_header(frame.data(), size, D ? D->d.dictID : 0u, checksumFlag ? 1u : 0u));
+    // far candidates (zl_enc_match.cuh): frames of more than one block get the table of earliest occurrences
+    const bool far = size > ZL_BLOCKSIZE_MAX && size < 0xFFFFFF00ull && !getenv("ZL_EMUL_NOFAR");
+    std::vector<u32> farTab;
+    if (far) {
+        const u32 flog = zl_far_log(size);
+        farTab.assign((size_t)1 << flog, 0xFFFFFFFFu);
+        for (size_t q = 0; q + 8 <= size; q++) {
+            const u32 h = zl_hash_long(rd32(src + q), rd32(src + q + 4), flog);
+            if ((u32)q < farTab[h]) farTab[h] = (u32)q;
+        }
+        g_far.frame = src; g_far.frameSize = (u32)size; g_far.log = flog; g_far.tab = farTab.data();
+    }
+    frame.resize(zl_write_frame_header(frame.data(), size, D ? D->d.dictID : 0u, checksumFlag ? 1u : 0u, far));
     size_t pos = 0; bool first = true;
     std::vector<u8> payload;
     do {
@@ -218,12 +244,14 @@ static size_t emul_compress(void* dstv, size_t cap, const void* srcv, size_t siz
         u8 bh[3];
         // (no RLE blocks: the reference only emits them for non-first blocks under 25 bytes of output, zstd.c:26873-26884;
         //  a run compresses to ~10 bytes as one sequence, so the product skips the special case)
+        g_far.blockOff = (u32)pos;
         u32 ps = emul_block(src + pos, n, P, K, payload, first, D);
-        if (ps == 0xFFFFFFFFu) return (size_t)0 - 1;
+        if (ps == 0xFFFFFFFFu) { g_far = EmulFar(); return (size_t)0 - 1; }
         if (!ps) { zl_write_block_header(bh, last, 0, n); frame.insert(frame.end(), bh, bh + 3); frame.insert(frame.end(), src + pos, src + pos + n); }
         else { zl_write_block_header(bh, last, 2, ps); frame.insert(frame.end(), bh, bh + 3); frame.insert(frame.end(), payload.begin(), payload.end()); }
         pos += n; first = false;
     } while (pos < size);
+    g_far = EmulFar();
     if (checksumFlag) for (u32 i = 0; i < 4; i++) frame.push_back((u8)(xxh32 >> (8 * i)));
     if (frame.size() > cap) return (size_t)0 - 70;
     memcpy(dstv, frame.data(), frame.size());

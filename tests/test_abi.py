@@ -78,7 +78,8 @@ def test_context_parameters_round_trip():
     assert L.ZSTD_getErrorName(L.ZSTD_CCtx_setParameter(c._p, 100, 4)) == b"Unsupported parameter" and c.settings()["level"] == 2
     # ... unless the caller opts into the level-3 engine for them; the label stays what was set, the engine is reported beside it
     f = z.zstd_cctx(level=99, level_fallback=True)
-    assert f.settings()["level"] == 22 and L.zl_cctx_engine_level(f._p) == 3 and L.zl_cctx_engine_level(z.zstd_cctx(level=-3)._p) == 1
+    fast = z.zstd_cctx(level=-3)
+    assert f.settings()["level"] == 22 and L.zl_cctx_engine_level(f._p) == 3 and L.zl_cctx_engine_level(fast._p) == 1
     assert z.zstd_cctx().settings() == {"level": 3, "num_threads": 0, "include_checksum": 0}
     assert L.ZSTD_isError(L.ZSTD_CCtx_setParameter(c._p, 201, 7))                    # checksumFlag out of bounds
     assert L.ZSTD_isError(L.ZSTD_CCtx_setParameter(c._p, 12345, 1))                  # unknown parameter

@@ -80,8 +80,12 @@ def test_one_shot_api_like_the_reference_tests(z, ref):
         z.zstd_decompress(bytes(bad))
     assert z.zstd_compress("héllo wörld" * 50) and z.zstd_decompress(z.zstd_compress("héllo wörld" * 50), type="string") == "héllo wörld" * 50
     assert z.zstd_cctx(level=1, num_threads=3, include_checksum=True).settings() == {"level": 1, "num_threads": 3, "include_checksum": 1}
-    for lvl in (-5, 0, 9, 22):                        # outside 1..3: nearest engine, still a valid frame
+    for lvl in (-5, 0):                               # fast levels run the level-1 engine, 0 is the default: valid frames
         assert ref.decompress(z.zstd_compress(d[:50000], level=lvl)) == d[:50000]
+    for lvl in (9, 22):                               # levels >= 4: refused, or -- opted in -- the level-3 engine's bytes under the caller's label
+        with pytest.raises(z.ZstdError, match="Bad compression level"):
+            z.zstd_compress(d[:50000], level=lvl)
+        assert z.zstd_compress(d[:50000], cctx=z.zstd_cctx(level=lvl, level_fallback=True)) == z.zstd_compress(d[:50000], level=3)
 
 
 def test_destination_too_small(z):
@@ -124,7 +128,8 @@ def test_compress_split_is_a_standard_multi_frame_stream(z, ref):
     blob = dst.raw[:r]
     assert ref.DCtx().decompress(blob, cap=len(d), all_frames=True) == d
     out = C.create_string_buffer(len(d))
-    rr = L.ZSTD_decompressDCtx(z.zstd_dctx()._p, out, len(d), blob, len(blob))
+    dctx = z.zstd_dctx()                                       # (kept alive: a temporary would be finalised before the call runs)
+    rr = L.ZSTD_decompressDCtx(dctx._p, out, len(d), blob, len(blob))
     assert rr == len(d) and out.raw == d
 
 

@@ -31,7 +31,7 @@ struct ZSTD_CCtx_s {
     cudaEvent_t stageEv[ZL_ENC_STAGES + 1] = {};
     double lastKernelMs = 0.0, lastStageMs[ZL_ENC_STAGES] = {};
     unsigned long long launches = 0;
-    ZlDevBuf dBlocks, dFrames, dM, dRecs, dLit, dHist, dMetas, dOuts, dPlans, dResults, dXxh, dXxhPtrs, dXxhSizes, dSrc, dDst, dAux;
+    ZlDevBuf dBlocks, dFrames, dM, dRecs, dLit, dHist, dMetas, dOuts, dPlans, dResults, dXxh, dXxhPtrs, dXxhSizes, dSrc, dDst, dAux, dFar;
     ZlPinBuf hBlocks, hFrames, hResults, hAux;
     // streaming session (ZSTD_compressStream2): input accumulated on the host until ZSTD_e_end, then one frame is produced
     std::vector<u8> sIn, sOut;
@@ -90,7 +90,7 @@ ZL_EXPORT size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
     c->kids.clear();
     ZlDeviceGuard guard(c->device);
     ZlDevBuf* bufs[] = {&c->dBlocks, &c->dFrames, &c->dM, &c->dRecs, &c->dLit, &c->dHist, &c->dMetas, &c->dOuts, &c->dPlans, &c->dResults,
-                        &c->dXxh, &c->dXxhPtrs, &c->dXxhSizes, &c->dSrc, &c->dDst, &c->dAux,
+                        &c->dXxh, &c->dXxhPtrs, &c->dXxhSizes, &c->dSrc, &c->dDst, &c->dAux, &c->dFar,
                         &c->dDict, &c->dDictContent, &c->dDictTabS, &c->dDictTabL};
     for (ZlDevBuf* b : bufs) b->release();
     c->hBlocks.release(); c->hFrames.release(); c->hResults.release(); c->hAux.release();
@@ -255,15 +255,22 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
         return ZL_ERROR(memory_allocation);
     ZlEncBlock* hb = c->hBlocks.as<ZlEncBlock>();
     ZlEncFrame* hf = c->hFrames.as<ZlEncFrame>();
-    size_t bi = 0;
+    size_t bi = 0, farEntries = 0;
+    static const bool farOff_disabled = getenv("ZL_ENC_NOFAR") != nullptr;      // (development switch)
     for (size_t i = f0; i < f1; i++) {
         ZlEncFrame& f = hf[i - f0];
         memset(&f, 0, sizeof(f));
         const size_t s = srcSize[i];
         f.dst = ddst[i]; f.dstCap = dstCap[i]; f.firstBlock = (u32)bi; f.checksumFlag = (u32)c->checksumFlag;
-        f.hdrSize = zl_write_frame_header(f.hdr, s, dict ? c->dictID : 0u, (u32)c->checksumFlag);
         const size_t nblk = s ? (s + ZL_BLOCKSIZE_MAX - 1) / ZL_BLOCKSIZE_MAX : 1;
         f.nblocks = (u32)nblk;
+        // far candidates (zl_enc_match.cuh): a frame of several blocks gets a frame-wide table, while the wave's tables fit 1 GiB
+        bool far = false;
+        if (nblk > 1 && s < 0xFFFFFF00ull && !farOff_disabled) {
+            const u32 flog = zl_far_log(s);
+            if (farEntries + ((size_t)1 << flog) <= ((size_t)1 << 28)) { f.pad = (u64)farEntries | ((u64)flog << 56); farEntries += (size_t)1 << flog; far = true; }
+        }
+        f.hdrSize = zl_write_frame_header(f.hdr, s, dict ? c->dictID : 0u, (u32)c->checksumFlag, far);
         for (size_t k = 0; k < nblk; k++) {
             ZlEncBlock& b = hb[bi++];
             b.src = dsrc[i] + k * ZL_BLOCKSIZE_MAX;
@@ -271,8 +278,12 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
             b.srcSize = (u32)(rem < ZL_BLOCKSIZE_MAX ? rem : ZL_BLOCKSIZE_MAX);
             b.frame = (u32)(i - f0);
             b.flags = (k == 0 ? ZL_BLK_FIRST : 0u) | (k + 1 == nblk ? ZL_BLK_LAST : 0u);
-            b.pad = 0;
+            b.pad = (u32)(k * ZL_BLOCKSIZE_MAX);
         }
+    }
+    if (farEntries) {
+        if (!c->dFar.reserve(farEntries * 4)) return ZL_ERROR(memory_allocation);
+        cudaMemsetAsync(c->dFar.p, 0xFF, farEntries * 4, st);
     }
     cudaMemcpyAsync(c->dBlocks.p, hb, nb * sizeof(ZlEncBlock), cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(c->dFrames.p, hf, nf * sizeof(ZlEncFrame), cudaMemcpyHostToDevice, st);
@@ -295,11 +306,12 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
     L.M = c->dM.as<u32>(); L.slotM = slotM; L.recs = c->dRecs.as<u64>(); L.slotRec = slotRec; L.lit = c->dLit.as<u8>(); L.slotLit = slotLit;
     L.hist = c->dHist.as<u32>(); L.metas = c->dMetas.as<ZlEncBlockMeta>(); L.outs = c->dOuts.as<ZlEncBlockOut>(); L.plans = c->dPlans.as<ZlEncBlockPlan>();
     L.streamCapWords = streamCapWords; L.streamWordsPerBlock = streamWordsPerBlock; L.seqCapWords = seqCapWords;
+    L.far = farEntries ? c->dFar.as<u32>() : nullptr;
     L.results = c->dResults.as<u64>() + f0; L.xxh = xxh; L.stageEv = timeIt ? c->stageEv : nullptr; L.stats = c->statsDev; L.maxBlock = maxBlock;
     static const int sideMode = getenv("ZL_ENC_SIDE") ? atoi(getenv("ZL_ENC_SIDE")) : 2;       // (development: 0 off, 1 few blocks, 2 always; measured +3..4% on 4,096 blocks, +13% on 128)
     if (sideMode == 2 || (sideMode == 1 && nb <= 1024)) { L.side = c->side; L.sideFork = c->sideFork; L.sideJoin = c->sideJoin; }
     cudaError_t e = zl_launch_encode(L, st);
-    c->launches += 6;
+    c->launches += 6 + (farEntries ? 1 : 0);
     if (e != cudaSuccess) { fprintf(stderr, "zstdlite_gpu: kernel launch failed: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
     return 0;
 }

@@ -86,9 +86,55 @@ __device__ __forceinline__ u32 zl_dict_match(const ZlEncDictDev& D, const u32* _
     return len;
 }
 
+// ---------------------------------------------------------------------------------------------- E0: far table (frames of > 1 block)
+// zl_enc_match.cuh, "far candidates": tab[hash8(position)] = min(position) over the whole frame.  ZlEncFrame::pad = offset of the frame's
+// table in the far arena (u32 units, low 56 bits) | log2 entries << 56 (0: the frame has no table); ZlEncBlock::pad = the block's offset
+// inside its frame.  CTA per block; the 8 bytes of a position may reach into the next block (the frame is contiguous).
+#define ZL_FAR_OFF_MASK 0x00FFFFFFFFFFFFFFull
+__global__ void __launch_bounds__(256)
+zl_k_far_build(const ZlEncBlock* __restrict__ blocks, const ZlEncFrame* __restrict__ frames, u32* __restrict__ farArena)
+{
+    const ZlEncBlock b = blocks[blockIdx.x];
+    const u64 fpad = frames[b.frame].pad;
+    const u32 flog = (u32)(fpad >> 56);
+    if (!flog || b.srcSize == 0) return;
+    u32* __restrict__ tab = farArena + (fpad & ZL_FAR_OFF_MASK);
+    const u32 n = b.srcSize;
+    const u32 bias = (u32)(((size_t)b.src) & 3);
+    const u32* __restrict__ wbase = reinterpret_cast<const u32*>(b.src - bias);
+    const bool last = (b.flags & ZL_BLK_LAST) != 0;
+    const u32 npos = last ? (n >= 8 ? n - 7 : 0u) : n;                      // positions whose 8 bytes lie inside the frame
+    const u32 lastWord = (bias + (last ? n - 1 : n + 7)) >> 2;
+    for (u32 p = threadIdx.x; p < npos; p += 256) {
+        u32 lo, hi;
+        zl_ld8(wbase, bias + p, lastWord, lo, hi);
+        atomicMin(tab + zl_hash_long(lo, hi, flog), b.pad + p);
+    }
+}
+// length of the match between block position p (bytes lo:hi, words of the block) and FRAME position q (words of the frame), <= lim
+__device__ __forceinline__ u32 zl_match_len_far(const u32* __restrict__ wbase, u32 bias, u32 lastWord, u32 p, const u32* __restrict__ fw, u32 fbias, u32 q,
+                                                u32 lo, u32 hi, u32 lim)
+{
+    u32 blo, bhi;
+    zl_ld8(fw, fbias + q, 0xFFFFFFFFu, blo, bhi);
+    u32 len = zl_common8(lo, hi, blo, bhi);
+    if (len == 8) {
+        for (u32 k = 8; k < lim; k += 8) {
+            u32 alo, ahi;
+            zl_ld8(wbase, bias + p + k, lastWord, alo, ahi);
+            zl_ld8(fw, fbias + q + k, 0xFFFFFFFFu, blo, bhi);
+            const u32 c = zl_common8(alo, ahi, blo, bhi);
+            len += c;
+            if (c < 8) break;
+        }
+    }
+    return len < lim ? len : lim;
+}
+
 template <bool kLong, bool kDict>
 __global__ void __launch_bounds__(ZL_MATCH_WARPS * 32)
-zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 slotM, ZlEncParams P, const ZlEncDictDev* __restrict__ dict)
+zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 slotM, ZlEncParams P, const ZlEncDictDev* __restrict__ dict,
+           const ZlEncFrame* __restrict__ frames, const u32* __restrict__ farArena)
 {
     extern __shared__ __align__(16) u8 smraw[];
     u16* tabS = reinterpret_cast<u16*>(smraw);
@@ -108,6 +154,13 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
     const u32 lastWord = (bias + n - 1) >> 2;
     const u32 ngroups = (n + 31) >> 5;
     const u32 ltMask = (1u << lane) - 1;
+    // far candidates (frames of more than one block): the frame-wide table of earliest occurrences, read through the frame's own words
+    const u64 fpad = farArena ? frames[b.frame].pad : 0ull;
+    const u32 flog = (u32)(fpad >> 56);
+    const u32* __restrict__ ftab = farArena + (fpad & ZL_FAR_OFF_MASK);
+    const u8* fbase = b.src - b.pad;
+    const u32 fbias = (u32)(((size_t)fbase) & 3);
+    const u32* __restrict__ fw = reinterpret_cast<const u32*>(fbase - fbias);
     // Each warp takes TWO consecutive 32-position groups per turn (64 positions): their loads and verifications overlap,
     // and the table token is passed half as often.
     const u32 npairs = (ngroups + 1) >> 1;
@@ -182,6 +235,13 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
                     if (bestLen < lim) {
                         const u32 l = zl_dict_match(*dict, dict->tabS, zl_hash_short(lo[h], hi[h], P.mls, dict->hlogS), wbase, bias, lastWord, p, lo[h], hi[h], lim, P.mls, dOff);
                         if (l > bestLen) { bestLen = l; bestOff = dOff; }
+                    }
+                }
+                if (flog) {
+                    const u32 pos = b.pad + p, q = __ldg(ftab + zl_hash_long(lo[h], hi[h], flog));
+                    if (q < pos && pos - q < ZL_FAR_MAX_OFF && pos - q > 65535u) {
+                        const u32 l = zl_match_len_far(wbase, bias, lastWord, p, fw, fbias, q, lo[h], hi[h], lim);
+                        if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; }
                     }
                 }
                 if (bestLen) m = (bestOff << 8) | bestLen;
@@ -689,13 +749,14 @@ cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st)
     if (e != cudaSuccess) return e;
     const u32 nb = L.nblocks;
     if (ev) cudaEventRecord(ev[0], st);
+    if (nb && L.far) zl_k_far_build<<<nb, 256, 0, st>>>(L.blocks, L.frames, L.far);
     if (nb) {
         if (L.params.hlogL) {
-            if (useDict) zl_k_match<true, true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, L.dict);
-            else zl_k_match<true, false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, nullptr);
+            if (useDict) zl_k_match<true, true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, L.dict, L.frames, L.far);
+            else zl_k_match<true, false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, nullptr, L.frames, L.far);
         } else {
-            if (useDict) zl_k_match<false, true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, L.dict);
-            else zl_k_match<false, false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, nullptr);
+            if (useDict) zl_k_match<false, true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, L.dict, L.frames, L.far);
+            else zl_k_match<false, false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, nullptr, L.frames, L.far);
         }
     }
     if (ev) cudaEventRecord(ev[1], st);

@@ -120,7 +120,7 @@ struct ZlEncBlock {          // one per block of <= 128 KiB (24 B)
     u32 srcSize;
     u32 frame;               // index into the frame array
     u32 flags;               // ZL_BLK_FIRST / ZL_BLK_LAST within its frame
-    u32 pad;
+    u32 pad;                 // offset of the block inside its frame (far candidates)
 };
 struct ZlEncFrame {          // one per frame (64 B)
     u8* dst;                 // device pointer to the frame's output
@@ -128,7 +128,7 @@ struct ZlEncFrame {          // one per frame (64 B)
     u32 firstBlock, nblocks;
     u32 hdrSize, checksumFlag;
     u8 hdr[24];              // frame header bytes, prepared on the host (zl_write_frame_header)
-    u64 pad;
+    u64 pad;                 // far-candidate table: offset in the far arena (u32 units, low 56 bits) | log2 entries << 56; 0 = none
 };
 struct ZlEncBlockMeta { u32 nseq, nlit; };
 struct ZlEncBlockPlan { u64 dstOff; u32 type, size; };     // offset inside the frame's output, block type, payload size
@@ -152,6 +152,7 @@ struct ZlEncodeLaunch {
     cudaStream_t side = nullptr; cudaEvent_t sideFork = nullptr, sideJoin = nullptr;   // optional: sequence coding next to literal coding
     u32 maxBlock = ZL_BLOCKSIZE_MAX;   // largest block of the wave (the parse kernel walks blocks of more than one segment with a CTA each)
     u32* stats = nullptr;              // dictionary training: sum literal / code statistics here after the parse and stop (zl_dict_train.cuh)
+    u32* far = nullptr;                // far-candidate tables of the wave's multi-block frames (zl_enc_match.cuh), preset to 0xFF; null: none
 };
 cudaError_t zl_enc_upload_const();
 size_t zl_enc_match_smem(const ZlEncParams& P);
