@@ -508,7 +508,11 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         for (size_t i = a; i < b; i++) tmpOrder[cnt[4095 - (srcSize[order[i]] >> keyShift)]++] = order[i];
         std::copy(tmpOrder.begin(), tmpOrder.end(), order.begin() + (ptrdiff_t)a);
     };
-    if (dev) sortRange(0, n);
+    static const bool sortOff = getenv("ZL_DEC_NOSORT") != nullptr;               // (development switch)
+    // (batches of small frames -- config 3's objects of a few hundred bytes -- are not sorted: the sort and the scattered access it causes in the
+    //  loops below cost the host 0.5 ms per 1e5 frames, the balance it buys the kernels 0.08 ms)
+    if (dev && !sortOff && maxSrc > 4096) sortRange(0, n);
+    const double tSort = hostMs();
     std::vector<size_t> cut(nslices + 1, n);
     {
         cut[0] = 0;
@@ -561,27 +565,52 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
             srunOf[i] = (u32)sr; drunOf[i] = (u32)dr;
         }
     }
+    // Descriptors.  Pass 1 only adds up the arenas (and the sums at every slice start); the 80-byte descriptors of a slice are written
+    // and uploaded right before the slice is launched, so that the device starts after 1/8 of the host work and the rest of it
+    // hides behind the kernels (config 3's 1e5 small frames: 8 MB of descriptors, 1.0 of 2.4 ms spent before the first launch).
+    // Batches with large frames (their index is uploaded up front) write everything first, as before.
+    static const bool midOff = getenv("ZL_DEC_NOMID") != nullptr;                 // (development switch)
+    auto isLarge = [&](u32 cap) { return cap >= ZL_LARGE_FRAME_BYTES || (!midOff && n <= 16 && cap > 2 * ZL_BLOCKSIZE_MAX); };
+    struct Sums { u64 lit, rec, hdr, par; };
+    std::vector<Sums> sliceBase(nslices + 1);
     u64 lit = 0, rec = 0, hdr = 0, par = 0;
     size_t nLargeTotal = 0;
-    for (size_t pos = 0; pos < n; pos++) {
-        const size_t i = order[pos];
-        ZlFrameDesc& d = hd[pos];
-        if (dev) { d.src = (const u8*)src[i]; d.dst = (u8*)dst[i]; }
-        else {
-            const ZlRun& rs = sruns[srunOf[i]]; const ZlRun& rd = druns[drunOf[i]];
-            d.src = c->dSrc.as<u8>() + rs.devOff + ((const u8*)src[i] - rs.hbase);
-            d.dst = c->dDst.as<u8>() + rd.devOff + ((const u8*)dst[i] - rd.hbase);
+    {
+        size_t k = 0;
+        for (size_t pos = 0; pos < n; pos++) {
+            while (k < nslices && pos == cut[k]) sliceBase[k++] = {lit, rec, hdr, par};
+            const size_t i = order[pos];
+            u32 litCap, recCap, hdrCap;
+            zl_plan_frame((u32)srcSize[i], (u32)dstCap[i], worst, &litCap, &recCap, &hdrCap);
+            if (isLarge((u32)dstCap[i])) { par += ((u64)dstCap[i] + 3) & ~3ull; nLargeTotal++; }
+            lit += ((u64)litCap + 15) & ~15ull; rec += recCap; hdr += hdrCap;
         }
-        d.srcSize = (u32)srcSize[i]; d.dstCap = (u32)dstCap[i];
-        zl_plan_frame(d.srcSize, d.dstCap, worst, &d.litCap, &d.recCap, &d.hdrCap);
-        d.litBase = lit; d.recBase = rec; d.hdrBase = hdr; d.parBase = par;
-        // block-parallel execute path (zl_dec_large.cuh): frames of >= 1 MiB, and in batches of a few frames -- where a warp walking
-        // a frame block after block is the whole critical path -- every frame of more than two blocks
-        static const bool midOff = getenv("ZL_DEC_NOMID") != nullptr;             // (development switch)
-        d.large = (d.dstCap >= ZL_LARGE_FRAME_BYTES || (!midOff && n <= 16 && d.dstCap > 2 * ZL_BLOCKSIZE_MAX)) ? 1u : 0u;
-        if (d.large) { par += ((u64)d.dstCap + 3) & ~3ull; nLargeTotal++; }
-        lit += ((u64)d.litCap + 15) & ~15ull; rec += d.recCap; hdr += d.hdrCap;
+        while (k <= nslices) sliceBase[k++] = {lit, rec, hdr, par};
     }
+    auto fillDescs = [&](size_t a, size_t b, Sums s) {
+        for (size_t pos = a; pos < b; pos++) {
+            const size_t i = order[pos];
+            ZlFrameDesc& d = hd[pos];
+            if (dev) { d.src = (const u8*)src[i]; d.dst = (u8*)dst[i]; }
+            else {
+                const ZlRun& rs = sruns[srunOf[i]]; const ZlRun& rd = druns[drunOf[i]];
+                d.src = c->dSrc.as<u8>() + rs.devOff + ((const u8*)src[i] - rs.hbase);
+                d.dst = c->dDst.as<u8>() + rd.devOff + ((const u8*)dst[i] - rd.hbase);
+            }
+            d.srcSize = (u32)srcSize[i]; d.dstCap = (u32)dstCap[i];
+            zl_plan_frame(d.srcSize, d.dstCap, worst, &d.litCap, &d.recCap, &d.hdrCap);
+            d.litBase = s.lit; d.recBase = s.rec; d.hdrBase = s.hdr; d.parBase = s.par;
+            // block-parallel execute path (zl_dec_large.cuh): frames of >= 1 MiB, and in batches of a few frames -- where a warp walking
+            // a frame block after block is the whole critical path -- every frame of more than two blocks
+            d.large = isLarge(d.dstCap) ? 1u : 0u;
+            if (d.large) s.par += ((u64)d.dstCap + 3) & ~3ull;
+            s.lit += ((u64)d.litCap + 15) & ~15ull; s.rec += d.recCap; s.hdr += d.hdrCap;
+        }
+    };
+    const double tPass1 = hostMs();
+    static const bool lazyOff = getenv("ZL_DEC_NOLAZY") != nullptr;                // (development switch)
+    const bool lazyDescs = nLargeTotal == 0 && nslices > 1 && !lazyOff;
+    if (!lazyDescs) fillDescs(0, n, Sums{0, 0, 0, 0});
     if (!c->dDescs.reserve(n * sizeof(ZlFrameDesc)) || !c->dInfos.reserve(n * sizeof(ZlFrameInfo)) || !c->dResults.reserve(n * 8) ||
         !c->dLit.reserve(lit + 64) || !c->dRec.reserve(rec * 8) ||
         !c->dNorm.reserve(nslices * (size_t)ZL_NORM_SLOTS * 3 * ZL_NORM_STRIDE * sizeof(i16)) ||
@@ -599,7 +628,7 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     }
     size_t largeSeen = 0;
     const double tPrep = hostMs();
-    cudaMemcpyAsync(c->dDescs.p, hd, n * sizeof(ZlFrameDesc), cudaMemcpyHostToDevice, st);
+    if (!lazyDescs) cudaMemcpyAsync(c->dDescs.p, hd, n * sizeof(ZlFrameDesc), cudaMemcpyHostToDevice, st);
     if (!c->stageEv[0]) for (cudaEvent_t& e : c->stageEv) cudaEventCreate(&e);
     const int verify = !c->forceIgnoreChecksum;
     cudaEventRecord(c->ev0, st);
@@ -633,13 +662,17 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
                 if (sruns[r].bytes) cudaMemcpyAsync(c->dSrc.as<u8>() + sruns[r].devOff, sruns[r].hbase, sruns[r].bytes, cudaMemcpyHostToDevice, ls);
             if (nslices > 1) cudaEventRecord(c->inDone[k % ZL_DEC_LANES], ls);
         }
+        if (lazyDescs) {
+            fillDescs(a, a + cnt, sliceBase[k]);
+            cudaMemcpyAsync(c->dDescs.as<ZlFrameDesc>() + a, hd + a, cnt * sizeof(ZlFrameDesc), cudaMemcpyHostToDevice, ls);
+        }
         if (trace) cudaEventRecord(tev[3 * k], ls);
         ZlDecodeLaunch L;
         L.descs = c->dDescs.as<ZlFrameDesc>() + a; L.infos = c->dInfos.as<ZlFrameInfo>() + a; L.hdrArena = c->dHdr.as<ZlBlockHdr>();
         L.descsAll = c->dDescs.as<ZlFrameDesc>(); L.infosAll = c->dInfos.as<ZlFrameInfo>(); L.frameBase = (u32)a;
         L.recArena = c->dRec.as<u64>(); L.litArena = c->dLit.as<u8>();
         L.normArena = c->dNorm.as<i16>() + k * (size_t)ZL_NORM_SLOTS * 3 * ZL_NORM_STRIDE; L.normSlots = ZL_NORM_SLOTS;
-        {   const u64 u0 = hd[a].hdrBase, u1 = cut[k + 1] < n ? hd[cut[k + 1]].hdrBase : hdr;      // the slice's share of the unit arena
+        {   const u64 u0 = sliceBase[k].hdr, u1 = sliceBase[k + 1].hdr;                             // the slice's share of the unit arena
             L.units = c->dUnits.as<ZlUnit>() + u0; L.unitCap = (u32)((u1 - u0) > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : (u1 - u0)); }
         L.counters = c->dCounters.as<u32>() + 4 * k;
         L.nLarge = 0; L.largeIdx = nullptr; L.largeMaxBlocks = 0; L.largeMaxBytes = 0; L.lbArena = nullptr; L.lcArena = nullptr; L.parentArena = nullptr;
@@ -717,7 +750,7 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
             cudaEventElapsedTime(&t0, tev[3 * nslices], tev[3 * k]); cudaEventElapsedTime(&t1, tev[3 * nslices], tev[3 * k + 1]); cudaEventElapsedTime(&t2, tev[3 * nslices], tev[3 * k + 2]);
             fprintf(stderr, "slice %zu (%zu frames): h2d done %.2f, kernels done %.2f, d2h done %.2f ms\n", k, cut[k + 1] - cut[k], t0, t1, t2);
         }
-        fprintf(stderr, "total %.2f ms; host: descriptors ready %.3f, launches issued %.3f, synchronised %.3f ms\n", ms, tPrep, tLaunch, tSync);
+        fprintf(stderr, "total %.2f ms; host: sorted %.3f, arenas summed %.3f, descriptors ready %.3f, launches issued %.3f, synchronised %.3f ms\n", ms, tSort, tPass1, tPrep, tLaunch, tSync);
         for (cudaEvent_t x : tev) cudaEventDestroy(x);
     }
     for (int k = 0; k < ZL_DEC_STAGES; k++) {
