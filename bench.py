@@ -189,6 +189,14 @@ def compress_traffic(level):
         return None
 
 
+def compress_traffic_bytes(level, nblocks):
+    """the capture's total DRAM bytes scaled to `nblocks` blocks (the capture holds fewer blocks of the same mix), or None"""
+    t = compress_traffic(level)
+    if not t:
+        return None, None
+    return int(t["dram_bytes_total"] * nblocks / t["blocks_in_capture"]), t.get("source")
+
+
 def pin_to_gpu_numa_node(local):
     """Bind this process (and the pinned host buffers it allocates afterwards) to the CPUs NVML reports as local to its GPU: with one
     process per GPU on a two-socket box, host staging otherwise lands on whichever node the launcher started on."""
@@ -327,13 +335,13 @@ def compress_leg(torch, dist, z, args, dev, rank, world):
         out[f"level{lvl}"] = {"GBps": world * n * fb / ms / 1e6, "ms": ms, "ratio": n * fb / csize, "size_vs_libzstd": ours / theirs,
                               "size_vs_libzstd_how": f"{len(range(0, n, max(1, n // 128)))} sampled frames, libzstd at the same level on the same slabs",
                               "kernel_ms": kernel_ms, "stages_ms": stages,
-                              "stages_how": "CUDA events between the kernels of the last wave of the last device-resident call (a call of more than 8,192 blocks runs in waves)",
+                              "stages_how": "CUDA events between the kernels, summed over the waves of the last device-resident call (a call of more than 8,192 blocks runs in waves)",
                               "frames_per_gpu": n, "frame_bytes": fb, "n_gpus": world,
                               "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / ms / 1e6 / peak,
                                            "peak_source": peak_src, "algorithmic_bytes_per_call": int(alg), "call_ms": ms,
                                            "dominant_kernel": ("zl_k_" + dom) if dom else None,
                                            "dominant_share_of_wave": (stages[dom] / sum(v for v in stages.values() if v > 0)) if dom else None,
-                                           "traffic": compress_traffic(lvl)}}
+                                           "traffic": compress_traffic_bytes(lvl, n)[0], "traffic_source": compress_traffic_bytes(lvl, n)[1]}}
         if e2e:
             out[f"level{lvl}"]["e2e"] = e2e
         if world == 1 and not args.no_cpu:
