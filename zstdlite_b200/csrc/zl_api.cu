@@ -483,7 +483,9 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     // kernels of the next.
     static const bool gradeOff = getenv("ZL_DEC_NOGRADE") != nullptr;      // (development switch)
     const bool graded = !dev && nslices >= 6 && !gradeOff;
-    if (graded) nslices = 6;
+    static const int gradeN = getenv("ZL_DEC_GRADE") ? atoi(getenv("ZL_DEC_GRADE")) : 6;      // (development switch: 6, 7 or 8 graded slices -- measured the same: 23.4 - 23.7 ms per GiB step;
+    // the floor is the chain latency of ONE frame through the three kernels, 2.4 ms, before the first copy back can start, plus 1.07 GB at the D2H rate)
+    if (graded) nslices = gradeN < 6 ? 6 : (gradeN > ZL_DEC_MAX_SLICES ? ZL_DEC_MAX_SLICES : (size_t)gradeN);
     if (nslices > 1 && !zl_dctx_lanes(c)) nslices = 1;
     // Scheduling order (device buffers): the frames are handed to the kernels by decreasing compressed size -- longest work
     // first, and frames of one kind next to each other, so that the quads of a warp and the warps of a CTA finish together.
@@ -519,7 +521,8 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         u64 acc = 0; size_t k = 1;
         for (size_t i = 0; i < n && k < nslices; i++) {
             acc += dstCap[order[i]];
-            const bool reached = graded && nslices == 6 ? acc * 32 >= contentTotal * (k == 1 ? 1 : k == 2 ? 2 : k == 3 ? 4 : k == 4 ? 8 : 16)
+            // graded: slice 0 and 1 take 1/2^(S-1) of the batch each, every later slice as much as all before it together
+            const bool reached = graded ? (acc << (nslices - 1)) >= contentTotal * ((u64)1 << (k - 1))
                                                         : acc * nslices >= contentTotal * k;
             if (reached) cut[k++] = i + 1;
         }
