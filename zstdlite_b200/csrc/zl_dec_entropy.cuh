@@ -702,8 +702,11 @@ ZL_HD void zl_lit_unit_head(ZlLitSm& f, const ZlFrameDesc& d, const ZlBlockHdr* 
             c.sLen[3] = litSize - 3 * seg;
             // libzstd's 4-stream decoder only insists on exact consumption when it cannot take its "fast" path, i.e. when a
             // stream is shorter than 8 bytes (HUF_DecompressFastArgs_init, zstd.c:38772-38850; the fast path checks the
-            // regenerated sizes only); the single-stream decoder always does (zstd.c:38647).  Same here, so that a damaged
-            // frame without checksum decodes to the same bytes as with the reference.
+            // regenerated sizes only); the single-stream decoder always does (zstd.c:38647).  Same here for bits LEFT OVER
+            // (sErr == 2), so that a damaged frame without checksum decodes to the same bytes as with the reference.  A
+            // reader that runs past the START of its stream (sErr == 1) is always an error here (zl_lit_unit_finish):
+            // libzstd's fast loop reads on into the bytes in front of the stream and returns garbage -- the one place
+            // where this decoder is deliberately stricter on damaged input ("Decoder limits").
             c.sStrict = (l1 < 8 || l2 < 8 || l3 < 8 || c.sEnd[3] - c.sBeg[3] < 8) ? 1u : 0u;
         }
     }
