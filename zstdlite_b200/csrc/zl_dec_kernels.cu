@@ -51,6 +51,14 @@ zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ i
     ZlLitSm& f = fs[quad];
     // stream ring: ZL_LIT_RING_SLOTS slots of 32 x 16 bytes behind the eight units (zl_huf_stream)
     const u32 ring = ZL_LIT_RING ? zl_smem_addr(smraw + ZL_QUADS_PER_WARP * sizeof(ZlLitSm)) + lane * 16u : 0u;
+    // the dictionary's Huffman table, once per CTA (behind the ring): units with treeless literals that fall back on it decode from this
+    // copy instead of copying 4 KB each (config 3: every object of a few hundred bytes did -- 512 load/store pairs per lane and unit)
+    u16* dictHuf = reinterpret_cast<u16*>(smraw + ZL_QUADS_PER_WARP * sizeof(ZlLitSm) + (ZL_LIT_RING ? ZL_LIT_RING_SLOTS * 32 * 16 : 0));
+    if (dict && dict->hasEntropy) {
+        const uint4* g = reinterpret_cast<const uint4*>(dict->huf);
+        for (u32 i = lane; i < 2048 * 2 / 16; i += 32) reinterpret_cast<uint4*>(dictHuf)[i] = g[i];
+        __syncwarp();
+    }
     const u32 nunits = *unitCount;
     for (;;) {
         const u32 ubase = zl_fetch_units(cursor, lane);
@@ -71,13 +79,11 @@ zl_k_literals(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ i
                 useDict = __shfl_sync(qmask, useDict, quad * 4);
                 __syncwarp(qmask);
                 const u32 fill = f.ctl.needHufFill, ns = f.ctl.err ? 0u : f.ctl.nStreams;
-                if (useDict) {                                         // zstd.c:42140-42159: the dictionary's tree
-                    for (u32 i = q; i < 2048; i += 4) f.huf[i] = dict->huf[i];
-                    if (q == 0) f.ctl.hufLog = dict->hufLog;
-                } else if (fill && !f.ctl.err) zl_huf_fill(f, q);
+                if (useDict) { if (q == 0) f.ctl.hufLog = dict->hufLog; }      // zstd.c:42140-42159: the dictionary's tree (the CTA's copy)
+                else if (fill && !f.ctl.err) zl_huf_fill(f, q);
                 __syncwarp(qmask);
                 if (q < ns)
-                    f.ctl.sErr[q] = zl_huf_stream(f.huf, f.ctl.hufLog, wbase, bias, f.ctl.sBeg[q], f.ctl.sEnd[q],
+                    f.ctl.sErr[q] = zl_huf_stream(useDict ? dictHuf : f.huf, f.ctl.hufLog, wbase, bias, f.ctl.sBeg[q], f.ctl.sEnd[q],
                                                   lits + f.ctl.sOut[q], f.ctl.sLen[q], ring);
                 __syncwarp(qmask);
                 if (q == 0) { const u32 e = zl_lit_unit_finish(f); if (e) infos[un.frame].err = e; }
@@ -380,6 +386,7 @@ zl_k_xxh64_large(const u8* const* __restrict__ ptrs, const u32* __restrict__ siz
 
 // ---- launchers ---------------------------------------------------------------------------------------
 size_t zl_literals_smem_bytes() { return ZL_QUADS_PER_WARP * sizeof(ZlLitSm) + (ZL_LIT_RING ? ZL_LIT_RING_SLOTS * 32 * 16 : 0); }
+static size_t zl_literals_smem_dict_bytes() { return zl_literals_smem_bytes() + 2048 * sizeof(u16); }      // + the dictionary's Huffman table
 size_t zl_sequences_smem_bytes() { return ZL_XTAB_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlSeqSm) + (ZL_SEQ_RING ? 4 * 8 * 16 : 0); }
 
 // occupancy of the two persistent entropy kernels, per device (function attributes are per device too); guarded: contexts of
@@ -400,7 +407,7 @@ cudaError_t zl_decode_grid_limits(u32* litCtas, u32* seqCtas)
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
         const size_t smA = zl_literals_smem_bytes(), smB = zl_sequences_smem_bytes();
-        e = cudaFuncSetAttribute(zl_k_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA);
+        e = cudaFuncSetAttribute(zl_k_literals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zl_literals_smem_dict_bytes());
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(zl_k_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB);
         if (e != cudaSuccess) return e;
@@ -421,7 +428,7 @@ cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
 {
     if (L.nframes == 0) return cudaSuccess;
     unsigned long long nk = 0;
-    const size_t smA = zl_literals_smem_bytes(), smB = zl_sequences_smem_bytes();
+    const size_t smA = L.dict ? zl_literals_smem_dict_bytes() : zl_literals_smem_bytes(), smB = zl_sequences_smem_bytes();
     u32 litCtas = 0, seqCtas = 0;
     cudaError_t e = zl_decode_grid_limits(&litCtas, &seqCtas);
     if (e != cudaSuccess) return e;
