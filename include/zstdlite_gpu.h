@@ -26,7 +26,7 @@ typedef struct ZSTD_DCtx_s ZSTD_DCtx;
 typedef enum { ZSTD_reset_session_only = 1, ZSTD_reset_parameters = 2, ZSTD_reset_session_and_parameters = 3 } ZSTD_ResetDirective;
 /* the parameters zstdlite sets: src/zstd/zstd.h:333,440,449,507-508,2083,2103 and 638-639,2422,2433 */
 typedef enum {
-    ZSTD_c_compressionLevel = 100, ZSTD_c_checksumFlag = 201, ZSTD_c_nbWorkers = 400,
+    ZSTD_c_compressionLevel = 100, ZSTD_c_windowLog = 101, ZSTD_c_checksumFlag = 201, ZSTD_c_nbWorkers = 400,
     ZSTD_c_stableInBuffer = 1006, ZSTD_c_stableOutBuffer = 1007
 } ZSTD_cParameter;
 typedef enum { ZSTD_d_windowLogMax = 100, ZSTD_d_stableOutBuffer = 1001, ZSTD_d_forceIgnoreChecksum = 1002 } ZSTD_dParameter;

@@ -60,14 +60,23 @@ static void emul_match(const u8* src, u32 n, const ZlEncParams& P, std::vector<u
             if (P.hlogL) { const u32 l = dict_match(*D, D->tabL, zl_hash_long(lo, hi, D->d.hlogL), src, n, p, P.mls, &dOff); if (l > bestLen) { bestLen = l; bestOff = dOff; } }
             if (bestLen < lim) { const u32 l = dict_match(*D, D->tabS, zl_hash_short(lo, hi, P.mls, D->d.hlogS), src, n, p, P.mls, &dOff); if (l > bestLen) { bestLen = l; bestOff = dOff; } }
         }
-        if (g_far.tab) {                                     // zl_far_candidate (zl_enc_match.cuh)
-            const u32 pos = g_far.blockOff + p;
-            const u32 q = g_far.tab[zl_hash_long(lo, hi, g_far.log)];
-            if (q < pos && pos - q < ZL_FAR_MAX_OFF && pos - q > 65535u) {
-                u32 limF = n - p; if (limF > ZL_M_CAP) limF = ZL_M_CAP;
+        if (g_far.tab) {                                     // far candidates (zl_k_match): own region, then the one before it
+            const u32 pos = g_far.blockOff + p, hF = zl_hash_long(lo, hi, g_far.log), reg = pos >> ZL_FAR_REGION_LOG;
+            u32 limF = n - p; if (limF > ZL_M_CAP) limF = ZL_M_CAP;
+            bool got = false;
+            u32 q = g_far.tab[((size_t)reg << g_far.log) + hF];
+            if (q < pos && pos - q > 65535u && pos - q < P.farMaxOff) {
                 u32 l = 0;
                 while (l < limF && g_far.frame[q + l] == src[p + l]) l++;
-                if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; }
+                if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; got = true; }
+            }
+            if (!got && reg) {
+                q = g_far.tab[((size_t)(reg - 1) << g_far.log) + hF];
+                if (q != 0xFFFFFFFFu && pos - q > 65535u && pos - q < P.farMaxOff) {
+                    u32 l = 0;
+                    while (l < limF && g_far.frame[q + l] == src[p + l]) l++;
+                    if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; }
+                }
             }
         }
         M[p] = bestLen ? ((bestOff << 8) | bestLen) : 0;
@@ -228,14 +237,14 @@ static size_t emul_compress(void* dstv, size_t cap, const void* srcv, size_t siz
     std::vector<u32> farTab;
     if (far) {
         const u32 flog = zl_far_log(size);
-        farTab.assign((size_t)1 << flog, 0xFFFFFFFFu);
+        farTab.assign((size_t)zl_far_entries(size), 0xFFFFFFFFu);
         for (size_t q = 0; q + 8 <= size; q++) {
-            const u32 h = zl_hash_long(rd32(src + q), rd32(src + q + 4), flog);
+            const size_t h = ((q >> ZL_FAR_REGION_LOG) << flog) + zl_hash_long(rd32(src + q), rd32(src + q + 4), flog);
             if ((u32)q < farTab[h]) farTab[h] = (u32)q;
         }
         g_far.frame = src; g_far.frameSize = (u32)size; g_far.log = flog; g_far.tab = farTab.data();
     }
-    frame.resize(zl_write_frame_header(frame.data(), size, D ? D->d.dictID : 0u, checksumFlag ? 1u : 0u, far));
+    frame.resize(zl_write_frame_header(frame.data(), size, D ? D->d.dictID : 0u, checksumFlag ? 1u : 0u, far ? P.farMaxOff : 0u));
     size_t pos = 0; bool first = true;
     std::vector<u8> payload;
     do {

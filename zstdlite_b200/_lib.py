@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("ZSTDLITE_GPU_LIB") or os.path.join(_HERE, "libzstdlit
 CONTENTSIZE_UNKNOWN = 2**64 - 1
 CONTENTSIZE_ERROR = 2**64 - 2
 ZSTD_c_compressionLevel, ZSTD_c_checksumFlag, ZSTD_c_nbWorkers = 100, 201, 400
+ZSTD_c_windowLog = 101
 ZSTD_c_stableInBuffer, ZSTD_c_stableOutBuffer = 1006, 1007
 ZSTD_d_stableOutBuffer, ZSTD_d_forceIgnoreChecksum = 1001, 1002
 

@@ -16,7 +16,7 @@
 #define ZL_WAVE_BLOCKS 8192u          // blocks per launch wave (bounds the scratch arenas: ~0.9 MB per 128 KiB block)
 
 struct ZSTD_CCtx_s {
-    int level = 3, nbWorkers = 0, checksumFlag = 0, stableIn = 0, stableOut = 0;
+    int level = 3, nbWorkers = 0, checksumFlag = 0, stableIn = 0, stableOut = 0, windowLog = 0;
     bool levelFallback = false;            // zl_cctx_allow_level_fallback: levels >= 4 run the level-3 engine instead of being refused
     unsigned long long pledged = ZSTD_CONTENTSIZE_UNKNOWN;
     std::vector<u8> dictRaw;
@@ -109,7 +109,7 @@ ZL_EXPORT size_t ZSTD_CCtx_reset(ZSTD_CCtx* c, ZSTD_ResetDirective r)          /
         c->pledged = ZSTD_CONTENTSIZE_UNKNOWN; c->sIn.clear(); c->sOut.clear(); c->sOutPos = 0; c->sFlushing = false;
     }
     if (r == ZSTD_reset_parameters || r == ZSTD_reset_session_and_parameters) {
-        c->level = 3; c->nbWorkers = 0; c->checksumFlag = 0; c->stableIn = 0; c->stableOut = 0; c->dictRaw.clear(); c->dictDirty = true; c->dictErr = 0;
+        c->level = 3; c->nbWorkers = 0; c->checksumFlag = 0; c->stableIn = 0; c->stableOut = 0; c->windowLog = 0; c->dictRaw.clear(); c->dictDirty = true; c->dictErr = 0;
     }
     return 0;
 }
@@ -133,6 +133,9 @@ ZL_EXPORT size_t ZSTD_CCtx_setParameter(ZSTD_CCtx* c, ZSTD_cParameter p, int v) 
         c->level = v == 0 ? 3 : v;
         return 0;
     }
+    // Blocks are 128 KiB, so a window below 2^17 cannot be honoured.  17 switches the far candidates of zl_enc_match.cuh off (every match
+    // stays inside its block: the fastest setting for one large buffer); 18 and more bound the far offsets (at most 2^24 in any case).
+    case ZSTD_c_windowLog: if (v != 0 && (v < 17 || v > 31)) return ZL_ERROR(parameter_outOfBound); c->windowLog = v; return 0;
     case ZSTD_c_nbWorkers: if (v < 0) v = 0; if (v > 256) v = 256; c->nbWorkers = v; return 0;
     case ZSTD_c_checksumFlag: if (v < 0 || v > 1) return ZL_ERROR(parameter_outOfBound); c->checksumFlag = v; return 0;
     case ZSTD_c_stableInBuffer: if (v < 0 || v > 1) return ZL_ERROR(parameter_outOfBound); c->stableIn = v; return 0;
@@ -148,6 +151,7 @@ ZL_EXPORT size_t ZSTD_CCtx_getParameter(const ZSTD_CCtx* c, ZSTD_cParameter p, i
 {
     switch ((int)p) {
     case ZSTD_c_compressionLevel: *v = c->level; return 0;
+    case ZSTD_c_windowLog: *v = c->windowLog; return 0;
     case ZSTD_c_nbWorkers: *v = c->nbWorkers; return 0;
     case ZSTD_c_checksumFlag: *v = c->checksumFlag; return 0;
     case ZSTD_c_stableInBuffer: *v = c->stableIn; return 0;
@@ -233,8 +237,9 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
 {
     cudaStream_t st = c->stream;
     const size_t nf = f1 - f0;
-    const ZlEncParams P = zl_enc_params(zl_engine_level(c->level));
+    ZlEncParams P = zl_enc_params(zl_engine_level(c->level));
     const ZlEncDictDev* dict = zl_cctx_dict(c, P);
+    if (c->windowLog) P.farMaxOff = c->windowLog <= 17 ? 0u : (c->windowLog >= 24 ? ZL_FAR_MAX_OFF : (1u << c->windowLog));
     if (c->dictErr && !c->dictRaw.empty()) return c->dictErr;
     size_t nb = 0; u32 maxBlock = 0;
     for (size_t i = f0; i < f1; i++) {
@@ -264,13 +269,14 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
         f.dst = ddst[i]; f.dstCap = dstCap[i]; f.firstBlock = (u32)bi; f.checksumFlag = (u32)c->checksumFlag;
         const size_t nblk = s ? (s + ZL_BLOCKSIZE_MAX - 1) / ZL_BLOCKSIZE_MAX : 1;
         f.nblocks = (u32)nblk;
-        // far candidates (zl_enc_match.cuh): a frame of several blocks gets a frame-wide table, while the wave's tables fit 1 GiB
+        // far candidates (zl_enc_match.cuh): a frame of several blocks gets a frame-wide table, while the wave's tables fit 4 GiB
         bool far = false;
-        if (nblk > 1 && s < 0xFFFFFF00ull && !farOff_disabled) {
+        if (nblk > 1 && s < 0xFFFFFF00ull && !farOff_disabled && P.farMaxOff) {
             const u32 flog = zl_far_log(s);
-            if (farEntries + ((size_t)1 << flog) <= ((size_t)1 << 28)) { f.pad = (u64)farEntries | ((u64)flog << 56); farEntries += (size_t)1 << flog; far = true; }
+            const size_t fe = (size_t)zl_far_entries(s);                  // one table per 8 MiB region
+            if (farEntries + fe <= ((size_t)1 << 30)) { f.pad = (u64)farEntries | ((u64)flog << 56); farEntries += fe; far = true; }
         }
-        f.hdrSize = zl_write_frame_header(f.hdr, s, dict ? c->dictID : 0u, (u32)c->checksumFlag, far);
+        f.hdrSize = zl_write_frame_header(f.hdr, s, dict ? c->dictID : 0u, (u32)c->checksumFlag, far ? P.farMaxOff : 0u);
         for (size_t k = 0; k < nblk; k++) {
             ZlEncBlock& b = hb[bi++];
             b.src = dsrc[i] + k * ZL_BLOCKSIZE_MAX;
@@ -397,7 +403,7 @@ ZL_EXPORT size_t zl_compress_batch(ZSTD_CCtx* c, const void* const* src, const s
     auto work = [&](size_t g) {
         ZSTD_CCtx_s* k = g ? c->kids[g - 1] : c;
         if (g) {
-            k->level = c->level; k->checksumFlag = c->checksumFlag; k->levelFallback = c->levelFallback; k->nbWorkers = 0;
+            k->level = c->level; k->checksumFlag = c->checksumFlag; k->windowLog = c->windowLog; k->levelFallback = c->levelFallback; k->nbWorkers = 0;
             if (k->dictGenSeen != c->dictGen) { k->dictRaw = c->dictRaw; k->dictDirty = true; k->dictErr = 0; k->dictGenSeen = c->dictGen; }
         }
         const size_t a = cut[g], cnt = cut[g + 1] - a;

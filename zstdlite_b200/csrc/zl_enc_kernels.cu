@@ -87,7 +87,7 @@ __device__ __forceinline__ u32 zl_dict_match(const ZlEncDictDev& D, const u32* _
 }
 
 // ---------------------------------------------------------------------------------------------- E0: far table (frames of > 1 block)
-// zl_enc_match.cuh, "far candidates": tab[hash8(position)] = min(position) over the whole frame.  ZlEncFrame::pad = offset of the frame's
+// zl_enc_match.cuh, "far candidates": tab[region][hash8(position)] = min(position) over the region (8 MiB of the frame).  ZlEncFrame::pad = offset of the frame's
 // table in the far arena (u32 units, low 56 bits) | log2 entries << 56 (0: the frame has no table); ZlEncBlock::pad = the block's offset
 // inside its frame.  CTA per block; the 8 bytes of a position may reach into the next block (the frame is contiguous).
 #define ZL_FAR_OFF_MASK 0x00FFFFFFFFFFFFFFull
@@ -98,7 +98,7 @@ zl_k_far_build(const ZlEncBlock* __restrict__ blocks, const ZlEncFrame* __restri
     const u64 fpad = frames[b.frame].pad;
     const u32 flog = (u32)(fpad >> 56);
     if (!flog || b.srcSize == 0) return;
-    u32* __restrict__ tab = farArena + (fpad & ZL_FAR_OFF_MASK);
+    u32* __restrict__ tab = farArena + (fpad & ZL_FAR_OFF_MASK) + ((size_t)(b.pad >> ZL_FAR_REGION_LOG) << flog);      // the block's region
     const u32 n = b.srcSize;
     const u32 bias = (u32)(((size_t)b.src) & 3);
     const u32* __restrict__ wbase = reinterpret_cast<const u32*>(b.src - bias);
@@ -237,11 +237,20 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
                         if (l > bestLen) { bestLen = l; bestOff = dOff; }
                     }
                 }
-                if (flog) {
-                    const u32 pos = b.pad + p, q = __ldg(ftab + zl_hash_long(lo[h], hi[h], flog));
-                    if (q < pos && pos - q < ZL_FAR_MAX_OFF && pos - q > 65535u) {
+                if (flog) {                                                    // own region first, then the one before it
+                    const u32 pos = b.pad + p, hF = zl_hash_long(lo[h], hi[h], flog), reg = pos >> ZL_FAR_REGION_LOG;
+                    bool got = false;
+                    u32 q = __ldg(ftab + ((size_t)reg << flog) + hF);
+                    if (q < pos && pos - q > 65535u && pos - q < P.farMaxOff) {
                         const u32 l = zl_match_len_far(wbase, bias, lastWord, p, fw, fbias, q, lo[h], hi[h], lim);
-                        if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; }
+                        if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; got = true; }
+                    }
+                    if (!got && reg) {
+                        q = __ldg(ftab + ((size_t)(reg - 1) << flog) + hF);
+                        if (q != 0xFFFFFFFFu && pos - q > 65535u && pos - q < P.farMaxOff) {
+                            const u32 l = zl_match_len_far(wbase, bias, lastWord, p, fw, fbias, q, lo[h], hi[h], lim);
+                            if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; }
+                        }
                     }
                 }
                 if (bestLen) m = (bestOff << 8) | bestLen;

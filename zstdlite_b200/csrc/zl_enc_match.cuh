@@ -28,6 +28,7 @@ struct ZlEncParams {       // derived from the compression level by zl_enc_param
     u32 mls;               // bytes hashed by the short table (also the minimum match length)
     u32 hlogS;             // log2 entries of the short table
     u32 hlogL;             // log2 entries of the long (8-byte) table, 0 = no long table
+    u32 farMaxOff;         // far candidates (below): offsets stay under this; 0 = none.  ZSTD_c_windowLog lowers it.
 };
 // levels map onto three table layouts (cf. the reference's rows for <= 128 KB inputs, zstd.c:29579-29582):
 //   1: fast-like   short 2^14            (32 KB of u16)
@@ -36,7 +37,7 @@ struct ZlEncParams {       // derived from the compression level by zl_enc_param
 static inline ZlEncParams zl_enc_params(int level)
 {
     ZlEncParams p;
-    p.level = (u32)level; p.mls = 5;
+    p.level = (u32)level; p.mls = 5; p.farMaxOff = 1u << 24;
     if (level <= 1) { p.hlogS = 14; p.hlogL = 0; }
     else if (level == 2) { p.hlogS = 15; p.hlogL = 0; }
     else { p.hlogS = 14; p.hlogL = 15; }
@@ -83,17 +84,28 @@ ZL_HD u32 zl_common8(u32 alo, u32 ahi, u32 blo, u32 bhi)
 // table: for every 8-byte hash the EARLIEST position of the frame where it occurs (zl_k_far_build: an atomicMin per position, so the
 // table does not depend on any order).  Every position looks its hash up; an earlier occurrence beyond the reach of the block tables
 // is verified like any candidate and taken when it is clearly longer than the near one (its offset costs more bits).  The frame
-// header then declares a window that covers the whole frame (decoders accept 2^27 by default, zstd.c:42431).
+// header then declares a window that covers the frame, at most 16 MiB (decoders accept 2^27 by default, zstd.c:42431).
 #define ZL_FAR_MAX_OFF (1u << 24)          // M[p] keeps 24 bits of offset
 #define ZL_FAR_MIN_LOG 17u
-#define ZL_FAR_MAX_LOG 25u
-// table size for a frame of n bytes: twice as many entries as positions (earliest-wins: a crowded table loses the later content)
+// Frames beyond 8 MiB are covered REGION by region (8 MiB each, one table per region, the earliest occurrence inside that region): a
+// position consults its own region's table and, when that gives nothing, the previous region's -- every such candidate is less than
+// 16 MiB back, which is what M[p] can hold and what the window descriptor then declares.  (One frame-wide table of earliest
+// occurrences stops helping once the earliest occurrence is out of reach: text of 48 MiB was back at 1.07x libzstd.)
+#define ZL_FAR_REGION_LOG 23u
+#ifndef ZL_FAR_MULTI_LOG
+#define ZL_FAR_MULTI_LOG 23u               // entries per region table of a multi-region frame (one per position)
+#endif
+ZL_HD u32 zl_far_regions(u64 n) { return (u32)((n + (1ull << ZL_FAR_REGION_LOG) - 1) >> ZL_FAR_REGION_LOG); }
+// table size (log2 entries per region) for a frame of n bytes: a single region gets twice as many entries as positions (earliest-wins:
+// a crowded table loses the later content)
 ZL_HD u32 zl_far_log(u64 n)
 {
+    if (n > (1ull << ZL_FAR_REGION_LOG)) return ZL_FAR_MULTI_LOG;
     u32 l = ZL_FAR_MIN_LOG;
-    while (l < ZL_FAR_MAX_LOG && (1ull << l) < 2 * n) l++;
+    while (l < ZL_FAR_REGION_LOG + 1 && (1ull << l) < 2 * n) l++;
     return l;
 }
+ZL_HD u64 zl_far_entries(u64 n) { return (u64)zl_far_regions(n) << zl_far_log(n); }
 // Is a far match of lenFar bytes better than the near one of bestLen bytes (0 = none)?  A far offset costs 2-3 bytes more than a near or
 // repeated one, so it must be clearly longer: lenFar > bestLen + 2 + bestLen / 2, and at least 8 bytes.  Measured on 2 - 16 MB buffers against
 // libzstd level 3 (tests/emul, ours / theirs): text 1.116 -> 1.013, columnar 0.965 -> 0.973; an eager rule (longer by 2) gives text 1.010 but
@@ -109,10 +121,10 @@ ZL_HD u32 zl_far_log(u64 n)
 #endif
 ZL_HD bool zl_far_better(u32 lenFar, u32 bestLen, u32 mls) { (void)mls; return lenFar >= ZL_FAR_MINLEN && lenFar > bestLen + ZL_FAR_MARGIN + ((bestLen * ZL_FAR_REL) >> 2); }
 // window descriptor byte of a multi-block frame of n bytes (zstd.c:41115-41121: window = (1 << (10 + exponent)) * (1 + mantissa / 8))
-ZL_HD u32 zl_window_descriptor(u64 n, bool far)
+ZL_HD u32 zl_window_descriptor(u64 n, u32 farMaxOff)
 {
     u32 wlog = 17;
-    if (far) while (wlog < 31 && (1ull << wlog) < n) wlog++;
+    while ((1ull << wlog) < farMaxOff && (1ull << wlog) < n) wlog++;      // far offsets stay below farMaxOff (0: no far candidates)
     return (wlog - 10) << 3;
 }
 
@@ -146,7 +158,7 @@ ZL_HD u32 zl_rep_encode(ZlReps& r, u32 off, u32 ll)
 // Frames of <= 128 KiB are single-segment like the reference's (window >= content).  Larger inputs are written as one
 // frame of 128 KiB blocks; its window descriptor says 128 KiB when nothing refers back across a block, or covers the frame
 // when far candidates are in use (above).
-ZL_HD u32 zl_write_frame_header(u8* dst, u64 contentSize, u32 dictID, u32 checksumFlag, bool far = false)
+ZL_HD u32 zl_write_frame_header(u8* dst, u64 contentSize, u32 dictID, u32 checksumFlag, u32 farMaxOff = 0)
 {
     const u32 single = contentSize <= ZL_BLOCKSIZE_MAX ? 1u : 0u;
     const u32 didCode = dictID == 0 ? 0u : (dictID < 256 ? 1u : (dictID < 65536 ? 2u : 3u));
@@ -156,7 +168,7 @@ ZL_HD u32 zl_write_frame_header(u8* dst, u64 contentSize, u32 dictID, u32 checks
     u32 p = 0;
     dst[p++] = 0x28; dst[p++] = 0xB5; dst[p++] = 0x2F; dst[p++] = 0xFD;
     dst[p++] = (u8)(didCode | (checksumFlag << 2) | (single << 5) | (fcsCode << 6));
-    if (!single) dst[p++] = (u8)zl_window_descriptor(contentSize, far);
+    if (!single) dst[p++] = (u8)zl_window_descriptor(contentSize, farMaxOff);
     if (didCode == 1) dst[p++] = (u8)dictID;
     else if (didCode == 2) { dst[p++] = (u8)dictID; dst[p++] = (u8)(dictID >> 8); }
     else if (didCode == 3) { for (u32 i = 0; i < 4; i++) dst[p++] = (u8)(dictID >> (8 * i)); }

@@ -9,6 +9,7 @@
 #include <mutex>
 #include <condition_variable>
 #include <atomic>
+#include <functional>
 #include "zl_common.cuh"
 #include "zl_launch.h"
 
@@ -76,10 +77,17 @@ public:
         size_t total = 0;
         for (const ZlCopySeg& s : segs) total += s.bytes;
         if (total < (4u << 20) || workers_.empty()) { for (const ZlCopySeg& s : segs) if (s.bytes) memcpy(s.dst, s.src, s.bytes); return; }
-        std::lock_guard<std::mutex> serial(runMutex_);            // one job at a time (contexts on different threads share the pool)
-        pieces_.clear();
+        std::vector<ZlCopySeg> pieces;
         for (const ZlCopySeg& s : segs)
-            for (size_t o = 0; o < s.bytes; o += kPiece) pieces_.push_back({(char*)s.dst + o, (const char*)s.src + o, s.bytes - o < kPiece ? s.bytes - o : kPiece});
+            for (size_t o = 0; o < s.bytes; o += kPiece) pieces.push_back({(char*)s.dst + o, (const char*)s.src + o, s.bytes - o < kPiece ? s.bytes - o : kPiece});
+        parallel(pieces.size(), [&](size_t i) { memcpy(pieces[i].dst, pieces[i].src, pieces[i].bytes); });
+    }
+    // fn(0) .. fn(n - 1) spread over the pool (and the caller); returns when all are done
+    void parallel(size_t n, const std::function<void(size_t)>& fn)
+    {
+        if (n < 2 || workers_.empty()) { for (size_t i = 0; i < n; i++) fn(i); return; }
+        std::lock_guard<std::mutex> serial(runMutex_);            // one job at a time (contexts on different threads share the pool)
+        fn_ = &fn; count_ = n;
         next_.store(0); pending_.store((int)workers_.size());
         { std::lock_guard<std::mutex> g(m_); generation_++; }
         cv_.notify_all();
@@ -108,8 +116,8 @@ private:
     {
         for (;;) {
             const size_t i = next_.fetch_add(1);
-            if (i >= pieces_.size()) break;
-            memcpy(pieces_[i].dst, pieces_[i].src, pieces_[i].bytes);
+            if (i >= count_) break;
+            (*fn_)(i);
         }
     }
     void loop()
@@ -122,7 +130,8 @@ private:
         }
     }
     std::vector<std::thread> workers_;
-    std::vector<ZlCopySeg> pieces_;
+    const std::function<void(size_t)>* fn_ = nullptr;
+    size_t count_ = 0;
     std::atomic<size_t> next_{0};
     std::atomic<int> pending_{0};
     std::mutex m_, runMutex_;
