@@ -61,18 +61,20 @@ static void emul_match(const u8* src, u32 n, const ZlEncParams& P, std::vector<u
             if (bestLen < lim) { const u32 l = dict_match(*D, D->tabS, zl_hash_short(lo, hi, P.mls, D->d.hlogS), src, n, p, P.mls, &dOff); if (l > bestLen) { bestLen = l; bestOff = dOff; } }
         }
         if (g_far.tab) {                                     // far candidates (zl_k_match): own region, then the one before it
-            const u32 pos = g_far.blockOff + p, hF = zl_hash_long(lo, hi, g_far.log), reg = pos >> ZL_FAR_REGION_LOG;
+            const u32 pos = g_far.blockOff + p, hx = zl_far_hash(lo, hi, g_far.log), hF = hx >> 8, reg = pos >> ZL_FAR_REGION_LOG;
             u32 limF = n - p; if (limF > ZL_M_CAP) limF = ZL_M_CAP;
             bool got = false;
-            u32 q = g_far.tab[((size_t)reg << g_far.log) + hF];
-            if (q < pos && pos - q > 65535u && pos - q < P.farMaxOff) {
+            u32 e = g_far.tab[((size_t)reg << g_far.log) + hF];
+            u32 q = (reg << ZL_FAR_REGION_LOG) + (e >> 8);
+            if (e != ZL_FAR_EMPTY && (e & 255u) == (hx & 255u) && q < pos && pos - q > 65535u && pos - q < P.farMaxOff) {
                 u32 l = 0;
                 while (l < limF && g_far.frame[q + l] == src[p + l]) l++;
                 if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; got = true; }
             }
-            if (!got && reg) {
-                q = g_far.tab[((size_t)(reg - 1) << g_far.log) + hF];
-                if (q != 0xFFFFFFFFu && pos - q > 65535u && pos - q < P.farMaxOff) {
+            if (!got && zl_far_use_prev(pos)) {
+                e = g_far.tab[((size_t)(reg - 1) << g_far.log) + hF];
+                q = ((reg - 1) << ZL_FAR_REGION_LOG) + (e >> 8);
+                if (e != ZL_FAR_EMPTY && (e & 255u) == (hx & 255u) && pos - q > 65535u && pos - q < P.farMaxOff) {
                     u32 l = 0;
                     while (l < limF && g_far.frame[q + l] == src[p + l]) l++;
                     if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; }
@@ -239,8 +241,10 @@ static size_t emul_compress(void* dstv, size_t cap, const void* srcv, size_t siz
         const u32 flog = zl_far_log(size);
         farTab.assign((size_t)zl_far_entries(size), 0xFFFFFFFFu);
         for (size_t q = 0; q + 8 <= size; q++) {
-            const size_t h = ((q >> ZL_FAR_REGION_LOG) << flog) + zl_hash_long(rd32(src + q), rd32(src + q + 4), flog);
-            if ((u32)q < farTab[h]) farTab[h] = (u32)q;
+            const u32 hx = zl_far_hash(rd32(src + q), rd32(src + q + 4), flog);
+            const size_t h = ((q >> ZL_FAR_REGION_LOG) << flog) + (hx >> 8);
+            const u32 e = (((u32)q & ((1u << ZL_FAR_REGION_LOG) - 1)) << 8) | (hx & 255u);
+            if (e < farTab[h]) farTab[h] = e;
         }
         g_far.frame = src; g_far.frameSize = (u32)size; g_far.log = flog; g_far.tab = farTab.data();
     }

@@ -89,15 +89,20 @@ __device__ __forceinline__ u32 zl_dict_match(const ZlEncDictDev& D, const u32* _
 // ---------------------------------------------------------------------------------------------- E0: far table (frames of > 1 block)
 // zl_enc_match.cuh, "far candidates": tab[region][hash8(position)] = min(position) over the region (8 MiB of the frame).  ZlEncFrame::pad = offset of the frame's
 // table in the far arena (u32 units, low 56 bits) | log2 entries << 56 (0: the frame has no table); ZlEncBlock::pad = the block's offset
-// inside its frame.  CTA per block; the 8 bytes of a position may reach into the next block (the frame is contiguous).
+// inside its frame.  A CTA takes 8 KiB of a block (ZL_FAR_CHUNKS CTAs per block), so the CTAs in flight (148 SMs x 8) cover about 9 MiB of the
+// frame: one or two regions, whose tables (32 MB each) then live in L2 -- with a CTA per block 148 MiB were in flight, 18 regions, and the
+// atomics went to DRAM (ncu: L2 hit rate 33 %, 6.9 ms for a 256 MiB frame).  The 8 bytes of a position may reach into the next block
+// (the frame is contiguous).
 #define ZL_FAR_OFF_MASK 0x00FFFFFFFFFFFFFFull
+#define ZL_FAR_CHUNKS 16u
 __global__ void __launch_bounds__(256)
 zl_k_far_build(const ZlEncBlock* __restrict__ blocks, const ZlEncFrame* __restrict__ frames, u32* __restrict__ farArena)
 {
-    const ZlEncBlock b = blocks[blockIdx.x];
+    const ZlEncBlock b = blocks[blockIdx.x / ZL_FAR_CHUNKS];
     const u64 fpad = frames[b.frame].pad;
     const u32 flog = (u32)(fpad >> 56);
     if (!flog || b.srcSize == 0) return;
+    const u32 p0 = (blockIdx.x % ZL_FAR_CHUNKS) * (ZL_BLOCKSIZE_MAX / ZL_FAR_CHUNKS);
     u32* __restrict__ tab = farArena + (fpad & ZL_FAR_OFF_MASK) + ((size_t)(b.pad >> ZL_FAR_REGION_LOG) << flog);      // the block's region
     const u32 n = b.srcSize;
     const u32 bias = (u32)(((size_t)b.src) & 3);
@@ -105,10 +110,15 @@ zl_k_far_build(const ZlEncBlock* __restrict__ blocks, const ZlEncFrame* __restri
     const bool last = (b.flags & ZL_BLK_LAST) != 0;
     const u32 npos = last ? (n >= 8 ? n - 7 : 0u) : n;                      // positions whose 8 bytes lie inside the frame
     const u32 lastWord = (bias + (last ? n - 1 : n + 7)) >> 2;
-    for (u32 p = threadIdx.x; p < npos; p += 256) {
+    const u32 p1 = min(npos, p0 + ZL_BLOCKSIZE_MAX / ZL_FAR_CHUNKS);
+    for (u32 p = p0 + threadIdx.x; p < p1; p += 256) {
         u32 lo, hi;
         zl_ld8(wbase, bias + p, lastWord, lo, hi);
-        atomicMin(tab + zl_hash_long(lo, hi, flog), b.pad + p);
+        const u32 hx = zl_far_hash(lo, hi, flog);
+        const u32 val = (((b.pad + p) & ((1u << ZL_FAR_REGION_LOG) - 1)) << 8) | (hx & 255u);
+        // entries only ever decrease: one that is already lower needs no atomic (text repeats its common strings thousands of times per
+        // region, and those atomics serialise on one L2 line)
+        if (__ldcg(tab + (hx >> 8)) > val) atomicMin(tab + (hx >> 8), val);
     }
 }
 // length of the match between block position p (bytes lo:hi, words of the block) and FRAME position q (words of the frame), <= lim
@@ -238,16 +248,18 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
                     }
                 }
                 if (flog) {                                                    // own region first, then the one before it
-                    const u32 pos = b.pad + p, hF = zl_hash_long(lo[h], hi[h], flog), reg = pos >> ZL_FAR_REGION_LOG;
+                    const u32 pos = b.pad + p, hx = zl_far_hash(lo[h], hi[h], flog), hF = hx >> 8, reg = pos >> ZL_FAR_REGION_LOG;
                     bool got = false;
-                    u32 q = __ldg(ftab + ((size_t)reg << flog) + hF);
-                    if (q < pos && pos - q > 65535u && pos - q < P.farMaxOff) {
+                    u32 e = __ldg(ftab + ((size_t)reg << flog) + hF);
+                    u32 q = (reg << ZL_FAR_REGION_LOG) + (e >> 8);
+                    if ((e & 255u) == (hx & 255u) && q < pos && pos - q > 65535u && pos - q < P.farMaxOff) {      // (an empty entry has q >= pos)
                         const u32 l = zl_match_len_far(wbase, bias, lastWord, p, fw, fbias, q, lo[h], hi[h], lim);
                         if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; got = true; }
                     }
-                    if (!got && reg) {
-                        q = __ldg(ftab + ((size_t)(reg - 1) << flog) + hF);
-                        if (q != 0xFFFFFFFFu && pos - q > 65535u && pos - q < P.farMaxOff) {
+                    if (!got && zl_far_use_prev(pos)) {
+                        e = __ldg(ftab + ((size_t)(reg - 1) << flog) + hF);
+                        q = ((reg - 1) << ZL_FAR_REGION_LOG) + (e >> 8);
+                        if (e != ZL_FAR_EMPTY && (e & 255u) == (hx & 255u) && pos - q > 65535u && pos - q < P.farMaxOff) {
                             const u32 l = zl_match_len_far(wbase, bias, lastWord, p, fw, fbias, q, lo[h], hi[h], lim);
                             if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; }
                         }
@@ -758,7 +770,7 @@ cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st)
     if (e != cudaSuccess) return e;
     const u32 nb = L.nblocks;
     if (ev) cudaEventRecord(ev[0], st);
-    if (nb && L.far) zl_k_far_build<<<nb, 256, 0, st>>>(L.blocks, L.frames, L.far);
+    if (nb && L.far) zl_k_far_build<<<nb * ZL_FAR_CHUNKS, 256, 0, st>>>(L.blocks, L.frames, L.far);
     if (nb) {
         if (L.params.hlogL) {
             if (useDict) zl_k_match<true, true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, L.dict, L.frames, L.far);

@@ -95,6 +95,12 @@ ZL_HD u32 zl_common8(u32 alo, u32 ahi, u32 blo, u32 bhi)
 #ifndef ZL_FAR_MULTI_LOG
 #define ZL_FAR_MULTI_LOG 23u               // entries per region table of a multi-region frame (one per position)
 #endif
+// the previous region's table is only consulted from the first ZL_FAR_PREV_SPAN bytes of a region: further in, the region's own table
+// already covers that much history (libzstd's level-3 window is 2 MiB, zstd.c:29527)
+#ifndef ZL_FAR_PREV_SPAN
+#define ZL_FAR_PREV_SPAN (1u << 21)
+#endif
+ZL_HD bool zl_far_use_prev(u32 pos) { return pos >= (1u << ZL_FAR_REGION_LOG) && (pos & ((1u << ZL_FAR_REGION_LOG) - 1)) < ZL_FAR_PREV_SPAN; }
 ZL_HD u32 zl_far_regions(u64 n) { return (u32)((n + (1ull << ZL_FAR_REGION_LOG) - 1) >> ZL_FAR_REGION_LOG); }
 // table size (log2 entries per region) for a frame of n bytes: a single region gets twice as many entries as positions (earliest-wins:
 // a crowded table loses the later content)
@@ -105,6 +111,11 @@ ZL_HD u32 zl_far_log(u64 n)
     while (l < ZL_FAR_REGION_LOG + 1 && (1ull << l) < 2 * n) l++;
     return l;
 }
+// A table entry is (position inside the region) << 8 | 8 more bits of the hash: atomicMin still keeps the earliest position, and a lookup
+// whose tag differs is a different string -- it is dropped without touching the candidate's bytes (a second random DRAM sector).
+// zl_far_hash: table index << 8 | tag (log <= 24, so it fits 32 bits)
+ZL_HD u32 zl_far_hash(u32 lo, u32 hi, u32 flog) { const u64 v = ((u64)hi << 32) | lo; return (u32)((v * 0xCF1BBCDCB7A56463ULL) >> (56 - flog)); }
+#define ZL_FAR_EMPTY 0xFFFFFFFFu
 ZL_HD u64 zl_far_entries(u64 n) { return (u64)zl_far_regions(n) << zl_far_log(n); }
 // Is a far match of lenFar bytes better than the near one of bestLen bytes (0 = none)?  A far offset costs 2-3 bytes more than a near or
 // repeated one, so it must be clearly longer: lenFar > bestLen + 2 + bestLen / 2, and at least 8 bytes.  Measured on 2 - 16 MB buffers against
