@@ -239,6 +239,7 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
     const size_t nf = f1 - f0;
     ZlEncParams P = zl_enc_params(zl_engine_level(c->level));
     const ZlEncDictDev* dict = zl_cctx_dict(c, P);
+    if (const char* hl = getenv("ZL_ENC_HLOG")) { unsigned a = 0, b2 = 0; if (sscanf(hl, "%u,%u", &a, &b2) == 2 && !dict) { P.hlogS = a; if (P.hlogL) P.hlogL = b2; } }   // (development: table sizes)
     if (c->windowLog) P.farMaxOff = c->windowLog <= 17 ? 0u : (c->windowLog >= 24 ? ZL_FAR_MAX_OFF : (1u << c->windowLog));
     if (c->dictErr && !c->dictRaw.empty()) return c->dictErr;
     size_t nb = 0; u32 maxBlock = 0;

@@ -141,6 +141,7 @@ __device__ __forceinline__ u32 zl_match_len_far(const u32* __restrict__ wbase, u
     return len < lim ? len : lim;
 }
 
+#define ZL_MATCH_SCRATCH 4096u      // u16 slots of the duplicate-detection scratch (8 KB per CTA)
 template <bool kLong, bool kDict>
 __global__ void __launch_bounds__(ZL_MATCH_WARPS * 32)
 zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 slotM, ZlEncParams P, const ZlEncDictDev* __restrict__ dict,
@@ -149,6 +150,7 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
     extern __shared__ __align__(16) u8 smraw[];
     u16* tabS = reinterpret_cast<u16*>(smraw);
     u16* tabL = tabS + (1u << P.hlogS);
+    volatile u16* scr = tabL + (kLong ? (1u << P.hlogL) : 0u);            // duplicate detection (below); never initialised, never trusted
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ZlEncBlock b = blocks[blockIdx.x];
     const u32 n = b.srcSize;
@@ -190,15 +192,37 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
             lo[h] = __funnelshift_r(w0, w1, sh); hi[h] = __funnelshift_r(w1, w2, sh);
             valid[h] = p + 8 <= n;
             hS[h] = valid[h] ? zl_hash_short(lo[h], hi[h], P.mls, P.hlogS) : (0x10000u + lane);
-            const u32 mS = __match_any_sync(ZL_FULL, hS[h]);
-            lastS[h] = (mS >> lane) == 1u;                    // no higher lane shares the hash: this lane's insert survives
-            prevS[h] = (mS & ltMask) ? (31 - __clz((int)(mS & ltMask))) : -1;
-            hL[h] = 0; lastL[h] = false; prevL[h] = -1;
+            hL[h] = 0; prevS[h] = -1; prevL[h] = -1; lastS[h] = true; lastL[h] = true;
+            if (kLong) hL[h] = valid[h] ? zl_hash_long(lo[h], hi[h], P.hlogL) : (0x10000u + lane);
+            // The tables are updated as if the 32 positions of a group were inserted one after the other: an entry ends up with the HIGHEST
+            // lane of its hash (lastS), and a lane's candidate is the highest LOWER lane with its hash (prevS), else the entry from before the
+            // group.  __match_any_sync answers both, but costs about 64 cycles of the ADU pipe an instruction, and with one or two of them
+            // per group that pipe was 78 % busy and bounded the kernel (ncu, profiles/r02_ncu_full_compress_kernels_raw.csv).  Groups in which
+            // two lanes share a hash are the minority (measured: text 17 % for 5 bytes and 4 % for 8, columnar 68 % / 26 %, noise 0), so
+            // every lane first drops its position into a small scratch table under its hash and reads the slot back: a lane that finds
+            // another value shared the slot with someone (a duplicate, a slot collision or another warp -- the scratch is the CTA's), and
+            // only then does the warp ask match.any.  Of two lanes with one hash at least one reads the other's value, so no duplicate is missed.
+            const u32 p16 = p & 0xFFFFu;
+            const u32 sS = hS[h] & (ZL_MATCH_SCRATCH - 1);
+            if (valid[h]) scr[sS] = (u16)p16;
+            __syncwarp();
+            const u32 rS = valid[h] ? (u32)scr[sS] : p16;
+            if (__ballot_sync(ZL_FULL, rS != p16)) {
+                const u32 mS = __match_any_sync(ZL_FULL, hS[h]);
+                lastS[h] = (mS >> lane) == 1u;                    // no higher lane shares the hash: this lane's insert survives
+                prevS[h] = (mS & ltMask) ? (31 - __clz((int)(mS & ltMask))) : -1;
+            }
             if (kLong) {
-                hL[h] = valid[h] ? zl_hash_long(lo[h], hi[h], P.hlogL) : (0x10000u + lane);
-                const u32 mL = __match_any_sync(ZL_FULL, hL[h]);
-                lastL[h] = (mL >> lane) == 1u;
-                prevL[h] = (mL & ltMask) ? (31 - __clz((int)(mL & ltMask))) : -1;
+                const u32 sL = (hL[h] ^ 0x555u) & (ZL_MATCH_SCRATCH - 1);
+                __syncwarp();
+                if (valid[h]) scr[sL] = (u16)p16;
+                __syncwarp();
+                const u32 rL = valid[h] ? (u32)scr[sL] : p16;
+                if (__ballot_sync(ZL_FULL, rL != p16)) {
+                    const u32 mL = __match_any_sync(ZL_FULL, hL[h]);
+                    lastL[h] = (mL >> lane) == 1u;
+                    prevL[h] = (mL & ltMask) ? (31 - __clz((int)(mL & ltMask))) : -1;
+                }
             }
         }
         // ---- table section, in position order across warps (and across the two groups: same-warp shared-memory order)
@@ -210,6 +234,9 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
             if (valid[h]) {
                 eS[h] = tabS[hS[h]];
                 if (kLong) eL[h] = tabL[hL[h]];
+            }
+            __syncwarp();                                     // (every lane has read the old entries before any lane writes)
+            if (valid[h]) {
                 if (lastS[h]) tabS[hS[h]] = (u16)p;
                 if (kLong && lastL[h]) tabL[hL[h]] = (u16)p;
             }
@@ -748,7 +775,7 @@ zl_k_dict_stats(u32 nblocks, const u64* __restrict__ recArena, u32 slotRec, cons
 }
 
 // ---------------------------------------------------------------------------------------------- launcher
-size_t zl_enc_match_smem(const ZlEncParams& P) { return ((size_t)2 << P.hlogS) + (P.hlogL ? ((size_t)2 << P.hlogL) : 0); }
+size_t zl_enc_match_smem(const ZlEncParams& P) { return ((size_t)2 << P.hlogS) + (P.hlogL ? ((size_t)2 << P.hlogL) : 0) + 2 * ZL_MATCH_SCRATCH; }
 
 cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st)
 {
