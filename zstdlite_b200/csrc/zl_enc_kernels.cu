@@ -141,11 +141,59 @@ __device__ __forceinline__ u32 zl_match_len_far(const u32* __restrict__ wbase, u
     return len < lim ? len : lim;
 }
 
+// E1b: the far candidate of every position of a multi-block frame, after E1 (zl_enc_match.cuh, "far candidates").  Its own kernel: in E1 it
+// cost 20 registers (two CTAs a SM instead of three) and its lookups went to DRAM, because the blocks in flight there cover more regions than
+// L2 holds tables for.  Here a CTA takes 8 KiB like the build, so the lookups of the CTAs in flight fall into one or two region tables, and
+// the high occupancy hides what latency is left.  M[p] is replaced when the far match is clearly better than what E1 found (zl_far_better).
+__global__ void __launch_bounds__(256)
+zl_k_far_match(const ZlEncBlock* __restrict__ blocks, const ZlEncFrame* __restrict__ frames, const u32* __restrict__ farArena, u32* __restrict__ Marena, u32 slotM, ZlEncParams P)
+{
+    const u32 blk = blockIdx.x / ZL_FAR_CHUNKS;
+    const ZlEncBlock b = blocks[blk];
+    const u64 fpad = frames[b.frame].pad;
+    const u32 flog = (u32)(fpad >> 56);
+    if (!flog || b.srcSize < 8) return;
+    const u32* __restrict__ ftab = farArena + (fpad & ZL_FAR_OFF_MASK);
+    u32* __restrict__ M = Marena + (size_t)blk * slotM;
+    const u32 n = b.srcSize;
+    const u32 bias = (u32)(((size_t)b.src) & 3);
+    const u32* __restrict__ wbase = reinterpret_cast<const u32*>(b.src - bias);
+    const u32 lastWord = (bias + n - 1) >> 2;
+    const u8* fbase = b.src - b.pad;                                          // the frame is contiguous
+    const u32 fbias = (u32)(((size_t)fbase) & 3);
+    const u32* __restrict__ fw = reinterpret_cast<const u32*>(fbase - fbias);
+    const u32 p0 = (blockIdx.x % ZL_FAR_CHUNKS) * (ZL_BLOCKSIZE_MAX / ZL_FAR_CHUNKS);
+    const u32 p1 = min(n - 7, p0 + ZL_BLOCKSIZE_MAX / ZL_FAR_CHUNKS);         // positions with 8 bytes inside the block, as in E1
+    for (u32 p = p0 + threadIdx.x; p < p1; p += 256) {
+        u32 lo, hi;
+        zl_ld8(wbase, bias + p, lastWord, lo, hi);
+        const u32 m = M[p];
+        u32 bestLen = m & 0xFFu, bestOff = 0;
+        const u32 lim = min(n - p, ZL_M_CAP);
+        const u32 pos = b.pad + p, hx = zl_far_hash(lo, hi, flog), hF = hx >> 8, reg = pos >> ZL_FAR_REGION_LOG;
+        bool got = false;                                                     // own region first, then the one before it
+        u32 e = __ldg(ftab + ((size_t)reg << flog) + hF);
+        u32 q = (reg << ZL_FAR_REGION_LOG) + (e >> 8);
+        if ((e & 255u) == (hx & 255u) && q < pos && pos - q > 65535u && pos - q < P.farMaxOff) {      // (an empty entry has q >= pos)
+            const u32 l = zl_match_len_far(wbase, bias, lastWord, p, fw, fbias, q, lo, hi, lim);
+            if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; got = true; }
+        }
+        if (!got && zl_far_use_prev(pos)) {
+            e = __ldg(ftab + ((size_t)(reg - 1) << flog) + hF);
+            q = ((reg - 1) << ZL_FAR_REGION_LOG) + (e >> 8);
+            if (e != ZL_FAR_EMPTY && (e & 255u) == (hx & 255u) && pos - q > 65535u && pos - q < P.farMaxOff) {
+                const u32 l = zl_match_len_far(wbase, bias, lastWord, p, fw, fbias, q, lo, hi, lim);
+                if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; }
+            }
+        }
+        if (bestOff) M[p] = (bestOff << 8) | bestLen;
+    }
+}
+
 #define ZL_MATCH_SCRATCH 4096u      // u16 slots of the duplicate-detection scratch (8 KB per CTA)
 template <bool kLong, bool kDict>
 __global__ void __launch_bounds__(ZL_MATCH_WARPS * 32)
-zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 slotM, ZlEncParams P, const ZlEncDictDev* __restrict__ dict,
-           const ZlEncFrame* __restrict__ frames, const u32* __restrict__ farArena)
+zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 slotM, ZlEncParams P, const ZlEncDictDev* __restrict__ dict)
 {
     extern __shared__ __align__(16) u8 smraw[];
     u16* tabS = reinterpret_cast<u16*>(smraw);
@@ -166,13 +214,6 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
     const u32 lastWord = (bias + n - 1) >> 2;
     const u32 ngroups = (n + 31) >> 5;
     const u32 ltMask = (1u << lane) - 1;
-    // far candidates (frames of more than one block): the frame-wide table of earliest occurrences, read through the frame's own words
-    const u64 fpad = farArena ? frames[b.frame].pad : 0ull;
-    const u32 flog = (u32)(fpad >> 56);
-    const u32* __restrict__ ftab = farArena + (fpad & ZL_FAR_OFF_MASK);
-    const u8* fbase = b.src - b.pad;
-    const u32 fbias = (u32)(((size_t)fbase) & 3);
-    const u32* __restrict__ fw = reinterpret_cast<const u32*>(fbase - fbias);
     // Each warp takes TWO consecutive 32-position groups per turn (64 positions): their loads and verifications overlap,
     // and the table token is passed half as often.
     const u32 npairs = (ngroups + 1) >> 1;
@@ -272,24 +313,6 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
                     if (bestLen < lim) {
                         const u32 l = zl_dict_match(*dict, dict->tabS, zl_hash_short(lo[h], hi[h], P.mls, dict->hlogS), wbase, bias, lastWord, p, lo[h], hi[h], lim, P.mls, dOff);
                         if (l > bestLen) { bestLen = l; bestOff = dOff; }
-                    }
-                }
-                if (flog) {                                                    // own region first, then the one before it
-                    const u32 pos = b.pad + p, hx = zl_far_hash(lo[h], hi[h], flog), hF = hx >> 8, reg = pos >> ZL_FAR_REGION_LOG;
-                    bool got = false;
-                    u32 e = __ldg(ftab + ((size_t)reg << flog) + hF);
-                    u32 q = (reg << ZL_FAR_REGION_LOG) + (e >> 8);
-                    if ((e & 255u) == (hx & 255u) && q < pos && pos - q > 65535u && pos - q < P.farMaxOff) {      // (an empty entry has q >= pos)
-                        const u32 l = zl_match_len_far(wbase, bias, lastWord, p, fw, fbias, q, lo[h], hi[h], lim);
-                        if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; got = true; }
-                    }
-                    if (!got && zl_far_use_prev(pos)) {
-                        e = __ldg(ftab + ((size_t)(reg - 1) << flog) + hF);
-                        q = ((reg - 1) << ZL_FAR_REGION_LOG) + (e >> 8);
-                        if (e != ZL_FAR_EMPTY && (e & 255u) == (hx & 255u) && pos - q > 65535u && pos - q < P.farMaxOff) {
-                            const u32 l = zl_match_len_far(wbase, bias, lastWord, p, fw, fbias, q, lo[h], hi[h], lim);
-                            if (zl_far_better(l, bestLen, P.mls)) { bestLen = l; bestOff = pos - q; }
-                        }
                     }
                 }
                 if (bestLen) m = (bestOff << 8) | bestLen;
@@ -800,12 +823,13 @@ cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st)
     if (nb && L.far) zl_k_far_build<<<nb * ZL_FAR_CHUNKS, 256, 0, st>>>(L.blocks, L.frames, L.far);
     if (nb) {
         if (L.params.hlogL) {
-            if (useDict) zl_k_match<true, true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, L.dict, L.frames, L.far);
-            else zl_k_match<true, false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, nullptr, L.frames, L.far);
+            if (useDict) zl_k_match<true, true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, L.dict);
+            else zl_k_match<true, false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, nullptr);
         } else {
-            if (useDict) zl_k_match<false, true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, L.dict, L.frames, L.far);
-            else zl_k_match<false, false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, nullptr, L.frames, L.far);
+            if (useDict) zl_k_match<false, true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, L.dict);
+            else zl_k_match<false, false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, nullptr);
         }
+        if (L.far) zl_k_far_match<<<nb * ZL_FAR_CHUNKS, 256, 0, st>>>(L.blocks, L.frames, L.far, L.M, L.slotM, L.params);
     }
     if (ev) cudaEventRecord(ev[1], st);
     {   const u32 segmented = L.maxBlock > ZL_PARSE_SEG ? 1u : 0u;
