@@ -27,6 +27,14 @@ cudaError_t zl_enc_upload_const()
 // ---------------------------------------------------------------------------------------------- helpers
 __device__ __forceinline__ void zl_bar_sync(u32 id, u32 count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void zl_bar_arrive(u32 id, u32 count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// shared-memory mbarriers (one arrival per phase): the table token of zl_k_match when a CTA has more warps than named barriers
+__device__ __forceinline__ void zl_mbar_init(u64* bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void zl_mbar_arrive(u64* bar) { asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((u32)__cvta_generic_to_shared(bar)) : "memory"); }
+__device__ __forceinline__ void zl_mbar_wait(u64* bar, u32 parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tZL_MBAR_WAIT:\n\tmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t@p bra ZL_MBAR_DONE;\n\tbra ZL_MBAR_WAIT;\n\tZL_MBAR_DONE:\n\t}"
+                 ::"r"((u32)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
 
 // 8 bytes at byte offset `bo` from the 4-aligned base; words past `lastWord` are clamped (callers bound lengths by the block size)
 __device__ __forceinline__ void zl_ld8(const u32* __restrict__ wbase, u32 bo, u32 lastWord, u32& lo, u32& hi)
@@ -35,17 +43,30 @@ __device__ __forceinline__ void zl_ld8(const u32* __restrict__ wbase, u32 bo, u3
     const u32 a = __ldg(wbase + min(wi, lastWord)), b = __ldg(wbase + min(wi + 1, lastWord)), c = __ldg(wbase + min(wi + 2, lastWord));
     lo = __funnelshift_r(a, b, sh); hi = __funnelshift_r(b, c, sh);
 }
-// length of the match between positions p and q (< p), capped at lim (<= ZL_M_CAP); (lo, hi) = the 8 bytes at p
+// The same from an 8-ALIGNED base, for candidate positions: every lane reads somewhere else, and the L1 pipe spends a wavefront per lane and
+// load instruction whatever the width -- so two 8-byte loads instead of three 4-byte loads, without a branch (a 16-byte load with a
+// conditional second one was measured slower: the divergent selection cost more than the loads it saved).  lastVec: last 8-byte unit.
+__device__ __forceinline__ void zl_ld8v(const u32* __restrict__ wbase, u32 bo, u32 lastVec, u32& lo, u32& hi)
+{
+    const uint2* __restrict__ vb = reinterpret_cast<const uint2*>(wbase);
+    const u32 vi = bo >> 3;
+    const uint2 a = __ldg(vb + min(vi, lastVec)), b = __ldg(vb + min(vi + 1, lastVec));
+    const bool up = (bo & 4) != 0;
+    const u32 w0 = up ? a.y : a.x, w1 = up ? b.x : a.y, w2 = up ? b.y : b.x;
+    const u32 sh = (bo & 3) * 8;
+    lo = __funnelshift_r(w0, w1, sh); hi = __funnelshift_r(w1, w2, sh);
+}
+// length of the match between positions p and q (< p), capped at lim (<= ZL_M_CAP); (lo, hi) = the 8 bytes at p.  wbase is 8-aligned here.
 __device__ __forceinline__ u32 zl_match_len(const u32* __restrict__ wbase, u32 bias, u32 lastWord, u32 p, u32 q, u32 lo, u32 hi, u32 lim)
 {
     u32 blo, bhi;
-    zl_ld8(wbase, bias + q, lastWord, blo, bhi);
+    zl_ld8v(wbase, bias + q, lastWord >> 1, blo, bhi);
     u32 len = zl_common8(lo, hi, blo, bhi);
     if (len == 8) {
         for (u32 k = 8; k < lim; k += 8) {
             u32 alo, ahi;
             zl_ld8(wbase, bias + p + k, lastWord, alo, ahi);
-            zl_ld8(wbase, bias + q + k, lastWord, blo, bhi);
+            zl_ld8v(wbase, bias + q + k, lastWord >> 1, blo, bhi);
             const u32 c = zl_common8(alo, ahi, blo, bhi);
             len += c;
             if (c < 8) break;
@@ -203,13 +224,18 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
     const ZlEncBlock b = blocks[blockIdx.x];
     const u32 n = b.srcSize;
     u32* __restrict__ M = Marena + (size_t)blockIdx.x * slotM;
+#if ZL_MATCH_WARPS > 15
+    __shared__ u64 token[ZL_MATCH_WARPS];
+    if (tid < ZL_MATCH_WARPS) zl_mbar_init(&token[tid], 1);
+    u32 nwait = 0;
+#endif
     {   const u32 bytes = (2u << P.hlogS) + (kLong ? (2u << P.hlogL) : 0u);
         uint4* z = reinterpret_cast<uint4*>(smraw);
         for (u32 i = tid; i < bytes / 16; i += ZL_MATCH_WARPS * 32) z[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
     if (n == 0) return;
-    const u32 bias = (u32)(((size_t)b.src) & 3);
+    const u32 bias = (u32)(((size_t)b.src) & 7);      // 8-aligned base: zl_ld8v
     const u32* __restrict__ wbase = reinterpret_cast<const u32*>(b.src - bias);
     const u32 lastWord = (bias + n - 1) >> 2;
     const u32 ngroups = (n + 31) >> 5;
@@ -217,7 +243,17 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
     // Each warp takes TWO consecutive 32-position groups per turn (64 positions): their loads and verifications overlap,
     // and the table token is passed half as often.
     const u32 npairs = (ngroups + 1) >> 1;
+    // the pair's own bytes are fetched one turn ahead: a warp used to spend a quarter of its stall samples waiting for this load (ncu)
+    u32 wq[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) wq[h] = lane < 11 ? __ldg(wbase + min(((bias + ((2 * warp + h) << 5)) >> 2) + lane, lastWord)) : 0u;
     for (u32 pr = warp; pr < npairs; pr += ZL_MATCH_WARPS) {
+        u32 wc[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            wc[h] = wq[h];
+            wq[h] = lane < 11 ? __ldg(wbase + min(((bias + ((2 * (pr + ZL_MATCH_WARPS) + h) << 5)) >> 2) + lane, lastWord)) : 0u;
+        }
         u32 lo[2], hi[2], hS[2], hL[2], eS[2], eL[2];
         i32 prevS[2], prevL[2];
         bool valid[2], lastS[2], lastL[2];
@@ -226,8 +262,7 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
             const u32 g = 2 * pr + h;
             const u32 p = (g << 5) + lane;
             // the 8 bytes at every position of the group from 11 coalesced words
-            const u32 wb = (bias + (g << 5)) >> 2;
-            const u32 w = lane < 11 ? __ldg(wbase + min(wb + lane, lastWord)) : 0u;
+            const u32 w = wc[h];
             const u32 bo = (bias & 3) + lane, j = bo >> 2, sh = (bo & 3) * 8;
             const u32 w0 = __shfl_sync(ZL_FULL, w, j), w1 = __shfl_sync(ZL_FULL, w, j + 1), w2 = __shfl_sync(ZL_FULL, w, j + 2);
             lo[h] = __funnelshift_r(w0, w1, sh); hi[h] = __funnelshift_r(w1, w2, sh);
@@ -267,7 +302,11 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
             }
         }
         // ---- table section, in position order across warps (and across the two groups: same-warp shared-memory order)
+#if ZL_MATCH_WARPS > 15
+        if (pr > 0) { zl_mbar_wait(&token[warp], nwait & 1u); nwait++; }
+#else
         if (ZL_MATCH_WARPS > 1 && pr > 0) zl_bar_sync(1 + warp, 64);
+#endif
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const u32 p = ((2 * pr + h) << 5) + lane;
@@ -283,7 +322,11 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
             }
             __syncwarp();
         }
+#if ZL_MATCH_WARPS > 15
+        if (pr + 1 < npairs) { __syncwarp(); if (lane == 0) zl_mbar_arrive(&token[(warp + 1) % ZL_MATCH_WARPS]); }
+#else
         if (ZL_MATCH_WARPS > 1 && pr + 1 < npairs) { __threadfence_block(); zl_bar_arrive(1 + (warp + 1) % ZL_MATCH_WARPS, 64); }
+#endif
         // ---- verify
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -370,7 +413,7 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
     const u32 segBeg = sg * ZL_PARSE_SEG, segEnd = min(n, segBeg + ZL_PARSE_SEG);
     u64* __restrict__ recs = recsAll + (size_t)sg * ZL_PARSE_SEG_RECS;
     u8* __restrict__ lit = litAll + segBeg;
-    const u32 bias = (u32)(((size_t)b.src) & 3);
+    const u32 bias = (u32)(((size_t)b.src) & 7);      // 8-aligned base: zl_ld8v
     const u32* __restrict__ wbase = reinterpret_cast<const u32*>(b.src - bias);
     const u32 lastWord = n ? (bias + n - 1) >> 2 : 0;
     const u32 ltMask = (1u << lane) - 1;

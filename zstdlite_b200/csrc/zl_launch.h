@@ -107,7 +107,9 @@ cudaError_t zl_launch_xxh64(const u8* const* ptrs, const u32* sizes, u64* out, u
 #include "zl_enc_entropy.cuh"
 #include "zl_enc_match.cuh"
 
-#define ZL_MATCH_WARPS 15     // named barriers 1..15 carry the table token (0 is __syncthreads)
+#ifndef ZL_MATCH_WARPS
+#define ZL_MATCH_WARPS 15     // named barriers 1..15 carry the table token (0 is __syncthreads); more than 15 warps share them (zl_k_match)
+#endif
 #define ZL_PARSE_WARPS (ZL_BLOCKSIZE_MAX / ZL_PARSE_SEG)     // one warp per segment of a block
 #define ZL_ASM_WARPS 4
 #define ZL_ENT_WARPS 4       // warps (= blocks) per CTA in the two entropy kernels
