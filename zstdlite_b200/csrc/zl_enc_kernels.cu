@@ -441,11 +441,12 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
             if (w0 >= segEnd || p >= w0 + 32) continue;          // past the end / window entirely inside a match
             const u32 m = mc[k], byte = bc[k];
             const u32 pos = w0 + lane;
-            u32 len = m & 0xFF;
+            // a match ends with its segment; one clipped below the format's minimum of 3 is no match (its bytes are literals)
+            u32 len = min(m & 0xFFu, pos < segEnd ? segEnd - pos : 0u);
             const u32 off = m >> 8;
             u32 c = p > w0 ? p - w0 : 0;
             const u32 cstart = c;
-            const u32 matchMask = __ballot_sync(ZL_FULL, len != 0);
+            const u32 matchMask = __ballot_sync(ZL_FULL, len >= 3);
             u32 takenMask = 0, myLL = 0, myOB = 0;
             for (;;) {
                 const u32 mm = c < 32 ? (matchMask >> c) << c : 0u;
@@ -454,9 +455,7 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
                 u32 l = __shfl_sync(ZL_FULL, len, c1);
                 u32 o = __shfl_sync(ZL_FULL, off, c1);
                 u32 pos1 = w0 + c1, c2 = c1;
-                if (l >= ZL_M_VERIFY && o <= pos1) l = zl_extend_match(wbase, bias, lastWord, segEnd, pos1, o, lane, ZL_M_VERIFY);   // (matches into the dictionary are not extended)
-                if (pos1 + l > segEnd) l = segEnd - pos1;        // a match ends with its segment
-                if (l < 3) { c = c1 + 1; continue; }             // (clipped below the format's minimum: literals)
+                if (l >= ZL_M_VERIFY && o <= pos1) l = zl_extend_match(wbase, bias, lastWord, segEnd, pos1, o, lane, ZL_M_VERIFY);   // (stops at segEnd; matches into the dictionary are not extended)
                 if (repPref && reps.r0 && o != reps.r0) {
                     // Dictionary mode only: lanes 0..2 probe the most recent offset at pos1, pos1+1, pos1+2 (same window).  Such a
                     // match costs no offset bits; it is taken when it is at most 4 bytes shorter (cf. the repcode checks at
