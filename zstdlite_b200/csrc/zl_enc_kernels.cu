@@ -507,8 +507,9 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
     if (lane == 0) { segSeq[warp] = nseq; segLit[warp] = nlit; segTail[warp] = segBeg < n ? segEnd - anchor : 0u; }
     __syncthreads();
     // ---- pack the segments: records and literals of segment w move down behind those of the segments before it (the CTA moves
-    // one segment after the other, 128 elements per step, reads before writes: source and destination may overlap); the literals
-    // a segment ends with belong to the first sequence that follows (its litLength grows by that count)
+    // one segment after the other, a step at a time, reads before writes: source and destination may overlap -- but only inside a
+    // step, because data moves DOWN: what a step overwrites is below everything later steps read, so one barrier a step is enough);
+    // the literals a segment ends with belong to the first sequence that follows (its litLength grows by that count)
     const u32 tid = threadIdx.x;
     u32 dSeq = segSeq[0], dLit = segLit[0], carry = segTail[0];
     for (u32 w = 1; w < ZL_PARSE_WARPS; w++) {
@@ -520,15 +521,15 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
             if (i == 0) r += carry;                              // litLength is the low field of a record (zl_enc_rec)
             __syncthreads();
             if (i < ns) recsAll[dSeq + i] = r;
-            __syncthreads();
         }
         const u8* __restrict__ ls = litAll + (size_t)w * ZL_PARSE_SEG;
-        for (u32 i0 = 0; i0 < nl; i0 += ZL_PARSE_WARPS * 32) {
-            const u32 i = i0 + tid;
-            const u8 v = i < nl ? ls[i] : (u8)0;
+        for (u32 i0 = 0; i0 < nl; i0 += 4 * ZL_PARSE_WARPS * 32) {
+            u8 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const u32 i = i0 + k * ZL_PARSE_WARPS * 32 + tid; v[k] = i < nl ? ls[i] : (u8)0; }
             __syncthreads();
-            if (i < nl) litAll[dLit + i] = v;
-            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const u32 i = i0 + k * ZL_PARSE_WARPS * 32 + tid; if (i < nl) litAll[dLit + i] = v[k]; }
         }
         carry = ns ? segTail[w] : carry + segTail[w];
         dSeq += ns; dLit += nl;
