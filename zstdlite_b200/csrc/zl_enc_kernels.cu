@@ -476,7 +476,9 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
                     }
                 }
                 const u32 ll = pos1 - anchor;
-                const u32 ob = zl_rep_encode(reps, o, ll);
+                u32 ob;                                          // most offsets are new: skip the repeat-offset cases with one (uniform) branch
+                if (o != reps.r0 && o != reps.r1 && o != reps.r2 && o + 1 != reps.r0) { ob = o + 3; reps.r2 = reps.r1; reps.r1 = reps.r0; reps.r0 = o; }
+                else ob = zl_rep_encode(reps, o, ll);
                 if (lane == c2) { len = l; myLL = ll; myOB = ob; }
                 takenMask |= 1u << c2;
                 anchor = pos1 + l;
