@@ -56,6 +56,20 @@ __device__ __forceinline__ void zl_ld8v(const u32* __restrict__ wbase, u32 bo, u
     const u32 sh = (bo & 3) * 8;
     lo = __funnelshift_r(w0, w1, sh); hi = __funnelshift_r(w1, w2, sh);
 }
+// the rest of a match whose first 8 bytes are equal (zl_match_len below), capped at lim
+__device__ __forceinline__ u32 zl_match_more(const u32* __restrict__ wbase, u32 bias, u32 lastWord, u32 p, u32 q, u32 lim)
+{
+    u32 len = 8;
+    for (u32 k = 8; k < lim; k += 8) {                        // (16 bytes a step, four loads in flight, was measured slower: +8 % at level 1)
+        u32 alo, ahi, blo, bhi;
+        zl_ld8(wbase, bias + p + k, lastWord, alo, ahi);
+        zl_ld8v(wbase, bias + q + k, lastWord >> 1, blo, bhi);
+        const u32 c = zl_common8(alo, ahi, blo, bhi);
+        len += c;
+        if (c < 8) break;
+    }
+    return len < lim ? len : lim;
+}
 // length of the match between positions p and q (< p), capped at lim (<= ZL_M_CAP); (lo, hi) = the 8 bytes at p.  wbase is 8-aligned here.
 __device__ __forceinline__ u32 zl_match_len(const u32* __restrict__ wbase, u32 bias, u32 lastWord, u32 p, u32 q, u32 lo, u32 hi, u32 lim)
 {
@@ -305,7 +319,9 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
 #if ZL_MATCH_WARPS > 15
         if (pr > 0) { zl_mbar_wait(&token[warp], nwait & 1u); nwait++; }
 #else
+#ifndef ZL_EXP_NOTOKEN      /* (timing experiment only: the warps run free and the tables are updated in any order) */
         if (ZL_MATCH_WARPS > 1 && pr > 0) zl_bar_sync(1 + warp, 64);
+#endif
 #endif
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -325,7 +341,11 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
 #if ZL_MATCH_WARPS > 15
         if (pr + 1 < npairs) { __syncwarp(); if (lane == 0) zl_mbar_arrive(&token[(warp + 1) % ZL_MATCH_WARPS]); }
 #else
-        if (ZL_MATCH_WARPS > 1 && pr + 1 < npairs) { __threadfence_block(); zl_bar_arrive(1 + (warp + 1) % ZL_MATCH_WARPS, 64); }
+        // (no fence before the arrive: st.shared; bar.arrive | bar.sync; ld.shared is the producer / consumer pattern the PTX manual gives
+        //  for named barriers, and a membar here also waited for the global loads this warp has in flight -- the prefetch above)
+#ifndef ZL_EXP_NOTOKEN
+        if (ZL_MATCH_WARPS > 1 && pr + 1 < npairs) zl_bar_arrive(1 + (warp + 1) % ZL_MATCH_WARPS, 64);
+#endif
 #endif
         // ---- verify
 #pragma unroll
@@ -336,15 +356,25 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
             if (valid[h]) {
                 const u32 lim = min(n - p, ZL_M_CAP), limV = min(n - p, ZL_M_VERIFY);     // dictionary / in-block candidates
                 u32 bestLen = 0, bestOff = 0;
-                if (kLong) {
-                    const i32 qL = prevL[h] >= 0 ? (i32)((g << 5) + (u32)prevL[h]) : zl_cand_pos(eL[h], p);
-                    if (qL >= 0) { const u32 l = zl_match_len(wbase, bias, lastWord, p, (u32)qL, lo[h], hi[h], limV); if (l >= P.mls) { bestLen = l; bestOff = p - (u32)qL; } }
-                }
+                // the first 8 bytes of BOTH candidates are requested before either is looked at: the two loads are a cache miss each more often
+                // than not, and one after the other they were the longest wait of a warp's turn
+                const i32 qL = !kLong ? -1 : (prevL[h] >= 0 ? (i32)((g << 5) + (u32)prevL[h]) : zl_cand_pos(eL[h], p));
                 const i32 qS = prevS[h] >= 0 ? (i32)((g << 5) + (u32)prevS[h]) : zl_cand_pos(eS[h], p);
+                u32 cLlo = 0, cLhi = 0, cSlo = 0, cShi = 0;
+                if (kLong && qL >= 0) zl_ld8v(wbase, bias + (u32)qL, lastWord >> 1, cLlo, cLhi);
+                if (qS >= 0) zl_ld8v(wbase, bias + (u32)qS, lastWord >> 1, cSlo, cShi);
+                if (kLong && qL >= 0) {
+                    u32 l = zl_common8(lo[h], hi[h], cLlo, cLhi);
+                    if (l == 8) l = zl_match_more(wbase, bias, lastWord, p, (u32)qL, limV);
+                    if (l > limV) l = limV;
+                    if (l >= P.mls) { bestLen = l; bestOff = p - (u32)qL; }
+                }
                 // a verified long-hash candidate (>= 8 bytes) is taken as it is, like the reference's double-fast search (zstd.c:29989);
                 // and a longer match is impossible once the limit is reached
                 if (qS >= 0 && bestLen < 8 && bestLen < limV) {
-                    const u32 l = zl_match_len(wbase, bias, lastWord, p, (u32)qS, lo[h], hi[h], limV);
+                    u32 l = zl_common8(lo[h], hi[h], cSlo, cShi);
+                    if (l == 8) l = zl_match_more(wbase, bias, lastWord, p, (u32)qS, limV);
+                    if (l > limV) l = limV;
                     if (l >= P.mls && l > bestLen) { bestLen = l; bestOff = p - (u32)qS; }
                 }
                 if (kDict && (b.flags & ZL_BLK_FIRST) && bestLen < lim) {      // dictionary content precedes the first block
