@@ -144,6 +144,11 @@ size_t zl_dctx_set_gpus(ZSTD_DCtx* dctx, int n);
  * them on the level-3 engine, which is announced once on stderr.  zl_cctx_engine_level: the engine a context's level runs (1..3). */
 size_t zl_cctx_allow_level_fallback(ZSTD_CCtx* cctx, int on);
 int zl_cctx_engine_level(const ZSTD_CCtx* cctx);
+/* ZSTD_c_windowLog (src/zstd/zstd.h:347): blocks are 128 KiB and searched on their own with offsets up to 64 KiB; frames of more than
+ * one block additionally look every position up in per-region tables of earlier occurrences ("far candidates", offsets below 2^24)
+ * and declare a window that covers them, at most 2^24.  0 (default) and 24..31: that; 18..23: far offsets stay below 2^windowLog;
+ * 17: no far candidates (the fastest setting for one large buffer, about 12 % larger output on text); below 17:
+ * parameter_outOfBound, a window smaller than a block cannot be honoured. */
 
 /* CUDA stream (cudaStream_t passed as void*) the context launches on; default: a private non-blocking stream */
 size_t zl_dctx_set_stream(ZSTD_DCtx* dctx, void* cuda_stream);
