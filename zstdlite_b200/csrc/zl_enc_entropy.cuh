@@ -404,6 +404,15 @@ ZL_HD u32 zl_huf_chunk_bits(const u8* nbBits, const u8* lit, u32 beg, u32 end)
 {
     u32 bits = 0, i = beg;
     while (i < end && (i & 3)) bits += nbBits[lit[i++]];
+    // (16 bytes a step, the four loads issued together: every lane streams through its own chunk, so each load is a cache miss of its
+    //  own and one after the other they were most of this kernel's time)
+    for (; i + 16 <= end; i += 16) {
+        u32 v[4];
+#pragma unroll
+        for (u32 q = 0; q < 4; q++) v[q] = *(const u32*)(lit + i + 4 * q);
+#pragma unroll
+        for (u32 q = 0; q < 4; q++) bits += nbBits[v[q] & 0xFF] + nbBits[(v[q] >> 8) & 0xFF] + nbBits[(v[q] >> 16) & 0xFF] + nbBits[v[q] >> 24];
+    }
     for (; i + 4 <= end; i += 4) { const u32 v = *(const u32*)(lit + i); bits += nbBits[v & 0xFF] + nbBits[(v >> 8) & 0xFF] + nbBits[(v >> 16) & 0xFF] + nbBits[v >> 24]; }
     while (i < end) bits += nbBits[lit[i++]];
     return bits;
@@ -417,6 +426,18 @@ ZL_HD void zl_huf_encode_chunk(const u16* code, const u8* lit, u32 beg, u32 end,
 #define ZL_CH_SYM(s) { const u32 e = code[s]; acc |= (u64)(e & 0xFFF) << n; n += e >> 12; }
     u32 i = end;
     while (i > beg && (i & 3)) { ZL_CH_SYM(lit[--i]); ZL_CH_FLUSH(); }
+    while (i >= beg + 16) {                                  // 16 bytes a step, the four loads issued together (see zl_huf_chunk_bits)
+        i -= 16;
+        u32 vv[4];
+#pragma unroll
+        for (u32 q = 0; q < 4; q++) vv[q] = *(const u32*)(lit + i + 4 * q);
+#pragma unroll
+        for (int q = 3; q >= 0; q--) {
+            const u32 v = vv[q];
+            ZL_CH_SYM(v >> 24); ZL_CH_SYM((v >> 16) & 0xFF); ZL_CH_FLUSH();
+            ZL_CH_SYM((v >> 8) & 0xFF); ZL_CH_SYM(v & 0xFF); ZL_CH_FLUSH();
+        }
+    }
     while (i >= beg + 4) {
         i -= 4;
         const u32 v = *(const u32*)(lit + i);
