@@ -628,7 +628,7 @@ zl_k_enc_literals(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u8* 
 struct ZlSeqWarpSm {
     ZlSeqEncSm f;
     u32 stage[96];
-    u32 codes[32];           // cLL | cOF<<8 | cML<<16 of the round's sequences
+    uint2 dd[3][32];         // (deltaNbBits, deltaFindState) of the round's sequences per table: looked up by all lanes, consumed by the chains
     u16 sbv[3][32];          // nbBits<<10 | bits emitted by each chain for the round's sequences
     u32 finalState[3];
     u32 pad;
@@ -708,20 +708,24 @@ zl_k_enc_sequences(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u64
             const u64 r = rNext;
             { const u32 jn = j + 32; rNext = jn < nbSeq ? recs[nbSeq - 1 - jn] : 0; }
             const u32 cLL = zl_seq_code(K, 0, r), cOF = zl_seq_code(K, 1, r), cML = zl_seq_code(K, 2, r);
-            w.codes[lane] = cLL | (cOF << 8) | (cML << 16);
+            // everything about a step that does not depend on the running state is fetched here, by the sequence's own lane:
+            // the chain lanes below then do one 8-byte load, the transition and one store per sequence
+            w.dd[0][lane] = make_uint2(f.dNb[0][cLL], (u32)f.dFS[0][cLL]);
+            w.dd[1][lane] = make_uint2(f.dNb[1][cOF], (u32)f.dFS[1][cOF]);
+            w.dd[2][lane] = make_uint2(f.dNb[2][cML], (u32)f.dFS[2][cML]);
             __syncwarp();
             if (lane < 3) {
                 const u32 cnt = min(32u, nbSeq - (rd << 5));
                 u32 s0 = 0;
+                const uint2* dd = w.dd[myT];
                 if (rd == 0) {                              // the first sequence written only initialises the state (zstd.c:21166-21170)
-                    const u32 code = (w.codes[0] >> (8 * myT)) & 0xFF;
-                    st = zl_fse_init_state(tbl, f.dNb[myT][code], f.dFS[myT][code]);
+                    st = zl_fse_init_state(tbl, dd[0].x, (i32)dd[0].y);
                     w.sbv[myT][0] = 0; s0 = 1;
                 }
 #pragma unroll 4
                 for (u32 s = s0; s < cnt; s++) {
-                    const u32 code = (w.codes[s] >> (8 * myT)) & 0xFF;
-                    const u32 e = zl_fse_step(tbl, f.dNb[myT][code], f.dFS[myT][code], st);
+                    const uint2 d = dd[s];
+                    const u32 e = zl_fse_step(tbl, d.x, (i32)d.y, st);
                     w.sbv[myT][s] = (u16)(((e >> 16) << 10) | (e & 0x3FF));
                 }
             }
