@@ -42,14 +42,16 @@ static EmulFar g_far;
 static void emul_match(const u8* src, u32 n, const ZlEncParams& P, std::vector<u32>& M, const EmulDict* D)
 {
     M.assign(n, 0);
-    std::vector<u16> tabS((size_t)1 << P.hlogS, 0), tabL(P.hlogL ? (size_t)1 << P.hlogL : 1, 0);
+    u32 hlogS, hlogL;
+    zl_block_hlog(P, n, hlogS, hlogL);                       // small blocks: small tables (zl_enc_match.cuh)
+    std::vector<u16> tabS((size_t)1 << hlogS, 0), tabL(hlogL ? (size_t)1 << hlogL : 1, 0);
     for (u32 p = 0; p + 8 <= n; p++) {
         const u32 lo = rd32(src + p), hi = rd32(src + p + 4);
-        const u32 hS = zl_hash_short(lo, hi, P.mls, P.hlogS);
+        const u32 hS = zl_hash_short(lo, hi, P.mls, hlogS);
         const i32 qS = zl_cand_pos(tabS[hS], p); tabS[hS] = (u16)p;
         u32 bestLen = 0, bestOff = 0;
         if (P.hlogL) {
-            const u32 hL = zl_hash_long(lo, hi, P.hlogL);
+            const u32 hL = zl_hash_long(lo, hi, hlogL);
             const i32 qL = zl_cand_pos(tabL[hL], p); tabL[hL] = (u16)p;
             if (qL >= 0) { const u32 l = match_len_capped(src, n, p, qL); if (l >= P.mls) { bestLen = l; bestOff = p - (u32)qL; } }
         }

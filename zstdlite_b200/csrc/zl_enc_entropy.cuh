@@ -593,6 +593,16 @@ struct ZlSeqEncSm {
     u16 cumul[3][66];
     ZlSeqEncCtl ctl;
 };
+// Encoding tables that exist before any block is looked at: the three predefined ones (built once per device, zl_enc_init_const) -- the
+// dictionary's live in ZlEncDictDev in the same form.  The device coder copies them with the whole warp instead of building them per block.
+struct ZlEncDefTables { u16 state[3][64]; u32 dNb[3][64]; i32 dFS[3][64]; };
+// In the first block of a frame compressed with a dictionary, blocks with few sequences do not get a table of their own (its description
+// would cost more than it saves next to the dictionary's table): below these counts the choice is between the dictionary's table and the
+// predefined one, and nothing is normalised or built.  The reference decides the same way at these levels (zstd.c:21040-21059: a valid
+// repeat table is taken below 1,000 sequences; dynamicFse_nbSeq_min = (1 << defaultNormLog) * mult >> 3, mult = 10 - strategy).  Without
+// a dictionary the cost comparison stays: on 400-byte objects a table of their own is worth 10 % of the size.
+#define ZL_SEQ_FSE_MIN_LLML 64u
+#define ZL_SEQ_FSE_MIN_OF 32u
 // code of table t (0 LL, 1 OF, 2 ML) for a record
 ZL_HD u32 zl_seq_code(const ZlEncConst& k, u32 t, u64 rec)
 {
@@ -622,8 +632,15 @@ ZL_HD void zl_seq_build_from_hist(ZlSeqEncSm& f, u32 t, u32 nbSeq, u32 maxSym, u
     }
     u32 costDef = 0xFFFFFFFFu;
     if (defOk) { u64 cst = 0; for (u32 s = 0; s <= maxSym; s++) cst += (u64)cnt[s] * zl_fse_cost256(def[s], defLog); costDef = (u32)(cst >> 8); }
+    u32 costRep = 0xFFFFFFFFu;                                                // the dictionary's table as a "repeat" table (zstd.c:21034-21076)
+    if (dict && maxSym <= dict->maxSym[t]) {
+        u64 cst = 0; bool ok = true;
+        for (u32 s = 0; s <= maxSym; s++) if (cnt[s]) { if (!dict->norm[t][s]) { ok = false; break; } cst += (u64)cnt[s] * zl_fse_cost256(dict->norm[t][s], dict->log[t]); }
+        if (ok) costRep = (u32)(cst >> 8);
+    }
     u32 costFse = 0xFFFFFFFFu, log = 0, nc = 0;
-    if (nbSeq >= 8 && maxCount != nbSeq) {
+    const bool fewSeqs = defOk && costRep != 0xFFFFFFFFu && nbSeq < (t == 1 ? ZL_SEQ_FSE_MIN_OF : ZL_SEQ_FSE_MIN_LLML);
+    if (nbSeq >= 8 && maxCount != nbSeq && !fewSeqs) {
         // the last sequence's symbol only initialises the state, it is not coded as a transition (zstd.c:21126-21129)
         u32 total = nbSeq;
         if (cnt[lastCode] > 1) { cnt[lastCode]--; total--; }
@@ -633,15 +650,14 @@ ZL_HD void zl_seq_build_from_hist(ZlSeqEncSm& f, u32 t, u32 nbSeq, u32 maxSym, u
             if (nc) { u64 cst = 0; for (u32 s = 0; s <= maxSym; s++) cst += (u64)cnt[s] * zl_fse_cost256(f.norm[t][s], log); costFse = (u32)(cst >> 8) + 8 * nc; }
         }
     }
-    if (dict && maxSym <= dict->maxSym[t]) {                                  // the dictionary's table as a "repeat" table (zstd.c:21034-21076)
-        u64 cst = 0; bool ok = true;
-        for (u32 s = 0; s <= maxSym; s++) if (cnt[s]) { if (!dict->norm[t][s]) { ok = false; break; } cst += (u64)cnt[s] * zl_fse_cost256(dict->norm[t][s], dict->log[t]); }
-        const u32 costRep = ok ? (u32)(cst >> 8) : 0xFFFFFFFFu;
-        if (costRep <= costDef && costRep <= costFse) {
+    {
+        if (costRep != 0xFFFFFFFFu && costRep <= costDef && costRep <= costFse) {
             const u32 dl = dict->log[t];
             c.mode[t] = 3; c.log[t] = dl; c.maxSym[t] = dict->maxSym[t]; c.hdrSize[t] = 0;
+#if !defined(__CUDA_ARCH__)                                                      // (the device coder copies the dictionary's tables with the whole warp)
             for (u32 i = 0; i < (1u << dl); i++) f.state[t][i] = dict->state[t][i];
             for (u32 s = 0; s < 64; s++) { f.dNb[t][s] = dict->dNb[t][s]; f.dFS[t][s] = dict->dFS[t][s]; }
+#endif
             return;
         }
     }
@@ -652,9 +668,11 @@ ZL_HD void zl_seq_build_from_hist(ZlSeqEncSm& f, u32 t, u32 nbSeq, u32 maxSym, u
     }
     // predefined table (always available for our offsets: the largest offset code is 17 < 28)
     const u32 defSyms = t == 0 ? 36u : (t == 1 ? 29u : 53u);
-    for (u32 s = 0; s < defSyms; s++) f.norm[t][s] = def[s];
     c.mode[t] = 0; c.log[t] = defLog; c.maxSym[t] = defSyms - 1;
+#if !defined(__CUDA_ARCH__)                                                      // (the device coder has the predefined tables prebuilt: ZlEncDefTables)
+    for (u32 s = 0; s < defSyms; s++) f.norm[t][s] = def[s];
     zl_fse_build_ctable(f.state[t], f.dNb[t], f.dFS[t], f.norm[t], defSyms - 1, defLog, f.symOf[t], f.cumul[t]);
+#endif
 }
 // serial form (CPU emulation): histogram, then the above
 ZL_HD void zl_seq_build_table(ZlSeqEncSm& f, u32 t, const u64* recs, u32 nbSeq, const ZlEncConst& k, const ZlEncDictDev* dict)

@@ -16,12 +16,25 @@
 #include "zl_launch.h"
 
 __constant__ ZlEncConst c_enc;
+__device__ ZlEncDefTables g_encDef;                 // predefined LL / OF / ML encoding tables, built once (zl_enc_entropy.cuh)
 
 cudaError_t zl_enc_upload_const()
 {
     ZlEncConst h;
     zl_enc_const_init(&h);
-    return cudaMemcpyToSymbol(c_enc, &h, sizeof(h));
+    cudaError_t e = cudaMemcpyToSymbol(c_enc, &h, sizeof(h));
+    if (e != cudaSuccess) return e;
+    static ZlEncDefTables d;                        // (the same bytes for every device)
+    static ZlSeqEncSm scratch;
+    for (u32 t = 0; t < 3; t++) {
+        const i16* def = t == 0 ? h.llDef : (t == 1 ? h.ofDef : h.mlDef);
+        const u32 defSyms = t == 0 ? 36u : (t == 1 ? 29u : 53u), defLog = t == 1 ? 5u : 6u;
+        i16 norm[64] = {};
+        for (u32 s = 0; s < defSyms; s++) norm[s] = def[s];
+        for (u32 s = 0; s < 64; s++) { d.dNb[t][s] = 0; d.dFS[t][s] = 0; }
+        zl_fse_build_ctable(d.state[t], d.dNb[t], d.dFS[t], norm, defSyms - 1, defLog, scratch.symOf[t], scratch.cumul[t]);
+    }
+    return cudaMemcpyToSymbol(g_encDef, &d, sizeof(d));
 }
 
 // ---------------------------------------------------------------------------------------------- helpers
@@ -225,10 +238,53 @@ zl_k_far_match(const ZlEncBlock* __restrict__ blocks, const ZlEncFrame* __restri
     }
 }
 
+// M[p] of one position (E1, both kernels): its candidates are the highest lower lane of its group with the same hash (prevS / prevL, -1 = none),
+// else the table entry from before the group (eS / eL); first block of a frame compressed with a dictionary: the dictionary's tables as well.
+template <bool kLong, bool kDict>
+__device__ __forceinline__ u32 zl_match_verify(const u32* __restrict__ wbase, u32 bias, u32 lastWord, u32 n, u32 p, u32 gbase, u32 lo, u32 hi, u32 eS, u32 eL,
+                                               i32 prevS, i32 prevL, u32 mls, bool firstBlock, const ZlEncDictDev* __restrict__ dict)
+{
+    const u32 lim = min(n - p, ZL_M_CAP), limV = min(n - p, ZL_M_VERIFY);     // dictionary / in-block candidates
+    u32 bestLen = 0, bestOff = 0;
+    // the first 8 bytes of BOTH candidates are requested before either is looked at: the two loads are a cache miss each more often
+    // than not, and one after the other they were the longest wait of a warp's turn
+    const i32 qL = !kLong ? -1 : (prevL >= 0 ? (i32)(gbase + (u32)prevL) : zl_cand_pos(eL, p));
+    const i32 qS = prevS >= 0 ? (i32)(gbase + (u32)prevS) : zl_cand_pos(eS, p);
+    u32 cLlo = 0, cLhi = 0, cSlo = 0, cShi = 0;
+    if (kLong && qL >= 0) zl_ld8v(wbase, bias + (u32)qL, lastWord >> 1, cLlo, cLhi);
+    if (qS >= 0) zl_ld8v(wbase, bias + (u32)qS, lastWord >> 1, cSlo, cShi);
+    if (kLong && qL >= 0) {
+        u32 l = zl_common8(lo, hi, cLlo, cLhi);
+        if (l == 8) l = zl_match_more(wbase, bias, lastWord, p, (u32)qL, limV);
+        if (l > limV) l = limV;
+        if (l >= mls) { bestLen = l; bestOff = p - (u32)qL; }
+    }
+    // a verified long-hash candidate (>= 8 bytes) is taken as it is, like the reference's double-fast search (zstd.c:29989);
+    // and a longer match is impossible once the limit is reached
+    if (qS >= 0 && bestLen < 8 && bestLen < limV) {
+        u32 l = zl_common8(lo, hi, cSlo, cShi);
+        if (l == 8) l = zl_match_more(wbase, bias, lastWord, p, (u32)qS, limV);
+        if (l > limV) l = limV;
+        if (l >= mls && l > bestLen) { bestLen = l; bestOff = p - (u32)qS; }
+    }
+    if (kDict && firstBlock && bestLen < lim) {      // dictionary content precedes the first block
+        u32 dOff = 0;
+        if (kLong) {
+            const u32 l = zl_dict_match(*dict, dict->tabL, zl_hash_long(lo, hi, dict->hlogL), wbase, bias, lastWord, p, lo, hi, lim, mls, dOff);
+            if (l > bestLen) { bestLen = l; bestOff = dOff; }
+        }
+        if (bestLen < lim) {
+            const u32 l = zl_dict_match(*dict, dict->tabS, zl_hash_short(lo, hi, mls, dict->hlogS), wbase, bias, lastWord, p, lo, hi, lim, mls, dOff);
+            if (l > bestLen) { bestLen = l; bestOff = dOff; }
+        }
+    }
+    return bestLen ? ((bestOff << 8) | bestLen) : 0u;
+}
+
 #define ZL_MATCH_SCRATCH 4096u      // u16 slots of the duplicate-detection scratch (8 KB per CTA)
 template <bool kLong, bool kDict>
 __global__ void __launch_bounds__(ZL_MATCH_WARPS * 32)
-zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 slotM, ZlEncParams P, const ZlEncDictDev* __restrict__ dict)
+zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 slotM, ZlEncParams P, const ZlEncDictDev* __restrict__ dict, u32 skipSmall)
 {
     extern __shared__ __align__(16) u8 smraw[];
     u16* tabS = reinterpret_cast<u16*>(smraw);
@@ -237,15 +293,19 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ZlEncBlock b = blocks[blockIdx.x];
     const u32 n = b.srcSize;
+    if (skipSmall && n <= ZL_SMALL_BLOCK) return;                        // zl_k_match_small's
+    u32 hlogS, hlogL;
+    zl_block_hlog(P, n, hlogS, hlogL);                                   // (the layout keeps the level's sizes; a small block uses less of it)
     u32* __restrict__ M = Marena + (size_t)blockIdx.x * slotM;
 #if ZL_MATCH_WARPS > 15
     __shared__ u64 token[ZL_MATCH_WARPS];
     if (tid < ZL_MATCH_WARPS) zl_mbar_init(&token[tid], 1);
     u32 nwait = 0;
 #endif
-    {   const u32 bytes = (2u << P.hlogS) + (kLong ? (2u << P.hlogL) : 0u);
-        uint4* z = reinterpret_cast<uint4*>(smraw);
-        for (u32 i = tid; i < bytes / 16; i += ZL_MATCH_WARPS * 32) z[i] = make_uint4(0, 0, 0, 0);
+    {   uint4* z = reinterpret_cast<uint4*>(tabS);
+        for (u32 i = tid; i < (2u << hlogS) / 16; i += ZL_MATCH_WARPS * 32) z[i] = make_uint4(0, 0, 0, 0);
+        z = reinterpret_cast<uint4*>(tabL);
+        if (kLong) for (u32 i = tid; i < (2u << hlogL) / 16; i += ZL_MATCH_WARPS * 32) z[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
     if (n == 0) return;
@@ -281,9 +341,9 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
             const u32 w0 = __shfl_sync(ZL_FULL, w, j), w1 = __shfl_sync(ZL_FULL, w, j + 1), w2 = __shfl_sync(ZL_FULL, w, j + 2);
             lo[h] = __funnelshift_r(w0, w1, sh); hi[h] = __funnelshift_r(w1, w2, sh);
             valid[h] = p + 8 <= n;
-            hS[h] = valid[h] ? zl_hash_short(lo[h], hi[h], P.mls, P.hlogS) : (0x10000u + lane);
+            hS[h] = valid[h] ? zl_hash_short(lo[h], hi[h], P.mls, hlogS) : (0x10000u + lane);
             hL[h] = 0; prevS[h] = -1; prevL[h] = -1; lastS[h] = true; lastL[h] = true;
-            if (kLong) hL[h] = valid[h] ? zl_hash_long(lo[h], hi[h], P.hlogL) : (0x10000u + lane);
+            if (kLong) hL[h] = valid[h] ? zl_hash_long(lo[h], hi[h], hlogL) : (0x10000u + lane);
             // The tables are updated as if the 32 positions of a group were inserted one after the other: an entry ends up with the HIGHEST
             // lane of its hash (lastS), and a lane's candidate is the highest LOWER lane with its hash (prevS), else the entry from before the
             // group.  __match_any_sync answers both, but costs about 64 cycles of the ADU pipe an instruction, and with one or two of them
@@ -352,46 +412,75 @@ zl_k_match(const ZlEncBlock* __restrict__ blocks, u32* __restrict__ Marena, u32 
         for (int h = 0; h < 2; h++) {
             const u32 g = 2 * pr + h;
             const u32 p = (g << 5) + lane;
-            u32 m = 0;
-            if (valid[h]) {
-                const u32 lim = min(n - p, ZL_M_CAP), limV = min(n - p, ZL_M_VERIFY);     // dictionary / in-block candidates
-                u32 bestLen = 0, bestOff = 0;
-                // the first 8 bytes of BOTH candidates are requested before either is looked at: the two loads are a cache miss each more often
-                // than not, and one after the other they were the longest wait of a warp's turn
-                const i32 qL = !kLong ? -1 : (prevL[h] >= 0 ? (i32)((g << 5) + (u32)prevL[h]) : zl_cand_pos(eL[h], p));
-                const i32 qS = prevS[h] >= 0 ? (i32)((g << 5) + (u32)prevS[h]) : zl_cand_pos(eS[h], p);
-                u32 cLlo = 0, cLhi = 0, cSlo = 0, cShi = 0;
-                if (kLong && qL >= 0) zl_ld8v(wbase, bias + (u32)qL, lastWord >> 1, cLlo, cLhi);
-                if (qS >= 0) zl_ld8v(wbase, bias + (u32)qS, lastWord >> 1, cSlo, cShi);
-                if (kLong && qL >= 0) {
-                    u32 l = zl_common8(lo[h], hi[h], cLlo, cLhi);
-                    if (l == 8) l = zl_match_more(wbase, bias, lastWord, p, (u32)qL, limV);
-                    if (l > limV) l = limV;
-                    if (l >= P.mls) { bestLen = l; bestOff = p - (u32)qL; }
-                }
-                // a verified long-hash candidate (>= 8 bytes) is taken as it is, like the reference's double-fast search (zstd.c:29989);
-                // and a longer match is impossible once the limit is reached
-                if (qS >= 0 && bestLen < 8 && bestLen < limV) {
-                    u32 l = zl_common8(lo[h], hi[h], cSlo, cShi);
-                    if (l == 8) l = zl_match_more(wbase, bias, lastWord, p, (u32)qS, limV);
-                    if (l > limV) l = limV;
-                    if (l >= P.mls && l > bestLen) { bestLen = l; bestOff = p - (u32)qS; }
-                }
-                if (kDict && (b.flags & ZL_BLK_FIRST) && bestLen < lim) {      // dictionary content precedes the first block
-                    u32 dOff = 0;
-                    if (kLong) {
-                        const u32 l = zl_dict_match(*dict, dict->tabL, zl_hash_long(lo[h], hi[h], dict->hlogL), wbase, bias, lastWord, p, lo[h], hi[h], lim, P.mls, dOff);
-                        if (l > bestLen) { bestLen = l; bestOff = dOff; }
-                    }
-                    if (bestLen < lim) {
-                        const u32 l = zl_dict_match(*dict, dict->tabS, zl_hash_short(lo[h], hi[h], P.mls, dict->hlogS), wbase, bias, lastWord, p, lo[h], hi[h], lim, P.mls, dOff);
-                        if (l > bestLen) { bestLen = l; bestOff = dOff; }
-                    }
-                }
-                if (bestLen) m = (bestOff << 8) | bestLen;
-            }
+            const u32 m = valid[h] ? zl_match_verify<kLong, kDict>(wbase, bias, lastWord, n, p, g << 5, lo[h], hi[h], eS[h], eL[h], prevS[h], prevL[h], P.mls,
+                                                                   (b.flags & ZL_BLK_FIRST) != 0, dict) : 0u;
             if (p < n) M[p] = m;
         }
+    }
+}
+
+// E1 for small blocks (<= ZL_SMALL_BLOCK bytes, zl_enc_match.cuh): a WARP per block, ZL_SMALL_WARPS blocks per CTA, 2 + 4 KB of tables per warp.
+// The groups of a block are taken in order by one warp, so there is no token; duplicates inside a group are found through the tables
+// themselves: every lane reads the old entry, stores its position, reads the entry back -- a lane that reads another position shares its hash
+// with a later store, and only then match.any sorts the group out and the highest lane of each hash stores again.
+#define ZL_SMALL_WARPS 8
+template <bool kLong, bool kDict>
+__global__ void __launch_bounds__(ZL_SMALL_WARPS * 32)
+zl_k_match_small(const ZlEncBlock* __restrict__ blocks, u32 nblocks, u32* __restrict__ Marena, u32 slotM, ZlEncParams P, const ZlEncDictDev* __restrict__ dict)
+{
+    constexpr u32 kPer = (2u << ZL_SMALL_HLOG_S) + (kLong ? (2u << ZL_SMALL_HLOG_L) : 0u);
+    __shared__ __align__(16) u8 sm[ZL_SMALL_WARPS * kPer];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 blk = blockIdx.x * ZL_SMALL_WARPS + warp;
+    if (blk >= nblocks) return;
+    const ZlEncBlock b = blocks[blk];
+    const u32 n = b.srcSize;
+    if (n == 0 || n > ZL_SMALL_BLOCK) return;                            // zl_k_match's
+    volatile u16* tabS = reinterpret_cast<u16*>(sm + warp * kPer);
+    volatile u16* tabL = tabS + (1u << ZL_SMALL_HLOG_S);
+    {   uint4* z = reinterpret_cast<uint4*>(sm + warp * kPer);
+        for (u32 i = lane; i < kPer / 16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    u32* __restrict__ M = Marena + (size_t)blk * slotM;
+    const u32 bias = (u32)(((size_t)b.src) & 7);
+    const u32* __restrict__ wbase = reinterpret_cast<const u32*>(b.src - bias);
+    const u32 lastWord = (bias + n - 1) >> 2;
+    const u32 ngroups = (n + 31) >> 5;
+    const u32 ltMask = (1u << lane) - 1;
+    const bool firstBlock = (b.flags & ZL_BLK_FIRST) != 0;
+    u32 wq = lane < 11 ? __ldg(wbase + min((bias >> 2) + lane, lastWord)) : 0u;
+    for (u32 g = 0; g < ngroups; g++) {
+        const u32 w = wq;
+        wq = lane < 11 ? __ldg(wbase + min(((bias + ((g + 1) << 5)) >> 2) + lane, lastWord)) : 0u;
+        const u32 p = (g << 5) + lane;
+        const u32 bo = (bias & 3) + lane, j = bo >> 2, sh = (bo & 3) * 8;
+        const u32 w0 = __shfl_sync(ZL_FULL, w, j), w1 = __shfl_sync(ZL_FULL, w, j + 1), w2 = __shfl_sync(ZL_FULL, w, j + 2);
+        const u32 lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        const bool valid = p + 8 <= n;
+        const u32 hS = valid ? zl_hash_short(lo, hi, P.mls, ZL_SMALL_HLOG_S) : (0x10000u + lane);
+        const u32 hL = !kLong ? 0u : (valid ? zl_hash_long(lo, hi, ZL_SMALL_HLOG_L) : (0x10000u + lane));
+        u32 eS = 0, eL = 0;
+        if (valid) { eS = tabS[hS]; if (kLong) eL = tabL[hL]; }
+        __syncwarp();
+        if (valid) { tabS[hS] = (u16)p; if (kLong) tabL[hL] = (u16)p; }
+        __syncwarp();
+        u32 rS = p, rL = p;
+        if (valid) { rS = tabS[hS]; if (kLong) rL = tabL[hL]; }
+        i32 prevS = -1, prevL = -1;
+        if (__ballot_sync(ZL_FULL, rS != p)) {
+            const u32 mS = __match_any_sync(ZL_FULL, hS);
+            prevS = (mS & ltMask) ? (31 - __clz((int)(mS & ltMask))) : -1;
+            if (valid && (mS >> lane) == 1u) tabS[hS] = (u16)p;          // no higher lane shares the hash: this lane's insert survives
+        }
+        if (kLong && __ballot_sync(ZL_FULL, rL != p)) {
+            const u32 mL = __match_any_sync(ZL_FULL, hL);
+            prevL = (mL & ltMask) ? (31 - __clz((int)(mL & ltMask))) : -1;
+            if (valid && (mL >> lane) == 1u) tabL[hL] = (u16)p;
+        }
+        __syncwarp();
+        const u32 m = valid ? zl_match_verify<kLong, kDict>(wbase, bias, lastWord, n, p, g << 5, lo, hi, eS, eL, prevS, prevL, P.mls, firstBlock, dict) : 0u;
+        if (p < n) M[p] = m;
     }
 }
 
@@ -697,6 +786,21 @@ zl_k_enc_sequences(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u64
     for (u32 i = lane; i < 96; i += 32) w.stage[i] = 0;
     u32 st = 0;                                             // lanes 0-2: running FSE state of their table
     const u32 myT = lane < 3 ? lane : 0;
+    // predefined and dictionary tables are not built per block: all 32 lanes copy the prebuilt ones into the block's slots (a lane building
+    // or copying one alone was most of the time of a 30-sequence block)
+#pragma unroll
+    for (u32 t = 0; t < 3; t++) {
+        const u32 md = f.ctl.mode[t];
+        if (md == 0 || md == 3) {
+            const u16* sS = md == 0 ? g_encDef.state[t] : dict->state[t];
+            const u32* sN = md == 0 ? g_encDef.dNb[t] : dict->dNb[t];
+            const i32* sF = md == 0 ? g_encDef.dFS[t] : dict->dFS[t];
+            const u32 sz = 1u << f.ctl.log[t];
+            for (u32 i = lane; i < sz; i += 32) f.state[t][i] = sS[i];
+            for (u32 i = lane; i < 64; i += 32) { f.dNb[t][i] = sN[i]; f.dFS[t][i] = sF[i]; }
+        }
+    }
+    __syncwarp();
     const u16* tbl = f.state[myT];
     u32 bitPos = 0, ovf = 0;
     const u32 rounds = (nbSeq + 31) >> 5;
@@ -710,9 +814,11 @@ zl_k_enc_sequences(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u64
             const u32 cLL = zl_seq_code(K, 0, r), cOF = zl_seq_code(K, 1, r), cML = zl_seq_code(K, 2, r);
             // everything about a step that does not depend on the running state is fetched here, by the sequence's own lane:
             // the chain lanes below then do one 8-byte load, the transition and one store per sequence
-            w.dd[0][lane] = make_uint2(f.dNb[0][cLL], (u32)f.dFS[0][cLL]);
-            w.dd[1][lane] = make_uint2(f.dNb[1][cOF], (u32)f.dFS[1][cOF]);
-            w.dd[2][lane] = make_uint2(f.dNb[2][cML], (u32)f.dFS[2][cML]);
+            if (j < nbSeq) {                                 // (lanes past the last sequence hold an empty record: its codes are no table indices)
+                w.dd[0][lane] = make_uint2(f.dNb[0][cLL], (u32)f.dFS[0][cLL]);
+                w.dd[1][lane] = make_uint2(f.dNb[1][cOF], (u32)f.dFS[1][cOF]);
+                w.dd[2][lane] = make_uint2(f.dNb[2][cML], (u32)f.dFS[2][cML]);
+            }
             __syncwarp();
             if (lane < 3) {
                 const u32 cnt = min(32u, nbSeq - (rd << 5));
@@ -901,12 +1007,26 @@ cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st)
     if (ev) cudaEventRecord(ev[0], st);
     if (nb && L.far) zl_k_far_build<<<nb * ZL_FAR_CHUNKS, 256, 0, st>>>(L.blocks, L.frames, L.far);
     if (nb) {
-        if (L.params.hlogL) {
-            if (useDict) zl_k_match<true, true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, L.dict);
-            else zl_k_match<true, false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, nullptr);
-        } else {
-            if (useDict) zl_k_match<false, true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, L.dict);
-            else zl_k_match<false, false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, nullptr);
+        // blocks of at most ZL_SMALL_BLOCK bytes go to the warp-per-block kernel, the others to the CTA-per-block one; each skips the other's
+        const u32 skipSmall = L.nSmall ? 1u : 0u;
+        if (L.nSmall) {
+            const u32 gs = (nb + ZL_SMALL_WARPS - 1) / ZL_SMALL_WARPS;
+            if (L.params.hlogL) {
+                if (useDict) zl_k_match_small<true, true><<<gs, ZL_SMALL_WARPS * 32, 0, st>>>(L.blocks, nb, L.M, L.slotM, L.params, L.dict);
+                else zl_k_match_small<true, false><<<gs, ZL_SMALL_WARPS * 32, 0, st>>>(L.blocks, nb, L.M, L.slotM, L.params, nullptr);
+            } else {
+                if (useDict) zl_k_match_small<false, true><<<gs, ZL_SMALL_WARPS * 32, 0, st>>>(L.blocks, nb, L.M, L.slotM, L.params, L.dict);
+                else zl_k_match_small<false, false><<<gs, ZL_SMALL_WARPS * 32, 0, st>>>(L.blocks, nb, L.M, L.slotM, L.params, nullptr);
+            }
+        }
+        if (L.nSmall < nb) {
+            if (L.params.hlogL) {
+                if (useDict) zl_k_match<true, true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, L.dict, skipSmall);
+                else zl_k_match<true, false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, nullptr, skipSmall);
+            } else {
+                if (useDict) zl_k_match<false, true><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, L.dict, skipSmall);
+                else zl_k_match<false, false><<<nb, ZL_MATCH_WARPS * 32, smM, st>>>(L.blocks, L.M, L.slotM, L.params, nullptr, skipSmall);
+            }
         }
         if (L.far) zl_k_far_match<<<nb * ZL_FAR_CHUNKS, 256, 0, st>>>(L.blocks, L.frames, L.far, L.M, L.slotM, L.params);
     }

@@ -44,6 +44,18 @@ static inline ZlEncParams zl_enc_params(int level)
     return p;
 }
 
+// Blocks of at most ZL_SMALL_BLOCK bytes (the small objects of configs[3]: a few hundred bytes each) use 2^10 / 2^11-entry tables whatever
+// the level: a CTA zeroing 96 KB of tables for 400 bytes of input was most of their match time, and with 6 KB of tables a WARP can take a
+// block of its own (zl_k_match_small).  The table size of a block depends on the block alone, never on what else is in the batch.
+#define ZL_SMALL_BLOCK 2048u
+#define ZL_SMALL_HLOG_S 10u
+#define ZL_SMALL_HLOG_L 11u
+ZL_HD void zl_block_hlog(const ZlEncParams& P, u32 blockSize, u32& hlogS, u32& hlogL)
+{
+    const bool small = blockSize <= ZL_SMALL_BLOCK;
+    hlogS = small ? ZL_SMALL_HLOG_S : P.hlogS;
+    hlogL = P.hlogL ? (small ? ZL_SMALL_HLOG_L : P.hlogL) : 0u;
+}
 ZL_HD u32 zl_hash_short(u32 lo, u32 hi, u32 mls, u32 hlog)
 {
     const u64 v = ((u64)hi << 32) | lo;

@@ -154,6 +154,7 @@ struct ZlEncodeLaunch {
     cudaStream_t side = nullptr; cudaEvent_t sideFork = nullptr, sideJoin = nullptr;   // optional: sequence coding next to literal coding
     u32 maxBlock = ZL_BLOCKSIZE_MAX;   // largest block of the wave (the parse kernel walks blocks of more than one segment with a CTA each)
     u32* stats = nullptr;              // dictionary training: sum literal / code statistics here after the parse and stop (zl_dict_train.cuh)
+    u32 nSmall = 0;                    // blocks of at most ZL_SMALL_BLOCK bytes (> 0, non-empty) in the wave: zl_k_match_small takes those
     u32* far = nullptr;                // far-candidate tables of the wave's multi-block frames (zl_enc_match.cuh), preset to 0xFF; null: none
 };
 cudaError_t zl_enc_upload_const();
