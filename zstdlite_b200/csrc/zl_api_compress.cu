@@ -28,7 +28,8 @@ struct ZSTD_CCtx_s {
     cudaStream_t stream = nullptr;
     bool ownStream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t stageEv[ZL_ENC_STAGES + 1] = {};
+    cudaEvent_t stageEv[ZL_ENC_PARTS][ZL_ENC_STAGES + 1] = {};   // per part of a wave (zl_enc_wave)
+    int waveParts = 1;
     double lastKernelMs = 0.0, lastStageMs[ZL_ENC_STAGES] = {};
     unsigned long long launches = 0;
     ZlDevBuf dBlocks, dFrames, dM, dRecs, dLit, dHist, dMetas, dOuts, dPlans, dResults, dXxh, dXxhPtrs, dXxhSizes, dSrc, dDst, dAux, dFar;
@@ -63,7 +64,7 @@ static bool zl_cctx_ready(ZSTD_CCtx* c)
     }
     if (!c->ev0) {
         if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) { (void)cudaGetLastError(); return false; }
-        for (cudaEvent_t& e : c->stageEv) if (cudaEventCreate(&e) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        for (auto& ps : c->stageEv) for (cudaEvent_t& e : ps) if (cudaEventCreate(&e) != cudaSuccess) { (void)cudaGetLastError(); return false; }
     }
     if (!c->side) {
         if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
@@ -95,7 +96,7 @@ ZL_EXPORT size_t ZSTD_freeCCtx(ZSTD_CCtx* c)
     for (ZlDevBuf* b : bufs) b->release();
     c->hBlocks.release(); c->hFrames.release(); c->hResults.release(); c->hAux.release();
     if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
-    for (cudaEvent_t e : c->stageEv) if (e) cudaEventDestroy(e);
+    for (auto& ps : c->stageEv) for (cudaEvent_t e : ps) if (e) cudaEventDestroy(e);
     if (c->side) { cudaStreamDestroy(c->side); cudaEventDestroy(c->sideFork); cudaEventDestroy(c->sideJoin); }
     if (c->copyIn) { cudaStreamDestroy(c->copyIn); cudaStreamDestroy(c->copyOut); for (int i = 0; i < 2; i++) { cudaEventDestroy(c->evIn[i]); cudaEventDestroy(c->evOut[i]); cudaEventDestroy(c->evGather[i]); } }
     c->dOutStage.release();
@@ -261,67 +262,82 @@ static size_t zl_enc_wave(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* src
         return ZL_ERROR(memory_allocation);
     ZlEncBlock* hb = c->hBlocks.as<ZlEncBlock>();
     ZlEncFrame* hf = c->hFrames.as<ZlEncFrame>();
-    size_t bi = 0, farEntries = 0; u32 nSmall = 0;
+    if (c->checksumFlag && (!c->hAux.reserve(nf * 16) || !c->dXxhPtrs.reserve(nf * 8) || !c->dXxhSizes.reserve(nf * 4) || !c->dXxh.reserve(nf * 8))) return ZL_ERROR(memory_allocation);
     static const bool farOff_disabled = getenv("ZL_ENC_NOFAR") != nullptr;      // (development switch)
-    for (size_t i = f0; i < f1; i++) {
-        ZlEncFrame& f = hf[i - f0];
-        memset(&f, 0, sizeof(f));
-        const size_t s = srcSize[i];
-        f.dst = ddst[i]; f.dstCap = dstCap[i]; f.firstBlock = (u32)bi; f.checksumFlag = (u32)c->checksumFlag;
-        const size_t nblk = s ? (s + ZL_BLOCKSIZE_MAX - 1) / ZL_BLOCKSIZE_MAX : 1;
-        f.nblocks = (u32)nblk;
-        // far candidates (zl_enc_match.cuh): a frame of several blocks gets a frame-wide table, while the wave's tables fit 4 GiB
-        bool far = false;
-        if (nblk > 1 && s < 0xFFFFFF00ull && !farOff_disabled && P.farMaxOff) {
-            const u32 flog = zl_far_log(s);
-            const size_t fe = (size_t)zl_far_entries(s);                  // one table per 8 MiB region
-            if (farEntries + fe <= ((size_t)1 << 30)) { f.pad = (u64)farEntries | ((u64)flog << 56); farEntries += fe; far = true; }
-        }
-        f.hdrSize = zl_write_frame_header(f.hdr, s, dict ? c->dictID : 0u, (u32)c->checksumFlag, far ? P.farMaxOff : 0u);
-        for (size_t k = 0; k < nblk; k++) {
-            ZlEncBlock& b = hb[bi++];
-            b.src = dsrc[i] + k * ZL_BLOCKSIZE_MAX;
-            const size_t rem = s - k * ZL_BLOCKSIZE_MAX;
-            b.srcSize = (u32)(rem < ZL_BLOCKSIZE_MAX ? rem : ZL_BLOCKSIZE_MAX);
-            b.frame = (u32)(i - f0);
-            b.flags = (k == 0 ? ZL_BLK_FIRST : 0u) | (k + 1 == nblk ? ZL_BLK_LAST : 0u);
-            b.pad = (u32)(k * ZL_BLOCKSIZE_MAX);
-            if (b.srcSize && b.srcSize <= ZL_SMALL_BLOCK) nSmall++;
-        }
-    }
-    if (farEntries) {
-        if (!c->dFar.reserve(farEntries * 4)) return ZL_ERROR(memory_allocation);
-        cudaMemsetAsync(c->dFar.p, 0xFF, farEntries * 4, st);
-    }
-    cudaMemcpyAsync(c->dBlocks.p, hb, nb * sizeof(ZlEncBlock), cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(c->dFrames.p, hf, nf * sizeof(ZlEncFrame), cudaMemcpyHostToDevice, st);
-    const u64* xxh = nullptr;
-    if (c->checksumFlag) {                                        // XXH64 of every frame's content (zstd.c:27022-27023)
-        if (!c->hAux.reserve(nf * 16) || !c->dXxhPtrs.reserve(nf * 8) || !c->dXxhSizes.reserve(nf * 4) || !c->dXxh.reserve(nf * 8)) return ZL_ERROR(memory_allocation);
-        const u8** hp = c->hAux.as<const u8*>();
-        u32* hs = reinterpret_cast<u32*>(hp + nf);
-        bool anyLarge = false;
-        for (size_t i = f0; i < f1; i++) { hp[i - f0] = dsrc[i]; hs[i - f0] = (u32)srcSize[i]; if (srcSize[i] >= ZL_LARGE_FRAME_BYTES) anyLarge = true; }
-        cudaMemcpyAsync(c->dXxhPtrs.p, hp, nf * 8, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(c->dXxhSizes.p, hs, nf * 4, cudaMemcpyHostToDevice, st);
-        if (zl_launch_xxh64(c->dXxhPtrs.as<const u8*>(), c->dXxhSizes.as<u32>(), c->dXxh.as<u64>(), (u32)nf, st, anyLarge) != cudaSuccess) return ZL_ERROR(GENERIC);
-        c->launches += 1;
-        xxh = c->dXxh.as<u64>();
-    }
-    ZlEncodeLaunch L;
-    L.blocks = c->dBlocks.as<ZlEncBlock>(); L.nblocks = (u32)nb; L.frames = c->dFrames.as<ZlEncFrame>(); L.nframes = (u32)nf;
-    L.params = P; L.dict = dict;
-    L.M = c->dM.as<u32>(); L.slotM = slotM; L.recs = c->dRecs.as<u64>(); L.slotRec = slotRec; L.lit = c->dLit.as<u8>(); L.slotLit = slotLit;
-    L.hist = c->dHist.as<u32>(); L.metas = c->dMetas.as<ZlEncBlockMeta>(); L.outs = c->dOuts.as<ZlEncBlockOut>(); L.plans = c->dPlans.as<ZlEncBlockPlan>();
-    L.streamCapWords = streamCapWords; L.streamWordsPerBlock = streamWordsPerBlock; L.seqCapWords = seqCapWords;
-    L.far = farEntries ? c->dFar.as<u32>() : nullptr;
-    L.nSmall = nSmall;
-    L.results = c->dResults.as<u64>() + f0; L.xxh = xxh; L.stageEv = timeIt ? c->stageEv : nullptr; L.stats = c->statsDev; L.maxBlock = maxBlock;
     static const int sideMode = getenv("ZL_ENC_SIDE") ? atoi(getenv("ZL_ENC_SIDE")) : 2;       // (development: 0 off, 1 few blocks, 2 always; measured +3..4% on 4,096 blocks, +13% on 128)
-    if (sideMode == 2 || (sideMode == 1 && nb <= 1024)) { L.side = c->side; L.sideFork = c->sideFork; L.sideJoin = c->sideJoin; }
-    cudaError_t e = zl_launch_encode(L, st);
-    c->launches += 6 + (farEntries ? 2 : 0) + ((nSmall && nSmall < nb) ? 1 : 0);
-    if (e != cudaSuccess) { fprintf(stderr, "zstdlite_gpu: kernel launch failed: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
+    // A wave of very many one-block frames (configs[3]: 1e5 small objects) is described, uploaded and launched in ZL_ENC_PARTS parts: writing
+    // 1e5 frame and block descriptors takes the host about a millisecond, a quarter of what the device then needs for them -- this way the
+    // device starts after the first part.  The parts use disjoint ranges of every host and device array; stream order keeps them apart.
+    static const int partsEnv = getenv("ZL_ENC_PARTS") ? atoi(getenv("ZL_ENC_PARTS")) : ZL_ENC_PARTS;      // (development switch)
+    const size_t parts = (nb == nf && nf >= 16384 && !c->statsDev && partsEnv > 1) ? (size_t)(partsEnv > ZL_ENC_PARTS ? ZL_ENC_PARTS : partsEnv) : 1;
+    c->waveParts = (int)parts;
+    size_t bi = 0, farEntries = 0;
+    for (size_t part = 0; part < parts; part++) {
+        const size_t fa = nf * part / parts, fb = nf * (part + 1) / parts;      // frames of the part, relative to f0
+        const size_t b0 = bi;                                                  // its first block
+        u32 nSmall = 0;
+        for (size_t r = fa; r < fb; r++) {
+            const size_t i = f0 + r;
+            ZlEncFrame& f = hf[r];
+            memset(&f, 0, sizeof(f));
+            const size_t s = srcSize[i];
+            f.dst = ddst[i]; f.dstCap = dstCap[i]; f.firstBlock = (u32)(bi - b0); f.checksumFlag = (u32)c->checksumFlag;
+            const size_t nblk = s ? (s + ZL_BLOCKSIZE_MAX - 1) / ZL_BLOCKSIZE_MAX : 1;
+            f.nblocks = (u32)nblk;
+            // far candidates (zl_enc_match.cuh): a frame of several blocks gets a frame-wide table, while the wave's tables fit 4 GiB
+            bool far = false;
+            if (nblk > 1 && s < 0xFFFFFF00ull && !farOff_disabled && P.farMaxOff) {
+                const u32 flog = zl_far_log(s);
+                const size_t fe = (size_t)zl_far_entries(s);                  // one table per 8 MiB region
+                if (farEntries + fe <= ((size_t)1 << 30)) { f.pad = (u64)farEntries | ((u64)flog << 56); farEntries += fe; far = true; }
+            }
+            f.hdrSize = zl_write_frame_header(f.hdr, s, dict ? c->dictID : 0u, (u32)c->checksumFlag, far ? P.farMaxOff : 0u);
+            for (size_t k = 0; k < nblk; k++) {
+                ZlEncBlock& b = hb[bi++];
+                b.src = dsrc[i] + k * ZL_BLOCKSIZE_MAX;
+                const size_t rem = s - k * ZL_BLOCKSIZE_MAX;
+                b.srcSize = (u32)(rem < ZL_BLOCKSIZE_MAX ? rem : ZL_BLOCKSIZE_MAX);
+                b.frame = (u32)(r - fa);
+                b.flags = (k == 0 ? ZL_BLK_FIRST : 0u) | (k + 1 == nblk ? ZL_BLK_LAST : 0u);
+                b.pad = (u32)(k * ZL_BLOCKSIZE_MAX);
+                if (b.srcSize && b.srcSize <= ZL_SMALL_BLOCK) nSmall++;
+            }
+        }
+        const size_t pnb = bi - b0, pnf = fb - fa;
+        if (farEntries) {                                             // (only with parts == 1: frames of several blocks)
+            if (!c->dFar.reserve(farEntries * 4)) return ZL_ERROR(memory_allocation);
+            cudaMemsetAsync(c->dFar.p, 0xFF, farEntries * 4, st);
+        }
+        cudaMemcpyAsync(c->dBlocks.as<ZlEncBlock>() + b0, hb + b0, pnb * sizeof(ZlEncBlock), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(c->dFrames.as<ZlEncFrame>() + fa, hf + fa, pnf * sizeof(ZlEncFrame), cudaMemcpyHostToDevice, st);
+        const u64* xxh = nullptr;
+        if (c->checksumFlag) {                                        // XXH64 of every frame's content (zstd.c:27022-27023)
+            const u8** hp = c->hAux.as<const u8*>();
+            u32* hs = reinterpret_cast<u32*>(hp + nf);
+            bool anyLarge = false;
+            for (size_t r = fa; r < fb; r++) { hp[r] = dsrc[f0 + r]; hs[r] = (u32)srcSize[f0 + r]; if (srcSize[f0 + r] >= ZL_LARGE_FRAME_BYTES) anyLarge = true; }
+            cudaMemcpyAsync(c->dXxhPtrs.as<const u8*>() + fa, hp + fa, pnf * 8, cudaMemcpyHostToDevice, st);
+            cudaMemcpyAsync(c->dXxhSizes.as<u32>() + fa, hs + fa, pnf * 4, cudaMemcpyHostToDevice, st);
+            if (zl_launch_xxh64(c->dXxhPtrs.as<const u8*>() + fa, c->dXxhSizes.as<u32>() + fa, c->dXxh.as<u64>() + fa, (u32)pnf, st, anyLarge) != cudaSuccess) return ZL_ERROR(GENERIC);
+            c->launches += 1;
+            xxh = c->dXxh.as<u64>() + fa;
+        }
+        ZlEncodeLaunch L;
+        L.blocks = c->dBlocks.as<ZlEncBlock>() + b0; L.nblocks = (u32)pnb; L.frames = c->dFrames.as<ZlEncFrame>() + fa; L.nframes = (u32)pnf;
+        L.params = P; L.dict = dict;
+        L.M = c->dM.as<u32>() + b0 * (size_t)slotM; L.slotM = slotM; L.recs = c->dRecs.as<u64>() + b0 * (size_t)slotRec; L.slotRec = slotRec;
+        L.lit = c->dLit.as<u8>() + b0 * (size_t)slotLit; L.slotLit = slotLit;
+        L.hist = c->dHist.as<u32>() + b0 * 256; L.metas = c->dMetas.as<ZlEncBlockMeta>() + b0; L.outs = c->dOuts.as<ZlEncBlockOut>() + b0;
+        L.plans = c->dPlans.as<ZlEncBlockPlan>() + b0;
+        L.streamCapWords = streamCapWords; L.streamWordsPerBlock = streamWordsPerBlock; L.seqCapWords = seqCapWords;
+        L.far = farEntries ? c->dFar.as<u32>() : nullptr;
+        L.nSmall = nSmall;
+        L.results = c->dResults.as<u64>() + f0 + fa; L.xxh = xxh; L.stageEv = timeIt ? c->stageEv[part] : nullptr; L.stats = c->statsDev; L.maxBlock = maxBlock;
+        if (sideMode == 2 || (sideMode == 1 && pnb <= 1024)) { L.side = c->side; L.sideFork = c->sideFork; L.sideJoin = c->sideJoin; }
+        cudaError_t e = zl_launch_encode(L, st);
+        c->launches += 6 + (farEntries ? 2 : 0) + ((nSmall && nSmall < pnb) ? 1 : 0);
+        if (e != cudaSuccess) { fprintf(stderr, "zstdlite_gpu: kernel launch failed: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
+    }
     return 0;
 }
 
@@ -352,7 +368,7 @@ static size_t zl_enc_run(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* srcS
         if (!firstWave) {                                         // the wave's host-side descriptor buffers are reused: drain first
             if (cudaStreamSynchronize(st) != cudaSuccess) return ZL_ERROR(GENERIC);
             float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); total += ms;
-            for (int k = 0; k < ZL_ENC_STAGES; k++) { float t = 0; cudaEventElapsedTime(&t, c->stageEv[k], c->stageEv[k + 1]); stage[k] += t; }
+            for (int q = 0; q < c->waveParts; q++) for (int k = 0; k < ZL_ENC_STAGES; k++) { float t = 0; cudaEventElapsedTime(&t, c->stageEv[q][k], c->stageEv[q][k + 1]); stage[k] += t; }
         }
         cudaEventRecord(c->ev0, st);
         const size_t r = zl_enc_wave(c, dsrc, srcSize, ddst, dstCap, f0, f1, n, true);
@@ -372,7 +388,7 @@ static size_t zl_enc_run(ZSTD_CCtx* c, const u8* const* dsrc, const size_t* srcS
     const cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { fprintf(stderr, "zstdlite_gpu: device error: %s\n", cudaGetErrorString(e)); return ZL_ERROR(GENERIC); }
     float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); total += ms;
-    for (int k = 0; k < ZL_ENC_STAGES; k++) { float t = 0; cudaEventElapsedTime(&t, c->stageEv[k], c->stageEv[k + 1]); stage[k] += t; }
+    for (int q = 0; q < c->waveParts; q++) for (int k = 0; k < ZL_ENC_STAGES; k++) { float t = 0; cudaEventElapsedTime(&t, c->stageEv[q][k], c->stageEv[q][k + 1]); stage[k] += t; }
     c->lastKernelMs = total;
     for (int k = 0; k < ZL_ENC_STAGES; k++) c->lastStageMs[k] = stage[k];
     return 0;

@@ -114,6 +114,7 @@ cudaError_t zl_launch_xxh64(const u8* const* ptrs, const u32* sizes, u64* out, u
 #define ZL_ASM_WARPS 4
 #define ZL_ENT_WARPS 4       // warps (= blocks) per CTA in the two entropy kernels
 #define ZL_ENC_STAGES 5      // match, parse, literals, sequences, plan+assemble
+#define ZL_ENC_PARTS 4       // a wave of very many one-block frames is described and launched in this many parts (zl_enc_wave)
 #define ZL_BLK_FIRST 1u
 #define ZL_BLK_LAST 2u
 
