@@ -347,3 +347,26 @@ def test_window_log_parameter(z, ref):
     cc = z.zstd_cctx(level=3)
     r = L.ZSTD_CCtx_setParameter(cc._p, z._lib.ZSTD_c_windowLog, 12)
     assert z.is_error(r) and z.error_name(r) == "Parameter is out of bound"
+
+
+def test_many_small_frames_in_parts(z, ref):
+    """A wave of >= 16,384 one-block frames is described and launched in four parts (zl_enc_wave), blocks of <= 2 KiB go to the warp-per-block
+    match kernel and the others to the CTA one, in the same wave; with checksums on, XXH64 runs per part too.  Every frame must be what the
+    same input gives on its own (the table size of a block depends on the block alone), decode with libzstd and carry the right checksum."""
+    from zstdlite_b200 import corpus
+    rng = np.random.default_rng(5)
+    n = 20000
+    sizes = rng.integers(1, 700, n)
+    sizes[::97] = rng.integers(2049, 6000, len(sizes[::97]))          # some blocks above the small-block limit, spread over all parts
+    sizes[5] = 0
+    pool = corpus.make("text", 1 << 20, 3).tobytes() + corpus.make("rdf", 1 << 20, 4).tobytes()
+    bufs = [pool[o:o + s] for o, s in zip(rng.integers(0, len(pool) - 6000, n), sizes)]
+    res, outs = _gpu_compress_batch(z, bufs, 3, True)
+    assert not any(z.is_error(int(r)) for r in res)
+    cc = z.zstd_cctx(level=3, include_checksum=True)
+    for i in list(range(0, n, 487)) + [5, 97, 194, n - 1]:
+        assert ref.decompress(outs[i]) == bufs[i], i
+        assert outs[i] == z.zstd_compress(bufs[i], cctx=cc), i
+    from tests.gpu_util import gpu_decompress_batch
+    res2, back = gpu_decompress_batch(outs, [len(b) for b in bufs])
+    assert back == bufs
