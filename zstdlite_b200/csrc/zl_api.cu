@@ -476,6 +476,8 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         if (nslices > n / ZL_DEC_SLICE_MIN_FRAMES) nslices = n / ZL_DEC_SLICE_MIN_FRAMES;
         if (nslices > ZL_DEC_MAX_SLICES) nslices = ZL_DEC_MAX_SLICES;
         if (nslices < 1) nslices = 1;
+        static const int forceSlices = getenv("ZL_DEC_SLICES") ? atoi(getenv("ZL_DEC_SLICES")) : 0;      // (development switch)
+        if (forceSlices > 0) nslices = (size_t)forceSlices < n ? (size_t)forceSlices : n;
     }
     // Host buffers, large batches: the device-to-host copy engine bounds the call, so it must start early and never run dry:
     // the first slices are small (their kernels end after little more than the chain latency of one frame, ~3 ms) and every
