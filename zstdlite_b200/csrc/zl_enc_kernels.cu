@@ -566,6 +566,11 @@ zl_k_parse(const ZlEncBlock* __restrict__ blocks, u32 nblocks, const u32* __rest
             u32 c = p > w0 ? p - w0 : 0;
             const u32 cstart = c;
             const u32 matchMask = __ballot_sync(ZL_FULL, len >= 3);
+            if (!matchMask && cstart == 0 && w0 + 32 <= segEnd) {          // a window without any match (noise, low-entropy data): 32 literals
+                lit[nlit + lane] = (u8)byte; atomicAdd(&hist[warp][byte], 1u);
+                nlit += 32; p = w0 + 32;
+                continue;
+            }
             u32 takenMask = 0, myLL = 0, myOB = 0;
             for (;;) {
                 const u32 mm = c < 32 ? (matchMask >> c) << c : 0u;
