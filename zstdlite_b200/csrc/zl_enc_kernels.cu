@@ -249,7 +249,8 @@ __device__ __forceinline__ u32 zl_match_verify(const u32* __restrict__ wbase, u3
     // the first 8 bytes of BOTH candidates are requested before either is looked at: the two loads are a cache miss each more often
     // than not, and one after the other they were the longest wait of a warp's turn
     const i32 qL = !kLong ? -1 : (prevL >= 0 ? (i32)(gbase + (u32)prevL) : zl_cand_pos(eL, p));
-    const i32 qS = prevS >= 0 ? (i32)(gbase + (u32)prevS) : zl_cand_pos(eS, p);
+    i32 qS = prevS >= 0 ? (i32)(gbase + (u32)prevS) : zl_cand_pos(eS, p);
+    if (kLong && qS == qL) qS = -1;                  // both tables name the same position (the usual case of a real match): one look is enough
     u32 cLlo = 0, cLhi = 0, cSlo = 0, cShi = 0;
     if (kLong && qL >= 0) zl_ld8v(wbase, bias + (u32)qL, lastWord >> 1, cLlo, cLhi);
     if (qS >= 0) zl_ld8v(wbase, bias + (u32)qS, lastWord >> 1, cSlo, cShi);
