@@ -1065,6 +1065,21 @@ cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// The per-frame results go back to the host through a kernel that stores into the pinned (device-mapped) result array, not through a
+// cudaMemcpyAsync: a copy engine serves its requests in submission order, and in the pipelined calls the few KB of results queued up behind
+// the previous chunk's hundreds of MB of output (measured: the last, short chunk of a 4 GiB call waited 8 ms for them).
+__global__ void zl_k_results_out(const u64* __restrict__ src, u64* __restrict__ hostDst, u32 n)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) hostDst[i] = src[i];
+}
+cudaError_t zl_launch_results_out(const u64* src, u64* hostDst, u32 n, cudaStream_t st)
+{
+    if (!n) return cudaSuccess;
+    zl_k_results_out<<<(n + 255) / 256, 256, 0, st>>>(src, hostDst, n);
+    return cudaGetLastError();
+}
+
 cudaError_t zl_launch_gather(const u8* const* srcs, const u64* sizes, const u64* offs, u8* dst, u32 n, cudaStream_t st)
 {
     if (!n) return cudaSuccess;

@@ -161,4 +161,5 @@ struct ZlEncodeLaunch {
 cudaError_t zl_enc_upload_const();
 size_t zl_enc_match_smem(const ZlEncParams& P);
 cudaError_t zl_launch_encode(const ZlEncodeLaunch& L, cudaStream_t st);
+cudaError_t zl_launch_results_out(const u64* src, u64* hostDst, u32 n, cudaStream_t st);      // hostDst: pinned host memory (device-mapped under UVA)
 cudaError_t zl_launch_gather(const u8* const* srcs, const u64* sizes, const u64* offs, u8* dst, u32 n, cudaStream_t st);
