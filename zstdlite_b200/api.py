@@ -27,18 +27,40 @@ def _check(r, what):
 
 
 def _as_buffer(x):
-    """bytes-like -> (ctypes pointer-able object, length). str is UTF-8 encoded (src/raw-file.c:41-46)."""
+    """bytes-like -> (pointer for the C ABI, length, object that keeps the memory alive).  No copy: the library reads the caller's own
+    memory, read-only or not, like the reference reads RAW(src) (src/raw-file.c:41-46; str is UTF-8 encoded as there)."""
     if isinstance(x, str):
         x = x.encode("utf-8")
     mv = memoryview(x).cast("B")
     n = mv.nbytes
     if n == 0:
         return C.c_char_p(b""), 0, mv
-    if mv.readonly:
-        buf = (C.c_char * n).from_buffer_copy(mv)
-    else:
-        buf = (C.c_char * n).from_buffer(mv)
-    return buf, n, mv
+    import numpy as np
+    arr = np.frombuffer(mv, dtype=np.uint8)
+    return C.c_void_p(arr.ctypes.data), n, (arr, mv)
+
+
+# One-shot outputs: a bytes object of the final size that the library writes into directly (PyBytes_FromStringAndSize(NULL, n) is the C API's
+# way to make one) -- a ctypes buffer would be zero-filled first and copied twice on the way out, which for a 64 MiB result cost more than
+# the decode.  Compressed output, whose size is only known afterwards, goes through an uninitialised numpy array and one copy of the result.
+_py = C.pythonapi
+_py.PyBytes_FromStringAndSize.restype = C.py_object
+_py.PyBytes_FromStringAndSize.argtypes = [C.c_void_p, C.c_ssize_t]
+_py.PyBytes_AsString.restype = C.c_void_p
+_py.PyBytes_AsString.argtypes = [C.py_object]
+
+
+def _new_bytes(n):
+    """(bytes object of n uninitialised bytes, its address)"""
+    b = _py.PyBytes_FromStringAndSize(None, n)
+    return b, _py.PyBytes_AsString(b)
+
+
+def _scratch(n):
+    """(uninitialised numpy byte array of n bytes, its address)"""
+    import numpy as np
+    a = np.empty(max(1, n), dtype=np.uint8)
+    return a, a.ctypes.data
 
 
 class zstd_dctx:
@@ -169,15 +191,15 @@ def zstd_compress(src, cctx=None, frame_size=None, **opts):
         frame_size = int(frame_size)
         nfr = max(1, -(-n // frame_size))
         cap = nfr * L.ZSTD_compressBound(min(n, frame_size))
-        dst = C.create_string_buffer(max(1, cap))
-        r = L.zl_compress_split(cctx._p, dst, cap, buf, n, frame_size, None, 0)
+        dst, dptr = _scratch(cap)
+        r = L.zl_compress_split(cctx._p, dptr, cap, buf, n, frame_size, None, 0)
         _check(r, "zstd_compress(): Compression error")
-        return dst.raw[:r]
+        return dst[:r].tobytes()
     cap = L.ZSTD_compressBound(n)
-    dst = C.create_string_buffer(max(1, cap))
-    r = L.ZSTD_compress2(cctx._p, dst, cap, buf, n)
+    dst, dptr = _scratch(cap)
+    r = L.ZSTD_compress2(cctx._p, dptr, cap, buf, n)
     _check(r, "zstd_compress(): Compression error")
-    return dst.raw[:r]
+    return dst[:r].tobytes()
 
 
 def zstd_decompress(src, type="raw", dctx=None, all_frames=False, **opts):
@@ -200,11 +222,12 @@ def zstd_decompress(src, type="raw", dctx=None, all_frames=False, **opts):
     if usize >= CONTENTSIZE_ERROR:
         # the reference does not check this and would try a 2^64 allocation; we raise instead
         raise ZstdError("zstd_decompress(): frame does not record its content size")
-    dst = C.create_string_buffer(max(1, usize))
+    out, optr = _new_bytes(usize)
     L.ZSTD_DCtx_setParameter(dctx._p, _lib.ZSTD_d_stableOutBuffer, 1)     # src/dctx.c:98-103
-    r = L.ZSTD_decompressDCtx(dctx._p, dst, usize, buf, csize)
+    r = L.ZSTD_decompressDCtx(dctx._p, optr, usize, buf, csize)
     _check(r, "zstd_decompress(): De-compression error")
-    out = dst.raw[:r]
+    if r != usize:
+        out = out[:r]
     return out.decode("utf-8") if type == "string" else out
 
 
