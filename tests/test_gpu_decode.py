@@ -271,3 +271,84 @@ def test_source_alignment_sweep(z, ref):
     for i, (r, w) in enumerate(zip(res, want)):
         assert not z.is_error(r), (i, z.error_name(r))
         assert r == len(w) and bufs[i][1][:len(w)].cpu().numpy().tobytes() == w, i
+
+
+def test_pageable_host_buffers_are_staged_by_the_copy_pool(z, ref):
+    """ordinary malloc'ed memory of >= 4 MiB (what the reference's C layer hands over: R vectors, src/raw-file.c:166,189) is packed into /
+    unpacked from pinned staging by the host copy pool with streaming stores (zl_host.h): every source / destination alignment, frames that
+    produce less than their slot, a frame that fails -- bytes identical to libzstd's, nothing written outside a frame's own bytes"""
+    from zstdlite_b200 import corpus
+    rng = np.random.default_rng(11)
+    n, fb = 288, 65536                                          # ~7 MiB compressed, 18 MiB of slots: both directions are staged
+    raws = []
+    for i in range(n):
+        fam = ("text", "rdf", "lowent", "rand")[i % 4]
+        size = fb if i % 5 else int(rng.integers(1, fb))            # a fifth of the frames fill only part of their slot
+        raws.append(corpus.make(fam, size, 100 + i).tobytes())
+    frames = [ref.compress(r, 3, include_checksum=bool(i % 3 == 0)) for i, r in enumerate(raws)]
+    bad = 37
+    frames[bad] = frames[bad][:-9] + bytes([frames[bad][-9] ^ 0x40]) + frames[bad][-8:]            # damaged: whatever libzstd makes of it
+    try:
+        want_bad = ref.decompress(frames[bad], cap=fb)
+    except ref.RefError:
+        want_bad = None
+    sizes = [len(f) for f in frames]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    d = z.zstd_dctx()
+    for shift_s, shift_d in ((0, 0), (1, 7), (13, 3)):
+        src = np.zeros(int(offs[-1]) + 64, dtype=np.uint8)            # pageable: plain numpy memory
+        src[shift_s:shift_s + int(offs[-1])] = np.frombuffer(b"".join(frames), dtype=np.uint8)
+        dst = np.full(n * fb + 64, 0xA5, dtype=np.uint8)
+        res = z.decompress_batch(d, [src.ctypes.data + shift_s + int(o) for o in offs[:-1]], sizes,
+                                 [dst.ctypes.data + shift_d + i * fb for i in range(n)], [fb] * n, device=False)
+        for i, r in enumerate(raws):
+            got = dst[shift_d + i * fb: shift_d + (i + 1) * fb]
+            if i == bad:
+                assert z.is_error(res[i]) == (want_bad is None)
+                if want_bad is None:
+                    assert (got == 0xA5).all()
+                    continue
+                r = want_bad
+            assert res[i] == len(r) and got[:len(r)].tobytes() == r, i
+            assert (got[len(r):] == 0xA5).all(), i                   # the rest of the slot is the caller's
+        assert (dst[:shift_d] == 0xA5).all() and (dst[shift_d + n * fb:] == 0xA5).all()
+    # the one-shot calls on one pageable buffer (ZSTD_compress2 / ZSTD_decompressDCtx: 64 MiB pieces through the same pool)
+    big = b"".join(raws)
+    c = z.zstd_compress(big, level=3, include_checksum=True)
+    assert ref.decompress(c) == big and z.zstd_decompress(c) == big
+
+
+def test_many_small_frames_descriptors_built_on_the_device(z, ref):
+    """>= 4,096 small frames in device memory: the per-frame descriptors come from zl_k_build_descs (the host only copies the caller's four
+    arrays).  Same verdict and bytes as libzstd for every frame: dictionary and plain frames, empty frames, a destination that is too small,
+    damaged frames, raw (incompressible) frames, checksums"""
+    from zstdlite_b200 import corpus
+    from tests.gpu_util import gpu_decompress_batch
+    rng = np.random.default_rng(23)
+    objs = corpus.small_objects(9000)
+    d = ref.train_dict(objs[:3000], 4096)
+    for use_dict in (True, False):
+        items = list(objs)
+        items[11] = b""
+        items[12] = bytes(rng.integers(0, 256, 900, dtype=np.uint8))           # incompressible: a raw block
+        items[13] = b"a" * 1500                                                # a run
+        frames = [ref.compress(o, 3, include_checksum=bool(i % 2), dict=d if use_dict else None) for i, o in enumerate(items)]
+        caps = [len(o) for o in items]
+        caps[20] = max(0, caps[20] - 1)                                        # too small for its frame
+        for i in (30, 31, 4000, 8999):                                         # damaged in the middle
+            f = bytearray(frames[i]); f[len(f) // 2] ^= 0x10; frames[i] = bytes(f)
+        dctx = z.zstd_dctx(dict=d if use_dict else None)
+        res, outs = gpu_decompress_batch(frames, caps, dctx=dctx)
+        rd = ref.DCtx(dict=d if use_dict else None)
+        for i, (f, o, c) in enumerate(zip(frames, items, caps)):
+            try:
+                want = rd.decompress(f, cap=c)
+            except ref.RefError:
+                want = None
+            if want is None:
+                assert z.is_error(res[i]), i
+            elif i in (30, 31, 4000, 8999) and z.is_error(res[i]):
+                pass                                                           # (damaged 4-stream literals: the documented stricter case, DESIGN.md section 2)
+            else:
+                assert not z.is_error(res[i]) and outs[i] == want, i
+        assert z.is_error(res[20]) and not z.is_error(res[21]) and outs[11] == b""

@@ -211,7 +211,7 @@ struct ZSTD_DCtx_s {
     // streaming session (ZSTD_decompressStream): input accumulated on the host until a whole frame is present
     std::vector<u8> sIn, sOut;
     size_t sOutPos = 0;
-    ZlDevBuf dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dNorm, dUnits, dCounters, dLargeIdx, dLb, dLc, dParent, dRemain, dSrc, dDst;
+    ZlDevBuf dRaw, dDescs, dInfos, dResults, dHdr, dRec, dCk, dLit, dNorm, dUnits, dCounters, dLargeIdx, dLb, dLc, dParent, dRemain, dSrc, dDst;
     ZlPinBuf hDescs, hResults, hLargeIdx, hRemain;
     std::vector<cudaEvent_t> sliceDone;    // staged host buffers: the copy back of a slice has landed
     // devices: the context's own (bound on first use) and, for batches of host buffers, the helpers on the other GPUs of the box
@@ -237,7 +237,7 @@ ZL_EXPORT size_t ZSTD_freeDCtx(ZSTD_DCtx* c)
     for (ZSTD_DCtx_s* k : c->kids) ZSTD_freeDCtx(k);
     c->kids.clear();
     ZlDeviceGuard guard(c->device);
-    ZlDevBuf* bufs[] = {&c->dDictContent, &c->dDict, &c->dDescs, &c->dInfos, &c->dResults, &c->dHdr, &c->dRec, &c->dCk, &c->dLit, &c->dNorm, &c->dUnits, &c->dCounters, &c->dLargeIdx, &c->dLb, &c->dLc, &c->dParent, &c->dRemain, &c->dSrc, &c->dDst};
+    ZlDevBuf* bufs[] = {&c->dDictContent, &c->dDict, &c->dRaw, &c->dDescs, &c->dInfos, &c->dResults, &c->dHdr, &c->dRec, &c->dCk, &c->dLit, &c->dNorm, &c->dUnits, &c->dCounters, &c->dLargeIdx, &c->dLb, &c->dLc, &c->dParent, &c->dRemain, &c->dSrc, &c->dDst};
     for (ZlDevBuf* b : bufs) b->release();
     c->hDescs.release(); c->hResults.release(); c->hLargeIdx.release(); c->hRemain.release();
     for (cudaEvent_t e : c->sliceDone) if (e) cudaEventDestroy(e);
@@ -462,11 +462,14 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     if (!c->hDescs.reserve(n * sizeof(ZlFrameDesc)) || !c->hResults.reserve(n * 8)) return ZL_ERROR(memory_allocation);
     ZlFrameDesc* hd = c->hDescs.as<ZlFrameDesc>();
     // ---- slices: contiguous frame ranges of about equal content; one slice when profiling or when the batch is small
-    u64 contentTotal = 0;
+    u64 contentTotal = 0, srcBytes = 0;
+    size_t maxSrc = 1, maxDst = 0;
     for (size_t i = 0; i < n; i++) {
-        if (srcSize[i] > 0xFFFFFFF0ull || dstCap[i] > 0x7FFFFFF0ull) return ZL_ERROR(memory_allocation);
-        contentTotal += dstCap[i];
+        const size_t s = srcSize[i], d = dstCap[i];
+        maxSrc = s > maxSrc ? s : maxSrc; maxDst = d > maxDst ? d : maxDst;
+        contentTotal += d; srcBytes += s;
     }
+    if (maxSrc > 0xFFFFFFF0ull || maxDst > 0x7FFFFFF0ull) return ZL_ERROR(memory_allocation);
     size_t nslices = 1;
     if (!c->profileStages) {
         // Host buffers: slices overlap the PCIe copies with the kernels.  Device buffers: one slice per internal stream, so that
@@ -489,6 +492,13 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     // the floor is the chain latency of ONE frame through the three kernels, 2.4 ms, before the first copy back can start, plus 1.07 GB at the D2H rate)
     if (graded) nslices = gradeN < 6 ? 6 : (gradeN > ZL_DEC_MAX_SLICES ? ZL_DEC_MAX_SLICES : (size_t)gradeN);
     if (nslices > 1 && !zl_dctx_lanes(c)) nslices = 1;
+    // Many SMALL frames in device memory (configs[3]: 1e5 objects of a few hundred bytes): the descriptors are built on the device from the
+    // caller's four arrays (zl_k_build_descs) -- the host copies 32 bytes per frame into pinned memory instead of planning and writing an
+    // 80-byte descriptor per frame (~10 ns each: 1.0 ms of a 2.0 ms call whose kernels take 0.8 ms).  Slices are cut by frame count and
+    // their arena shares sized from per-slice sums (upper bounds of the per-frame roundings); the kernel places the frames inside.
+    static const bool devBuildOff = getenv("ZL_DEC_NODEVBUILD") != nullptr;          // (development switch)
+    static_assert(sizeof(size_t) == 8 && sizeof(void*) == 8, "the raw descriptor arrays are copied as u64");
+    const bool devBuild = dev && !devBuildOff && nslices > 1 && n >= 4096 && maxSrc <= 4096 && maxDst <= 2 * ZL_BLOCKSIZE_MAX;
     // Scheduling order (device buffers): the frames are handed to the kernels by decreasing compressed size -- longest work
     // first, and frames of one kind next to each other, so that the quads of a warp and the warps of a CTA finish together.
     // Measured on config 2 with the families interleaved: 112 -> 143 GB/s.  order[pos] = caller's index of the frame at
@@ -497,8 +507,6 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     // balance (measured: sorting inside the slices 40.3 -> 39.8 GB/s).
     std::vector<u32> order(n), tmpOrder;
     for (size_t i = 0; i < n; i++) order[i] = (u32)i;
-    size_t maxSrc = 1;
-    for (size_t i = 0; i < n; i++) if (srcSize[i] > maxSrc) maxSrc = srcSize[i];
     int keyShift = 0;
     while ((maxSrc >> keyShift) >= 4096) keyShift++;
     // stable counting sort of order[a, b) by decreasing size class (4,096 classes): O(n), ~50 us for 16,384 frames
@@ -518,7 +526,8 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     if (dev && !sortOff && maxSrc > 4096) sortRange(0, n);
     const double tSort = hostMs();
     std::vector<size_t> cut(nslices + 1, n);
-    {
+    if (devBuild) for (size_t k = 0; k <= nslices; k++) cut[k] = n * k / nslices;
+    else {
         cut[0] = 0;
         u64 acc = 0; size_t k = 1;
         for (size_t i = 0; i < n && k < nslices; i++) {
@@ -580,7 +589,17 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     std::vector<Sums> sliceBase(nslices + 1);
     u64 lit = 0, rec = 0, hdr = 0, par = 0;
     size_t nLargeTotal = 0;
-    {
+    if (devBuild) {
+        for (size_t k = 0; k < nslices; k++) {
+            sliceBase[k] = {lit, rec, hdr, par};
+            u64 S = 0, D = 0;
+            for (size_t i = cut[k]; i < cut[k + 1]; i++) { S += srcSize[i]; D += dstCap[i]; }
+            const u64 m = cut[k + 1] - cut[k];
+            const u64 h = worst ? S / 3 + m : S / 32 + 16 * m;                 // >= the sum of the frames' hdrCap (zl_plan_frame) ...
+            hdr += h; rec += (D / 3 + 9 * h + 17 * m + 1) & ~1ull; lit += (D + 15 * m + 15) & ~15ull;      // ... recCap (even) and 16-aligned litCap
+        }
+        sliceBase[nslices] = {lit, rec, hdr, par};
+    } else {
         size_t k = 0;
         for (size_t pos = 0; pos < n; pos++) {
             while (k < nslices && pos == cut[k]) sliceBase[k++] = {lit, rec, hdr, par};
@@ -616,8 +635,9 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     static const bool lazyOff = getenv("ZL_DEC_NOLAZY") != nullptr;                // (development switch)
     // (filling the descriptors of >= 32,768 frames with the copy pool's threads was measured and lost: 1e5 small frames 2.94 ms against
     //  2.03 ms slice by slice on this thread -- waking the workers costs more than the 0.5 ms of stores they share)
-    const bool lazyDescs = nLargeTotal == 0 && nslices > 1 && !lazyOff;
-    if (!lazyDescs) fillDescs(0, n, Sums{0, 0, 0, 0});
+    const bool lazyDescs = nLargeTotal == 0 && nslices > 1 && !lazyOff && !devBuild;
+    if (!lazyDescs && !devBuild) fillDescs(0, n, Sums{0, 0, 0, 0});
+    if (devBuild && !c->dRaw.reserve(n * 32)) return ZL_ERROR(memory_allocation);
     if (!c->dDescs.reserve(n * sizeof(ZlFrameDesc)) || !c->dInfos.reserve(n * sizeof(ZlFrameInfo)) || !c->dResults.reserve(n * 8) ||
         !c->dLit.reserve(lit + 64) || !c->dRec.reserve(rec * 8) ||
         !c->dNorm.reserve(nslices * (size_t)ZL_NORM_SLOTS * 3 * ZL_NORM_STRIDE * sizeof(i16)) ||
@@ -635,7 +655,7 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
     }
     size_t largeSeen = 0;
     const double tPrep = hostMs();
-    if (!lazyDescs) cudaMemcpyAsync(c->dDescs.p, hd, n * sizeof(ZlFrameDesc), cudaMemcpyHostToDevice, st);
+    if (!lazyDescs && !devBuild) cudaMemcpyAsync(c->dDescs.p, hd, n * sizeof(ZlFrameDesc), cudaMemcpyHostToDevice, st);
     if (!c->stageEv[0]) for (cudaEvent_t& e : c->stageEv) cudaEventCreate(&e);
     const int verify = !c->forceIgnoreChecksum;
     cudaEventRecord(c->ev0, st);
@@ -668,6 +688,15 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
             for (size_t r = srunCut[k]; r < srunCut[k + 1]; r++)
                 if (sruns[r].bytes) cudaMemcpyAsync(c->dSrc.as<u8>() + sruns[r].devOff, sruns[r].hbase, sruns[r].bytes, cudaMemcpyHostToDevice, ls);
             if (nslices > 1) cudaEventRecord(c->inDone[k % ZL_DEC_LANES], ls);
+        }
+        if (devBuild) {
+            u64* hraw = reinterpret_cast<u64*>(hd) + 4 * a;                    // (the pinned descriptor buffer holds 80 bytes per frame)
+            memcpy(hraw, src + a, cnt * 8); memcpy(hraw + cnt, dst + a, cnt * 8);
+            memcpy(hraw + 2 * cnt, srcSize + a, cnt * 8); memcpy(hraw + 3 * cnt, dstCap + a, cnt * 8);
+            cudaMemcpyAsync(c->dRaw.as<u64>() + 4 * a, hraw, cnt * 32, cudaMemcpyHostToDevice, ls);
+            e = zl_launch_build_descs(c->dRaw.as<u64>() + 4 * a, (u32)cnt, c->dDescs.as<ZlFrameDesc>() + a, sliceBase[k].lit, sliceBase[k].rec, sliceBase[k].hdr, worst, ls);
+            c->launches += 1;
+            if (e != cudaSuccess) break;
         }
         if (lazyDescs) {
             fillDescs(a, a + cnt, sliceBase[k]);
@@ -766,7 +795,8 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
         c->lastStageMs[k] = t;
     }
     const u64* hr = c->hResults.as<u64>();
-    for (size_t pos = 0; pos < n; pos++) result[order[pos]] = (size_t)hr[pos];
+    if (devBuild) memcpy(result, hr, n * 8);                                  // (the caller's order was kept)
+    else for (size_t pos = 0; pos < n; pos++) result[order[pos]] = (size_t)hr[pos];
     return 0;
 }
 

@@ -10,6 +10,13 @@
 #include <condition_variable>
 #include <atomic>
 #include <functional>
+#if defined(__linux__)
+#include <sched.h>
+#endif
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#define ZL_HAVE_STREAM_COPY 1
+#endif
 #include "zl_common.cuh"
 #include "zl_launch.h"
 
@@ -66,9 +73,37 @@ struct ZlRun { size_t first, count; const uint8_t* hbase; size_t bytes; size_t d
 // The reference's C layer hands over PAGEABLE memory (R vectors: src/raw-file.c:166,189).  cudaMemcpyAsync on such memory goes
 // through the driver's own staging, synchronously and on one thread (measured: 8.4 GB/s for config 2 end to end against 41 GB/s
 // with pinned buffers).  The library stages pageable and scattered buffers through its own pinned memory instead and moves the
-// bytes with this pool: a few worker threads (ZL_COPY_THREADS, default min(8, cores / 2)) that split a list of copies into
+// bytes with this pool: a few worker threads (ZL_COPY_THREADS, default 3/4 of the CPUs in the affinity mask, at most 16) that split a list of copies into
 // 256 KiB pieces and pull them from a shared counter; the calling thread takes part.  Process-wide, created on first use.
 struct ZlCopySeg { void* dst; const void* src; size_t bytes; };
+// A piece of a staging copy: plain loads, NON-TEMPORAL stores.  Neither side of these copies is read again by this core -- packed input is
+// fetched from DRAM by the copy engine, unpacked output is a gigabyte the caller reads later -- and a 256 KiB memcpy stays below glibc's
+// non-temporal threshold, so every destination line was first read for ownership: three DRAM transfers per byte instead of two, with eight
+// threads sharing the memory controllers (measured on the development host, 1 GiB in 256 KiB pieces: memcpy 16 - 23 GB/s, this 22 - 36 GB/s).
+static inline void zl_copy_stream(void* dstv, const void* srcv, size_t n)
+{
+#ifdef ZL_HAVE_STREAM_COPY
+    char* d = (char*)dstv; const char* s = (const char*)srcv;
+    size_t head = (size_t)(16 - ((uintptr_t)d & 15)) & 15;
+    if (head > n) head = n;
+    memcpy(d, s, head); d += head; s += head; n -= head;
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        const __m128i a0 = _mm_loadu_si128((const __m128i*)(s + i)), a1 = _mm_loadu_si128((const __m128i*)(s + i + 16));
+        const __m128i a2 = _mm_loadu_si128((const __m128i*)(s + i + 32)), a3 = _mm_loadu_si128((const __m128i*)(s + i + 48));
+        const __m128i a4 = _mm_loadu_si128((const __m128i*)(s + i + 64)), a5 = _mm_loadu_si128((const __m128i*)(s + i + 80));
+        const __m128i a6 = _mm_loadu_si128((const __m128i*)(s + i + 96)), a7 = _mm_loadu_si128((const __m128i*)(s + i + 112));
+        _mm_stream_si128((__m128i*)(d + i), a0); _mm_stream_si128((__m128i*)(d + i + 16), a1);
+        _mm_stream_si128((__m128i*)(d + i + 32), a2); _mm_stream_si128((__m128i*)(d + i + 48), a3);
+        _mm_stream_si128((__m128i*)(d + i + 64), a4); _mm_stream_si128((__m128i*)(d + i + 80), a5);
+        _mm_stream_si128((__m128i*)(d + i + 96), a6); _mm_stream_si128((__m128i*)(d + i + 112), a7);
+    }
+    _mm_sfence();                                   // the stores are globally visible before the piece counts as done
+    memcpy(d + i, s + i, n - i);
+#else
+    memcpy(dstv, srcv, n);
+#endif
+}
 class ZlCopyPool {
 public:
     static ZlCopyPool& get() { static ZlCopyPool p; return p; }
@@ -80,7 +115,8 @@ public:
         std::vector<ZlCopySeg> pieces;
         for (const ZlCopySeg& s : segs)
             for (size_t o = 0; o < s.bytes; o += kPiece) pieces.push_back({(char*)s.dst + o, (const char*)s.src + o, s.bytes - o < kPiece ? s.bytes - o : kPiece});
-        parallel(pieces.size(), [&](size_t i) { memcpy(pieces[i].dst, pieces[i].src, pieces[i].bytes); });
+        static const bool plain = getenv("ZL_COPY_PLAIN") != nullptr;              // (development switch: memcpy instead of streaming stores)
+        parallel(pieces.size(), [&](size_t i) { if (plain || pieces[i].bytes < 4096) memcpy(pieces[i].dst, pieces[i].src, pieces[i].bytes); else zl_copy_stream(pieces[i].dst, pieces[i].src, pieces[i].bytes); });
     }
     // fn(0) .. fn(n - 1) spread over the pool (and the caller); returns when all are done
     void parallel(size_t n, const std::function<void(size_t)>& fn)
@@ -100,8 +136,15 @@ private:
     static constexpr size_t kPiece = 256u << 10;
     ZlCopyPool()
     {
-        unsigned n = std::thread::hardware_concurrency() / 2;
-        if (n > 8) n = 8;
+        // three quarters of the CPUs this process may run on (its affinity mask: a rank bound to its GPU's share of the box sizes the pool
+        // for that share), at most 16.  Measured on a 16-core box, config 2 end to end with malloc'ed buffers: 4 threads 21.6, 8 threads
+        // 25.6, 12 threads 27.8, 16 threads 28.3 GB/s.
+        unsigned cpus = std::thread::hardware_concurrency();
+#if defined(__linux__)
+        { cpu_set_t set; CPU_ZERO(&set); if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) cpus = (unsigned)CPU_COUNT(&set); }
+#endif
+        unsigned n = cpus - cpus / 4;
+        if (n > 16) n = 16;
         if (const char* e = getenv("ZL_COPY_THREADS")) n = (unsigned)atoi(e);
         if (n < 1) n = 1;
         for (unsigned i = 1; i < n; i++) workers_.emplace_back([this] { loop(); });

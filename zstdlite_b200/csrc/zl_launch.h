@@ -101,6 +101,8 @@ struct ZlDecodeLaunch {          // one slice of a batch: frames [frameBase, fra
 size_t zl_literals_smem_bytes();
 size_t zl_sequences_smem_bytes();
 cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st);
+// descriptors of a slice of small frames from the caller's arrays (raw = [src | dst | srcSize | dstCap], cnt u64 each), zl_dec_kernels.cu
+cudaError_t zl_launch_build_descs(const u64* raw, u32 cnt, ZlFrameDesc* descs, u64 lit0, u64 rec0, u64 hdr0, bool worst, cudaStream_t st);
 cudaError_t zl_launch_xxh64(const u8* const* ptrs, const u32* sizes, u64* out, u32 n, cudaStream_t st, bool anyLarge = false);
 
 // ---- compression --------------------------------------------------------------------------------------------------
