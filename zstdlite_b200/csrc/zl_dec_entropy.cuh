@@ -970,11 +970,11 @@ __device__ __forceinline__ u32 zl_seq_fast_loop(const ZlSeqSm& f, const u32* xta
         const u32* wb16 = wbase - s16;
         const i32 clow = (wlow + (i32)s16) >> 2;
         wi += (i32)s16;
-        zl_ring_start<4>(ring, 7, wb16, wi, clow);
+        zl_ring_start<4>(ring, ZL_SEQ_RING_SH, wb16, wi, clow);
 #if ZL_SEQ_RING_SYNC == 1
-        ZL_SEQ_LOOP(ZL_REFILL_RING_(7, 4, ZL_SEQ_RING_PF, "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t"), ZL_REFILL_RING_(7, 4, ZL_SEQ_RING_PF, "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t"))
+        ZL_SEQ_LOOP(ZL_REFILL_RING_(ZL_SEQ_RING_SH, 4, ZL_SEQ_RING_PF, "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t"), ZL_REFILL_RING_(ZL_SEQ_RING_SH, 4, ZL_SEQ_RING_PF, "cp.async.commit_group;\n\tcp.async.wait_group 8;\n\t"))
 #else   // one group per sequence (two refills): a chunk is used 6 sequences or more after its copy was issued
-        ZL_SEQ_LOOP(ZL_REFILL_RING_(7, 4, ZL_SEQ_RING_PF, "cp.async.commit_group;\n\tcp.async.wait_group 4;\n\t"), ZL_REFILL_RING_(7, 4, ZL_SEQ_RING_PF, ""))
+        ZL_SEQ_LOOP(ZL_REFILL_RING_(ZL_SEQ_RING_SH, 4, ZL_SEQ_RING_PF, "cp.async.commit_group;\n\tcp.async.wait_group 4;\n\t"), ZL_REFILL_RING_(ZL_SEQ_RING_SH, 4, ZL_SEQ_RING_PF, ""))
 #endif
         asm volatile("cp.async.wait_all;" ::: "memory");
         wi -= (i32)s16;

@@ -29,10 +29,10 @@ zl_k_index(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ info
 }
 
 // Units are fetched dynamically, 8 at a time per warp (one per quad), so expensive and cheap blocks balance across the grid.
-__device__ __forceinline__ u32 zl_fetch_units(u32* cursor, u32 lane)
+__device__ __forceinline__ u32 zl_fetch_units(u32* cursor, u32 lane, u32 count = ZL_QUADS_PER_WARP)
 {
     u32 base = 0;
-    if (lane == 0) base = atomicAdd(cursor, (u32)ZL_QUADS_PER_WARP);
+    if (lane == 0) base = atomicAdd(cursor, count);
     return __shfl_sync(0xFFFFFFFFu, base, 0);
 }
 
@@ -109,18 +109,19 @@ zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ 
     u32* xtab = reinterpret_cast<u32*>(smraw);
     ZlSeqSm* fs = reinterpret_cast<ZlSeqSm*>(smraw + ZL_XTAB_BYTES);
     const ZlConstTables& ct = c_tables;          // constant memory: only the header parser and the rare generic step index it
-    const u32 lane = threadIdx.x, quad = lane >> 2, q = lane & 3;
-    const u32 qmask = 0xFu << (quad * 4);
+    // ZL_SEQ_G lanes share a unit (ZL_SEQ_UNITS units per warp): lane 0 of the group runs the serial chains, all of them build the tables
+    const u32 lane = threadIdx.x, quad = lane / ZL_SEQ_G, q = lane % ZL_SEQ_G;
+    const u32 qmask = (0xFFFFFFFFu >> (32 - ZL_SEQ_G)) << (quad * ZL_SEQ_G);
     for (u32 i = lane; i < ZL_XTAB_WORDS; i += 32)
         xtab[i] = i < 36 ? (c_tables.llBase[i] | ((u32)c_tables.llBits[i] << 24)) : (c_tables.mlBase[i - 36] | ((u32)c_tables.mlBits[i - 36] << 24));
     __syncwarp();
     ZlSeqSm& f = fs[quad];
-    // stream ring of the decoding lanes: 4 slots of 8 x 16 bytes behind the eight units (zl_seq_fast_loop)
-    const u32 ring = ZL_SEQ_RING ? zl_smem_addr(smraw + ZL_XTAB_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlSeqSm)) + quad * 16u : 0u;
-    i16* norm = normArena + ((size_t)blockIdx.x * ZL_QUADS_PER_WARP + quad) * (3 * ZL_NORM_STRIDE);     // scratch per resident quad
+    // stream ring of the decoding lanes: 4 slots of ZL_SEQ_UNITS x 16 bytes behind the units (zl_seq_fast_loop)
+    const u32 ring = ZL_SEQ_RING ? zl_smem_addr(smraw + ZL_XTAB_BYTES + ZL_SEQ_UNITS * sizeof(ZlSeqSm)) + quad * 16u : 0u;
+    i16* norm = normArena + ((size_t)blockIdx.x * ZL_SEQ_UNITS + quad) * (3 * ZL_NORM_STRIDE);     // scratch per resident unit
     const u32 nunits = *unitCount;
     for (;;) {
-        const u32 ubase = zl_fetch_units(cursor, lane);
+        const u32 ubase = zl_fetch_units(cursor, lane, ZL_SEQ_UNITS);
         if (ubase >= nunits) break;
         const u32 u = ubase + quad;
         if (u < nunits) {
@@ -134,11 +135,19 @@ zl_k_sequences(const ZlFrameDesc* __restrict__ descs, ZlFrameInfo* __restrict__ 
                 __syncwarp(qmask);
                 const u32 build = f.ctl.err ? 0u : f.ctl.needBuild, useDict = f.ctl.err ? 0u : f.ctl.useDict;
                 if (useDict) {                                     // zstd.c:42140-42159: tables of the dictionary
-                    if (useDict & 1) { for (u32 i = q; i < 512; i += 4) f.fseLL[i] = dict->fseLL[i]; if (q == 0) f.ctl.tlog[0] = dict->tlog[0]; }
-                    if (useDict & 2) { for (u32 i = q; i < 256; i += 4) f.fseOF[i] = dict->fseOF[i]; if (q == 0) f.ctl.tlog[1] = dict->tlog[1]; }
-                    if (useDict & 4) { for (u32 i = q; i < 512; i += 4) f.fseML[i] = dict->fseML[i]; if (q == 0) f.ctl.tlog[2] = dict->tlog[2]; }
+                    if (useDict & 1) { for (u32 i = q; i < 512; i += ZL_SEQ_G) f.fseLL[i] = dict->fseLL[i]; if (q == 0) f.ctl.tlog[0] = dict->tlog[0]; }
+                    if (useDict & 2) { for (u32 i = q; i < 256; i += ZL_SEQ_G) f.fseOF[i] = dict->fseOF[i]; if (q == 0) f.ctl.tlog[1] = dict->tlog[1]; }
+                    if (useDict & 4) { for (u32 i = q; i < 512; i += ZL_SEQ_G) f.fseML[i] = dict->fseML[i]; if (q == 0) f.ctl.tlog[2] = dict->tlog[2]; }
                 }
-                if (build && q < 3) zl_seq_fse_build(f, q, norm);
+                if (build) {
+#if ZL_SEQ_G >= 3
+                    if (q < 3) zl_seq_fse_build(f, q, norm);
+#elif ZL_SEQ_G == 2
+                    if (q == 0) { zl_seq_fse_build(f, 0, norm); zl_seq_fse_build(f, 1, norm); } else zl_seq_fse_build(f, 2, norm);     // LL + OF | ML
+#else
+                    for (u32 t = 0; t < 3; t++) zl_seq_fse_build(f, t, norm);
+#endif
+                }
                 __syncwarp(qmask);
                 if (q == 0) {
                     const u32 nrec = zl_seq_decode(f, recArena + d.recBase + hdrs[un.block].recOff, wbase, bias, ct, xtab, ring);
@@ -388,7 +397,7 @@ zl_k_xxh64_large(const u8* const* __restrict__ ptrs, const u32* __restrict__ siz
 // ---- launchers ---------------------------------------------------------------------------------------
 size_t zl_literals_smem_bytes() { return ZL_QUADS_PER_WARP * sizeof(ZlLitSm) + (ZL_LIT_RING ? ZL_LIT_RING_SLOTS * 32 * 16 : 0); }
 static size_t zl_literals_smem_dict_bytes() { return zl_literals_smem_bytes() + 2048 * sizeof(u16); }      // + the dictionary's Huffman table
-size_t zl_sequences_smem_bytes() { return ZL_XTAB_BYTES + ZL_QUADS_PER_WARP * sizeof(ZlSeqSm) + (ZL_SEQ_RING ? 4 * 8 * 16 : 0); }
+size_t zl_sequences_smem_bytes() { return ZL_XTAB_BYTES + ZL_SEQ_UNITS * sizeof(ZlSeqSm) + (ZL_SEQ_RING ? 4 * ZL_SEQ_UNITS * 16 : 0); }
 
 // occupancy of the two persistent entropy kernels, per device (function attributes are per device too); guarded: contexts of
 // several host threads may decode for the first time at once
@@ -436,8 +445,9 @@ cudaError_t zl_launch_decode(const ZlDecodeLaunch& L, cudaStream_t st)
     // persistent grids: never more CTAs than fit the device at once or than there could be units (8 per CTA)
     const u32 maxCtas = (L.unitCap + ZL_QUADS_PER_WARP - 1) / ZL_QUADS_PER_WARP;
     if (litCtas > maxCtas) litCtas = maxCtas;
-    if (seqCtas > maxCtas) seqCtas = maxCtas;
-    if (seqCtas > L.normSlots / ZL_QUADS_PER_WARP) seqCtas = L.normSlots / ZL_QUADS_PER_WARP;
+    const u32 maxSeqCtas = (L.unitCap + ZL_SEQ_UNITS - 1) / ZL_SEQ_UNITS;
+    if (seqCtas > maxSeqCtas) seqCtas = maxSeqCtas;
+    if (seqCtas > L.normSlots / ZL_SEQ_UNITS) seqCtas = L.normSlots / ZL_SEQ_UNITS;
     if (!litCtas) litCtas = 1;
     if (!seqCtas) seqCtas = 1;
     cudaEvent_t* ev = L.stageEv;
