@@ -21,3 +21,9 @@ cc, dc = z.zstd_cctx(level=3, dict=dic), z.zstd_dctx(dict=dic)
 for o in objs[3000:3004]:
     assert z.zstd_decompress(z.zstd_compress(o, cctx=cc), dctx=dc) == o
 print("ok")
+# many small frames in device memory: their descriptors are built by zl_k_build_descs
+from tests.gpu_util import gpu_decompress_batch
+many = corpus.small_objects(6000)
+res, outs = gpu_decompress_batch([ref.compress(o, 3, dict=dic) for o in many], [len(o) for o in many], dctx=z.zstd_dctx(dict=dic))
+assert outs == many
+print("ok (device-built descriptors)")
