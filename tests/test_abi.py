@@ -72,10 +72,13 @@ def test_context_parameters_round_trip():
     c = z.zstd_cctx(level=2, num_threads=4, include_checksum=True)
     assert c.settings() == {"level": 2, "num_threads": 4, "include_checksum": 1}
     assert z.zstd_cctx(level=-99).settings()["level"] == -5                           # clamp, src/cctx.c:261-268
-    # levels 4..22 are not implemented: refused (parameter_unsupported -> "Bad compression level"), never served under another label ...
+    # levels 4 and 5 run the level-3 engine (within 3 % of libzstd at those levels); 6..22 are not implemented: refused
+    # (parameter_unsupported -> "Bad compression level"), never served under another label ...
     with pytest.raises(z.ZstdError, match="Bad compression level"):
         z.zstd_cctx(level=9)
-    assert L.ZSTD_getErrorName(L.ZSTD_CCtx_setParameter(c._p, 100, 4)) == b"Unsupported parameter" and c.settings()["level"] == 2
+    assert L.ZSTD_getErrorName(L.ZSTD_CCtx_setParameter(c._p, 100, 6)) == b"Unsupported parameter" and c.settings()["level"] == 2
+    five = z.zstd_cctx(level=5)
+    assert five.settings()["level"] == 5 and L.zl_cctx_engine_level(five._p) == 3
     # ... unless the caller opts into the level-3 engine for them; the label stays what was set, the engine is reported beside it
     f = z.zstd_cctx(level=99, level_fallback=True)
     fast = z.zstd_cctx(level=-3)

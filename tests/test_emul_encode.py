@@ -34,6 +34,31 @@ def test_emulated_ratio_within_3_percent(ref):
                 assert ours <= theirs * 1.03, (fam, fb, lvl, ours, theirs)
 
 
+def test_levels_4_and_5_within_3_percent_of_libzstd_at_those_levels(ref):
+    """levels 4 and 5 are served by the level-3 engine (ZSTD_c_compressionLevel in zl_api_compress.cu): the claim behind that is this bar --
+    its output within 3 % of libzstd's at the SAME level, per family, from 4 KB objects to a 2 MiB single frame, and with a dictionary.
+    Level 6 is outside it (text of 2 MiB: 1.035x) and stays refused."""
+    from zstdlite_b200 import corpus
+    from tests import emul_util
+    for lvl in (4, 5):
+        for fam in ("text", "rdf", "lowent"):
+            for fb, cnt in ((4000, 8), (131072, 4)):
+                bufs = [corpus.make(fam, fb, 300 + i).tobytes() for i in range(cnt)]
+                ours = sum(len(emul_util.compress_frame(b, lvl)) for b in bufs)
+                theirs = sum(len(ref.compress(b, lvl)) for b in bufs)
+                assert ours <= theirs * 1.03, (fam, fb, lvl, ours, theirs)
+        big = corpus.make("text", 2 << 20, 300).tobytes()
+        c = emul_util.compress_frame(big, lvl)
+        assert ref.decompress(c) == big and len(c) <= len(ref.compress(big, lvl)) * 1.03, lvl
+        objs = corpus.small_objects(4500)
+        d = ref.train_dict(objs[:3000], 5000)
+        test = objs[3000:4500:3]
+        ours = sum(len(emul_util.compress_frame(o, lvl, dict=d)) for o in test)
+        assert ours <= sum(len(ref.compress(o, lvl, dict=d)) for o in test) * 1.03, lvl
+    big6 = len(emul_util.compress_frame(big, 6)) / len(ref.compress(big, 6))
+    assert big6 > 1.03, big6            # (if this ever fails, level 6 can be served as well)
+
+
 def test_odd_inputs(ref):
     """few symbols, skewed histograms (depth-limited Huffman), long runs, tiny alphabets, binary ramps"""
     from tests import emul_util

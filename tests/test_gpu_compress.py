@@ -82,7 +82,7 @@ def test_one_shot_api_like_the_reference_tests(z, ref):
     assert z.zstd_cctx(level=1, num_threads=3, include_checksum=True).settings() == {"level": 1, "num_threads": 3, "include_checksum": 1}
     for lvl in (-5, 0):                               # fast levels run the level-1 engine, 0 is the default: valid frames
         assert ref.decompress(z.zstd_compress(d[:50000], level=lvl)) == d[:50000]
-    for lvl in (9, 22):                               # levels >= 4: refused, or -- opted in -- the level-3 engine's bytes under the caller's label
+    for lvl in (6, 9, 22):                            # levels >= 6: refused, or -- opted in -- the level-3 engine's bytes under the caller's label
         with pytest.raises(z.ZstdError, match="Bad compression level"):
             z.zstd_compress(d[:50000], level=lvl)
         assert z.zstd_compress(d[:50000], cctx=z.zstd_cctx(level=lvl, level_fallback=True)) == z.zstd_compress(d[:50000], level=3)
@@ -111,6 +111,31 @@ def test_batch_ratio_vs_reference(z, ref):
     # host-pointer path gives the same bytes
     res_h, outs_h = _gpu_compress_batch(z, bufs[:6], 3, device=False)
     assert outs_h == outs[:6]
+
+
+def test_levels_4_and_5_are_within_3_percent_of_libzstd_at_those_levels(z, ref):
+    """levels 4 and 5 are served by the level-3 engine (every position inserted and verified, two tables): its output must stay within 3 %
+    of what libzstd produces AT THE SAME LEVEL -- 128 KiB slabs per family, a 2 MiB single frame, small objects with a dictionary"""
+    from zstdlite_b200 import corpus
+    for lvl in (4, 5):
+        for fam in ("text", "rdf", "lowent"):
+            bufs = [corpus.make(fam, 131072, 300 + i).tobytes() for i in range(8)]
+            res, outs = _gpu_compress_batch(z, bufs, lvl)
+            for b, c in zip(bufs, outs):
+                assert ref.decompress(c) == b
+            ours, theirs = sum(len(c) for c in outs), sum(len(ref.compress(b, lvl)) for b in bufs)
+            assert ours <= theirs * 1.03, (fam, lvl, ours, theirs)
+        for fam in ("text", "rdf"):
+            big = corpus.make(fam, 2 << 20, 300).tobytes()
+            c = z.zstd_compress(big, level=lvl)
+            assert ref.decompress(c) == big and len(c) <= len(ref.compress(big, lvl)) * 1.03, (fam, lvl)
+        objs = corpus.small_objects(6000)
+        d = ref.train_dict(objs[:3000], 5000)
+        test = objs[3000:6000:3]
+        res, outs = _gpu_compress_batch(z, test, lvl, dict=d)
+        rd = ref.DCtx(dict=d)
+        assert all(rd.decompress(c, cap=len(o)) == o for o, c in list(zip(test, outs))[::50])
+        assert sum(len(c) for c in outs) <= sum(len(ref.compress(o, lvl, dict=d)) for o in test) * 1.03, lvl
 
 
 def test_compress_split_is_a_standard_multi_frame_stream(z, ref):

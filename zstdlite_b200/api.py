@@ -121,7 +121,8 @@ class zstd_cctx:
     """zstd_cctx(level = 3, num_threads = 1, include_checksum = FALSE, dict = NULL)  (R/cctx.R:38-48, src/cctx.c:213-315)."""
 
     def __init__(self, level=3, num_threads=1, include_checksum=False, dict=None, level_fallback=False, **unknown):
-        """level_fallback (extension): levels 4..22 are not implemented on the GPU and are refused ("init_cctx(): Bad compression level",
+        """Levels 4 and 5 run the level-3 engine (within 3 % of libzstd at those levels).
+        level_fallback (extension): levels 6..22 are not implemented on the GPU and are refused ("init_cctx(): Bad compression level",
         src/cctx.c:265) unless this is True (or ZSTDLITE_GPU_LEVEL_FALLBACK=1): then they run the level-3 engine."""
         for k in unknown:
             warnings.warn(f"init_cctx(): Unknown option '{k}'")          # src/cctx.c:288
@@ -133,7 +134,7 @@ class zstd_cctx:
         if level_fallback:
             L.zl_cctx_allow_level_fallback(self._p, 1)
         if is_error(L.ZSTD_CCtx_setParameter(self._p, _lib.ZSTD_c_compressionLevel, level)):
-            raise ZstdError("init_cctx(): Bad compression level")        # src/cctx.c:265 (levels >= 4: see level_fallback)
+            raise ZstdError("init_cctx(): Bad compression level")        # src/cctx.c:265 (levels >= 6: see level_fallback)
         if int(num_threads) > 1:                                          # src/cctx.c:269-277
             _check(L.ZSTD_CCtx_setParameter(self._p, _lib.ZSTD_c_nbWorkers, int(num_threads)), "init_cctx() num_threads")
         _check(L.ZSTD_CCtx_setParameter(self._p, _lib.ZSTD_c_checksumFlag, 1 if include_checksum else 0), "init_cctx() checksum")
