@@ -2,6 +2,7 @@
 // piece copy at every source / destination alignment and length class, and ZlCopyPool::run over many segments on several threads.
 // Built and run by tests/test_host_copy.py; no CUDA call is made (the header's device helpers are unused inline functions).
 #include "zl_host.h"
+#include "zl_plan.h"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -54,6 +55,27 @@ int main()
         const std::vector<size_t> cut = zl_split_ranges(w.data(), w.size(), 4);
         if (cut.size() != 5 || cut[0] != 0 || cut[4] != w.size()) bad++;
         for (int k = 0; k < 4; k++) if (cut[k] > cut[k + 1]) bad++;
+    }
+    // arena shares of a slice whose descriptors are built on the device: the bound from the slice's totals must cover the per-frame sums
+    {
+        unsigned long long x = 88172645463325252ull;
+        auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+        for (int trial = 0; trial < 2000; trial++) {
+            const unsigned m = 1 + (unsigned)(rnd() % 3000);
+            const bool worst = trial & 1;
+            const unsigned smax = trial % 5 == 0 ? 4096u : 1u + (unsigned)(rnd() % 4096), dmax = trial % 7 == 0 ? 262144u : 1u + (unsigned)(rnd() % 262144);
+            unsigned long long S = 0, D = 0, lit = 0, rec = 0, hdr = 0;
+            for (unsigned i = 0; i < m; i++) {
+                const u32 sz = (u32)(rnd() % (smax + 1)), dc = (u32)(rnd() % (dmax + 1));
+                u32 lc, rc, hc;
+                zl_plan_frame(sz, dc, worst, &lc, &rc, &hc);
+                S += sz; D += dc; lit += ((unsigned long long)lc + 15) & ~15ull; rec += rc; hdr += hc;
+                if (rc & 1) bad++;
+            }
+            unsigned long long bl, br, bh;
+            zl_plan_slice_bound(S, D, m, worst, &bl, &br, &bh);
+            if (bl < lit || br < rec || bh < hdr || (bl & 15) || (br & 1)) bad++;
+        }
     }
     printf("bad=%d\n", bad);
     return bad ? 1 : 0;

@@ -594,9 +594,9 @@ static size_t zl_decompress_batch_impl(ZSTD_DCtx* c, const void* const* src, con
             sliceBase[k] = {lit, rec, hdr, par};
             u64 S = 0, D = 0;
             for (size_t i = cut[k]; i < cut[k + 1]; i++) { S += srcSize[i]; D += dstCap[i]; }
-            const u64 m = cut[k + 1] - cut[k];
-            const u64 h = worst ? S / 3 + m : S / 32 + 16 * m;                 // >= the sum of the frames' hdrCap (zl_plan_frame) ...
-            hdr += h; rec += (D / 3 + 9 * h + 17 * m + 1) & ~1ull; lit += (D + 15 * m + 15) & ~15ull;      // ... recCap (even) and 16-aligned litCap
+            unsigned long long bl, br, bh;                                     // >= the sums of the frames' litCap (16-aligned), recCap (even) and hdrCap
+            zl_plan_slice_bound(S, D, cut[k + 1] - cut[k], worst, &bl, &br, &bh);
+            hdr += bh; rec += br; lit += bl;
         }
         sliceBase[nslices] = {lit, rec, hdr, par};
     } else {
